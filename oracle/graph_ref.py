@@ -1,0 +1,130 @@
+"""Oracle (test infrastructure only): periodic-boundary kNN graph construction.
+
+NumPy float32 restatement of models/utils/graph_utils.py (reference):
+  get_apply_pbc      :13-37   minimum image  dr - round(dr @ inv(cell)) @ cell
+  nearest_neighbors  :40-72   dense (N,N,3) difference (+1e-7), PBC, d^2,
+                              stable argsort, first k
+  build_graph        :248-324 vmap over the batch, n_edge = [[k]]*B (k, not E)
+NumPy evaluates every float32 operation with a separate IEEE rounding (no FMA
+contraction), which is the arithmetic SURVEY.md C.3 specifies.  Memory is
+O(N^2): use only at sizes that finish in seconds (N <= ~5000).
+"""
+from __future__ import annotations
+
+from typing import Callable, NamedTuple, Optional
+
+import numpy as np
+
+EPS = np.float32(1e-7)  # graph_utils.py:11
+
+
+class GraphsTuple(NamedTuple):
+    """Field-for-field mirror of jraph.GraphsTuple."""
+    nodes: object
+    edges: object
+    receivers: object
+    senders: object
+    globals: object
+    n_node: object
+    n_edge: object
+
+
+def get_apply_pbc(std=None, cell=None) -> Callable:
+    """graph_utils.py:13-37."""
+    if cell is None:
+        cell = np.eye(3, dtype=np.float32)
+    cell = np.asarray(cell, dtype=np.float32)
+    if std is not None:
+        cell = (cell / np.asarray(std, dtype=np.float32)[:3]).astype(np.float32)
+    cell_inv = np.linalg.inv(cell).astype(np.float32)
+
+    def apply_pbc(dr):
+        dr = np.asarray(dr, dtype=np.float32)
+        n = np.round(_dot3(dr, cell_inv))          # np.round == rint, ties to even
+        return (dr - _dot3(n, cell)).astype(np.float32)
+
+    apply_pbc.cell = cell
+    apply_pbc.cell_inv = cell_inv
+    return apply_pbc
+
+
+def _dot3(a, m):
+    """(...,3) @ (3,3) in float32 with the fixed order ((a0*m0 + a1*m1) + a2*m2).
+
+    For the diagonal cells every reference caller uses, two of the three
+    products are exact zeros, so the order is immaterial."""
+    a = a.astype(np.float32)
+    m = m.astype(np.float32)
+    return ((a[..., 0:1] * m[0] + a[..., 1:2] * m[1]) + a[..., 2:3] * m[2]).astype(np.float32)
+
+
+def nearest_neighbors(x, k: int, apply_pbc: Optional[Callable] = None):
+    """graph_utils.py:40-72 -> (sources, targets, dr[sources, targets])."""
+    x = np.asarray(x, dtype=np.float32)
+    n = x.shape[0]
+    dr = (x[:, None, :] - x[None, :, :]) + EPS
+    if apply_pbc is not None:
+        dr = apply_pbc(dr)
+    sq = dr * dr
+    dist = (sq[..., 0] + sq[..., 1]) + sq[..., 2]
+    idx = np.argsort(dist, axis=-1, kind="stable")[:, :k]
+    sources = np.repeat(np.arange(n, dtype=np.int32), k)
+    targets = idx.reshape(-1).astype(np.int32)
+    return sources, targets, dr[sources, targets]
+
+
+def bessel_np(x, n, x_max):
+    x = np.asarray(x, dtype=np.float32)[..., None]
+    j = np.arange(1, n + 1, dtype=np.float32)
+    xs = np.where(x == 0, np.float32(1), x)
+    val = np.where(x == 0, j * np.float32(np.pi) / np.float32(x_max),
+                   np.sin(j * np.float32(np.pi) / np.float32(x_max) * xs) / xs)
+    return (np.sqrt(np.float32(2.0) / np.float32(x_max)) * val).astype(np.float32)
+
+
+def build_graph(node_feats, global_feats, k, use_edges=True, apply_pbc=None, n_radial_basis=0,
+                r_max=1.0, use_3d_distances=False) -> GraphsTuple:
+    """graph_utils.py:248-324, kNN branch (radius branch is broken upstream: `x` undefined :277)."""
+    node_feats = np.asarray(node_feats, dtype=np.float32)
+    B, N = node_feats.shape[:2]
+    n_node = np.array([[N]] * B)
+    res = [nearest_neighbors(node_feats[b, :, :3], k, apply_pbc) for b in range(B)]
+    sources = np.stack([r[0] for r in res])
+    targets = np.stack([r[1] for r in res])
+    distances = np.stack([r[2] for r in res])
+    n_edge = np.array(B * [[k]])
+    if use_edges:
+        if use_3d_distances:
+            edges = distances
+        else:
+            edges = np.sqrt(np.sum(distances ** 2, axis=-1, keepdims=True))
+        if n_radial_basis > 0:
+            edges = np.squeeze(bessel_np(edges, n_radial_basis, r_max))
+        if use_3d_distances:
+            edges = edges.reshape(edges.shape[0], edges.shape[1], -1)
+    else:
+        edges = None
+    if edges is not None and edges.ndim < 3:
+        edges = edges[None]
+    return GraphsTuple(nodes=node_feats, edges=edges, receivers=targets, senders=sources,
+                       globals=global_feats, n_node=n_node, n_edge=n_edge)
+
+
+# rotation helpers used by the reference's tests (graph_utils.py:334-364)
+def rotation_matrix(angle_deg, axis):
+    a_rad = np.radians(angle_deg)
+    axis = np.asarray(axis, dtype=np.float64)
+    axis = axis / np.linalg.norm(axis)
+    a = np.cos(a_rad / 2)
+    b, c, d = -axis * np.sin(a_rad / 2)
+    return np.array([
+        [a * a + b * b - c * c - d * d, 2 * (b * c - a * d), 2 * (b * d + a * c)],
+        [2 * (b * c + a * d), a * a + c * c - b * b - d * d, 2 * (c * d - a * b)],
+        [2 * (b * d - a * c), 2 * (c * d + a * b), a * a + d * d - b * b - c * c],
+    ])
+
+
+def rotate_representation(data, angle_deg, axis):
+    R = rotation_matrix(angle_deg, axis)
+    pos, vel, sc = data[:, :3], data[:, 3:6], data[:, 6:]
+    return np.concatenate([(R @ pos.T).T, (R @ vel.T).T, sc], axis=1)
