@@ -1,0 +1,351 @@
+// Dense fp32 building block: C (+)= epi(alpha * pro(A) @ B) with arbitrary element
+// strides, fused activation prologue / epilogue and deterministic split-K (sm_100a).
+//
+// Serves (a) the radial MLP of models/nequip.py:62-66 (e3nn MultiLayerPerceptron:
+// x @ W / sqrt(fan_in), normalised gelu) forward, data-gradient and weight-gradient,
+// (b) every irreps Linear of the interaction block lowered to a dense matrix
+// (nequip.py:43,85,162,197) and (c) the read-out MLP (models/mlp.py).  fp32 FMA on the
+// CUDA cores: this is the exact-arithmetic path the 1e-5 parity contract is checked on.
+#include "common.cuh"
+
+namespace {
+
+struct GemmP {
+  int64_t M, N, K;
+  float alpha;
+  const float* A;
+  int64_t sam, sak;
+  const float* B;
+  int64_t sbk, sbn;
+  float* C;
+  int64_t scm, scn;
+  int accumulate, pro, epi;
+  float pro_scale, epi_scale;
+  const float* aux;
+  int64_t ld_aux;
+  int ksplit;
+  int64_t k_per_split;
+  float* partial;
+};
+
+__device__ __forceinline__ float apply_pro(float v, int pro, float s) {
+  return pro == 1 ? gelu_tanh(v) * s : v;
+}
+
+__device__ __forceinline__ void store_out(const GemmP& p, int64_t m, int64_t n, float v) {
+  if (p.epi == 1) v += p.aux[n];
+  else if (p.epi == 2) v *= gelu_tanh_grad(p.aux[m * p.ld_aux + n]) * p.epi_scale;
+  float* c = p.C + m * p.scm + n * p.scn;
+  if (p.accumulate) v += *c;
+  *c = v;
+}
+
+constexpr int BK = 16;
+
+// AMODE: 0 scalar generic | 1 float4 along K (sak == 1) | 2 float4 along M (sam == 1)
+// BMODE: 0 scalar generic | 1 float4 along N (sbn == 1)
+template <int BM, int BN, int TM, int TN, int AMODE, int BMODE>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN))
+gemm_kernel(const GemmP p) {
+  constexpr int NT = (BM / TM) * (BN / TN);
+  constexpr int LDA_S = BM + 4, LDB_S = BN + 4;
+  constexpr int EA = BM * BK / NT, EB = (BN * BK + NT - 1) / NT;
+  constexpr int EBV = (BN * BK / 4 + NT - 1) / NT;   // float4s of the B tile per thread
+  constexpr int RB = EB > 4 * EBV ? EB : 4 * EBV;
+  static_assert(BM * BK % NT == 0 && EA % 4 == 0, "A tile must split evenly into float4s");
+  __shared__ __align__(16) float As[2][BK][LDA_S];
+  __shared__ __align__(16) float Bs[2][BK][LDB_S];
+
+  const int tid = threadIdx.x;
+  const int tx = tid % (BN / TN), ty = tid / (BN / TN);
+  const int64_t m0 = (int64_t)blockIdx.x * BM, n0 = (int64_t)blockIdx.y * BN;
+  const int64_t kbeg = (int64_t)blockIdx.z * p.k_per_split;
+  const int64_t kend = min(p.K, kbeg + p.k_per_split);
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  float ra[EA], rb[RB];
+  // column j of this thread's TN-wide fragment (two interleaved halves when TN == 8: conflict-free LDS.128)
+  auto col_of = [&](int j) { return TN == 8 ? (j < 4 ? tx * 4 + j : BN / 2 + tx * 4 + (j - 4)) : tx * TN + j; };
+
+  auto load_tile = [&](int64_t k0) {
+    if (AMODE == 1) {
+#pragma unroll
+      for (int v = 0; v < EA / 4; ++v) {
+        const int idx = tid + v * NT;           // float4 index: (mm, k4)
+        const int mm = idx / (BK / 4), k4 = idx % (BK / 4);
+        const int64_t m = m0 + mm, k = k0 + 4 * k4;
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m < p.M && k + 3 < kend) t = *reinterpret_cast<const float4*>(p.A + m * p.sam + k);
+        else if (m < p.M) {
+          float* tp = reinterpret_cast<float*>(&t);
+          for (int q = 0; q < 4; ++q) if (k + q < kend) tp[q] = p.A[m * p.sam + k + q];
+        }
+        ra[4 * v + 0] = apply_pro(t.x, p.pro, p.pro_scale);
+        ra[4 * v + 1] = apply_pro(t.y, p.pro, p.pro_scale);
+        ra[4 * v + 2] = apply_pro(t.z, p.pro, p.pro_scale);
+        ra[4 * v + 3] = apply_pro(t.w, p.pro, p.pro_scale);
+      }
+    } else if (AMODE == 2) {
+#pragma unroll
+      for (int v = 0; v < EA / 4; ++v) {
+        const int idx = tid + v * NT;           // float4 index: (kk, m4)
+        const int kk = idx / (BM / 4), m4 = idx % (BM / 4);
+        const int64_t m = m0 + 4 * m4, k = k0 + kk;
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k < kend && m + 3 < p.M) t = *reinterpret_cast<const float4*>(p.A + k * p.sak + m);
+        else if (k < kend) {
+          float* tp = reinterpret_cast<float*>(&t);
+          for (int q = 0; q < 4; ++q) if (m + q < p.M) tp[q] = p.A[k * p.sak + m + q];
+        }
+        ra[4 * v + 0] = apply_pro(t.x, p.pro, p.pro_scale);
+        ra[4 * v + 1] = apply_pro(t.y, p.pro, p.pro_scale);
+        ra[4 * v + 2] = apply_pro(t.z, p.pro, p.pro_scale);
+        ra[4 * v + 3] = apply_pro(t.w, p.pro, p.pro_scale);
+      }
+    } else {
+      const bool kfast = p.sak <= p.sam;
+#pragma unroll
+      for (int v = 0; v < EA; ++v) {
+        const int idx = tid + v * NT;
+        const int mm = kfast ? idx / BK : idx % BM, kk = kfast ? idx % BK : idx / BM;
+        const int64_t m = m0 + mm, k = k0 + kk;
+        float t = 0.f;
+        if (m < p.M && k < kend) t = apply_pro(p.A[m * p.sam + k * p.sak], p.pro, p.pro_scale);
+        ra[v] = t;
+      }
+    }
+    if (BMODE == 1) {
+#pragma unroll
+      for (int v = 0; v < EBV; ++v) {
+        const int idx = tid + v * NT;           // float4 index: (kk, n4)
+        const int kk = idx / (BN / 4), n4 = idx % (BN / 4);
+        const int64_t n = n0 + 4 * n4, k = k0 + kk;
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (idx < BN * BK / 4) {
+          if (k < kend && n + 3 < p.N) t = *reinterpret_cast<const float4*>(p.B + k * p.sbk + n);
+          else if (k < kend) {
+            float* tp = reinterpret_cast<float*>(&t);
+            for (int q = 0; q < 4; ++q) if (n + q < p.N) tp[q] = p.B[k * p.sbk + n + q];
+          }
+        }
+        rb[4 * v + 0] = t.x;
+        rb[4 * v + 1] = t.y;
+        rb[4 * v + 2] = t.z;
+        rb[4 * v + 3] = t.w;
+      }
+    } else {
+      const bool nfast = p.sbn <= p.sbk;
+#pragma unroll
+      for (int v = 0; v < EB; ++v) {
+        const int idx = tid + v * NT;
+        const int kk = nfast ? idx / BN : idx % BK, nn = nfast ? idx % BN : idx / BK;
+        const int64_t n = n0 + nn, k = k0 + kk;
+        float t = 0.f;
+        if (idx < BN * BK && n < p.N && k < kend) t = p.B[k * p.sbk + n * p.sbn];
+        rb[v] = t;
+      }
+    }
+  };
+
+  auto store_tile = [&](int buf) {
+    if (AMODE == 1) {
+#pragma unroll
+      for (int v = 0; v < EA / 4; ++v) {
+        const int idx = tid + v * NT;
+        const int mm = idx / (BK / 4), k4 = idx % (BK / 4);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) As[buf][4 * k4 + q][mm] = ra[4 * v + q];
+      }
+    } else if (AMODE == 2) {
+#pragma unroll
+      for (int v = 0; v < EA / 4; ++v) {
+        const int idx = tid + v * NT;
+        const int kk = idx / (BM / 4), m4 = idx % (BM / 4);
+        *reinterpret_cast<float4*>(&As[buf][kk][4 * m4]) =
+            make_float4(ra[4 * v], ra[4 * v + 1], ra[4 * v + 2], ra[4 * v + 3]);
+      }
+    } else {
+      const bool kfast = p.sak <= p.sam;
+#pragma unroll
+      for (int v = 0; v < EA; ++v) {
+        const int idx = tid + v * NT;
+        const int mm = kfast ? idx / BK : idx % BM, kk = kfast ? idx % BK : idx / BM;
+        As[buf][kk][mm] = ra[v];
+      }
+    }
+    if (BMODE == 1) {
+#pragma unroll
+      for (int v = 0; v < EBV; ++v) {
+        const int idx = tid + v * NT;
+        const int kk = idx / (BN / 4), n4 = idx % (BN / 4);
+        if (idx < BN * BK / 4)
+          *reinterpret_cast<float4*>(&Bs[buf][kk][4 * n4]) =
+              make_float4(rb[4 * v], rb[4 * v + 1], rb[4 * v + 2], rb[4 * v + 3]);
+      }
+    } else {
+      const bool nfast = p.sbn <= p.sbk;
+#pragma unroll
+      for (int v = 0; v < EB; ++v) {
+        const int idx = tid + v * NT;
+        const int kk = nfast ? idx / BN : idx % BK, nn = nfast ? idx % BN : idx / BK;
+        if (idx < BN * BK) Bs[buf][kk][nn] = rb[v];
+      }
+    }
+  };
+
+  int buf = 0;
+  if (kbeg < kend) {
+    load_tile(kbeg);
+    store_tile(0);
+  }
+  __syncthreads();
+  for (int64_t k0 = kbeg; k0 < kend; k0 += BK) {
+    const bool more = k0 + BK < kend;
+    if (more) load_tile(k0 + BK);
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float a[TM], b[TN];
+#pragma unroll
+      for (int i = 0; i < TM; i += 4) {
+        const float4 t = *reinterpret_cast<const float4*>(&As[buf][kk][ty * TM + i]);
+        a[i] = t.x; a[i + 1] = t.y; a[i + 2] = t.z; a[i + 3] = t.w;
+      }
+      if (TN % 4 == 0) {
+#pragma unroll
+        for (int j = 0; j < TN; j += 4) {
+          const float4 t = *reinterpret_cast<const float4*>(&Bs[buf][kk][col_of(j)]);
+          b[j] = t.x; b[j + 1] = t.y; b[j + 2] = t.z; b[j + 3] = t.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < TN; ++j) b[j] = Bs[buf][kk][tx * TN + j];
+      }
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (more) store_tile(buf ^ 1);
+    __syncthreads();
+    buf ^= 1;
+  }
+
+  if (p.ksplit > 1) {
+    float* part = p.partial + (size_t)blockIdx.z * p.M * p.N;
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+      const int64_t m = m0 + ty * TM + i;
+      if (m >= p.M) continue;
+#pragma unroll
+      for (int j = 0; j < TN; ++j) {
+        const int64_t n = n0 + col_of(j);
+        if (n < p.N) part[m * p.N + n] = acc[i][j];
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+      const int64_t m = m0 + ty * TM + i;
+      if (m >= p.M) continue;
+#pragma unroll
+      for (int j = 0; j < TN; ++j) {
+        const int64_t n = n0 + col_of(j);
+        if (n < p.N) store_out(p, m, n, p.alpha * acc[i][j]);
+      }
+    }
+  }
+}
+
+__global__ void splitk_reduce_kernel(const GemmP p) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.M * p.N) return;
+  float s = 0.f;
+  for (int z = 0; z < p.ksplit; ++z) s += p.partial[(size_t)z * p.M * p.N + i];
+  store_out(p, i / p.N, i % p.N, p.alpha * s);
+}
+
+struct SplitPlan {
+  int ksplit;
+  int64_t k_per_split;
+};
+
+SplitPlan plan_split(int64_t M, int64_t N, int64_t K, int bm, int bn) {
+  const int64_t tiles = ceil_div64(M, bm) * ceil_div64(N, bn);
+  SplitPlan s{1, K};
+  if (tiles < 148 && K >= 4096) {
+    int64_t want = (2 * 148 + tiles - 1) / tiles;
+    int64_t maxs = K / 1024;
+    int64_t ks = want < maxs ? want : maxs;
+    if (ks > 1) {
+      int64_t per = ceil_div64(ceil_div64(K, ks), BK) * BK;
+      s.k_per_split = per;
+      s.ksplit = (int)ceil_div64(K, per);
+    }
+  }
+  return s;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+template <int BM, int BN, int TM, int TN>
+void launch(const GemmP& p, int amode, int bmode, cudaStream_t st) {
+  dim3 grid((unsigned)ceil_div64(p.M, BM), (unsigned)ceil_div64(p.N, BN), (unsigned)p.ksplit);
+  constexpr int NT = (BM / TM) * (BN / TN);
+#define EQNN_GEMM_CASE(AM, BMD) \
+  if (amode == AM && bmode == BMD) { gemm_kernel<BM, BN, TM, TN, AM, BMD><<<grid, NT, 0, st>>>(p); return; }
+  EQNN_GEMM_CASE(0, 0) EQNN_GEMM_CASE(0, 1) EQNN_GEMM_CASE(1, 0) EQNN_GEMM_CASE(1, 1) EQNN_GEMM_CASE(2, 0)
+  EQNN_GEMM_CASE(2, 1)
+#undef EQNN_GEMM_CASE
+}
+
+}  // namespace
+
+extern "C" size_t eqnn_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K) {
+  const int bn = N <= 16 ? 16 : (N <= 32 ? 32 : 128);
+  SplitPlan s = plan_split(M, N, K, 128, bn);
+  return s.ksplit > 1 ? (size_t)s.ksplit * M * N * sizeof(float) : 0;
+}
+
+extern "C" int eqnn_gemm_f32(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t sam,
+                             int64_t sak, const float* B, int64_t sbk, int64_t sbn, float* C, int64_t scm,
+                             int64_t scn, int flags, int pro, float pro_scale, int epi, const float* aux,
+                             int64_t ld_aux, float epi_scale, void* ws, size_t ws_bytes, eqnn_stream_t stream) {
+  EQNN_CHECK_ARG(M >= 0 && N >= 0 && K >= 0, "gemm: negative dimension");
+  if (M == 0 || N == 0) return EQNN_OK;
+  EQNN_CHECK_ARG(A && B && C, "gemm: null pointer");
+  EQNN_CHECK_ARG(pro == 0 || pro == 1, "gemm: unknown prologue");
+  EQNN_CHECK_ARG(epi >= 0 && epi <= 2, "gemm: unknown epilogue");
+  EQNN_CHECK_ARG(epi == 0 || aux, "gemm: epilogue needs aux");
+  EQNN_CHECK_ARG(ceil_div64(N, 16) <= 65535, "gemm: N too large for grid.y");
+  GemmP p;
+  p.M = M; p.N = N; p.K = K; p.alpha = alpha;
+  p.A = A; p.sam = sam; p.sak = sak;
+  p.B = B; p.sbk = sbk; p.sbn = sbn;
+  p.C = C; p.scm = scm; p.scn = scn;
+  p.accumulate = (flags & EQNN_GEMM_ACCUMULATE) ? 1 : 0;
+  p.pro = pro; p.pro_scale = pro_scale;
+  p.epi = epi; p.aux = aux; p.ld_aux = ld_aux; p.epi_scale = epi_scale;
+  const int bn = N <= 16 ? 16 : (N <= 32 ? 32 : 128);
+  SplitPlan s = plan_split(M, N, K, 128, bn);
+  p.ksplit = s.ksplit; p.k_per_split = s.k_per_split;
+  p.partial = reinterpret_cast<float*>(ws);
+  if (s.ksplit > 1)
+    EQNN_CHECK_ARG(ws && ws_bytes >= (size_t)s.ksplit * M * N * sizeof(float) ? 1 : 0, "gemm: split-K workspace too small");
+  int amode = 0, bmode = 0;
+  if (sak == 1 && sam % 4 == 0 && aligned16(A)) amode = 1;
+  else if (sam == 1 && sak % 4 == 0 && aligned16(A)) amode = 2;
+  if (sbn == 1 && sbk % 4 == 0 && aligned16(B)) bmode = 1;
+  // float4 loads along K need every split to start on a multiple of 4 (k_per_split is a multiple of BK)
+  cudaStream_t st = as_stream(stream);
+  if (bn == 16) launch<128, 16, 8, 1>(p, amode, bmode, st);
+  else if (bn == 32) launch<128, 32, 8, 2>(p, amode, bmode, st);
+  else launch<128, 128, 8, 8>(p, amode, bmode, st);
+  if (s.ksplit > 1) splitk_reduce_kernel<<<(unsigned)ceil_div64(M * N, 256), 256, 0, st>>>(p);
+  EQNN_CHECK_LAUNCH();
+  return EQNN_OK;
+}

@@ -1,0 +1,359 @@
+// NequIP interaction block: spherical harmonics + Clebsch-Gordan tensor product +
+// per-irrep radial weights + receiver-side reduction, fused (sm_100a).
+//
+// Reference arithmetic: models/nequip.py:46-52 (Y_lm, tensor_product), :68
+// (W_R * m), jraph segment_sum / segment_mean (:118-120).  One CTA owns ROWS
+// consecutive receiver rows of the receiver-sorted CSR:
+//   phase 1  one lane per incoming edge: coalesced stream of (src, r_hat, w_t columns),
+//            32-byte gather of the sender record, Y_lm and the sparse CG contraction in
+//            registers (generated straight-line code, csrc/gen/tp_gen.cuh), message
+//            written to shared memory (row stride odd => conflict-free);
+//   phase 2  one thread per (row, component): sequential sum over the row's edges in
+//            ascending edge id -- no atomics, deterministic, and the same order as the
+//            CPU scatter-add of the reference.
+// The backward kernel mirrors it: dL/dA rows staged in shared memory, one lane per
+// edge produces dL/dw_t (coalesced column-major store) and the 32-byte dL/dxt record
+// stored at the original edge id (one full sector per edge).
+#include "common.cuh"
+#include "gen/tp_gen.cuh"
+
+namespace {
+
+constexpr int TPC_THREADS = 128;
+constexpr int TPC_ROWS = 6;
+
+template <class TP>
+__device__ __forceinline__ void load_x(const float* __restrict__ xt, int s, float* x) {
+  const float4* p = reinterpret_cast<const float4*>(xt + (size_t)s * TP::DXP);
+#pragma unroll
+  for (int i = 0; i < TP::DXP / 4; ++i) {
+    float4 v = __ldg(p + i);
+    x[4 * i + 0] = v.x;
+    x[4 * i + 1] = v.y;
+    x[4 * i + 2] = v.z;
+    x[4 * i + 3] = v.w;
+  }
+}
+
+template <class TP>
+__global__ void __launch_bounds__(TPC_THREADS)
+tpconv_fwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src,
+                  const float4* __restrict__ geom, const float* __restrict__ w_t, int64_t n_edges,
+                  const float* __restrict__ xt, int n_nodes, int agg, float* __restrict__ A, int ld_a) {
+  constexpr int DL = TP::DLIVE;
+  constexpr int STRIDE = DL | 1;
+  constexpr int ITEMS = (TPC_ROWS * DL + TPC_THREADS - 1) / TPC_THREADS;
+  __shared__ float sm[TPC_THREADS * STRIDE];
+  __shared__ int s_rowptr[TPC_ROWS + 1];
+  const int tid = threadIdx.x;
+  const int r0 = blockIdx.x * TPC_ROWS;
+  const int nr = min(TPC_ROWS, n_nodes - r0);
+  if (tid <= nr) s_rowptr[tid] = rowptr[r0 + tid];
+  __syncthreads();
+  const int p0 = s_rowptr[0], p1 = s_rowptr[nr];
+  float acc[ITEMS];
+#pragma unroll
+  for (int it = 0; it < ITEMS; ++it) acc[it] = 0.f;
+
+  for (int base = p0; base < p1; base += TPC_THREADS) {
+    const int p = base + tid;
+    if (p < p1) {
+      const int s = src[p];
+      const float4 g = geom[p];
+      float x[TP::DXP], w[TP::NLIVE], Y[TP::NY], m[DL];
+      load_x<TP>(xt, s, x);
+#pragma unroll
+      for (int c = 0; c < TP::NLIVE; ++c) w[c] = w_t[(size_t)c * n_edges + p];
+      TP::sh(g.x, g.y, g.z, Y);
+      TP::fwd(x, Y, w, m);
+#pragma unroll
+      for (int i = 0; i < DL; ++i) sm[tid * STRIDE + i] = m[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < ITEMS; ++it) {
+      const int item = tid + it * TPC_THREADS;
+      if (item < nr * DL) {
+        const int row = item / DL, comp = item - row * DL;
+        const int lo = max(s_rowptr[row], base) - base;
+        const int hi = min(s_rowptr[row + 1], base + TPC_THREADS) - base;
+        float a = acc[it];
+        for (int q = lo; q < hi; ++q) a += sm[q * STRIDE + comp];
+        acc[it] = a;
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int it = 0; it < ITEMS; ++it) {
+    const int item = tid + it * TPC_THREADS;
+    if (item < nr * DL) {
+      const int row = item / DL, comp = item - row * DL;
+      float a = acc[it];
+      if (agg == 1) {
+        const int deg = s_rowptr[row + 1] - s_rowptr[row];
+        a = a / (float)max(deg, 1);
+      }
+      A[(size_t)(r0 + row) * ld_a + comp] = a;
+    }
+  }
+}
+
+template <class TP>
+__global__ void __launch_bounds__(TPC_THREADS)
+tpconv_bwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src,
+                  const int32_t* __restrict__ perm, const float4* __restrict__ geom,
+                  const float* __restrict__ w_t, int64_t n_edges, const float* __restrict__ xt, int n_nodes,
+                  int agg, const float* __restrict__ gA, int ld_ga, float* __restrict__ dw_t,
+                  float* __restrict__ dxe) {
+  constexpr int DL = TP::DLIVE;
+  constexpr int GS = DL | 1;
+  __shared__ float sG[TPC_ROWS * GS];
+  __shared__ int s_rowptr[TPC_ROWS + 1];
+  const int tid = threadIdx.x;
+  const int r0 = blockIdx.x * TPC_ROWS;
+  const int nr = min(TPC_ROWS, n_nodes - r0);
+  if (tid <= nr) s_rowptr[tid] = rowptr[r0 + tid];
+  __syncthreads();
+  for (int item = tid; item < nr * DL; item += TPC_THREADS) {
+    const int row = item / DL, comp = item - row * DL;
+    float g = gA[(size_t)(r0 + row) * ld_ga + comp];
+    if (agg == 1) {
+      const int deg = s_rowptr[row + 1] - s_rowptr[row];
+      g = g / (float)max(deg, 1);
+    }
+    sG[row * GS + comp] = g;
+  }
+  __syncthreads();
+  const int p0 = s_rowptr[0], p1 = s_rowptr[nr];
+  for (int p = p0 + tid; p < p1; p += TPC_THREADS) {
+    int row = 0;
+#pragma unroll
+    for (int r = 1; r < TPC_ROWS; ++r) row += (r < nr && p >= s_rowptr[r]) ? 1 : 0;
+    const int s = src[p];
+    const int e = perm[p];
+    const float4 gm = geom[p];
+    float x[TP::DXP], w[TP::NLIVE], Y[TP::NY], g[DL], dw[TP::NLIVE], dx[TP::DXP];
+    load_x<TP>(xt, s, x);
+#pragma unroll
+    for (int c = 0; c < TP::NLIVE; ++c) w[c] = w_t[(size_t)c * n_edges + p];
+#pragma unroll
+    for (int i = 0; i < DL; ++i) g[i] = sG[row * GS + i];
+    TP::sh(gm.x, gm.y, gm.z, Y);
+    TP::bwd(x, Y, w, g, dw, dx);
+#pragma unroll
+    for (int c = 0; c < TP::NLIVE; ++c) dw_t[(size_t)c * n_edges + p] = dw[c];
+    float4* o = reinterpret_cast<float4*>(dxe + (size_t)e * TP::DXP);
+#pragma unroll
+    for (int i = 0; i < TP::DXP / 4; ++i) o[i] = make_float4(dx[4 * i], dx[4 * i + 1], dx[4 * i + 2], dx[4 * i + 3]);
+  }
+}
+
+__global__ void sender_reduce_kernel(const float* __restrict__ dxe, int n_nodes, int k, int dxp,
+                                     float* __restrict__ dxt) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)n_nodes * dxp) return;
+  const int64_t s = i / dxp;
+  const int c = (int)(i - s * dxp);
+  const float* p = dxe + (size_t)s * k * dxp + c;
+  float a = 0.f;
+  for (int j = 0; j < k; ++j) a += p[(size_t)j * dxp];
+  dxt[i] = a;
+}
+
+// general out-degree: dxt[s, :] = sum_{q in row s of the sender-sorted CSR} dxe[perm_s[q], :]
+__global__ void segment_gather_sum_kernel(const float* __restrict__ dxe, const int32_t* __restrict__ rowptr_s,
+                                          const int32_t* __restrict__ perm_s, int n_nodes, int dxp,
+                                          float* __restrict__ dxt) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)n_nodes * dxp) return;
+  const int64_t s = i / dxp;
+  const int c = (int)(i - s * dxp);
+  float a = 0.f;
+  for (int q = rowptr_s[s]; q < rowptr_s[s + 1]; ++q) a += dxe[(size_t)perm_s[q] * dxp + c];
+  dxt[i] = a;
+}
+
+// node_attrs[r] = scale * sum_{e->r} Y(r_hat_e): one warp per row, lane per edge, shuffle reduce
+template <class SH>
+__global__ void __launch_bounds__(256) sh_scatter_kernel(const int32_t* __restrict__ rowptr,
+                                                         const float4* __restrict__ geom, int n_nodes, float scale,
+                                                         float* __restrict__ attrs) {
+  constexpr int NY = SH::NY;
+  const int lane = threadIdx.x & 31;
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= n_nodes) return;
+  const int p0 = rowptr[row], p1 = rowptr[row + 1];
+  float acc[NY];
+#pragma unroll
+  for (int i = 0; i < NY; ++i) acc[i] = 0.f;
+  for (int p = p0 + lane; p < p1; p += 32) {
+    const float4 g = geom[p];
+    float Y[NY];
+    SH::sh(g.x, g.y, g.z, Y);
+#pragma unroll
+    for (int i = 0; i < NY; ++i) acc[i] += Y[i];
+  }
+#pragma unroll
+  for (int i = 0; i < NY; ++i) {
+    float v = acc[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    acc[i] = v;
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NY; ++i) attrs[(size_t)row * NY + i] = acc[i] * scale;
+  }
+}
+
+template <class TP>
+__global__ void node_tp_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y, int64_t n,
+                                   float* __restrict__ T) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float xr[TP::DXP], Y[TP::NY], w[TP::NLIVE], m[TP::DLIVE];
+  load_x<TP>(x, (int)i, xr);
+#pragma unroll
+  for (int j = 0; j < TP::NY; ++j) Y[j] = y[(size_t)i * TP::NY + j];
+#pragma unroll
+  for (int c = 0; c < TP::NLIVE; ++c) w[c] = 1.f;
+  TP::fwd(xr, Y, w, m);
+#pragma unroll
+  for (int j = 0; j < TP::DLIVE; ++j) T[(size_t)i * TP::DLIVE + j] = m[j];
+}
+
+template <class TP>
+__global__ void node_tp_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                   const float* __restrict__ gT, int64_t n, float* __restrict__ dxo) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float xr[TP::DXP], Y[TP::NY], w[TP::NLIVE], g[TP::DLIVE], dw[TP::NLIVE], dx[TP::DXP];
+  load_x<TP>(x, (int)i, xr);
+#pragma unroll
+  for (int j = 0; j < TP::NY; ++j) Y[j] = y[(size_t)i * TP::NY + j];
+#pragma unroll
+  for (int c = 0; c < TP::NLIVE; ++c) w[c] = 1.f;
+#pragma unroll
+  for (int j = 0; j < TP::DLIVE; ++j) g[j] = gT[(size_t)i * TP::DLIVE + j];
+  TP::bwd(xr, Y, w, g, dw, dx);
+#pragma unroll
+  for (int j = 0; j < TP::DXP; ++j) dxo[(size_t)i * TP::DXP + j] = dx[j];
+}
+
+}  // namespace
+
+extern "C" int eqnn_tp_signature_count(void) { return EQNN_TP_COUNT; }
+extern "C" const char* eqnn_tp_signature(int id) {
+  return (id >= 0 && id < EQNN_TP_COUNT) ? EQNN_TP_SIGNATURES[id] : nullptr;
+}
+extern "C" int eqnn_tp_lookup(const char* sig) {
+  if (!sig) return -1;
+  for (int i = 0; i < EQNN_TP_COUNT; ++i)
+    if (strcmp(sig, EQNN_TP_SIGNATURES[i]) == 0) return i;
+  return -1;
+}
+extern "C" int eqnn_tp_dims(int id, int* dxp, int* ny, int* n_live, int* d_live) {
+  EQNN_TP_DISPATCH(id, {
+    if (dxp) *dxp = TP::DXP;
+    if (ny) *ny = TP::NY;
+    if (n_live) *n_live = TP::NLIVE;
+    if (d_live) *d_live = TP::DLIVE;
+  });
+  return EQNN_OK;
+}
+
+extern "C" int eqnn_tpconv_fwd(int tp_id, const int32_t* rowptr, const int32_t* src, const float* geom,
+                               const float* w_t, int64_t n_edges, const float* xt, int n_nodes, int agg, float* A,
+                               int ld_a, eqnn_stream_t stream) {
+  EQNN_CHECK_ARG(rowptr && src && geom && w_t && xt && A, "tpconv_fwd: null pointer");
+  EQNN_CHECK_ARG(agg == 0 || agg == 1, "tpconv_fwd: agg must be 0 (sum) or 1 (mean)");
+  EQNN_CHECK_ARG(((uintptr_t)geom & 15) == 0 && ((uintptr_t)xt & 15) == 0, "tpconv_fwd: geom/xt must be 16-byte aligned");
+  if (n_nodes <= 0) return EQNN_OK;
+  const unsigned grid = (unsigned)((n_nodes + TPC_ROWS - 1) / TPC_ROWS);
+  EQNN_TP_DISPATCH(tp_id, {
+    EQNN_CHECK_ARG(ld_a >= TP::DLIVE, "tpconv_fwd: ld_a smaller than live width");
+    tpconv_fwd_kernel<TP><<<grid, TPC_THREADS, 0, as_stream(stream)>>>(
+        rowptr, src, reinterpret_cast<const float4*>(geom), w_t, n_edges, xt, n_nodes, agg, A, ld_a);
+  });
+  EQNN_CHECK_LAUNCH();
+  return EQNN_OK;
+}
+
+extern "C" int eqnn_tpconv_bwd(int tp_id, const int32_t* rowptr, const int32_t* src, const int32_t* perm,
+                               const float* geom, const float* w_t, int64_t n_edges, const float* xt, int n_nodes,
+                               int agg, const float* gA, int ld_ga, float* dw_t, float* dxe,
+                               eqnn_stream_t stream) {
+  EQNN_CHECK_ARG(rowptr && src && perm && geom && w_t && xt && gA && dw_t && dxe, "tpconv_bwd: null pointer");
+  EQNN_CHECK_ARG(agg == 0 || agg == 1, "tpconv_bwd: agg must be 0 (sum) or 1 (mean)");
+  EQNN_CHECK_ARG(((uintptr_t)geom & 15) == 0 && ((uintptr_t)xt & 15) == 0 && ((uintptr_t)dxe & 15) == 0,
+                 "tpconv_bwd: geom/xt/dxe must be 16-byte aligned");
+  if (n_nodes <= 0) return EQNN_OK;
+  const unsigned grid = (unsigned)((n_nodes + TPC_ROWS - 1) / TPC_ROWS);
+  EQNN_TP_DISPATCH(tp_id, {
+    EQNN_CHECK_ARG(ld_ga >= TP::DLIVE, "tpconv_bwd: ld_ga smaller than live width");
+    tpconv_bwd_kernel<TP><<<grid, TPC_THREADS, 0, as_stream(stream)>>>(
+        rowptr, src, perm, reinterpret_cast<const float4*>(geom), w_t, n_edges, xt, n_nodes, agg, gA, ld_ga, dw_t,
+        dxe);
+  });
+  EQNN_CHECK_LAUNCH();
+  return EQNN_OK;
+}
+
+extern "C" int eqnn_sender_reduce(const float* dxe, int n_nodes, int k, int dxp, float* dxt,
+                                  eqnn_stream_t stream) {
+  EQNN_CHECK_ARG(dxe && dxt && k >= 1 && dxp >= 1, "sender_reduce: bad argument");
+  if (n_nodes <= 0) return EQNN_OK;
+  const int64_t n = (int64_t)n_nodes * dxp;
+  sender_reduce_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, as_stream(stream)>>>(dxe, n_nodes, k, dxp, dxt);
+  EQNN_CHECK_LAUNCH();
+  return EQNN_OK;
+}
+
+extern "C" int eqnn_segment_gather_sum(const float* dxe, const int32_t* rowptr_s, const int32_t* perm_s,
+                                       int n_nodes, int dxp, float* dxt, eqnn_stream_t stream) {
+  EQNN_CHECK_ARG(dxe && rowptr_s && perm_s && dxt && dxp >= 1, "segment_gather_sum: bad argument");
+  if (n_nodes <= 0) return EQNN_OK;
+  const int64_t n = (int64_t)n_nodes * dxp;
+  segment_gather_sum_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, as_stream(stream)>>>(dxe, rowptr_s, perm_s,
+                                                                                        n_nodes, dxp, dxt);
+  EQNN_CHECK_LAUNCH();
+  return EQNN_OK;
+}
+
+extern "C" int eqnn_sh_scatter(int lmax, const int32_t* rowptr, const float* geom, int n_nodes, float scale,
+                               float* attrs, eqnn_stream_t stream) {
+  EQNN_CHECK_ARG(rowptr && geom && attrs, "sh_scatter: null pointer");
+  EQNN_CHECK_ARG(lmax >= 1 && lmax <= 3, "sh_scatter: lmax must be 1..3");
+  if (n_nodes <= 0) return EQNN_OK;
+  const unsigned grid = (unsigned)ceil_div64((int64_t)n_nodes * 32, 256);
+  const float4* g = reinterpret_cast<const float4*>(geom);
+  cudaStream_t st = as_stream(stream);
+  if (lmax == 1) sh_scatter_kernel<SH_1><<<grid, 256, 0, st>>>(rowptr, g, n_nodes, scale, attrs);
+  else if (lmax == 2) sh_scatter_kernel<SH_2><<<grid, 256, 0, st>>>(rowptr, g, n_nodes, scale, attrs);
+  else sh_scatter_kernel<SH_3><<<grid, 256, 0, st>>>(rowptr, g, n_nodes, scale, attrs);
+  EQNN_CHECK_LAUNCH();
+  return EQNN_OK;
+}
+
+extern "C" int eqnn_node_tp_fwd(int tp_id, const float* x, const float* y, int64_t n, float* T,
+                                eqnn_stream_t stream) {
+  EQNN_CHECK_ARG(x && y && T, "node_tp_fwd: null pointer");
+  if (n <= 0) return EQNN_OK;
+  EQNN_TP_DISPATCH(tp_id, {
+    node_tp_fwd_kernel<TP><<<(unsigned)ceil_div64(n, 128), 128, 0, as_stream(stream)>>>(x, y, n, T);
+  });
+  EQNN_CHECK_LAUNCH();
+  return EQNN_OK;
+}
+
+extern "C" int eqnn_node_tp_bwd(int tp_id, const float* x, const float* y, const float* gT, int64_t n, float* dx,
+                                eqnn_stream_t stream) {
+  EQNN_CHECK_ARG(x && y && gT && dx, "node_tp_bwd: null pointer");
+  if (n <= 0) return EQNN_OK;
+  EQNN_TP_DISPATCH(tp_id, {
+    node_tp_bwd_kernel<TP><<<(unsigned)ceil_div64(n, 128), 128, 0, as_stream(stream)>>>(x, y, gT, n, dx);
+  });
+  EQNN_CHECK_LAUNCH();
+  return EQNN_OK;
+}

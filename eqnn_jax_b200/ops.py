@@ -1,0 +1,218 @@
+"""Thin torch-tensor wrappers over the C ABI (include/eqnn_b200.h).
+
+torch supplies device memory and the CUDA stream only; every computation below
+is a hand-written sm_100a kernel reached through ctypes.  All tensors must be
+CUDA tensors (fp32 / int32, contiguous unless strides are passed explicitly).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from ._lib import check, lib
+
+_F32, _I32 = torch.float32, torch.int32
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _req(t: torch.Tensor, dtype, name: str, contiguous: bool = True) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor (this path has no CPU implementation)")
+    if t.dtype != dtype:
+        raise RuntimeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if contiguous and not t.is_contiguous():
+        raise RuntimeError(f"{name}: expected a contiguous tensor")
+    return t
+
+
+# ---------------------------------------------------------------- signatures
+def tp_lookup(signature: str) -> int:
+    i = lib().eqnn_tp_lookup(signature.encode())
+    if i < 0:
+        have = [lib().eqnn_tp_signature(j).decode() for j in range(lib().eqnn_tp_signature_count())]
+        raise RuntimeError(
+            f"tensor-product signature {signature!r} is not compiled into libeqnn_b200.so; add it to "
+            f"eqnn_jax_b200.codegen.PREBUILT and rebuild. Available: {have}")
+    return i
+
+
+def tp_dims(tp_id: int) -> Tuple[int, int, int, int]:
+    v = [C.c_int() for _ in range(4)]
+    check(lib().eqnn_tp_dims(tp_id, *[C.byref(x) for x in v]), "tp_dims")
+    return tuple(x.value for x in v)
+
+
+# ---------------------------------------------------------------- graph build
+def knn_pbc(x: torch.Tensor, k: int, cell=None, cell_inv=None, fma: bool = False, want_dr: bool = True):
+    """x [B, N, F>=3] -> senders [B,E], receivers [B,E] (int32), dr [B,E,3]."""
+    _req(x, _F32, "x")
+    B, N, F = x.shape
+    E = N * k
+    senders = torch.empty((B, E), dtype=_I32, device=x.device)
+    receivers = torch.empty((B, E), dtype=_I32, device=x.device)
+    dr = torch.empty((B, E, 3), dtype=_F32, device=x.device) if want_dr else None
+    flags = (1 if cell is not None else 0) | (2 if fma else 0)
+    c9 = (C.c_float * 9)(*[float(v) for v in cell.reshape(-1)]) if cell is not None else None
+    ci9 = (C.c_float * 9)(*[float(v) for v in cell_inv.reshape(-1)]) if cell is not None else None
+    check(lib().eqnn_knn_pbc(_ptr(x), F, c9, ci9, B, N, k, flags, _ptr(senders), _ptr(receivers), _ptr(dr),
+                             None, 0, _stream()), "knn_pbc")
+    return senders, receivers, dr
+
+
+def edge_features(dr: torch.Tensor, n_rb: int, r_max: float) -> torch.Tensor:
+    """dr [..., 3] -> |dr| [..., 1] (n_rb == 0) or bessel basis [..., n_rb]."""
+    _req(dr, _F32, "dr")
+    n = dr.numel() // 3
+    out = torch.empty(dr.shape[:-1] + (max(n_rb, 1),), dtype=_F32, device=dr.device)
+    check(lib().eqnn_edge_features(_ptr(dr), n, n_rb, float(r_max), _ptr(out), _stream()), "edge_features")
+    return out
+
+
+def csr_build(senders: torch.Tensor, receivers: torch.Tensor, n_nodes_per_graph: int):
+    """[B,E] local ids -> rowptr [B*N+1], perm [B*E], src [B*E] (all int32, global ids)."""
+    _req(senders, _I32, "senders")
+    _req(receivers, _I32, "receivers")
+    B, E = receivers.shape
+    N = n_nodes_per_graph
+    dev = receivers.device
+    rowptr = torch.empty((B * N + 1,), dtype=_I32, device=dev)
+    perm = torch.empty((B * E,), dtype=_I32, device=dev)
+    src = torch.empty((B * E,), dtype=_I32, device=dev)
+    nbytes = lib().eqnn_csr_workspace_bytes(B, N, E)
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+    check(lib().eqnn_csr_build(_ptr(senders), _ptr(receivers), B, N, E, _ptr(rowptr), _ptr(perm), _ptr(src),
+                               _ptr(ws), nbytes, _stream()), "csr_build")
+    return rowptr, perm, src
+
+
+def edge_geom(pos: torch.Tensor, ld_pos: int, n_nodes: int, rowptr, src, n_rb: int, r_cut: float):
+    """-> geom [Etot,4] (r_hat, d), radial [Etot, max(n_rb,1)]."""
+    n_edges = src.numel()
+    geom = torch.empty((n_edges, 4), dtype=_F32, device=src.device)
+    radial = torch.empty((n_edges, max(n_rb, 1)), dtype=_F32, device=src.device)
+    check(lib().eqnn_edge_geom(_ptr(pos), ld_pos, n_nodes, _ptr(rowptr), _ptr(src), n_rb, float(r_cut),
+                               _ptr(geom), _ptr(radial), _stream()), "edge_geom")
+    return geom, radial
+
+
+# ---------------------------------------------------------------- interaction block
+def tpconv_fwd(tp_id, rowptr, src, geom, w_t, xt, n_nodes, agg, out, ld_out):
+    check(lib().eqnn_tpconv_fwd(tp_id, _ptr(rowptr), _ptr(src), _ptr(geom), _ptr(w_t), src.numel(), _ptr(xt),
+                                n_nodes, agg, _ptr(out), ld_out, _stream()), "tpconv_fwd")
+
+
+def tpconv_bwd(tp_id, rowptr, src, perm, geom, w_t, xt, n_nodes, agg, gA, ld_ga, dw_t, dxe):
+    check(lib().eqnn_tpconv_bwd(tp_id, _ptr(rowptr), _ptr(src), _ptr(perm), _ptr(geom), _ptr(w_t), src.numel(),
+                                _ptr(xt), n_nodes, agg, _ptr(gA), ld_ga, _ptr(dw_t), _ptr(dxe), _stream()),
+          "tpconv_bwd")
+
+
+def sender_reduce(dxe, n_nodes, k, dxp, dxt):
+    check(lib().eqnn_sender_reduce(_ptr(dxe), n_nodes, k, dxp, _ptr(dxt), _stream()), "sender_reduce")
+
+
+def segment_gather_sum(dxe, rowptr_s, perm_s, n_nodes, dxp, dxt):
+    check(lib().eqnn_segment_gather_sum(_ptr(dxe), _ptr(rowptr_s), _ptr(perm_s), n_nodes, dxp, _ptr(dxt), _stream()),
+          "segment_gather_sum")
+
+
+def sh_scatter(lmax, rowptr, geom, n_nodes, scale, attrs):
+    check(lib().eqnn_sh_scatter(lmax, _ptr(rowptr), _ptr(geom), n_nodes, float(scale), _ptr(attrs), _stream()),
+          "sh_scatter")
+
+
+def node_tp_fwd(tp_id, x, y, n, T):
+    check(lib().eqnn_node_tp_fwd(tp_id, _ptr(x), _ptr(y), n, _ptr(T), _stream()), "node_tp_fwd")
+
+
+def node_tp_bwd(tp_id, x, y, gT, n, dx):
+    check(lib().eqnn_node_tp_bwd(tp_id, _ptr(x), _ptr(y), _ptr(gT), n, _ptr(dx), _stream()), "node_tp_bwd")
+
+
+# ---------------------------------------------------------------- dense
+class GemmWorkspace:
+    """Grow-only split-K scratch buffer (torch owns the memory)."""
+
+    def __init__(self):
+        self.buf: Optional[torch.Tensor] = None
+
+    def get(self, nbytes: int, device) -> Tuple[C.c_void_p, int]:
+        if nbytes == 0:
+            return C.c_void_p(0), 0
+        if self.buf is None or self.buf.numel() < nbytes or self.buf.device != device:
+            self.buf = torch.empty((nbytes,), dtype=torch.uint8, device=device)
+        return C.c_void_p(self.buf.data_ptr()), self.buf.numel()
+
+
+_GEMM_WS = GemmWorkspace()
+
+
+def gemm(M, N, K, alpha, A, sam, sak, B, sbk, sbn, Cm, scm, scn, accumulate=False, pro=0, pro_scale=1.0, epi=0,
+         aux=None, ld_aux=0, epi_scale=1.0, a_off=0, b_off=0, c_off=0, aux_off=0):
+    """C[m,n] (+)= epi(alpha * sum_k pro(A[m,k]) B[k,n]); element strides; *_off = element offsets."""
+    L = lib()
+    need = L.eqnn_gemm_workspace_bytes(M, N, K)
+    ws, ws_bytes = _GEMM_WS.get(need, Cm.device)
+    pa = C.c_void_p(A.data_ptr() + 4 * a_off)
+    pb = C.c_void_p(B.data_ptr() + 4 * b_off)
+    pc = C.c_void_p(Cm.data_ptr() + 4 * c_off)
+    px = C.c_void_p(0 if aux is None else aux.data_ptr() + 4 * aux_off)
+    check(L.eqnn_gemm_f32(M, N, K, float(alpha), pa, sam, sak, pb, sbk, sbn, pc, scm, scn, 1 if accumulate else 0,
+                          pro, float(pro_scale), epi, px, ld_aux, float(epi_scale), ws, ws_bytes, _stream()), "gemm")
+
+
+def _int_arr(v: Sequence[int]):
+    return (C.c_int * max(len(v), 1))(*v)
+
+
+def gate_fwd(z, n, n_extra, n_gates, mul, l, inv_c_act, inv_c_gate, out):
+    check(lib().eqnn_gate_fwd(_ptr(z), n, n_extra, n_gates, len(mul), _int_arr(mul), _int_arr(l), inv_c_act,
+                              inv_c_gate, _ptr(out), _stream()), "gate_fwd")
+
+
+def gate_bwd(z, gout, n, n_extra, n_gates, mul, l, inv_c_act, inv_c_gate, gz):
+    check(lib().eqnn_gate_bwd(_ptr(z), _ptr(gout), n, n_extra, n_gates, len(mul), _int_arr(mul), _int_arr(l),
+                              inv_c_act, inv_c_gate, _ptr(gz), _stream()), "gate_bwd")
+
+
+def pool_fwd(x, B, N, D, mode, out):
+    check(lib().eqnn_pool_fwd(_ptr(x), B, N, D, mode, _ptr(out), _stream()), "pool_fwd")
+
+
+def pool_bwd(gout, B, N, D, mode, gx):
+    check(lib().eqnn_pool_bwd(_ptr(gout), B, N, D, mode, _ptr(gx), _stream()), "pool_bwd")
+
+
+def colsum(x, M, N, y, x_off=0, y_off=0):
+    check(lib().eqnn_colsum(C.c_void_p(x.data_ptr() + 4 * x_off), M, N, C.c_void_p(y.data_ptr() + 4 * y_off),
+                            _stream()), "colsum")
+
+
+def weights_expand(params, idx, scale, dst):
+    check(lib().eqnn_weights_expand(_ptr(params), _ptr(idx), _ptr(scale), dst.numel(), _ptr(dst), _stream()),
+          "weights_expand")
+
+
+def weights_contract(ddst, pidx, ptr, tidx, scale_t, grads):
+    check(lib().eqnn_weights_contract(_ptr(ddst), _ptr(pidx), _ptr(ptr), _ptr(tidx), _ptr(scale_t), pidx.numel(),
+                                      _ptr(grads), _stream()), "weights_contract")
+
+
+def mse_loss(pred, target, gscale, loss, gpred):
+    B, O = pred.shape
+    check(lib().eqnn_mse_loss(_ptr(pred), _ptr(target), B, O, float(gscale), _ptr(loss), _ptr(gpred), _stream()),
+          "mse_loss")
+
+
+def adamw(params, grads, m, v, lr, b1, b2, eps, wd, step):
+    check(lib().eqnn_adamw(_ptr(params), _ptr(grads), _ptr(m), _ptr(v), params.numel(), lr, b1, b2, eps, wd, step,
+                           _stream()), "adamw")

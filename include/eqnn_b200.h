@@ -1,0 +1,185 @@
+/*
+ * eqnn_b200 -- C ABI of the B200-native (sm_100a) kernels behind eqnn-jax's
+ * equivariant message-passing hot path.
+ *
+ * The reference (smsharma/eqnn-jax) is pure Python on jax/e3nn-jax/jraph and
+ * exposes no FFI of its own; each entry point below therefore cites the Python
+ * call site(s) whose arithmetic it replaces (paths relative to the reference
+ * root).  INTEGRATION.md shows the jax.ffi binding a maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the comment says "host";
+ *   - all arrays are dense fp32 / int32, row-major unless stated otherwise;
+ *   - the caller owns every buffer (inputs, outputs, workspaces); the library
+ *     never allocates or frees device memory and keeps no pointer after return;
+ *   - kernels are enqueued asynchronously on `stream`; no call synchronises the
+ *     device, so every call is CUDA-graph capturable;
+ *   - return value 0 = ok, non-zero = EQNN_ERR_*; eqnn_last_error_string()
+ *     gives the thread-local message.  No exception crosses this boundary.
+ *   - a batch of B graphs with N nodes each is addressed with GLOBAL node ids
+ *     n = b*N + i and GLOBAL edge ids e = b*E + j.
+ */
+#ifndef EQNN_B200_H_
+#define EQNN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* eqnn_stream_t; /* cudaStream_t */
+
+enum {
+  EQNN_OK = 0,
+  EQNN_ERR_ARG = 1,        /* invalid argument */
+  EQNN_ERR_WORKSPACE = 2,  /* workspace too small */
+  EQNN_ERR_SIGNATURE = 3,  /* tensor-product signature not compiled in */
+  EQNN_ERR_CUDA = 4        /* CUDA runtime error at launch */
+};
+
+const char* eqnn_last_error_string(void);
+int eqnn_version(void);
+
+/* ---- tensor-product signatures compiled into the library (csrc/gen/tp_gen.cuh) ---- */
+int eqnn_tp_signature_count(void);
+const char* eqnn_tp_signature(int id);       /* host string */
+int eqnn_tp_lookup(const char* signature);   /* -> id or -1 */
+int eqnn_tp_dims(int id, int* dxp, int* ny, int* n_live, int* d_live);
+
+/* ---- graph construction -------------------------------------------------------------
+ * eqnn_knn_pbc replaces models/utils/graph_utils.py:40-72 `nearest_neighbors` vmapped
+ * over the batch (:280-282) with `apply_pbc` of :13-37 fused in.  Bit-exact contract
+ * (SURVEY.md C.3): every fp32 operation individually rounded (no FMA contraction)
+ *     d_c  = (x_i[c] - x_j[c]) + 1e-7f
+ *     d_c -= rint(d . cell_inv)[.] . cell          (only if EQNN_KNN_PBC)
+ *     D_ij = (d_0^2 + d_1^2) + d_2^2
+ * and the k smallest D_ij per row in stable order (ties -> smaller j); j == i included.
+ *   x          [B, N, ld_x] fp32, the first three columns are the coordinates
+ *   cell, cell_inv   HOST pointers to 9 floats (row-major 3x3); may be NULL without PBC
+ *   senders    [B, N*k] int32  = repeat(arange(N), k)          (graph_utils.py:70)
+ *   receivers  [B, N*k] int32  = neighbour indices, local ids  (graph_utils.py:71)
+ *   dr         [B, N*k, 3] fp32 = wrapped displacement of each selected pair (:72); may be NULL
+ * flags: EQNN_KNN_PBC; EQNN_KNN_FMA contracts D_ij as fma(d2,d2,fma(d1,d1,d0*d0))
+ *        (what an FMA-fusing CPU backend would produce; off by default).            */
+enum { EQNN_KNN_PBC = 1, EQNN_KNN_FMA = 2 };
+size_t eqnn_knn_workspace_bytes(int B, int N, int k);
+int eqnn_knn_pbc(const float* x, int ld_x, const float* cell, const float* cell_inv, int B, int N, int k,
+                 int flags, int32_t* senders, int32_t* receivers, float* dr, void* ws, size_t ws_bytes,
+                 eqnn_stream_t stream);
+
+/* GraphsTuple.edges of build_graph (models/utils/graph_utils.py:298-302):
+ *   n_rb == 0: out [n_edges, 1] = |dr|;  n_rb > 0: out [n_edges, n_rb] = e3nn.bessel(|dr|, n_rb, r_max) */
+int eqnn_edge_features(const float* dr, int64_t n_edges, int n_rb, double r_max, float* out, eqnn_stream_t stream);
+
+/* Receiver-sorted CSR of the batch (replaces the unsorted scatter of
+ * jraph segment_sum/segment_mean at models/nequip.py:118-120,154-159).
+ *   senders/receivers [B, E] local ids  ->
+ *   rowptr [B*N + 1]  global CSR offsets per global receiver id
+ *   perm   [B*E]      global edge id stored at each CSR position (ascending inside a row,
+ *                     i.e. the sequential order of a CPU scatter-add)
+ *   src    [B*E]      global sender id at each CSR position                          */
+size_t eqnn_csr_workspace_bytes(int B, int N, int E);
+int eqnn_csr_build(const int32_t* senders, const int32_t* receivers, int B, int N, int E, int32_t* rowptr,
+                   int32_t* perm, int32_t* src, void* ws, size_t ws_bytes, eqnn_stream_t stream);
+
+/* Per-edge geometry in CSR order (models/nequip.py:129-134 r_ij = x_s - x_r, no PBC, no EPS;
+ * :55 d = |r_ij|; :57 e3nn.bessel):
+ *   geom   [B*E] float4 = (r_hat.x, r_hat.y, r_hat.z, d); r_hat = 0 where d == 0
+ *   radial [B*E, n_rb]  = sqrt(2/r_cut) sin(j pi d / r_cut)/d, j=1..n_rb (limit at d=0);
+ *                         if n_rb == 0: radial [B*E, 1] = d (nequip.py:59)
+ * Every operation is rounded to fp32 where the reference's XLA:CPU graph rounds (the Bessel
+ * phase j*pi/r_cut*d is ill-conditioned; reproducing its rounding points is what keeps parity). */
+int eqnn_edge_geom(const float* pos, int ld_pos, int n_nodes, const int32_t* rowptr, const int32_t* src,
+                   int n_rb, double r_cut, float* geom, float* radial, eqnn_stream_t stream);
+
+/* ---- NequIP interaction block -------------------------------------------------------
+ * eqnn_tpconv_fwd: for every receiver r
+ *     A[r, :] = agg_{e -> r}  w_t[:, e] (x)  CG( xt[src(e)],  Y_lm(r_hat_e) )
+ * = models/nequip.py:46-52 (spherical harmonics, tensor_product), :68 (per-irrep
+ * radial weights) and the jraph aggregation :118-120, restricted to live columns.
+ *   tp_id  signature id (x irreps, lmax, live set)
+ *   xt     [n_nodes, DXP] regrouped + padded sender record (Linear of :43 applied)
+ *   w_t    [NLIVE, n_edges] column-major radial weights in CSR order
+ *   agg    0 = sum, 1 = mean (divide by max(in-degree, 1))
+ *   A      [n_nodes, ld_a], first DLIVE columns written
+ * Harmonics are unit-norm ("norm"); the caller folds the e3nn normalisation factor
+ * of each l into the weights that produce w_t.                                       */
+int eqnn_tpconv_fwd(int tp_id, const int32_t* rowptr, const int32_t* src, const float* geom, const float* w_t,
+                    int64_t n_edges, const float* xt, int n_nodes, int agg, float* A, int ld_a,
+                    eqnn_stream_t stream);
+/* Backward of the above w.r.t. w_t and xt (the custom_vjp rule):
+ *   gA    [n_nodes, ld_ga]  dL/dA
+ *   dw_t  [NLIVE, n_edges]  dL/dw_t
+ *   dxe   [n_edges, DXP]    per-edge dL/dxt contribution, stored at the ORIGINAL edge id
+ *                           (perm) so that senders' k edges are contiguous            */
+int eqnn_tpconv_bwd(int tp_id, const int32_t* rowptr, const int32_t* src, const int32_t* perm, const float* geom,
+                    const float* w_t, int64_t n_edges, const float* xt, int n_nodes, int agg, const float* gA,
+                    int ld_ga, float* dw_t, float* dxe, eqnn_stream_t stream);
+/* dxt[s, :] = sum_{j<k} dxe[s*k + j, :]   (sender-major fixed out-degree k, graph_utils.py:70) */
+int eqnn_sender_reduce(const float* dxe, int n_nodes, int k, int dxp, float* dxt, eqnn_stream_t stream);
+/* general out-degree: dxt[s, :] = sum over row s of a SENDER-sorted CSR (eqnn_csr_build with the roles of
+ * senders and receivers swapped) of dxe[perm_s[q], :]; ascending edge id inside a row => deterministic */
+int eqnn_segment_gather_sum(const float* dxe, const int32_t* rowptr_s, const int32_t* perm_s, int n_nodes, int dxp,
+                            float* dxt, eqnn_stream_t stream);
+
+/* node_attrs = scatter_sum(Y(r_ij), receivers) * scale   (models/nequip.py:180-191), unit-norm Y */
+int eqnn_sh_scatter(int lmax, const int32_t* rowptr, const float* geom, int n_nodes, float scale, float* attrs,
+                    eqnn_stream_t stream);
+/* T = tensor_product(x, y) restricted to live columns, per node (models/nequip.py:197) */
+int eqnn_node_tp_fwd(int tp_id, const float* x, const float* y, int64_t n, float* T, eqnn_stream_t stream);
+int eqnn_node_tp_bwd(int tp_id, const float* x, const float* y, const float* gT, int64_t n, float* dx,
+                     eqnn_stream_t stream);
+
+/* ---- dense building block ------------------------------------------------------------
+ * C[m,n] (+)= epi( alpha * sum_k pro(A[m,k]) * B[k,n] ), arbitrary element strides.
+ * Used for the radial MLP (e3nn.flax.MultiLayerPerceptron, nequip.py:62-66), the
+ * irreps Linear layers lowered to dense matrices (:43,85,162,197) and models/mlp.py.
+ *   pro: 0 none | 1 A := gelu_tanh(A) * pro_scale
+ *   epi: 0 none | 1 += bias[n] (aux = bias) | 2 *= gelu_tanh'(aux[m*ld_aux+n]) * epi_scale
+ *   flags: EQNN_GEMM_ACCUMULATE adds to C.  Large-K problems are split over CTAs
+ *   through `ws` (eqnn_gemm_workspace_bytes) and reduced in a fixed order.          */
+enum { EQNN_GEMM_ACCUMULATE = 1 };
+size_t eqnn_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K);
+int eqnn_gemm_f32(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t sam, int64_t sak,
+                  const float* B, int64_t sbk, int64_t sbn, float* C, int64_t scm, int64_t scn, int flags,
+                  int pro, float pro_scale, int epi, const float* aux, int64_t ld_aux, float epi_scale, void* ws,
+                  size_t ws_bytes, eqnn_stream_t stream);
+
+/* e3nn.gate with default activations (models/nequip.py:88-90):
+ *   z   [n, n_extra + n_gates + sum_c mul_c (2 l_c + 1)] = [scalars | gates | gated chunks]
+ *   out [n, n_extra + gated dims] = [gelu(z_extra)/c_act | sigmoid(gate)/c_gate * gated]
+ *   mul, l: HOST arrays of the n_chunks gated chunks.                                */
+int eqnn_gate_fwd(const float* z, int64_t n, int n_extra, int n_gates, int n_chunks, const int* mul, const int* l,
+                  float inv_c_act, float inv_c_gate, float* out, eqnn_stream_t stream);
+int eqnn_gate_bwd(const float* z, const float* gout, int64_t n, int n_extra, int n_gates, int n_chunks,
+                  const int* mul, const int* l, float inv_c_act, float inv_c_gate, float* gz,
+                  eqnn_stream_t stream);
+
+/* out[b, :] = reduce_n x[b, n, :]   (mode 0 sum, 1 mean; nequip.py:196-199) and its backward */
+int eqnn_pool_fwd(const float* x, int B, int N, int D, int mode, float* out, eqnn_stream_t stream);
+int eqnn_pool_bwd(const float* gout, int B, int N, int D, int mode, float* gx, eqnn_stream_t stream);
+/* y[n] = sum_m x[m, n]  (bias gradients) */
+int eqnn_colsum(const float* x, int64_t M, int N, float* y, eqnn_stream_t stream);
+
+/* ---- parameter plumbing ----------------------------------------------------------------
+ * dst[t] = idx[t] < 0 ? 0 : scale[t] * params[idx[t]]     (Linear -> dense matrix, live columns)
+ * grads[pidx[j]] = sum_{t in [ptr[j], ptr[j+1])} scale_t[t] * ddst[tidx[t]]               */
+int eqnn_weights_expand(const float* params, const int32_t* idx, const float* scale, int64_t n_dst, float* dst,
+                        eqnn_stream_t stream);
+int eqnn_weights_contract(const float* ddst, const int32_t* pidx, const int32_t* ptr, const int32_t* tidx,
+                          const float* scale_t, int64_t n_params, float* grads, eqnn_stream_t stream);
+
+/* ---- training step tail (benchmarks/galaxies/train_cosmology.py:236-247) --------------- */
+/* loss = mean_b mean_o (pred - target)^2 ; gpred = dloss/dpred * gscale                    */
+int eqnn_mse_loss(const float* pred, const float* target, int B, int O, float gscale, float* loss, float* gpred,
+                  eqnn_stream_t stream);
+/* optax.adamw (decoupled weight decay); lr read from the host argument                     */
+int eqnn_adamw(float* params, const float* grads, float* m, float* v, int64_t n, float lr, float b1, float b2,
+               float eps, float wd, int step, eqnn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EQNN_B200_H_ */

@@ -215,8 +215,25 @@ def gate(x: IrrepsArray, even_act="gelu", even_gate_act="sigmoid") -> IrrepsArra
 # ----------------------------------------------------------------------------
 # e3nn.bessel (A.7), e3nn.flax.MultiLayerPerceptron (A.5), models/mlp.py
 # ----------------------------------------------------------------------------
-def bessel(d: torch.Tensor, n: int, x_max: float) -> torch.Tensor:
+def bessel(d: torch.Tensor, n: int, x_max: float, reference_rounding: bool = True) -> torch.Tensor:
+    """e3nn.bessel: sqrt(2/c) * sin(j pi / c * x) / x  (limit j pi / c at x = 0).
+
+    The phase j*pi/c*x reaches O(1e2..1e3) on this path, so its fp32 rounding moves the
+    result by up to ~1e-4: it is the one place where the reference's fp32 arithmetic is
+    not reproducible by "exact" math.  With ``reference_rounding`` the phase is formed
+    with the reference's fp32 rounding points, ((j * pi) / c) * x with j, pi, c, x in
+    fp32 (JAX weak-type promotion of the Python scalars), also when the oracle runs in
+    fp64; everything downstream of the phase is evaluated in the working dtype."""
     x = d[..., None]
+    if reference_rounding:
+        x32 = x.to(torch.float32)
+        j32 = torch.arange(1, n + 1, dtype=torch.float32)
+        w32 = (j32 * math.pi) / x_max                       # fp32 mul, fp32 div (scalars cast to fp32)
+        xs32 = torch.where(x32 == 0, torch.ones_like(x32), x32)
+        phase = (w32 * xs32).to(d.dtype)
+        w, xs = w32.to(d.dtype), xs32.to(d.dtype)
+        val = torch.where(x == 0, w + 0 * x, torch.sin(phase) / xs)
+        return float(np.float32(math.sqrt(2.0 / x_max))) * val   # jnp.sqrt(2.0 / x_max): weak-typed fp32 constant
     j = torch.arange(1, n + 1, dtype=d.dtype)
     xs = torch.where(x == 0, torch.ones_like(x), x)
     val = torch.where(x == 0, j * math.pi / x_max + 0 * x, torch.sin(j * math.pi / x_max * xs) / xs)

@@ -115,8 +115,13 @@ def apply_single(params, cfg: NequIPConfig, graph: GraphsTuple, irreps_in, inter
     irreps_hidden = balanced_irreps(lmax=cfg.l_max, feature_size=cfg.d_hidden, use_sh=True)
     irreps_out = Irreps(cfg.irreps_out) if cfg.irreps_out is not None else irreps_in
 
-    pos = nodes.first_irrep_copy().array                       # nequip.py:129-132
-    r_ij = pos[senders] - pos[receivers]                        # :134
+    # nequip.py:129-134.  The reference holds positions in fp32; r_ij and |r_ij| are formed with its
+    # fp32 rounding points (they feed the ill-conditioned Bessel phase, see e3nn_ref.bessel), then promoted.
+    pos32 = nodes.first_irrep_copy().array.to(torch.float32)
+    r32 = pos32[senders] - pos32[receivers]
+    sq = r32 * r32
+    d32 = torch.sqrt((sq[:, 0] + sq[:, 1]) + sq[:, 2])          # jnp.linalg.norm (:55), sequential fp32 sum
+    r_ij = r32.to(dtype)
     li = 0
     for s in range(cfg.message_passing_steps):
         # ---- update_edge_fn (:39-71), called by jraph.GraphNetwork with nodes[senders]
@@ -125,7 +130,7 @@ def apply_single(params, cfg: NequIPConfig, graph: GraphsTuple, irreps_in, inter
         a = E.IrrepsArray(Irreps.spherical_harmonics(cfg.l_max),
                           spherical_harmonics(cfg.l_max, r_ij, True, cfg.sphharm_norm))  # :46-51
         m = E.tensor_product(m, a)                                                    # :52
-        d = torch.sqrt((r_ij * r_ij).sum(-1))                                         # :55
+        d = d32.to(dtype)                                                             # :55
         R = E.bessel(d, cfg.n_radial_basis, cfg.r_cutoff) if cfg.n_radial_basis > 0 else d[..., None]
         W = E.e3nn_mlp_apply(params[f"MultiLayerPerceptron_{s}"], R, cfg.activation, False)  # :62-66
         m = m.mul_by_scalars(W)                                                       # :68

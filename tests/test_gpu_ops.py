@@ -1,0 +1,132 @@
+"""GPU parity of the dense building block, gate, pooling and parameter plumbing against plain torch fp64."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def gelu(x):
+    return 0.5 * x * (1.0 + torch.tanh(math.sqrt(2.0 / math.pi) * (x + 0.044715 * x ** 3)))
+
+
+def gelu_grad(x):
+    x = x.clone().requires_grad_(True)
+    gelu(x).sum().backward()
+    return x.grad
+
+
+def _rel(got, want):
+    return float((got.double().cpu() - want).abs().max() / want.abs().max().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("M,N,K", [(1, 1, 1), (8, 2, 256), (40000, 192, 33), (40000, 7, 170), (5000, 8, 7),
+                                   (70001, 128, 64), (30000, 128, 128), (30000, 11, 128), (300, 130, 50)])
+@pytest.mark.parametrize("ta,tb,tc", [(False, False, False), (True, False, False), (False, True, False),
+                                      (True, True, True)])
+def test_gemm_layouts(M, N, K, ta, tb, tc):
+    from eqnn_jax_b200.nequip import _mm
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g, dtype=torch.float64)
+    B = torch.randn(K, N, generator=g, dtype=torch.float64)
+    want = 0.37 * (A @ B)
+    Ad = (A.t().contiguous() if ta else A).float().cuda()
+    Bd = (B.t().contiguous() if tb else B).float().cuda()
+    Cd = torch.full((N, M) if tc else (M, N), float("nan"), dtype=torch.float32).cuda()
+    _mm(M, N, K, 0.37, Ad, 0, M if ta else K, Bd, 0, K if tb else N, Cd, 0, M if tc else N, ta=ta, tb=tb, tc=tc)
+    got = Cd.t() if tc else Cd
+    assert _rel(got, want) < 2e-6
+
+
+def test_gemm_split_k_weight_gradient_shape_is_deterministic():
+    from eqnn_jax_b200.nequip import _mm
+    g = torch.Generator().manual_seed(0)
+    E, K, N = 200_000, 128, 128
+    Z = torch.randn(E, K, generator=g).cuda()
+    dZ = torch.randn(E, N, generator=g).cuda()
+    outs = []
+    for _ in range(2):
+        C = torch.empty(K, N).cuda()
+        _mm(K, N, E, 0.1, Z, 0, K, dZ, 0, N, C, 0, N, ta=True, pro=1, pro_scale=1.5)
+        outs.append(C.clone())
+    assert torch.equal(outs[0], outs[1])
+    want = 0.1 * ((gelu(Z.double().cpu()) * 1.5).t() @ dZ.double().cpu())
+    assert _rel(outs[0], want) < 1e-5
+
+
+def test_gemm_prologue_epilogue_accumulate_offsets():
+    from eqnn_jax_b200.nequip import _mm
+    g = torch.Generator().manual_seed(1)
+    M, N, K = 999, 70, 45
+    A = torch.randn(M, K, generator=g, dtype=torch.float64)
+    B = torch.randn(K, N, generator=g, dtype=torch.float64)
+    bias = torch.randn(N, generator=g, dtype=torch.float64)
+    aux = torch.randn(M, N, generator=g, dtype=torch.float64)
+    C0 = torch.randn(M, N, generator=g, dtype=torch.float64)
+    buf = torch.zeros(5 + K * N).cuda()
+    buf[5:] = B.float().reshape(-1).cuda()
+    # bias epilogue + gelu prologue, B read at an element offset
+    C = torch.empty(M, N).cuda()
+    _mm(M, N, K, 1.0, A.float().cuda(), 0, K, buf, 5, N, C, 0, N, pro=1, pro_scale=0.7, epi=1, aux=bias.float().cuda())
+    assert _rel(C, (gelu(A) * 0.7) @ B + bias) < 3e-6
+    # derivative epilogue + accumulate
+    C = C0.float().cuda()
+    _mm(M, N, K, 2.0, A.float().cuda(), 0, K, buf, 5, N, C, 0, N, epi=2, aux=aux.float().cuda(), ld_aux=N,
+        epi_scale=1.3, accumulate=True)
+    assert _rel(C, C0 + 2.0 * (A @ B) * gelu_grad(aux) * 1.3) < 3e-6
+
+
+def test_gate_forward_backward():
+    from eqnn_jax_b200 import ops
+    g = torch.Generator().manual_seed(2)
+    n, n_extra, mul, l = 77, 9, [3, 2], [1, 2]
+    n_gates = sum(mul)
+    dg = sum(m * (2 * ll + 1) for m, ll in zip(mul, l))
+    z = torch.randn(n, n_extra + n_gates + dg, generator=g, dtype=torch.float64, requires_grad=True)
+    ca, cg = 1 / 0.652, 1 / 0.5416
+    ext = gelu(z[:, :n_extra]) * ca
+    gates = torch.sigmoid(z[:, n_extra:n_extra + n_gates]) * cg
+    rep = torch.tensor([2 * ll + 1 for m, ll in zip(mul, l) for _ in range(m)])
+    want = torch.cat([ext, torch.repeat_interleave(gates, rep, dim=1) * z[:, n_extra + n_gates:]], 1)
+    cot = torch.randn(want.shape, generator=g, dtype=torch.float64)
+    (want * cot).sum().backward()
+    zd = z.detach().float().cuda()
+    out = torch.empty(n, n_extra + dg).cuda()
+    ops.gate_fwd(zd, n, n_extra, n_gates, mul, l, ca, cg, out)
+    assert _rel(out, want.detach()) < 2e-6
+    gz = torch.empty_like(zd)
+    ops.gate_bwd(zd, cot.float().cuda(), n, n_extra, n_gates, mul, l, ca, cg, gz)
+    assert _rel(gz, z.grad) < 2e-6
+
+
+def test_pool_colsum_mse_adamw():
+    from eqnn_jax_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    B, N, D = 3, 211, 70
+    x = torch.randn(B, N, D, generator=g, dtype=torch.float64)
+    out = torch.empty(B, D).cuda()
+    ops.pool_fwd(x.float().cuda(), B, N, D, 1, out)
+    assert _rel(out, x.mean(1)) < 2e-6
+    gx = torch.empty(B, N, D).cuda()
+    ops.pool_bwd(out, B, N, D, 0, gx)
+    assert torch.equal(gx[:, 5], out)
+    y = torch.empty(D).cuda()
+    ops.colsum(x.float().cuda().reshape(B * N, D), B * N, D, y)
+    assert _rel(y, x.reshape(-1, D).sum(0)) < 5e-6
+    pred, tgt = torch.randn(4, 2, generator=g), torch.randn(4, 2, generator=g)
+    loss, gp = torch.empty(1).cuda(), torch.empty(4, 2).cuda()
+    ops.mse_loss(pred.cuda(), tgt.cuda(), 1.0, loss, gp)
+    assert _rel(loss, ((pred - tgt).double() ** 2).mean().reshape(1)) < 1e-6
+    assert _rel(gp, 2 * (pred - tgt).double() / 8) < 1e-6
+    p = torch.randn(1000, generator=g)
+    gr = torch.randn(1000, generator=g)
+    ref = torch.nn.Parameter(p.clone().double())
+    opt = torch.optim.AdamW([ref], lr=3e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5)
+    pd, m, v = p.clone().cuda(), torch.zeros(1000).cuda(), torch.zeros(1000).cuda()
+    for step in (1, 2, 3):
+        ref.grad = gr.double()
+        opt.step()
+        ops.adamw(pd, gr.cuda(), m, v, 3e-4, 0.9, 0.999, 1e-8, 1e-5, step)
+    assert _rel(pd, ref.detach()) < 1e-6

@@ -1,0 +1,165 @@
+"""Pins for the CPU oracle (no GPU): closed forms, independent CG, equivariance, param counts,
+and the reference's own PBC sanity tests (tests/test_pbcs.py) re-run on the restatement."""
+import dataclasses
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import e3nn_ref as E
+from oracle import graph_ref as G
+from oracle import nequip_ref as NQ
+from oracle import so3
+
+IRREPS_IN = "1o+1o+1x0e"
+
+
+def test_cg_closed_forms():
+    # C(1,1,0) = delta/sqrt3, C(1,1,1) = +eps/sqrt6
+    np.testing.assert_allclose(so3.clebsch_gordan(1, 1, 0)[:, :, 0], np.eye(3) / np.sqrt(3), atol=1e-14)
+    c = so3.clebsch_gordan(1, 1, 1) * np.sqrt(6)
+    eps = np.zeros((3, 3, 3))
+    for i, j, k in [(0, 1, 2), (1, 2, 0), (2, 0, 1)]:
+        eps[i, j, k], eps[j, i, k] = 1, -1
+    np.testing.assert_allclose(c, eps, atol=1e-14)
+    for l1, l2, l3 in [(1, 2, 3), (2, 2, 2), (1, 3, 4), (3, 2, 1)]:
+        assert abs(np.sum(so3.clebsch_gordan(l1, l2, l3) ** 2) - 1) < 1e-13
+
+
+def test_product_cg_matches_sympy_oracle():
+    from eqnn_jax_b200 import so3 as p
+    for l1 in range(4):
+        for l2 in range(5):
+            for l3 in range(abs(l1 - l2), min(l1 + l2, 4) + 1):
+                np.testing.assert_allclose(p.real_cg(l1, l2, l3), so3.clebsch_gordan(l1, l2, l3), atol=1e-13)
+    for l in (2, 3, 4):
+        assert abs(p.sh_recursion_constant(l) - so3._sh_recursion_constant(l)) < 1e-12
+
+
+def test_sh_closed_forms_and_scipy():
+    rng = np.random.default_rng(0)
+    v = rng.normal(size=(50, 3))
+    u = v / np.linalg.norm(v, axis=-1, keepdims=True)
+    x, y, z = u.T
+    Y = so3.spherical_harmonics(3, v, True, "norm")
+    np.testing.assert_allclose(Y[:, 0], 1.0)
+    np.testing.assert_allclose(Y[:, 1:4], u, atol=1e-14)
+    s3 = np.sqrt(3)
+    l2 = np.stack([s3 * x * z, s3 * x * y, y * y - 0.5 * (x * x + z * z), s3 * y * z, s3 / 2 * (z * z - x * x)], -1)
+    np.testing.assert_allclose(Y[:, 4:9], l2, atol=1e-13)
+    # l = 3 against scipy's complex harmonics: e3nn axes (x,y,z) = standard (y,z,x)
+    from scipy.special import sph_harm_y
+    xs, ys, zs = z, x, y                      # standard coordinates of the same points
+    theta, phi = np.arccos(np.clip(zs, -1, 1)), np.arctan2(ys, xs)
+    for l in (1, 2, 3):
+        cols = []
+        for m in range(-l, l + 1):
+            Yc = sph_harm_y(l, abs(m), theta, phi)
+            if m < 0:
+                r = np.sqrt(2) * (-1) ** m * Yc.imag
+            elif m == 0:
+                r = Yc.real
+            else:
+                r = np.sqrt(2) * (-1) ** m * Yc.real
+            cols.append(r * np.sqrt(4 * np.pi / (2 * l + 1)))
+        np.testing.assert_allclose(Y[:, l * l:(l + 1) ** 2], np.stack(cols, -1), atol=1e-12)
+    # zero-vector guard and normalisations
+    Y0 = so3.spherical_harmonics(2, np.zeros((1, 3)), True, "integral")[0]
+    assert Y0[0] == pytest.approx(np.sqrt(1 / (4 * np.pi))) and np.all(Y0[1:] == 0)
+    Yc = so3.spherical_harmonics(2, v, True, "component")
+    np.testing.assert_allclose(Yc[:, 4:9], np.sqrt(5) * Y[:, 4:9], atol=1e-13)
+
+
+def test_tensor_product_equivariance():
+    rng = np.random.default_rng(1)
+    R = G.rotation_matrix(37.0, np.array([1.0, -2.0, 0.5]))
+    for Rm in (R, -R):
+        irx, iry = so3.Irreps("1x0e+2x1o+1x2e"), so3.Irreps.spherical_harmonics(2)
+        x = torch.tensor(rng.normal(size=(4, irx.dim)))
+        y = torch.tensor(rng.normal(size=(4, iry.dim)))
+        Dx, Dy = so3.irreps_rotation_matrix(irx, Rm), so3.irreps_rotation_matrix(iry, Rm)
+        out = E.tensor_product(E.IrrepsArray(irx, x), E.IrrepsArray(iry, y))
+        out_r = E.tensor_product(E.IrrepsArray(irx, x @ torch.tensor(Dx.T)), E.IrrepsArray(iry, y @ torch.tensor(Dy.T)))
+        Do = so3.irreps_rotation_matrix(out.irreps, Rm)
+        np.testing.assert_allclose(out_r.array.numpy(), out.array.numpy() @ Do.T, atol=1e-12)
+
+
+def test_message_irreps_table():
+    # SURVEY.md section 3.2
+    for lmax, want, n_irr in [(1, "3x0e+3x1o+2x1e+2x2e", 10),
+                              (2, "3x0e+5x1o+2x1e+3x2e+2x2o+2x3o", 17),
+                              (3, "3x0e+5x1o+2x1e+5x2e+2x2o+3x3o+2x3e+2x4e", 24)]:
+        m = NQ._message_irreps(so3.Irreps(IRREPS_IN), lmax)
+        assert m == so3.Irreps(want) and m.num_irreps == n_irr
+    assert so3.balanced_irreps(2, 128) == "88x0e+14x1o+8x2e"
+    assert so3.balanced_irreps(3, 128) == "100x0e+10x1o+6x2e+4x3o"
+
+
+def test_param_counts():
+    # hand count of the current models/nequip.py (the notebook's 391,622 predates it)
+    cfg = NQ.NequIPConfig(n_outputs=2, n_radial_basis=64, r_cutoff=0.6)
+    assert NQ.count_params(NQ.init_params(cfg, "1o")) == 388_676
+    cfg2 = NQ.NequIPConfig(d_hidden=128, l_max=2, sphharm_norm="integral", message_passing_steps=4, n_layers=3,
+                           n_outputs=2, n_radial_basis=64, r_cutoff=0.6)
+    assert NQ.count_params(NQ.init_params(cfg2, IRREPS_IN)) == 439_342
+    assert NQ.count_params(NQ.init_params(dataclasses.replace(cfg2, l_max=3), IRREPS_IN)) == 443_062
+
+
+def test_normalize_constants():
+    # SURVEY.md A.6 (grid values)
+    assert E.normalization_constant("gelu") == pytest.approx(0.652059099, abs=2e-8)
+    assert E.normalization_constant("sigmoid") == pytest.approx(0.541644565, abs=2e-8)
+    from eqnn_jax_b200.nequip import normalize_constant
+    assert normalize_constant("gelu") == pytest.approx(E.normalization_constant("gelu"), rel=1e-10)
+    assert normalize_constant("sigmoid") == pytest.approx(E.normalization_constant("sigmoid"), rel=1e-10)
+
+
+def _graph(x, k=5):
+    g = G.build_graph(x, None, k)
+    return g._replace(nodes=torch.tensor(g.nodes, dtype=torch.float64))
+
+
+@pytest.mark.parametrize("task", ["node", "graph"])
+def test_reference_equivariance_tests_on_oracle(task):
+    """tests/test_equivariance.py:337-388 (NequIP node / graph), rtol 0.05, same rotation."""
+    rng = np.random.default_rng(0)
+    x = rng.normal(size=(2, 5, 7)).astype(np.float32)
+    axis = np.array([0, 1 / np.sqrt(2), 1 / np.sqrt(2)])
+    xr = np.stack([G.rotate_representation(x[b], 45.0, axis) for b in range(2)]).astype(np.float32)
+    cfg = NQ.NequIPConfig(message_passing_steps=2, d_hidden=32, n_layers=3, task=task,
+                          irreps_out="1o + 1o + 1x0e" if task == "node" else "1x0e")
+    p = NQ.to_torch(NQ.init_params(cfg, IRREPS_IN, seed=0))
+    o1 = NQ.apply_batched(p, cfg, _graph(x), IRREPS_IN)
+    o2 = NQ.apply_batched(p, cfg, _graph(xr), IRREPS_IN)
+    if task == "node":
+        a, b = o1.nodes.numpy(), o2.nodes.numpy()
+        ar = np.stack([G.rotate_representation(a[i], 45.0, axis) for i in range(2)])
+        assert not np.allclose(a, b, rtol=0.05)
+        assert np.allclose(b, ar, rtol=0.05)
+        np.testing.assert_allclose(b, ar, atol=2e-5 * np.abs(a).max())
+    else:
+        np.testing.assert_allclose(o1.numpy(), o2.numpy(), rtol=1e-4)
+
+
+def test_pbc_sanity_reference_tests():
+    """tests/test_pbcs.py:8-33 and :35-62."""
+    rng = np.random.default_rng(0)
+    pos = rng.uniform(size=(1, 10, 3)).astype(np.float32)
+    g0 = G.build_graph(pos, None, k=10, apply_pbc=None)
+    g1 = G.build_graph(pos, None, k=10, apply_pbc=G.get_apply_pbc())
+    assert g0.edges.mean() > g1.edges.mean()
+    assert g0.edges.max() > np.sqrt(3) / 2 and g1.edges.max() < np.sqrt(3) / 2
+    pos = rng.uniform(size=(1, 100, 3)).astype(np.float32)
+    std = pos.std(axis=(0, 1))
+    spos = (pos - pos.mean(axis=(0, 1))) / std
+    gs = G.build_graph(spos, None, k=10, apply_pbc=G.get_apply_pbc(std))
+    g = G.build_graph(pos, None, k=10, apply_pbc=G.get_apply_pbc())
+    assert gs.edges.mean() * std[0] == pytest.approx(g.edges.mean(), rel=0.05)
+
+
+def test_knn_self_is_first_and_ties_are_stable():
+    x = np.zeros((6, 3), dtype=np.float32)
+    x[3:] = 1.0                      # two clusters of coincident points: all-tie rows
+    s, t, dr = G.nearest_neighbors(x, 3)
+    assert t.reshape(6, 3).tolist() == [[0, 1, 2]] * 3 + [[3, 4, 5]] * 3
+    assert s.tolist() == np.repeat(np.arange(6), 3).tolist()
