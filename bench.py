@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""Benchmark: NequIP forward+backward edges/sec on synthetic Quijote-shaped halo clouds.
+
+Workload (BASELINE.json configs[1]): 5000-node clouds, kNN k=20 with PBC in a 1000 Mpc/h box,
+NequIP l_max=2 (benchmarks/galaxies/train_cosmology.py NEQUIP_PARAMS + n_radial_basis 64,
+r_cutoff 0.6), graph-level regression of 2 targets, MSE loss.  One "step" = one full pass of
+the hot path over a batch of `--graphs-per-gpu` clouds per GPU: kNN graph build, CSR + edge
+geometry, forward, loss, backward, gradient all-reduce (N>1) and the AdamW update.
+
+    python bench.py --gpus N --steps K --warmup W            (torchrun for N>1)
+    python bench.py --impl reference ...                     (CPU reference arm, host cores)
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+# benchmarks/galaxies/dataset.py:16-17 (standardisation constants of the halo catalogue)
+MEAN = np.array([499.91877075908684, 500.0947802559321, 499.964508664328,
+                 -0.0512854365234889, -0.01263126442198149, -0.06458034372345466])
+STD = np.array([288.71092533309235, 288.7525818573022, 288.70234893905575,
+                344.0231468131901, 343.9333673335964, 344.071876710777])
+BOX = 1000.0
+N_NODES, K_NN = 5000, 20
+MODEL_KW = dict(d_hidden=128, l_max=2, sphharm_norm="integral", message_passing_steps=4, n_layers=3,
+                message_passing_agg="mean", readout_agg="mean", mlp_readout_widths=(4, 2, 2), task="graph",
+                n_outputs=2, n_radial_basis=64, r_cutoff=0.6)
+IRREPS_IN = "1o+1o+1x0e"
+
+
+def synth_batch(seed0: int, n_graphs: int):
+    """Quijote-shaped synthetic halos: uniform positions in the box, Gaussian velocities, standardised."""
+    halos = np.empty((n_graphs, N_NODES, 7), dtype=np.float32)
+    for i in range(n_graphs):
+        rng = np.random.default_rng(seed0 + i)
+        pos = rng.uniform(0.0, BOX, size=(N_NODES, 3))
+        vel = rng.normal(0.0, 344.0, size=(N_NODES, 3))
+        halos[i, :, :6] = ((np.concatenate([pos, vel], -1) - MEAN) / STD).astype(np.float32)
+        halos[i, :, 6] = 1.0
+    y = np.random.default_rng(10_000 + seed0).normal(size=(n_graphs, 2)).astype(np.float32)
+    return halos, y
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    which="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, which="fallback")
+
+
+def algorithmic(n_live, d_live, d_in=7, k=K_NN, n_rb=64, H=128, L=3):
+    """per edge and message-passing step."""
+    b_fwd = 8 + 4 * n_live + (12 + 4 * d_in + 4 * d_live) / k
+    b_bwd = 8 + 8 * n_live + (12 + 8 * d_in + 4 * d_live) / k
+    f_fwd = 2 * (n_rb * H + (L - 1) * H * H + H * n_live)
+    f_bwd = 2 * f_fwd - 2 * n_rb * H
+    return b_fwd, b_bwd, f_fwd, f_bwd
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for t, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7 or not (t0 - 0.05 <= t <= t1 + 0.15):
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------
+# CPU reference arm: the oracle restatement on the host cores (JAX is not installable here)
+# --------------------------------------------------------------------------------------
+def cpu_reference_step(halos, y, tree, threads):
+    """One fwd+bwd of the reference algorithm (dense PBC kNN + NequIP + MSE grads) on one cloud batch."""
+    import torch
+    from oracle import graph_ref as G
+    from oracle import nequip_ref as NQ
+    torch.set_num_threads(threads)
+    cfg = NQ.NequIPConfig(**MODEL_KW)
+    t0 = time.perf_counter()
+    g = G.build_graph(halos, None, K_NN, apply_pbc=G.get_apply_pbc((STD[:3] / BOX).astype(np.float32)))
+    p = NQ.to_torch(tree, torch.float32, requires_grad=True)
+    out = NQ.apply_batched(p, cfg, g._replace(nodes=torch.tensor(halos), edges=None), IRREPS_IN)
+    loss = ((out - torch.tensor(y)) ** 2).mean()
+    loss.backward()
+    return time.perf_counter() - t0, float(loss.detach())
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from oracle import nequip_ref as NQ
+    threads = os.cpu_count() or 1
+    tree = NQ.init_params(NQ.NequIPConfig(**MODEL_KW), IRREPS_IN, seed=0)
+    halos, y = synth_batch(0, 1)
+    for _ in range(args.warmup):
+        cpu_reference_step(halos, y, tree, threads)
+    ts = [cpu_reference_step(halos, y, tree, threads)[0] for _ in range(args.steps)]
+    edges = N_NODES * K_NN
+    val = edges * len(ts) / sum(ts)
+    line = {"impl": "reference", "metric": "NequIP fwd+bwd edges/sec", "value": val, "unit": "edges/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(ts) / len(ts),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "NequIP lmax=2, 5000-node kNN-20 PBC clouds, graph regression (cfg-2)",
+                       "graphs_per_step": 1, "edges_per_graph": edges},
+            "cpu_baseline": {"value": val, "unit": "edges/s", "cores": threads, "kind": "port",
+                             "sample": "1 cloud (100k edges) per step: dense PBC kNN + fwd + bwd, torch-CPU fp32 "
+                                       "restatement (JAX/e3nn-jax not installable in this image)"},
+            "e2e": {"value": val, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------
+# B200 arm
+# --------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--graphs-per-gpu", type=int, default=32)   # train_cosmology.py:648 batch_size
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-steps", type=int, default=2)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from eqnn_jax_b200 import _lib, graph_utils as GU, ops
+    from eqnn_jax_b200.nequip import NequIP
+    from eqnn_jax_b200.train import TrainState, train_step, wrap_nodes
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py --impl b200 needs a GPU (no CPU fallback exists for this path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+    B = args.graphs_per_gpu
+    E_step = B * N_NODES * K_NN
+
+    # inputs: two different host batches per rank (pinned), cycled
+    host = []
+    for j in range(2):
+        h, y = synth_batch(1000 * rank + 100 * j, B)
+        host.append((torch.from_numpy(h).pin_memory(), torch.from_numpy(y).pin_memory()))
+    resident = [(h.to(dev), y.to(dev)) for h, y in host]
+    apply_pbc = GU.get_apply_pbc(std=(STD[:3] / BOX).astype(np.float32))   # train_cosmology.py:401
+
+    model = NequIP(**MODEL_KW)
+    g0 = GU.GraphsTuple(nodes=wrap_nodes(resident[0][0]), edges=None, receivers=None, senders=None, globals=None,
+                        n_node=None, n_edge=None)
+    params = model.init(0, g0)                       # same seed on every rank = replicated parameters
+    state = TrainState(model, params)
+    plan = model.plan(IRREPS_IN)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
+        e0.record()
+        for i in range(n):
+            fn(i)
+        e1.record()
+        barrier()
+        t1 = time.time()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), t0, t1
+
+    def step_resident(i):
+        h, y = resident[i % 2]
+        train_step(state, h, y, K_NN, apply_pbc, world)
+
+    hbuf = torch.empty_like(resident[0][0])
+    ybuf = torch.empty_like(resident[0][1])
+    loss_host = torch.empty((1,), dtype=torch.float32).pin_memory()
+
+    def step_e2e(i):
+        h, y = host[i % 2]
+        hbuf.copy_(h, non_blocking=True)
+        ybuf.copy_(y, non_blocking=True)
+        loss = train_step(state, hbuf, ybuf, K_NN, apply_pbc, world)
+        loss_host.copy_(loss, non_blocking=True)
+        torch.cuda.current_stream().synchronize()      # the reference reads the loss every step (:468)
+
+    for i in range(args.warmup):
+        step_resident(i)
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = L.eqnn_launch_count()
+    ms, t0, t1 = timed(step_resident, args.steps)
+    launches = L.eqnn_launch_count() - l0
+    clocks = sampler.stop(t0, t1) if sampler else None
+    for i in range(2):
+        step_e2e(i)
+    ms_e2e, _, _ = timed(step_e2e, args.steps)
+
+    # instrumented pass: per-kernel CUDA-event durations on the launching stream
+    ops.TIMER = ops.KernelTimer()
+    for i in range(args.profile_steps):
+        step_resident(i)
+    prof = ops.TIMER.summary()
+    ops.TIMER = None
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    n_live, d_live = plan.tp.n_live, plan.tp.d_live
+    b_fwd, b_bwd, f_fwd, f_bwd = algorithmic(n_live, d_live)
+    steps_mp = MODEL_KW["message_passing_steps"]
+
+    def per_launch(tag):
+        n, t = prof.get(tag, (0, 0.0))
+        return n, (t / n if n else float("nan"))
+
+    n_f, ms_mf = per_launch("radial_mlp_fwd")
+    n_b, ms_mb = per_launch("radial_mlp_bwd")
+    mlp_ms_step = (n_f * ms_mf + n_b * ms_mb) / args.profile_steps
+    mlp_flops_step = E_step * steps_mp * (f_fwd + f_bwd)
+    mlp_tf = mlp_flops_step / (mlp_ms_step * 1e-3) / 1e12 if mlp_ms_step > 0 else float("nan")
+    _, ms_tf = per_launch("tpconv_fwd")
+    _, ms_tb = per_launch("tpconv_bwd")
+    tp_gbs = E_step * (b_fwd + b_bwd) / ((ms_tf + ms_tb) * 1e-3) / 1e9
+    _, ms_knn = per_launch("knn_pbc")
+    total_prof = sum(t for _, t in prof.values()) / args.profile_steps
+
+    value = world * E_step * args.steps / (ms * 1e-3)
+    e2e = world * E_step * args.steps / (ms_e2e * 1e-3)
+    line = {
+        "metric": "NequIP fwd+bwd edges/sec", "value": value, "unit": "edges/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "NequIP lmax=2, 5000-node kNN-20 PBC clouds, graph regression (cfg-2)",
+                   "graphs_per_gpu": B, "edges_per_gpu_step": E_step, "message_passing_steps": steps_mp,
+                   "step": "kNN graph build + CSR/geometry + forward + MSE + backward + grad all-reduce + AdamW",
+                   "l2": "inputs larger than L2 (per-step working set of several GB)",
+                   "parallelism": f"dp{world}"},
+        "e2e": {"value": e2e, "unit": "edges/s", "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": int(hbuf.numel() * 4 + ybuf.numel() * 4), "d2h_bytes_per_step": 4},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"kernel": "radial MLP GEMMs (fwd+bwd), fp32 FMA on CUDA cores", "bound": "tensor",
+                     "achieved": mlp_tf, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": mlp_tf / pk["tf_sust"],
+                     "traffic": None, "peak_source": f"bf16_tflops_sustained of {pk['which']}",
+                     "launches_per_step": (n_f + n_b) / args.profile_steps, "ms_per_step": mlp_ms_step,
+                     "flops_per_edge_step": f_fwd + f_bwd},
+        "roofline_tpconv": {"kernel": "tpconv_fwd + tpconv_bwd", "bound": "hbm", "achieved": tp_gbs, "peak": pk["hbm"],
+                            "unit": "GB/s", "frac": tp_gbs / pk["hbm"], "traffic": None,
+                            "bytes_per_edge_step": b_fwd + b_bwd, "ms_fwd": ms_tf, "ms_bwd": ms_tb,
+                            "n_live": n_live, "d_live": d_live, "peak_source": f"hbm_gbs of {pk['which']}"},
+        "breakdown_ms_per_step": {k: t / args.profile_steps for k, (n, t) in sorted(prof.items())},
+        "knn": {"ms_per_batch": ms_knn, "pairs_per_s": B * N_NODES * N_NODES / (ms_knn * 1e-3)},
+        "profiled_kernel_ms_per_step": total_prof,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import nequip_ref as NQ
+        threads = os.cpu_count() or 1
+        tree = NQ.init_params(NQ.NequIPConfig(**MODEL_KW), IRREPS_IN, seed=0)
+        h1, y1 = synth_batch(0, 1)
+        cpu_reference_step(h1, y1, tree, threads)               # warm-up
+        ts = [cpu_reference_step(h1, y1, tree, threads)[0] for _ in range(2)]
+        line["cpu_baseline"] = {"value": N_NODES * K_NN * len(ts) / sum(ts), "unit": "edges/s", "cores": threads,
+                                "kind": "port", "sample": "1 cloud (100k edges), dense PBC kNN + fwd + bwd, "
+                                "torch-CPU fp32 restatement of the reference (JAX not installable here)"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

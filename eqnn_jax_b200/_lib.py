@@ -21,6 +21,7 @@ _p, _i, _i64, _f, _d, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_doubl
 SIGNATURES: Dict[str, tuple] = {
     "eqnn_last_error_string": (C.c_char_p, []),
     "eqnn_version": (_i, []),
+    "eqnn_launch_count": (C.c_longlong, []),
     "eqnn_tp_signature_count": (_i, []),
     "eqnn_tp_signature": (C.c_char_p, [_i]),
     "eqnn_tp_lookup": (_i, [C.c_char_p]),

@@ -8,14 +8,16 @@
 #include "../../include/eqnn_b200.h"
 
 int eqnn_fail(int code, const char* msg);  // sets the thread-local error string, returns code
+void eqnn_count_launches(int n);           // process-wide count of kernels enqueued by this library
 
 #define EQNN_CHECK_ARG(cond, msg)                        \
   do {                                                   \
     if (!(cond)) return eqnn_fail(EQNN_ERR_ARG, msg);    \
   } while (0)
 
-#define EQNN_CHECK_LAUNCH()                                              \
+#define EQNN_CHECK_LAUNCH_N(n)                                           \
   do {                                                                   \
+    eqnn_count_launches(n);                                              \
     cudaError_t _e = cudaPeekAtLastError();                              \
     if (_e != cudaSuccess) return eqnn_fail(EQNN_ERR_CUDA, cudaGetErrorString(_e)); \
   } while (0)
@@ -25,6 +27,8 @@ int eqnn_fail(int code, const char* msg);  // sets the thread-local error string
     cudaError_t _e = (call);                                             \
     if (_e != cudaSuccess) return eqnn_fail(EQNN_ERR_CUDA, cudaGetErrorString(_e)); \
   } while (0)
+
+#define EQNN_CHECK_LAUNCH() EQNN_CHECK_LAUNCH_N(1)
 
 static inline cudaStream_t as_stream(eqnn_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }

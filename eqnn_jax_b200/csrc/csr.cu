@@ -195,7 +195,7 @@ extern "C" int eqnn_csr_build(const int32_t* senders, const int32_t* receivers, 
     rowsort_kernel<<<(unsigned)ceil_div64(n_rows * 32, 256), 256, 0, st>>>(rowptr, n_rows, senders, E, N, perm,
                                                                          perm_tmp, src);
   }
-  EQNN_CHECK_LAUNCH();
+  EQNN_CHECK_LAUNCH_N(n_edges > 0 ? 4 : 1);
   return EQNN_OK;
 }
 

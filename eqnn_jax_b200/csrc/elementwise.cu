@@ -294,5 +294,9 @@ int eqnn_fail(int code, const char* msg) {
   snprintf(g_err, sizeof(g_err), "%s", msg ? msg : "unknown error");
   return code;
 }
+#include <atomic>
+static std::atomic<long long> g_launches{0};
+void eqnn_count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+extern "C" long long eqnn_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 extern "C" const char* eqnn_last_error_string(void) { return g_err; }
 extern "C" int eqnn_version(void) { return 100; }

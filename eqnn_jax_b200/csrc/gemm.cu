@@ -346,6 +346,6 @@ extern "C" int eqnn_gemm_f32(int64_t M, int64_t N, int64_t K, float alpha, const
   else if (bn == 32) launch<128, 32, 8, 2>(p, amode, bmode, st);
   else launch<128, 128, 8, 8>(p, amode, bmode, st);
   if (s.ksplit > 1) splitk_reduce_kernel<<<(unsigned)ceil_div64(M * N, 256), 256, 0, st>>>(p);
-  EQNN_CHECK_LAUNCH();
+  EQNN_CHECK_LAUNCH_N(s.ksplit > 1 ? 2 : 1);
   return EQNN_OK;
 }

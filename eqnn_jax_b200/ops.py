@@ -16,6 +16,36 @@ from ._lib import check, lib
 _F32, _I32 = torch.float32, torch.int32
 
 
+class KernelTimer:
+    """Optional CUDA-event timing of individual launches (bench.py's instrumented pass).
+    Events are recorded on torch's current stream, the one every kernel is launched on."""
+
+    def __init__(self):
+        self.records = []   # (tag, start_event, end_event)
+
+    def begin(self):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def end(self, tag, start):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        self.records.append((tag, start, e))
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for tag, a, b in self.records:
+            ms = a.elapsed_time(b)
+            n, t = out.get(tag, (0, 0.0))
+            out[tag] = (n + 1, t + ms)
+        return out
+
+
+TIMER: Optional[KernelTimer] = None
+
+
 def _stream() -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -63,8 +93,11 @@ def knn_pbc(x: torch.Tensor, k: int, cell=None, cell_inv=None, fma: bool = False
     flags = (1 if cell is not None else 0) | (2 if fma else 0)
     c9 = (C.c_float * 9)(*[float(v) for v in cell.reshape(-1)]) if cell is not None else None
     ci9 = (C.c_float * 9)(*[float(v) for v in cell_inv.reshape(-1)]) if cell is not None else None
+    t0 = TIMER.begin() if TIMER else None
     check(lib().eqnn_knn_pbc(_ptr(x), F, c9, ci9, B, N, k, flags, _ptr(senders), _ptr(receivers), _ptr(dr),
                              None, 0, _stream()), "knn_pbc")
+    if TIMER:
+        TIMER.end("knn_pbc", t0)
     return senders, receivers, dr
 
 
@@ -106,14 +139,20 @@ def edge_geom(pos: torch.Tensor, ld_pos: int, n_nodes: int, rowptr, src, n_rb: i
 
 # ---------------------------------------------------------------- interaction block
 def tpconv_fwd(tp_id, rowptr, src, geom, w_t, xt, n_nodes, agg, out, ld_out):
+    t0 = TIMER.begin() if TIMER else None
     check(lib().eqnn_tpconv_fwd(tp_id, _ptr(rowptr), _ptr(src), _ptr(geom), _ptr(w_t), src.numel(), _ptr(xt),
                                 n_nodes, agg, _ptr(out), ld_out, _stream()), "tpconv_fwd")
+    if TIMER:
+        TIMER.end("tpconv_fwd", t0)
 
 
 def tpconv_bwd(tp_id, rowptr, src, perm, geom, w_t, xt, n_nodes, agg, gA, ld_ga, dw_t, dxe):
+    t0 = TIMER.begin() if TIMER else None
     check(lib().eqnn_tpconv_bwd(tp_id, _ptr(rowptr), _ptr(src), _ptr(perm), _ptr(geom), _ptr(w_t), src.numel(),
                                 _ptr(xt), n_nodes, agg, _ptr(gA), ld_ga, _ptr(dw_t), _ptr(dxe), _stream()),
           "tpconv_bwd")
+    if TIMER:
+        TIMER.end("tpconv_bwd", t0)
 
 
 def sender_reduce(dxe, n_nodes, k, dxp, dxt):
@@ -157,7 +196,7 @@ _GEMM_WS = GemmWorkspace()
 
 
 def gemm(M, N, K, alpha, A, sam, sak, B, sbk, sbn, Cm, scm, scn, accumulate=False, pro=0, pro_scale=1.0, epi=0,
-         aux=None, ld_aux=0, epi_scale=1.0, a_off=0, b_off=0, c_off=0, aux_off=0):
+         aux=None, ld_aux=0, epi_scale=1.0, a_off=0, b_off=0, c_off=0, aux_off=0, tag="gemm"):
     """C[m,n] (+)= epi(alpha * sum_k pro(A[m,k]) B[k,n]); element strides; *_off = element offsets."""
     L = lib()
     need = L.eqnn_gemm_workspace_bytes(M, N, K)
@@ -166,8 +205,11 @@ def gemm(M, N, K, alpha, A, sam, sak, B, sbk, sbn, Cm, scm, scn, accumulate=Fals
     pb = C.c_void_p(B.data_ptr() + 4 * b_off)
     pc = C.c_void_p(Cm.data_ptr() + 4 * c_off)
     px = C.c_void_p(0 if aux is None else aux.data_ptr() + 4 * aux_off)
+    t0 = TIMER.begin() if TIMER else None
     check(L.eqnn_gemm_f32(M, N, K, float(alpha), pa, sam, sak, pb, sbk, sbn, pc, scm, scn, 1 if accumulate else 0,
                           pro, float(pro_scale), epi, px, ld_aux, float(epi_scale), ws, ws_bytes, _stream()), "gemm")
+    if TIMER:
+        TIMER.end(tag, t0)
 
 
 def _int_arr(v: Sequence[int]):

@@ -1,0 +1,82 @@
+"""Data-parallel training step for the cosmology benchmark on B200s.
+
+Mirrors ``train_step`` of benchmarks/galaxies/train_cosmology.py:219-255 (reference):
+build the kNN graph of the local batch, forward, MSE loss (:216,236-243), gradients,
+mean of the gradients over devices (``jax.lax.pmean``, :246) and an ``optax.adamw`` update
+with a cosine-decay learning rate (:439-440).  One process per GPU; the only collective is
+one NCCL all-reduce (AVG) of the flat fp32 gradient bucket, with the loss riding in its
+last element (the metric ``pmean`` of :253).  The reference's second, metrics-only forward
+(:249-252) recomputes the same loss value and is not repeated.
+"""
+from __future__ import annotations
+
+import dataclasses
+import math
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from . import graph_utils as GU
+from . import ops
+from .nequip import IrrepsArray, NequIP, NequIPParams
+
+
+def cosine_decay_lr(step: int, init_value: float, decay_steps: int, alpha: float = 0.0) -> float:
+    """optax.cosine_decay_schedule."""
+    c = min(step, decay_steps) / float(decay_steps)
+    return init_value * ((1.0 - alpha) * 0.5 * (1.0 + math.cos(math.pi * c)) + alpha)
+
+
+@dataclasses.dataclass
+class TrainState:
+    model: NequIP
+    params: NequIPParams
+    learning_rate: float = 3e-4          # train_cosmology.py:645
+    weight_decay: float = 1e-5           # :646
+    decay_steps: int = 2000              # :439
+    step: int = 0
+
+    def __post_init__(self):
+        n = self.params.flat.numel()
+        dev = self.params.flat.device
+        # gradient bucket with one extra slot for the loss: a single all-reduce per step
+        self.bucket = torch.zeros((n + 1,), dtype=torch.float32, device=dev)
+        self.params.grad = self.bucket[:n]
+        self.mu = torch.zeros((n,), dtype=torch.float32, device=dev)
+        self.nu = torch.zeros((n,), dtype=torch.float32, device=dev)
+        self._gpred: Optional[torch.Tensor] = None
+
+
+def wrap_nodes(halos: torch.Tensor) -> IrrepsArray:
+    """GraphWrapper of train_cosmology.py:192-199: positions-only clouds are tiled to 1o+1o+1x0e."""
+    if halos.shape[-1] == 3:
+        ones = torch.ones(halos.shape[:2] + (1,), dtype=halos.dtype, device=halos.device)
+        halos = torch.cat([halos, halos, ones], dim=-1)
+    return IrrepsArray("1o + 1o + 1x0e", halos.contiguous())
+
+
+def train_step(state: TrainState, halo_batch: torch.Tensor, y_batch: torch.Tensor, k: int,
+               apply_pbc: Optional[GU.ApplyPBC] = None, world_size: int = 1) -> torch.Tensor:
+    """One optimisation step on this rank's shard; returns the (device) mean loss over all ranks."""
+    model, params = state.model, state.params
+    n = params.flat.numel()
+    graph = GU.build_graph(halo_batch, None, k=k, apply_pbc=apply_pbc, use_edges=True,
+                           n_radial_basis=model.n_radial_basis, r_max=model.r_cutoff)
+    g = GU.GraphsTuple(nodes=wrap_nodes(graph.nodes), edges=None, receivers=graph.receivers,
+                       senders=graph.senders, globals=None, n_node=graph.n_node, n_edge=graph.n_edge)
+    loss_slot = state.bucket[n:]
+
+    def grad_fn(out: torch.Tensor) -> torch.Tensor:
+        if state._gpred is None or state._gpred.shape != out.shape:
+            state._gpred = torch.empty_like(out)
+        ops.mse_loss(out, y_batch, 1.0, loss_slot, state._gpred)
+        return state._gpred
+
+    model.forward_backward(params, g, grad_fn)
+    if world_size > 1:
+        dist.all_reduce(state.bucket, op=dist.ReduceOp.AVG)
+    state.step += 1
+    lr = cosine_decay_lr(state.step - 1, state.learning_rate, state.decay_steps)
+    ops.adamw(params.flat, params.grad, state.mu, state.nu, lr, 0.9, 0.999, 1e-8, state.weight_decay, state.step)
+    return loss_slot

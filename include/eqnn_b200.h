@@ -41,6 +41,7 @@ enum {
 
 const char* eqnn_last_error_string(void);
 int eqnn_version(void);
+long long eqnn_launch_count(void); /* kernels enqueued by this library since load (process-wide) */
 
 /* ---- tensor-product signatures compiled into the library (csrc/gen/tp_gen.cuh) ---- */
 int eqnn_tp_signature_count(void);
