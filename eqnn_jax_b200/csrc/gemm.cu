@@ -305,6 +305,11 @@ void launch(const GemmP& p, int amode, int bmode, cudaStream_t st) {
 
 }  // namespace
 
+int eqnn_tc_rowgemm_try(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t sam, int64_t sak,
+                        const float* B, int64_t sbk, int64_t sbn, float* C, int64_t scm, int64_t scn, int accumulate,
+                        int pro, float pro_scale, int epi, const float* aux, int64_t ld_aux, float epi_scale,
+                        cudaStream_t st);
+
 extern "C" size_t eqnn_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K) {
   const int bn = N <= 16 ? 16 : (N <= 32 ? 32 : 128);
   SplitPlan s = plan_split(M, N, K, 128, bn);
@@ -322,6 +327,13 @@ extern "C" int eqnn_gemm_f32(int64_t M, int64_t N, int64_t K, float alpha, const
   EQNN_CHECK_ARG(epi >= 0 && epi <= 2, "gemm: unknown epilogue");
   EQNN_CHECK_ARG(epi == 0 || aux, "gemm: epilogue needs aux");
   EQNN_CHECK_ARG(ceil_div64(N, 16) <= 65535, "gemm: N too large for grid.y");
+  if (flags & EQNN_GEMM_TF32X3) {
+    const int r = eqnn_tc_rowgemm_try(M, N, K, alpha, A, sam, sak, B, sbk, sbn, C, scm, scn,
+                                      (flags & EQNN_GEMM_ACCUMULATE) ? 1 : 0, pro, pro_scale, epi, aux, ld_aux,
+                                      epi_scale, as_stream(stream));
+    if (r == 1) return EQNN_OK;
+    if (r < 0) return -r;
+  }
   GemmP p;
   p.M = M; p.N = N; p.K = K; p.alpha = alpha;
   p.A = A; p.sam = sam; p.sak = sak;

@@ -334,6 +334,9 @@ class NequIP:
     sphharm_norm: str = "component"
     irreps_out: Optional[Union[str, Irreps]] = None
     residual: bool = True
+    # not a reference field: run the radial-MLP GEMMs on tcgen05 tensor cores with 3xTF32 operand
+    # splitting (fp32-class accuracy); False = fp32 FMA on the CUDA cores
+    tensor_cores: bool = True
 
     def __post_init__(self):
         self._plans: Dict[Irreps, _Plan] = {}
@@ -477,13 +480,13 @@ def _forward(model: NequIP, plan: _Plan, theta: torch.Tensor, pg: PreparedGraph,
         for (koff, fan, hdim) in st["mlp"][:-1]:
             Z = torch.empty((Et, hdim), **f32)
             _mm(Et, hdim, fan, 1.0 / math.sqrt(fan), a, 0, fan, theta, koff, hdim, Z, 0, hdim,
-                pro=pro, pro_scale=plan.inv_c_act, tag="radial_mlp_fwd")
+                pro=pro, pro_scale=plan.inv_c_act, tag="radial_mlp_fwd", tf32x3=model.tensor_cores)
             Zs.append(Z)
             a, pro = Z, 1
         _, fan, _ = st["mlp"][-1]
         w_t = torch.empty((n_live, Et), **f32)
         _mm(Et, n_live, fan, 1.0 / math.sqrt(fan), a, 0, fan, wexp, st["W4L"].off, n_live, w_t, 0, Et, tc=True,
-            pro=pro, pro_scale=plan.inv_c_act, tag="radial_mlp_fwd")
+            pro=pro, pro_scale=plan.inv_c_act, tag="radial_mlp_fwd", tf32x3=model.tensor_cores)
         A = torch.empty((Nt, d_live), **f32)
         ops.tpconv_fwd(tp_id, pg.rowptr, pg.src, pg.geom, w_t, xt, Nt, agg, A, d_live)
         z = torch.empty((Nt, plan.d_z), **f32)
@@ -618,21 +621,21 @@ def _backward(model: NequIP, plan: _Plan, theta: torch.Tensor, pg: PreparedGraph
         a_last, pro_last = (Zs[-1], 1) if nh > 0 else (pg.radial, 0)
         # dW4L = al * act(Z_last)^T @ dw_t^T
         _mm(fan, n_live, Et, al, a_last, 0, fan, dw_t, 0, Et, gwexp, st["W4L"].off, n_live, ta=True, tb=True,
-            pro=pro_last, pro_scale=plan.inv_c_act, tag="radial_mlp_bwd")
+            pro=pro_last, pro_scale=plan.inv_c_act, tag="radial_mlp_bwd", tf32x3=model.tensor_cores)
         if nh > 0:
             dZ = torch.empty((Et, fan), **f32)
             _mm(Et, fan, n_live, al, dw_t, 0, Et, wexp, st["W4L"].off, n_live, dZ, 0, fan, ta=True, tb=True,
-                epi=2, aux=Zs[-1], ld_aux=fan, epi_scale=plan.inv_c_act, tag="radial_mlp_bwd")
+                epi=2, aux=Zs[-1], ld_aux=fan, epi_scale=plan.inv_c_act, tag="radial_mlp_bwd", tf32x3=model.tensor_cores)
             for l in range(nh - 1, -1, -1):
                 koff, fan_l, hdim = mlp[l]
                 al = 1.0 / math.sqrt(fan_l)
                 a_prev, pro_prev = (Zs[l - 1], 1) if l > 0 else (pg.radial, 0)
                 _mm(fan_l, hdim, Et, al, a_prev, 0, fan_l, dZ, 0, hdim, gtheta, koff, hdim, ta=True,
-                    pro=pro_prev, pro_scale=plan.inv_c_act, tag="radial_mlp_bwd")
+                    pro=pro_prev, pro_scale=plan.inv_c_act, tag="radial_mlp_bwd", tf32x3=model.tensor_cores)
                 if l > 0:
                     dZp = torch.empty((Et, fan_l), **f32)
                     _mm(Et, fan_l, hdim, al, dZ, 0, hdim, theta, koff, hdim, dZp, 0, fan_l, tb=True,
-                        epi=2, aux=Zs[l - 1], ld_aux=fan_l, epi_scale=plan.inv_c_act, tag="radial_mlp_bwd")
+                        epi=2, aux=Zs[l - 1], ld_aux=fan_l, epi_scale=plan.inv_c_act, tag="radial_mlp_bwd", tf32x3=model.tensor_cores)
                     dZ = dZp
         # sender side: dxt = sum over each sender's edges, then through W0x
         dxt = torch.empty((Nt, dxp), **f32)

@@ -141,7 +141,10 @@ int eqnn_node_tp_bwd(int tp_id, const float* x, const float* y, const float* gT,
  *   epi: 0 none | 1 += bias[n] (aux = bias) | 2 *= gelu_tanh'(aux[m*ld_aux+n]) * epi_scale
  *   flags: EQNN_GEMM_ACCUMULATE adds to C.  Large-K problems are split over CTAs
  *   through `ws` (eqnn_gemm_workspace_bytes) and reduced in a fixed order.          */
-enum { EQNN_GEMM_ACCUMULATE = 1 };
+/*   EQNN_GEMM_TF32X3: large-M problems with K, N <= 128 run on the tensor cores (tcgen05, TMEM) with every
+ *   operand split into two TF32 halves and three MMAs per product (fp32-class accuracy, error ~2^-21);
+ *   shapes the tensor-core kernels do not cover silently use the fp32 CUDA-core kernel.           */
+enum { EQNN_GEMM_ACCUMULATE = 1, EQNN_GEMM_TF32X3 = 2 };
 size_t eqnn_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K);
 int eqnn_gemm_f32(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t sam, int64_t sak,
                   const float* B, int64_t sbk, int64_t sbn, float* C, int64_t scm, int64_t scn, int flags,

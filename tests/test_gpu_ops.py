@@ -130,3 +130,54 @@ def test_pool_colsum_mse_adamw():
         opt.step()
         ops.adamw(pd, gr.cuda(), m, v, 3e-4, 0.9, 0.999, 1e-8, 1e-5, step)
     assert _rel(pd, ref.detach()) < 1e-6
+
+
+@pytest.mark.parametrize("case", ["fwd64", "fwd128", "dgrad128", "last16", "dgrad_last"])
+@pytest.mark.parametrize("M", [4096, 70001])
+def test_tensor_core_3xtf32_gemm_matches_fp64(case, M):
+    """tcgen05 radial-MLP GEMMs (operands split into two TF32 halves, 3 MMAs per product)."""
+    from eqnn_jax_b200.nequip import _mm
+    g = torch.Generator().manual_seed(M)
+    inv_c = 1.0 / 0.652
+    if case in ("fwd64", "fwd128"):
+        K, N = (64, 128) if case == "fwd64" else (128, 128)
+        pro = 0 if case == "fwd64" else 1
+        A = torch.randn(M, K, generator=g, dtype=torch.float64) * (3.0 if pro else 1.0)
+        B = torch.randn(K, N, generator=g, dtype=torch.float64)
+        want = 0.125 * ((gelu(A) * inv_c if pro else A) @ B)
+        C = torch.full((M, N), float("nan")).cuda()
+        _mm(M, N, K, 0.125, A.float().cuda(), 0, K, B.float().cuda(), 0, N, C, 0, N, pro=pro, pro_scale=inv_c,
+            tf32x3=True)
+        got = C
+    elif case == "dgrad128":
+        K, N = 128, 128
+        dZ = torch.randn(M, K, generator=g, dtype=torch.float64)
+        W = torch.randn(N, K, generator=g, dtype=torch.float64)      # stored [in][out]; B = W^T
+        Zp = torch.randn(M, N, generator=g, dtype=torch.float64) * 2
+        want = 0.1 * (dZ @ W.t()) * gelu_grad(Zp) * inv_c
+        C = torch.full((M, N), float("nan")).cuda()
+        _mm(M, N, K, 0.1, dZ.float().cuda(), 0, K, W.float().cuda(), 0, K, C, 0, N, tb=True, epi=2,
+            aux=Zp.float().cuda(), ld_aux=N, epi_scale=inv_c, tf32x3=True)
+        got = C
+    elif case == "last16":
+        K, N = 128, 11
+        A = torch.randn(M, K, generator=g, dtype=torch.float64) * 2
+        B = torch.randn(K, N, generator=g, dtype=torch.float64)
+        want = (0.09 * (gelu(A) * inv_c) @ B).t()
+        C = torch.full((N, M), float("nan")).cuda()
+        _mm(M, N, K, 0.09, A.float().cuda(), 0, K, B.float().cuda(), 0, N, C, 0, M, tc=True, pro=1, pro_scale=inv_c,
+            tf32x3=True)
+        got = C
+    else:
+        K, N = 11, 128
+        dWt = torch.randn(K, M, generator=g, dtype=torch.float64)     # column-major A
+        W4 = torch.randn(N, K, generator=g, dtype=torch.float64)      # [in=128][live=11]; B = W4^T
+        Zp = torch.randn(M, N, generator=g, dtype=torch.float64) * 2
+        want = 0.09 * (dWt.t() @ W4.t()) * gelu_grad(Zp) * inv_c
+        C = torch.full((M, N), float("nan")).cuda()
+        _mm(M, N, K, 0.09, dWt.float().cuda(), 0, M, W4.float().cuda(), 0, K, C, 0, N, ta=True, tb=True, epi=2,
+            aux=Zp.float().cuda(), ld_aux=N, epi_scale=inv_c, tf32x3=True)
+        got = C
+    torch.cuda.synchronize()
+    assert not torch.isnan(got).any()
+    assert _rel(got, want) < 3e-6
