@@ -36,7 +36,8 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 
 // gelu (tanh approximation, flax.linen.gelu default) written as x * sigmoid(2u),
 // u = sqrt(2/pi) (x + 0.044715 x^3); identical to 0.5 x (1 + tanh u).
-__device__ __forceinline__ float sigmoid_acc(float t) { return 1.0f / (1.0f + __expf(-t)); }
+// ex2.approx + rcp.approx: relative error ~1e-7, well inside the 1e-5 parity budget
+__device__ __forceinline__ float sigmoid_acc(float t) { return __fdividef(1.0f, 1.0f + __expf(-t)); }
 __device__ __forceinline__ float gelu_tanh(float x) {
   const float k0 = 0.7978845608028654f, k1 = 0.044715f;
   float u2 = 2.0f * k0 * (x + k1 * x * x * x);

@@ -310,10 +310,17 @@ int eqnn_tc_rowgemm_try(int64_t M, int64_t N, int64_t K, float alpha, const floa
                         int pro, float pro_scale, int epi, const float* aux, int64_t ld_aux, float epi_scale,
                         cudaStream_t st);
 
+size_t eqnn_tc_wgrad_workspace_bytes(int64_t M, int64_t N, int64_t K);
+int eqnn_tc_wgrad_try(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t sam, int64_t sak,
+                      const float* B, int64_t sbk, int64_t sbn, float* C, int64_t scm, int64_t scn, int accumulate,
+                      int pro, float pro_scale, int epi, void* ws, size_t ws_bytes, cudaStream_t st);
+
 extern "C" size_t eqnn_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K) {
   const int bn = N <= 16 ? 16 : (N <= 32 ? 32 : 128);
   SplitPlan s = plan_split(M, N, K, 128, bn);
-  return s.ksplit > 1 ? (size_t)s.ksplit * M * N * sizeof(float) : 0;
+  const size_t simt = s.ksplit > 1 ? (size_t)s.ksplit * M * N * sizeof(float) : 0;
+  const size_t tcw = eqnn_tc_wgrad_workspace_bytes(M, N, K);
+  return simt > tcw ? simt : tcw;
 }
 
 extern "C" int eqnn_gemm_f32(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t sam,
@@ -333,6 +340,11 @@ extern "C" int eqnn_gemm_f32(int64_t M, int64_t N, int64_t K, float alpha, const
                                       epi_scale, as_stream(stream));
     if (r == 1) return EQNN_OK;
     if (r < 0) return -r;
+    const int w = eqnn_tc_wgrad_try(M, N, K, alpha, A, sam, sak, B, sbk, sbn, C, scm, scn,
+                                    (flags & EQNN_GEMM_ACCUMULATE) ? 1 : 0, pro, pro_scale, epi, ws, ws_bytes,
+                                    as_stream(stream));
+    if (w == 1) return EQNN_OK;
+    if (w < 0) return -w;
   }
   GemmP p;
   p.M = M; p.N = N; p.K = K; p.alpha = alpha;

@@ -85,13 +85,16 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 //   K-major : 8-row groups of 128-byte rows; SBO = bytes between 8-row groups; LBO unused (1)
 //   MN-major: atoms of 8 K-rows x 128 bytes of M/N; LBO = bytes between atoms along M/N,
 //             SBO = bytes between atoms along K
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+//   MN-major fp32/tf32 operands only exist as SWIZZLE_128B_BASE32B (layout type 1): atoms of 4 K-rows x
+//             128 bytes, 32-byte chunks XOR-swizzled with the row index (cute Layout_MN_SW128_32B_Atom).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint32_t layout_type = 2) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((saddr >> 4) & 0x3fff);
   d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3fff) << 16;
   d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3fff) << 32;
   d |= 1ull << 46;   // version = 1 (Blackwell)
-  d |= 2ull << 61;   // layout type SWIZZLE_128B
+  d |= static_cast<uint64_t>(layout_type) << 61;   // 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B
   return d;
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor) for kind::tf32, fp32 accumulate.
@@ -124,6 +127,12 @@ __device__ __forceinline__ void split_tf32(float a, float& hi, float& lo) {
 // byte offset of element (row, 16-byte chunk c) inside a 128-byte-swizzled tile whose rows are 128 bytes
 __device__ __forceinline__ uint32_t sw128(uint32_t row, uint32_t chunk) {
   return (row >> 3) * 1024u + (row & 7u) * 128u + ((chunk ^ (row & 7u)) << 4);
+}
+
+// byte offset of (k-row r, 16-byte chunk c of a 128-byte row) in an MN-major SWIZZLE_128B_BASE32B slab whose
+// 4-row atoms are packed 512 bytes apart along K
+__device__ __forceinline__ uint32_t sw128_base32(uint32_t r, uint32_t c) {
+  return (r >> 2) * 512u + (r & 3u) * 128u + ((((c >> 1) ^ (r & 3u)) << 5) | ((c & 1u) << 4));
 }
 
 }  // namespace tc

@@ -23,9 +23,9 @@ namespace {
 
 using namespace tc;
 
-constexpr int EPI_WARPS = 4, PROD_WARPS = 8;
-constexpr int MMA_WARP = EPI_WARPS;                          // warp 4
-constexpr int TC_THREADS = (EPI_WARPS + 1 + PROD_WARPS) * 32; // 416
+constexpr int EPI_WARPS = 8, PROD_WARPS = 8;   // epilogue warp w: TMEM lane quarter w%4, column half w/4
+constexpr int MMA_WARP = EPI_WARPS;                          // warp 8
+constexpr int TC_THREADS = (EPI_WARPS + 1 + PROD_WARPS) * 32; // 544
 constexpr int PT = PROD_WARPS * 32;                          // 256 producer threads
 constexpr int TILE_M = 128;
 constexpr uint32_t A_HALF = TILE_M * 128;                    // 16 KB: 128 rows x 128 B (32 tf32)
@@ -113,54 +113,73 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_rowgemm_kernel(const RowGemm
 
   if (warp >= MMA_WARP + 1) {
     // =========================== producers ===========================
+    // Two chunks of 128-bit loads are always in flight per thread (register prefetch): the loop is
+    // bound by HBM latency x bytes in flight, not by the split/activation arithmetic.
     const int pt = tid - (MMA_WARP + 1) * 32;
-    uint32_t it = 0;   // global chunk counter -> ring stage / parity
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int64_t m0 = tile * TILE_M;
-      for (int c = 0; c < Cfg::NCH; ++c, ++it) {
-        const int s = it % Cfg::NSTAGE;
-        const uint32_t par = (it / Cfg::NSTAGE) & 1u;
-        float4 v[4];
-        if (AMODE == 0) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int f = pt + i * PT, row = f >> 3, c4 = f & 7;
-            const int64_t m = m0 + row;
-            v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (m < p.M) v[i] = __ldg(reinterpret_cast<const float4*>(p.A + m * p.lda + 32 * c + 4 * c4));
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int f = pt + i * PT, row = f & 127, c4 = f >> 7;   // c4 in 0..7
-            const int64_t m = m0 + row;
-            float t[4] = {0.f, 0.f, 0.f, 0.f};
-            if (m < p.M) {
-#pragma unroll
-              for (int q = 0; q < 4; ++q)
-                if (4 * c4 + q < p.k_valid) t[q] = __ldg(p.A + (int64_t)(4 * c4 + q) * p.lda + m);
-            }
-            v[i] = make_float4(t[0], t[1], t[2], t[3]);
-          }
-        }
-        mbar_wait(a_empty(s), par ^ 1u);
-        const uint32_t st_hi = sA + s * STAGE_BYTES - base, st_lo = st_hi + A_HALF;
+    const uint32_t my_tiles = (blockIdx.x < n_tiles) ? (uint32_t)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0u;
+    const uint32_t total = my_tiles * Cfg::NCH;
+    auto issue = [&](uint32_t g, float4 (&v)[4]) {
+      if (g >= total) return;
+      const int64_t m0 = ((int64_t)blockIdx.x + (int64_t)(g / Cfg::NCH) * gridDim.x) * TILE_M;
+      const int c = g % Cfg::NCH;
+      if (AMODE == 0) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const int f = pt + i * PT;
-          const int row = (AMODE == 0) ? (f >> 3) : (f & 127), c4 = (AMODE == 0) ? (f & 7) : (f >> 7);
-          float x[4] = {v[i].x, v[i].y, v[i].z, v[i].w}, hi[4], lo[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            if (PRO == 1) x[q] = gelu_tanh(x[q]) * p.pro_scale;
-            split_tf32(x[q], hi[q], lo[q]);
-          }
-          const uint32_t off = sw128(row, c4);
-          *reinterpret_cast<float4*>(gen_base + st_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<float4*>(gen_base + st_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+          const int f = pt + i * PT, row = f >> 3, c4 = f & 7;
+          const int64_t m = m0 + row;
+          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (m < p.M) v[i] = __ldg(reinterpret_cast<const float4*>(p.A + m * p.lda + 32 * c + 4 * c4));
         }
-        fence_proxy_async_smem();
-        mbar_arrive(a_full(s));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int f = pt + i * PT, row = f & 127, c4 = f >> 7;   // c4 in 0..7
+          const int64_t m = m0 + row;
+          float t[4] = {0.f, 0.f, 0.f, 0.f};
+          if (m < p.M) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (4 * c4 + q < p.k_valid) t[q] = __ldg(p.A + (int64_t)(4 * c4 + q) * p.lda + m);
+          }
+          v[i] = make_float4(t[0], t[1], t[2], t[3]);
+        }
+      }
+    };
+    auto consume = [&](uint32_t g, float4 (&v)[4]) {
+      const int s = g % Cfg::NSTAGE;
+      const uint32_t par = (g / Cfg::NSTAGE) & 1u;
+      mbar_wait(a_empty(s), par ^ 1u);
+      const uint32_t st_hi = sA + s * STAGE_BYTES - base, st_lo = st_hi + A_HALF;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int f = pt + i * PT;
+        const int row = (AMODE == 0) ? (f >> 3) : (f & 127), c4 = (AMODE == 0) ? (f & 7) : (f >> 7);
+        float x[4] = {v[i].x, v[i].y, v[i].z, v[i].w}, hi[4], lo[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (PRO == 1) x[q] = gelu_tanh(x[q]) * p.pro_scale;
+          split_tf32(x[q], hi[q], lo[q]);
+        }
+        const uint32_t off = sw128(row, c4);
+        *reinterpret_cast<float4*>(gen_base + st_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<float4*>(gen_base + st_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(a_full(s));
+    };
+    float4 v0[4], v1[4], v2[4];
+    issue(0, v0);
+    issue(1, v1);
+    for (uint32_t g = 0; g < total; g += 3) {
+      issue(g + 2, v2);
+      consume(g, v0);
+      if (g + 1 < total) {
+        issue(g + 3, v0);
+        consume(g + 1, v1);
+      }
+      if (g + 2 < total) {
+        issue(g + 4, v1);
+        consume(g + 2, v2);
       }
     }
   } else if (warp == MMA_WARP) {
@@ -195,54 +214,71 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_rowgemm_kernel(const RowGemm
     __syncwarp();
   } else {
     // =========================== epilogue ===========================
-    const int row = warp * 32 + lane;
+    // warp w reads TMEM lanes (w%4)*32.. (hardware rule) and the column half w/4 of the accumulator
+    const int quarter = warp & 3, half = warp >> 2;
+    const int row = quarter * 32 + lane;
     uint32_t tcount = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
       const uint32_t ab = tcount & 1u;
       const int64_t m = tile * TILE_M + row;
-      mbar_wait(t_full(ab), (tcount >> 1) & 1u);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + ab * Cfg::ACC_STRIDE;
-      if (N >= 32) {
-#pragma unroll 1
-        for (int cb = 0; cb < N / 32; ++cb) {
-          float v[32];
-          tmem_ld32(taddr + cb * 32, v);
+      const bool live = m < p.M;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + ab * Cfg::ACC_STRIDE;
+      if (N >= 64) {
+        constexpr int NB16 = (N / 2) / 16;               // 16-column batches per warp
+        float4 ax[4];
+        const int col0 = half * (N / 2);
+        if (EPI == 2 && live) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) ax[j] = __ldg(reinterpret_cast<const float4*>(p.aux + m * p.ld_aux + col0) + j);
+        }
+        mbar_wait(t_full(ab), (tcount >> 1) & 1u);
+        tc_fence_after();
+#pragma unroll
+        for (int cb = 0; cb < NB16; ++cb) {
+          float v[16];
+          tmem_ld16(taddr + col0 + cb * 16, v);
+          float4 an[4];
+          if (EPI == 2 && live && cb + 1 < NB16) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              an[j] = __ldg(reinterpret_cast<const float4*>(p.aux + m * p.ld_aux + col0 + (cb + 1) * 16) + j);
+          }
           tmem_ld_wait();
-          if (cb == N / 32 - 1) {
+          if (cb == NB16 - 1) {
             tc_fence_before();
             mbar_arrive(t_empty(ab));
           }
-          if (m < p.M) {
-            if (CMODE == 0) {
-              float* crow = p.C + m * p.ldc + cb * 32;
-              const float* arow = (EPI == 2) ? p.aux + m * p.ld_aux + cb * 32 : nullptr;
+          if (live) {
+            float* crow = p.C + m * p.ldc + col0 + cb * 16;
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                float o[4] = {p.alpha * v[j], p.alpha * v[j + 1], p.alpha * v[j + 2], p.alpha * v[j + 3]};
-                if (EPI == 2) {
-                  const float4 a = __ldg(reinterpret_cast<const float4*>(arow + j));
-                  o[0] *= gelu_tanh_grad(a.x) * p.epi_scale;
-                  o[1] *= gelu_tanh_grad(a.y) * p.epi_scale;
-                  o[2] *= gelu_tanh_grad(a.z) * p.epi_scale;
-                  o[3] *= gelu_tanh_grad(a.w) * p.epi_scale;
-                }
-                *reinterpret_cast<float4*>(crow + j) = make_float4(o[0], o[1], o[2], o[3]);
+            for (int j = 0; j < 4; ++j) {
+              float o[4] = {p.alpha * v[4 * j], p.alpha * v[4 * j + 1], p.alpha * v[4 * j + 2], p.alpha * v[4 * j + 3]};
+              if (EPI == 2) {
+                o[0] *= gelu_tanh_grad(ax[j].x) * p.epi_scale;
+                o[1] *= gelu_tanh_grad(ax[j].y) * p.epi_scale;
+                o[2] *= gelu_tanh_grad(ax[j].z) * p.epi_scale;
+                o[3] *= gelu_tanh_grad(ax[j].w) * p.epi_scale;
               }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (cb * 32 + j < p.n_valid) p.C[(int64_t)(cb * 32 + j) * p.ldc + m] = p.alpha * v[j];
+              *reinterpret_cast<float4*>(crow + 4 * j) = make_float4(o[0], o[1], o[2], o[3]);
             }
+          }
+          if (EPI == 2 && cb + 1 < NB16) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) ax[j] = an[j];
           }
         }
       } else {
+        // narrow output (N = 16): each warp of the lower half stores; the upper half only keeps the protocol
+        mbar_wait(t_full(ab), (tcount >> 1) & 1u);
+        tc_fence_after();
         float v[16];
-        tmem_ld16(taddr, v);
-        tmem_ld_wait();
+        if (half == 0) {
+          tmem_ld16(taddr, v);
+          tmem_ld_wait();
+        }
         tc_fence_before();
         mbar_arrive(t_empty(ab));
-        if (m < p.M) {
+        if (half == 0 && live) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             if (j < p.n_valid) {
@@ -281,7 +317,307 @@ int launch_rowgemm(const RowGemmP& p, cudaStream_t st) {
   return EQNN_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// tc_wgrad:  dW[Mi x N] = alpha * sum_e pro(X[e, :Mi])^T (x) G[e, :N]      (weight gradients, K = #edges)
+//   X = saved pre-activations (row-major, Mi in {64,128} contiguous), G = upstream gradient, either
+//   row-major [E][128] (MN-major B operand) or column-major [N<=16][E] (K-major B operand).
+//   Each CTA reduces a contiguous slice of edges into one TMEM accumulator and writes a partial
+//   [Mi x N]; a second kernel sums the per-CTA partials in a fixed order (deterministic).
+// ------------------------------------------------------------------------------------------------
+struct WgradP {
+  const float* X;
+  int64_t ldx;
+  const float* G;
+  int64_t ldg;
+  int n_valid;
+  int64_t E;
+  float pro_scale;
+  float* partial;   // [gridDim.x][MI][NPAD]
+};
+
+template <int MI, int N, int GMODE, int PRO>   // GMODE 0: G row-major [E][N]; 1: G column-major [n][E], N = 16
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const WgradP p) {
+  constexpr uint32_t A_HALF_W = 4 * 4096;                       // 4 m-blocks x (4 k-groups x 1 KB): M padded to 128
+  constexpr uint32_t B_HALF_W = (GMODE == 0) ? (N / 32) * 4096 : N * 128;
+  constexpr uint32_t STAGE_W = 2 * A_HALF_W + 2 * B_HALF_W;
+  constexpr int NSTAGE = 3;
+  // The tensor core's fp32 accumulation is not round-to-nearest: its error grows linearly with the number of
+  // accumulated MMAs.  The accumulator is therefore drained every SEG chunks (128 edges) into fp32 registers of
+  // the epilogue warps (IEEE adds) while the MMAs continue into the second TMEM accumulator.
+  constexpr uint32_t SEG = 4;
+  constexpr uint32_t ACC_STRIDE = N < 32 ? 32 : N;
+  constexpr uint32_t TMEM_COLS = 2 * ACC_STRIDE;
+  constexpr int EPI_ACTIVE = (N >= 64) ? EPI_WARPS : 4;     // warps that drain (column halves only when N >= 64)
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = base + NSTAGE * STAGE_W;
+  auto a_full = [&](int s) { return bars + 8u * s; };
+  auto a_empty = [&](int s) { return bars + 8u * (NSTAGE + s); };
+  auto t_full = [&](int b) { return bars + 8u * (2 * NSTAGE + b); };
+  auto t_empty = [&](int b) { return bars + 8u * (2 * NSTAGE + 2 + b); };
+  const uint32_t tmem_slot = bars + 8u * (2 * NSTAGE + 4);
+  uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  const int64_t n_chunks = (p.E + 31) / 32;
+  const int64_t per = (n_chunks + gridDim.x - 1) / gridDim.x;
+  const int64_t c_beg = (int64_t)blockIdx.x * per;
+  const int64_t c_end = (c_beg + per < n_chunks) ? c_beg + per : n_chunks;
+  const uint32_t total = c_end > c_beg ? (uint32_t)(c_end - c_beg) : 0u;
+
+  if (tid == 0) {
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(a_full(s), PT);
+      mbar_init(a_empty(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(t_full(b), 1);
+      mbar_init(t_empty(b), EPI_ACTIVE * 32);
+    }
+    mbar_fence_init();
+  }
+  if (warp == MMA_WARP) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (MI < 128) {   // rows MI..127 of the (padded) A operand are never written by the producers: zero them once
+    for (uint32_t o = tid * 16; o < NSTAGE * STAGE_W; o += TC_THREADS * 16)
+      *reinterpret_cast<float4*>(gen_base + o) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - base));
+
+  if (warp >= MMA_WARP + 1) {
+    // =========================== producers ===========================
+    const int pt = tid - (MMA_WARP + 1) * 32;
+    constexpr int XV = MI / 32;                         // float4 of X per thread per chunk
+    constexpr int GV = (GMODE == 0) ? N / 32 : 1;       // float4 of G per thread per chunk
+    auto issue = [&](uint32_t g, float4 (&xv)[XV], float4 (&gv)[GV]) {
+      if (g >= total) return;
+      const int64_t e0 = (c_beg + g) * 32;
+#pragma unroll
+      for (int i = 0; i < XV; ++i) {
+        const int f = pt + i * PT, row = f / (MI / 4), c4 = f % (MI / 4);
+        const int64_t e = e0 + row;
+        xv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e < p.E) xv[i] = __ldg(reinterpret_cast<const float4*>(p.X + e * p.ldx) + c4);
+      }
+      if (GMODE == 0) {
+#pragma unroll
+        for (int i = 0; i < GV; ++i) {
+          const int f = pt + i * PT, row = f / (N / 4), c4 = f % (N / 4);
+          const int64_t e = e0 + row;
+          gv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (e < p.E) gv[i] = __ldg(reinterpret_cast<const float4*>(p.G + e * p.ldg) + c4);
+        }
+      } else {
+        gv[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int n = pt >> 3, c4 = pt & 7;             // 16 rows x 8 float4 (32 edges)
+        if (pt < 128 && n < p.n_valid) {
+          const int64_t e = e0 + 4 * c4;
+          const float* src = p.G + (int64_t)n * p.ldg + e;
+          if (e + 3 < p.E) gv[0] = __ldg(reinterpret_cast<const float4*>(src));
+          else {
+            float t[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int q = 0; q < 4; ++q) if (e + q < p.E) t[q] = __ldg(src + q);
+            gv[0] = make_float4(t[0], t[1], t[2], t[3]);
+          }
+        }
+      }
+    };
+    auto put = [&](uint32_t off_hi, uint32_t off_lo, float4 v, bool act) {
+      float x[4] = {v.x, v.y, v.z, v.w}, hi[4], lo[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (act) x[q] = gelu_tanh(x[q]) * p.pro_scale;
+        split_tf32(x[q], hi[q], lo[q]);
+      }
+      *reinterpret_cast<float4*>(gen_base + off_hi) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<float4*>(gen_base + off_lo) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    };
+    auto consume = [&](uint32_t g, float4 (&xv)[XV], float4 (&gv)[GV]) {
+      const int s = g % NSTAGE;
+      mbar_wait(a_empty(s), ((g / NSTAGE) & 1u) ^ 1u);
+      const uint32_t sa = s * STAGE_W, sb = sa + 2 * A_HALF_W;
+#pragma unroll
+      for (int i = 0; i < XV; ++i) {
+        const int f = pt + i * PT, row = f / (MI / 4), c4 = f % (MI / 4);
+        // MN-major slab [m-block of 32][32 k-rows]: 4-row atoms, 32-byte-chunk swizzle
+        const uint32_t off = (c4 >> 3) * 4096 + sw128_base32(row, c4 & 7);
+        put(sa + off, sa + A_HALF_W + off, xv[i], PRO == 1);
+      }
+      if (GMODE == 0) {
+#pragma unroll
+        for (int i = 0; i < GV; ++i) {
+          const int f = pt + i * PT, row = f / (N / 4), c4 = f % (N / 4);
+          const uint32_t off = (c4 >> 3) * 4096 + sw128_base32(row, c4 & 7);
+          put(sb + off, sb + B_HALF_W + off, gv[i], false);
+        }
+      } else if (pt < 128) {
+        const int n = pt >> 3, c4 = pt & 7;             // K-major: row n, 32 edges per 128-byte row
+        const uint32_t off = sw128(n, c4);
+        put(sb + off, sb + B_HALF_W + off, gv[0], false);
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(a_full(s));
+    };
+    float4 x0[XV], x1[XV], g0[GV], g1[GV];
+    issue(0, x0, g0);
+    for (uint32_t g = 0; g < total; g += 2) {
+      issue(g + 1, x1, g1);
+      consume(g, x0, g0);
+      if (g + 1 < total) {
+        issue(g + 2, x0, g0);
+        consume(g + 1, x1, g1);
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    if (lane == 0 && total > 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(128, N, 1, GMODE == 0 ? 1 : 0);
+      for (uint32_t g = 0; g < total; ++g) {
+        const int s = g % NSTAGE;
+        const uint32_t sgm = g / SEG, ab = sgm & 1u;
+        if (g % SEG == 0) {
+          mbar_wait(t_empty(ab), ((sgm >> 1) & 1u) ^ 1u);
+          tc_fence_after();
+        }
+        mbar_wait(a_full(s), (g / NSTAGE) & 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + ab * ACC_STRIDE;
+        const uint32_t a_hi = base + s * STAGE_W, a_lo = a_hi + A_HALF_W;
+        const uint32_t b_hi = a_hi + 2 * A_HALF_W, b_lo = b_hi + B_HALF_W;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {               // 8 edges per MMA
+          // MN-major: LBO = bytes between 32-wide M/N blocks, SBO = bytes between 4-row K atoms
+          const uint64_t dah = make_desc(a_hi + kk * 1024, 4096, 512, 1), dal = make_desc(a_lo + kk * 1024, 4096, 512, 1);
+          uint64_t dbh, dbl;
+          if (GMODE == 0) {
+            dbh = make_desc(b_hi + kk * 1024, 4096, 512, 1);
+            dbl = make_desc(b_lo + kk * 1024, 4096, 512, 1);
+          } else {
+            dbh = make_desc(b_hi + kk * 32, 16, 1024);
+            dbl = make_desc(b_lo + kk * 32, 16, 1024);
+          }
+          mma_tf32(d_tmem, dah, dbh, idesc, ((g % SEG) | kk) ? 1u : 0u);
+          mma_tf32(d_tmem, dal, dbh, idesc, 1u);
+          mma_tf32(d_tmem, dah, dbl, idesc, 1u);
+        }
+        mma_commit(a_empty(s));
+        if (g % SEG == SEG - 1 || g == total - 1) mma_commit(t_full(ab));
+      }
+    }
+    __syncwarp();
+  } else if (warp < EPI_ACTIVE) {
+    // ============== epilogue: drain TMEM segments into fp32 registers, then partial[cta] ==============
+    const int quarter = warp & 3, half = warp >> 2;
+    const int row = quarter * 32 + lane;               // = input-feature index i
+    constexpr int CW = (N >= 64) ? N / 2 : N;          // columns owned by this warp
+    const int col0 = half * CW;
+    float acc[CW];
+#pragma unroll
+    for (int j = 0; j < CW; ++j) acc[j] = 0.f;
+    const uint32_t n_seg = (total + SEG - 1) / SEG;
+    for (uint32_t sgm = 0; sgm < n_seg; ++sgm) {
+      const uint32_t ab = sgm & 1u;
+      mbar_wait(t_full(ab), (sgm >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + ab * ACC_STRIDE + col0;
+#pragma unroll
+      for (int cb = 0; cb < CW / 16; ++cb) {
+        float v[16];
+        tmem_ld16(taddr + cb * 16, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[cb * 16 + j] += v[j];
+      }
+      tc_fence_before();
+      mbar_arrive(t_empty(ab));
+    }
+    if (row < MI) {
+      float* out = p.partial + ((size_t)blockIdx.x * MI + row) * N + col0;
+#pragma unroll
+      for (int j = 0; j < CW; j += 4) *reinterpret_cast<float4*>(out + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int n_parts, int MI, int NPAD, int n_valid,
+                                    float alpha, float* __restrict__ out, int64_t ldo) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= MI * n_valid) return;
+  const int r = i / n_valid, c = i - r * n_valid;
+  float s = 0.f;
+  for (int q = 0; q < n_parts; ++q) s += partial[((size_t)q * MI + r) * NPAD + c];
+  out[(int64_t)r * ldo + c] = alpha * s;
+}
+
+template <int MI, int N, int GMODE, int PRO>
+int launch_wgrad(const WgradP& p, int grid, cudaStream_t st) {
+  constexpr uint32_t A_HALF_W = 4 * 4096;
+  constexpr uint32_t B_HALF_W = (GMODE == 0) ? (N / 32) * 4096 : N * 128;
+  constexpr uint32_t SMEM = 3 * (2 * A_HALF_W + 2 * B_HALF_W) + 1024 + 256;
+  auto kern = tc_wgrad_kernel<MI, N, GMODE, PRO>;
+  static bool configured = false;
+  if (!configured) {
+    EQNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    configured = true;
+  }
+  kern<<<grid, TC_THREADS, SMEM, st>>>(p);
+  EQNN_CHECK_LAUNCH();
+  return EQNN_OK;
+}
+
 }  // namespace
+
+size_t eqnn_tc_wgrad_workspace_bytes(int64_t M, int64_t N, int64_t K) {
+  if (K < 4096 || M > 128 || N > 128) return 0;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return (size_t)sms * 128 * 128 * sizeof(float);
+}
+
+// dW[M x N] = alpha * pro(X)^T @ G with the edge dimension as K.  Same return convention as below.
+int eqnn_tc_wgrad_try(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t sam, int64_t sak,
+                      const float* B, int64_t sbk, int64_t sbn, float* C, int64_t scm, int64_t scn, int accumulate,
+                      int pro, float pro_scale, int epi, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (accumulate || epi != 0 || K < 4096 || scn != 1) return 0;
+  if (!(M == 64 || M == 128) || sam != 1 || sak % 4 != 0 || (reinterpret_cast<uintptr_t>(A) & 15)) return 0;
+  if (reinterpret_cast<uintptr_t>(B) & 15) return 0;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t n_chunks = (K + 31) / 32;
+  const int grid = (int)(n_chunks < sms ? n_chunks : sms);
+  WgradP p;
+  p.X = A; p.ldx = sak; p.G = B; p.E = K; p.pro_scale = pro_scale; p.n_valid = (int)N;
+  p.partial = reinterpret_cast<float*>(ws);
+  int rc = 0, npad = 0;
+  if (N == 128 && sbn == 1 && sbk % 4 == 0) {
+    npad = 128; p.ldg = sbk;
+    if (!ws || ws_bytes < (size_t)grid * M * npad * 4) return 0;
+    if (M == 128) rc = pro ? launch_wgrad<128, 128, 0, 1>(p, grid, st) : launch_wgrad<128, 128, 0, 0>(p, grid, st);
+    else rc = pro ? launch_wgrad<64, 128, 0, 1>(p, grid, st) : launch_wgrad<64, 128, 0, 0>(p, grid, st);
+  } else if (N <= 16 && sbk == 1 && sbn % 4 == 0) {
+    npad = 16; p.ldg = sbn;
+    if (!ws || ws_bytes < (size_t)grid * M * npad * 4) return 0;
+    if (M == 128) rc = pro ? launch_wgrad<128, 16, 1, 1>(p, grid, st) : launch_wgrad<128, 16, 1, 0>(p, grid, st);
+    else rc = pro ? launch_wgrad<64, 16, 1, 1>(p, grid, st) : launch_wgrad<64, 16, 1, 0>(p, grid, st);
+  } else {
+    return 0;
+  }
+  if (rc) return -rc;
+  const int tot = (int)(M * N);
+  wgrad_reduce_kernel<<<(tot + 255) / 256, 256, 0, st>>>(p.partial, grid, (int)M, npad, (int)N, alpha, C, scm);
+  eqnn_count_launches(1);
+  return 1;
+}
 
 // Returns 1 if the problem was handled on the tensor cores, 0 if the caller must use the SIMT
 // path, negative EQNN_ERR_* on a launch error.

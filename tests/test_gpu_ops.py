@@ -132,6 +132,38 @@ def test_pool_colsum_mse_adamw():
     assert _rel(pd, ref.detach()) < 1e-6
 
 
+@pytest.mark.parametrize("case", ["w128", "w64", "w128x11", "w64x11"])
+@pytest.mark.parametrize("E", [4096, 70001, 1_000_003])
+def test_tensor_core_3xtf32_weight_gradient(case, E):
+    """tcgen05 weight-gradient kernel: dW = alpha * act(Z)^T @ dZ with the edge axis as K."""
+    from eqnn_jax_b200.nequip import _mm
+    g = torch.Generator().manual_seed(E)
+    inv_c = 1.0 / 0.652
+    Mi = 128 if case.startswith("w128") else 64
+    pro = 1 if Mi == 128 else 0
+    Z = (torch.randn(E, Mi, generator=g) * 1.5).cuda()
+    Zd = Z.double().cpu()
+    act = gelu(Zd) * inv_c if pro else Zd
+    outs = []
+    if case.endswith("x11"):
+        dWt = torch.randn(11, E, generator=g).cuda()
+        want = 0.1 * act.t() @ dWt.double().cpu().t()
+        for _ in range(2):
+            C = torch.full((Mi, 11), float("nan")).cuda()
+            _mm(Mi, 11, E, 0.1, Z, 0, Mi, dWt, 0, E, C, 0, 11, ta=True, tb=True, pro=pro, pro_scale=inv_c, tf32x3=True)
+            outs.append(C)
+    else:
+        dZ = torch.randn(E, 128, generator=g).cuda()
+        want = 0.1 * act.t() @ dZ.double().cpu()
+        for _ in range(2):
+            C = torch.full((Mi, 128), float("nan")).cuda()
+            _mm(Mi, 128, E, 0.1, Z, 0, Mi, dZ, 0, 128, C, 0, 128, ta=True, pro=pro, pro_scale=inv_c, tf32x3=True)
+            outs.append(C)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1]), "weight gradients must be bit-reproducible"
+    assert _rel(outs[0], want) < 3e-6
+
+
 @pytest.mark.parametrize("case", ["fwd64", "fwd128", "dgrad128", "last16", "dgrad_last"])
 @pytest.mark.parametrize("M", [4096, 70001])
 def test_tensor_core_3xtf32_gemm_matches_fp64(case, M):
