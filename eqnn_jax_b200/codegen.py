@@ -22,7 +22,8 @@ _HIDDEN_LIVE = {1: "0e+1o", 2: "0e+1o+2e", 3: "0e+1o+2e+3o"}
 PREBUILT: List[Tuple[str, int, str]] = []
 for _x in ("1o+1o+1x0e", "1o"):
     for _l in (1, 2, 3):
-        PREBUILT.append((_x, _l, _HIDDEN_LIVE[_l]))   # interaction block (nequip.py:52)
+        PREBUILT.append((_x, _l, _HIDDEN_LIVE[_l]))   # interaction block (nequip.py:52), all hidden irreps
+        PREBUILT.append((_x, _l, "0e+1o"))            # interaction block, irreps that survive nequip.py:162
         PREBUILT.append((_x, _l, "0e"))               # invariant read-out (nequip.py:197)
 
 

@@ -119,19 +119,17 @@ __global__ void geom_kernel(const float* __restrict__ pos, int ld, int n_nodes, 
     const float d = __fsqrt_rn(d2);
     const float dn = (d2 == 0.f) ? 1.f : d;  // e3nn guard: divide by 1 at the origin
     geom[p] = make_float4(__fdiv_rn(rx, dn), __fdiv_rn(ry, dn), __fdiv_rn(rz, dn), d);
-    if (radial) {
-      if (n_rb == 0) {
-        radial[p] = d;
-      } else {
-        float* out = radial + (size_t)p * n_rb;
-        for (int j = 1; j <= n_rb; ++j) {
-          // e3nn.bessel: sqrt(2/c) * sin(j*pi/c * x)/x, fp32 rounding points of the reference
-          const float w = __fdiv_rn(__fmul_rn((float)j, PI_F), r_cut);
-          float v;
-          if (d == 0.f) v = w;
-          else v = __fdiv_rn(sinf(__fmul_rn(w, d)), d);
-          out[j - 1] = __fmul_rn(pref, v);
-        }
+    if (radial && n_rb == 0) radial[p] = d;
+  }
+  if (radial && n_rb > 0) {
+    // e3nn.bessel: sqrt(2/c) * sin(j*pi/c * x)/x with the fp32 rounding points of the reference.  Lanes own
+    // basis indices j (coalesced stores of each edge's n_rb values); edge lengths are re-read (L1 hits).
+    for (int p = p0; p < p1; ++p) {
+      const float d = geom[p].w;
+      for (int j = 1 + lane; j <= n_rb; j += 32) {
+        const float w = __fdiv_rn(__fmul_rn((float)j, PI_F), r_cut);
+        const float v = (d == 0.f) ? w : __fdiv_rn(sinf(__fmul_rn(w, d)), d);
+        radial[(size_t)p * n_rb + j - 1] = __fmul_rn(pref, v);
       }
     }
   }

@@ -128,7 +128,12 @@ class _Plan:
         upd = (Irreps([(n_gated, 0, 1)]) + irr).regroup()
         if upd.filter(keep=msg) != upd:
             raise NotImplementedError("hidden irreps absent from the messages are not supported")
-        self.tp = make_tp_plan(irreps_in, cfg.l_max, upd)
+        # Live message columns: irreps that (a) the node Linear reads (they occur in `upd`) and (b) can still
+        # reach the step's output.  Every step re-projects to the input irreps (nequip.py:162), so hidden
+        # irreps that do not occur in the input (e.g. 2e, 3o for "1o+1o+1x0e") are dropped by that Linear:
+        # their messages, gates and weights cannot influence outputs, and their gradients are exact zeros
+        # in the reference as well.
+        self.tp = make_tp_plan(irreps_in, cfg.l_max, upd.filter(keep=irreps_in))
         self.tp_sig = self.tp.signature
         self.upd = upd
         scal = [(m, l, p) for m, l, p in upd if l == 0]
@@ -182,7 +187,8 @@ class _Plan:
                         self._entries.append((st["W4L"].off + r * self.tp.n_live + c.live, koff + r * kh + c.col,
                                               self.shn[c.l2]))
             lp = make_linear_plan(msg, upd)
-            st["W1"] = self._add_linear(f"Linear_{li}", lp, row_map=full_to_live, rows=self.tp.d_live); li += 1
+            st["W1"] = self._add_linear(f"Linear_{li}", lp, row_map=full_to_live, rows=self.tp.d_live,
+                                        skip_dead_rows=True); li += 1
             if cfg.residual:
                 lp = make_linear_plan(irreps_in, upd, force_irreps_out=True)
                 st["W2"] = self._add_linear(f"Linear_{li}", lp); li += 1
@@ -266,12 +272,15 @@ class _Plan:
         self._n_exp += rows * cols
         return d
 
-    def _add_linear(self, name: str, lp: LinearPlan, row_map=None, rows=None, row_scale=None) -> _Dense:
+    def _add_linear(self, name: str, lp: LinearPlan, row_map=None, rows=None, row_scale=None,
+                    skip_dead_rows: bool = False) -> _Dense:
         offs = {pn: self._add_param((name, pn), shp) for pn, shp in lp.param_shapes.items()}
         d = self._new_dense(rows if rows is not None else lp.rows, lp.cols)
         for r, c, pn, flat, sc in lp.entries:
             if row_map is not None:
                 if r not in row_map:
+                    if skip_dead_rows:
+                        continue    # parameter exists (zero gradient), its input is never computed
                     raise AssertionError("Linear reads a message component that is not live")
                 r = row_map[r]
             if row_scale is not None:

@@ -61,10 +61,14 @@ def train_step(state: TrainState, halo_batch: torch.Tensor, y_batch: torch.Tenso
     """One optimisation step on this rank's shard; returns the (device) mean loss over all ranks."""
     model, params = state.model, state.params
     n = params.flat.numel()
-    graph = GU.build_graph(halo_batch, None, k=k, apply_pbc=apply_pbc, use_edges=True,
-                           n_radial_basis=model.n_radial_basis, r_max=model.r_cutoff)
-    g = GU.GraphsTuple(nodes=wrap_nodes(graph.nodes), edges=None, receivers=graph.receivers,
-                       senders=graph.senders, globals=None, n_node=graph.n_node, n_edge=graph.n_edge)
+    # build_graph (train_cosmology.py:226-235) also expands |dr| in a Bessel basis into graph.edges, which the
+    # NequIP wrapper discards (edges=None, :201-208); under jax.jit XLA removes that dead computation, so only
+    # the neighbour search is run here.
+    B, N = halo_batch.shape[:2]
+    senders, receivers, _ = ops.knn_pbc(halo_batch, k, None if apply_pbc is None else apply_pbc.cell,
+                                        None if apply_pbc is None else apply_pbc.cell_inv, want_dr=False)
+    g = GU.GraphsTuple(nodes=wrap_nodes(halo_batch), edges=None, receivers=receivers, senders=senders, globals=None,
+                       n_node=torch.full((B, 1), N, dtype=torch.int32), n_edge=torch.full((B, 1), k, dtype=torch.int32))
     loss_slot = state.bucket[n:]
 
     def grad_fn(out: torch.Tensor) -> torch.Tensor:
