@@ -48,6 +48,26 @@ class TrainState:
         self._gpred: Optional[torch.Tensor] = None
 
 
+def shard_batch(x, rank: int, world_size: int):
+    """``split_batches`` of train_cosmology.py:283-298: rank r takes the r-th contiguous slice of the batch."""
+    if x.shape[0] % world_size != 0:
+        raise ValueError(f"batch of {x.shape[0]} graphs does not split over {world_size} devices")
+    per = x.shape[0] // world_size
+    return x[rank * per:(rank + 1) * per]
+
+
+def allreduce_mean_(bucket: torch.Tensor, world_size: int) -> torch.Tensor:
+    """``jax.lax.pmean(grads, "batch")`` (train_cosmology.py:246,253) on the flat gradient+loss bucket.
+    NCCL averages in the collective; backends without AVG (gloo) sum and scale."""
+    if world_size > 1:
+        if dist.get_backend() == "nccl":
+            dist.all_reduce(bucket, op=dist.ReduceOp.AVG)
+        else:
+            dist.all_reduce(bucket, op=dist.ReduceOp.SUM)
+            bucket.mul_(1.0 / world_size)
+    return bucket
+
+
 def wrap_nodes(halos: torch.Tensor) -> IrrepsArray:
     """GraphWrapper of train_cosmology.py:192-199: positions-only clouds are tiled to 1o+1o+1x0e."""
     if halos.shape[-1] == 3:
@@ -78,8 +98,7 @@ def train_step(state: TrainState, halo_batch: torch.Tensor, y_batch: torch.Tenso
         return state._gpred
 
     model.forward_backward(params, g, grad_fn)
-    if world_size > 1:
-        dist.all_reduce(state.bucket, op=dist.ReduceOp.AVG)
+    allreduce_mean_(state.bucket, world_size)
     state.step += 1
     lr = cosine_decay_lr(state.step - 1, state.learning_rate, state.decay_steps)
     ops.adamw(params.flat, params.grad, state.mu, state.nu, lr, 0.9, 0.999, 1e-8, state.weight_decay, state.step)
