@@ -117,6 +117,19 @@ __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+// 256-bit global accesses (sm_100+): one thread moves a whole 32-byte sector, so a warp that owns one matrix ROW
+// per lane (the tcgen05.ld register layout) still reads/writes complete sectors without a shared-memory transpose.
+__device__ __forceinline__ void ldg256(const float* p, float* v) {
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void stg256(float* p, const float* v) {
+  asm volatile("st.global.v8.f32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};" ::"f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "l"(p)
+               : "memory");
+}
+
 // fp32 -> (hi, lo) with hi exactly representable in tf32 (10 explicit mantissa bits) and lo = a - hi exact.
 // a*b ~= hi_a*hi_b + lo_a*hi_b + hi_a*lo_b with relative error ~2^-21: fp32-class accuracy on the tf32 pipe.
 __device__ __forceinline__ void split_tf32(float a, float& hi, float& lo) {

@@ -46,6 +46,15 @@ struct RowGemmP {
   float alpha, pro_scale, epi_scale;
 };
 
+// ---- row-GEMM thread layout: 8 epilogue warps, 1 MMA warp, 16 producer warps ----
+constexpr int RG_PROD_WARPS = 16;
+constexpr int RG_PT = RG_PROD_WARPS * 32;                          // 512 producer threads
+constexpr int RG_THREADS = (EPI_WARPS + 1 + RG_PROD_WARPS) * 32;   // 800
+constexpr int RG_NSTAGE = 3;
+constexpr int RG_DEPTH = 3;                                        // chunks of loads in flight per producer thread
+constexpr uint32_t STG_ROW = 20;                                   // epilogue staging row stride (floats): 16 + 4 pad
+constexpr uint32_t STG_WARP = 32 * STG_ROW * 4;                    // 2560 B per epilogue warp
+
 template <int K, int N>
 struct RowCfg {
   static constexpr int NCH = (K + 31) / 32;
@@ -53,29 +62,30 @@ struct RowCfg {
   static constexpr uint32_t B_ATOM = N * 128;                 // one 32-wide k slab of B: N rows x 128 B
   static constexpr uint32_t B_HALF = NCH * B_ATOM;
   static constexpr uint32_t B_BYTES = 2 * B_HALF;
-  static constexpr int NSTAGE = (B_BYTES + 3 * STAGE_BYTES + 2048 <= SMEM_LIMIT) ? 3 : 2;
-  static constexpr uint32_t SMEM = B_BYTES + NSTAGE * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr uint32_t STG_BYTES = 0;                   // (epilogue needs no staging: 256-bit row accesses)
+  static constexpr uint32_t SMEM = B_BYTES + RG_NSTAGE * STAGE_BYTES + STG_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr uint32_t ACC_STRIDE = N < 32 ? 32 : N;     // TMEM columns between the two accumulators
   static constexpr uint32_t TMEM_COLS = (2 * ACC_STRIDE <= 64) ? 64 : (2 * ACC_STRIDE <= 128 ? 128 : 256);
+  static_assert(SMEM <= SMEM_LIMIT, "shared memory budget exceeded");
 };
 
 // AMODE 0: A row-major (k contiguous), K % 32 == 0.  AMODE 1: A column-major (m contiguous), K <= 32.
 // PRO 1: A := gelu_tanh(A) * pro_scale.  EPI 2: C *= gelu_tanh'(aux) * epi_scale.
 // CMODE 0: C row-major [M][ldc]; CMODE 1: C column-major [n][ldc] (only the first n_valid columns).
 template <int K, int N, int AMODE, int PRO, int EPI, int CMODE>
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_rowgemm_kernel(const RowGemmP p) {
+__global__ void __launch_bounds__(RG_THREADS, 1) tc_rowgemm_kernel(const RowGemmP p) {
   using Cfg = RowCfg<K, N>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sB_hi = base, sB_lo = base + Cfg::B_HALF;
   const uint32_t sA = base + Cfg::B_BYTES;
-  const uint32_t bars = sA + Cfg::NSTAGE * STAGE_BYTES;
-  // barrier slots (8 bytes each)
+  const uint32_t sStg = sA + RG_NSTAGE * STAGE_BYTES;
+  const uint32_t bars = sStg + Cfg::STG_BYTES;
   auto a_full = [&](int s) { return bars + 8u * s; };
-  auto a_empty = [&](int s) { return bars + 8u * (Cfg::NSTAGE + s); };
-  auto t_full = [&](int b) { return bars + 8u * (2 * Cfg::NSTAGE + b); };
-  auto t_empty = [&](int b) { return bars + 8u * (2 * Cfg::NSTAGE + 2 + b); };
-  const uint32_t tmem_slot = bars + 8u * (2 * Cfg::NSTAGE + 4);
+  auto a_empty = [&](int s) { return bars + 8u * (RG_NSTAGE + s); };
+  auto t_full = [&](int b) { return bars + 8u * (2 * RG_NSTAGE + b); };
+  auto t_empty = [&](int b) { return bars + 8u * (2 * RG_NSTAGE + 2 + b); };
+  const uint32_t tmem_slot = bars + 8u * (2 * RG_NSTAGE + 4);
   uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -83,8 +93,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_rowgemm_kernel(const RowGemm
 
   // ---- one-time setup ----
   if (tid == 0) {
-    for (int s = 0; s < Cfg::NSTAGE; ++s) {
-      mbar_init(a_full(s), PT);
+    for (int s = 0; s < RG_NSTAGE; ++s) {
+      mbar_init(a_full(s), RG_PT);
       mbar_init(a_empty(s), 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -95,7 +105,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_rowgemm_kernel(const RowGemm
   }
   if (warp == MMA_WARP) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
   // resident B: element (n, k) <- B[k*sbk + n*sbn], split hi/lo, K-major 128B-swizzled slabs
-  for (int idx = tid; idx < Cfg::NCH * 32 * N; idx += TC_THREADS) {
+  for (int idx = tid; idx < Cfg::NCH * 32 * N; idx += RG_THREADS) {
     const int k = idx % (Cfg::NCH * 32), n = idx / (Cfg::NCH * 32);
     float v = 0.f;
     if (k < p.k_valid && n < p.n_valid) v = p.B[(int64_t)k * p.sbk + (int64_t)n * p.sbn];
@@ -113,27 +123,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_rowgemm_kernel(const RowGemm
 
   if (warp >= MMA_WARP + 1) {
     // =========================== producers ===========================
-    // Two chunks of 128-bit loads are always in flight per thread (register prefetch): the loop is
-    // bound by HBM latency x bytes in flight, not by the split/activation arithmetic.
+    // RG_DEPTH chunks of 128-bit loads are in flight per thread (register ring): the stream is bound by
+    // HBM latency x bytes in flight (512 threads x 3 x 32 B = 48 KB per SM), not by the split arithmetic.
     const int pt = tid - (MMA_WARP + 1) * 32;
     const uint32_t my_tiles = (blockIdx.x < n_tiles) ? (uint32_t)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0u;
     const uint32_t total = my_tiles * Cfg::NCH;
-    auto issue = [&](uint32_t g, float4 (&v)[4]) {
+    auto issue = [&](uint32_t g, float4 (&v)[2]) {
       if (g >= total) return;
       const int64_t m0 = ((int64_t)blockIdx.x + (int64_t)(g / Cfg::NCH) * gridDim.x) * TILE_M;
       const int c = g % Cfg::NCH;
-      if (AMODE == 0) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int f = pt + i * PT, row = f >> 3, c4 = f & 7;
+      for (int i = 0; i < 2; ++i) {
+        const int f = pt + i * RG_PT;
+        if (AMODE == 0) {
+          const int row = f >> 3, c4 = f & 7;
           const int64_t m = m0 + row;
           v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (m < p.M) v[i] = __ldg(reinterpret_cast<const float4*>(p.A + m * p.lda + 32 * c + 4 * c4));
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int f = pt + i * PT, row = f & 127, c4 = f >> 7;   // c4 in 0..7
+        } else {
+          const int row = f & 127, c4 = f >> 7;   // c4 in 0..7
           const int64_t m = m0 + row;
           float t[4] = {0.f, 0.f, 0.f, 0.f};
           if (m < p.M) {
@@ -145,14 +153,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_rowgemm_kernel(const RowGemm
         }
       }
     };
-    auto consume = [&](uint32_t g, float4 (&v)[4]) {
-      const int s = g % Cfg::NSTAGE;
-      const uint32_t par = (g / Cfg::NSTAGE) & 1u;
+    auto consume = [&](uint32_t g, float4 (&v)[2]) {
+      const int s = g % RG_NSTAGE;
+      const uint32_t par = (g / RG_NSTAGE) & 1u;
       mbar_wait(a_empty(s), par ^ 1u);
       const uint32_t st_hi = sA + s * STAGE_BYTES - base, st_lo = st_hi + A_HALF;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int f = pt + i * PT;
+      for (int i = 0; i < 2; ++i) {
+        const int f = pt + i * RG_PT;
         const int row = (AMODE == 0) ? (f >> 3) : (f & 127), c4 = (AMODE == 0) ? (f & 7) : (f >> 7);
         float x[4] = {v[i].x, v[i].y, v[i].z, v[i].w}, hi[4], lo[4];
 #pragma unroll
@@ -167,20 +175,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_rowgemm_kernel(const RowGemm
       fence_proxy_async_smem();
       mbar_arrive(a_full(s));
     };
-    float4 v0[4], v1[4], v2[4];
+    float4 v0[2], v1[2], v2[2], v3[2];
     issue(0, v0);
     issue(1, v1);
-    for (uint32_t g = 0; g < total; g += 3) {
-      issue(g + 2, v2);
+    issue(2, v2);
+    for (uint32_t g = 0; g < total; g += 4) {
+      issue(g + 3, v3);
       consume(g, v0);
-      if (g + 1 < total) {
-        issue(g + 3, v0);
-        consume(g + 1, v1);
-      }
-      if (g + 2 < total) {
-        issue(g + 4, v1);
-        consume(g + 2, v2);
-      }
+      if (g + 1 < total) { issue(g + 4, v0); consume(g + 1, v1); }
+      if (g + 2 < total) { issue(g + 5, v1); consume(g + 2, v2); }
+      if (g + 3 < total) { issue(g + 6, v2); consume(g + 3, v3); }
     }
   } else if (warp == MMA_WARP) {
     // =========================== MMA issuer ===========================
@@ -193,8 +197,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_rowgemm_kernel(const RowGemm
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + ab * Cfg::ACC_STRIDE;
         for (int c = 0; c < Cfg::NCH; ++c, ++it) {
-          const int s = it % Cfg::NSTAGE;
-          mbar_wait(a_full(s), (it / Cfg::NSTAGE) & 1u);
+          const int s = it % RG_NSTAGE;
+          mbar_wait(a_full(s), (it / RG_NSTAGE) & 1u);
           tc_fence_after();
           const uint32_t a_hi = sA + s * STAGE_BYTES, a_lo = a_hi + A_HALF;
           const uint32_t b_hi = sB_hi + c * Cfg::B_ATOM, b_lo = sB_lo + c * Cfg::B_ATOM;
@@ -214,7 +218,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_rowgemm_kernel(const RowGemm
     __syncwarp();
   } else {
     // =========================== epilogue ===========================
-    // warp w reads TMEM lanes (w%4)*32.. (hardware rule) and the column half w/4 of the accumulator
+    // warp w reads TMEM lanes (w%4)*32.. (hardware rule) and the column half w/4 of the accumulator.
+    // tcgen05.ld hands every thread one ROW; rows are read (aux) and written (C) with 256-bit accesses so
+    // that each lane moves whole 32-byte sectors.
     const int quarter = warp & 3, half = warp >> 2;
     const int row = quarter * 32 + lane;
     uint32_t tcount = 0;
@@ -225,11 +231,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_rowgemm_kernel(const RowGemm
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + ab * Cfg::ACC_STRIDE;
       if (N >= 64) {
         constexpr int NB16 = (N / 2) / 16;               // 16-column batches per warp
-        float4 ax[4];
         const int col0 = half * (N / 2);
+        float ax[16], an[16];
+        const float* arow = (EPI == 2 && live) ? p.aux + m * p.ld_aux + col0 : nullptr;
         if (EPI == 2 && live) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) ax[j] = __ldg(reinterpret_cast<const float4*>(p.aux + m * p.ld_aux + col0) + j);
+          ldg256(arow, ax);
+          ldg256(arow + 8, ax + 8);
         }
         mbar_wait(t_full(ab), (tcount >> 1) & 1u);
         tc_fence_after();
@@ -237,11 +244,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_rowgemm_kernel(const RowGemm
         for (int cb = 0; cb < NB16; ++cb) {
           float v[16];
           tmem_ld16(taddr + col0 + cb * 16, v);
-          float4 an[4];
           if (EPI == 2 && live && cb + 1 < NB16) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              an[j] = __ldg(reinterpret_cast<const float4*>(p.aux + m * p.ld_aux + col0 + (cb + 1) * 16) + j);
+            ldg256(arow + (cb + 1) * 16, an);
+            ldg256(arow + (cb + 1) * 16 + 8, an + 8);
           }
           tmem_ld_wait();
           if (cb == NB16 - 1) {
@@ -249,26 +254,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_rowgemm_kernel(const RowGemm
             mbar_arrive(t_empty(ab));
           }
           if (live) {
-            float* crow = p.C + m * p.ldc + col0 + cb * 16;
+            float o[16];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float o[4] = {p.alpha * v[4 * j], p.alpha * v[4 * j + 1], p.alpha * v[4 * j + 2], p.alpha * v[4 * j + 3]};
-              if (EPI == 2) {
-                o[0] *= gelu_tanh_grad(ax[j].x) * p.epi_scale;
-                o[1] *= gelu_tanh_grad(ax[j].y) * p.epi_scale;
-                o[2] *= gelu_tanh_grad(ax[j].z) * p.epi_scale;
-                o[3] *= gelu_tanh_grad(ax[j].w) * p.epi_scale;
-              }
-              *reinterpret_cast<float4*>(crow + 4 * j) = make_float4(o[0], o[1], o[2], o[3]);
+            for (int j = 0; j < 16; ++j) {
+              o[j] = p.alpha * v[j];
+              if (EPI == 2) o[j] *= gelu_tanh_grad(ax[j]) * p.epi_scale;
             }
+            float* crow = p.C + m * p.ldc + col0 + cb * 16;
+            stg256(crow, o);
+            stg256(crow + 8, o + 8);
           }
           if (EPI == 2 && cb + 1 < NB16) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) ax[j] = an[j];
+            for (int j = 0; j < 16; ++j) ax[j] = an[j];
           }
         }
       } else {
-        // narrow output (N = 16): each warp of the lower half stores; the upper half only keeps the protocol
+        // narrow output (N = 16): the lower column half stores; the upper half only keeps the protocol
         mbar_wait(t_full(ab), (tcount >> 1) & 1u);
         tc_fence_after();
         float v[16];
@@ -312,7 +314,7 @@ int launch_rowgemm(const RowGemmP& p, cudaStream_t st) {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t n_tiles = (p.M + TILE_M - 1) / TILE_M;
   const unsigned grid = (unsigned)(n_tiles < sms ? n_tiles : sms);
-  kern<<<grid, TC_THREADS, Cfg::SMEM, st>>>(p);
+  kern<<<grid, RG_THREADS, Cfg::SMEM, st>>>(p);
   EQNN_CHECK_LAUNCH();
   return EQNN_OK;
 }
@@ -633,8 +635,9 @@ int eqnn_tc_rowgemm_try(int64_t M, int64_t N, int64_t K, float alpha, const floa
   p.alpha = alpha; p.pro_scale = pro_scale; p.epi_scale = epi_scale;
   int rc = 0;
   const bool a_row = (sak == 1 && sam % 4 == 0 && al16(A));
-  const bool c_row = (scn == 1 && scm % 4 == 0 && al16(C));
-  const bool aux_ok = (epi == 0) || (ld_aux % 4 == 0 && al16(aux));
+  auto al32 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 31) == 0; };
+  const bool c_row = (scn == 1 && scm % 8 == 0 && al32(C));          // 256-bit row stores
+  const bool aux_ok = (epi == 0) || (ld_aux % 8 == 0 && al32(aux));  // 256-bit row loads
   if (N == 128 && a_row && c_row && aux_ok && (K == 128 || K == 64)) {
     p.lda = sam; p.ldc = scm;
 #define EQNN_TC_CASE(KK, PR, EP)                                                              \
