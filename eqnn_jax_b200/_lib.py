@@ -44,6 +44,11 @@ SIGNATURES: Dict[str, tuple] = {
                            _p, _i64, _f, _p, _sz, _p]),
     "eqnn_gate_fwd": (_i, [_p, _i64, _i, _i, _i, _p, _p, _f, _f, _p, _p]),
     "eqnn_gate_bwd": (_i, [_p, _p, _i64, _i, _i, _i, _p, _p, _f, _f, _p, _p]),
+    "eqnn_node_update_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "eqnn_node_update_fwd": (_i, [_p, _i, _i, _p, _i, _p, _f, _p, _i, _i, _i, _p, _p, _f, _f, _p, _p, _i, _i64, _p, _p,
+                                  _p, _p]),
+    "eqnn_node_update_bwd": (_i, [_p, _i, _i, _p, _i, _p, _f, _p, _i, _i, _i, _p, _p, _f, _f, _p, _p, _p, _i64, _p, _p,
+                                  _p, _p, _p, _p, _sz, _p]),
     "eqnn_pool_fwd": (_i, [_p, _i, _i, _i, _i, _p, _p]),
     "eqnn_pool_bwd": (_i, [_p, _i, _i, _i, _i, _p, _p]),
     "eqnn_colsum": (_i, [_p, _i64, _i, _p, _p]),

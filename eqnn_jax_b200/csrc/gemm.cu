@@ -248,14 +248,38 @@ gemm_kernel(const GemmP p) {
       }
     }
   } else {
+    // fast path: row-major C, 16-byte aligned rows, plain or accumulate epilogue -> 128-bit stores
+    const bool vec = (TN % 4 == 0) && p.scn == 1 && (p.scm % 4 == 0) && p.epi == 0 &&
+                     ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
 #pragma unroll
     for (int i = 0; i < TM; ++i) {
       const int64_t m = m0 + ty * TM + i;
       if (m >= p.M) continue;
+      if (TN % 4 == 0 && vec) {
 #pragma unroll
-      for (int j = 0; j < TN; ++j) {
-        const int64_t n = n0 + col_of(j);
-        if (n < p.N) store_out(p, m, n, p.alpha * acc[i][j]);
+        for (int j = 0; j < TN; j += 4) {
+          const int64_t n = n0 + col_of(j);
+          if (n + 3 < p.N) {
+            float4* c = reinterpret_cast<float4*>(p.C + m * p.scm + n);
+            float4 o = make_float4(p.alpha * acc[i][j], p.alpha * acc[i][j + 1], p.alpha * acc[i][j + 2],
+                                   p.alpha * acc[i][j + 3]);
+            if (p.accumulate) {
+              const float4 q = *c;
+              o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
+            }
+            *c = o;
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (n + q < p.N) store_out(p, m, n + q, p.alpha * acc[i][j + q]);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+          const int64_t n = n0 + col_of(j);
+          if (n < p.N) store_out(p, m, n, p.alpha * acc[i][j]);
+        }
       }
     }
   }

@@ -133,7 +133,8 @@ class _Plan:
         # irreps that do not occur in the input (e.g. 2e, 3o for "1o+1o+1x0e") are dropped by that Linear:
         # their messages, gates and weights cannot influence outputs, and their gradients are exact zeros
         # in the reference as well.
-        self.tp = make_tp_plan(irreps_in, cfg.l_max, upd.filter(keep=irreps_in))
+        # (0e is always kept: scalar messages feed the gate scalars of the surviving l>0 irreps.)
+        self.tp = make_tp_plan(irreps_in, cfg.l_max, upd.filter(keep=irreps_in + Irreps("1x0e")))
         self.tp_sig = self.tp.signature
         self.upd = upd
         scal = [(m, l, p) for m, l, p in upd if l == 0]
@@ -141,12 +142,39 @@ class _Plan:
         if any(p == -1 for _, _, p in scal) or len(scal) != 1:
             raise NotImplementedError("odd scalars are not on the reference's path")
         n_s = scal[0][0]
-        self.n_gates = sum(m for m, _, _ in gated)
-        self.n_extra = n_s - self.n_gates
-        self.gate_mul = [m for m, _, _ in gated]
-        self.gate_l = [l for _, l, _ in gated]
-        self.g_irreps = Irreps(([(self.n_extra, 0, 1)] if self.n_extra else []) + gated)
-        self.d_z, self.d_g, self.d_in = upd.dim, self.g_irreps.dim, D
+        n_gates_full = sum(m for m, _, _ in gated)
+        self.n_extra = n_s - n_gates_full
+        self.g_irreps = Irreps(([(self.n_extra, 0, 1)] if self.n_extra else []) + gated)   # reference layout
+        # Node update restricted to the live irreps (same argument as for the messages): gated chunks whose
+        # irrep does not occur in the input are dropped together with their gate scalars.  zmap / gmap send a
+        # component index of the reference's z / gate-output layout to the compact layout (or -1).
+        live_types = {(l, p) for _, l, p in irreps_in}
+        z_full, g_full = upd.dim, self.g_irreps.dim
+        self.zmap, self.gmap = [-1] * z_full, [-1] * g_full
+        for c in range(self.n_extra):
+            self.zmap[c] = self.gmap[c] = c
+        self.gate_mul, self.gate_l = [], []
+        zg, zc, gate_pos, comp_pos = self.n_extra, 0, [], []
+        n_gates_live = sum(m for m, l, pp in gated if (l, pp) in live_types)
+        goff_full, coff_full, glive, clive = 0, 0, 0, 0
+        for m, l, pp in gated:
+            d = 2 * l + 1
+            if (l, pp) in live_types:
+                self.gate_mul.append(m)
+                self.gate_l.append(l)
+                for u in range(m):
+                    self.zmap[self.n_extra + goff_full + u] = self.n_extra + glive + u
+                for q in range(m * d):
+                    self.zmap[self.n_extra + n_gates_full + coff_full + q] = self.n_extra + n_gates_live + clive + q
+                    self.gmap[self.n_extra + coff_full + q] = self.n_extra + clive + q
+                glive += m
+                clive += m * d
+            goff_full += m
+            coff_full += m * d
+        self.n_gates = n_gates_live
+        self.d_z = self.n_extra + n_gates_live + clive
+        self.d_g = self.n_extra + clive
+        self.d_in = D
         self.n_rad_in = cfg.n_radial_basis if cfg.n_radial_basis > 0 else 1
         self.shn = [so3.sh_norm_factor(l, cfg.sphharm_norm) for l in range(cfg.l_max + 1)]
         self.inv_c_act = 1.0 / normalize_constant("gelu")
@@ -187,13 +215,15 @@ class _Plan:
                         self._entries.append((st["W4L"].off + r * self.tp.n_live + c.live, koff + r * kh + c.col,
                                               self.shn[c.l2]))
             lp = make_linear_plan(msg, upd)
+            zcols = {c: v for c, v in enumerate(self.zmap) if v >= 0}
             st["W1"] = self._add_linear(f"Linear_{li}", lp, row_map=full_to_live, rows=self.tp.d_live,
-                                        skip_dead_rows=True); li += 1
+                                        skip_dead=True, col_map=zcols, cols=self.d_z); li += 1
             if cfg.residual:
                 lp = make_linear_plan(irreps_in, upd, force_irreps_out=True)
-                st["W2"] = self._add_linear(f"Linear_{li}", lp); li += 1
+                st["W2"] = self._add_linear(f"Linear_{li}", lp, skip_dead=True, col_map=zcols, cols=self.d_z); li += 1
             lp = make_linear_plan(self.g_irreps, irreps_in)
-            st["W3"] = self._add_linear(f"Linear_{li}", lp); li += 1
+            st["W3"] = self._add_linear(f"Linear_{li}", lp, row_map={r: v for r, v in enumerate(self.gmap) if v >= 0},
+                                        rows=self.d_g, skip_dead=True); li += 1
             self.steps.append(st)
 
         self.irreps_out = Irreps(cfg.irreps_out) if cfg.irreps_out is not None else irreps_in
@@ -273,19 +303,29 @@ class _Plan:
         return d
 
     def _add_linear(self, name: str, lp: LinearPlan, row_map=None, rows=None, row_scale=None,
-                    skip_dead_rows: bool = False) -> _Dense:
+                    skip_dead: bool = False, col_map=None, cols=None) -> _Dense:
+        """Registers the Linear's Flax parameters and its dense lowering.  row_map / col_map re-index the dense
+        matrix into a compact (live-only) layout; with skip_dead, entries that touch a dropped row or column are
+        omitted: the parameter still exists (and receives an exact zero gradient), its term is never computed."""
         offs = {pn: self._add_param((name, pn), shp) for pn, shp in lp.param_shapes.items()}
-        d = self._new_dense(rows if rows is not None else lp.rows, lp.cols)
+        ncols = cols if cols is not None else lp.cols
+        d = self._new_dense(rows if rows is not None else lp.rows, ncols)
         for r, c, pn, flat, sc in lp.entries:
             if row_map is not None:
                 if r not in row_map:
-                    if skip_dead_rows:
-                        continue    # parameter exists (zero gradient), its input is never computed
-                    raise AssertionError("Linear reads a message component that is not live")
+                    if skip_dead:
+                        continue
+                    raise AssertionError("Linear reads a component that is not live")
                 r = row_map[r]
+            if col_map is not None:
+                if c not in col_map:
+                    if skip_dead:
+                        continue
+                    raise AssertionError("Linear writes a component that is not live")
+                c = col_map[c]
             if row_scale is not None:
                 sc = sc * row_scale[r]
-            self._entries.append((d.off + r * lp.cols + c, offs[pn] + flat, sc))
+            self._entries.append((d.off + r * ncols + c, offs[pn] + flat, sc))
         return d
 
     def device_tables(self, device) -> Dict[str, torch.Tensor]:
@@ -346,6 +386,8 @@ class NequIP:
     # not a reference field: run the radial-MLP GEMMs on tcgen05 tensor cores with 3xTF32 operand
     # splitting (fp32-class accuracy); False = fp32 FMA on the CUDA cores
     tensor_cores: bool = True
+    # not a reference field: Linear + self-connection + gate + re-projection as one fused N-row kernel
+    fuse_node_update: bool = True
 
     def __post_init__(self):
         self._plans: Dict[Irreps, _Plan] = {}
@@ -499,13 +541,20 @@ def _forward(model: NequIP, plan: _Plan, theta: torch.Tensor, pg: PreparedGraph,
         A = torch.empty((Nt, d_live), **f32)
         ops.tpconv_fwd(tp_id, pg.rowptr, pg.src, pg.geom, w_t, xt, Nt, agg, A, d_live)
         z = torch.empty((Nt, plan.d_z), **f32)
-        _mm(Nt, plan.d_z, d_live, inv_sqrt_k, A, 0, d_live, wexp, st["W1"].off, plan.d_z, z, 0, plan.d_z)
-        if model.residual:
-            _mm(Nt, plan.d_z, D, 1.0, h, 0, D, wexp, st["W2"].off, plan.d_z, z, 0, plan.d_z, accumulate=True)
-        g = torch.empty((Nt, plan.d_g), **f32)
-        ops.gate_fwd(z, Nt, plan.n_extra, plan.n_gates, plan.gate_mul, plan.gate_l, plan.inv_c_act, plan.inv_c_gate, g)
         hn = torch.empty((Nt, D), **f32)
-        _mm(Nt, D, plan.d_g, 1.0, g, 0, plan.d_g, wexp, st["W3"].off, D, hn, 0, D)
+        g = None
+        if model.fuse_node_update:
+            ops.node_update_fwd(A, d_live, d_live, h, D, wexp, st["W1"].off, inv_sqrt_k,
+                                st["W2"].off if model.residual else None, plan.n_extra, plan.n_gates, plan.gate_mul,
+                                plan.gate_l, plan.inv_c_act, plan.inv_c_gate, st["W3"].off, Nt, z, hn)
+        else:
+            _mm(Nt, plan.d_z, d_live, inv_sqrt_k, A, 0, d_live, wexp, st["W1"].off, plan.d_z, z, 0, plan.d_z)
+            if model.residual:
+                _mm(Nt, plan.d_z, D, 1.0, h, 0, D, wexp, st["W2"].off, plan.d_z, z, 0, plan.d_z, accumulate=True)
+            g = torch.empty((Nt, plan.d_g), **f32)
+            ops.gate_fwd(z, Nt, plan.n_extra, plan.n_gates, plan.gate_mul, plan.gate_l, plan.inv_c_act,
+                         plan.inv_c_gate, g)
+            _mm(Nt, D, plan.d_g, 1.0, g, 0, plan.d_g, wexp, st["W3"].off, D, hn, 0, D)
         if save:
             saved["steps"].append(dict(h=h, xt=xt, Zs=Zs, w_t=w_t, A=A, z=z, g=g))
         h = hn
@@ -604,22 +653,29 @@ def _backward(model: NequIP, plan: _Plan, theta: torch.Tensor, pg: PreparedGraph
     for st, sv in zip(reversed(plan.steps), reversed(saved["steps"])):
         h, xt, Zs, w_t, A, z, g = sv["h"], sv["xt"], sv["Zs"], sv["w_t"], sv["A"], sv["z"], sv["g"]
         # h' = g @ W3
-        dg = torch.empty((Nt, plan.d_g), **f32)
-        _mm(Nt, plan.d_g, D, 1.0, dh, 0, D, wexp, st["W3"].off, D, dg, 0, plan.d_g, tb=True)
-        _mm(plan.d_g, D, Nt, 1.0, g, 0, plan.d_g, dh, 0, D, gwexp, st["W3"].off, D, ta=True)
-        dz = torch.empty((Nt, plan.d_z), **f32)
-        ops.gate_bwd(z, dg, Nt, plan.n_extra, plan.n_gates, plan.gate_mul, plan.gate_l, plan.inv_c_act,
-                     plan.inv_c_gate, dz)
-        # z = A @ W1 / sqrt(k) + h @ W2
         dA = torch.empty((Nt, d_live), **f32)
-        _mm(Nt, d_live, plan.d_z, inv_sqrt_k, dz, 0, plan.d_z, wexp, st["W1"].off, plan.d_z, dA, 0, d_live, tb=True)
-        _mm(d_live, plan.d_z, Nt, inv_sqrt_k, A, 0, d_live, dz, 0, plan.d_z, gwexp, st["W1"].off, plan.d_z, ta=True)
         dh_prev = torch.empty((Nt, D), **f32)
-        if model.residual:
-            _mm(Nt, D, plan.d_z, 1.0, dz, 0, plan.d_z, wexp, st["W2"].off, plan.d_z, dh_prev, 0, D, tb=True)
-            _mm(D, plan.d_z, Nt, 1.0, h, 0, D, dz, 0, plan.d_z, gwexp, st["W2"].off, plan.d_z, ta=True)
+        if model.fuse_node_update:
+            ops.node_update_bwd(A, d_live, d_live, h, D, wexp, st["W1"].off, inv_sqrt_k,
+                                st["W2"].off if model.residual else None, plan.n_extra, plan.n_gates, plan.gate_mul,
+                                plan.gate_l, plan.inv_c_act, plan.inv_c_gate, st["W3"].off, z, dh, Nt, dA, dh_prev,
+                                gwexp)
         else:
-            dh_prev.zero_()
+            # h' = g @ W3
+            dg = torch.empty((Nt, plan.d_g), **f32)
+            _mm(Nt, plan.d_g, D, 1.0, dh, 0, D, wexp, st["W3"].off, D, dg, 0, plan.d_g, tb=True)
+            _mm(plan.d_g, D, Nt, 1.0, g, 0, plan.d_g, dh, 0, D, gwexp, st["W3"].off, D, ta=True)
+            dz = torch.empty((Nt, plan.d_z), **f32)
+            ops.gate_bwd(z, dg, Nt, plan.n_extra, plan.n_gates, plan.gate_mul, plan.gate_l, plan.inv_c_act,
+                         plan.inv_c_gate, dz)
+            # z = A @ W1 / sqrt(k) + h @ W2
+            _mm(Nt, d_live, plan.d_z, inv_sqrt_k, dz, 0, plan.d_z, wexp, st["W1"].off, plan.d_z, dA, 0, d_live, tb=True)
+            _mm(d_live, plan.d_z, Nt, inv_sqrt_k, A, 0, d_live, dz, 0, plan.d_z, gwexp, st["W1"].off, plan.d_z, ta=True)
+            if model.residual:
+                _mm(Nt, D, plan.d_z, 1.0, dz, 0, plan.d_z, wexp, st["W2"].off, plan.d_z, dh_prev, 0, D, tb=True)
+                _mm(D, plan.d_z, Nt, 1.0, h, 0, D, dz, 0, plan.d_z, gwexp, st["W2"].off, plan.d_z, ta=True)
+            else:
+                dh_prev.zero_()
         # interaction block
         ops.tpconv_bwd(tp_id, pg.rowptr, pg.src, pg.perm, pg.geom, w_t, xt, Nt, agg, dA, d_live, dw_t, dxe)
         # radial MLP backward

@@ -226,6 +226,40 @@ def gate_bwd(z, gout, n, n_extra, n_gates, mul, l, inv_c_act, inv_c_gate, gz):
                               inv_c_act, inv_c_gate, _ptr(gz), _stream()), "gate_bwd")
 
 
+_NODE_WS = GemmWorkspace()
+
+
+def _off(t, off):
+    return C.c_void_p(0) if off is None else C.c_void_p(t.data_ptr() + 4 * off)
+
+
+def node_update_fwd(A, ld_a, d_a, h, d_h, wexp, w1_off, alpha1, w2_off, n_extra, n_gates, mul, l, inv_c_act,
+                    inv_c_gate, w3_off, n, z, h_out, w0n_off=None, dxp=0, xt_out=None):
+    """Fused z = alpha1*A@W1 + h@W2; h' = gate(z)@W3 (weights are slices of the expanded-weight buffer)."""
+    t0 = TIMER.begin() if TIMER else None
+    check(lib().eqnn_node_update_fwd(_ptr(A), ld_a, d_a, _ptr(h), d_h, _off(wexp, w1_off), float(alpha1),
+                                     _off(wexp, w2_off), n_extra, n_gates, len(mul), _int_arr(mul), _int_arr(l),
+                                     inv_c_act, inv_c_gate, _off(wexp, w3_off), _off(wexp, w0n_off), dxp, n, _ptr(z),
+                                     _ptr(h_out), _ptr(xt_out), _stream()), "node_update_fwd")
+    if TIMER:
+        TIMER.end("node_update_fwd", t0)
+
+
+def node_update_bwd(A, ld_a, d_a, h, d_h, wexp, w1_off, alpha1, w2_off, n_extra, n_gates, mul, l, inv_c_act,
+                    inv_c_gate, w3_off, z, dh_out, n, dA, dh_in, gwexp):
+    d_gated = sum(m * (2 * ll + 1) for m, ll in zip(mul, l))
+    need = lib().eqnn_node_update_workspace_bytes(d_a, d_h, n_extra + n_gates + d_gated, n_extra + d_gated)
+    ws, ws_bytes = _NODE_WS.get(need, z.device)
+    t0 = TIMER.begin() if TIMER else None
+    check(lib().eqnn_node_update_bwd(_ptr(A), ld_a, d_a, _ptr(h), d_h, _off(wexp, w1_off), float(alpha1),
+                                     _off(wexp, w2_off), n_extra, n_gates, len(mul), _int_arr(mul), _int_arr(l),
+                                     inv_c_act, inv_c_gate, _off(wexp, w3_off), _ptr(z), _ptr(dh_out), n, _ptr(dA),
+                                     _ptr(dh_in), _off(gwexp, w1_off), _off(gwexp, w2_off), _off(gwexp, w3_off), ws,
+                                     ws_bytes, _stream()), "node_update_bwd")
+    if TIMER:
+        TIMER.end("node_update_bwd", t0)
+
+
 def pool_fwd(x, B, N, D, mode, out):
     check(lib().eqnn_pool_fwd(_ptr(x), B, N, D, mode, _ptr(out), _stream()), "pool_fwd")
 

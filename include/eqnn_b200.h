@@ -161,6 +161,24 @@ int eqnn_gate_bwd(const float* z, const float* gout, int64_t n, int n_extra, int
                   const int* mul, const int* l, float inv_c_act, float inv_c_gate, float* gz,
                   eqnn_stream_t stream);
 
+/* Fused node update of one interaction step (models/nequip.py:80-90 and :162):
+ *     z = alpha1 * A @ W1 + h @ W2 ;  h_out = gate(z) @ W3 ;  xt_out = h_out @ W0n (optional, next step's :43)
+ *   A [n, ld_a] (first d_a columns), h [n, d_h]; W1 [d_a, d_z], W2 [d_h, d_z] or NULL, W3 [d_g, d_h],
+ *   W0n [d_h, dxp] or NULL: dense lowerings of the irreps Linear layers;  gate layout and constants as in
+ *   eqnn_gate_fwd;  z [n, d_z] is saved for the backward pass, the gate output never leaves the SM.
+ * Backward: dA [n, d_a], dh_in [n, d_h] (self-connection part), dW1/dW2/dW3 (dense, overwritten; dW2 may be
+ * NULL iff W2 is); weight gradients are reduced per thread -> per CTA -> fixed-order sum (deterministic).     */
+size_t eqnn_node_update_workspace_bytes(int d_a, int d_h, int d_z, int d_g);
+int eqnn_node_update_fwd(const float* A, int ld_a, int d_a, const float* h, int d_h, const float* W1, float alpha1,
+                         const float* W2, int n_extra, int n_gates, int n_chunks, const int* mul, const int* l,
+                         float inv_c_act, float inv_c_gate, const float* W3, const float* W0n, int dxp, int64_t n,
+                         float* z, float* h_out, float* xt_out, eqnn_stream_t stream);
+int eqnn_node_update_bwd(const float* A, int ld_a, int d_a, const float* h, int d_h, const float* W1, float alpha1,
+                         const float* W2, int n_extra, int n_gates, int n_chunks, const int* mul, const int* l,
+                         float inv_c_act, float inv_c_gate, const float* W3, const float* z, const float* dh_out,
+                         int64_t n, float* dA, float* dh_in, float* dW1, float* dW2, float* dW3, void* ws,
+                         size_t ws_bytes, eqnn_stream_t stream);
+
 /* out[b, :] = reduce_n x[b, n, :]   (mode 0 sum, 1 mean; nequip.py:196-199) and its backward */
 int eqnn_pool_fwd(const float* x, int B, int N, int D, int mode, float* out, eqnn_stream_t stream);
 int eqnn_pool_bwd(const float* gout, int B, int N, int D, int mode, float* gx, eqnn_stream_t stream);
