@@ -49,6 +49,12 @@ SIGNATURES: Dict[str, tuple] = {
                                   _p, _p]),
     "eqnn_node_update_bwd": (_i, [_p, _i, _i, _p, _i, _p, _f, _p, _i, _i, _i, _p, _p, _f, _f, _p, _p, _p, _i64, _p, _p,
                                   _p, _p, _p, _p, _sz, _p]),
+    "eqnn_egnn_geom_fwd": (_i, [_p, _i, _i, _p, _p, _p, _p, _i, _d, _p, _p, _p]),
+    "eqnn_egnn_coord_fwd": (_i, [_p, _p, _i, _i, _p, _i, _p, _i, _p, _p, _p, _i, _p]),
+    "eqnn_egnn_coord_bwd": (_i, [_p, _p, _i, _i, _p, _p, _i, _p, _i, _d, _p, _p, _p, _p, _p]),
+    "eqnn_egnn_sender_acc": (_i, [_p, _p, _p, _i, _p, _p]),
+    "eqnn_colsum_workspace_bytes": (_sz, [_i]),
+    "eqnn_colsum_tall": (_i, [_p, _i64, _i, _p, _p, _sz, _p]),
     "eqnn_pool_fwd": (_i, [_p, _i, _i, _i, _i, _p, _p]),
     "eqnn_pool_bwd": (_i, [_p, _i, _i, _i, _i, _p, _p]),
     "eqnn_colsum": (_i, [_p, _i64, _i, _p, _p]),

@@ -1,0 +1,329 @@
+// EGNN edge geometry, coordinate update and their backward passes (sm_100a).
+//
+// Reference: models/egnn.py (positions-only layer): :82-90 r_ij = x_i - x_j + 1e-7 (+PBC), |r_ij|, e3nn.bessel;
+// :107-114 x_ij = clip(r_ij * [tanh](t), +-100); jraph segment_{sum,mean} over receivers; :146-150
+// x' = PBC(x + agg).  The two 128-wide edge MLPs in between (phi_e, phi_x) run on the tensor-core GEMMs of
+// tc_mlp.cu.  All kernels walk the receiver-sorted CSR: one warp per receiver row, lanes over its edges,
+// shuffle reductions -- no atomics, deterministic.
+#include "common.cuh"
+
+namespace {
+
+struct Cell3 {
+  float c[9], ci[9];
+  int pbc, diag;
+};
+
+__device__ __forceinline__ void wrap(float& x, float& y, float& z, const Cell3& cl) {
+  if (!cl.pbc) return;
+  if (cl.diag) {
+    x -= rintf(x * cl.ci[0]) * cl.c[0];
+    y -= rintf(y * cl.ci[4]) * cl.c[4];
+    z -= rintf(z * cl.ci[8]) * cl.c[8];
+  } else {
+    const float n0 = rintf(x * cl.ci[0] + y * cl.ci[3] + z * cl.ci[6]);
+    const float n1 = rintf(x * cl.ci[1] + y * cl.ci[4] + z * cl.ci[7]);
+    const float n2 = rintf(x * cl.ci[2] + y * cl.ci[5] + z * cl.ci[8]);
+    x -= n0 * cl.c[0] + n1 * cl.c[3] + n2 * cl.c[6];
+    y -= n0 * cl.c[1] + n1 * cl.c[4] + n2 * cl.c[7];
+    z -= n0 * cl.c[2] + n1 * cl.c[5] + n2 * cl.c[8];
+  }
+}
+
+// rij4[p] = (r_ij, |r_ij|) in CSR order; feats[p, :] = bessel(|r_ij|) (or |r_ij| if n_rb == 0)
+__global__ void __launch_bounds__(256) egnn_geom_fwd_kernel(const float* __restrict__ pos, int ld, int n_nodes,
+                                                            const int32_t* __restrict__ rowptr,
+                                                            const int32_t* __restrict__ src, Cell3 cl, int n_rb,
+                                                            float r_max, float pref, float4* __restrict__ rij4,
+                                                            float* __restrict__ feats) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= n_nodes) return;
+  const int p0 = rowptr[row], p1 = rowptr[row + 1];
+  const float xr = pos[(size_t)row * ld], yr = pos[(size_t)row * ld + 1], zr = pos[(size_t)row * ld + 2];
+  for (int p = p0 + lane; p < p1; p += 32) {
+    const int s = src[p];
+    float rx = (pos[(size_t)s * ld] - xr) + 1e-7f;
+    float ry = (pos[(size_t)s * ld + 1] - yr) + 1e-7f;
+    float rz = (pos[(size_t)s * ld + 2] - zr) + 1e-7f;
+    wrap(rx, ry, rz, cl);
+    const float d = sqrtf(rx * rx + ry * ry + rz * rz);
+    rij4[p] = make_float4(rx, ry, rz, d);
+    if (n_rb == 0) feats[p] = d;
+  }
+  if (n_rb > 0) {
+    const float PI_F = 3.14159265358979323846f;
+    for (int p = p0; p < p1; ++p) {
+      const float d = rij4[p].w;
+      for (int j = 1 + lane; j <= n_rb; j += 32) {
+        const float w = (float)j * PI_F / r_max;
+        feats[(size_t)p * n_rb + j - 1] = pref * ((d == 0.f) ? w : sinf(w * d) / d);
+      }
+    }
+  }
+}
+
+// x_ij = clip(r_ij * t', +-100), t' = tanh(t) or t; agg over the row; pos_out = wrap(pos + agg)
+__global__ void __launch_bounds__(256) egnn_coord_fwd_kernel(const float4* __restrict__ rij4,
+                                                             const float* __restrict__ t, int use_tanh, int agg,
+                                                             const int32_t* __restrict__ rowptr, int n_nodes,
+                                                             const float* __restrict__ pos, int ld, Cell3 cl,
+                                                             float* __restrict__ pos_out, int ld_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= n_nodes) return;
+  const int p0 = rowptr[row], p1 = rowptr[row + 1];
+  float ax = 0.f, ay = 0.f, az = 0.f;
+  for (int p = p0 + lane; p < p1; p += 32) {
+    const float4 r = rij4[p];
+    float tt = t[p];
+    if (use_tanh) tt = tanhf(tt);
+    ax += fminf(fmaxf(r.x * tt, -100.f), 100.f);
+    ay += fminf(fmaxf(r.y * tt, -100.f), 100.f);
+    az += fminf(fmaxf(r.z * tt, -100.f), 100.f);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ax += __shfl_xor_sync(0xffffffffu, ax, o);
+    ay += __shfl_xor_sync(0xffffffffu, ay, o);
+    az += __shfl_xor_sync(0xffffffffu, az, o);
+  }
+  if (lane == 0) {
+    const float inv = (agg == 1) ? 1.f / (float)max(p1 - p0, 1) : 1.f;
+    float x = pos[(size_t)row * ld] + ax * inv, y = pos[(size_t)row * ld + 1] + ay * inv,
+          z = pos[(size_t)row * ld + 2] + az * inv;
+    wrap(x, y, z, cl);
+    pos_out[(size_t)row * ld_out] = x;
+    pos_out[(size_t)row * ld_out + 1] = y;
+    pos_out[(size_t)row * ld_out + 2] = z;
+  }
+}
+
+// Backward of the coordinate update and of the geometry, fused:
+//   g = dL/dpos_out[row] (wrap has unit Jacobian almost everywhere), d x_ij = g / deg (mean) ,
+//   dt[p]  = [1 - tanh^2] * sum_c r_c g_c mask_c ,   dr = t' g mask + (dL/d|r|) r/|r| ,
+//   dL/d|r| = sum_j dfeats[p,j] * d bessel_j / d|r|        (dfeats may be NULL: first sweep computes dt only)
+//   dpos_in[row] = g - sum_p dr[p]   (receiver end);  dre[perm[p]] = dr[p]   (sender end, gathered afterwards)
+// mode 0: write dt only (phase A, before the MLP backward); mode 1: needs dfeats, writes dre and dpos_in.
+__global__ void __launch_bounds__(256) egnn_coord_bwd_kernel(const float4* __restrict__ rij4,
+                                                             const float* __restrict__ t, int use_tanh, int agg,
+                                                             const int32_t* __restrict__ rowptr,
+                                                             const int32_t* __restrict__ perm, int n_nodes,
+                                                             const float* __restrict__ dpos_out, int n_rb, float r_max,
+                                                             float pref, const float* __restrict__ dfeats, int mode,
+                                                             float* __restrict__ dt, float4* __restrict__ dre,
+                                                             float* __restrict__ dpos_in) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= n_nodes) return;
+  const int p0 = rowptr[row], p1 = rowptr[row + 1];
+  const float inv = (agg == 1) ? 1.f / (float)max(p1 - p0, 1) : 1.f;
+  const float gx = dpos_out[(size_t)row * 3] * inv, gy = dpos_out[(size_t)row * 3 + 1] * inv,
+              gz = dpos_out[(size_t)row * 3 + 2] * inv;
+  const float PI_F = 3.14159265358979323846f;
+  float sx = 0.f, sy = 0.f, sz = 0.f;
+  for (int pb = p0; pb < p1; pb += 32) {
+    const int p = pb + lane;
+    const bool on = p < p1;
+    float4 r = make_float4(0.f, 0.f, 0.f, 1.f);
+    float tt = 0.f, tp = 0.f;
+    if (on) {
+      r = rij4[p];
+      tt = t[p];
+      tp = use_tanh ? tanhf(tt) : tt;
+    }
+    const float mx = (fabsf(r.x * tp) <= 100.f) ? 1.f : 0.f, my = (fabsf(r.y * tp) <= 100.f) ? 1.f : 0.f,
+                mz = (fabsf(r.z * tp) <= 100.f) ? 1.f : 0.f;
+    if (mode == 0) {
+      if (on) {
+        float d = r.x * gx * mx + r.y * gy * my + r.z * gz * mz;
+        if (use_tanh) d *= (1.f - tp * tp);
+        dt[p] = d;
+      }
+      continue;
+    }
+    // dL/d|r| from the radial features: lanes cooperate over the basis index for each edge of this batch
+    float dd = 0.f;
+    const int nb = min(32, p1 - pb);
+    for (int q = 0; q < nb; ++q) {
+      const float dq = __shfl_sync(0xffffffffu, r.w, q);
+      float part = 0.f;
+      if (n_rb == 0) {
+        if (lane == 0) part = dfeats[pb + q];
+      } else {
+        for (int j = 1 + lane; j <= n_rb; j += 32) {
+          const float w = (float)j * PI_F / r_max;
+          float sn, cs;
+          sincosf(w * dq, &sn, &cs);
+          const float db = (dq == 0.f) ? 0.f : pref * (w * cs * dq - sn) / (dq * dq);
+          part += dfeats[(size_t)(pb + q) * n_rb + j - 1] * db;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+      if (lane == q) dd = part;
+    }
+    if (on) {
+      const float invd = (r.w > 0.f) ? 1.f / r.w : 0.f;
+      const float dx = tp * gx * mx + dd * r.x * invd, dy = tp * gy * my + dd * r.y * invd,
+                  dz = tp * gz * mz + dd * r.z * invd;
+      dre[perm[p]] = make_float4(dx, dy, dz, 0.f);
+      sx += dx; sy += dy; sz += dz;
+    }
+  }
+  if (mode == 0) return;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sx += __shfl_xor_sync(0xffffffffu, sx, o);
+    sy += __shfl_xor_sync(0xffffffffu, sy, o);
+    sz += __shfl_xor_sync(0xffffffffu, sz, o);
+  }
+  if (lane == 0) {
+    dpos_in[(size_t)row * 3] = dpos_out[(size_t)row * 3] - sx;
+    dpos_in[(size_t)row * 3 + 1] = dpos_out[(size_t)row * 3 + 1] - sy;
+    dpos_in[(size_t)row * 3 + 2] = dpos_out[(size_t)row * 3 + 2] - sz;
+  }
+}
+
+// dpos[s, c] += sum over the edges sent by s of dre[e, c]   (sender-sorted CSR, c < 3)
+__global__ void egnn_sender_acc_kernel(const float4* __restrict__ dre, const int32_t* __restrict__ rowptr_s,
+                                       const int32_t* __restrict__ perm_s, int n_nodes, float* __restrict__ dpos) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_nodes) return;
+  float ax = 0.f, ay = 0.f, az = 0.f;
+  for (int q = rowptr_s[s]; q < rowptr_s[s + 1]; ++q) {
+    const float4 v = dre[perm_s[q]];
+    ax += v.x; ay += v.y; az += v.z;
+  }
+  dpos[s * 3] += ax;
+  dpos[s * 3 + 1] += ay;
+  dpos[s * 3 + 2] += az;
+}
+
+// two-stage column sum for tall matrices (bias gradients): partial[cta][n] then fixed-order reduce
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ x, int64_t M, int N,
+                                                             int64_t rows_per_cta, float* __restrict__ partial) {
+  __shared__ float sm[8][129];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 8 row-lanes x 32 column-lanes (x4 columns each)
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta, r1 = min(M, r0 + rows_per_cta);
+  for (int c0 = 0; c0 < N; c0 += 128) {
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    const int c = c0 + tx * 4;
+    if (c + 3 < N && (N & 3) == 0) {
+      for (int64_t r = r0 + ty; r < r1; r += 8) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x + r * N + c));
+        a[0] += v.x; a[1] += v.y; a[2] += v.z; a[3] += v.w;
+      }
+    } else {
+      for (int64_t r = r0 + ty; r < r1; r += 8)
+        for (int q = 0; q < 4; ++q)
+          if (c + q < N) a[q] += x[r * N + c + q];
+    }
+    for (int q = 0; q < 4; ++q) sm[ty][tx * 4 + q] = a[q];
+    __syncthreads();
+    if (threadIdx.x < 128 && c0 + threadIdx.x < N) {
+      float s = 0.f;
+      for (int q = 0; q < 8; ++q) s += sm[q][threadIdx.x];
+      partial[(size_t)blockIdx.x * N + c0 + threadIdx.x] = s;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void colsum_final_kernel(const float* __restrict__ partial, int n_parts, int N, float* __restrict__ y) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= N) return;
+  float s = 0.f;
+  for (int q = 0; q < n_parts; ++q) s += partial[(size_t)q * N + c];
+  y[c] = s;
+}
+
+int make_cell(Cell3& cl, const float* cell, const float* cell_inv) {
+  cl.pbc = (cell != nullptr) ? 1 : 0;
+  cl.diag = 1;
+  for (int i = 0; i < 9; ++i) {
+    cl.c[i] = cell ? cell[i] : ((i % 4 == 0) ? 1.f : 0.f);
+    cl.ci[i] = cell_inv ? cell_inv[i] : ((i % 4 == 0) ? 1.f : 0.f);
+    if (cell && i % 4 != 0 && (cell[i] != 0.f || cell_inv[i] != 0.f)) cl.diag = 0;
+  }
+  EQNN_CHECK_ARG(!cell || cell_inv, "egnn: cell given without cell_inv");
+  return EQNN_OK;
+}
+
+constexpr int COLSUM_PARTS = 296;
+
+}  // namespace
+
+extern "C" int eqnn_egnn_geom_fwd(const float* pos, int ld_pos, int n_nodes, const int32_t* rowptr,
+                                  const int32_t* src, const float* cell, const float* cell_inv, int n_rb, double r_max,
+                                  float* rij4, float* feats, eqnn_stream_t stream) {
+  EQNN_CHECK_ARG(pos && rowptr && src && rij4 && feats && ld_pos >= 3, "egnn_geom_fwd: bad argument");
+  EQNN_CHECK_ARG(((uintptr_t)rij4 & 15) == 0, "egnn_geom_fwd: rij4 must be 16-byte aligned");
+  EQNN_CHECK_ARG(n_rb == 0 || r_max > 0.0, "egnn_geom_fwd: r_max must be positive");
+  if (n_nodes <= 0) return EQNN_OK;
+  Cell3 cl;
+  int rc = make_cell(cl, cell, cell_inv);
+  if (rc) return rc;
+  const float pref = n_rb > 0 ? (float)sqrt(2.0 / r_max) : 1.f;
+  egnn_geom_fwd_kernel<<<(unsigned)ceil_div64((int64_t)n_nodes * 32, 256), 256, 0, as_stream(stream)>>>(
+      pos, ld_pos, n_nodes, rowptr, src, cl, n_rb, (float)r_max, pref, reinterpret_cast<float4*>(rij4), feats);
+  EQNN_CHECK_LAUNCH();
+  return EQNN_OK;
+}
+
+extern "C" int eqnn_egnn_coord_fwd(const float* rij4, const float* t, int use_tanh, int agg, const int32_t* rowptr,
+                                   int n_nodes, const float* pos, int ld_pos, const float* cell, const float* cell_inv,
+                                   float* pos_out, int ld_out, eqnn_stream_t stream) {
+  EQNN_CHECK_ARG(rij4 && t && rowptr && pos && pos_out && ld_pos >= 3 && ld_out >= 3, "egnn_coord_fwd: bad argument");
+  EQNN_CHECK_ARG(agg == 0 || agg == 1, "egnn_coord_fwd: agg must be 0 (sum) or 1 (mean)");
+  if (n_nodes <= 0) return EQNN_OK;
+  Cell3 cl;
+  int rc = make_cell(cl, cell, cell_inv);
+  if (rc) return rc;
+  egnn_coord_fwd_kernel<<<(unsigned)ceil_div64((int64_t)n_nodes * 32, 256), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const float4*>(rij4), t, use_tanh, agg, rowptr, n_nodes, pos, ld_pos, cl, pos_out, ld_out);
+  EQNN_CHECK_LAUNCH();
+  return EQNN_OK;
+}
+
+extern "C" int eqnn_egnn_coord_bwd(const float* rij4, const float* t, int use_tanh, int agg, const int32_t* rowptr,
+                                   const int32_t* perm, int n_nodes, const float* dpos_out, int n_rb, double r_max,
+                                   const float* dfeats, float* dt, float* dre, float* dpos_in, eqnn_stream_t stream) {
+  EQNN_CHECK_ARG(rij4 && t && rowptr && dpos_out, "egnn_coord_bwd: bad argument");
+  EQNN_CHECK_ARG(agg == 0 || agg == 1, "egnn_coord_bwd: agg must be 0 (sum) or 1 (mean)");
+  const int mode = dfeats ? 1 : 0;
+  EQNN_CHECK_ARG(mode == 1 ? (perm && dre && dpos_in) : (dt != nullptr), "egnn_coord_bwd: missing output for this phase");
+  if (n_nodes <= 0) return EQNN_OK;
+  const float pref = n_rb > 0 ? (float)sqrt(2.0 / r_max) : 1.f;
+  egnn_coord_bwd_kernel<<<(unsigned)ceil_div64((int64_t)n_nodes * 32, 256), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const float4*>(rij4), t, use_tanh, agg, rowptr, perm, n_nodes, dpos_out, n_rb, (float)r_max, pref,
+      dfeats, mode, dt, reinterpret_cast<float4*>(dre), dpos_in);
+  EQNN_CHECK_LAUNCH();
+  return EQNN_OK;
+}
+
+extern "C" int eqnn_egnn_sender_acc(const float* dre, const int32_t* rowptr_s, const int32_t* perm_s, int n_nodes,
+                                    float* dpos, eqnn_stream_t stream) {
+  EQNN_CHECK_ARG(dre && rowptr_s && perm_s && dpos, "egnn_sender_acc: bad argument");
+  if (n_nodes <= 0) return EQNN_OK;
+  egnn_sender_acc_kernel<<<(unsigned)ceil_div64(n_nodes, 256), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const float4*>(dre), rowptr_s, perm_s, n_nodes, dpos);
+  EQNN_CHECK_LAUNCH();
+  return EQNN_OK;
+}
+
+extern "C" size_t eqnn_colsum_workspace_bytes(int N) { return (size_t)COLSUM_PARTS * N * sizeof(float); }
+
+extern "C" int eqnn_colsum_tall(const float* x, int64_t M, int N, float* y, void* ws, size_t ws_bytes,
+                                eqnn_stream_t stream) {
+  EQNN_CHECK_ARG(x && y && M >= 0 && N >= 1, "colsum_tall: bad argument");
+  EQNN_CHECK_ARG(ws && ws_bytes >= eqnn_colsum_workspace_bytes(N), "colsum_tall: workspace too small");
+  EQNN_CHECK_ARG(((uintptr_t)x & 15) == 0, "colsum_tall: x must be 16-byte aligned");
+  const int parts = (int)min((int64_t)COLSUM_PARTS, max((int64_t)1, (M + 255) / 256));
+  const int64_t rpc = (M + parts - 1) / parts;
+  cudaStream_t st = as_stream(stream);
+  colsum_partial_kernel<<<parts, 256, 0, st>>>(x, M, N, rpc, reinterpret_cast<float*>(ws));
+  colsum_final_kernel<<<(N + 127) / 128, 128, 0, st>>>(reinterpret_cast<float*>(ws), parts, N, y);
+  EQNN_CHECK_LAUNCH_N(2);
+  return EQNN_OK;
+}

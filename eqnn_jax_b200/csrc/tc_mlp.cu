@@ -70,7 +70,7 @@ struct RowCfg {
 };
 
 // AMODE 0: A row-major (k contiguous), K % 32 == 0.  AMODE 1: A column-major (m contiguous), K <= 32.
-// PRO 1: A := gelu_tanh(A) * pro_scale.  EPI 2: C *= gelu_tanh'(aux) * epi_scale.
+// PRO 1: A := gelu_tanh(A) * pro_scale.  EPI 1: C += bias (aux[n]).  EPI 2: C *= gelu_tanh'(aux) * epi_scale.
 // CMODE 0: C row-major [M][ldc]; CMODE 1: C column-major [n][ldc] (only the first n_valid columns).
 template <int K, int N, int AMODE, int PRO, int EPI, int CMODE>
 __global__ void __launch_bounds__(RG_THREADS, 1) tc_rowgemm_kernel(const RowGemmP p) {
@@ -258,6 +258,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) tc_rowgemm_kernel(const RowGemm
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               o[j] = p.alpha * v[j];
+              if (EPI == 1) o[j] += __ldg(p.aux + col0 + cb * 16 + j);      // bias[n] (models/mlp.py Dense)
               if (EPI == 2) o[j] *= gelu_tanh_grad(ax[j]) * p.epi_scale;
             }
             float* crow = p.C + m * p.ldc + col0 + cb * 16;
@@ -270,22 +271,31 @@ __global__ void __launch_bounds__(RG_THREADS, 1) tc_rowgemm_kernel(const RowGemm
           }
         }
       } else {
-        // narrow output (N = 16): the lower column half stores; the upper half only keeps the protocol
+        // narrow output (N = 16 or 32): the lower column half stores; the upper half only keeps the protocol
         mbar_wait(t_full(ab), (tcount >> 1) & 1u);
         tc_fence_after();
-        float v[16];
+        float v[N];
         if (half == 0) {
-          tmem_ld16(taddr, v);
+          if (N == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
           tmem_ld_wait();
         }
         tc_fence_before();
         mbar_arrive(t_empty(ab));
         if (half == 0 && live) {
+          if (CMODE == 0 && N == 32) {
+            float o[32];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            if (j < p.n_valid) {
-              if (CMODE == 1) p.C[(int64_t)j * p.ldc + m] = p.alpha * v[j];
-              else p.C[m * p.ldc + j] = p.alpha * v[j];
+            for (int j = 0; j < 32; ++j) o[j] = p.alpha * v[j];
+            float* crow = p.C + m * p.ldc;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) stg256(crow + j, o + j);
+          } else {
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+              if (j < p.n_valid) {
+                if (CMODE == 1) p.C[(int64_t)j * p.ldc + m] = p.alpha * v[j];
+                else p.C[m * p.ldc + j] = p.alpha * v[j];
+              }
             }
           }
         }
@@ -590,7 +600,7 @@ int eqnn_tc_wgrad_try(int64_t M, int64_t N, int64_t K, float alpha, const float*
                       const float* B, int64_t sbk, int64_t sbn, float* C, int64_t scm, int64_t scn, int accumulate,
                       int pro, float pro_scale, int epi, void* ws, size_t ws_bytes, cudaStream_t st) {
   if (accumulate || epi != 0 || K < 4096 || scn != 1) return 0;
-  if (!(M == 64 || M == 128) || sam != 1 || sak % 4 != 0 || (reinterpret_cast<uintptr_t>(A) & 15)) return 0;
+  if (!(M == 32 || M == 64 || M == 128) || sam != 1 || sak % 4 != 0 || (reinterpret_cast<uintptr_t>(A) & 15)) return 0;
   if (reinterpret_cast<uintptr_t>(B) & 15) return 0;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -605,12 +615,14 @@ int eqnn_tc_wgrad_try(int64_t M, int64_t N, int64_t K, float alpha, const float*
     npad = 128; p.ldg = sbk;
     if (!ws || ws_bytes < (size_t)grid * M * npad * 4) return 0;
     if (M == 128) rc = pro ? launch_wgrad<128, 128, 0, 1>(p, grid, st) : launch_wgrad<128, 128, 0, 0>(p, grid, st);
-    else rc = pro ? launch_wgrad<64, 128, 0, 1>(p, grid, st) : launch_wgrad<64, 128, 0, 0>(p, grid, st);
+    else if (M == 64) rc = pro ? launch_wgrad<64, 128, 0, 1>(p, grid, st) : launch_wgrad<64, 128, 0, 0>(p, grid, st);
+    else rc = pro ? launch_wgrad<32, 128, 0, 1>(p, grid, st) : launch_wgrad<32, 128, 0, 0>(p, grid, st);
   } else if (N <= 16 && sbk == 1 && sbn % 4 == 0) {
     npad = 16; p.ldg = sbn;
     if (!ws || ws_bytes < (size_t)grid * M * npad * 4) return 0;
     if (M == 128) rc = pro ? launch_wgrad<128, 16, 1, 1>(p, grid, st) : launch_wgrad<128, 16, 1, 0>(p, grid, st);
-    else rc = pro ? launch_wgrad<64, 16, 1, 1>(p, grid, st) : launch_wgrad<64, 16, 1, 0>(p, grid, st);
+    else if (M == 64) rc = pro ? launch_wgrad<64, 16, 1, 1>(p, grid, st) : launch_wgrad<64, 16, 1, 0>(p, grid, st);
+    else return 0;
   } else {
     return 0;
   }
@@ -627,7 +639,7 @@ int eqnn_tc_rowgemm_try(int64_t M, int64_t N, int64_t K, float alpha, const floa
                         const float* B, int64_t sbk, int64_t sbn, float* C, int64_t scm, int64_t scn, int accumulate,
                         int pro, float pro_scale, int epi, const float* aux, int64_t ld_aux, float epi_scale,
                         cudaStream_t st) {
-  if (accumulate || M < 4096 || epi == 1) return 0;
+  if (accumulate || M < 4096) return 0;
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   RowGemmP p;
   p.A = A; p.B = B; p.sbk = sbk; p.sbn = sbn; p.k_valid = (int)K; p.n_valid = (int)N;
@@ -637,22 +649,28 @@ int eqnn_tc_rowgemm_try(int64_t M, int64_t N, int64_t K, float alpha, const floa
   const bool a_row = (sak == 1 && sam % 4 == 0 && al16(A));
   auto al32 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 31) == 0; };
   const bool c_row = (scn == 1 && scm % 8 == 0 && al32(C));          // 256-bit row stores
-  const bool aux_ok = (epi == 0) || (ld_aux % 8 == 0 && al32(aux));  // 256-bit row loads
-  if (N == 128 && a_row && c_row && aux_ok && (K == 128 || K == 64)) {
+  const bool aux_ok = (epi != 2) || (ld_aux % 8 == 0 && al32(aux));  // 256-bit row loads
+  if (N == 128 && a_row && c_row && aux_ok && (K == 128 || K == 64 || K == 32)) {
     p.lda = sam; p.ldc = scm;
 #define EQNN_TC_CASE(KK, PR, EP)                                                              \
   if (K == KK && pro == PR && epi == EP) { rc = launch_rowgemm<KK, 128, 0, PR, EP, 0>(p, st); return rc ? -rc : 1; }
     EQNN_TC_CASE(64, 0, 0) EQNN_TC_CASE(128, 1, 0) EQNN_TC_CASE(128, 0, 2) EQNN_TC_CASE(128, 0, 0)
     EQNN_TC_CASE(64, 1, 0) EQNN_TC_CASE(128, 1, 2) EQNN_TC_CASE(64, 0, 2)
+    EQNN_TC_CASE(32, 0, 0) EQNN_TC_CASE(32, 0, 1) EQNN_TC_CASE(64, 0, 1) EQNN_TC_CASE(128, 0, 1) EQNN_TC_CASE(128, 1, 1)
 #undef EQNN_TC_CASE
     return 0;
   }
-  if (N <= 16 && K == 128 && a_row && scm == 1 && epi == 0) {      // last radial layer -> column-major w_t
+  if (N <= 16 && K == 128 && a_row && scm == 1 && epi == 0) {      // narrow last layer -> column-major output
     p.lda = sam; p.ldc = scn;
     rc = (pro == 1) ? launch_rowgemm<128, 16, 0, 1, 0, 1>(p, st) : launch_rowgemm<128, 16, 0, 0, 0, 1>(p, st);
     return rc ? -rc : 1;
   }
-  if (N == 128 && K <= 16 && sam == 1 && c_row && aux_ok && pro == 0) {   // data-gradient of the last layer
+  if (N == 32 && K == 128 && a_row && c_row && scm == 32 && pro == 0 && epi == 0) {   // data-gradient w.r.t. 32 radial features
+    p.lda = sam; p.ldc = scm;
+    rc = launch_rowgemm<128, 32, 0, 0, 0, 0>(p, st);
+    return rc ? -rc : 1;
+  }
+  if (N == 128 && K <= 16 && sam == 1 && c_row && aux_ok && pro == 0 && epi != 1) {   // data-gradient of the last layer
     p.lda = sak; p.ldc = scm;
     rc = (epi == 2) ? launch_rowgemm<16, 128, 1, 0, 2, 0>(p, st) : launch_rowgemm<16, 128, 1, 0, 0, 0>(p, st);
     return rc ? -rc : 1;

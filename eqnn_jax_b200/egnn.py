@@ -1,0 +1,278 @@
+"""EGNN on B200 kernels, behind the reference's module interface.
+
+Drop-in for ``models/egnn.py`` (reference) in the configuration the cosmology benchmark and the example notebook
+use: ``positions_only=True`` on 3-d nodes (benchmarks/galaxies/train_cosmology.py:67-81 with feats='pos';
+notebooks/examples.ipynb cell 14).  Same dataclass fields and defaults (:240-255), ``GraphsTuple`` in ->
+``GraphsTuple`` (task="node") or ``(B, n_outputs)`` (task="graph") out, Flax parameter names (MLP_i / Dense_s).
+
+Per message-passing step, edges in receiver-sorted order:
+    r_ij, |r_ij|, bessel      eqnn_egnn_geom_fwd                       egnn.py:82-90
+    m   = phi_e(bessel)       tcgen05 3xTF32 GEMMs (+bias, gelu)        egnn.py:63-67,98
+    t   = Dense_1(phi_x(m))   tcgen05 3xTF32 GEMMs                      egnn.py:70-79,107
+    x'  = wrap(x + agg clip(r_ij t))   eqnn_egnn_coord_fwd              egnn.py:110-114,146-150 + jraph segment reduce
+With 3-d nodes the aggregated messages m_i are never read (egnn.py:143-150), so they are not aggregated
+(XLA removes that dead reduction under jit as well).  Not built yet: scalar/velocity node attributes,
+soft_edges=True, globals, max aggregation -> NotImplementedError, never a silent fallback.
+"""
+from __future__ import annotations
+
+import dataclasses
+import math
+from typing import Callable, Dict, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import ops
+from .graph_utils import ApplyPBC, GraphsTuple
+from .nequip import NequIPParams as FlatParams
+from .nequip import _mm
+
+
+@dataclasses.dataclass
+class EGNN:
+    """Field names and defaults of the reference module (models/egnn.py:240-255)."""
+    message_passing_steps: int = 3
+    d_hidden: int = 128
+    n_layers: int = 3
+    activation: str = "gelu"
+    soft_edges: bool = True
+    positions_only: bool = False
+    tanh_out: bool = False
+    n_radial_basis: int = 16
+    r_max: float = 0.3
+    decouple_pos_vel_updates: bool = False
+    message_passing_agg: str = "sum"
+    readout_agg: str = "mean"
+    mlp_readout_widths: Sequence[int] = (4, 2, 2)
+    task: str = "graph"
+    n_outputs: int = 1
+    apply_pbc: Optional[ApplyPBC] = None
+    tensor_cores: bool = True     # not a reference field: tcgen05 3xTF32 GEMMs (False: fp32 CUDA-core GEMMs)
+
+    # ---- static layout ------------------------------------------------------------------
+    def _check(self, n_feat: int) -> None:
+        if not self.positions_only or n_feat != 3:
+            raise NotImplementedError("B200 EGNN covers positions_only=True on 3-d nodes (the benchmarked configuration)")
+        if self.soft_edges:
+            raise NotImplementedError("soft_edges=True is not built on the B200 path yet")
+        if self.activation != "gelu":
+            raise NotImplementedError("only activation='gelu' has a B200 kernel on this path")
+        if self.message_passing_agg not in ("sum", "mean") or self.readout_agg not in ("sum", "mean"):
+            raise NotImplementedError("aggregations must be 'sum' or 'mean' on the B200 path")
+        if self.n_layers < 2:
+            raise NotImplementedError("n_layers >= 2 expected")
+
+    def _layout(self):
+        d, L = self.d_hidden, self.n_layers
+        nf = self.n_radial_basis if self.n_radial_basis > 0 else 1
+        layout: List[Tuple[Tuple[str, ...], Tuple[int, ...], int]] = []
+        off = 0
+
+        def add(path, shape):
+            nonlocal off
+            layout.append((path, tuple(shape), off))
+            o = off
+            off += int(np.prod(shape))
+            return o
+
+        steps, mi = [], 0
+        for s in range(self.message_passing_steps):
+            st = {"phi_e": [], "phi_x": []}
+            fan = nf
+            for l in range(L):
+                st["phi_e"].append((add((f"MLP_{mi}", f"Dense_{l}", "kernel"), (fan, d)),
+                                    add((f"MLP_{mi}", f"Dense_{l}", "bias"), (d,)), fan))
+                fan = d
+            mi += 1
+            for l in range(L - 1):
+                st["phi_x"].append((add((f"MLP_{mi}", f"Dense_{l}", "kernel"), (d, d)),
+                                    add((f"MLP_{mi}", f"Dense_{l}", "bias"), (d,)), d))
+            mi += 1
+            st["k_last"] = add((f"Dense_{s}", "kernel"), (d, 1))
+            mi += 1   # phi_a is constructed (takes a name) but owns parameters only with soft_edges
+            steps.append(st)
+        readout = []
+        if self.task == "graph":
+            ws = [self.mlp_readout_widths[0] * 3] + [w * d for w in self.mlp_readout_widths[1:]] + [self.n_outputs]
+            fan = 3
+            for l, h in enumerate(ws):
+                readout.append((add((f"MLP_{mi}", f"Dense_{l}", "kernel"), (fan, h)),
+                                add((f"MLP_{mi}", f"Dense_{l}", "bias"), (h,)), fan, h))
+                fan = h
+        return layout, steps, readout, off
+
+    def init(self, rng: Union[int, np.random.Generator], graphs: GraphsTuple) -> FlatParams:
+        self._check(graphs.nodes.shape[-1])
+        layout, steps, readout, n = self._layout()
+        rng = np.random.default_rng(rng) if not isinstance(rng, np.random.Generator) else rng
+        host = np.zeros((n,), dtype=np.float32)
+        for path, shape, off in layout:
+            if path[-1] == "bias":
+                continue
+            if path[0].startswith("Dense_"):       # variance_scaling(1e-2, fan_in, uniform), egnn.py:73-78
+                lim = math.sqrt(3.0 * 1e-2 / shape[0])
+            else:                                  # xavier_uniform, models/mlp.py:19
+                lim = math.sqrt(6.0 / (shape[0] + shape[1]))
+            host[off:off + int(np.prod(shape))] = rng.uniform(-lim, lim, size=shape).reshape(-1)
+        return FlatParams(layout, torch.from_numpy(host).to(graphs.nodes.device))
+
+    # ---- forward / backward -----------------------------------------------------------------
+    def _prepare(self, graphs: GraphsTuple):
+        x = graphs.nodes
+        if x.dim() == 2:
+            x = x.unsqueeze(0)
+        B, N, F = x.shape
+        self._check(F)
+        if graphs.globals is not None:
+            raise NotImplementedError("graph globals are not on the B200 EGNN path yet")
+        senders = graphs.senders.reshape(B, -1).contiguous()
+        receivers = graphs.receivers.reshape(B, -1).contiguous()
+        rowptr, perm, src = ops.csr_build(senders, receivers, N)
+        rowptr_s, perm_s, _ = ops.csr_build(receivers, senders, N)
+        return x.contiguous(), B, N, senders.shape[1], (rowptr, perm, src, rowptr_s, perm_s)
+
+    def forward_backward(self, params: FlatParams, graphs: GraphsTuple, grad_fn=None):
+        """Forward (and, if ``grad_fn(out) -> dL/dout`` is given, backward into ``params.grad``)."""
+        x, B, N, E, csr = self._prepare(graphs)
+        out, saved = self._forward(params.flat, x, B, N, E, csr)
+        if grad_fn is not None:
+            self._backward(params.flat, params.grad, saved, grad_fn(out).contiguous(), B, N, E, csr)
+        return out
+
+    def apply(self, params: FlatParams, graphs: GraphsTuple):
+        out = _EGNNFunction.apply(params.flat, self, graphs)
+        if self.task == "graph":
+            return out
+        return graphs._replace(nodes=out)
+
+    __call__ = apply
+
+    def _forward(self, theta, x, B, N, E, csr):
+        rowptr, perm, src, rowptr_s, perm_s = csr
+        dev = x.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        layout, steps, readout, _ = self._layout()
+        Nt, Et = B * N, B * E
+        d = self.d_hidden
+        nf = self.n_radial_basis if self.n_radial_basis > 0 else 1
+        cell = None if self.apply_pbc is None else self.apply_pbc.cell
+        cinv = None if self.apply_pbc is None else self.apply_pbc.cell_inv
+        agg = 1 if self.message_passing_agg == "mean" else 0
+        tc = self.tensor_cores
+        pos = x.reshape(Nt, 3)
+        saved = {"steps": []}
+        for st in steps:
+            rij4 = torch.empty((Et, 4), **f32)
+            feats = torch.empty((Et, nf), **f32)
+            ops.egnn_geom_fwd(pos, 3, Nt, rowptr, src, cell, cinv, self.n_radial_basis, self.r_max, rij4, feats)
+            acts, a, pro = [], feats, 0
+            for (ko, bo, fan) in st["phi_e"] + st["phi_x"]:
+                Z = torch.empty((Et, d), **f32)
+                _mm(Et, d, fan, 1.0, a, 0, fan, theta, ko, d, Z, 0, d, pro=pro, pro_scale=1.0, epi=1, aux=theta,
+                    aux_off=bo, tag="egnn_mlp_fwd", tf32x3=tc)
+                acts.append(Z)
+                a, pro = Z, 1
+            t = torch.empty((Et,), **f32)
+            _mm(Et, 1, d, 1.0, a, 0, d, theta, st["k_last"], 1, t, 0, Et, tc=True, pro=1, pro_scale=1.0,
+                tag="egnn_mlp_fwd", tf32x3=tc)
+            pos_next = torch.empty((Nt, 3), **f32)
+            ops.egnn_coord_fwd(rij4, t, self.tanh_out, agg, rowptr, Nt, pos, 3, cell, cinv, pos_next, 3)
+            saved["steps"].append(dict(rij4=rij4, feats=feats, acts=acts, t=t))
+            pos = pos_next
+        if self.task == "node":
+            return pos.view(B, N, 3), saved
+        pooled = torch.empty((B, 3), **f32)
+        ops.pool_fwd(pos, B, N, 3, 1 if self.readout_agg == "mean" else 0, pooled)
+        zs, a, pro = [], pooled, 0
+        for (ko, bo, fan, h) in readout:
+            zl = torch.empty((B, h), **f32)
+            _mm(B, h, fan, 1.0, a, 0, fan, theta, ko, h, zl, 0, h, pro=pro, pro_scale=1.0, epi=1, aux=theta, aux_off=bo)
+            zs.append(zl)
+            a, pro = zl, 1
+        saved.update(pooled=pooled, ro_z=zs)
+        return zs[-1], saved
+
+    def _backward(self, theta, gtheta, saved, gout, B, N, E, csr):
+        rowptr, perm, src, rowptr_s, perm_s = csr
+        dev = theta.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        layout, steps, readout, _ = self._layout()
+        Nt, Et = B * N, B * E
+        d = self.d_hidden
+        nf = self.n_radial_basis if self.n_radial_basis > 0 else 1
+        agg = 1 if self.message_passing_agg == "mean" else 0
+        tc = self.tensor_cores
+        gtheta.zero_()
+        if self.task == "node":
+            dpos = gout.reshape(Nt, 3).clone()
+        else:
+            zs = saved["ro_z"]
+            dz = gout.reshape(B, -1).contiguous()
+            for l in range(len(readout) - 1, -1, -1):
+                ko, bo, fan, h = readout[l]
+                a_prev = zs[l - 1] if l > 0 else saved["pooled"]
+                _mm(fan, h, B, 1.0, a_prev, 0, fan, dz, 0, h, gtheta, ko, h, ta=True, pro=1 if l > 0 else 0, pro_scale=1.0)
+                ops.colsum(dz, B, h, gtheta, y_off=bo)
+                dprev = torch.empty((B, fan), **f32)
+                if l > 0:
+                    _mm(B, fan, h, 1.0, dz, 0, h, theta, ko, h, dprev, 0, fan, tb=True, epi=2, aux=zs[l - 1], ld_aux=fan,
+                        epi_scale=1.0)
+                else:
+                    _mm(B, fan, h, 1.0, dz, 0, h, theta, ko, h, dprev, 0, fan, tb=True)
+                dz = dprev
+            dpos = torch.empty((Nt, 3), **f32)
+            ops.pool_bwd(dz, B, N, 3, 1 if self.readout_agg == "mean" else 0, dpos)
+        dt = torch.empty((Et,), **f32)
+        dre = torch.empty((Et, 4), **f32)
+        for si in range(len(steps) - 1, -1, -1):
+            st, sv = steps[si], saved["steps"][si]
+            rij4, feats, acts, t = sv["rij4"], sv["feats"], sv["acts"], sv["t"]
+            ops.egnn_coord_bwd(rij4, t, self.tanh_out, agg, rowptr, perm, Nt, dpos, self.n_radial_basis, self.r_max,
+                               None, dt, None, None)
+            layers = st["phi_e"] + st["phi_x"]
+            last = acts[-1]
+            # t = gelu(U_last) @ k_last
+            _mm(d, 1, Et, 1.0, last, 0, d, dt, 0, Et, gtheta, st["k_last"], 1, ta=True, tb=True, pro=1, pro_scale=1.0,
+                tag="egnn_mlp_bwd", tf32x3=tc)
+            dZ = torch.empty((Et, d), **f32)
+            _mm(Et, d, 1, 1.0, dt, 0, Et, theta, st["k_last"], 1, dZ, 0, d, ta=True, tb=True, epi=2, aux=last, ld_aux=d,
+                epi_scale=1.0, tag="egnn_mlp_bwd", tf32x3=tc)
+            dfeats = None
+            for l in range(len(layers) - 1, -1, -1):
+                ko, bo, fan = layers[l]
+                a_prev, pro = (acts[l - 1], 1) if l > 0 else (feats, 0)
+                _mm(fan, d, Et, 1.0, a_prev, 0, fan, dZ, 0, d, gtheta, ko, d, ta=True, pro=pro, pro_scale=1.0,
+                    tag="egnn_mlp_bwd", tf32x3=tc)
+                ops.colsum_tall(dZ, Et, d, gtheta, y_off=bo)
+                if l > 0:
+                    dZp = torch.empty((Et, fan), **f32)
+                    _mm(Et, fan, d, 1.0, dZ, 0, d, theta, ko, d, dZp, 0, fan, tb=True, epi=2, aux=acts[l - 1], ld_aux=fan,
+                        epi_scale=1.0, tag="egnn_mlp_bwd", tf32x3=tc)
+                    dZ = dZp
+                elif si > 0:
+                    dfeats = torch.empty((Et, nf), **f32)
+                    _mm(Et, nf, d, 1.0, dZ, 0, d, theta, ko, d, dfeats, 0, nf, tb=True, tag="egnn_mlp_bwd", tf32x3=tc)
+            if si > 0:
+                dpos_in = torch.empty((Nt, 3), **f32)
+                ops.egnn_coord_bwd(rij4, t, self.tanh_out, agg, rowptr, perm, Nt, dpos, self.n_radial_basis, self.r_max,
+                                   dfeats, None, dre, dpos_in)
+                ops.egnn_sender_acc(dre, rowptr_s, perm_s, Nt, dpos_in)
+                dpos = dpos_in
+        return None
+
+
+class _EGNNFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, theta, model, graphs):
+        x, B, N, E, csr = model._prepare(graphs)
+        out, saved = model._forward(theta.detach(), x, B, N, E, csr)
+        ctx.stuff = (model, saved, B, N, E, csr, theta.detach())
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        model, saved, B, N, E, csr, theta = ctx.stuff
+        g = torch.zeros_like(theta)
+        model._backward(theta, g, saved, gout.contiguous(), B, N, E, csr)
+        return g, None, None

@@ -260,6 +260,41 @@ def node_update_bwd(A, ld_a, d_a, h, d_h, wexp, w1_off, alpha1, w2_off, n_extra,
         TIMER.end("node_update_bwd", t0)
 
 
+def _c9(a):
+    return None if a is None else (C.c_float * 9)(*[float(v) for v in a.reshape(-1)])
+
+
+def egnn_geom_fwd(pos, ld_pos, n_nodes, rowptr, src, cell, cell_inv, n_rb, r_max, rij4, feats):
+    check(lib().eqnn_egnn_geom_fwd(_ptr(pos), ld_pos, n_nodes, _ptr(rowptr), _ptr(src), _c9(cell), _c9(cell_inv), n_rb,
+                                   float(r_max), _ptr(rij4), _ptr(feats), _stream()), "egnn_geom_fwd")
+
+
+def egnn_coord_fwd(rij4, t, use_tanh, agg, rowptr, n_nodes, pos, ld_pos, cell, cell_inv, pos_out, ld_out):
+    check(lib().eqnn_egnn_coord_fwd(_ptr(rij4), _ptr(t), int(use_tanh), agg, _ptr(rowptr), n_nodes, _ptr(pos), ld_pos,
+                                    _c9(cell), _c9(cell_inv), _ptr(pos_out), ld_out, _stream()), "egnn_coord_fwd")
+
+
+def egnn_coord_bwd(rij4, t, use_tanh, agg, rowptr, perm, n_nodes, dpos_out, n_rb, r_max, dfeats, dt, dre, dpos_in):
+    check(lib().eqnn_egnn_coord_bwd(_ptr(rij4), _ptr(t), int(use_tanh), agg, _ptr(rowptr), _ptr(perm), n_nodes,
+                                    _ptr(dpos_out), n_rb, float(r_max), _ptr(dfeats), _ptr(dt), _ptr(dre),
+                                    _ptr(dpos_in), _stream()), "egnn_coord_bwd")
+
+
+def egnn_sender_acc(dre, rowptr_s, perm_s, n_nodes, dpos):
+    check(lib().eqnn_egnn_sender_acc(_ptr(dre), _ptr(rowptr_s), _ptr(perm_s), n_nodes, _ptr(dpos), _stream()),
+          "egnn_sender_acc")
+
+
+_COLSUM_WS = GemmWorkspace()
+
+
+def colsum_tall(x, M, N, y, y_off=0):
+    need = lib().eqnn_colsum_workspace_bytes(N)
+    ws, ws_bytes = _COLSUM_WS.get(need, x.device)
+    check(lib().eqnn_colsum_tall(_ptr(x), M, N, C.c_void_p(y.data_ptr() + 4 * y_off), ws, ws_bytes, _stream()),
+          "colsum_tall")
+
+
 def pool_fwd(x, B, N, D, mode, out):
     check(lib().eqnn_pool_fwd(_ptr(x), B, N, D, mode, _ptr(out), _stream()), "pool_fwd")
 

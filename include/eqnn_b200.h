@@ -185,6 +185,29 @@ int eqnn_pool_bwd(const float* gout, int B, int N, int D, int mode, float* gx, e
 /* y[n] = sum_m x[m, n]  (bias gradients) */
 int eqnn_colsum(const float* x, int64_t M, int N, float* y, eqnn_stream_t stream);
 
+/* ---- EGNN coordinate layer (models/egnn.py, positions-only) ---------------------------------------------
+ * geometry (:82-90):  rij4[p] = (r_ij, |r_ij|), r_ij = x_s - x_r + 1e-7 then minimum image (cell may be NULL);
+ *                     feats[p, :] = e3nn.bessel(|r_ij|, n_rb, r_max)  ([n_edges, 1] = |r_ij| if n_rb == 0)
+ * coordinates (:107-114, jraph segment reduce, :146-150):
+ *                     pos_out[r] = wrap( pos[r] + agg_{e->r} clip(r_ij * [tanh](t_e), +-100) )
+ * backward, two phases around the edge-MLP backward:  dfeats == NULL -> dt[p];  dfeats given -> dre (per-edge
+ * dL/dr_ij stored at the ORIGINAL edge id) and dpos_in (identity + receiver end); eqnn_egnn_sender_acc adds the
+ * sender end from the sender-sorted CSR.  cell / cell_inv: HOST pointers to 9 floats or NULL.                  */
+int eqnn_egnn_geom_fwd(const float* pos, int ld_pos, int n_nodes, const int32_t* rowptr, const int32_t* src,
+                       const float* cell, const float* cell_inv, int n_rb, double r_max, float* rij4, float* feats,
+                       eqnn_stream_t stream);
+int eqnn_egnn_coord_fwd(const float* rij4, const float* t, int use_tanh, int agg, const int32_t* rowptr, int n_nodes,
+                        const float* pos, int ld_pos, const float* cell, const float* cell_inv, float* pos_out,
+                        int ld_out, eqnn_stream_t stream);
+int eqnn_egnn_coord_bwd(const float* rij4, const float* t, int use_tanh, int agg, const int32_t* rowptr,
+                        const int32_t* perm, int n_nodes, const float* dpos_out, int n_rb, double r_max,
+                        const float* dfeats, float* dt, float* dre, float* dpos_in, eqnn_stream_t stream);
+int eqnn_egnn_sender_acc(const float* dre, const int32_t* rowptr_s, const int32_t* perm_s, int n_nodes, float* dpos,
+                         eqnn_stream_t stream);
+/* y[n] = sum_m x[m, n] for tall x (bias gradients of the edge MLPs): two-stage, fixed order */
+size_t eqnn_colsum_workspace_bytes(int N);
+int eqnn_colsum_tall(const float* x, int64_t M, int N, float* y, void* ws, size_t ws_bytes, eqnn_stream_t stream);
+
 /* ---- parameter plumbing ----------------------------------------------------------------
  * dst[t] = idx[t] < 0 ? 0 : scale[t] * params[idx[t]]     (Linear -> dense matrix, live columns)
  * grads[pidx[j]] = sum_{t in [ptr[j], ptr[j+1])} scale_t[t] * ddst[tidx[t]]               */

@@ -164,6 +164,49 @@ def test_tensor_core_3xtf32_weight_gradient(case, E):
     assert _rel(outs[0], want) < 3e-6
 
 
+def test_tensor_core_egnn_shapes():
+    """K = 32 with bias epilogue, N = 32 data-gradient, M = 32 weight-gradient, N = 1 last layer (EGNN edge MLPs)."""
+    from eqnn_jax_b200.nequip import _mm
+    g = torch.Generator().manual_seed(9)
+    E = 70016
+    F = torch.randn(E, 32, generator=g, dtype=torch.float64)
+    K0 = torch.randn(32, 128, generator=g, dtype=torch.float64)
+    b0 = torch.randn(128, generator=g, dtype=torch.float64)
+    dZ = torch.randn(E, 128, generator=g, dtype=torch.float64)
+    Z = torch.empty(E, 128).cuda()
+    _mm(E, 128, 32, 1.0, F.float().cuda(), 0, 32, K0.float().cuda(), 0, 128, Z, 0, 128, epi=1, aux=b0.float().cuda(),
+        tf32x3=True)
+    assert _rel(Z, F @ K0 + b0) < 3e-6
+    Z1 = (torch.randn(E, 128, generator=g, dtype=torch.float64) * 2)
+    Z2 = torch.empty(E, 128).cuda()
+    _mm(E, 128, 128, 1.0, Z1.float().cuda(), 0, 128, K0.float().cuda().new_tensor(torch.randn(128, 128, generator=g)), 0,
+        128, Z2, 0, 128, pro=1, pro_scale=1.0, epi=1, aux=b0.float().cuda(), tf32x3=True)
+    dF = torch.empty(E, 32).cuda()
+    _mm(E, 32, 128, 1.0, dZ.float().cuda(), 0, 128, K0.float().cuda(), 0, 128, dF, 0, 32, tb=True, tf32x3=True)
+    assert _rel(dF, dZ @ K0.t()) < 3e-6
+    dK = torch.empty(32, 128).cuda()
+    _mm(32, 128, E, 1.0, F.float().cuda(), 0, 32, dZ.float().cuda(), 0, 128, dK, 0, 128, ta=True, tf32x3=True)
+    assert _rel(dK, F.t() @ dZ) < 3e-6
+    kl = torch.randn(128, 1, generator=g, dtype=torch.float64)
+    t = torch.empty(E).cuda()
+    _mm(E, 1, 128, 1.0, Z1.float().cuda(), 0, 128, kl.float().cuda(), 0, 1, t, 0, E, tc=True, pro=1, pro_scale=1.0,
+        tf32x3=True)
+    assert _rel(t, (gelu(Z1) @ kl)[:, 0]) < 3e-6
+    dt = torch.randn(E, generator=g, dtype=torch.float64)
+    dkl = torch.empty(128, 1).cuda()
+    _mm(128, 1, E, 1.0, Z1.float().cuda(), 0, 128, dt.float().cuda(), 0, E, dkl, 0, 1, ta=True, tb=True, pro=1,
+        pro_scale=1.0, tf32x3=True)
+    assert _rel(dkl, gelu(Z1).t() @ dt[:, None]) < 3e-6
+    dU = torch.empty(E, 128).cuda()
+    _mm(E, 128, 1, 1.0, dt.float().cuda(), 0, E, kl.float().cuda(), 0, 1, dU, 0, 128, ta=True, tb=True, epi=2,
+        aux=Z1.float().cuda(), ld_aux=128, epi_scale=1.0, tf32x3=True)
+    assert _rel(dU, dt[:, None] * kl.t() * gelu_grad(Z1)) < 3e-6
+    y = torch.empty(128).cuda()
+    from eqnn_jax_b200 import ops
+    ops.colsum_tall(dZ.float().cuda(), E, 128, y)
+    assert _rel(y, dZ.sum(0)) < 1e-5
+
+
 @pytest.mark.parametrize("case", ["fwd64", "fwd128", "dgrad128", "last16", "dgrad_last"])
 @pytest.mark.parametrize("M", [4096, 70001])
 def test_tensor_core_3xtf32_gemm_matches_fp64(case, M):

@@ -105,6 +105,28 @@ def test_param_counts():
     assert NQ.count_params(NQ.init_params(dataclasses.replace(cfg2, l_max=3), IRREPS_IN)) == 443_062
 
 
+def test_egnn_param_count_matches_notebook():
+    # notebooks/examples.ipynb cells 14-15: EGNN(positions_only=True, n_outputs=2, n_layers=4, 64 Bessel, tanh_out) -> 441778
+    from oracle import egnn_ref as EG
+    cfg = EG.EGNNConfig(positions_only=True, n_outputs=2, n_layers=4, n_radial_basis=64, r_max=0.6, tanh_out=True)
+    assert NQ.count_params(EG.init_params(cfg, 3)) == 441_778
+    from eqnn_jax_b200.egnn import EGNN
+    m = EGNN(positions_only=True, n_outputs=2, n_layers=4, n_radial_basis=64, r_max=0.6, tanh_out=True)
+    assert m._layout()[3] == 441_778 - 3 * (128 * 128 + 128)      # soft-edge MLPs (phi_a) are not built on the GPU path
+    tree = EG.init_params(EG.EGNNConfig(positions_only=True, soft_edges=False, n_outputs=2), 3)
+    m2 = EGNN(positions_only=True, soft_edges=False, n_outputs=2)
+    flat = {}
+
+    def walk(d, pre=()):
+        for k, v in d.items():
+            if isinstance(v, dict):
+                walk(v, pre + (k,))
+            else:
+                flat[pre + (k,)] = tuple(np.shape(v))
+    walk(tree)
+    assert {p: s for p, s, _ in m2._layout()[0]} == flat
+
+
 def test_normalize_constants():
     # SURVEY.md A.6 (grid values)
     assert E.normalization_constant("gelu") == pytest.approx(0.652059099, abs=2e-8)
