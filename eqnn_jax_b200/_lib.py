@@ -53,6 +53,8 @@ SIGNATURES: Dict[str, tuple] = {
     "eqnn_egnn_coord_fwd": (_i, [_p, _p, _i, _i, _p, _i, _p, _i, _p, _p, _p, _i, _p]),
     "eqnn_egnn_coord_bwd": (_i, [_p, _p, _i, _i, _p, _p, _i, _p, _i, _d, _p, _p, _p, _p, _p]),
     "eqnn_egnn_sender_acc": (_i, [_p, _p, _p, _i, _p, _p]),
+    "eqnn_softgate_fwd": (_i, [_p, _p, _i64, _p, _p]),
+    "eqnn_softgate_bwd": (_i, [_p, _p, _p, _i64, _p, _p, _p]),
     "eqnn_colsum_workspace_bytes": (_sz, [_i]),
     "eqnn_colsum_tall": (_i, [_p, _i64, _i, _p, _p, _sz, _p]),
     "eqnn_pool_fwd": (_i, [_p, _i, _i, _i, _i, _p, _p]),

@@ -238,6 +238,27 @@ __global__ void colsum_final_kernel(const float* __restrict__ partial, int n_par
   y[c] = s;
 }
 
+__global__ void softgate_fwd_kernel(const float4* __restrict__ z, const float4* __restrict__ za, int64_t n4,
+                                    float4* __restrict__ m) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 a = z[i], b = za[i];
+  m[i] = make_float4(gelu_tanh(a.x) * sigmoid_acc(b.x), gelu_tanh(a.y) * sigmoid_acc(b.y),
+                     gelu_tanh(a.z) * sigmoid_acc(b.z), gelu_tanh(a.w) * sigmoid_acc(b.w));
+}
+
+__global__ void softgate_bwd_kernel(const float4* __restrict__ z, const float4* __restrict__ za,
+                                    const float4* __restrict__ dm, int64_t n4, float4* __restrict__ dza,
+                                    float4* __restrict__ g1) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 a = z[i], b = za[i], d = dm[i];
+  const float s0 = sigmoid_acc(b.x), s1 = sigmoid_acc(b.y), s2 = sigmoid_acc(b.z), s3 = sigmoid_acc(b.w);
+  dza[i] = make_float4(d.x * gelu_tanh(a.x) * s0 * (1.f - s0), d.y * gelu_tanh(a.y) * s1 * (1.f - s1),
+                       d.z * gelu_tanh(a.z) * s2 * (1.f - s2), d.w * gelu_tanh(a.w) * s3 * (1.f - s3));
+  g1[i] = make_float4(d.x * s0, d.y * s1, d.z * s2, d.w * s3);
+}
+
 int make_cell(Cell3& cl, const float* cell, const float* cell_inv) {
   cl.pbc = (cell != nullptr) ? 1 : 0;
   cl.diag = 1;
@@ -308,6 +329,26 @@ extern "C" int eqnn_egnn_sender_acc(const float* dre, const int32_t* rowptr_s, c
   if (n_nodes <= 0) return EQNN_OK;
   egnn_sender_acc_kernel<<<(unsigned)ceil_div64(n_nodes, 256), 256, 0, as_stream(stream)>>>(
       reinterpret_cast<const float4*>(dre), rowptr_s, perm_s, n_nodes, dpos);
+  EQNN_CHECK_LAUNCH();
+  return EQNN_OK;
+}
+
+extern "C" int eqnn_softgate_fwd(const float* z, const float* za, int64_t n, float* m, eqnn_stream_t stream) {
+  EQNN_CHECK_ARG(z && za && m && n >= 0 && n % 4 == 0, "softgate_fwd: bad argument (n must be a multiple of 4)");
+  if (n == 0) return EQNN_OK;
+  softgate_fwd_kernel<<<(unsigned)ceil_div64(n / 4, 256), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const float4*>(z), reinterpret_cast<const float4*>(za), n / 4, reinterpret_cast<float4*>(m));
+  EQNN_CHECK_LAUNCH();
+  return EQNN_OK;
+}
+
+extern "C" int eqnn_softgate_bwd(const float* z, const float* za, const float* dm, int64_t n, float* dza, float* g1,
+                                 eqnn_stream_t stream) {
+  EQNN_CHECK_ARG(z && za && dm && dza && g1 && n >= 0 && n % 4 == 0, "softgate_bwd: bad argument");
+  if (n == 0) return EQNN_OK;
+  softgate_bwd_kernel<<<(unsigned)ceil_div64(n / 4, 256), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const float4*>(z), reinterpret_cast<const float4*>(za), reinterpret_cast<const float4*>(dm), n / 4,
+      reinterpret_cast<float4*>(dza), reinterpret_cast<float4*>(g1));
   EQNN_CHECK_LAUNCH();
   return EQNN_OK;
 }

@@ -36,7 +36,8 @@ __device__ __forceinline__ void store_out(const GemmP& p, int64_t m, int64_t n, 
   if (p.epi == 1) v += p.aux[n];
   else if (p.epi == 2) v *= gelu_tanh_grad(p.aux[m * p.ld_aux + n]) * p.epi_scale;
   float* c = p.C + m * p.scm + n * p.scn;
-  if (p.accumulate) v += *c;
+  if (p.epi == 3) v = (v + *c) * gelu_tanh_grad(p.aux[m * p.ld_aux + n]) * p.epi_scale;
+  else if (p.accumulate) v += *c;
   *c = v;
 }
 
@@ -355,7 +356,7 @@ extern "C" int eqnn_gemm_f32(int64_t M, int64_t N, int64_t K, float alpha, const
   if (M == 0 || N == 0) return EQNN_OK;
   EQNN_CHECK_ARG(A && B && C, "gemm: null pointer");
   EQNN_CHECK_ARG(pro == 0 || pro == 1, "gemm: unknown prologue");
-  EQNN_CHECK_ARG(epi >= 0 && epi <= 2, "gemm: unknown epilogue");
+  EQNN_CHECK_ARG(epi >= 0 && epi <= 3, "gemm: unknown epilogue");
   EQNN_CHECK_ARG(epi == 0 || aux, "gemm: epilogue needs aux");
   EQNN_CHECK_ARG(ceil_div64(N, 16) <= 65535, "gemm: N too large for grid.y");
   if (flags & EQNN_GEMM_TF32X3) {

@@ -71,6 +71,7 @@ struct RowCfg {
 
 // AMODE 0: A row-major (k contiguous), K % 32 == 0.  AMODE 1: A column-major (m contiguous), K <= 32.
 // PRO 1: A := gelu_tanh(A) * pro_scale.  EPI 1: C += bias (aux[n]).  EPI 2: C *= gelu_tanh'(aux) * epi_scale.
+// EPI 3: C = (alpha*acc + C_old) * gelu_tanh'(aux) * epi_scale  (two gradient branches meeting at one activation).
 // CMODE 0: C row-major [M][ldc]; CMODE 1: C column-major [n][ldc] (only the first n_valid columns).
 template <int K, int N, int AMODE, int PRO, int EPI, int CMODE>
 __global__ void __launch_bounds__(RG_THREADS, 1) tc_rowgemm_kernel(const RowGemmP p) {
@@ -233,8 +234,8 @@ __global__ void __launch_bounds__(RG_THREADS, 1) tc_rowgemm_kernel(const RowGemm
         constexpr int NB16 = (N / 2) / 16;               // 16-column batches per warp
         const int col0 = half * (N / 2);
         float ax[16], an[16];
-        const float* arow = (EPI == 2 && live) ? p.aux + m * p.ld_aux + col0 : nullptr;
-        if (EPI == 2 && live) {
+        const float* arow = ((EPI == 2 || EPI == 3) && live) ? p.aux + m * p.ld_aux + col0 : nullptr;
+        if ((EPI == 2 || EPI == 3) && live) {
           ldg256(arow, ax);
           ldg256(arow + 8, ax + 8);
         }
@@ -244,7 +245,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) tc_rowgemm_kernel(const RowGemm
         for (int cb = 0; cb < NB16; ++cb) {
           float v[16];
           tmem_ld16(taddr + col0 + cb * 16, v);
-          if (EPI == 2 && live && cb + 1 < NB16) {
+          if ((EPI == 2 || EPI == 3) && live && cb + 1 < NB16) {
             ldg256(arow + (cb + 1) * 16, an);
             ldg256(arow + (cb + 1) * 16 + 8, an + 8);
           }
@@ -254,18 +255,23 @@ __global__ void __launch_bounds__(RG_THREADS, 1) tc_rowgemm_kernel(const RowGemm
             mbar_arrive(t_empty(ab));
           }
           if (live) {
-            float o[16];
+            float o[16], cold[16];
+            if (EPI == 3) {
+              ldg256(p.C + m * p.ldc + col0 + cb * 16, cold);
+              ldg256(p.C + m * p.ldc + col0 + cb * 16 + 8, cold + 8);
+            }
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               o[j] = p.alpha * v[j];
+              if (EPI == 3) o[j] += cold[j];                                  // second gradient branch already in C
               if (EPI == 1) o[j] += __ldg(p.aux + col0 + cb * 16 + j);      // bias[n] (models/mlp.py Dense)
-              if (EPI == 2) o[j] *= gelu_tanh_grad(ax[j]) * p.epi_scale;
+              if (EPI == 2 || EPI == 3) o[j] *= gelu_tanh_grad(ax[j]) * p.epi_scale;
             }
             float* crow = p.C + m * p.ldc + col0 + cb * 16;
             stg256(crow, o);
             stg256(crow + 8, o + 8);
           }
-          if (EPI == 2 && cb + 1 < NB16) {
+          if ((EPI == 2 || EPI == 3) && cb + 1 < NB16) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) ax[j] = an[j];
           }
@@ -649,14 +655,14 @@ int eqnn_tc_rowgemm_try(int64_t M, int64_t N, int64_t K, float alpha, const floa
   const bool a_row = (sak == 1 && sam % 4 == 0 && al16(A));
   auto al32 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 31) == 0; };
   const bool c_row = (scn == 1 && scm % 8 == 0 && al32(C));          // 256-bit row stores
-  const bool aux_ok = (epi != 2) || (ld_aux % 8 == 0 && al32(aux));  // 256-bit row loads
+  const bool aux_ok = (epi != 2 && epi != 3) || (ld_aux % 8 == 0 && al32(aux));  // 256-bit row loads
   if (N == 128 && a_row && c_row && aux_ok && (K == 128 || K == 64 || K == 32)) {
     p.lda = sam; p.ldc = scm;
 #define EQNN_TC_CASE(KK, PR, EP)                                                              \
   if (K == KK && pro == PR && epi == EP) { rc = launch_rowgemm<KK, 128, 0, PR, EP, 0>(p, st); return rc ? -rc : 1; }
     EQNN_TC_CASE(64, 0, 0) EQNN_TC_CASE(128, 1, 0) EQNN_TC_CASE(128, 0, 2) EQNN_TC_CASE(128, 0, 0)
     EQNN_TC_CASE(64, 1, 0) EQNN_TC_CASE(128, 1, 2) EQNN_TC_CASE(64, 0, 2)
-    EQNN_TC_CASE(32, 0, 0) EQNN_TC_CASE(32, 0, 1) EQNN_TC_CASE(64, 0, 1) EQNN_TC_CASE(128, 0, 1) EQNN_TC_CASE(128, 1, 1)
+    EQNN_TC_CASE(128, 0, 3) EQNN_TC_CASE(32, 0, 0) EQNN_TC_CASE(32, 0, 1) EQNN_TC_CASE(64, 0, 1) EQNN_TC_CASE(128, 0, 1) EQNN_TC_CASE(128, 1, 1)
 #undef EQNN_TC_CASE
     return 0;
   }

@@ -11,8 +11,8 @@ Per message-passing step, edges in receiver-sorted order:
     t   = Dense_1(phi_x(m))   tcgen05 3xTF32 GEMMs                      egnn.py:70-79,107
     x'  = wrap(x + agg clip(r_ij t))   eqnn_egnn_coord_fwd              egnn.py:110-114,146-150 + jraph segment reduce
 With 3-d nodes the aggregated messages m_i are never read (egnn.py:143-150), so they are not aggregated
-(XLA removes that dead reduction under jit as well).  Not built yet: scalar/velocity node attributes,
-soft_edges=True, globals, max aggregation -> NotImplementedError, never a silent fallback.
+(XLA removes that dead reduction under jit as well).  soft_edges (egnn.py:101-105) is supported.  Not built yet:
+scalar/velocity node attributes, globals, max aggregation -> NotImplementedError, never a silent fallback.
 """
 from __future__ import annotations
 
@@ -54,8 +54,6 @@ class EGNN:
     def _check(self, n_feat: int) -> None:
         if not self.positions_only or n_feat != 3:
             raise NotImplementedError("B200 EGNN covers positions_only=True on 3-d nodes (the benchmarked configuration)")
-        if self.soft_edges:
-            raise NotImplementedError("soft_edges=True is not built on the B200 path yet")
         if self.activation != "gelu":
             raise NotImplementedError("only activation='gelu' has a B200 kernel on this path")
         if self.message_passing_agg not in ("sum", "mean") or self.readout_agg not in ("sum", "mean"):
@@ -90,7 +88,10 @@ class EGNN:
                                     add((f"MLP_{mi}", f"Dense_{l}", "bias"), (d,)), d))
             mi += 1
             st["k_last"] = add((f"Dense_{s}", "kernel"), (d, 1))
-            mi += 1   # phi_a is constructed (takes a name) but owns parameters only with soft_edges
+            # phi_a is constructed in every step (takes the name) but owns parameters only with soft_edges
+            st["phi_a"] = (add((f"MLP_{mi}", "Dense_0", "kernel"), (d, d)),
+                           add((f"MLP_{mi}", "Dense_0", "bias"), (d,))) if self.soft_edges else None
+            mi += 1
             steps.append(st)
         readout = []
         if self.task == "graph":
@@ -167,7 +168,18 @@ class EGNN:
             feats = torch.empty((Et, nf), **f32)
             ops.egnn_geom_fwd(pos, 3, Nt, rowptr, src, cell, cinv, self.n_radial_basis, self.r_max, rij4, feats)
             acts, a, pro = [], feats, 0
-            for (ko, bo, fan) in st["phi_e"] + st["phi_x"]:
+            Za = Mg = None
+            nE = len(st["phi_e"])
+            for li, (ko, bo, fan) in enumerate(st["phi_e"] + st["phi_x"]):
+                if li == nE and st["phi_a"] is not None:
+                    # soft edges (egnn.py:101-105): m <- m * sigmoid(phi_a(m)), m = gelu(Z_L)
+                    ka, ba = st["phi_a"]
+                    Za = torch.empty((Et, d), **f32)
+                    _mm(Et, d, d, 1.0, a, 0, d, theta, ka, d, Za, 0, d, pro=1, pro_scale=1.0, epi=1, aux=theta,
+                        aux_off=ba, tag="egnn_mlp_fwd", tf32x3=tc)
+                    Mg = torch.empty((Et, d), **f32)
+                    ops.softgate_fwd(a, Za, Mg)
+                    a, pro = Mg, 0
                 Z = torch.empty((Et, d), **f32)
                 _mm(Et, d, fan, 1.0, a, 0, fan, theta, ko, d, Z, 0, d, pro=pro, pro_scale=1.0, epi=1, aux=theta,
                     aux_off=bo, tag="egnn_mlp_fwd", tf32x3=tc)
@@ -178,7 +190,7 @@ class EGNN:
                 tag="egnn_mlp_fwd", tf32x3=tc)
             pos_next = torch.empty((Nt, 3), **f32)
             ops.egnn_coord_fwd(rij4, t, self.tanh_out, agg, rowptr, Nt, pos, 3, cell, cinv, pos_next, 3)
-            saved["steps"].append(dict(rij4=rij4, feats=feats, acts=acts, t=t))
+            saved["steps"].append(dict(rij4=rij4, feats=feats, acts=acts, t=t, Za=Za, Mg=Mg))
             pos = pos_next
         if self.task == "node":
             return pos.view(B, N, 3), saved
@@ -239,12 +251,31 @@ class EGNN:
             _mm(Et, d, 1, 1.0, dt, 0, Et, theta, st["k_last"], 1, dZ, 0, d, ta=True, tb=True, epi=2, aux=last, ld_aux=d,
                 epi_scale=1.0, tag="egnn_mlp_bwd", tf32x3=tc)
             dfeats = None
+            nE = len(st["phi_e"])
             for l in range(len(layers) - 1, -1, -1):
                 ko, bo, fan = layers[l]
                 a_prev, pro = (acts[l - 1], 1) if l > 0 else (feats, 0)
+                gated = (l == nE and st["phi_a"] is not None)      # this layer's input is the soft-gated message
+                if gated:
+                    a_prev, pro = sv["Mg"], 0
                 _mm(fan, d, Et, 1.0, a_prev, 0, fan, dZ, 0, d, gtheta, ko, d, ta=True, pro=pro, pro_scale=1.0,
                     tag="egnn_mlp_bwd", tf32x3=tc)
                 ops.colsum_tall(dZ, Et, d, gtheta, y_off=bo)
+                if gated:
+                    ka, ba = st["phi_a"]
+                    ZL, Za = acts[l - 1], sv["Za"]
+                    dM = torch.empty((Et, d), **f32)
+                    _mm(Et, d, d, 1.0, dZ, 0, d, theta, ko, d, dM, 0, d, tb=True, tag="egnn_mlp_bwd", tf32x3=tc)
+                    dZa = torch.empty((Et, d), **f32)
+                    ops.softgate_bwd(ZL, Za, dM, dZa, dM)           # dM <- dM * sigmoid(Za)  (first branch into Z_L)
+                    _mm(d, d, Et, 1.0, ZL, 0, d, dZa, 0, d, gtheta, ka, d, ta=True, pro=1, pro_scale=1.0,
+                        tag="egnn_mlp_bwd", tf32x3=tc)
+                    ops.colsum_tall(dZa, Et, d, gtheta, y_off=ba)
+                    # dZ_L = (dZa @ Ka^T + dM) * gelu'(Z_L): second branch accumulated in the epilogue (EPI 3)
+                    _mm(Et, d, d, 1.0, dZa, 0, d, theta, ka, d, dM, 0, d, tb=True, epi=3, aux=ZL, ld_aux=d, epi_scale=1.0,
+                        tag="egnn_mlp_bwd", tf32x3=tc)
+                    dZ = dM
+                    continue
                 if l > 0:
                     dZp = torch.empty((Et, fan), **f32)
                     _mm(Et, fan, d, 1.0, dZ, 0, d, theta, ko, d, dZp, 0, fan, tb=True, epi=2, aux=acts[l - 1], ld_aux=fan,

@@ -285,6 +285,14 @@ def egnn_sender_acc(dre, rowptr_s, perm_s, n_nodes, dpos):
           "egnn_sender_acc")
 
 
+def softgate_fwd(z, za, m):
+    check(lib().eqnn_softgate_fwd(_ptr(z), _ptr(za), z.numel(), _ptr(m), _stream()), "softgate_fwd")
+
+
+def softgate_bwd(z, za, dm, dza, g1):
+    check(lib().eqnn_softgate_bwd(_ptr(z), _ptr(za), _ptr(dm), z.numel(), _ptr(dza), _ptr(g1), _stream()), "softgate_bwd")
+
+
 _COLSUM_WS = GemmWorkspace()
 
 

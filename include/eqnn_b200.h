@@ -139,6 +139,7 @@ int eqnn_node_tp_bwd(int tp_id, const float* x, const float* y, const float* gT,
  * irreps Linear layers lowered to dense matrices (:43,85,162,197) and models/mlp.py.
  *   pro: 0 none | 1 A := gelu_tanh(A) * pro_scale
  *   epi: 0 none | 1 += bias[n] (aux = bias) | 2 *= gelu_tanh'(aux[m*ld_aux+n]) * epi_scale
+ *        | 3 C = (alpha*acc + C) * gelu_tanh'(aux[m*ld_aux+n]) * epi_scale
  *   flags: EQNN_GEMM_ACCUMULATE adds to C.  Large-K problems are split over CTAs
  *   through `ws` (eqnn_gemm_workspace_bytes) and reduced in a fixed order.          */
 /*   EQNN_GEMM_TF32X3: large-M problems with K, N <= 128 run on the tensor cores (tcgen05, TMEM) with every
@@ -204,6 +205,11 @@ int eqnn_egnn_coord_bwd(const float* rij4, const float* t, int use_tanh, int agg
                         const float* dfeats, float* dt, float* dre, float* dpos_in, eqnn_stream_t stream);
 int eqnn_egnn_sender_acc(const float* dre, const int32_t* rowptr_s, const int32_t* perm_s, int n_nodes, float* dpos,
                          eqnn_stream_t stream);
+/* soft edges (egnn.py:101-105): m = gelu(z) * sigmoid(za); backward: dza = dm * gelu(z) * sigmoid'(za),
+ * g1 = dm * sigmoid(za)  (g1 may alias dm) */
+int eqnn_softgate_fwd(const float* z, const float* za, int64_t n, float* m, eqnn_stream_t stream);
+int eqnn_softgate_bwd(const float* z, const float* za, const float* dm, int64_t n, float* dza, float* g1,
+                      eqnn_stream_t stream);
 /* y[n] = sum_m x[m, n] for tall x (bias gradients of the edge MLPs): two-stage, fixed order */
 size_t eqnn_colsum_workspace_bytes(int N);
 int eqnn_colsum_tall(const float* x, int64_t M, int N, float* y, void* ws, size_t ws_bytes, eqnn_stream_t stream);

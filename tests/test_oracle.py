@@ -112,7 +112,7 @@ def test_egnn_param_count_matches_notebook():
     assert NQ.count_params(EG.init_params(cfg, 3)) == 441_778
     from eqnn_jax_b200.egnn import EGNN
     m = EGNN(positions_only=True, n_outputs=2, n_layers=4, n_radial_basis=64, r_max=0.6, tanh_out=True)
-    assert m._layout()[3] == 441_778 - 3 * (128 * 128 + 128)      # soft-edge MLPs (phi_a) are not built on the GPU path
+    assert m._layout()[3] == 441_778
     tree = EG.init_params(EG.EGNNConfig(positions_only=True, soft_edges=False, n_outputs=2), 3)
     m2 = EGNN(positions_only=True, soft_edges=False, n_outputs=2)
     flat = {}
