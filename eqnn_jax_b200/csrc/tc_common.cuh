@@ -39,7 +39,25 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 
 // generic-proxy shared-memory writes -> visible to the async proxy (tensor core reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
+#ifndef EQNN_EXPERIMENT_NOFENCE
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
+}
+
+// ---- bulk asynchronous copies (TMA, non-tensor form): global -> shared, completion counted on an mbarrier ----
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// dst (shared), src (global) and bytes are multiples of 16
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+// contiguous block -> L2 (no data returned to the SM); addr and bytes multiples of 16
+__device__ __forceinline__ void l2_prefetch_bulk(const void* gptr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
 }
 
 // ---- tensor memory ----------------------------------------------------------------------
@@ -135,6 +153,88 @@ __device__ __forceinline__ void stg256(float* p, const float* v) {
 __device__ __forceinline__ void split_tf32(float a, float& hi, float& lo) {
   hi = __uint_as_float(__float_as_uint(a) & 0xffffe000u);
   lo = a - hi;
+}
+
+// ---- packed fp32x2 arithmetic (FFMA2 / FMUL2 / FADD2: one issue slot for two lanes' worth of fp32) ----------
+// The producer and epilogue warps of the GEMM kernels are issue-bound, so their element-wise math is written on
+// register pairs.  ex2/rcp stay scalar (MUFU).
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float a, float b) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float rcp_ftz(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// sigmoid(2*k0*(x + k1*x^3)) for a pair: 1 / (1 + 2^(x*(C0 + C1*x^2))), C0 = -2*k0*log2(e), C1 = C0*k1
+__device__ __forceinline__ f32x2 gelu_sigmoid2(f32x2 x, f32x2 xx) {
+  constexpr float C0 = -2.0f * 0.7978845608028654f * 1.4426950408889634f, C1 = C0 * 0.044715f;
+  const f32x2 t = mul2(fma2(xx, pk2(C1, C1), pk2(C0, C0)), x);
+  float t0, t1;
+  upk2(t, t0, t1);
+  const f32x2 d = add2(pk2(ex2_ftz(t0), ex2_ftz(t1)), pk2(1.f, 1.f));
+  float d0, d1;
+  upk2(d, d0, d1);
+  return pk2(rcp_ftz(d0), rcp_ftz(d1));
+}
+// gelu_tanh(x) * scale for a pair (same function as common.cuh gelu_tanh)
+__device__ __forceinline__ f32x2 gelu2(f32x2 x, f32x2 scale) {
+  return mul2(mul2(x, scale), gelu_sigmoid2(x, mul2(x, x)));
+}
+// d/dx gelu_tanh(x) for a pair: s + x*s*(1-s)*2*k0*(1 + 3*k1*x^2)
+__device__ __forceinline__ f32x2 gelu_grad2(f32x2 x) {
+  constexpr float D0 = 2.0f * 0.7978845608028654f, D1 = D0 * 3.0f * 0.044715f;
+  const f32x2 xx = mul2(x, x);
+  const f32x2 s = gelu_sigmoid2(x, xx);
+  const f32x2 w = mul2(x, fma2(xx, pk2(D1, D1), pk2(D0, D0)));
+  const f32x2 q = mul2(s, fma2(s, pk2(-1.f, -1.f), pk2(1.f, 1.f)));
+  return fma2(q, w, s);
+}
+// (hi, lo) split of a pair: hi = tf32-representable head, lo = exact remainder
+__device__ __forceinline__ void split2(f32x2 a, f32x2& hi, f32x2& lo) {
+  hi = a & 0xffffe000ffffe000ull;
+  lo = fma2(hi, pk2(-1.f, -1.f), a);
+}
+// float4 -> optional gelu*scale -> (hi, lo) float4s
+template <bool ACT>
+__device__ __forceinline__ void act_split4(const float4& v, float scale, float4& hi, float4& lo) {
+  f32x2 a = pk2(v.x, v.y), b = pk2(v.z, v.w);
+  if (ACT) {
+    const f32x2 sc = pk2(scale, scale);
+    a = gelu2(a, sc);
+    b = gelu2(b, sc);
+  }
+  f32x2 ah, al, bh, bl;
+  split2(a, ah, al);
+  split2(b, bh, bl);
+  upk2(ah, hi.x, hi.y);
+  upk2(bh, hi.z, hi.w);
+  upk2(al, lo.x, lo.y);
+  upk2(bl, lo.z, lo.w);
 }
 
 // byte offset of element (row, 16-byte chunk c) inside a 128-byte-swizzled tile whose rows are 128 bytes

@@ -18,6 +18,7 @@
 //   B (the <=128x128 weight matrix) is split once per CTA and stays resident in shared memory.
 #include "common.cuh"
 #include "tc_common.cuh"
+#include <type_traits>
 
 namespace {
 
@@ -50,20 +51,24 @@ struct RowGemmP {
 constexpr int RG_PROD_WARPS = 16;
 constexpr int RG_PT = RG_PROD_WARPS * 32;                          // 512 producer threads
 constexpr int RG_THREADS = (EPI_WARPS + 1 + RG_PROD_WARPS) * 32;   // 800
-constexpr int RG_NSTAGE = 3;
+#ifndef RG_L2_PREFETCH
+#define RG_L2_PREFETCH 1
+#endif
 constexpr int RG_DEPTH = 3;                                        // chunks of loads in flight per producer thread
-constexpr uint32_t STG_ROW = 20;                                   // epilogue staging row stride (floats): 16 + 4 pad
-constexpr uint32_t STG_WARP = 32 * STG_ROW * 4;                    // 2560 B per epilogue warp
+constexpr uint32_t STG_WARP = 32 * 128;                            // epilogue staging: 32 rows x 128 B per warp
 
-template <int K, int N>
+template <int K, int N, bool STAGED = true>
 struct RowCfg {
   static constexpr int NCH = (K + 31) / 32;
   static constexpr int KSTEPS = (K < 32 ? K : 32) / 8;
   static constexpr uint32_t B_ATOM = N * 128;                 // one 32-wide k slab of B: N rows x 128 B
   static constexpr uint32_t B_HALF = NCH * B_ATOM;
   static constexpr uint32_t B_BYTES = 2 * B_HALF;
-  static constexpr uint32_t STG_BYTES = 0;                   // (epilogue needs no staging: 256-bit row accesses)
-  static constexpr uint32_t SMEM = B_BYTES + RG_NSTAGE * STAGE_BYTES + STG_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  // wide outputs are transposed through shared memory so that global stores cover whole 128-byte lines
+  static constexpr uint32_t STG_BYTES = (N >= 64 && STAGED) ? EPI_WARPS * STG_WARP : 0;
+  static constexpr uint32_t FIXED = B_BYTES + STG_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int NSTAGE = (FIXED + 3 * STAGE_BYTES <= SMEM_LIMIT) ? 3 : 2;   // A-operand ring depth
+  static constexpr uint32_t SMEM = FIXED + NSTAGE * STAGE_BYTES;
   static constexpr uint32_t ACC_STRIDE = N < 32 ? 32 : N;     // TMEM columns between the two accumulators
   static constexpr uint32_t TMEM_COLS = (2 * ACC_STRIDE <= 64) ? 64 : (2 * ACC_STRIDE <= 128 ? 128 : 256);
   static_assert(SMEM <= SMEM_LIMIT, "shared memory budget exceeded");
@@ -75,18 +80,18 @@ struct RowCfg {
 // CMODE 0: C row-major [M][ldc]; CMODE 1: C column-major [n][ldc] (only the first n_valid columns).
 template <int K, int N, int AMODE, int PRO, int EPI, int CMODE>
 __global__ void __launch_bounds__(RG_THREADS, 1) tc_rowgemm_kernel(const RowGemmP p) {
-  using Cfg = RowCfg<K, N>;
+  using Cfg = RowCfg<K, N, AMODE == 0>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sB_hi = base, sB_lo = base + Cfg::B_HALF;
   const uint32_t sA = base + Cfg::B_BYTES;
-  const uint32_t sStg = sA + RG_NSTAGE * STAGE_BYTES;
+  const uint32_t sStg = sA + Cfg::NSTAGE * STAGE_BYTES;
   const uint32_t bars = sStg + Cfg::STG_BYTES;
   auto a_full = [&](int s) { return bars + 8u * s; };
-  auto a_empty = [&](int s) { return bars + 8u * (RG_NSTAGE + s); };
-  auto t_full = [&](int b) { return bars + 8u * (2 * RG_NSTAGE + b); };
-  auto t_empty = [&](int b) { return bars + 8u * (2 * RG_NSTAGE + 2 + b); };
-  const uint32_t tmem_slot = bars + 8u * (2 * RG_NSTAGE + 4);
+  auto a_empty = [&](int s) { return bars + 8u * (Cfg::NSTAGE + s); };
+  auto t_full = [&](int b) { return bars + 8u * (2 * Cfg::NSTAGE + b); };
+  auto t_empty = [&](int b) { return bars + 8u * (2 * Cfg::NSTAGE + 2 + b); };
+  const uint32_t tmem_slot = bars + 8u * (2 * Cfg::NSTAGE + 4);
   uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -94,8 +99,8 @@ __global__ void __launch_bounds__(RG_THREADS, 1) tc_rowgemm_kernel(const RowGemm
 
   // ---- one-time setup ----
   if (tid == 0) {
-    for (int s = 0; s < RG_NSTAGE; ++s) {
-      mbar_init(a_full(s), RG_PT);
+    for (int s = 0; s < Cfg::NSTAGE; ++s) {
+      mbar_init(a_full(s), RG_PROD_WARPS);
       mbar_init(a_empty(s), 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -129,52 +134,65 @@ __global__ void __launch_bounds__(RG_THREADS, 1) tc_rowgemm_kernel(const RowGemm
     const int pt = tid - (MMA_WARP + 1) * 32;
     const uint32_t my_tiles = (blockIdx.x < n_tiles) ? (uint32_t)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0u;
     const uint32_t total = my_tiles * Cfg::NCH;
+    // this thread's two 16-byte pieces of every chunk: fixed (row, 16-byte column) and swizzled smem offset
+    int prow[2], pc4[2];
+    uint32_t poff[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int f = pt + i * RG_PT;
+      prow[i] = (AMODE == 0) ? (f >> 3) : (f & 127);
+      pc4[i] = (AMODE == 0) ? (f & 7) : (f >> 7);
+      poff[i] = sw128(prow[i], pc4[i]);
+    }
+    const int64_t tile_rows = (int64_t)gridDim.x * TILE_M;
+    const int64_t m_last = p.M - 1;
     auto issue = [&](uint32_t g, float4 (&v)[2]) {
       if (g >= total) return;
-      const int64_t m0 = ((int64_t)blockIdx.x + (int64_t)(g / Cfg::NCH) * gridDim.x) * TILE_M;
+      const int64_t m0 = (int64_t)blockIdx.x * TILE_M + (int64_t)(g / Cfg::NCH) * tile_rows;
       const int c = g % Cfg::NCH;
+      if (RG_L2_PREFETCH && AMODE == 0 && c == 0 && pt == 0) {
+        // The k-chunks of a tile visit every 512-byte row four times, microseconds apart: to DRAM that is one
+        // row activation per 128 bytes.  Pull the NEXT tile (and its aux rows) into L2 as whole contiguous blocks.
+        const int64_t mn = m0 + tile_rows;
+        if (mn < p.M) {
+          const int64_t rows = (p.M - mn < TILE_M) ? (p.M - mn) : TILE_M;
+          if (p.lda == K) l2_prefetch_bulk(p.A + mn * p.lda, (uint32_t)(rows * K * 4));
+          if ((EPI == 2 || EPI == 3) && p.ld_aux == N) l2_prefetch_bulk(p.aux + mn * p.ld_aux, (uint32_t)(rows * N * 4));
+        }
+      }
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
-        const int f = pt + i * RG_PT;
+        // rows past M (last tile only) re-read row M-1: their accumulator rows are never stored
+        const int64_t m = (m0 + prow[i] < m_last) ? (m0 + prow[i]) : m_last;
         if (AMODE == 0) {
-          const int row = f >> 3, c4 = f & 7;
-          const int64_t m = m0 + row;
-          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (m < p.M) v[i] = __ldg(reinterpret_cast<const float4*>(p.A + m * p.lda + 32 * c + 4 * c4));
+          v[i] = __ldg(reinterpret_cast<const float4*>(p.A + m * p.lda + 32 * c + 4 * pc4[i]));
         } else {
-          const int row = f & 127, c4 = f >> 7;   // c4 in 0..7
-          const int64_t m = m0 + row;
           float t[4] = {0.f, 0.f, 0.f, 0.f};
-          if (m < p.M) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-              if (4 * c4 + q < p.k_valid) t[q] = __ldg(p.A + (int64_t)(4 * c4 + q) * p.lda + m);
-          }
+          for (int q = 0; q < 4; ++q)
+            if (4 * pc4[i] + q < p.k_valid) t[q] = __ldg(p.A + (int64_t)(4 * pc4[i] + q) * p.lda + m);
           v[i] = make_float4(t[0], t[1], t[2], t[3]);
         }
       }
     };
-    auto consume = [&](uint32_t g, float4 (&v)[2]) {
-      const int s = g % RG_NSTAGE;
-      const uint32_t par = (g / RG_NSTAGE) & 1u;
-      mbar_wait(a_empty(s), par ^ 1u);
-      const uint32_t st_hi = sA + s * STAGE_BYTES - base, st_lo = st_hi + A_HALF;
+    uint32_t cs = 0, cpar = 1;                       // ring position of the next chunk to publish
+    auto consume = [&](float4 (&v)[2]) {
+      mbar_wait(a_empty(cs), cpar);
+      uint8_t* st_hi = gen_base + (sA - base) + cs * STAGE_BYTES;
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
-        const int f = pt + i * RG_PT;
-        const int row = (AMODE == 0) ? (f >> 3) : (f & 127), c4 = (AMODE == 0) ? (f & 7) : (f >> 7);
-        float x[4] = {v[i].x, v[i].y, v[i].z, v[i].w}, hi[4], lo[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          if (PRO == 1) x[q] = gelu_tanh(x[q]) * p.pro_scale;
-          split_tf32(x[q], hi[q], lo[q]);
-        }
-        const uint32_t off = sw128(row, c4);
-        *reinterpret_cast<float4*>(gen_base + st_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<float4*>(gen_base + st_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        float4 hi, lo;
+        act_split4<PRO == 1>(v[i], p.pro_scale, hi, lo);
+        *reinterpret_cast<float4*>(st_hi + poff[i]) = hi;
+        *reinterpret_cast<float4*>(st_hi + A_HALF + poff[i]) = lo;
       }
       fence_proxy_async_smem();
-      mbar_arrive(a_full(s));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_full(cs));        // one arrival per producer warp
+      if (++cs == Cfg::NSTAGE) {
+        cs = 0;
+        cpar ^= 1u;
+      }
     };
     float4 v0[2], v1[2], v2[2], v3[2];
     issue(0, v0);
@@ -182,10 +200,10 @@ __global__ void __launch_bounds__(RG_THREADS, 1) tc_rowgemm_kernel(const RowGemm
     issue(2, v2);
     for (uint32_t g = 0; g < total; g += 4) {
       issue(g + 3, v3);
-      consume(g, v0);
-      if (g + 1 < total) { issue(g + 4, v0); consume(g + 1, v1); }
-      if (g + 2 < total) { issue(g + 5, v1); consume(g + 2, v2); }
-      if (g + 3 < total) { issue(g + 6, v2); consume(g + 3, v3); }
+      consume(v0);
+      if (g + 1 < total) { issue(g + 4, v0); consume(v1); }
+      if (g + 2 < total) { issue(g + 5, v1); consume(v2); }
+      if (g + 3 < total) { issue(g + 6, v2); consume(v3); }
     }
   } else if (warp == MMA_WARP) {
     // =========================== MMA issuer ===========================
@@ -198,8 +216,8 @@ __global__ void __launch_bounds__(RG_THREADS, 1) tc_rowgemm_kernel(const RowGemm
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + ab * Cfg::ACC_STRIDE;
         for (int c = 0; c < Cfg::NCH; ++c, ++it) {
-          const int s = it % RG_NSTAGE;
-          mbar_wait(a_full(s), (it / RG_NSTAGE) & 1u);
+          const int s = it % Cfg::NSTAGE;
+          mbar_wait(a_full(s), (it / Cfg::NSTAGE) & 1u);
           tc_fence_after();
           const uint32_t a_hi = sA + s * STAGE_BYTES, a_lo = a_hi + A_HALF;
           const uint32_t b_hi = sB_hi + c * Cfg::B_ATOM, b_lo = sB_lo + c * Cfg::B_ATOM;
@@ -233,6 +251,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) tc_rowgemm_kernel(const RowGemm
       if (N >= 64) {
         constexpr int NB16 = (N / 2) / 16;               // 16-column batches per warp
         const int col0 = half * (N / 2);
+        uint8_t* stg = gen_base + (sStg - base) + warp * STG_WARP;
         float ax[16], an[16];
         const float* arow = ((EPI == 2 || EPI == 3) && live) ? p.aux + m * p.ld_aux + col0 : nullptr;
         if ((EPI == 2 || EPI == 3) && live) {
@@ -260,16 +279,38 @@ __global__ void __launch_bounds__(RG_THREADS, 1) tc_rowgemm_kernel(const RowGemm
               ldg256(p.C + m * p.ldc + col0 + cb * 16, cold);
               ldg256(p.C + m * p.ldc + col0 + cb * 16 + 8, cold + 8);
             }
+            const f32x2 al2 = pk2(p.alpha, p.alpha), es2 = pk2(p.epi_scale, p.epi_scale);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              o[j] = p.alpha * v[j];
-              if (EPI == 3) o[j] += cold[j];                                  // second gradient branch already in C
-              if (EPI == 1) o[j] += __ldg(p.aux + col0 + cb * 16 + j);      // bias[n] (models/mlp.py Dense)
-              if (EPI == 2 || EPI == 3) o[j] *= gelu_tanh_grad(ax[j]) * p.epi_scale;
+            for (int j = 0; j < 16; j += 2) {
+              f32x2 r = mul2(pk2(v[j], v[j + 1]), al2);
+              if (EPI == 3) r = add2(r, pk2(cold[j], cold[j + 1]));            // second gradient branch already in C
+              if (EPI == 1)                                                      // bias[n] (models/mlp.py Dense)
+                r = add2(r, pk2(__ldg(p.aux + col0 + cb * 16 + j), __ldg(p.aux + col0 + cb * 16 + j + 1)));
+              if (EPI == 2 || EPI == 3) r = mul2(r, mul2(gelu_grad2(pk2(ax[j], ax[j + 1])), es2));
+              upk2(r, o[j], o[j + 1]);
             }
-            float* crow = p.C + m * p.ldc + col0 + cb * 16;
-            stg256(crow, o);
-            stg256(crow + 8, o + 8);
+            if (AMODE != 0) {
+              float* crow = p.C + m * p.ldc + col0 + cb * 16;
+              stg256(crow, o);
+              stg256(crow + 8, o + 8);
+            }
+            // stage: lane = row, 16-byte chunk index XOR-swizzled by the row (conflict-free both ways)
+#pragma unroll
+            for (int j = 0; AMODE == 0 && j < 4; ++j)
+              *reinterpret_cast<float4*>(stg + lane * 128 + ((((cb & 1) * 4 + j) ^ (lane & 7)) << 4)) =
+                  make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+          }
+          if (AMODE == 0 && (cb & 1)) {
+            // 32 staged columns: each store instruction writes four whole 128-byte row segments
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int r = i * 4 + (lane >> 3), ch = lane & 7;
+              const float4 t = *reinterpret_cast<const float4*>(stg + r * 128 + ((ch ^ (r & 7)) << 4));
+              const int64_t mr = tile * TILE_M + quarter * 32 + r;
+              if (mr < p.M) *reinterpret_cast<float4*>(p.C + mr * p.ldc + col0 + (cb >> 1) * 32 + ch * 4) = t;
+            }
+            __syncwarp();
           }
           if ((EPI == 2 || EPI == 3) && cb + 1 < NB16) {
 #pragma unroll
@@ -318,7 +359,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) tc_rowgemm_kernel(const RowGemm
 
 template <int K, int N, int AMODE, int PRO, int EPI, int CMODE>
 int launch_rowgemm(const RowGemmP& p, cudaStream_t st) {
-  using Cfg = RowCfg<K, N>;
+  using Cfg = RowCfg<K, N, AMODE == 0>;
   auto kern = tc_rowgemm_kernel<K, N, AMODE, PRO, EPI, CMODE>;
   static bool configured = false;   // attribute is per function; setting it again is harmless
   if (!configured) {
@@ -353,12 +394,29 @@ struct WgradP {
   float* partial;   // [gridDim.x][MI][NPAD]
 };
 
+// wgrad thread layout: 8 drain warps, 1 MMA warp, 8 transform warps, 1 loader warp
+constexpr int WG_LOADER_WARP = MMA_WARP + 1 + PROD_WARPS;    // warp 17
+constexpr int WG_THREADS = (WG_LOADER_WARP + 1) * 32;         // 576
+
+template <int MI, int N, int GMODE>
+struct WgradCfg {
+  static constexpr uint32_t A_HALF_W = 4 * 4096;              // 4 m-blocks x (4 k-groups x 1 KB): M padded to 128
+  static constexpr uint32_t B_HALF_W = (GMODE == 0) ? (N / 32) * 4096 : N * 128;
+  static constexpr uint32_t STAGE_W = 2 * A_HALF_W + 2 * B_HALF_W;
+  static constexpr int NSTAGE = 2;                            // split (hi, lo) operand stages
+  static constexpr uint32_t XRAW = 32 * MI * 4;               // one 32-edge chunk of X, as it lies in HBM
+  static constexpr uint32_t GRAW = (GMODE == 0) ? 32 * N * 4 : 16 * 128;
+  static constexpr uint32_t RAW_STAGE = XRAW + GRAW;
+  static constexpr int RAW_NS = (NSTAGE * STAGE_W + 4 * RAW_STAGE + 2048 <= SMEM_LIMIT) ? 4 : 3;   // raw ring depth
+  static constexpr uint32_t SMEM = NSTAGE * STAGE_W + RAW_NS * RAW_STAGE + 1024 + 256;
+  static_assert(SMEM <= SMEM_LIMIT, "shared memory budget exceeded");
+};
+
 template <int MI, int N, int GMODE, int PRO>   // GMODE 0: G row-major [E][N]; 1: G column-major [n][E], N = 16
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const WgradP p) {
-  constexpr uint32_t A_HALF_W = 4 * 4096;                       // 4 m-blocks x (4 k-groups x 1 KB): M padded to 128
-  constexpr uint32_t B_HALF_W = (GMODE == 0) ? (N / 32) * 4096 : N * 128;
-  constexpr uint32_t STAGE_W = 2 * A_HALF_W + 2 * B_HALF_W;
-  constexpr int NSTAGE = 3;
+__global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const WgradP p) {
+  using Cfg = WgradCfg<MI, N, GMODE>;
+  constexpr uint32_t A_HALF_W = Cfg::A_HALF_W, B_HALF_W = Cfg::B_HALF_W, STAGE_W = Cfg::STAGE_W;
+  constexpr int NSTAGE = Cfg::NSTAGE, RAW_NS = Cfg::RAW_NS;
   // The tensor core's fp32 accumulation is not round-to-nearest: its error grows linearly with the number of
   // accumulated MMAs.  The accumulator is therefore drained every SEG chunks (128 edges) into fp32 registers of
   // the epilogue warps (IEEE adds) while the MMAs continue into the second TMEM accumulator.
@@ -368,12 +426,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const WgradP p)
   constexpr int EPI_ACTIVE = (N >= 64) ? EPI_WARPS : 4;     // warps that drain (column halves only when N >= 64)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bars = base + NSTAGE * STAGE_W;
+  const uint32_t raw0 = base + NSTAGE * STAGE_W;
+  const uint32_t bars = raw0 + RAW_NS * Cfg::RAW_STAGE;
   auto a_full = [&](int s) { return bars + 8u * s; };
   auto a_empty = [&](int s) { return bars + 8u * (NSTAGE + s); };
   auto t_full = [&](int b) { return bars + 8u * (2 * NSTAGE + b); };
   auto t_empty = [&](int b) { return bars + 8u * (2 * NSTAGE + 2 + b); };
-  const uint32_t tmem_slot = bars + 8u * (2 * NSTAGE + 4);
+  auto r_full = [&](int s) { return bars + 8u * (2 * NSTAGE + 4 + s); };
+  auto r_empty = [&](int s) { return bars + 8u * (2 * NSTAGE + 4 + RAW_NS + s); };
+  const uint32_t tmem_slot = bars + 8u * (2 * NSTAGE + 4 + 2 * RAW_NS);
   uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -385,18 +446,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const WgradP p)
 
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
-      mbar_init(a_full(s), PT);
+      mbar_init(a_full(s), PROD_WARPS);
       mbar_init(a_empty(s), 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(t_full(b), 1);
       mbar_init(t_empty(b), EPI_ACTIVE * 32);
     }
+    for (int s = 0; s < RAW_NS; ++s) {
+      mbar_init(r_full(s), 1);
+      mbar_init(r_empty(s), PROD_WARPS);
+    }
     mbar_fence_init();
   }
   if (warp == MMA_WARP) tmem_alloc(tmem_slot, TMEM_COLS);
   if (MI < 128) {   // rows MI..127 of the (padded) A operand are never written by the producers: zero them once
-    for (uint32_t o = tid * 16; o < NSTAGE * STAGE_W; o += TC_THREADS * 16)
+    for (uint32_t o = tid * 16; o < NSTAGE * STAGE_W; o += WG_THREADS * 16)
       *reinterpret_cast<float4*>(gen_base + o) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   fence_proxy_async_smem();
@@ -405,88 +470,91 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const WgradP p)
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - base));
 
-  if (warp >= MMA_WARP + 1) {
-    // =========================== producers ===========================
+  if (warp == WG_LOADER_WARP) {
+    // =========================== loader: bulk copies HBM -> raw ring ===========================
+    // A 32-edge chunk of X (and of a row-major G) is one contiguous block: one bulk copy each, up to RAW_NS chunks
+    // (128 KB) in flight per SM with no registers involved.
+    const bool x_dense = (p.ldx == MI), g_dense = (GMODE == 0 && p.ldg == N);
+    for (uint32_t g = 0; g < total; ++g) {
+      const int rs = g % RAW_NS;
+      if (lane == 0) mbar_wait(r_empty(rs), ((g / RAW_NS) & 1u) ^ 1u);
+      __syncwarp();
+      const int64_t e0 = (c_beg + g) * 32;
+      const uint32_t rows = (uint32_t)((p.E - e0 < 32) ? (p.E - e0) : 32);
+      const uint32_t xdst = raw0 + rs * Cfg::RAW_STAGE, gdst = xdst + Cfg::XRAW;
+      const uint32_t gbytes = (GMODE == 0) ? rows * N * 4u : (uint32_t)p.n_valid * rows * 4u;
+      if (lane == 0) mbar_expect_tx(r_full(rs), rows * MI * 4u + gbytes);
+      __syncwarp();
+      if (x_dense) {
+        if (lane == 0) bulk_g2s(xdst, p.X + e0 * p.ldx, rows * MI * 4u, r_full(rs));
+      } else if ((uint32_t)lane < rows) {
+        bulk_g2s(xdst + lane * MI * 4u, p.X + (e0 + lane) * p.ldx, MI * 4u, r_full(rs));
+      }
+      if (GMODE == 0) {
+        if (g_dense) {
+          if (lane == 0) bulk_g2s(gdst, p.G + e0 * p.ldg, rows * N * 4u, r_full(rs));
+        } else if ((uint32_t)lane < rows) {
+          bulk_g2s(gdst + lane * N * 4u, p.G + (e0 + lane) * p.ldg, N * 4u, r_full(rs));
+        }
+      } else if (lane < p.n_valid) {
+        bulk_g2s(gdst + lane * 128u, p.G + (int64_t)lane * p.ldg + e0, rows * 4u, r_full(rs));   // 32 edges of column n
+      }
+    }
+  } else if (warp >= MMA_WARP + 1) {
+    // =========================== transform: raw ring -> split (hi, lo) operand stages ===========================
     const int pt = tid - (MMA_WARP + 1) * 32;
     constexpr int XV = MI / 32;                         // float4 of X per thread per chunk
     constexpr int GV = (GMODE == 0) ? N / 32 : 1;       // float4 of G per thread per chunk
-    auto issue = [&](uint32_t g, float4 (&xv)[XV], float4 (&gv)[GV]) {
-      if (g >= total) return;
+    auto put = [&](uint32_t off_hi, uint32_t off_lo, const float4& v, auto act) {
+      float4 hi, lo;
+      act_split4<decltype(act)::value>(v, p.pro_scale, hi, lo);
+      *reinterpret_cast<float4*>(gen_base + off_hi) = hi;
+      *reinterpret_cast<float4*>(gen_base + off_lo) = lo;
+    };
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (uint32_t g = 0; g < total; ++g) {
+      const int s = g % NSTAGE, rs = g % RAW_NS;
       const int64_t e0 = (c_beg + g) * 32;
-#pragma unroll
-      for (int i = 0; i < XV; ++i) {
-        const int f = pt + i * PT, row = f / (MI / 4), c4 = f % (MI / 4);
-        const int64_t e = e0 + row;
-        xv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (e < p.E) xv[i] = __ldg(reinterpret_cast<const float4*>(p.X + e * p.ldx) + c4);
-      }
-      if (GMODE == 0) {
-#pragma unroll
-        for (int i = 0; i < GV; ++i) {
-          const int f = pt + i * PT, row = f / (N / 4), c4 = f % (N / 4);
-          const int64_t e = e0 + row;
-          gv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (e < p.E) gv[i] = __ldg(reinterpret_cast<const float4*>(p.G + e * p.ldg) + c4);
-        }
-      } else {
-        gv[0] = make_float4(0.f, 0.f, 0.f, 0.f);
-        const int n = pt >> 3, c4 = pt & 7;             // 16 rows x 8 float4 (32 edges)
-        if (pt < 128 && n < p.n_valid) {
-          const int64_t e = e0 + 4 * c4;
-          const float* src = p.G + (int64_t)n * p.ldg + e;
-          if (e + 3 < p.E) gv[0] = __ldg(reinterpret_cast<const float4*>(src));
-          else {
-            float t[4] = {0.f, 0.f, 0.f, 0.f};
-            for (int q = 0; q < 4; ++q) if (e + q < p.E) t[q] = __ldg(src + q);
-            gv[0] = make_float4(t[0], t[1], t[2], t[3]);
-          }
-        }
-      }
-    };
-    auto put = [&](uint32_t off_hi, uint32_t off_lo, float4 v, bool act) {
-      float x[4] = {v.x, v.y, v.z, v.w}, hi[4], lo[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        if (act) x[q] = gelu_tanh(x[q]) * p.pro_scale;
-        split_tf32(x[q], hi[q], lo[q]);
-      }
-      *reinterpret_cast<float4*>(gen_base + off_hi) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-      *reinterpret_cast<float4*>(gen_base + off_lo) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-    };
-    auto consume = [&](uint32_t g, float4 (&xv)[XV], float4 (&gv)[GV]) {
-      const int s = g % NSTAGE;
+      const int rows = (int)((p.E - e0 < 32) ? (p.E - e0) : 32);
+      mbar_wait(r_full(rs), (g / RAW_NS) & 1u);
       mbar_wait(a_empty(s), ((g / NSTAGE) & 1u) ^ 1u);
+      const uint8_t* xraw = gen_base + (raw0 - base) + rs * Cfg::RAW_STAGE;
+      const uint8_t* graw = xraw + Cfg::XRAW;
       const uint32_t sa = s * STAGE_W, sb = sa + 2 * A_HALF_W;
 #pragma unroll
       for (int i = 0; i < XV; ++i) {
         const int f = pt + i * PT, row = f / (MI / 4), c4 = f % (MI / 4);
+        const float4 v = (row < rows) ? *reinterpret_cast<const float4*>(xraw + (uint32_t)f * 16u) : zero4;
         // MN-major slab [m-block of 32][32 k-rows]: 4-row atoms, 32-byte-chunk swizzle
         const uint32_t off = (c4 >> 3) * 4096 + sw128_base32(row, c4 & 7);
-        put(sa + off, sa + A_HALF_W + off, xv[i], PRO == 1);
+        put(sa + off, sa + A_HALF_W + off, v, std::integral_constant<bool, PRO == 1>{});
       }
       if (GMODE == 0) {
 #pragma unroll
         for (int i = 0; i < GV; ++i) {
           const int f = pt + i * PT, row = f / (N / 4), c4 = f % (N / 4);
+          const float4 v = (row < rows) ? *reinterpret_cast<const float4*>(graw + (uint32_t)f * 16u) : zero4;
           const uint32_t off = (c4 >> 3) * 4096 + sw128_base32(row, c4 & 7);
-          put(sb + off, sb + B_HALF_W + off, gv[i], false);
+          put(sb + off, sb + B_HALF_W + off, v, std::false_type{});
         }
       } else if (pt < 128) {
         const int n = pt >> 3, c4 = pt & 7;             // K-major: row n, 32 edges per 128-byte row
+        float4 v = zero4;
+        if (n < p.n_valid) {
+          v = *reinterpret_cast<const float4*>(graw + n * 128 + c4 * 16);
+          if (4 * c4 + 0 >= rows) v.x = 0.f;
+          if (4 * c4 + 1 >= rows) v.y = 0.f;
+          if (4 * c4 + 2 >= rows) v.z = 0.f;
+          if (4 * c4 + 3 >= rows) v.w = 0.f;
+        }
         const uint32_t off = sw128(n, c4);
-        put(sb + off, sb + B_HALF_W + off, gv[0], false);
+        put(sb + off, sb + B_HALF_W + off, v, std::false_type{});
       }
       fence_proxy_async_smem();
-      mbar_arrive(a_full(s));
-    };
-    float4 x0[XV], x1[XV], g0[GV], g1[GV];
-    issue(0, x0, g0);
-    for (uint32_t g = 0; g < total; g += 2) {
-      issue(g + 1, x1, g1);
-      consume(g, x0, g0);
-      if (g + 1 < total) {
-        issue(g + 2, x0, g0);
-        consume(g + 1, x1, g1);
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(a_full(s));       // operands published to the MMA warp
+        mbar_arrive(r_empty(rs));     // raw slot may be refilled
       }
     }
   } else if (warp == MMA_WARP) {
@@ -577,16 +645,14 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int n_par
 
 template <int MI, int N, int GMODE, int PRO>
 int launch_wgrad(const WgradP& p, int grid, cudaStream_t st) {
-  constexpr uint32_t A_HALF_W = 4 * 4096;
-  constexpr uint32_t B_HALF_W = (GMODE == 0) ? (N / 32) * 4096 : N * 128;
-  constexpr uint32_t SMEM = 3 * (2 * A_HALF_W + 2 * B_HALF_W) + 1024 + 256;
+  constexpr uint32_t SMEM = WgradCfg<MI, N, GMODE>::SMEM;
   auto kern = tc_wgrad_kernel<MI, N, GMODE, PRO>;
   static bool configured = false;
   if (!configured) {
     EQNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
     configured = true;
   }
-  kern<<<grid, TC_THREADS, SMEM, st>>>(p);
+  kern<<<grid, WG_THREADS, SMEM, st>>>(p);
   EQNN_CHECK_LAUNCH();
   return EQNN_OK;
 }

@@ -6,7 +6,7 @@ from eqnn_jax_b200.nequip import _mm
 
 E = int(sys.argv[1]) if len(sys.argv) > 1 else 3_200_000
 dev = "cuda"
-def t(fn, n=5):
+def t(fn, n=int(os.environ.get('REPS', '5'))):
     fn(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -16,7 +16,7 @@ def t(fn, n=5):
 R = torch.randn(E, 64, device=dev); Z = torch.randn(E, 128, device=dev); Z2 = torch.empty(E, 128, device=dev)
 W1 = torch.randn(64, 128, device=dev); W2 = torch.randn(128, 128, device=dev); W4 = torch.randn(128, 11, device=dev)
 wt = torch.empty(11, E, device=dev); dW = torch.empty(128, 128, device=dev); dW4 = torch.empty(128, 11, device=dev)
-for tc in (False, True):
+for tc in ((True,) if os.environ.get('TC_ONLY') else (False, True)):
     r = {}
     r["fwd 64->128"] = t(lambda: _mm(E, 128, 64, .1, R, 0, 64, W1, 0, 128, Z2, 0, 128, tf32x3=tc))
     r["fwd 128->128 (gelu pro)"] = t(lambda: _mm(E, 128, 128, .1, Z, 0, 128, W2, 0, 128, Z2, 0, 128, pro=1, pro_scale=1.5, tf32x3=tc))
