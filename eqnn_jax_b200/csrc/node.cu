@@ -13,6 +13,7 @@ namespace {
 
 constexpr int NT = 256;        // threads per CTA (one z column per thread)
 constexpr int TILE = 16;       // nodes per tile
+constexpr int CTAS_PER_SM = 3; // resident CTAs (registers <= 85, shared memory ~58 KB each)
 constexpr int MAX_IN = 32;     // d_a + d_h
 constexpr int MAX_DH = 8;
 constexpr int MAX_CH = 8;
@@ -48,49 +49,81 @@ __device__ __forceinline__ int gate_of(const NodeP& p, int j) {   // gated compo
   return g;
 }
 
-// shared-memory carve-up (floats)
+// shared-memory carve-up (floats).  Layout rules that make the inner loops cheap:
+//   * matrices that are walked along a row with 128-bit loads by lanes holding DIFFERENT rows (W12, dz) use a row
+//     stride of 4*odd floats: eight consecutive rows then start in eight different 16-byte bank groups;
+//   * per-tile operands that every lane reads at the same address (inputs, dh_out) are stored TRANSPOSED,
+//     [feature][node], so that the 16 nodes of a tile are four broadcast 128-bit loads.
 struct Smem {
-  float* W12;   // [d_in][d_z]   rows 0..d_a-1 = alpha1*W1, rows d_a.. = W2
+  float* W12;   // [d_in][ldw]    rows 0..d_a-1 = alpha1*W1, rows d_a.. = W2, pad columns zero
   float* W3;    // [d_g][d_h]
   float* W0n;   // [d_h][dxp]
-  float* in;    // [TILE][d_in]
+  float* inT;   // [d_in][TILE]
   float* z;     // [TILE][d_z]
-  float* g;     // [TILE][d_g]   (forward: gate output; backward: dg then reused)
-  float* t;     // [TILE][MAX_DH] small per-node vectors (h', dh_out)
+  float* g;     // [TILE][d_g]    gate output
+  float* tT;    // [MAX_DH][TILE] h' (forward) / dh_out (backward)
+  float* dz;    // [TILE][ldw]    backward only, pad columns zero
+  float* dg;    // [TILE][d_g]    backward only
+  int* gidx;    // [d_gated]      gated component -> gate index
+  int* goff;    // [n_gates]      gate -> first gated component
+  int* gdim;    // [n_gates]      gate -> number of components it gates
 };
 
-// odd row stride for the matrices that are read "one row per lane" (conflict-free shared-memory banks)
-__host__ __device__ __forceinline__ int odd(int n) { return n | 1; }
-
-__device__ __forceinline__ Smem carve(float* base, const NodeP& p, int d_in) {
-  Smem s;
-  s.W12 = base;
-  s.W3 = s.W12 + d_in * odd(p.d_z);
-  s.W0n = s.W3 + p.d_g * p.d_h;
-  s.in = s.W0n + p.d_h * (p.dxp > 0 ? p.dxp : 1);
-  s.z = s.in + TILE * d_in;
-  s.g = s.z + TILE * p.d_z;
-  s.t = s.g + TILE * p.d_g;
-  return s;
+__host__ __device__ __forceinline__ int row4odd(int n) {   // smallest multiple of 4 >= n whose quarter is odd
+  int r = (n + 3) / 4;
+  if ((r & 1) == 0) ++r;
+  return 4 * r;
 }
 
-size_t smem_floats(const NodeP& p) {
-  const int d_in = p.d_a + p.d_h;
-  return (size_t)d_in * odd(p.d_z) + (size_t)p.d_g * p.d_h + (size_t)p.d_h * (p.dxp > 0 ? p.dxp : 1) +
-         (size_t)TILE * (d_in + p.d_z + p.d_g + MAX_DH) + 2 * (size_t)TILE * odd(p.d_z);   // + dz, gact in backward
+__host__ __device__ __forceinline__ size_t smem_layout(const NodeP& p, Smem* s, float* base) {
+  const int d_in = p.d_a + p.d_h, ldw = row4odd(p.d_z);
+  size_t o = 0;
+  auto take = [&](size_t n) { size_t at = o; o += (n + 3) / 4 * 4; return at; };   // keep every array 16-byte aligned
+  const size_t oW12 = take((size_t)d_in * ldw), oW3 = take((size_t)p.d_g * p.d_h);
+  const size_t oW0 = take((size_t)p.d_h * (p.dxp > 0 ? p.dxp : 1)), oIn = take((size_t)d_in * TILE);
+  const size_t oZ = take((size_t)TILE * p.d_z), oG = take((size_t)TILE * p.d_g), oT = take((size_t)MAX_DH * TILE);
+  const size_t oDz = take((size_t)TILE * ldw), oDg = take((size_t)TILE * p.d_g);
+  const size_t oGi = take(p.d_gated > 0 ? p.d_gated : 1), oGo = take(p.n_gates > 0 ? p.n_gates : 1);
+  const size_t oGd = take(p.n_gates > 0 ? p.n_gates : 1);
+  if (s) {
+    s->W12 = base + oW12; s->W3 = base + oW3; s->W0n = base + oW0; s->inT = base + oIn; s->z = base + oZ;
+    s->g = base + oG; s->tT = base + oT; s->dz = base + oDz; s->dg = base + oDg;
+    s->gidx = reinterpret_cast<int*>(base + oGi); s->goff = reinterpret_cast<int*>(base + oGo);
+    s->gdim = reinterpret_cast<int*>(base + oGd);
+  }
+  return o;
 }
+
+size_t smem_floats(const NodeP& p) { return smem_layout(p, nullptr, nullptr); }
 
 __device__ __forceinline__ void load_weights(const NodeP& p, const Smem& s, int d_in) {
-  for (int i = threadIdx.x; i < d_in * p.d_z; i += NT) {
-    const int r = i / p.d_z, c = i - r * p.d_z;
-    float v;
-    if (r < p.d_a) v = p.alpha1 * p.W1[(size_t)r * p.d_z + c];
-    else v = p.W2 ? p.W2[(size_t)(r - p.d_a) * p.d_z + c] : 0.f;
-    s.W12[r * odd(p.d_z) + c] = v;
+  const int ldw = row4odd(p.d_z);
+  for (int i = threadIdx.x; i < d_in * ldw; i += NT) {
+    const int r = i / ldw, c = i - r * ldw;
+    float v = 0.f;
+    if (c < p.d_z) {
+      if (r < p.d_a) v = p.alpha1 * p.W1[(size_t)r * p.d_z + c];
+      else v = p.W2 ? p.W2[(size_t)(r - p.d_a) * p.d_z + c] : 0.f;
+    }
+    s.W12[i] = v;
   }
+  for (int i = threadIdx.x; i < TILE * ldw; i += NT) s.dz[i] = 0.f;
   for (int i = threadIdx.x; i < p.d_g * p.d_h; i += NT) s.W3[i] = p.W3[i];
   if (p.W0n)
     for (int i = threadIdx.x; i < p.d_h * p.dxp; i += NT) s.W0n[i] = p.W0n[i];
+  for (int j = threadIdx.x; j < p.d_gated; j += NT) s.gidx[j] = gate_of(p, j);
+  for (int gi = threadIdx.x; gi < p.n_gates; gi += NT) {
+    int rem = gi, off = 0, dim = 1;
+#pragma unroll
+    for (int k = 0; k < MAX_CH; ++k) {
+      if (k < p.n_chunks) {
+        if (rem >= 0 && rem < p.mul[k]) { off += rem * p.dim[k]; dim = p.dim[k]; rem = -1; }
+        else if (rem >= 0) { rem -= p.mul[k]; off += p.mul[k] * p.dim[k]; }
+      }
+    }
+    s.goff[gi] = off;
+    s.gdim[gi] = dim;
+  }
 }
 
 __device__ __forceinline__ void load_inputs(const NodeP& p, const Smem& s, int d_in, int64_t n0, int nn) {
@@ -98,16 +131,34 @@ __device__ __forceinline__ void load_inputs(const NodeP& p, const Smem& s, int d
     const int node = i / d_in, r = i - node * d_in;
     float v = 0.f;
     if (node < nn) v = (r < p.d_a) ? p.A[(n0 + node) * p.ld_a + r] : p.h[(n0 + node) * p.d_h + (r - p.d_a)];
-    s.in[i] = v;
+    s.inT[r * TILE + node] = v;
   }
 }
 
-__global__ void __launch_bounds__(NT) node_fwd_kernel(const NodeP p) {
+// the TILE node values of feature row `r` of a transposed operand: broadcast 128-bit loads
+__device__ __forceinline__ void load_tile_row(const float* rowT, float (&v)[TILE]) {
+#pragma unroll
+  for (int q = 0; q < TILE; q += 4) {
+    const float4 t = *reinterpret_cast<const float4*>(rowT + q);
+    v[q] = t.x; v[q + 1] = t.y; v[q + 2] = t.z; v[q + 3] = t.w;
+  }
+}
+
+__device__ __forceinline__ float dot4(const float4& a, const float4& b, float acc) {
+  acc = fmaf(a.x, b.x, acc);
+  acc = fmaf(a.y, b.y, acc);
+  acc = fmaf(a.z, b.z, acc);
+  return fmaf(a.w, b.w, acc);
+}
+
+__global__ void __launch_bounds__(NT, 3) node_fwd_kernel(const NodeP p) {
   extern __shared__ __align__(16) float smem_f[];
-  const int d_in = p.d_a + p.d_h;
-  const Smem s = carve(smem_f, p, d_in);
+  const int d_in = p.d_a + p.d_h, ldw = row4odd(p.d_z);
+  Smem s;
+  smem_layout(p, &s, smem_f);
   load_weights(p, s, d_in);
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int parts = (2 * TILE * p.d_h <= NT) ? 2 : 1;      // lanes sharing one h' element
   const int64_t n_tiles = (p.n + TILE - 1) / TILE;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t n0 = tile * TILE;
@@ -115,15 +166,17 @@ __global__ void __launch_bounds__(NT) node_fwd_kernel(const NodeP p) {
     __syncthreads();
     load_inputs(p, s, d_in, n0, nn);
     __syncthreads();
-    // z[node][c]: thread = column, weights of the column in registers would need d_in <= 32 registers; stream from smem
+    // z[node][c]: thread = column c, 16 nodes in registers; per input feature 1 weight + 4 broadcast loads, 16 FMAs
     if (tid < p.d_z) {
       float acc[TILE];
 #pragma unroll
       for (int q = 0; q < TILE; ++q) acc[q] = 0.f;
       for (int r = 0; r < d_in; ++r) {
-        const float w = s.W12[r * odd(p.d_z) + tid];
+        const float w = s.W12[r * ldw + tid];
+        float in[TILE];
+        load_tile_row(s.inT + r * TILE, in);
 #pragma unroll
-        for (int q = 0; q < TILE; ++q) acc[q] = fmaf(s.in[q * d_in + r], w, acc[q]);
+        for (int q = 0; q < TILE; ++q) acc[q] = fmaf(in[q], w, acc[q]);
       }
 #pragma unroll
       for (int q = 0; q < TILE; ++q) s.z[q * p.d_z + tid] = acc[q];
@@ -131,32 +184,37 @@ __global__ void __launch_bounds__(NT) node_fwd_kernel(const NodeP p) {
     __syncthreads();
     // save z (coalesced), gate
     for (int i = tid; i < nn * p.d_z; i += NT) p.z[n0 * p.d_z + i] = s.z[i];
-    for (int i = tid; i < TILE * p.d_g; i += NT) {
-      const int node = i / p.d_g, c = i - node * p.d_g;
+    for (int node = warp; node < TILE; node += NT / 32) {       // warp per node, lanes over components: no divisions
       const float* zr = s.z + node * p.d_z;
-      float v;
-      if (c < p.n_extra) v = gelu_tanh(zr[c]) * p.inv_c_act;
-      else {
-        const int j = c - p.n_extra;
-        v = sigmoid_acc(zr[p.n_extra + gate_of(p, j)]) * p.inv_c_gate * zr[p.n_extra + p.n_gates + j];
+      for (int c = lane; c < p.d_g; c += 32) {
+        float v;
+        if (c < p.n_extra) v = gelu_tanh(zr[c]) * p.inv_c_act;
+        else {
+          const int j = c - p.n_extra;
+          v = sigmoid_acc(zr[p.n_extra + s.gidx[j]]) * p.inv_c_gate * zr[p.n_extra + p.n_gates + j];
+        }
+        s.g[node * p.d_g + c] = v;
       }
-      s.g[i] = v;
     }
     __syncthreads();
-    // h'[node][o] = sum_j g[node][j] W3[j][o]
-    if (tid < TILE * p.d_h) {
-      const int node = tid / p.d_h, o = tid - node * p.d_h;
+    // h'[node][o] = sum_j g[node][j] W3[j][o]: `parts` adjacent lanes split the sum
+    if (tid < parts * TILE * p.d_h) {
+      const int part = tid % parts, idx = tid / parts;
+      const int node = idx / p.d_h, o = idx - node * p.d_h;
       const float* gr = s.g + node * p.d_g;
       float a = 0.f;
-      for (int j = 0; j < p.d_g; ++j) a = fmaf(gr[j], s.W3[j * p.d_h + o], a);
-      s.t[node * MAX_DH + o] = a;
-      if (node < nn) p.h_out[(n0 + node) * p.d_h + o] = a;
+      for (int j = part; j < p.d_g; j += parts) a = fmaf(gr[j], s.W3[j * p.d_h + o], a);
+      if (parts == 2) a += __shfl_xor_sync(0xffffffffu, a, 1);
+      if (part == 0) {
+        s.tT[o * TILE + node] = a;
+        if (node < nn) p.h_out[(n0 + node) * p.d_h + o] = a;
+      }
     }
     __syncthreads();
     if (p.W0n && tid < TILE * p.dxp) {
       const int node = tid / p.dxp, c = tid - node * p.dxp;
       float a = 0.f;
-      for (int r = 0; r < p.d_h; ++r) a = fmaf(s.t[node * MAX_DH + r], s.W0n[r * p.dxp + c], a);
+      for (int r = 0; r < p.d_h; ++r) a = fmaf(s.tT[r * TILE + node], s.W0n[r * p.dxp + c], a);
       if (node < nn) p.xt_out[(n0 + node) * p.dxp + c] = a;
     }
   }
@@ -164,15 +222,13 @@ __global__ void __launch_bounds__(NT) node_fwd_kernel(const NodeP p) {
 
 // Backward: given dh_out, produces dA, dh_in (self-connection part) and per-CTA partial weight gradients
 // laid out as [dW12 (d_in x d_z) | dW3 (d_g x d_h)].
-__global__ void __launch_bounds__(NT) node_bwd_kernel(const NodeP p) {
+__global__ void __launch_bounds__(NT, 3) node_bwd_kernel(const NodeP p) {
   extern __shared__ __align__(16) float smem_f[];
-  const int d_in = p.d_a + p.d_h;
-  const Smem s = carve(smem_f, p, d_in);
-  const int ldz = odd(p.d_z);
-  float* dz = s.t + TILE * MAX_DH;            // [TILE][ldz]
-  float* gact = dz + TILE * ldz;              // [TILE][d_g]: dg, reused between phases
+  const int d_in = p.d_a + p.d_h, ldw = row4odd(p.d_z);
+  Smem s;
+  smem_layout(p, &s, smem_f);
   load_weights(p, s, d_in);
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // weight-gradient accumulators: thread c < d_z owns column c of dW12; thread j < d_g owns row j of dW3
   float aw[MAX_IN], a3[MAX_DH];
 #pragma unroll
@@ -188,80 +244,99 @@ __global__ void __launch_bounds__(NT) node_bwd_kernel(const NodeP p) {
     for (int i = tid; i < TILE * p.d_z; i += NT) s.z[i] = (i < nn * p.d_z) ? p.z[n0 * p.d_z + i] : 0.f;
     for (int i = tid; i < TILE * MAX_DH; i += NT) {
       const int node = i / MAX_DH, o = i - node * MAX_DH;
-      s.t[i] = (node < nn && o < p.d_h) ? p.dh_out[(n0 + node) * p.d_h + o] : 0.f;
+      s.tT[o * TILE + node] = (node < nn && o < p.d_h) ? p.dh_out[(n0 + node) * p.d_h + o] : 0.f;
     }
     __syncthreads();
     // g (recomputed) and dg[node][j] = sum_o dh_out[node][o] W3[j][o]
-    for (int i = tid; i < TILE * p.d_g; i += NT) {
-      const int node = i / p.d_g, c = i - node * p.d_g;
+    for (int node = warp; node < TILE; node += NT / 32) {       // warp per node, lanes over components
       const float* zr = s.z + node * p.d_z;
-      float dg = 0.f;
-      for (int o = 0; o < p.d_h; ++o) dg = fmaf(s.t[node * MAX_DH + o], s.W3[c * p.d_h + o], dg);
-      float gv;
-      if (c < p.n_extra) {
-        gv = gelu_tanh(zr[c]) * p.inv_c_act;
-        dz[node * ldz + c] = dg * gelu_tanh_grad(zr[c]) * p.inv_c_act;
-      } else {
-        const int j = c - p.n_extra;
-        const float sg = sigmoid_acc(zr[p.n_extra + gate_of(p, j)]) * p.inv_c_gate;
-        gv = sg * zr[p.n_extra + p.n_gates + j];
-        dz[node * ldz + p.n_extra + p.n_gates + j] = dg * sg;
+      float dho[MAX_DH];
+#pragma unroll
+      for (int o = 0; o < MAX_DH; ++o) dho[o] = s.tT[o * TILE + node];
+      for (int c = lane; c < p.d_g; c += 32) {
+        float dg = 0.f;
+#pragma unroll
+        for (int o = 0; o < MAX_DH; ++o)
+          if (o < p.d_h) dg = fmaf(dho[o], s.W3[c * p.d_h + o], dg);
+        float gv;
+        if (c < p.n_extra) {
+          gv = gelu_tanh(zr[c]) * p.inv_c_act;
+          s.dz[node * ldw + c] = dg * gelu_tanh_grad(zr[c]) * p.inv_c_act;
+        } else {
+          const int j = c - p.n_extra;
+          const float sg = sigmoid_acc(zr[p.n_extra + s.gidx[j]]) * p.inv_c_gate;
+          gv = sg * zr[p.n_extra + p.n_gates + j];
+          s.dz[node * ldw + p.n_extra + p.n_gates + j] = dg * sg;
+        }
+        s.g[node * p.d_g + c] = gv;        // gate output (for dW3)
+        s.dg[node * p.d_g + c] = dg;       // dg (for the gate-scalar gradients)
       }
-      s.g[i] = gv;        // gate output (for dW3)
-      gact[i] = dg;       // dg (for the gate-scalar gradients)
     }
     __syncthreads();
     // gradients of the gate scalars: sum over the components they gate
-    for (int i = tid; i < TILE * p.n_gates; i += NT) {
-      const int node = i / p.n_gates, gi = i - node * p.n_gates;
-      int rem = gi, off = 0, dim = 1;
-#pragma unroll
-      for (int k = 0; k < MAX_CH; ++k) {
-        if (k < p.n_chunks) {
-          if (rem >= 0 && rem < p.mul[k]) { off += rem * p.dim[k]; dim = p.dim[k]; rem = -1; }
-          else if (rem >= 0) { rem -= p.mul[k]; off += p.mul[k] * p.dim[k]; }
-        }
-      }
+    for (int node = warp; node < TILE; node += NT / 32) {
       const float* zr = s.z + node * p.d_z;
-      float acc = 0.f;
-      for (int q = 0; q < dim; ++q) acc += gact[node * p.d_g + p.n_extra + off + q] * zr[p.n_extra + p.n_gates + off + q];
-      const float sg = sigmoid_acc(zr[p.n_extra + gi]);
-      dz[node * ldz + p.n_extra + gi] = acc * sg * (1.f - sg) * p.inv_c_gate;
+      for (int gi = lane; gi < p.n_gates; gi += 32) {
+        const int off = s.goff[gi], dim = s.gdim[gi];
+        float acc = 0.f;
+        for (int q = 0; q < dim; ++q) acc += s.dg[node * p.d_g + p.n_extra + off + q] * zr[p.n_extra + p.n_gates + off + q];
+        const float sg = sigmoid_acc(zr[p.n_extra + gi]);
+        s.dz[node * ldw + p.n_extra + gi] = acc * sg * (1.f - sg) * p.inv_c_gate;
+      }
     }
     __syncthreads();
-    // weight gradients (registers) ...
+    // weight gradients (registers): the thread's column of dz for the 16 nodes, then per input feature
+    // 4 broadcast loads + 16 FMAs
     if (tid < p.d_z) {
+      float dzc[TILE];
+#pragma unroll
+      for (int q = 0; q < TILE; ++q) dzc[q] = s.dz[q * ldw + tid];
 #pragma unroll
       for (int r = 0; r < MAX_IN; ++r) {
         if (r < d_in) {
+          float in[TILE];
+          load_tile_row(s.inT + r * TILE, in);
           float a = aw[r];
 #pragma unroll
-          for (int q = 0; q < TILE; ++q) a = fmaf(s.in[q * d_in + r], dz[q * ldz + tid], a);
+          for (int q = 0; q < TILE; ++q) a = fmaf(in[q], dzc[q], a);
           aw[r] = a;
         }
       }
     }
     if (tid < p.d_g) {
+      float gq[TILE];
+#pragma unroll
+      for (int q = 0; q < TILE; ++q) gq[q] = s.g[q * p.d_g + tid];
 #pragma unroll
       for (int o = 0; o < MAX_DH; ++o) {
         if (o < p.d_h) {
+          float t[TILE];
+          load_tile_row(s.tT + o * TILE, t);
           float a = a3[o];
 #pragma unroll
-          for (int q = 0; q < TILE; ++q) a = fmaf(s.g[q * p.d_g + tid], s.t[q * MAX_DH + o], a);
+          for (int q = 0; q < TILE; ++q) a = fmaf(gq[q], t[q], a);
           a3[o] = a;
         }
       }
     }
-    // ... and data gradients d_in[node][r] = sum_c dz[node][c] W12[r][c]
-    for (int i = tid; i < TILE * d_in; i += NT) {
-      const int node = i / d_in, r = i - node * d_in;
-      const float* dzr = dz + node * ldz;
-      const float* wr = s.W12 + r * odd(p.d_z);
-      float a = 0.f;
-      for (int c = 0; c < p.d_z; ++c) a = fmaf(dzr[c], wr[c], a);
-      if (node < nn) {
-        if (r < p.d_a) p.dA[(n0 + node) * p.d_a + r] = a;
-        else p.dh_in[(n0 + node) * p.d_h + (r - p.d_a)] = p.W2 ? a : 0.f;
+    // ... and data gradients d_in[node][r] = sum_c dz[node][c] W12[r][c]  (128-bit loads along c; pads are zero)
+    for (int node = warp; node < TILE; node += NT / 32) {       // warp per node, lanes over input features
+      const float4* dzr = reinterpret_cast<const float4*>(s.dz + node * ldw);
+      for (int r = lane; r < d_in; r += 32) {
+        const float4* wr = reinterpret_cast<const float4*>(s.W12 + r * ldw);
+        float a0 = 0.f, a1 = 0.f;
+        const int n4 = (p.d_z + 3) / 4;
+        int c = 0;
+        for (; c + 1 < n4; c += 2) {
+          a0 = dot4(dzr[c], wr[c], a0);
+          a1 = dot4(dzr[c + 1], wr[c + 1], a1);
+        }
+        if (c < n4) a0 = dot4(dzr[c], wr[c], a0);
+        const float a = a0 + a1;
+        if (node < nn) {
+          if (r < p.d_a) p.dA[(n0 + node) * p.d_a + r] = a;
+          else p.dh_in[(n0 + node) * p.d_h + (r - p.d_a)] = p.W2 ? a : 0.f;
+        }
       }
     }
   }
@@ -324,7 +399,7 @@ int grid_for(int64_t n) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t tiles = (n + TILE - 1) / TILE;
-  const int64_t g = 2 * (int64_t)sms;
+  const int64_t g = CTAS_PER_SM * (int64_t)sms;
   return (int)(tiles < g ? tiles : g);
 }
 
@@ -334,7 +409,7 @@ extern "C" size_t eqnn_node_update_workspace_bytes(int d_a, int d_h, int d_z, in
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  return (size_t)2 * sms * ((size_t)(d_a + d_h) * d_z + (size_t)d_g * d_h) * sizeof(float);
+  return (size_t)CTAS_PER_SM * sms * ((size_t)(d_a + d_h) * d_z + (size_t)d_g * d_h) * sizeof(float);
 }
 
 extern "C" int eqnn_node_update_fwd(const float* A, int ld_a, int d_a, const float* h, int d_h, const float* W1,
