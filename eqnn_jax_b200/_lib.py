@@ -60,6 +60,8 @@ SIGNATURES: Dict[str, tuple] = {
     "eqnn_pool_fwd": (_i, [_p, _i, _i, _i, _i, _p, _p]),
     "eqnn_pool_bwd": (_i, [_p, _i, _i, _i, _i, _p, _p]),
     "eqnn_colsum": (_i, [_p, _i64, _i, _p, _p]),
+    "eqnn_layernorm_fwd": (_i, [_p, _i, _p, _i, _i, _p, _p, _f, _p, _p, _p]),
+    "eqnn_layernorm_bwd": (_i, [_p, _i, _p, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
     "eqnn_weights_expand": (_i, [_p, _p, _p, _i64, _p, _p]),
     "eqnn_weights_contract": (_i, [_p, _p, _p, _p, _p, _i64, _p, _p]),
     "eqnn_mse_loss": (_i, [_p, _p, _i, _i, _f, _p, _p, _p]),

@@ -193,6 +193,76 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
   p[i] = pi - lr * (mh / (sqrtf(vh) + eps) + wd * pi);
 }
 
+
+// ---- LayerNorm over [pooled | globals] rows (nequip.py:201-205; flax.linen.LayerNorm: eps 1e-6, scale + bias) ----
+// one warp per row; x = concat(a[b, :da], g[b, :dg]); stats[b] = (mean, rstd)
+__global__ void layernorm_fwd_kernel(const float* __restrict__ a, int da, const float* __restrict__ g, int dg, int B,
+                                     const float* __restrict__ scale, const float* __restrict__ bias, float eps,
+                                     float* __restrict__ y, float* __restrict__ stats) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= B) return;
+  const int D = da + dg;
+  auto x = [&](int c) { return c < da ? a[(size_t)row * da + c] : g[(size_t)row * dg + (c - da)]; };
+  float s = 0.f;
+  for (int c = lane; c < D; c += 32) s += x(c);
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mu = s / (float)D;
+  float v = 0.f;
+  for (int c = lane; c < D; c += 32) {
+    const float d = x(c) - mu;
+    v = fmaf(d, d, v);
+  }
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const float rstd = rsqrtf(v / (float)D + eps);
+  for (int c = lane; c < D; c += 32) y[(size_t)row * D + c] = (x(c) - mu) * rstd * scale[c] + bias[c];
+  if (lane == 0) {
+    stats[2 * row] = mu;
+    stats[2 * row + 1] = rstd;
+  }
+}
+
+// dx = rstd * (dyh - mean(dyh) - xh * mean(dyh * xh)), dyh = dy * scale; only the first da columns are returned
+__global__ void layernorm_bwd_kernel(const float* __restrict__ a, int da, const float* __restrict__ g, int dg, int B,
+                                     const float* __restrict__ scale, const float* __restrict__ stats,
+                                     const float* __restrict__ dy, float* __restrict__ d_a) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= B) return;
+  const int D = da + dg;
+  const float mu = stats[2 * row], rstd = stats[2 * row + 1];
+  auto xh = [&](int c) { return ((c < da ? a[(size_t)row * da + c] : g[(size_t)row * dg + (c - da)]) - mu) * rstd; };
+  float s1 = 0.f, s2 = 0.f;
+  for (int c = lane; c < D; c += 32) {
+    const float t = dy[(size_t)row * D + c] * scale[c];
+    s1 += t;
+    s2 = fmaf(t, xh(c), s2);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  s1 /= (float)D;
+  s2 /= (float)D;
+  for (int c = lane; c < da; c += 32)
+    d_a[(size_t)row * da + c] = rstd * (dy[(size_t)row * D + c] * scale[c] - s1 - xh(c) * s2);
+}
+
+// dscale[c] = sum_b dy[b,c] * xh[b,c];  dbias[c] = sum_b dy[b,c]   (rows in ascending order: deterministic)
+__global__ void layernorm_wgrad_kernel(const float* __restrict__ a, int da, const float* __restrict__ g, int dg, int B,
+                                       const float* __restrict__ stats, const float* __restrict__ dy,
+                                       float* __restrict__ dscale, float* __restrict__ dbias) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x, D = da + dg;
+  if (c >= D) return;
+  float ds = 0.f, db = 0.f;
+  for (int b = 0; b < B; ++b) {
+    const float x = c < da ? a[(size_t)b * da + c] : g[(size_t)b * dg + (c - da)];
+    const float t = dy[(size_t)b * D + c];
+    ds = fmaf(t, (x - stats[2 * b]) * stats[2 * b + 1], ds);
+    db += t;
+  }
+  dscale[c] = ds;
+  dbias[c] = db;
+}
+
 }  // namespace
 
 extern "C" int eqnn_gate_fwd(const float* z, int64_t n, int n_extra, int n_gates, int n_chunks, const int* mul,
@@ -219,6 +289,27 @@ extern "C" int eqnn_gate_bwd(const float* z, const float* gout, int64_t n, int n
   if (tot == 0) return EQNN_OK;
   gate_bwd_kernel<<<(unsigned)ceil_div64(tot, 256), 256, 0, as_stream(stream)>>>(z, gout, n, d, gz);
   EQNN_CHECK_LAUNCH();
+  return EQNN_OK;
+}
+
+extern "C" int eqnn_layernorm_fwd(const float* a, int da, const float* g, int dg, int B, const float* scale,
+                                  const float* bias, float eps, float* y, float* stats, eqnn_stream_t stream) {
+  EQNN_CHECK_ARG(a && (g || dg == 0) && scale && bias && y && stats && B >= 1 && da >= 1 && dg >= 0,
+                 "layernorm_fwd: bad argument");
+  layernorm_fwd_kernel<<<(B + 7) / 8, 256, 0, as_stream(stream)>>>(a, da, g, dg, B, scale, bias, eps, y, stats);
+  EQNN_CHECK_LAUNCH();
+  return EQNN_OK;
+}
+
+extern "C" int eqnn_layernorm_bwd(const float* a, int da, const float* g, int dg, int B, const float* scale,
+                                  const float* stats, const float* dy, float* d_a, float* dscale, float* dbias,
+                                  eqnn_stream_t stream) {
+  EQNN_CHECK_ARG(a && (g || dg == 0) && scale && stats && dy && d_a && dscale && dbias && B >= 1 && da >= 1 && dg >= 0,
+                 "layernorm_bwd: bad argument");
+  cudaStream_t st = as_stream(stream);
+  layernorm_bwd_kernel<<<(B + 7) / 8, 256, 0, st>>>(a, da, g, dg, B, scale, stats, dy, d_a);
+  layernorm_wgrad_kernel<<<(da + dg + 127) / 128, 128, 0, st>>>(a, da, g, dg, B, stats, dy, dscale, dbias);
+  EQNN_CHECK_LAUNCH_N(2);
   return EQNN_OK;
 }
 

@@ -109,8 +109,9 @@ class _Dense:
 
 
 class _Plan:
-    def __init__(self, cfg: "NequIP", irreps_in: Irreps):
+    def __init__(self, cfg: "NequIP", irreps_in: Irreps, n_globals: int = 0):
         self.irreps_in = irreps_in
+        self.n_globals = int(n_globals)
         D = irreps_in.dim
         if len(irreps_in) == 0 or irreps_in[0][1] != 1:
             raise ValueError("the first irrep of the node features must be a vector (positions), nequip.py:129-132")
@@ -250,7 +251,12 @@ class _Plan:
                         ro_scale[c.live_off + i] = self.shn[c.l2]
             self.Wro = self._add_linear(f"Linear_{li}", lp, row_map=ro_map, rows=self.tp_ro.d_live,
                                         row_scale=ro_scale); li += 1
-            n_pool = cfg.d_hidden
+            # graph globals are concatenated to the pooled scalars and LayerNorm-ed (nequip.py:201-205)
+            n_pool = cfg.d_hidden + self.n_globals
+            self.ln = None
+            if self.n_globals > 0:
+                self.ln = (self._add_param(("LayerNorm_0", "scale"), (n_pool,)),
+                           self._add_param(("LayerNorm_0", "bias"), (n_pool,)))
             ws = [cfg.mlp_readout_widths[0] * n_pool] + [w * cfg.d_hidden for w in cfg.mlp_readout_widths[1:]] + \
                  [cfg.n_outputs]
             self.ro_mlp = []
@@ -393,11 +399,13 @@ class NequIP:
         self._plans: Dict[Irreps, _Plan] = {}
 
     # -- plans / params -----------------------------------------------------------------
-    def plan(self, irreps_in) -> _Plan:
+    def plan(self, irreps_in, n_globals: int = 0) -> _Plan:
         irreps_in = Irreps(irreps_in)
-        if irreps_in not in self._plans:
-            self._plans[irreps_in] = _Plan(self, irreps_in)
-        return self._plans[irreps_in]
+        n_globals = int(n_globals) if self.task == "graph" else 0
+        key = (irreps_in, n_globals)
+        if key not in self._plans:
+            self._plans[key] = _Plan(self, irreps_in, n_globals)
+        return self._plans[key]
 
     @staticmethod
     def _nodes_of(graphs: GraphsTuple) -> Tuple[Irreps, torch.Tensor]:
@@ -410,14 +418,14 @@ class NequIP:
         """Flax-style ``model.init``: draws parameters with the library initialisers' distributions
         (e3nn Linear / MultiLayerPerceptron: N(0,1); models/mlp.py Dense: xavier-uniform, zero bias)."""
         irreps_in, arr = self._nodes_of(graphs)
-        plan = self.plan(irreps_in)
-        if globals_present(graphs):
-            raise NotImplementedError("graph globals (LayerNorm branch, nequip.py:201-205) are not on the B200 path yet")
+        plan = self.plan(irreps_in, _n_globals_of(graphs))
         rng = np.random.default_rng(rng) if not isinstance(rng, np.random.Generator) else rng
         host = np.empty((plan._n_params,), dtype=np.float32)
         for path, shape, off in plan.layout:
             n = int(np.prod(shape))
-            if path[0] == "MLP_0":
+            if path[0] == "LayerNorm_0":
+                v = np.ones(shape) if path[-1] == "scale" else np.zeros(shape)
+            elif path[0] == "MLP_0":
                 if path[-1] == "bias":
                     v = np.zeros(shape)
                 else:
@@ -451,12 +459,10 @@ class NequIP:
         unbatched = arr.dim() == 2
         if unbatched:
             arr = arr.unsqueeze(0)
-        if globals_present(graphs):
-            raise NotImplementedError("graph globals (LayerNorm branch, nequip.py:201-205) are not on the B200 path yet")
-        plan = self.plan(irreps_in)
+        plan = self.plan(irreps_in, _n_globals_of(graphs))
         pg = prepared if prepared is not None else self.prepare(graphs)
         k = _n_edge_of(graphs)
-        out = _NequIPFunction.apply(params.flat, self, plan, pg, arr.contiguous(), k)
+        out = _NequIPFunction.apply(params.flat, self, plan, pg, arr.contiguous(), k, _globals_of(graphs, arr.shape[0]))
         if self.task == "graph":
             return out[0] if unbatched else out
         nodes = out[0] if unbatched else out
@@ -471,10 +477,11 @@ class NequIP:
         irreps_in, arr = self._nodes_of(graphs)
         if arr.dim() == 2:
             arr = arr.unsqueeze(0)
-        plan = self.plan(irreps_in)
+        plan = self.plan(irreps_in, _n_globals_of(graphs))
         pg = prepared if prepared is not None else self.prepare(graphs)
         k = _n_edge_of(graphs)
-        out, saved = _forward(self, plan, params.flat, pg, arr.contiguous(), k, save=True)
+        out, saved = _forward(self, plan, params.flat, pg, arr.contiguous(), k, save=True,
+                              globals_=_globals_of(graphs, arr.shape[0]))
         gout = grad_fn(out)
         _backward(self, plan, params.flat, pg, saved, gout.contiguous(), k, params.grad)
         return out
@@ -482,6 +489,20 @@ class NequIP:
 
 def globals_present(graphs: GraphsTuple) -> bool:
     return graphs.globals is not None
+
+
+def _n_globals_of(graphs: GraphsTuple) -> int:
+    return 0 if graphs.globals is None else int(graphs.globals.shape[-1])
+
+
+def _globals_of(graphs: GraphsTuple, B: int) -> Optional[torch.Tensor]:
+    """(B, G) fp32 device tensor of graph-level features, or None."""
+    if graphs.globals is None:
+        return None
+    g = graphs.globals
+    if not isinstance(g, torch.Tensor) or not g.is_cuda:
+        raise RuntimeError("graphs.globals must be a CUDA tensor (this path has no CPU implementation)")
+    return g.reshape(B, -1).to(torch.float32).contiguous()
 
 
 def _n_edge_of(graphs: GraphsTuple) -> float:
@@ -496,8 +517,8 @@ def _n_edge_of(graphs: GraphsTuple) -> float:
 
 class _NequIPFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, theta, model, plan, pg, nodes, k):
-        out, saved = _forward(model, plan, theta.detach(), pg, nodes, k, save=True)
+    def forward(ctx, theta, model, plan, pg, nodes, k, globals_=None):
+        out, saved = _forward(model, plan, theta.detach(), pg, nodes, k, save=True, globals_=globals_)
         ctx.model, ctx.plan, ctx.pg, ctx.saved, ctx.k = model, plan, pg, saved, k
         ctx.theta = theta.detach()
         return out
@@ -506,11 +527,11 @@ class _NequIPFunction(torch.autograd.Function):
     def backward(ctx, gout):
         g = torch.zeros_like(ctx.theta)
         _backward(ctx.model, ctx.plan, ctx.theta, ctx.pg, ctx.saved, gout.contiguous(), ctx.k, g)
-        return g, None, None, None, None, None
+        return g, None, None, None, None, None, None
 
 
 def _forward(model: NequIP, plan: _Plan, theta: torch.Tensor, pg: PreparedGraph, nodes: torch.Tensor, k: float,
-             save: bool):
+             save: bool, globals_: Optional[torch.Tensor] = None):
     dev = nodes.device
     B, N, D = nodes.shape
     Nt, Et = B * N, B * pg.E
@@ -580,14 +601,23 @@ def _forward(model: NequIP, plan: _Plan, theta: torch.Tensor, pg: PreparedGraph,
     _mm(Nt, dh, tpr.d_live, 1.0, T0, 0, tpr.d_live, wexp, plan.Wro.off, dh, pre, 0, dh)
     pooled = torch.empty((B, dh), **f32)
     ops.pool_fwd(pre, B, N, dh, 1 if model.readout_agg == "mean" else 0, pooled)
-    zs, a, pro = [], pooled, 0
+    ln_stats = None
+    a = pooled
+    if plan.ln is not None:
+        if globals_ is None or globals_.shape != (B, plan.n_globals):
+            raise ValueError(f"graphs.globals must have shape ({B}, {plan.n_globals})")
+        a = torch.empty((B, dh + plan.n_globals), **f32)
+        ln_stats = torch.empty((B, 2), **f32)
+        ops.layernorm_fwd(pooled, globals_, theta, plan.ln[0], plan.ln[1], 1e-6, a, ln_stats)
+    zs, pro = [], 0
+    ro_in = a
     for (ko, bo, fan, hdim) in plan.ro_mlp:
         zl = torch.empty((B, hdim), **f32)
         _mm(B, hdim, fan, 1.0, a, 0, fan, theta, ko, hdim, zl, 0, hdim, pro=pro, pro_scale=1.0, epi=1, aux=theta,
             aux_off=bo)
         zs.append(zl)
         a, pro = zl, 1
-    saved.update(attrs=attrs, hr=hr, T0=T0, pooled=pooled, ro_z=zs)
+    saved.update(attrs=attrs, hr=hr, T0=T0, pooled=pooled, ro_z=zs, ro_in=ro_in, ln_stats=ln_stats, globals=globals_)
     return zs[-1], saved
 
 
@@ -624,7 +654,7 @@ def _backward(model: NequIP, plan: _Plan, theta: torch.Tensor, pg: PreparedGraph
         nl = len(plan.ro_mlp)
         for l in range(nl - 1, -1, -1):
             ko, bo, fan, hdim = plan.ro_mlp[l]
-            a_prev = zs[l - 1] if l > 0 else saved["pooled"]
+            a_prev = zs[l - 1] if l > 0 else saved["ro_in"]
             # dK = act(z_{l-1})^T dz ; db = colsum(dz)
             _mm(fan, hdim, B, 1.0, a_prev, 0, fan, dz, 0, hdim, gtheta, ko, hdim, ta=True, pro=1 if l > 0 else 0,
                 pro_scale=1.0)
@@ -637,6 +667,11 @@ def _backward(model: NequIP, plan: _Plan, theta: torch.Tensor, pg: PreparedGraph
                 _mm(B, fan, hdim, 1.0, dz, 0, hdim, theta, ko, hdim, dprev, 0, fan, tb=True)
             dz = dprev
         dhid = model.d_hidden
+        if plan.ln is not None:
+            d_pool = torch.empty((B, dhid), **f32)
+            ops.layernorm_bwd(saved["pooled"], saved["globals"], theta, plan.ln[0], saved["ln_stats"], dz, d_pool,
+                              gtheta, plan.ln[0], plan.ln[1])
+            dz = d_pool
         dpre = torch.empty((Nt, dhid), **f32)
         ops.pool_bwd(dz, B, N, dhid, 1 if model.readout_agg == "mean" else 0, dpre)
         T0 = saved["T0"]

@@ -311,6 +311,25 @@ def pool_bwd(gout, B, N, D, mode, gx):
     check(lib().eqnn_pool_bwd(_ptr(gout), B, N, D, mode, _ptr(gx), _stream()), "pool_bwd")
 
 
+def layernorm_fwd(a, g, scale_buf, scale_off, bias_off, eps, y, stats):
+    """y = LayerNorm(concat(a, g)) (nequip.py:201-205); scale/bias live in the flat parameter buffer."""
+    B, da = a.shape
+    dg = 0 if g is None else g.shape[1]
+    check(lib().eqnn_layernorm_fwd(_ptr(a), da, _ptr(g) if g is not None else None, dg, B,
+                                   C.c_void_p(scale_buf.data_ptr() + 4 * scale_off),
+                                   C.c_void_p(scale_buf.data_ptr() + 4 * bias_off), eps, _ptr(y), _ptr(stats), _stream()),
+          "layernorm_fwd")
+
+
+def layernorm_bwd(a, g, scale_buf, scale_off, stats, dy, d_a, grad_buf, dscale_off, dbias_off):
+    B, da = a.shape
+    dg = 0 if g is None else g.shape[1]
+    check(lib().eqnn_layernorm_bwd(_ptr(a), da, _ptr(g) if g is not None else None, dg, B,
+                                   C.c_void_p(scale_buf.data_ptr() + 4 * scale_off), _ptr(stats), _ptr(dy), _ptr(d_a),
+                                   C.c_void_p(grad_buf.data_ptr() + 4 * dscale_off),
+                                   C.c_void_p(grad_buf.data_ptr() + 4 * dbias_off), _stream()), "layernorm_bwd")
+
+
 def colsum(x, M, N, y, x_off=0, y_off=0):
     check(lib().eqnn_colsum(C.c_void_p(x.data_ptr() + 4 * x_off), M, N, C.c_void_p(y.data_ptr() + 4 * y_off),
                             _stream()), "colsum")

@@ -183,6 +183,13 @@ int eqnn_node_update_bwd(const float* A, int ld_a, int d_a, const float* h, int 
 /* out[b, :] = reduce_n x[b, n, :]   (mode 0 sum, 1 mean; nequip.py:196-199) and its backward */
 int eqnn_pool_fwd(const float* x, int B, int N, int D, int mode, float* out, eqnn_stream_t stream);
 int eqnn_pool_bwd(const float* gout, int B, int N, int D, int mode, float* gx, eqnn_stream_t stream);
+/* LayerNorm over x[b, :] = concat(a[b, :da], g[b, :dg]) (pooled node scalars | graph globals), nequip.py:201-205:
+ * y = (x - mean) * rsqrt(var + eps) * scale + bias, flax.linen.LayerNorm defaults (eps = 1e-6).  stats[b] = (mean,
+ * rstd) is kept for the backward, which returns d_a (B x da; the globals are data), dscale and dbias (da + dg). */
+int eqnn_layernorm_fwd(const float* a, int da, const float* g, int dg, int B, const float* scale, const float* bias,
+                       float eps, float* y, float* stats, eqnn_stream_t stream);
+int eqnn_layernorm_bwd(const float* a, int da, const float* g, int dg, int B, const float* scale, const float* stats,
+                       const float* dy, float* d_a, float* dscale, float* dbias, eqnn_stream_t stream);
 /* y[n] = sum_m x[m, n]  (bias gradients) */
 int eqnn_colsum(const float* x, int64_t M, int N, float* y, eqnn_stream_t stream);
 

@@ -153,6 +153,54 @@ def test_model_forward_and_gradients(lmax, agg, task, norm):
     assert zero_cols == set(np.where(np.abs(want_last).max(0) == 0)[0].tolist())
 
 
+def test_graph_globals_layernorm_branch():
+    """nequip.py:201-205: graph globals (the TPCF vector of train_cosmology.py) are concatenated to the pooled
+    scalars and LayerNorm-ed before the read-out MLP, whose first width scales with d_hidden + n_globals."""
+    from eqnn_jax_b200 import graph_utils as GU
+    from eqnn_jax_b200.nequip import IrrepsArray, NequIP
+    from eqnn_jax_b200.irreps import Irreps
+    rng = np.random.default_rng(5)
+    B, N, k, G_ = 3, 120, 10, 24
+    x = rng.normal(size=(B, N, 7)).astype(np.float32)
+    x[..., :3] = rng.uniform(-1.7, 1.7, size=(B, N, 3))
+    glob = rng.normal(size=(B, G_)).astype(np.float32)
+    kw = dict(d_hidden=64, l_max=2, sphharm_norm="integral", message_passing_steps=2, n_layers=2, n_outputs=2,
+              n_radial_basis=16, r_cutoff=0.6, message_passing_agg="mean", task="graph")
+    g = G.build_graph(x, glob, k)
+    cfg = NQ.NequIPConfig(**kw)
+    tree = NQ.init_params(cfg, IRR, seed=2, n_globals=G_)
+    tree["LayerNorm_0"]["scale"] = rng.uniform(0.5, 1.5, size=tree["LayerNorm_0"]["scale"].shape)
+    tree["LayerNorm_0"]["bias"] = rng.normal(size=tree["LayerNorm_0"]["bias"].shape) * 0.1
+    model = NequIP(**kw)
+    gg = GU.GraphsTuple(nodes=IrrepsArray(Irreps(IRR), torch.tensor(x).cuda()), edges=None,
+                        receivers=torch.tensor(g.receivers).cuda(), senders=torch.tensor(g.senders).cuda(),
+                        globals=torch.tensor(glob).cuda(), n_node=torch.tensor(g.n_node), n_edge=torch.tensor(g.n_edge))
+    params = model.init(0, gg)
+    assert params.tree["LayerNorm_0"]["scale"].shape == (64 + G_,)
+    assert params.tree["MLP_0"]["Dense_0"]["kernel"].shape == (64 + G_, 4 * (64 + G_))
+    params.load_tree(tree)
+    cot = rng.normal(size=(B, 2))
+    want, grads = _oracle(cfg, tree, g, IRR, cot)
+    flat = params.flat.requires_grad_(True)
+    out = model.apply(params, gg)
+    _close(out.detach().cpu().numpy(), want, "output")
+    (out * torch.tensor(cot, dtype=torch.float32).cuda()).sum().backward()
+    params.grad.copy_(flat.grad)
+    gt = params.grad_tree
+    ms = _module_scales(grads)
+    for path, w in _leaves(grads):
+        got = gt
+        for q in path:
+            got = got[q]
+        if np.abs(w.grad.numpy()).max() == 0:
+            assert float(got.abs().max()) == 0.0
+            continue
+        _close(got.cpu().numpy(), w.grad.numpy(), "grad " + "/".join(path), scale=ms[path[0]])
+    # fast path (no autograd) gives the same output
+    out2 = model.forward_backward(params, gg, lambda o: torch.tensor(cot, dtype=torch.float32).cuda())
+    assert torch.equal(out2, out.detach())
+
+
 @pytest.mark.parametrize("flags", [dict(tensor_cores=False, fuse_node_update=False),
                                    dict(tensor_cores=True, fuse_node_update=False),
                                    dict(tensor_cores=False, fuse_node_update=True)])
