@@ -394,9 +394,16 @@ struct WgradP {
   float* partial;   // [gridDim.x][MI][NPAD]
 };
 
-// wgrad thread layout: 8 drain warps, 1 MMA warp, 8 transform warps, 1 loader warp
-constexpr int WG_LOADER_WARP = MMA_WARP + 1 + PROD_WARPS;    // warp 17
-constexpr int WG_THREADS = (WG_LOADER_WARP + 1) * 32;         // 576
+// wgrad thread layout (warpgroup-aligned so that registers can be re-balanced with setmaxnreg):
+//   warps 0..7 drain (TMEM -> fp32 register accumulators, 64 columns each: register-hungry),
+//   warps 8..19 transform (raw ring -> split operands: latency-bound, few registers), warp 20 MMA, warp 21 loader
+constexpr int WG_TW = 12;                                     // transform warps
+constexpr int WG_PT = WG_TW * 32;                             // 384 transform threads
+constexpr int WG_TW0 = EPI_WARPS;                             // first transform warp (8)
+constexpr int WG_MMA_WARP = WG_TW0 + WG_TW;                   // warp 20
+constexpr int WG_LOADER_WARP = WG_MMA_WARP + 1;               // warp 21
+constexpr int WG_THREADS = (WG_LOADER_WARP + 1) * 32;         // 704 threads, 80 registers each at launch
+constexpr int WG_REGS_DRAIN = 112, WG_REGS_TRANSFORM = 56;    // launch: 80/thread; 8*(112-80) <= 12*(80-56)
 
 template <int MI, int N, int GMODE>
 struct WgradCfg {
@@ -446,7 +453,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const WgradP p)
 
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
-      mbar_init(a_full(s), PROD_WARPS);
+      mbar_init(a_full(s), WG_TW);
       mbar_init(a_empty(s), 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -455,11 +462,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const WgradP p)
     }
     for (int s = 0; s < RAW_NS; ++s) {
       mbar_init(r_full(s), 1);
-      mbar_init(r_empty(s), PROD_WARPS);
+      mbar_init(r_empty(s), WG_TW);
     }
     mbar_fence_init();
   }
-  if (warp == MMA_WARP) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == WG_MMA_WARP) tmem_alloc(tmem_slot, TMEM_COLS);
   if (MI < 128) {   // rows MI..127 of the (padded) A operand are never written by the producers: zero them once
     for (uint32_t o = tid * 16; o < NSTAGE * STAGE_W; o += WG_THREADS * 16)
       *reinterpret_cast<float4*>(gen_base + o) = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -500,11 +507,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const WgradP p)
         bulk_g2s(gdst + lane * 128u, p.G + (int64_t)lane * p.ldg + e0, rows * 4u, r_full(rs));   // 32 edges of column n
       }
     }
-  } else if (warp >= MMA_WARP + 1) {
+  } else if (warp >= WG_TW0 && warp < WG_MMA_WARP) {
     // =========================== transform: raw ring -> split (hi, lo) operand stages ===========================
-    const int pt = tid - (MMA_WARP + 1) * 32;
-    constexpr int XV = MI / 32;                         // float4 of X per thread per chunk
-    constexpr int GV = (GMODE == 0) ? N / 32 : 1;       // float4 of G per thread per chunk
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WG_REGS_TRANSFORM));
+    const int pt = tid - WG_TW0 * 32;
+    constexpr int XI = (8 * MI + WG_PT - 1) / WG_PT;                       // float4 of X per thread per chunk
+    constexpr int GI = (GMODE == 0) ? (8 * N + WG_PT - 1) / WG_PT : 1;     // float4 of G per thread per chunk
     auto put = [&](uint32_t off_hi, uint32_t off_lo, const float4& v, auto act) {
       float4 hi, lo;
       act_split4<decltype(act)::value>(v, p.pro_scale, hi, lo);
@@ -522,20 +530,26 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const WgradP p)
       const uint8_t* graw = xraw + Cfg::XRAW;
       const uint32_t sa = s * STAGE_W, sb = sa + 2 * A_HALF_W;
 #pragma unroll
-      for (int i = 0; i < XV; ++i) {
-        const int f = pt + i * PT, row = f / (MI / 4), c4 = f % (MI / 4);
-        const float4 v = (row < rows) ? *reinterpret_cast<const float4*>(xraw + (uint32_t)f * 16u) : zero4;
-        // MN-major slab [m-block of 32][32 k-rows]: 4-row atoms, 32-byte-chunk swizzle
-        const uint32_t off = (c4 >> 3) * 4096 + sw128_base32(row, c4 & 7);
-        put(sa + off, sa + A_HALF_W + off, v, std::integral_constant<bool, PRO == 1>{});
+      for (int i = 0; i < XI; ++i) {
+        const int f = pt + i * WG_PT;
+        if (f < 8 * MI) {
+          const int row = f / (MI / 4), c4 = f % (MI / 4);
+          const float4 v = (row < rows) ? *reinterpret_cast<const float4*>(xraw + (uint32_t)f * 16u) : zero4;
+          // MN-major slab [m-block of 32][32 k-rows]: 4-row atoms, 32-byte-chunk swizzle
+          const uint32_t off = (c4 >> 3) * 4096 + sw128_base32(row, c4 & 7);
+          put(sa + off, sa + A_HALF_W + off, v, std::integral_constant<bool, PRO == 1>{});
+        }
       }
       if (GMODE == 0) {
 #pragma unroll
-        for (int i = 0; i < GV; ++i) {
-          const int f = pt + i * PT, row = f / (N / 4), c4 = f % (N / 4);
-          const float4 v = (row < rows) ? *reinterpret_cast<const float4*>(graw + (uint32_t)f * 16u) : zero4;
-          const uint32_t off = (c4 >> 3) * 4096 + sw128_base32(row, c4 & 7);
-          put(sb + off, sb + B_HALF_W + off, v, std::false_type{});
+        for (int i = 0; i < GI; ++i) {
+          const int f = pt + i * WG_PT;
+          if (f < 8 * N) {
+            const int row = f / (N / 4), c4 = f % (N / 4);
+            const float4 v = (row < rows) ? *reinterpret_cast<const float4*>(graw + (uint32_t)f * 16u) : zero4;
+            const uint32_t off = (c4 >> 3) * 4096 + sw128_base32(row, c4 & 7);
+            put(sb + off, sb + B_HALF_W + off, v, std::false_type{});
+          }
         }
       } else if (pt < 128) {
         const int n = pt >> 3, c4 = pt & 7;             // K-major: row n, 32 edges per 128-byte row
@@ -557,7 +571,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const WgradP p)
         mbar_arrive(r_empty(rs));     // raw slot may be refilled
       }
     }
-  } else if (warp == MMA_WARP) {
+  } else if (warp == WG_MMA_WARP) {
     if (lane == 0 && total > 0) {
       constexpr uint32_t idesc = make_idesc_tf32(128, N, 1, GMODE == 0 ? 1 : 0);
       for (uint32_t g = 0; g < total; ++g) {
@@ -593,7 +607,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const WgradP p)
       }
     }
     __syncwarp();
-  } else if (warp < EPI_ACTIVE) {
+  } else if (warp < EPI_WARPS) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(WG_REGS_DRAIN));
+    if (warp < EPI_ACTIVE) {
     // ============== epilogue: drain TMEM segments into fp32 registers, then partial[cta] ==============
     const int quarter = warp & 3, half = warp >> 2;
     const int row = quarter * 32 + lane;               // = input-feature index i
@@ -624,10 +640,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const WgradP p)
 #pragma unroll
       for (int j = 0; j < CW; j += 4) *reinterpret_cast<float4*>(out + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
     }
+    }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == MMA_WARP) {
+  if (warp == WG_MMA_WARP) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
