@@ -355,15 +355,25 @@ __global__ void __launch_bounds__(NT, 3) node_bwd_kernel(const NodeP p) {
 }
 
 // dW1 = alpha1 * sum partial rows < d_a ; dW2 = sum partial rows >= d_a ; dW3 = sum partial tail
-__global__ void node_wgrad_reduce_kernel(const float* __restrict__ partial, int n_parts, int d_a, int d_h, int d_z,
-                                         int d_g, float alpha1, float* __restrict__ dW1, float* __restrict__ dW2,
-                                         float* __restrict__ dW3) {
+__global__ void __launch_bounds__(256) node_wgrad_reduce_kernel(const float* __restrict__ partial, int n_parts, int d_a,
+                                                                int d_h, int d_z, int d_g, float alpha1,
+                                                                float* __restrict__ dW1, float* __restrict__ dW2,
+                                                                float* __restrict__ dW3) {
+  // 32 outputs x 8 part-groups per block; the 8 group sums are combined in a fixed order (deterministic)
+  __shared__ float red[8][33];
   const int d_in = d_a + d_h;
   const int tot = d_in * d_z + d_g * d_h;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= tot) return;
-  float sum = 0.f;
-  for (int q = 0; q < n_parts; ++q) sum += partial[(size_t)q * tot + i];
+  const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;
+  float s = 0.f;
+  if (i < tot)
+    for (int q = grp; q < n_parts; q += 8) s += partial[(size_t)q * tot + i];
+  red[grp][lane] = s;
+  __syncthreads();
+  if (grp != 0 || i >= tot) return;
+  float sum = red[0][lane];
+#pragma unroll
+  for (int g = 1; g < 8; ++g) sum += red[g][lane];
   if (i < d_a * d_z) dW1[i] = alpha1 * sum;     // forward used alpha1*W1: d/dW1 = alpha1 * d/d(alpha1 W1)
   else if (i < d_in * d_z) { if (dW2) dW2[i - d_a * d_z] = sum; }
   else dW3[i - d_in * d_z] = sum;
@@ -455,7 +465,7 @@ extern "C" int eqnn_node_update_bwd(const float* A, int ld_a, int d_a, const flo
   EQNN_CUDA(cudaFuncSetAttribute(node_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaStream_t st = as_stream(stream);
   node_bwd_kernel<<<grid, NT, smem, st>>>(p);
-  node_wgrad_reduce_kernel<<<(unsigned)((per + 255) / 256), 256, 0, st>>>(p.partial, grid, d_a, d_h, p.d_z, p.d_g,
+  node_wgrad_reduce_kernel<<<(unsigned)((per + 31) / 32), 256, 0, st>>>(p.partial, grid, d_a, d_h, p.d_z, p.d_g,
                                                                         alpha1, dW1, dW2, dW3);
   EQNN_CHECK_LAUNCH_N(2);
   return EQNN_OK;

@@ -650,14 +650,27 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const WgradP p)
   }
 }
 
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int n_parts, int MI, int NPAD, int n_valid,
-                                    float alpha, float* __restrict__ out, int64_t ldo) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= MI * n_valid) return;
-  const int r = i / n_valid, c = i - r * n_valid;
+// out = alpha * sum over the per-CTA partials.  32 outputs x 8 part-groups per block: every group walks its share of
+// the partials (coalesced across the 32 outputs), the 8 group sums are added in a fixed order (deterministic).
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, int n_parts, int MI,
+                                                           int NPAD, int n_valid, float alpha, float* __restrict__ out,
+                                                           int64_t ldo) {
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;
+  const bool ok = i < MI * n_valid;
+  const int r = ok ? i / n_valid : 0, c = ok ? i - r * n_valid : 0;
   float s = 0.f;
-  for (int q = 0; q < n_parts; ++q) s += partial[((size_t)q * MI + r) * NPAD + c];
-  out[(int64_t)r * ldo + c] = alpha * s;
+  if (ok)
+    for (int q = grp; q < n_parts; q += 8) s += partial[((size_t)q * MI + r) * NPAD + c];
+  red[grp][lane] = s;
+  __syncthreads();
+  if (grp == 0 && ok) {
+    float t = red[0][lane];
+#pragma unroll
+    for (int g = 1; g < 8; ++g) t += red[g][lane];
+    out[(int64_t)r * ldo + c] = alpha * t;
+  }
 }
 
 template <int MI, int N, int GMODE, int PRO>
@@ -717,7 +730,7 @@ int eqnn_tc_wgrad_try(int64_t M, int64_t N, int64_t K, float alpha, const float*
   }
   if (rc) return -rc;
   const int tot = (int)(M * N);
-  wgrad_reduce_kernel<<<(tot + 255) / 256, 256, 0, st>>>(p.partial, grid, (int)M, npad, (int)N, alpha, C, scm);
+  wgrad_reduce_kernel<<<(tot + 31) / 32, 256, 0, st>>>(p.partial, grid, (int)M, npad, (int)N, alpha, C, scm);
   eqnn_count_launches(1);
   return 1;
 }
