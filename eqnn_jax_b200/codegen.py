@@ -93,12 +93,21 @@ def _emit_bwd(plan: TPPlan) -> List[str]:
         out.append("    {")
         for t, (i, j, k, c) in enumerate(terms):
             out.append(f"      const float c{tag}_{t} = {_f(c)} * Y[{l2 * l2 + j}];")
+        by_i = {}
+        for t, (i, j, k, c) in enumerate(terms):
+            by_i.setdefault(i, []).append((t, k))
         for col in cols:
+            # s_i = sum over the terms that touch x[i] of c_t * g[k]: one FMA per term, then dw += s_i x[i], dx[i] += w s_i
             out.append("      {")
-            out.append("        float acc = 0.0f, q;")
-            for t, (i, j, k, c) in enumerate(terms):
-                out.append(f"        q = c{tag}_{t} * g[{col.live_off + k}]; acc = fmaf(q, x[{col.x_off + i}], acc); "
-                           f"dx[{col.x_off + i}] = fmaf(q, w[{col.live}], dx[{col.x_off + i}]);")
+            out.append("        float acc = 0.0f, s;")
+            for i, tk in by_i.items():
+                t0, k0 = tk[0]
+                line = f"        s = c{tag}_{t0} * g[{col.live_off + k0}];"
+                for t, k in tk[1:]:
+                    line += f" s = fmaf(c{tag}_{t}, g[{col.live_off + k}], s);"
+                out.append(line)
+                out.append(f"        acc = fmaf(s, x[{col.x_off + i}], acc); "
+                           f"dx[{col.x_off + i}] = fmaf(s, w[{col.live}], dx[{col.x_off + i}]);")
             out.append(f"        dw[{col.live}] = acc;")
             out.append("      }")
         out.append("    }")

@@ -78,7 +78,14 @@ tpconv_fwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
         const int lo = max(s_rowptr[row], base) - base;
         const int hi = min(s_rowptr[row + 1], base + TPC_THREADS) - base;
         float a = acc[it];
-        for (int q = lo; q < hi; ++q) a += sm[q * STRIDE + comp];
+        const float* col = sm + comp;
+        int q = lo;
+        for (; q + 3 < hi; q += 4) {                 // same ascending order, a quarter of the loop overhead
+          const float v0 = col[q * STRIDE], v1 = col[(q + 1) * STRIDE], v2 = col[(q + 2) * STRIDE],
+                      v3 = col[(q + 3) * STRIDE];
+          a = (((a + v0) + v1) + v2) + v3;
+        }
+        for (; q < hi; ++q) a += col[q * STRIDE];
         acc[it] = a;
       }
     }
