@@ -273,6 +273,140 @@ int make_cell(Cell3& cl, const float* cell, const float* cell_inv) {
 
 constexpr int COLSUM_PARTS = 296;
 
+
+// ---- node layouts with velocities and scalar attributes, nodes[n] = (x, v, h) (egnn.py:38-60, 198-229) ----
+
+// edge-MLP input U[p] = [feats[p] | h[sender(p)] | h[receiver(p)]] in receiver-sorted order: warp per receiver row
+__global__ void __launch_bounds__(256) egnn_edge_input_fwd_kernel(const float* __restrict__ feats, int nf,
+                                                                  const float* __restrict__ h, int ld_h, int dh,
+                                                                  const int32_t* __restrict__ rowptr,
+                                                                  const int32_t* __restrict__ src, int n_nodes,
+                                                                  float* __restrict__ U) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= n_nodes) return;
+  const int K0 = nf + 2 * dh;
+  const int p0 = rowptr[row], p1 = rowptr[row + 1];
+  for (int64_t i = (int64_t)p0 * K0 + lane; i < (int64_t)p1 * K0; i += 32) {
+    const int64_t p = i / K0;
+    const int c = (int)(i - p * K0);
+    float v;
+    if (c < nf) v = feats[p * nf + c];
+    else if (c < nf + dh) v = h[(size_t)src[p] * ld_h + (c - nf)];
+    else v = h[(size_t)row * ld_h + (c - nf - dh)];
+    U[i] = v;
+  }
+}
+
+// backward of the concatenation: dfeats (copy), receiver part summed over the row (+= into dh_out), sender part
+// stored at the ORIGINAL edge id for the sender-sorted gather that follows
+__global__ void __launch_bounds__(256) egnn_edge_input_bwd_kernel(const float* __restrict__ dU, int nf, int dh,
+                                                                  const int32_t* __restrict__ rowptr,
+                                                                  const int32_t* __restrict__ perm, int n_nodes,
+                                                                  float* __restrict__ dfeats, float* __restrict__ dhs_e,
+                                                                  float* __restrict__ dh_out, int ld_dh) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= n_nodes) return;
+  const int K0 = nf + 2 * dh;
+  const int p0 = rowptr[row], p1 = rowptr[row + 1];
+  if (dfeats)
+    for (int64_t i = (int64_t)p0 * nf + lane; i < (int64_t)p1 * nf; i += 32) {
+      const int64_t p = i / nf;
+      dfeats[i] = dU[p * K0 + (i - p * nf)];
+    }
+  for (int64_t i = (int64_t)p0 * dh + lane; i < (int64_t)p1 * dh; i += 32) {
+    const int64_t p = i / dh;
+    dhs_e[(size_t)perm[p] * dh + (i - p * dh)] = dU[p * K0 + nf + (i - p * dh)];
+  }
+  for (int c = 0; c < dh; ++c) {                       // receiver end: lanes over the row's edges, shuffle reduce
+    float a = 0.f;
+    for (int p = p0 + lane; p < p1; p += 32) a += dU[(size_t)p * K0 + nf + dh + c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) dh_out[(size_t)row * ld_dh + c] += a;
+  }
+}
+
+// out[s, :w] += sum over the edges sent by s of rows[e, :w]   (sender-sorted CSR; fixed order)
+__global__ void egnn_segment_gather_add_kernel(const float* __restrict__ rows, int w, const int32_t* __restrict__ rowptr_s,
+                                               const int32_t* __restrict__ perm_s, int n_nodes, float* __restrict__ out,
+                                               int ld_out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)n_nodes * w) return;
+  const int64_t s = i / w;
+  const int c = (int)(i - s * w);
+  float a = 0.f;
+  for (int q = rowptr_s[s]; q < rowptr_s[s + 1]; ++q) a += rows[(size_t)perm_s[q] * w + c];
+  out[(size_t)s * ld_out + c] += a;
+}
+
+// base[n] = sx[n] * x[n] + sv[n] * v[n]   (sx == NULL: 1, coupled update egnn.py:223-224; else :216-221)
+__global__ void egnn_xv_base_kernel(const float* __restrict__ nodes, int F, const float* __restrict__ sx,
+                                    const float* __restrict__ sv, int64_t n, float* __restrict__ base) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * 3) return;
+  const int64_t node = i / 3;
+  const int c = (int)(i - node * 3);
+  const float a = sx ? sx[node] : 1.f;
+  base[i] = a * nodes[node * F + c] + sv[node] * nodes[node * F + 3 + c];
+}
+
+// nodes_next[n] = (x' (already written), v (unchanged, :229), h + ph)
+__global__ void egnn_node_assemble_kernel(const float* __restrict__ nodes, int F, int dh, const float* __restrict__ ph,
+                                          int64_t n, float* __restrict__ nodes_next) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int w = F - 3;
+  if (i >= n * w) return;
+  const int64_t node = i / w;
+  const int c = 3 + (int)(i - node * w);
+  float v = nodes[node * F + c];
+  if (c >= 6) v += ph[node * dh + (c - 6)];
+  nodes_next[node * F + c] = v;
+}
+
+// backward of the node update given g = dL/dx' (cols 0..2 of dnext), the pass-through gradients of v and h in dnext,
+// and mix = g + geometry gradient of x (NULL in the first step: no input gradient needed, din may then be NULL):
+//   dsx = g.x, dsv = g.v ; din = (sx g + (mix - g), sv g + dnext_v, dnext_h)
+__global__ void egnn_xv_bwd_kernel(const float* __restrict__ nodes, int F, const float* __restrict__ sx,
+                                   const float* __restrict__ sv, const float* __restrict__ dnext,
+                                   const float* __restrict__ mix, int64_t n, float* __restrict__ din,
+                                   float* __restrict__ dsx, float* __restrict__ dsv) {
+  const int64_t node = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (node >= n) return;
+  const float* nd = nodes + node * F;
+  const float* dn = dnext + node * F;
+  float gx = 0.f, gv = 0.f;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    gx = fmaf(dn[c], nd[c], gx);
+    gv = fmaf(dn[c], nd[3 + c], gv);
+  }
+  if (dsx) dsx[node] = gx;
+  dsv[node] = gv;
+  if (din) {
+    float* o = din + node * F;
+    const float a = sx ? sx[node] : 1.f, b = sv[node];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float g = dn[c];
+      o[c] = a * g + (mix ? (mix[node * 3 + c] - g) : 0.f);
+      o[3 + c] = b * g + dn[3 + c];
+    }
+    for (int c = 6; c < F; ++c) o[c] = dn[c];
+  }
+}
+
+// dst[n, c0d + j] = src[n, c0s + j], j < w  (strided column block copy)
+__global__ void copy_cols_kernel(const float* __restrict__ src, int ld_s, int c0s, int w, int64_t n,
+                                 float* __restrict__ dst, int ld_d, int c0d) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * w) return;
+  const int64_t r = i / w;
+  const int j = (int)(i - r * w);
+  dst[r * ld_d + c0d + j] = src[r * ld_s + c0s + j];
+}
+
 }  // namespace
 
 extern "C" int eqnn_egnn_geom_fwd(const float* pos, int ld_pos, int n_nodes, const int32_t* rowptr,
@@ -329,6 +463,72 @@ extern "C" int eqnn_egnn_sender_acc(const float* dre, const int32_t* rowptr_s, c
   if (n_nodes <= 0) return EQNN_OK;
   egnn_sender_acc_kernel<<<(unsigned)ceil_div64(n_nodes, 256), 256, 0, as_stream(stream)>>>(
       reinterpret_cast<const float4*>(dre), rowptr_s, perm_s, n_nodes, dpos);
+  EQNN_CHECK_LAUNCH();
+  return EQNN_OK;
+}
+
+extern "C" int eqnn_egnn_edge_input_fwd(const float* feats, int nf, const float* h, int ld_h, int dh,
+                                        const int32_t* rowptr, const int32_t* src, int n_nodes, float* U,
+                                        eqnn_stream_t stream) {
+  EQNN_CHECK_ARG(feats && h && rowptr && src && U && nf >= 1 && dh >= 1 && ld_h >= dh, "egnn_edge_input_fwd: bad argument");
+  if (n_nodes <= 0) return EQNN_OK;
+  egnn_edge_input_fwd_kernel<<<(unsigned)ceil_div64((int64_t)n_nodes * 32, 256), 256, 0, as_stream(stream)>>>(
+      feats, nf, h, ld_h, dh, rowptr, src, n_nodes, U);
+  EQNN_CHECK_LAUNCH();
+  return EQNN_OK;
+}
+
+extern "C" int eqnn_egnn_edge_input_bwd(const float* dU, int nf, int dh, const int32_t* rowptr, const int32_t* perm,
+                                        const int32_t* rowptr_s, const int32_t* perm_s, int n_nodes, float* dfeats,
+                                        float* dhs_e, float* dh_out, int ld_dh, eqnn_stream_t stream) {
+  EQNN_CHECK_ARG(dU && rowptr && perm && rowptr_s && perm_s && dhs_e && dh_out && nf >= 1 && dh >= 1 && ld_dh >= dh,
+                 "egnn_edge_input_bwd: bad argument");
+  if (n_nodes <= 0) return EQNN_OK;
+  cudaStream_t st = as_stream(stream);
+  egnn_edge_input_bwd_kernel<<<(unsigned)ceil_div64((int64_t)n_nodes * 32, 256), 256, 0, st>>>(
+      dU, nf, dh, rowptr, perm, n_nodes, dfeats, dhs_e, dh_out, ld_dh);
+  egnn_segment_gather_add_kernel<<<(unsigned)ceil_div64((int64_t)n_nodes * dh, 256), 256, 0, st>>>(
+      dhs_e, dh, rowptr_s, perm_s, n_nodes, dh_out, ld_dh);
+  EQNN_CHECK_LAUNCH_N(2);
+  return EQNN_OK;
+}
+
+extern "C" int eqnn_egnn_xv_base(const float* nodes, int F, const float* sx, const float* sv, int64_t n, float* base,
+                                 eqnn_stream_t stream) {
+  EQNN_CHECK_ARG(nodes && sv && base && F >= 6, "egnn_xv_base: bad argument");
+  if (n <= 0) return EQNN_OK;
+  egnn_xv_base_kernel<<<(unsigned)ceil_div64(n * 3, 256), 256, 0, as_stream(stream)>>>(nodes, F, sx, sv, n, base);
+  EQNN_CHECK_LAUNCH();
+  return EQNN_OK;
+}
+
+extern "C" int eqnn_egnn_node_assemble(const float* nodes, int F, int dh, const float* ph, int64_t n, float* nodes_next,
+                                       eqnn_stream_t stream) {
+  EQNN_CHECK_ARG(nodes && nodes_next && F == 6 + dh && (ph || dh == 0), "egnn_node_assemble: bad argument");
+  if (n <= 0) return EQNN_OK;
+  egnn_node_assemble_kernel<<<(unsigned)ceil_div64(n * (F - 3), 256), 256, 0, as_stream(stream)>>>(nodes, F, dh, ph, n,
+                                                                                                 nodes_next);
+  EQNN_CHECK_LAUNCH();
+  return EQNN_OK;
+}
+
+extern "C" int eqnn_egnn_xv_bwd(const float* nodes, int F, const float* sx, const float* sv, const float* dnext,
+                                const float* mix, int64_t n, float* din, float* dsx, float* dsv, eqnn_stream_t stream) {
+  EQNN_CHECK_ARG(nodes && sv && dnext && dsv && F >= 6 && (!sx || dsx), "egnn_xv_bwd: bad argument");
+  if (n <= 0) return EQNN_OK;
+  egnn_xv_bwd_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, as_stream(stream)>>>(nodes, F, sx, sv, dnext, mix, n, din,
+                                                                                 dsx, dsv);
+  EQNN_CHECK_LAUNCH();
+  return EQNN_OK;
+}
+
+extern "C" int eqnn_copy_cols(const float* src, int ld_src, int col_src, int width, int64_t n, float* dst, int ld_dst,
+                              int col_dst, eqnn_stream_t stream) {
+  EQNN_CHECK_ARG(src && dst && width >= 1 && col_src >= 0 && col_dst >= 0 && ld_src >= col_src + width &&
+                     ld_dst >= col_dst + width, "copy_cols: bad argument");
+  if (n <= 0) return EQNN_OK;
+  copy_cols_kernel<<<(unsigned)ceil_div64(n * width, 256), 256, 0, as_stream(stream)>>>(src, ld_src, col_src, width, n,
+                                                                                       dst, ld_dst, col_dst);
   EQNN_CHECK_LAUNCH();
   return EQNN_OK;
 }

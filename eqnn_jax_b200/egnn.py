@@ -11,8 +11,14 @@ Per message-passing step, edges in receiver-sorted order:
     t   = Dense_1(phi_x(m))   tcgen05 3xTF32 GEMMs                      egnn.py:70-79,107
     x'  = wrap(x + agg clip(r_ij t))   eqnn_egnn_coord_fwd              egnn.py:110-114,146-150 + jraph segment reduce
 With 3-d nodes the aggregated messages m_i are never read (egnn.py:143-150), so they are not aggregated
-(XLA removes that dead reduction under jit as well).  soft_edges (egnn.py:101-105) is supported.  Not built yet:
-scalar/velocity node attributes, globals, max aggregation -> NotImplementedError, never a silent fallback.
+(XLA removes that dead reduction under jit as well).  soft_edges (egnn.py:101-105) is supported.
+
+The (x, v, h) layout -- ``positions_only=False`` with >= 7 node features, the configuration of the reference's own
+equivariance test (tests/test_equivariance.py:224-250) -- is supported as well: the edge MLP reads
+[bessel | h_sender | h_receiver] (egnn.py:47-60), the node update is v' = phi_v(h) v + agg, x' = wrap(phi_xx(h) x + v')
+(or x + v'), h' = h + phi_h(h), and (x', v, h') is returned (egnn.py:198-229); m_i is unused there too.
+Not built yet: (x, h) and (x, v) layouts (they consume the aggregated messages), globals, max aggregation ->
+NotImplementedError, never a silent fallback.
 """
 from __future__ import annotations
 
@@ -51,9 +57,18 @@ class EGNN:
     tensor_cores: bool = True     # not a reference field: tcgen05 3xTF32 GEMMs (False: fp32 CUDA-core GEMMs)
 
     # ---- static layout ------------------------------------------------------------------
+    def _variant(self, n_feat: int) -> Tuple[bool, int]:
+        """(has velocities, number of scalar attributes) for a node-feature width."""
+        if self.positions_only:
+            if n_feat != 3:
+                raise NotImplementedError("B200 EGNN: positions_only=True is built for 3-d nodes (no scalar attributes)")
+            return False, 0
+        if n_feat < 7:
+            raise NotImplementedError("B200 EGNN: positions_only=False needs (x, v, h) nodes with >= 1 scalar attribute")
+        return True, n_feat - 6
+
     def _check(self, n_feat: int) -> None:
-        if not self.positions_only or n_feat != 3:
-            raise NotImplementedError("B200 EGNN covers positions_only=True on 3-d nodes (the benchmarked configuration)")
+        self._variant(n_feat)
         if self.activation != "gelu":
             raise NotImplementedError("only activation='gelu' has a B200 kernel on this path")
         if self.message_passing_agg not in ("sum", "mean") or self.readout_agg not in ("sum", "mean"):
@@ -61,9 +76,10 @@ class EGNN:
         if self.n_layers < 2:
             raise NotImplementedError("n_layers >= 2 expected")
 
-    def _layout(self):
+    def _layout(self, n_feat: int = 3):
         d, L = self.d_hidden, self.n_layers
         nf = self.n_radial_basis if self.n_radial_basis > 0 else 1
+        vel, dh = self._variant(n_feat)
         layout: List[Tuple[Tuple[str, ...], Tuple[int, ...], int]] = []
         off = 0
 
@@ -74,10 +90,18 @@ class EGNN:
             off += int(np.prod(shape))
             return o
 
+        def add_mlp(mi, fan, widths):
+            out = []
+            for l, w in enumerate(widths):
+                out.append((add((f"MLP_{mi}", f"Dense_{l}", "kernel"), (fan, w)),
+                            add((f"MLP_{mi}", f"Dense_{l}", "bias"), (w,)), fan, w))
+                fan = w
+            return out
+
         steps, mi = [], 0
         for s in range(self.message_passing_steps):
             st = {"phi_e": [], "phi_x": []}
-            fan = nf
+            fan = nf + 2 * dh
             for l in range(L):
                 st["phi_e"].append((add((f"MLP_{mi}", f"Dense_{l}", "kernel"), (fan, d)),
                                     add((f"MLP_{mi}", f"Dense_{l}", "bias"), (d,)), fan))
@@ -92,20 +116,22 @@ class EGNN:
             st["phi_a"] = (add((f"MLP_{mi}", "Dense_0", "kernel"), (d, d)),
                            add((f"MLP_{mi}", "Dense_0", "bias"), (d,))) if self.soft_edges else None
             mi += 1
+            if vel:                                          # node function, egnn.py:208-222
+                st["phi_v"] = add_mlp(mi, dh, [d] * (L - 1) + [1]); mi += 1
+                st["phi_h"] = add_mlp(mi, dh, [d] * (L - 1) + [dh]); mi += 1
+                st["phi_xx"] = None
+                if self.decouple_pos_vel_updates:
+                    st["phi_xx"] = add_mlp(mi, dh, [d] * (L - 1) + [1]); mi += 1
             steps.append(st)
         readout = []
         if self.task == "graph":
-            ws = [self.mlp_readout_widths[0] * 3] + [w * d for w in self.mlp_readout_widths[1:]] + [self.n_outputs]
-            fan = 3
-            for l, h in enumerate(ws):
-                readout.append((add((f"MLP_{mi}", f"Dense_{l}", "kernel"), (fan, h)),
-                                add((f"MLP_{mi}", f"Dense_{l}", "bias"), (h,)), fan, h))
-                fan = h
+            ws = [self.mlp_readout_widths[0] * n_feat] + [w * d for w in self.mlp_readout_widths[1:]] + [self.n_outputs]
+            readout = add_mlp(mi, n_feat, ws)
         return layout, steps, readout, off
 
     def init(self, rng: Union[int, np.random.Generator], graphs: GraphsTuple) -> FlatParams:
         self._check(graphs.nodes.shape[-1])
-        layout, steps, readout, n = self._layout()
+        layout, steps, readout, n = self._layout(graphs.nodes.shape[-1])
         rng = np.random.default_rng(rng) if not isinstance(rng, np.random.Generator) else rng
         host = np.zeros((n,), dtype=np.float32)
         for path, shape, off in layout:
@@ -149,25 +175,60 @@ class EGNN:
 
     __call__ = apply
 
+    # ---- N-row MLPs of the node function (models/mlp.py: Dense + bias, gelu between layers) ----------------
+    def _mlp_fwd(self, theta, layers, a, a_off, lda, M):
+        zs, pro = [], 0
+        for (ko, bo, fan, w) in layers:
+            Z = torch.empty((M, w), dtype=torch.float32, device=theta.device)
+            _mm(M, w, fan, 1.0, a, a_off, lda, theta, ko, w, Z, 0, w, pro=pro, pro_scale=1.0, epi=1, aux=theta, aux_off=bo,
+                tag="egnn_node_mlp", tf32x3=self.tensor_cores)
+            zs.append(Z)
+            a, a_off, lda, pro = Z, 0, w, 1
+        return zs
+
+    def _mlp_bwd(self, theta, gtheta, layers, zs, a0, a0_off, lda0, M, dz, din=None):
+        """dz: dense (M, width_last).  din = (tensor, offset, ld): the input gradient is ACCUMULATED there."""
+        for l in range(len(layers) - 1, -1, -1):
+            ko, bo, fan, w = layers[l]
+            a_prev, ap_off, ap_ld, pro = (zs[l - 1], 0, fan, 1) if l > 0 else (a0, a0_off, lda0, 0)
+            _mm(fan, w, M, 1.0, a_prev, ap_off, ap_ld, dz, 0, w, gtheta, ko, w, ta=True, pro=pro, pro_scale=1.0,
+                tag="egnn_node_mlp", tf32x3=self.tensor_cores)
+            ops.colsum_tall(dz, M, w, gtheta, y_off=bo)
+            if l > 0:
+                dprev = torch.empty((M, fan), dtype=torch.float32, device=theta.device)
+                _mm(M, fan, w, 1.0, dz, 0, w, theta, ko, w, dprev, 0, fan, tb=True, epi=2, aux=zs[l - 1], ld_aux=fan,
+                    epi_scale=1.0, tag="egnn_node_mlp", tf32x3=self.tensor_cores)
+                dz = dprev
+            elif din is not None:
+                t, off, ld = din
+                _mm(M, fan, w, 1.0, dz, 0, w, theta, ko, w, t, off, ld, tb=True, accumulate=True, tag="egnn_node_mlp")
+
     def _forward(self, theta, x, B, N, E, csr):
         rowptr, perm, src, rowptr_s, perm_s = csr
         dev = x.device
         f32 = dict(dtype=torch.float32, device=dev)
-        layout, steps, readout, _ = self._layout()
+        F = x.shape[-1]
+        vel, dh = self._variant(F)
+        layout, steps, readout, _ = self._layout(F)
         Nt, Et = B * N, B * E
         d = self.d_hidden
         nf = self.n_radial_basis if self.n_radial_basis > 0 else 1
+        K0 = nf + 2 * dh
         cell = None if self.apply_pbc is None else self.apply_pbc.cell
         cinv = None if self.apply_pbc is None else self.apply_pbc.cell_inv
         agg = 1 if self.message_passing_agg == "mean" else 0
         tc = self.tensor_cores
-        pos = x.reshape(Nt, 3)
+        nodes = x.reshape(Nt, F)
         saved = {"steps": []}
         for st in steps:
             rij4 = torch.empty((Et, 4), **f32)
             feats = torch.empty((Et, nf), **f32)
-            ops.egnn_geom_fwd(pos, 3, Nt, rowptr, src, cell, cinv, self.n_radial_basis, self.r_max, rij4, feats)
-            acts, a, pro = [], feats, 0
+            ops.egnn_geom_fwd(nodes, F, Nt, rowptr, src, cell, cinv, self.n_radial_basis, self.r_max, rij4, feats)
+            U = feats
+            if dh > 0:                                       # [bessel | h_sender | h_receiver], egnn.py:47-60,93-96
+                U = torch.empty((Et, K0), **f32)
+                ops.egnn_edge_input_fwd(feats, nf, nodes, F, 6, dh, rowptr, src, Nt, U)
+            acts, a, pro = [], U, 0
             Za = Mg = None
             nE = len(st["phi_e"])
             for li, (ko, bo, fan) in enumerate(st["phi_e"] + st["phi_x"]):
@@ -188,14 +249,25 @@ class EGNN:
             t = torch.empty((Et,), **f32)
             _mm(Et, 1, d, 1.0, a, 0, d, theta, st["k_last"], 1, t, 0, Et, tc=True, pro=1, pro_scale=1.0,
                 tag="egnn_mlp_fwd", tf32x3=tc)
-            pos_next = torch.empty((Nt, 3), **f32)
-            ops.egnn_coord_fwd(rij4, t, self.tanh_out, agg, rowptr, Nt, pos, 3, cell, cinv, pos_next, 3)
-            saved["steps"].append(dict(rij4=rij4, feats=feats, acts=acts, t=t, Za=Za, Mg=Mg))
-            pos = pos_next
+            nodes_next = torch.empty((Nt, F), **f32)
+            sv = dict(rij4=rij4, U=U, acts=acts, t=t, Za=Za, Mg=Mg, nodes=nodes)
+            if not vel:
+                ops.egnn_coord_fwd(rij4, t, self.tanh_out, agg, rowptr, Nt, nodes, F, cell, cinv, nodes_next, F)
+            else:
+                zv = self._mlp_fwd(theta, st["phi_v"], nodes, 6, F, Nt)
+                zh = self._mlp_fwd(theta, st["phi_h"], nodes, 6, F, Nt)
+                zx = self._mlp_fwd(theta, st["phi_xx"], nodes, 6, F, Nt) if st["phi_xx"] is not None else None
+                base = torch.empty((Nt, 3), **f32)
+                ops.egnn_xv_base(nodes, F, None if zx is None else zx[-1], zv[-1], Nt, base)
+                ops.egnn_coord_fwd(rij4, t, self.tanh_out, agg, rowptr, Nt, base, 3, cell, cinv, nodes_next, F)
+                ops.egnn_node_assemble(nodes, F, dh, zh[-1], Nt, nodes_next)
+                sv.update(zv=zv, zh=zh, zx=zx)
+            saved["steps"].append(sv)
+            nodes = nodes_next
         if self.task == "node":
-            return pos.view(B, N, 3), saved
-        pooled = torch.empty((B, 3), **f32)
-        ops.pool_fwd(pos, B, N, 3, 1 if self.readout_agg == "mean" else 0, pooled)
+            return nodes.view(B, N, F), saved
+        pooled = torch.empty((B, F), **f32)
+        ops.pool_fwd(nodes, B, N, F, 1 if self.readout_agg == "mean" else 0, pooled)
         zs, a, pro = [], pooled, 0
         for (ko, bo, fan, h) in readout:
             zl = torch.empty((B, h), **f32)
@@ -209,15 +281,18 @@ class EGNN:
         rowptr, perm, src, rowptr_s, perm_s = csr
         dev = theta.device
         f32 = dict(dtype=torch.float32, device=dev)
-        layout, steps, readout, _ = self._layout()
+        F = saved["steps"][0]["nodes"].shape[-1]
+        vel, dh = self._variant(F)
+        layout, steps, readout, _ = self._layout(F)
         Nt, Et = B * N, B * E
         d = self.d_hidden
         nf = self.n_radial_basis if self.n_radial_basis > 0 else 1
+        K0 = nf + 2 * dh
         agg = 1 if self.message_passing_agg == "mean" else 0
         tc = self.tensor_cores
         gtheta.zero_()
         if self.task == "node":
-            dpos = gout.reshape(Nt, 3).clone()
+            dN = gout.reshape(Nt, F).clone()
         else:
             zs = saved["ro_z"]
             dz = gout.reshape(B, -1).contiguous()
@@ -233,14 +308,18 @@ class EGNN:
                 else:
                     _mm(B, fan, h, 1.0, dz, 0, h, theta, ko, h, dprev, 0, fan, tb=True)
                 dz = dprev
-            dpos = torch.empty((Nt, 3), **f32)
-            ops.pool_bwd(dz, B, N, 3, 1 if self.readout_agg == "mean" else 0, dpos)
+            dN = torch.empty((Nt, F), **f32)
+            ops.pool_bwd(dz, B, N, F, 1 if self.readout_agg == "mean" else 0, dN)
         dt = torch.empty((Et,), **f32)
         dre = torch.empty((Et, 4), **f32)
         for si in range(len(steps) - 1, -1, -1):
             st, sv = steps[si], saved["steps"][si]
-            rij4, feats, acts, t = sv["rij4"], sv["feats"], sv["acts"], sv["t"]
-            ops.egnn_coord_bwd(rij4, t, self.tanh_out, agg, rowptr, perm, Nt, dpos, self.n_radial_basis, self.r_max,
+            rij4, U, acts, t, nodes = sv["rij4"], sv["U"], sv["acts"], sv["t"], sv["nodes"]
+            g3 = dN
+            if F != 3:                                       # dL/dx' as a dense (Nt, 3) array
+                g3 = torch.empty((Nt, 3), **f32)
+                ops.copy_cols(dN, F, 0, 3, Nt, g3, 3, 0)
+            ops.egnn_coord_bwd(rij4, t, self.tanh_out, agg, rowptr, perm, Nt, g3, self.n_radial_basis, self.r_max,
                                None, dt, None, None)
             layers = st["phi_e"] + st["phi_x"]
             last = acts[-1]
@@ -250,11 +329,11 @@ class EGNN:
             dZ = torch.empty((Et, d), **f32)
             _mm(Et, d, 1, 1.0, dt, 0, Et, theta, st["k_last"], 1, dZ, 0, d, ta=True, tb=True, epi=2, aux=last, ld_aux=d,
                 epi_scale=1.0, tag="egnn_mlp_bwd", tf32x3=tc)
-            dfeats = None
+            dU = None
             nE = len(st["phi_e"])
             for l in range(len(layers) - 1, -1, -1):
                 ko, bo, fan = layers[l]
-                a_prev, pro = (acts[l - 1], 1) if l > 0 else (feats, 0)
+                a_prev, pro = (acts[l - 1], 1) if l > 0 else (U, 0)
                 gated = (l == nE and st["phi_a"] is not None)      # this layer's input is the soft-gated message
                 if gated:
                     a_prev, pro = sv["Mg"], 0
@@ -282,14 +361,38 @@ class EGNN:
                         epi_scale=1.0, tag="egnn_mlp_bwd", tf32x3=tc)
                     dZ = dZp
                 elif si > 0:
-                    dfeats = torch.empty((Et, nf), **f32)
-                    _mm(Et, nf, d, 1.0, dZ, 0, d, theta, ko, d, dfeats, 0, nf, tb=True, tag="egnn_mlp_bwd", tf32x3=tc)
+                    dU = torch.empty((Et, fan), **f32)
+                    _mm(Et, fan, d, 1.0, dZ, 0, d, theta, ko, d, dU, 0, fan, tb=True, tag="egnn_mlp_bwd", tf32x3=tc)
+            mix = None
             if si > 0:
-                dpos_in = torch.empty((Nt, 3), **f32)
-                ops.egnn_coord_bwd(rij4, t, self.tanh_out, agg, rowptr, perm, Nt, dpos, self.n_radial_basis, self.r_max,
-                                   dfeats, None, dre, dpos_in)
-                ops.egnn_sender_acc(dre, rowptr_s, perm_s, Nt, dpos_in)
-                dpos = dpos_in
+                dfeats = dU
+                if dh > 0:
+                    dfeats = torch.empty((Et, nf), **f32)
+                    ops.copy_cols(dU, K0, 0, nf, Et, dfeats, nf, 0)
+                mix = torch.empty((Nt, 3), **f32)
+                ops.egnn_coord_bwd(rij4, t, self.tanh_out, agg, rowptr, perm, Nt, g3, self.n_radial_basis, self.r_max,
+                                   dfeats, None, dre, mix)
+                ops.egnn_sender_acc(dre, rowptr_s, perm_s, Nt, mix)
+            if not vel:
+                dN = mix
+                continue
+            # ---- node function backward (egnn.py:208-229)
+            zv, zh, zx = sv["zv"], sv["zh"], sv["zx"]
+            dN_in = torch.empty((Nt, F), **f32) if si > 0 else None
+            dsv = torch.empty((Nt, 1), **f32)
+            dsx = torch.empty((Nt, 1), **f32) if zx is not None else None
+            ops.egnn_xv_bwd(nodes, F, None if zx is None else zx[-1], zv[-1], dN, mix, Nt, dN_in, dsx, dsv)
+            din = (dN_in, 6, F) if si > 0 else None
+            if si > 0:
+                dhs_e = torch.empty((Et, dh), **f32)
+                ops.egnn_edge_input_bwd(dU, nf, dh, rowptr, perm, rowptr_s, perm_s, Nt, None, dhs_e, dN_in, F, 6)
+            dph = torch.empty((Nt, dh), **f32)
+            ops.copy_cols(dN, F, 6, dh, Nt, dph, dh, 0)
+            self._mlp_bwd(theta, gtheta, st["phi_h"], zh, nodes, 6, F, Nt, dph, din)
+            self._mlp_bwd(theta, gtheta, st["phi_v"], zv, nodes, 6, F, Nt, dsv, din)
+            if zx is not None:
+                self._mlp_bwd(theta, gtheta, st["phi_xx"], zx, nodes, 6, F, Nt, dsx, din)
+            dN = dN_in
         return None
 
 

@@ -285,6 +285,38 @@ def egnn_sender_acc(dre, rowptr_s, perm_s, n_nodes, dpos):
           "egnn_sender_acc")
 
 
+def _off(t, off):
+    return C.c_void_p(t.data_ptr() + 4 * off)
+
+
+def egnn_edge_input_fwd(feats, nf, nodes, F, h_off, dh, rowptr, src, n_nodes, U):
+    check(lib().eqnn_egnn_edge_input_fwd(_ptr(feats), nf, _off(nodes, h_off), F, dh, _ptr(rowptr), _ptr(src), n_nodes,
+                                         _ptr(U), _stream()), "egnn_edge_input_fwd")
+
+
+def egnn_edge_input_bwd(dU, nf, dh, rowptr, perm, rowptr_s, perm_s, n_nodes, dfeats, dhs_e, dnodes, F, h_off):
+    check(lib().eqnn_egnn_edge_input_bwd(_ptr(dU), nf, dh, _ptr(rowptr), _ptr(perm), _ptr(rowptr_s), _ptr(perm_s), n_nodes,
+                                         _ptr(dfeats), _ptr(dhs_e), _off(dnodes, h_off), F, _stream()),
+          "egnn_edge_input_bwd")
+
+
+def egnn_xv_base(nodes, F, sx, sv, n, base):
+    check(lib().eqnn_egnn_xv_base(_ptr(nodes), F, _ptr(sx), _ptr(sv), n, _ptr(base), _stream()), "egnn_xv_base")
+
+
+def egnn_node_assemble(nodes, F, dh, ph, n, nodes_next):
+    check(lib().eqnn_egnn_node_assemble(_ptr(nodes), F, dh, _ptr(ph), n, _ptr(nodes_next), _stream()), "egnn_node_assemble")
+
+
+def egnn_xv_bwd(nodes, F, sx, sv, dnext, mix, n, din, dsx, dsv):
+    check(lib().eqnn_egnn_xv_bwd(_ptr(nodes), F, _ptr(sx), _ptr(sv), _ptr(dnext), _ptr(mix), n, _ptr(din), _ptr(dsx),
+                                 _ptr(dsv), _stream()), "egnn_xv_bwd")
+
+
+def copy_cols(src, ld_src, col_src, width, n, dst, ld_dst, col_dst):
+    check(lib().eqnn_copy_cols(_ptr(src), ld_src, col_src, width, n, _ptr(dst), ld_dst, col_dst, _stream()), "copy_cols")
+
+
 def softgate_fwd(z, za, m):
     check(lib().eqnn_softgate_fwd(_ptr(z), _ptr(za), z.numel(), _ptr(m), _stream()), "softgate_fwd")
 

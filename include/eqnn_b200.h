@@ -212,6 +212,27 @@ int eqnn_egnn_coord_bwd(const float* rij4, const float* t, int use_tanh, int agg
                         const float* dfeats, float* dt, float* dre, float* dpos_in, eqnn_stream_t stream);
 int eqnn_egnn_sender_acc(const float* dre, const int32_t* rowptr_s, const int32_t* perm_s, int n_nodes, float* dpos,
                          eqnn_stream_t stream);
+/* node layout (x, v, h) with scalar attributes (egnn.py:47-60, 198-229):
+ * edge-MLP input U[p] = [feats[p] (nf) | h[sender] (dh) | h[receiver] (dh)] in receiver-sorted order, and its backward
+ * (dfeats may be NULL; dh_out[n, :dh] += receiver row sums + sender-sorted gather; dhs_e: [n_edges, dh] scratch). */
+int eqnn_egnn_edge_input_fwd(const float* feats, int nf, const float* h, int ld_h, int dh, const int32_t* rowptr,
+                             const int32_t* src, int n_nodes, float* U, eqnn_stream_t stream);
+int eqnn_egnn_edge_input_bwd(const float* dU, int nf, int dh, const int32_t* rowptr, const int32_t* perm,
+                             const int32_t* rowptr_s, const int32_t* perm_s, int n_nodes, float* dfeats, float* dhs_e,
+                             float* dh_out, int ld_dh, eqnn_stream_t stream);
+/* base[n] = sx[n] x[n] + sv[n] v[n] (sx NULL = 1): the coordinate layer then forms x' = wrap(base + agg)  (:213-227) */
+int eqnn_egnn_xv_base(const float* nodes, int F, const float* sx, const float* sv, int64_t n, float* base,
+                      eqnn_stream_t stream);
+/* nodes_next[n, 3:] = (v, h + ph)   (x' is written by eqnn_egnn_coord_fwd; the OLD velocity is returned, :229) */
+int eqnn_egnn_node_assemble(const float* nodes, int F, int dh, const float* ph, int64_t n, float* nodes_next,
+                            eqnn_stream_t stream);
+/* backward of the node update: dsx = g.x, dsv = g.v, din = (sx g + (mix - g), sv g + dnext_v, dnext_h); mix = g +
+ * geometry gradient (NULL: none); din may be NULL (first step) */
+int eqnn_egnn_xv_bwd(const float* nodes, int F, const float* sx, const float* sv, const float* dnext, const float* mix,
+                     int64_t n, float* din, float* dsx, float* dsv, eqnn_stream_t stream);
+/* dst[n, col_dst + j] = src[n, col_src + j], j < width */
+int eqnn_copy_cols(const float* src, int ld_src, int col_src, int width, int64_t n, float* dst, int ld_dst, int col_dst,
+                   eqnn_stream_t stream);
 /* soft edges (egnn.py:101-105): m = gelu(z) * sigmoid(za); backward: dza = dm * gelu(z) * sigmoid'(za),
  * g1 = dm * sigmoid(za)  (g1 may alias dm) */
 int eqnn_softgate_fwd(const float* z, const float* za, int64_t n, float* m, eqnn_stream_t stream);

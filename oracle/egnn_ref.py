@@ -6,9 +6,9 @@ Restatement of models/egnn.py (reference):
   EGNN.__call__                   :257-347  message passing, graph read-out (mean over nodes -> MLP)
 and of models/mlp.py (Dense + bias, xavier-uniform, gelu-tanh).  jraph.GraphNetwork semantics per
 SURVEY.md A.9 (the tuple (x_ij_trans, m_ij) is aggregated over receivers leaf by leaf).
-Flax auto-names: inside one step the edge function creates MLP_{3s} (phi_e), MLP_{3s+1} (phi_x),
-Dense_{s} (last layer of phi_x), MLP_{3s+2} (phi_a, parameters only when soft_edges), then the node
-function its MLPs.  The notebook's parameter count (441 778, cell 15) is reproduced by this bookkeeping.
+Flax auto-names: inside one step the edge function creates phi_e, phi_x, Dense_{s} (last layer of phi_x)
+and phi_a (its MLP index is reserved, parameters only when soft_edges), then the node function its MLPs
+(phi_v, phi_h, phi_xx as the node layout requires); MLP indices run on across steps.  The notebook's parameter count (441 778, cell 15) is reproduced by this bookkeeping.
 """
 from __future__ import annotations
 
@@ -48,27 +48,50 @@ def _mlp_init(rng, n_in, widths):
     return E.flax_mlp_init(rng, n_in, widths)
 
 
+def _variant(cfg: EGNNConfig, F: int):
+    """(has_vel, d_scalar) of a node-feature width, egnn.py:38-60 / :145-229."""
+    if cfg.positions_only:
+        if F < 3:
+            raise ValueError("positions_only needs >= 3 node features")
+        return False, F - 3
+    if F < 6:
+        raise ValueError("positions + velocities need >= 6 node features")
+    return True, F - 6
+
+
 def init_params(cfg: EGNNConfig, n_feat: int, seed: int = 0) -> Dict:
-    """Positions-only clouds without scalar attributes (n_feat == 3): the benchmarked configuration
-    (train_cosmology.py:67-81 with feats='pos')."""
-    if not (cfg.positions_only and n_feat == 3):
-        raise NotImplementedError("oracle covers positions_only=True with 3-d nodes")
+    """All four node-feature layouts of the reference: (x), (x, h), (x, v), (x, v, h); no graph globals.
+    Flax auto-names follow construction order: phi_e, phi_x, [Dense], phi_a, then the node function's phi_v / phi_h /
+    phi_xx (egnn.py:63-79,100,161,177-189,210-222)."""
     rng = np.random.default_rng(seed)
     p: Dict = {}
     d, L = cfg.d_hidden, cfg.n_layers
     n_msg = cfg.n_radial_basis if cfg.n_radial_basis > 0 else 1
-    mi = 0
+    mi, F = 0, n_feat
     for s in range(cfg.message_passing_steps):
-        p[f"MLP_{mi}"] = _mlp_init(rng, n_msg, [d] * (L - 1) + [d]); mi += 1           # phi_e
+        vel, dh = _variant(cfg, F)
+        p[f"MLP_{mi}"] = _mlp_init(rng, n_msg + 2 * dh, [d] * (L - 1) + [d]); mi += 1   # phi_e
         p[f"MLP_{mi}"] = _mlp_init(rng, d, [d] * (L - 1)); mi += 1                      # phi_x
         lim = math.sqrt(3.0 * 1e-2 / d)                                                 # variance_scaling(1e-2, fan_in, uniform)
         p[f"Dense_{s}"] = {"kernel": rng.uniform(-lim, lim, size=(d, 1))}
         if cfg.soft_edges:
             p[f"MLP_{mi}"] = _mlp_init(rng, d, [d])                                     # phi_a
         mi += 1
+        if not vel:
+            if dh > 0:
+                p[f"MLP_{mi}"] = _mlp_init(rng, dh + d, [d] * (L - 1) + [dh]); mi += 1  # phi_h([h_i, m_i])
+        else:
+            n_in = d if dh == 0 else dh                                                 # concats = m_i | h_i
+            p[f"MLP_{mi}"] = _mlp_init(rng, n_in, [d] * (L - 1) + [1]); mi += 1         # phi_v
+            if dh > 0:
+                p[f"MLP_{mi}"] = _mlp_init(rng, n_in, [d] * (L - 1) + [dh]); mi += 1    # phi_h
+            if cfg.decouple_pos_vel_updates:
+                p[f"MLP_{mi}"] = _mlp_init(rng, n_in, [d] * (L - 1) + [1]); mi += 1     # phi_xx
+            if dh == 0:
+                F = 6 + d                                                               # returns [x', v, m_i] (:196)
     if cfg.task == "graph":
-        w = [cfg.mlp_readout_widths[0] * n_feat] + [x * d for x in cfg.mlp_readout_widths[1:]] + [cfg.n_outputs]
-        p[f"MLP_{mi}"] = _mlp_init(rng, n_feat, w)
+        w = [cfg.mlp_readout_widths[0] * F] + [x * d for x in cfg.mlp_readout_widths[1:]] + [cfg.n_outputs]
+        p[f"MLP_{mi}"] = _mlp_init(rng, F, w)
     return p
 
 
@@ -77,43 +100,63 @@ def _mlp(params, x, activate_final):
 
 
 def apply_single(params, cfg: EGNNConfig, graph: GraphsTuple):
-    """EGNN.__call__ on one un-batched graph; nodes (N,3)."""
-    x = graph.nodes
-    dtype = x.dtype
+    """EGNN.__call__ on one un-batched graph; nodes (N, F)."""
+    nodes = graph.nodes
+    dtype = nodes.dtype
     senders = torch.as_tensor(np.asarray(graph.senders)).long()
     receivers = torch.as_tensor(np.asarray(graph.receivers)).long()
-    N = x.shape[0]
+    N = nodes.shape[0]
     agg = E.SEGMENT[cfg.message_passing_agg]
     pbc = cfg.apply_pbc
+    if pbc is not None:
+        cell = torch.as_tensor(pbc.cell, dtype=dtype)
+        cell_inv = torch.as_tensor(pbc.cell_inv, dtype=dtype)
+    wrap = (lambda a: a - torch.round(a @ cell_inv) @ cell) if pbc is not None else (lambda a: a)
     mi = 0
     for s in range(cfg.message_passing_steps):
-        x_i, x_j = x[senders], x[receivers]
-        # egnn.py:82-85; the reference forms r_ij in fp32: keep its rounding points for the ill-conditioned Bessel phase
-        r_ij = x_i - x_j + 1e-7
-        if pbc is not None:
-            cell = torch.as_tensor(pbc.cell, dtype=dtype)
-            cell_inv = torch.as_tensor(pbc.cell_inv, dtype=dtype)
-            r_ij = r_ij - torch.round(r_ij @ cell_inv) @ cell
+        vel, dh = _variant(cfg, nodes.shape[1])
+        x = nodes[:, :3]
+        v = nodes[:, 3:6] if vel else None
+        h = nodes[:, (6 if vel else 3):] if dh > 0 else None
+        # ---- edge update, egnn.py:38-116 (jraph: "senders" = nodes[senders], "receivers" = nodes[receivers])
+        r_ij = wrap(x[senders] - x[receivers] + 1e-7)
         d = torch.sqrt((r_ij ** 2).sum(1))
         feats = E.bessel(d, cfg.n_radial_basis, cfg.r_max, reference_rounding=False) if cfg.n_radial_basis > 0 \
             else d[:, None]
+        if dh > 0:
+            feats = torch.cat([feats, h[senders], h[receivers]], -1)
         m = _mlp(params[f"MLP_{mi}"], feats, True); mi += 1
         phi_x = params[f"MLP_{mi}"]; mi += 1
         if cfg.soft_edges:
-            a = torch.sigmoid(_mlp(params[f"MLP_{mi}"], m, False))
-            m = m * a
+            m = m * torch.sigmoid(_mlp(params[f"MLP_{mi}"], m, False))
         mi += 1
         t = _mlp(phi_x, m, True) @ params[f"Dense_{s}"]["kernel"]
         if cfg.tanh_out:
             t = torch.tanh(t)
         xt = torch.clamp(r_ij * t, -100.0, 100.0)
-        agg_x = agg(xt, receivers, N)
-        x = x + agg_x                                                    # egnn.py:146-150
-        if pbc is not None:
-            x = x - torch.round(x @ cell_inv) @ cell
+        agg_x, m_i = agg(xt, receivers, N), agg(m, receivers, N)
+        # ---- node update, egnn.py:143-229
+        if not vel:
+            x_p = wrap(x + agg_x)
+            if dh == 0:
+                nodes = x_p
+            else:
+                h_p = h + _mlp(params[f"MLP_{mi}"], torch.cat([h, m_i], -1), False); mi += 1
+                nodes = torch.cat([x_p, h_p], -1)
+        else:
+            c = m_i if dh == 0 else h
+            v_p = _mlp(params[f"MLP_{mi}"], c, False) * v + agg_x; mi += 1
+            if dh > 0:
+                h_p = h + _mlp(params[f"MLP_{mi}"], c, False); mi += 1
+            if cfg.decouple_pos_vel_updates:
+                x_p = _mlp(params[f"MLP_{mi}"], c, False) * x + v_p; mi += 1
+            else:
+                x_p = x + v_p
+            x_p = wrap(x_p)
+            nodes = torch.cat([x_p, v, c if dh == 0 else h_p], -1)      # the OLD velocity is returned (:196,229)
     if cfg.task == "node":
-        return graph._replace(nodes=x)
-    pooled = {"mean": x.mean(0), "sum": x.sum(0), "max": x.max(0).values}[cfg.readout_agg]
+        return graph._replace(nodes=nodes)
+    pooled = {"mean": nodes.mean(0), "sum": nodes.sum(0), "max": nodes.max(0).values}[cfg.readout_agg]
     return _mlp(params[f"MLP_{mi}"], pooled, False)
 
 

@@ -34,17 +34,19 @@ def _leaves(tree, pre=()):
             yield pre + (k,), v
 
 
-def _run(kw, B=2, N=256, k=8, pbc=False, seed=0):
+def _run(kw, B=2, N=256, k=8, pbc=False, seed=0, F=3):
     from eqnn_jax_b200 import graph_utils as GU
     from eqnn_jax_b200.egnn import EGNN
     rng = np.random.default_rng(seed)
     x = rng.uniform(-1.0, 1.7, size=(B, N, 3)).astype(np.float32)      # non-zero mean: the read-out pools positions
+    if F > 3:                                                          # (x, v, h): small velocities, O(1) scalars
+        x = np.concatenate([x, 0.05 * rng.normal(size=(B, N, 3)), rng.normal(size=(B, N, F - 6))], -1).astype(np.float32)
     cell = np.eye(3, dtype=np.float32) * 3.4
     opbc = G.get_apply_pbc(cell=cell) if pbc else None
     gpbc = GU.get_apply_pbc(cell=cell) if pbc else None
     g = G.build_graph(x, None, k, apply_pbc=opbc)
     cfg = EG.EGNNConfig(**kw, apply_pbc=opbc)
-    tree = EG.init_params(cfg, 3, seed=seed + 1)
+    tree = EG.init_params(cfg, F, seed=seed + 1)
     # make the coordinate updates O(1e-3..1e-2) instead of O(1e-4) so that every path carries signal, without
     # turning the layer stack into a chaotic map (large moves amplify fp32 rounding through the Bessel phase)
     for s in range(cfg.message_passing_steps):
@@ -109,6 +111,75 @@ def test_egnn_forward_and_gradients(kw, pbc):
             f"grad {'/'.join(path)}: err {err:.3e}, scale {scales[path[0]]:.3e}, fp32 floor {floor:.3e}"
 
 
+XVH = dict(positions_only=False, n_layers=3, r_max=0.6, message_passing_steps=2, n_outputs=2)
+
+
+@pytest.mark.parametrize("kw,pbc,F", [
+    (dict(XVH, soft_edges=True, tanh_out=True, decouple_pos_vel_updates=True, d_hidden=32, n_radial_basis=16,
+          message_passing_agg="mean", task="node", message_passing_steps=3), False, 7),   # tests/test_equivariance.py:224-250
+    (dict(XVH, soft_edges=False, decouple_pos_vel_updates=False, d_hidden=128, n_radial_basis=32,
+          message_passing_agg="mean", task="graph"), True, 9),                            # tensor-core edge MLPs
+    (dict(XVH, soft_edges=True, tanh_out=True, decouple_pos_vel_updates=True, d_hidden=64, n_radial_basis=0,
+          message_passing_agg="sum", task="graph"), False, 8),
+])
+def test_egnn_xvh_forward_and_gradients(kw, pbc, F):
+    """(x, v, h) node layout, egnn.py:47-60 and :198-229."""
+    got, want, params, p, x, p32 = _run(kw, pbc=pbc, F=F, seed=3)
+    got = got.cpu().numpy()
+    if kw["task"] == "node":
+        _close(got, want, "nodes")
+        _close(got[..., :3] - x[..., :3], want[..., :3] - x[..., :3], "coordinate update", rtol=1e-3)
+        assert np.array_equal(got[..., 3:6], x[..., 3:6])                      # the old velocity is returned (:229)
+    else:
+        _close(got, want, "output")
+    gt = params.grad_tree
+    scales, floors = {}, {}
+    for (path, w), (_, w32) in zip(_leaves(p), _leaves(p32)):
+        scales[path[0]] = max(scales.get(path[0], 0.0), float(w.grad.abs().max()))
+        floors[path[0]] = max(floors.get(path[0], 0.0), float((w32.grad.double() - w.grad).abs().max()))
+    gmax = max(scales.values())
+    for path, w in _leaves(p):
+        g = gt
+        for q in path:
+            g = g[q]
+        err = np.abs(g.cpu().numpy().astype(np.float64) - w.grad.numpy()).max()
+        # Dense_s (one 1-column kernel per step) is a module of its own, so its floor is a single sample of the
+        # reference-precision rounding noise instead of a maximum over many tensors: 10 x that sample here
+        # ... and modules whose gradients are orders of magnitude below the dominant flow of the same backward pass
+        # (here: the position path of a read-out that pools O(1) scalars) inherit that flow's fp32 rounding: 1e-7 of it
+        assert err <= RTOL * scales[path[0]] + 10.0 * floors[path[0]] + 1e-7 * gmax, \
+            f"grad {'/'.join(path)}: err {err:.3e}, scale {scales[path[0]]:.3e}, fp32 floor {10 * floors[path[0]]:.3e}"
+
+
+def test_egnn_xvh_equivariance_property():
+    """The reference's own EGNN test (tests/test_equivariance.py:224-250): 7 features, soft edges, tanh,
+    decoupled position/velocity updates, node task; positions and velocities rotate, the scalar does not."""
+    from eqnn_jax_b200 import graph_utils as GU
+    from eqnn_jax_b200.egnn import EGNN
+    rng = np.random.default_rng(4)
+    x = rng.normal(size=(2, 64, 7)).astype(np.float32)
+    R = G.rotation_matrix(45.0, np.array([0, 1 / np.sqrt(2), 1 / np.sqrt(2)]))
+    xr = x.copy()
+    xr[..., :3] = x[..., :3] @ R.T
+    xr[..., 3:6] = x[..., 3:6] @ R.T
+    model = EGNN(message_passing_steps=3, d_hidden=32, n_layers=3, activation="gelu", tanh_out=True, soft_edges=True,
+                 positions_only=False, task="node", decouple_pos_vel_updates=True)
+
+    def graph(a):
+        a = torch.tensor(a).cuda()
+        return GU.build_graph(a, None, 5)._replace(edges=None)
+    g0, g1 = graph(x), graph(xr)
+    params = model.init(0, g0)
+    o0 = model.forward_backward(params, g0).cpu().numpy()
+    o1 = model.forward_backward(params, g1).cpu().numpy()
+    want = o0.copy()
+    want[..., :3] = o0[..., :3] @ R.T
+    want[..., 3:6] = o0[..., 3:6] @ R.T
+    assert not np.allclose(o0[..., :3], o1[..., :3], rtol=0.05)
+    assert np.allclose(o1, want, rtol=0.05, atol=1e-4)
+    _close(o1, want, "equivariance", rtol=1e-4)
+
+
 def test_egnn_equivariance_property():
     """tests/test_equivariance.py:224-250 style check on the B200 path: f(Rx) = R f(x)."""
     from eqnn_jax_b200 import graph_utils as GU
@@ -135,8 +206,10 @@ def test_egnn_equivariance_property():
 
 def test_egnn_unsupported_variants_fail_loudly():
     from eqnn_jax_b200.egnn import EGNN
-    g = type("G", (), {"nodes": torch.zeros(1, 4, 7).cuda()})()
+    g = type("G", (), {"nodes": torch.zeros(1, 4, 6).cuda()})()
     with pytest.raises(NotImplementedError):
-        EGNN(positions_only=False).init(0, g)
+        EGNN(positions_only=False).init(0, g)                       # (x, v) layout: consumes aggregated messages
+    with pytest.raises(NotImplementedError):
+        EGNN(positions_only=True).init(0, type("G", (), {"nodes": torch.zeros(1, 4, 5).cuda()})())   # (x, h) layout
     with pytest.raises(NotImplementedError):
         EGNN(positions_only=True, message_passing_agg="max").init(0, type("G", (), {"nodes": torch.zeros(1, 4, 3).cuda()})())

@@ -163,6 +163,37 @@ def test_reference_equivariance_tests_on_oracle(task):
         np.testing.assert_allclose(o1.numpy(), o2.numpy(), rtol=1e-4)
 
 
+@pytest.mark.parametrize("F,kw", [(3, dict(positions_only=True)), (5, dict(positions_only=True)),
+                                  (6, dict(positions_only=False)),
+                                  (7, dict(positions_only=False, decouple_pos_vel_updates=True))])
+def test_reference_egnn_equivariance_test_on_oracle(F, kw):
+    """tests/test_equivariance.py:224-250 (EGNN, 7 features, soft edges, tanh, decoupled updates) on the oracle,
+    and the other three node layouts of models/egnn.py:38-60: vectors rotate, scalars are invariant."""
+    from oracle import egnn_ref as EG
+    rng = np.random.default_rng(1)
+    x = rng.normal(size=(2, 5, F)).astype(np.float32)
+    axis = np.array([0, 1 / np.sqrt(2), 1 / np.sqrt(2)])
+    R = G.rotation_matrix(45.0, axis)
+    n_vec = 1 if kw["positions_only"] else 2
+
+    def rot(a):
+        a = np.array(a, dtype=np.float64)
+        for v in range(n_vec):
+            a[..., 3 * v:3 * v + 3] = a[..., 3 * v:3 * v + 3] @ R.T
+        return a
+    cfg = EG.EGNNConfig(message_passing_steps=3, d_hidden=32, n_layers=3, tanh_out=True, soft_edges=True, task="node", **kw)
+    p = NQ.to_torch(EG.init_params(cfg, F, seed=0))
+    g0 = G.build_graph(x, None, 5)
+    g1 = G.build_graph(rot(x).astype(np.float32), None, 5)
+    assert np.array_equal(g0.senders, g1.senders)
+    o0 = EG.apply_batched(p, cfg, g0._replace(nodes=torch.tensor(x, dtype=torch.float64))).nodes.numpy()
+    o1 = EG.apply_batched(p, cfg, g1._replace(nodes=torch.tensor(rot(x)))).nodes.numpy()
+    assert not np.allclose(o0[..., :3], o1[..., :3], rtol=0.05)
+    np.testing.assert_allclose(o1, rot(o0), rtol=0.05, atol=1e-6)
+    # exact up to the reference's `+ 1e-7` on every component of r_ij (egnn.py:82-83), which is not a vector
+    np.testing.assert_allclose(o1, rot(o0), atol=2e-5 * max(1.0, np.abs(o0).max()))
+
+
 def test_pbc_sanity_reference_tests():
     """tests/test_pbcs.py:8-33 and :35-62."""
     rng = np.random.default_rng(0)
