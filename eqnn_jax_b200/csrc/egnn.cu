@@ -352,17 +352,56 @@ __global__ void egnn_xv_base_kernel(const float* __restrict__ nodes, int F, cons
   base[i] = a * nodes[node * F + c] + sv[node] * nodes[node * F + 3 + c];
 }
 
-// nodes_next[n] = (x' (already written), v (unchanged, :229), h + ph)
-__global__ void egnn_node_assemble_kernel(const float* __restrict__ nodes, int F, int dh, const float* __restrict__ ph,
+// nodes_next[n, 3:] = (pass-through columns [3, h_off) (the old velocity, :229), h + ph); x' is already written
+__global__ void egnn_node_assemble_kernel(const float* __restrict__ nodes, int F, int h_off, const float* __restrict__ ph,
                                           int64_t n, float* __restrict__ nodes_next) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int w = F - 3;
+  const int w = F - 3, dh = F - h_off;
   if (i >= n * w) return;
   const int64_t node = i / w;
   const int c = 3 + (int)(i - node * w);
   float v = nodes[node * F + c];
-  if (c >= 6) v += ph[node * dh + (c - 6)];
+  if (c >= h_off) v += ph[node * dh + (c - h_off)];
   nodes_next[node * F + c] = v;
+}
+
+// aggregated messages m_i[r, :] = agg_{e->r} act(rows[e, :]) (jraph segment_sum / segment_mean of m_ij, egnn.py:141,
+// read by the (x, h) and (x, v) node functions): warp per receiver row, lanes over the d columns, edges in CSR order
+__global__ void __launch_bounds__(256) egnn_segment_rows_fwd_kernel(const float* __restrict__ rows, int d, int act,
+                                                                    const int32_t* __restrict__ rowptr, int n_nodes,
+                                                                    int agg, float* __restrict__ out, int ld_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= n_nodes) return;
+  const int p0 = rowptr[row], p1 = rowptr[row + 1];
+  const float inv = (agg == 1) ? 1.f / (float)max(p1 - p0, 1) : 1.f;
+  for (int c = lane; c < d; c += 32) {
+    float a = 0.f;
+    for (int p = p0; p < p1; ++p) {
+      const float v = rows[(size_t)p * d + c];
+      a += act ? gelu_tanh(v) : v;
+    }
+    out[(size_t)row * ld_out + c] = a * inv;
+  }
+}
+
+// its backward: target[e, :] += dmi[r(e), :] / deg * (act ? gelu'(z[e, :]) : 1)
+__global__ void __launch_bounds__(256) egnn_segment_rows_bwd_kernel(const float* __restrict__ dmi, int ld_dmi, int d,
+                                                                    const float* __restrict__ z, int act,
+                                                                    const int32_t* __restrict__ rowptr, int n_nodes,
+                                                                    int agg, float* __restrict__ target) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= n_nodes) return;
+  const int p0 = rowptr[row], p1 = rowptr[row + 1];
+  const float inv = (agg == 1) ? 1.f / (float)max(p1 - p0, 1) : 1.f;
+  for (int c = lane; c < d; c += 32) {
+    const float g = dmi[(size_t)row * ld_dmi + c] * inv;
+    for (int p = p0; p < p1; ++p) {
+      const size_t i = (size_t)p * d + c;
+      target[i] += act ? g * gelu_tanh_grad(z[i]) : g;
+    }
+  }
 }
 
 // backward of the node update given g = dL/dx' (cols 0..2 of dnext), the pass-through gradients of v and h in dnext,
@@ -502,12 +541,34 @@ extern "C" int eqnn_egnn_xv_base(const float* nodes, int F, const float* sx, con
   return EQNN_OK;
 }
 
-extern "C" int eqnn_egnn_node_assemble(const float* nodes, int F, int dh, const float* ph, int64_t n, float* nodes_next,
-                                       eqnn_stream_t stream) {
-  EQNN_CHECK_ARG(nodes && nodes_next && F == 6 + dh && (ph || dh == 0), "egnn_node_assemble: bad argument");
-  if (n <= 0) return EQNN_OK;
-  egnn_node_assemble_kernel<<<(unsigned)ceil_div64(n * (F - 3), 256), 256, 0, as_stream(stream)>>>(nodes, F, dh, ph, n,
+extern "C" int eqnn_egnn_node_assemble(const float* nodes, int F, int h_off, const float* ph, int64_t n,
+                                       float* nodes_next, eqnn_stream_t stream) {
+  EQNN_CHECK_ARG(nodes && nodes_next && h_off >= 3 && h_off <= F && (ph || h_off == F), "egnn_node_assemble: bad argument");
+  if (n <= 0 || F == 3) return EQNN_OK;
+  egnn_node_assemble_kernel<<<(unsigned)ceil_div64(n * (F - 3), 256), 256, 0, as_stream(stream)>>>(nodes, F, h_off, ph, n,
                                                                                                  nodes_next);
+  EQNN_CHECK_LAUNCH();
+  return EQNN_OK;
+}
+
+extern "C" int eqnn_egnn_segment_rows_fwd(const float* rows, int d, int act, const int32_t* rowptr, int n_nodes, int agg,
+                                          float* out, int ld_out, eqnn_stream_t stream) {
+  EQNN_CHECK_ARG(rows && rowptr && out && d >= 1 && ld_out >= d && (agg == 0 || agg == 1), "egnn_segment_rows_fwd: bad argument");
+  if (n_nodes <= 0) return EQNN_OK;
+  egnn_segment_rows_fwd_kernel<<<(unsigned)ceil_div64((int64_t)n_nodes * 32, 256), 256, 0, as_stream(stream)>>>(
+      rows, d, act, rowptr, n_nodes, agg, out, ld_out);
+  EQNN_CHECK_LAUNCH();
+  return EQNN_OK;
+}
+
+extern "C" int eqnn_egnn_segment_rows_bwd(const float* dmi, int ld_dmi, int d, const float* z, int act,
+                                          const int32_t* rowptr, int n_nodes, int agg, float* target,
+                                          eqnn_stream_t stream) {
+  EQNN_CHECK_ARG(dmi && rowptr && target && d >= 1 && ld_dmi >= d && (agg == 0 || agg == 1) && (z || !act),
+                 "egnn_segment_rows_bwd: bad argument");
+  if (n_nodes <= 0) return EQNN_OK;
+  egnn_segment_rows_bwd_kernel<<<(unsigned)ceil_div64((int64_t)n_nodes * 32, 256), 256, 0, as_stream(stream)>>>(
+      dmi, ld_dmi, d, z, act, rowptr, n_nodes, agg, target);
   EQNN_CHECK_LAUNCH();
   return EQNN_OK;
 }

@@ -17,8 +17,10 @@ The (x, v, h) layout -- ``positions_only=False`` with >= 7 node features, the co
 equivariance test (tests/test_equivariance.py:224-250) -- is supported as well: the edge MLP reads
 [bessel | h_sender | h_receiver] (egnn.py:47-60), the node update is v' = phi_v(h) v + agg, x' = wrap(phi_xx(h) x + v')
 (or x + v'), h' = h + phi_h(h), and (x', v, h') is returned (egnn.py:198-229); m_i is unused there too.
-Not built yet: (x, h) and (x, v) layouts (they consume the aggregated messages), globals, max aggregation ->
-NotImplementedError, never a silent fallback.
+The (x, h) layout (``positions_only=True`` with scalar attributes: train_cosmology.py --feats all) reads the
+aggregated messages: h' = h + phi_h([h, m_i]) (egnn.py:152-166), m_i = segment reduce of m_ij.
+Not built yet: the (x, v) layout without scalars (its node width grows to 6 + d_hidden after the first step),
+globals, max aggregation -> NotImplementedError, never a silent fallback.
 """
 from __future__ import annotations
 
@@ -60,9 +62,9 @@ class EGNN:
     def _variant(self, n_feat: int) -> Tuple[bool, int]:
         """(has velocities, number of scalar attributes) for a node-feature width."""
         if self.positions_only:
-            if n_feat != 3:
-                raise NotImplementedError("B200 EGNN: positions_only=True is built for 3-d nodes (no scalar attributes)")
-            return False, 0
+            if n_feat < 3:
+                raise ValueError("positions_only=True needs >= 3 node features")
+            return False, n_feat - 3
         if n_feat < 7:
             raise NotImplementedError("B200 EGNN: positions_only=False needs (x, v, h) nodes with >= 1 scalar attribute")
         return True, n_feat - 6
@@ -116,6 +118,8 @@ class EGNN:
             st["phi_a"] = (add((f"MLP_{mi}", "Dense_0", "kernel"), (d, d)),
                            add((f"MLP_{mi}", "Dense_0", "bias"), (d,))) if self.soft_edges else None
             mi += 1
+            if not vel and dh > 0:                           # node function, egnn.py:159-166: phi_h([h_i, m_i])
+                st["phi_h"] = add_mlp(mi, dh + d, [d] * (L - 1) + [dh]); mi += 1
             if vel:                                          # node function, egnn.py:208-222
                 st["phi_v"] = add_mlp(mi, dh, [d] * (L - 1) + [1]); mi += 1
                 st["phi_h"] = add_mlp(mi, dh, [d] * (L - 1) + [dh]); mi += 1
@@ -214,6 +218,7 @@ class EGNN:
         d = self.d_hidden
         nf = self.n_radial_basis if self.n_radial_basis > 0 else 1
         K0 = nf + 2 * dh
+        ho = 6 if vel else 3                                 # first scalar-attribute column
         cell = None if self.apply_pbc is None else self.apply_pbc.cell
         cinv = None if self.apply_pbc is None else self.apply_pbc.cell_inv
         agg = 1 if self.message_passing_agg == "mean" else 0
@@ -227,7 +232,7 @@ class EGNN:
             U = feats
             if dh > 0:                                       # [bessel | h_sender | h_receiver], egnn.py:47-60,93-96
                 U = torch.empty((Et, K0), **f32)
-                ops.egnn_edge_input_fwd(feats, nf, nodes, F, 6, dh, rowptr, src, Nt, U)
+                ops.egnn_edge_input_fwd(feats, nf, nodes, F, ho, dh, rowptr, src, Nt, U)
             acts, a, pro = [], U, 0
             Za = Mg = None
             nE = len(st["phi_e"])
@@ -253,6 +258,15 @@ class EGNN:
             sv = dict(rij4=rij4, U=U, acts=acts, t=t, Za=Za, Mg=Mg, nodes=nodes)
             if not vel:
                 ops.egnn_coord_fwd(rij4, t, self.tanh_out, agg, rowptr, Nt, nodes, F, cell, cinv, nodes_next, F)
+                if dh > 0:                                   # (x, h): h' = h + phi_h([h, m_i]), egnn.py:152-166
+                    Cc = torch.empty((Nt, dh + d), **f32)
+                    ops.copy_cols(nodes, F, 3, dh, Nt, Cc, dh + d, 0)
+                    gated = st["phi_a"] is not None
+                    ops.egnn_segment_rows_fwd(Mg if gated else acts[nE - 1], d, not gated, rowptr, Nt, agg, Cc, dh + d,
+                                              col_off=dh)
+                    zh = self._mlp_fwd(theta, st["phi_h"], Cc, 0, dh + d, Nt)
+                    ops.egnn_node_assemble(nodes, F, 3, zh[-1], Nt, nodes_next)
+                    sv.update(Cc=Cc, zh=zh)
             else:
                 zv = self._mlp_fwd(theta, st["phi_v"], nodes, 6, F, Nt)
                 zh = self._mlp_fwd(theta, st["phi_h"], nodes, 6, F, Nt)
@@ -260,7 +274,7 @@ class EGNN:
                 base = torch.empty((Nt, 3), **f32)
                 ops.egnn_xv_base(nodes, F, None if zx is None else zx[-1], zv[-1], Nt, base)
                 ops.egnn_coord_fwd(rij4, t, self.tanh_out, agg, rowptr, Nt, base, 3, cell, cinv, nodes_next, F)
-                ops.egnn_node_assemble(nodes, F, dh, zh[-1], Nt, nodes_next)
+                ops.egnn_node_assemble(nodes, F, 6, zh[-1], Nt, nodes_next)
                 sv.update(zv=zv, zh=zh, zx=zx)
             saved["steps"].append(sv)
             nodes = nodes_next
@@ -288,6 +302,7 @@ class EGNN:
         d = self.d_hidden
         nf = self.n_radial_basis if self.n_radial_basis > 0 else 1
         K0 = nf + 2 * dh
+        ho = 6 if vel else 3
         agg = 1 if self.message_passing_agg == "mean" else 0
         tc = self.tensor_cores
         gtheta.zero_()
@@ -321,6 +336,15 @@ class EGNN:
                 ops.copy_cols(dN, F, 0, 3, Nt, g3, 3, 0)
             ops.egnn_coord_bwd(rij4, t, self.tanh_out, agg, rowptr, perm, Nt, g3, self.n_radial_basis, self.r_max,
                                None, dt, None, None)
+            dC = None
+            if not vel and dh > 0:
+                # (x, h) node function first: it yields dL/dm_i, which joins the message gradient below.
+                # dC starts as [dL/dh' | 0]; the MLP input gradient is accumulated on top: [dL/dh (so far) | dL/dm_i]
+                dph = torch.empty((Nt, dh), **f32)
+                ops.copy_cols(dN, F, 3, dh, Nt, dph, dh, 0)
+                dC = torch.zeros((Nt, dh + d), **f32)
+                ops.copy_cols(dN, F, 3, dh, Nt, dC, dh + d, 0)
+                self._mlp_bwd(theta, gtheta, st["phi_h"], sv["zh"], sv["Cc"], 0, dh + d, Nt, dph, (dC, 0, dh + d))
             layers = st["phi_e"] + st["phi_x"]
             last = acts[-1]
             # t = gelu(U_last) @ k_last
@@ -345,6 +369,8 @@ class EGNN:
                     ZL, Za = acts[l - 1], sv["Za"]
                     dM = torch.empty((Et, d), **f32)
                     _mm(Et, d, d, 1.0, dZ, 0, d, theta, ko, d, dM, 0, d, tb=True, tag="egnn_mlp_bwd", tf32x3=tc)
+                    if dC is not None:                              # + dL/dm_i / deg on the gated message
+                        ops.egnn_segment_rows_bwd(dC, dh + d, dh, d, None, 0, rowptr, Nt, agg, dM)
                     dZa = torch.empty((Et, d), **f32)
                     ops.softgate_bwd(ZL, Za, dM, dZa, dM)           # dM <- dM * sigmoid(Za)  (first branch into Z_L)
                     _mm(d, d, Et, 1.0, ZL, 0, d, dZa, 0, d, gtheta, ka, d, ta=True, pro=1, pro_scale=1.0,
@@ -359,6 +385,8 @@ class EGNN:
                     dZp = torch.empty((Et, fan), **f32)
                     _mm(Et, fan, d, 1.0, dZ, 0, d, theta, ko, d, dZp, 0, fan, tb=True, epi=2, aux=acts[l - 1], ld_aux=fan,
                         epi_scale=1.0, tag="egnn_mlp_bwd", tf32x3=tc)
+                    if dC is not None and l == nE:                  # message = gelu(Z_L): + dL/dm_i / deg * gelu'(Z_L)
+                        ops.egnn_segment_rows_bwd(dC, dh + d, dh, d, acts[l - 1], 1, rowptr, Nt, agg, dZp)
                     dZ = dZp
                 elif si > 0:
                     dU = torch.empty((Et, fan), **f32)
@@ -374,7 +402,15 @@ class EGNN:
                                    dfeats, None, dre, mix)
                 ops.egnn_sender_acc(dre, rowptr_s, perm_s, Nt, mix)
             if not vel:
-                dN = mix
+                if dh == 0 or si == 0:
+                    dN = mix
+                    continue
+                dN_in = torch.empty((Nt, F), **f32)
+                ops.copy_cols(mix, 3, 0, 3, Nt, dN_in, F, 0)
+                ops.copy_cols(dC, dh + d, 0, dh, Nt, dN_in, F, 3)
+                dhs_e = torch.empty((Et, dh), **f32)
+                ops.egnn_edge_input_bwd(dU, nf, dh, rowptr, perm, rowptr_s, perm_s, Nt, None, dhs_e, dN_in, F, 3)
+                dN = dN_in
                 continue
             # ---- node function backward (egnn.py:208-229)
             zv, zh, zx = sv["zv"], sv["zh"], sv["zx"]

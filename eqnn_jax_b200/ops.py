@@ -304,8 +304,19 @@ def egnn_xv_base(nodes, F, sx, sv, n, base):
     check(lib().eqnn_egnn_xv_base(_ptr(nodes), F, _ptr(sx), _ptr(sv), n, _ptr(base), _stream()), "egnn_xv_base")
 
 
-def egnn_node_assemble(nodes, F, dh, ph, n, nodes_next):
-    check(lib().eqnn_egnn_node_assemble(_ptr(nodes), F, dh, _ptr(ph), n, _ptr(nodes_next), _stream()), "egnn_node_assemble")
+def egnn_node_assemble(nodes, F, h_off, ph, n, nodes_next):
+    check(lib().eqnn_egnn_node_assemble(_ptr(nodes), F, h_off, _ptr(ph), n, _ptr(nodes_next), _stream()),
+          "egnn_node_assemble")
+
+
+def egnn_segment_rows_fwd(rows, d, act, rowptr, n_nodes, agg, out, ld_out, col_off=0):
+    check(lib().eqnn_egnn_segment_rows_fwd(_ptr(rows), d, int(act), _ptr(rowptr), n_nodes, agg, _off(out, col_off), ld_out,
+                                           _stream()), "egnn_segment_rows_fwd")
+
+
+def egnn_segment_rows_bwd(dmi, ld_dmi, col_off, d, z, act, rowptr, n_nodes, agg, target):
+    check(lib().eqnn_egnn_segment_rows_bwd(_off(dmi, col_off), ld_dmi, d, _ptr(z), int(act), _ptr(rowptr), n_nodes, agg,
+                                           _ptr(target), _stream()), "egnn_segment_rows_bwd")
 
 
 def egnn_xv_bwd(nodes, F, sx, sv, dnext, mix, n, din, dsx, dsv):

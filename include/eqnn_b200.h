@@ -223,9 +223,17 @@ int eqnn_egnn_edge_input_bwd(const float* dU, int nf, int dh, const int32_t* row
 /* base[n] = sx[n] x[n] + sv[n] v[n] (sx NULL = 1): the coordinate layer then forms x' = wrap(base + agg)  (:213-227) */
 int eqnn_egnn_xv_base(const float* nodes, int F, const float* sx, const float* sv, int64_t n, float* base,
                       eqnn_stream_t stream);
-/* nodes_next[n, 3:] = (v, h + ph)   (x' is written by eqnn_egnn_coord_fwd; the OLD velocity is returned, :229) */
-int eqnn_egnn_node_assemble(const float* nodes, int F, int dh, const float* ph, int64_t n, float* nodes_next,
+/* nodes_next[n, 3:] = (columns [3, h_off) unchanged (the OLD velocity, :229), h + ph); x' is written by
+ * eqnn_egnn_coord_fwd */
+int eqnn_egnn_node_assemble(const float* nodes, int F, int h_off, const float* ph, int64_t n, float* nodes_next,
                             eqnn_stream_t stream);
+/* aggregated messages (jraph segment_sum / segment_mean of m_ij; read by the (x, h) and (x, v) node functions,
+ * egnn.py:161-166,180-196): out[r, :d] = agg_{e->r} act(rows[e, :]) with act 1 = gelu (messages kept as
+ * pre-activations) and its backward target[e, :] += dmi[r(e), :] / deg * act'(z[e, :]) */
+int eqnn_egnn_segment_rows_fwd(const float* rows, int d, int act, const int32_t* rowptr, int n_nodes, int agg, float* out,
+                               int ld_out, eqnn_stream_t stream);
+int eqnn_egnn_segment_rows_bwd(const float* dmi, int ld_dmi, int d, const float* z, int act, const int32_t* rowptr,
+                               int n_nodes, int agg, float* target, eqnn_stream_t stream);
 /* backward of the node update: dsx = g.x, dsv = g.v, din = (sx g + (mix - g), sv g + dnext_v, dnext_h); mix = g +
  * geometry gradient (NULL: none); din may be NULL (first step) */
 int eqnn_egnn_xv_bwd(const float* nodes, int F, const float* sx, const float* sv, const float* dnext, const float* mix,

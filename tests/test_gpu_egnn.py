@@ -39,7 +39,9 @@ def _run(kw, B=2, N=256, k=8, pbc=False, seed=0, F=3):
     from eqnn_jax_b200.egnn import EGNN
     rng = np.random.default_rng(seed)
     x = rng.uniform(-1.0, 1.7, size=(B, N, 3)).astype(np.float32)      # non-zero mean: the read-out pools positions
-    if F > 3:                                                          # (x, v, h): small velocities, O(1) scalars
+    if F > 3 and kw.get("positions_only", False):                      # (x, h): O(1) scalars
+        x = np.concatenate([x, rng.normal(size=(B, N, F - 3))], -1).astype(np.float32)
+    elif F > 3:                                                        # (x, v, h): small velocities, O(1) scalars
         x = np.concatenate([x, 0.05 * rng.normal(size=(B, N, 3)), rng.normal(size=(B, N, F - 6))], -1).astype(np.float32)
     cell = np.eye(3, dtype=np.float32) * 3.4
     opbc = G.get_apply_pbc(cell=cell) if pbc else None
@@ -121,15 +123,21 @@ XVH = dict(positions_only=False, n_layers=3, r_max=0.6, message_passing_steps=2,
           message_passing_agg="mean", task="graph"), True, 9),                            # tensor-core edge MLPs
     (dict(XVH, soft_edges=True, tanh_out=True, decouple_pos_vel_updates=True, d_hidden=64, n_radial_basis=0,
           message_passing_agg="sum", task="graph"), False, 8),
+    # (x, h): train_cosmology.py --feats all with EGNN_PARAMS (positions_only=True, velocities as scalars)
+    (dict(XVH, positions_only=True, soft_edges=False, d_hidden=128, n_radial_basis=32, message_passing_agg="mean",
+          task="graph"), True, 6),
+    (dict(XVH, positions_only=True, soft_edges=True, tanh_out=True, d_hidden=32, n_radial_basis=8,
+          message_passing_agg="sum", task="node", message_passing_steps=3), False, 5),
 ])
 def test_egnn_xvh_forward_and_gradients(kw, pbc, F):
-    """(x, v, h) node layout, egnn.py:47-60 and :198-229."""
+    """(x, v, h) node layout, egnn.py:47-60 and :198-229; (x, h) layout, :42-46 and :152-166."""
     got, want, params, p, x, p32 = _run(kw, pbc=pbc, F=F, seed=3)
     got = got.cpu().numpy()
     if kw["task"] == "node":
         _close(got, want, "nodes")
         _close(got[..., :3] - x[..., :3], want[..., :3] - x[..., :3], "coordinate update", rtol=1e-3)
-        assert np.array_equal(got[..., 3:6], x[..., 3:6])                      # the old velocity is returned (:229)
+        if not kw["positions_only"]:
+            assert np.array_equal(got[..., 3:6], x[..., 3:6])                  # the old velocity is returned (:229)
     else:
         _close(got, want, "output")
     gt = params.grad_tree
@@ -209,7 +217,5 @@ def test_egnn_unsupported_variants_fail_loudly():
     g = type("G", (), {"nodes": torch.zeros(1, 4, 6).cuda()})()
     with pytest.raises(NotImplementedError):
         EGNN(positions_only=False).init(0, g)                       # (x, v) layout: consumes aggregated messages
-    with pytest.raises(NotImplementedError):
-        EGNN(positions_only=True).init(0, type("G", (), {"nodes": torch.zeros(1, 4, 5).cuda()})())   # (x, h) layout
     with pytest.raises(NotImplementedError):
         EGNN(positions_only=True, message_passing_agg="max").init(0, type("G", (), {"nodes": torch.zeros(1, 4, 3).cuda()})())
