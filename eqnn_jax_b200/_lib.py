@@ -59,7 +59,7 @@ SIGNATURES: Dict[str, tuple] = {
     "eqnn_egnn_node_assemble": (_i, [_p, _i, _i, _p, _i64, _p, _p]),
     "eqnn_egnn_segment_rows_fwd": (_i, [_p, _i, _i, _p, _i, _i, _p, _i, _p]),
     "eqnn_egnn_segment_rows_bwd": (_i, [_p, _i, _i, _p, _i, _p, _i, _i, _p, _p]),
-    "eqnn_egnn_xv_bwd": (_i, [_p, _i, _p, _p, _p, _p, _i64, _p, _p, _p, _p]),
+    "eqnn_egnn_xv_bwd": (_i, [_p, _i, _p, _p, _p, _i, _p, _i64, _p, _p, _p, _p]),
     "eqnn_copy_cols": (_i, [_p, _i, _i, _i, _i64, _p, _i, _i, _p]),
     "eqnn_softgate_fwd": (_i, [_p, _p, _i64, _p, _p]),
     "eqnn_softgate_bwd": (_i, [_p, _p, _p, _i64, _p, _p, _p]),

@@ -408,13 +408,13 @@ __global__ void __launch_bounds__(256) egnn_segment_rows_bwd_kernel(const float*
 // and mix = g + geometry gradient of x (NULL in the first step: no input gradient needed, din may then be NULL):
 //   dsx = g.x, dsv = g.v ; din = (sx g + (mix - g), sv g + dnext_v, dnext_h)
 __global__ void egnn_xv_bwd_kernel(const float* __restrict__ nodes, int F, const float* __restrict__ sx,
-                                   const float* __restrict__ sv, const float* __restrict__ dnext,
+                                   const float* __restrict__ sv, const float* __restrict__ dnext, int ld_dnext,
                                    const float* __restrict__ mix, int64_t n, float* __restrict__ din,
                                    float* __restrict__ dsx, float* __restrict__ dsv) {
   const int64_t node = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (node >= n) return;
   const float* nd = nodes + node * F;
-  const float* dn = dnext + node * F;
+  const float* dn = dnext + node * ld_dnext;
   float gx = 0.f, gv = 0.f;
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
@@ -574,11 +574,12 @@ extern "C" int eqnn_egnn_segment_rows_bwd(const float* dmi, int ld_dmi, int d, c
 }
 
 extern "C" int eqnn_egnn_xv_bwd(const float* nodes, int F, const float* sx, const float* sv, const float* dnext,
-                                const float* mix, int64_t n, float* din, float* dsx, float* dsv, eqnn_stream_t stream) {
-  EQNN_CHECK_ARG(nodes && sv && dnext && dsv && F >= 6 && (!sx || dsx), "egnn_xv_bwd: bad argument");
+                                int ld_dnext, const float* mix, int64_t n, float* din, float* dsx, float* dsv,
+                                eqnn_stream_t stream) {
+  EQNN_CHECK_ARG(nodes && sv && dnext && dsv && F >= 6 && ld_dnext >= F && (!sx || dsx), "egnn_xv_bwd: bad argument");
   if (n <= 0) return EQNN_OK;
-  egnn_xv_bwd_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, as_stream(stream)>>>(nodes, F, sx, sv, dnext, mix, n, din,
-                                                                                 dsx, dsv);
+  egnn_xv_bwd_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, as_stream(stream)>>>(nodes, F, sx, sv, dnext, ld_dnext, mix,
+                                                                                 n, din, dsx, dsv);
   EQNN_CHECK_LAUNCH();
   return EQNN_OK;
 }

@@ -1,8 +1,8 @@
 """EGNN on B200 kernels, behind the reference's module interface.
 
-Drop-in for ``models/egnn.py`` (reference) in the configuration the cosmology benchmark and the example notebook
-use: ``positions_only=True`` on 3-d nodes (benchmarks/galaxies/train_cosmology.py:67-81 with feats='pos';
-notebooks/examples.ipynb cell 14).  Same dataclass fields and defaults (:240-255), ``GraphsTuple`` in ->
+Drop-in for ``models/egnn.py`` (reference).  The configuration the cosmology benchmark and the example notebook
+use is ``positions_only=True`` on 3-d nodes (benchmarks/galaxies/train_cosmology.py:67-81 with feats='pos';
+notebooks/examples.ipynb cell 14); the other node layouts are described below.  Same dataclass fields and defaults (:240-255), ``GraphsTuple`` in ->
 ``GraphsTuple`` (task="node") or ``(B, n_outputs)`` (task="graph") out, Flax parameter names (MLP_i / Dense_s).
 
 Per message-passing step, edges in receiver-sorted order:
@@ -18,9 +18,10 @@ equivariance test (tests/test_equivariance.py:224-250) -- is supported as well: 
 [bessel | h_sender | h_receiver] (egnn.py:47-60), the node update is v' = phi_v(h) v + agg, x' = wrap(phi_xx(h) x + v')
 (or x + v'), h' = h + phi_h(h), and (x', v, h') is returned (egnn.py:198-229); m_i is unused there too.
 The (x, h) layout (``positions_only=True`` with scalar attributes: train_cosmology.py --feats all) reads the
-aggregated messages: h' = h + phi_h([h, m_i]) (egnn.py:152-166), m_i = segment reduce of m_ij.
-Not built yet: the (x, v) layout without scalars (its node width grows to 6 + d_hidden after the first step),
-globals, max aggregation -> NotImplementedError, never a silent fallback.
+aggregated messages: h' = h + phi_h([h, m_i]) (egnn.py:152-166), m_i = segment reduce of m_ij.  The (x, v) layout
+(6 features) feeds m_i to phi_v / phi_xx and returns (x', v, m_i): the node width grows to 6 + d_hidden and the
+following steps run as (x, v, h) with d_hidden scalars (egnn.py:171-196) -- all four layouts of the reference.
+Not built yet: graph globals, max aggregation -> NotImplementedError, never a silent fallback.
 """
 from __future__ import annotations
 
@@ -65,8 +66,8 @@ class EGNN:
             if n_feat < 3:
                 raise ValueError("positions_only=True needs >= 3 node features")
             return False, n_feat - 3
-        if n_feat < 7:
-            raise NotImplementedError("B200 EGNN: positions_only=False needs (x, v, h) nodes with >= 1 scalar attribute")
+        if n_feat < 6:
+            raise ValueError("positions_only=False needs >= 6 node features (x, v)")
         return True, n_feat - 6
 
     def _check(self, n_feat: int) -> None:
@@ -81,7 +82,6 @@ class EGNN:
     def _layout(self, n_feat: int = 3):
         d, L = self.d_hidden, self.n_layers
         nf = self.n_radial_basis if self.n_radial_basis > 0 else 1
-        vel, dh = self._variant(n_feat)
         layout: List[Tuple[Tuple[str, ...], Tuple[int, ...], int]] = []
         off = 0
 
@@ -100,9 +100,10 @@ class EGNN:
                 fan = w
             return out
 
-        steps, mi = [], 0
+        steps, mi, Fs = [], 0, n_feat
         for s in range(self.message_passing_steps):
-            st = {"phi_e": [], "phi_x": []}
+            vel, dh = self._variant(Fs)
+            st = {"phi_e": [], "phi_x": [], "F": Fs, "vel": vel, "dh": dh}
             fan = nf + 2 * dh
             for l in range(L):
                 st["phi_e"].append((add((f"MLP_{mi}", f"Dense_{l}", "kernel"), (fan, d)),
@@ -120,17 +121,23 @@ class EGNN:
             mi += 1
             if not vel and dh > 0:                           # node function, egnn.py:159-166: phi_h([h_i, m_i])
                 st["phi_h"] = add_mlp(mi, dh + d, [d] * (L - 1) + [dh]); mi += 1
-            if vel:                                          # node function, egnn.py:208-222
-                st["phi_v"] = add_mlp(mi, dh, [d] * (L - 1) + [1]); mi += 1
-                st["phi_h"] = add_mlp(mi, dh, [d] * (L - 1) + [dh]); mi += 1
+            if vel:                                          # node function, egnn.py:171-229
+                n_in = dh if dh > 0 else d                   # concats = h_i, or m_i when there are no scalars
+                st["phi_v"] = add_mlp(mi, n_in, [d] * (L - 1) + [1]); mi += 1
+                st["phi_h"] = None
+                if dh > 0:
+                    st["phi_h"] = add_mlp(mi, n_in, [d] * (L - 1) + [dh]); mi += 1
                 st["phi_xx"] = None
                 if self.decouple_pos_vel_updates:
-                    st["phi_xx"] = add_mlp(mi, dh, [d] * (L - 1) + [1]); mi += 1
+                    st["phi_xx"] = add_mlp(mi, n_in, [d] * (L - 1) + [1]); mi += 1
+                if dh == 0:
+                    Fs = 6 + d                               # (x', v, m_i) is returned, egnn.py:196
+            st["F_out"] = Fs
             steps.append(st)
         readout = []
         if self.task == "graph":
-            ws = [self.mlp_readout_widths[0] * n_feat] + [w * d for w in self.mlp_readout_widths[1:]] + [self.n_outputs]
-            readout = add_mlp(mi, n_feat, ws)
+            ws = [self.mlp_readout_widths[0] * Fs] + [w * d for w in self.mlp_readout_widths[1:]] + [self.n_outputs]
+            readout = add_mlp(mi, Fs, ws)
         return layout, steps, readout, off
 
     def init(self, rng: Union[int, np.random.Generator], graphs: GraphsTuple) -> FlatParams:
@@ -211,21 +218,20 @@ class EGNN:
         rowptr, perm, src, rowptr_s, perm_s = csr
         dev = x.device
         f32 = dict(dtype=torch.float32, device=dev)
-        F = x.shape[-1]
-        vel, dh = self._variant(F)
-        layout, steps, readout, _ = self._layout(F)
+        layout, steps, readout, _ = self._layout(x.shape[-1])
         Nt, Et = B * N, B * E
         d = self.d_hidden
         nf = self.n_radial_basis if self.n_radial_basis > 0 else 1
-        K0 = nf + 2 * dh
-        ho = 6 if vel else 3                                 # first scalar-attribute column
         cell = None if self.apply_pbc is None else self.apply_pbc.cell
         cinv = None if self.apply_pbc is None else self.apply_pbc.cell_inv
         agg = 1 if self.message_passing_agg == "mean" else 0
         tc = self.tensor_cores
-        nodes = x.reshape(Nt, F)
+        nodes = x.reshape(Nt, x.shape[-1])
         saved = {"steps": []}
         for st in steps:
+            F, vel, dh, F_out = st["F"], st["vel"], st["dh"], st["F_out"]
+            K0 = nf + 2 * dh
+            ho = 6 if vel else 3                             # first scalar-attribute column
             rij4 = torch.empty((Et, 4), **f32)
             feats = torch.empty((Et, nf), **f32)
             ops.egnn_geom_fwd(nodes, F, Nt, rowptr, src, cell, cinv, self.n_radial_basis, self.r_max, rij4, feats)
@@ -254,30 +260,40 @@ class EGNN:
             t = torch.empty((Et,), **f32)
             _mm(Et, 1, d, 1.0, a, 0, d, theta, st["k_last"], 1, t, 0, Et, tc=True, pro=1, pro_scale=1.0,
                 tag="egnn_mlp_fwd", tf32x3=tc)
-            nodes_next = torch.empty((Nt, F), **f32)
+            nodes_next = torch.empty((Nt, F_out), **f32)
             sv = dict(rij4=rij4, U=U, acts=acts, t=t, Za=Za, Mg=Mg, nodes=nodes)
+            gated = st["phi_a"] is not None
             if not vel:
                 ops.egnn_coord_fwd(rij4, t, self.tanh_out, agg, rowptr, Nt, nodes, F, cell, cinv, nodes_next, F)
                 if dh > 0:                                   # (x, h): h' = h + phi_h([h, m_i]), egnn.py:152-166
                     Cc = torch.empty((Nt, dh + d), **f32)
                     ops.copy_cols(nodes, F, 3, dh, Nt, Cc, dh + d, 0)
-                    gated = st["phi_a"] is not None
                     ops.egnn_segment_rows_fwd(Mg if gated else acts[nE - 1], d, not gated, rowptr, Nt, agg, Cc, dh + d,
                                               col_off=dh)
                     zh = self._mlp_fwd(theta, st["phi_h"], Cc, 0, dh + d, Nt)
                     ops.egnn_node_assemble(nodes, F, 3, zh[-1], Nt, nodes_next)
                     sv.update(Cc=Cc, zh=zh)
             else:
-                zv = self._mlp_fwd(theta, st["phi_v"], nodes, 6, F, Nt)
-                zh = self._mlp_fwd(theta, st["phi_h"], nodes, 6, F, Nt)
-                zx = self._mlp_fwd(theta, st["phi_xx"], nodes, 6, F, Nt) if st["phi_xx"] is not None else None
+                if dh > 0:                                   # concats = h_i (egnn.py:207)
+                    cin, c_off, c_ld = nodes, 6, F
+                else:                                        # concats = m_i (egnn.py:180), returned as new scalars
+                    cin, c_off, c_ld = torch.empty((Nt, d), **f32), 0, d
+                    ops.egnn_segment_rows_fwd(Mg if gated else acts[nE - 1], d, not gated, rowptr, Nt, agg, cin, d)
+                zv = self._mlp_fwd(theta, st["phi_v"], cin, c_off, c_ld, Nt)
+                zh = self._mlp_fwd(theta, st["phi_h"], cin, c_off, c_ld, Nt) if dh > 0 else None
+                zx = self._mlp_fwd(theta, st["phi_xx"], cin, c_off, c_ld, Nt) if st["phi_xx"] is not None else None
                 base = torch.empty((Nt, 3), **f32)
                 ops.egnn_xv_base(nodes, F, None if zx is None else zx[-1], zv[-1], Nt, base)
-                ops.egnn_coord_fwd(rij4, t, self.tanh_out, agg, rowptr, Nt, base, 3, cell, cinv, nodes_next, F)
-                ops.egnn_node_assemble(nodes, F, 6, zh[-1], Nt, nodes_next)
-                sv.update(zv=zv, zh=zh, zx=zx)
+                ops.egnn_coord_fwd(rij4, t, self.tanh_out, agg, rowptr, Nt, base, 3, cell, cinv, nodes_next, F_out)
+                if dh > 0:
+                    ops.egnn_node_assemble(nodes, F, 6, zh[-1], Nt, nodes_next)
+                else:
+                    ops.copy_cols(nodes, F, 3, 3, Nt, nodes_next, F_out, 3)
+                    ops.copy_cols(cin, d, 0, d, Nt, nodes_next, F_out, 6)
+                sv.update(zv=zv, zh=zh, zx=zx, cin=cin, c_off=c_off, c_ld=c_ld)
             saved["steps"].append(sv)
             nodes = nodes_next
+        F = nodes.shape[-1]
         if self.task == "node":
             return nodes.view(B, N, F), saved
         pooled = torch.empty((B, F), **f32)
@@ -295,14 +311,11 @@ class EGNN:
         rowptr, perm, src, rowptr_s, perm_s = csr
         dev = theta.device
         f32 = dict(dtype=torch.float32, device=dev)
-        F = saved["steps"][0]["nodes"].shape[-1]
-        vel, dh = self._variant(F)
-        layout, steps, readout, _ = self._layout(F)
+        layout, steps, readout, _ = self._layout(saved["steps"][0]["nodes"].shape[-1])
         Nt, Et = B * N, B * E
         d = self.d_hidden
         nf = self.n_radial_basis if self.n_radial_basis > 0 else 1
-        K0 = nf + 2 * dh
-        ho = 6 if vel else 3
+        F = steps[-1]["F_out"]                               # width of the final node features
         agg = 1 if self.message_passing_agg == "mean" else 0
         tc = self.tensor_cores
         gtheta.zero_()
@@ -330,14 +343,29 @@ class EGNN:
         for si in range(len(steps) - 1, -1, -1):
             st, sv = steps[si], saved["steps"][si]
             rij4, U, acts, t, nodes = sv["rij4"], sv["U"], sv["acts"], sv["t"], sv["nodes"]
+            F, vel, dh, F_out = st["F"], st["vel"], st["dh"], st["F_out"]      # dN is (Nt, F_out) here
+            K0 = nf + 2 * dh
+            nE = len(st["phi_e"])
             g3 = dN
-            if F != 3:                                       # dL/dx' as a dense (Nt, 3) array
+            if F_out != 3:                                   # dL/dx' as a dense (Nt, 3) array
                 g3 = torch.empty((Nt, 3), **f32)
-                ops.copy_cols(dN, F, 0, 3, Nt, g3, 3, 0)
+                ops.copy_cols(dN, F_out, 0, 3, Nt, g3, 3, 0)
             ops.egnn_coord_bwd(rij4, t, self.tanh_out, agg, rowptr, perm, Nt, g3, self.n_radial_basis, self.r_max,
                                None, dt, None, None)
-            dC = None
+            dC, dC_ld, dC_off = None, 0, 0                    # dL/dm_i lives in dC[:, dC_off:], row stride dC_ld
+            if vel and dh == 0:
+                # (x, v) node function first: m_i feeds phi_v / phi_xx and is returned as the new scalar attributes
+                zv, zx = sv["zv"], sv["zx"]
+                dsv = torch.empty((Nt, 1), **f32)
+                dsx = torch.empty((Nt, 1), **f32) if zx is not None else None
+                ops.egnn_xv_bwd(nodes, F, None if zx is None else zx[-1], zv[-1], dN, F_out, None, Nt, None, dsx, dsv)
+                dC, dC_ld, dC_off = torch.empty((Nt, d), **f32), d, 0
+                ops.copy_cols(dN, F_out, 6, d, Nt, dC, d, 0)
+                self._mlp_bwd(theta, gtheta, st["phi_v"], zv, sv["cin"], 0, d, Nt, dsv, (dC, 0, d))
+                if zx is not None:
+                    self._mlp_bwd(theta, gtheta, st["phi_xx"], zx, sv["cin"], 0, d, Nt, dsx, (dC, 0, d))
             if not vel and dh > 0:
+                dC_ld, dC_off = dh + d, dh
                 # (x, h) node function first: it yields dL/dm_i, which joins the message gradient below.
                 # dC starts as [dL/dh' | 0]; the MLP input gradient is accumulated on top: [dL/dh (so far) | dL/dm_i]
                 dph = torch.empty((Nt, dh), **f32)
@@ -354,7 +382,6 @@ class EGNN:
             _mm(Et, d, 1, 1.0, dt, 0, Et, theta, st["k_last"], 1, dZ, 0, d, ta=True, tb=True, epi=2, aux=last, ld_aux=d,
                 epi_scale=1.0, tag="egnn_mlp_bwd", tf32x3=tc)
             dU = None
-            nE = len(st["phi_e"])
             for l in range(len(layers) - 1, -1, -1):
                 ko, bo, fan = layers[l]
                 a_prev, pro = (acts[l - 1], 1) if l > 0 else (U, 0)
@@ -370,7 +397,7 @@ class EGNN:
                     dM = torch.empty((Et, d), **f32)
                     _mm(Et, d, d, 1.0, dZ, 0, d, theta, ko, d, dM, 0, d, tb=True, tag="egnn_mlp_bwd", tf32x3=tc)
                     if dC is not None:                              # + dL/dm_i / deg on the gated message
-                        ops.egnn_segment_rows_bwd(dC, dh + d, dh, d, None, 0, rowptr, Nt, agg, dM)
+                        ops.egnn_segment_rows_bwd(dC, dC_ld, dC_off, d, None, 0, rowptr, Nt, agg, dM)
                     dZa = torch.empty((Et, d), **f32)
                     ops.softgate_bwd(ZL, Za, dM, dZa, dM)           # dM <- dM * sigmoid(Za)  (first branch into Z_L)
                     _mm(d, d, Et, 1.0, ZL, 0, d, dZa, 0, d, gtheta, ka, d, ta=True, pro=1, pro_scale=1.0,
@@ -386,7 +413,7 @@ class EGNN:
                     _mm(Et, fan, d, 1.0, dZ, 0, d, theta, ko, d, dZp, 0, fan, tb=True, epi=2, aux=acts[l - 1], ld_aux=fan,
                         epi_scale=1.0, tag="egnn_mlp_bwd", tf32x3=tc)
                     if dC is not None and l == nE:                  # message = gelu(Z_L): + dL/dm_i / deg * gelu'(Z_L)
-                        ops.egnn_segment_rows_bwd(dC, dh + d, dh, d, acts[l - 1], 1, rowptr, Nt, agg, dZp)
+                        ops.egnn_segment_rows_bwd(dC, dC_ld, dC_off, d, acts[l - 1], 1, rowptr, Nt, agg, dZp)
                     dZ = dZp
                 elif si > 0:
                     dU = torch.empty((Et, fan), **f32)
@@ -412,12 +439,15 @@ class EGNN:
                 ops.egnn_edge_input_bwd(dU, nf, dh, rowptr, perm, rowptr_s, perm_s, Nt, None, dhs_e, dN_in, F, 3)
                 dN = dN_in
                 continue
-            # ---- node function backward (egnn.py:208-229)
+            # ---- node function backward (egnn.py:171-229)
             zv, zh, zx = sv["zv"], sv["zh"], sv["zx"]
             dN_in = torch.empty((Nt, F), **f32) if si > 0 else None
             dsv = torch.empty((Nt, 1), **f32)
             dsx = torch.empty((Nt, 1), **f32) if zx is not None else None
-            ops.egnn_xv_bwd(nodes, F, None if zx is None else zx[-1], zv[-1], dN, mix, Nt, dN_in, dsx, dsv)
+            ops.egnn_xv_bwd(nodes, F, None if zx is None else zx[-1], zv[-1], dN, F_out, mix, Nt, dN_in, dsx, dsv)
+            if dh == 0:                                      # (x, v): the MLPs were differentiated above; 6 columns only
+                dN = dN_in
+                continue
             din = (dN_in, 6, F) if si > 0 else None
             if si > 0:
                 dhs_e = torch.empty((Et, dh), **f32)

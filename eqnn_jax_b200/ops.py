@@ -319,9 +319,9 @@ def egnn_segment_rows_bwd(dmi, ld_dmi, col_off, d, z, act, rowptr, n_nodes, agg,
                                            _ptr(target), _stream()), "egnn_segment_rows_bwd")
 
 
-def egnn_xv_bwd(nodes, F, sx, sv, dnext, mix, n, din, dsx, dsv):
-    check(lib().eqnn_egnn_xv_bwd(_ptr(nodes), F, _ptr(sx), _ptr(sv), _ptr(dnext), _ptr(mix), n, _ptr(din), _ptr(dsx),
-                                 _ptr(dsv), _stream()), "egnn_xv_bwd")
+def egnn_xv_bwd(nodes, F, sx, sv, dnext, ld_dnext, mix, n, din, dsx, dsv):
+    check(lib().eqnn_egnn_xv_bwd(_ptr(nodes), F, _ptr(sx), _ptr(sv), _ptr(dnext), ld_dnext, _ptr(mix), n, _ptr(din),
+                                 _ptr(dsx), _ptr(dsv), _stream()), "egnn_xv_bwd")
 
 
 def copy_cols(src, ld_src, col_src, width, n, dst, ld_dst, col_dst):

@@ -235,9 +235,10 @@ int eqnn_egnn_segment_rows_fwd(const float* rows, int d, int act, const int32_t*
 int eqnn_egnn_segment_rows_bwd(const float* dmi, int ld_dmi, int d, const float* z, int act, const int32_t* rowptr,
                                int n_nodes, int agg, float* target, eqnn_stream_t stream);
 /* backward of the node update: dsx = g.x, dsv = g.v, din = (sx g + (mix - g), sv g + dnext_v, dnext_h); mix = g +
- * geometry gradient (NULL: none); din may be NULL (first step) */
-int eqnn_egnn_xv_bwd(const float* nodes, int F, const float* sx, const float* sv, const float* dnext, const float* mix,
-                     int64_t n, float* din, float* dsx, float* dsv, eqnn_stream_t stream);
+ * geometry gradient (NULL: none); din may be NULL (first step); dnext has row stride ld_dnext >= F (the (x, v) layout
+ * returns 6 + d_hidden columns) */
+int eqnn_egnn_xv_bwd(const float* nodes, int F, const float* sx, const float* sv, const float* dnext, int ld_dnext,
+                     const float* mix, int64_t n, float* din, float* dsx, float* dsv, eqnn_stream_t stream);
 /* dst[n, col_dst + j] = src[n, col_src + j], j < width */
 int eqnn_copy_cols(const float* src, int ld_src, int col_src, int width, int64_t n, float* dst, int ld_dst, int col_dst,
                    eqnn_stream_t stream);

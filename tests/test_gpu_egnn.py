@@ -128,6 +128,11 @@ XVH = dict(positions_only=False, n_layers=3, r_max=0.6, message_passing_steps=2,
           task="graph"), True, 6),
     (dict(XVH, positions_only=True, soft_edges=True, tanh_out=True, d_hidden=32, n_radial_basis=8,
           message_passing_agg="sum", task="node", message_passing_steps=3), False, 5),
+    # (x, v): train_cosmology.py --feats all with positions_only=False; the node width grows to 6 + d_hidden (egnn.py:196)
+    (dict(XVH, soft_edges=False, decouple_pos_vel_updates=True, d_hidden=32, n_radial_basis=8,
+          message_passing_agg="mean", task="node", message_passing_steps=3), False, 6),
+    (dict(XVH, soft_edges=True, tanh_out=True, decouple_pos_vel_updates=False, d_hidden=64, n_radial_basis=16,
+          message_passing_agg="sum", task="graph"), True, 6),
 ])
 def test_egnn_xvh_forward_and_gradients(kw, pbc, F):
     """(x, v, h) node layout, egnn.py:47-60 and :198-229; (x, h) layout, :42-46 and :152-166."""
@@ -214,8 +219,7 @@ def test_egnn_equivariance_property():
 
 def test_egnn_unsupported_variants_fail_loudly():
     from eqnn_jax_b200.egnn import EGNN
-    g = type("G", (), {"nodes": torch.zeros(1, 4, 6).cuda()})()
     with pytest.raises(NotImplementedError):
-        EGNN(positions_only=False).init(0, g)                       # (x, v) layout: consumes aggregated messages
+        EGNN(positions_only=True, activation="relu").init(0, type("G", (), {"nodes": torch.zeros(1, 4, 3).cuda()})())
     with pytest.raises(NotImplementedError):
         EGNN(positions_only=True, message_passing_agg="max").init(0, type("G", (), {"nodes": torch.zeros(1, 4, 3).cuda()})())
