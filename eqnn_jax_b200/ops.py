@@ -285,10 +285,6 @@ def egnn_sender_acc(dre, rowptr_s, perm_s, n_nodes, dpos):
           "egnn_sender_acc")
 
 
-def _off(t, off):
-    return C.c_void_p(t.data_ptr() + 4 * off)
-
-
 def egnn_edge_input_fwd(feats, nf, nodes, F, h_off, dh, rowptr, src, n_nodes, U):
     check(lib().eqnn_egnn_edge_input_fwd(_ptr(feats), nf, _off(nodes, h_off), F, dh, _ptr(rowptr), _ptr(src), n_nodes,
                                          _ptr(U), _stream()), "egnn_edge_input_fwd")
