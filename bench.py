@@ -60,6 +60,11 @@ def peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, which="fallback")
 
 
+# measured with `ncu --set full` on this code (profiles/r1c_*_raw.csv): DRAM read + write bytes per edge and step
+NCU_MLP_DRAM_BYTES = 10788       # algorithmic: 10848
+NCU_TPCONV_DRAM_BYTES = 150.6    # fwd 55.9 + bwd 94.7; algorithmic: 45.6 + 79.0 (the 32-byte dL/dx_t records are re-read)
+
+
 def algorithmic(n_live, d_live, d_in=7, k=K_NN, n_rb=64, H=128, L=3):
     """per edge and message-passing step."""
     b_fwd = 8 + 4 * n_live + (12 + 4 * d_in + 4 * d_live) / k
@@ -306,7 +311,11 @@ def main():
         "roofline": {"kernel": "radial MLP GEMMs fwd+dgrad+wgrad (tc_rowgemm_kernel / tc_wgrad_kernel, tcgen05 "
                                "kind::tf32 x3): stream the per-edge activations layer by layer", "bound": "hbm",
                      "achieved": mlp_gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": mlp_gbs / pk["hbm"],
-                     "traffic": None, "peak_source": f"hbm_gbs of {pk['which']}",
+                     # DRAM bytes (read + write) of the same kernels under `ncu --set full`, per edge and step, summed over
+                     # the 11 GEMMs of one message-passing step (profiles/r1c_tc_microbench_raw.csv; that capture aliases the
+                     # dgrad kernel's aux operand with A, so its 512 B/edge are added); given per average launch
+                     "traffic": NCU_MLP_DRAM_BYTES * E_step * steps_mp / max((n_f + n_b) / args.profile_steps, 1),
+                     "traffic_bytes_per_edge_step": NCU_MLP_DRAM_BYTES, "peak_source": f"hbm_gbs of {pk['which']}",
                      "bytes_per_edge_step": mlp_bytes, "launches_per_step": (n_f + n_b) / args.profile_steps,
                      "ms_per_step": mlp_ms_step,
                      "note": "algorithmic traffic: fwd 256+512 | 2x(512+512) | 512+4n ; dgrad 4n+512+512 | "
@@ -317,7 +326,9 @@ def main():
                                 "peak_source": f"bf16_tflops_sustained of {pk['which']}",
                                 "flops_per_edge_step": f_fwd + f_bwd},
         "roofline_tpconv": {"kernel": "tpconv_fwd + tpconv_bwd", "bound": "hbm", "achieved": tp_gbs, "peak": pk["hbm"],
-                            "unit": "GB/s", "frac": tp_gbs / pk["hbm"], "traffic": None,
+                            "unit": "GB/s", "frac": tp_gbs / pk["hbm"],
+                            "traffic": NCU_TPCONV_DRAM_BYTES * E_step / 2,   # per launch (fwd and bwd averaged), ncu
+                            "traffic_bytes_per_edge_step": NCU_TPCONV_DRAM_BYTES,
                             "bytes_per_edge_step": b_fwd + b_bwd, "ms_fwd": ms_tf, "ms_bwd": ms_tb,
                             "n_live": n_live, "d_live": d_live, "peak_source": f"hbm_gbs of {pk['which']}"},
         "breakdown_ms_per_step": {k: t / args.profile_steps for k, (n, t) in sorted(prof.items())},
