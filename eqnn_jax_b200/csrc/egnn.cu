@@ -6,6 +6,7 @@
 // tc_mlp.cu.  All kernels walk the receiver-sorted CSR: one warp per receiver row, lanes over its edges,
 // shuffle reductions -- no atomics, deterministic.
 #include "common.cuh"
+#include "gen/tp_gen.cuh"
 
 namespace {
 
@@ -446,6 +447,81 @@ __global__ void copy_cols_kernel(const float* __restrict__ src, int ld_s, int c0
   dst[r * ld_d + c0d + j] = src[r * ld_s + c0s + j];
 }
 
+
+// ---- steerable graph attributes (models/utils/equivariant_graph_utils.py:27-102) -----------------------------
+struct ShScale { float f[5]; };      // e3nn `normalization=` factor per degree l
+
+// per edge, in the reference's edge order: r_ij = x[sender] - x[receiver] (minimum image, no EPS; :46-52),
+// edge attributes = normalisation * Y_lm(r_ij / |r_ij|) with e3nn's guard for |r| = 0 (:56-61)
+template <class SH>
+__global__ void steerable_edge_kernel(const float* __restrict__ pos, int ld, int N, int E, int64_t n_edges,
+                                      const int32_t* __restrict__ senders, const int32_t* __restrict__ receivers,
+                                      Cell3 cl, ShScale sc, float* __restrict__ r_ij, float* __restrict__ edge_attrs) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_edges) return;
+  const int64_t b = e / E;
+  const float* xs = pos + (size_t)(b * N + senders[e]) * ld;
+  const float* xr = pos + (size_t)(b * N + receivers[e]) * ld;
+  float rx = xs[0] - xr[0], ry = xs[1] - xr[1], rz = xs[2] - xr[2];
+  wrap(rx, ry, rz, cl);
+  r_ij[e * 3] = rx; r_ij[e * 3 + 1] = ry; r_ij[e * 3 + 2] = rz;
+  const float n2 = rx * rx + ry * ry + rz * rz;
+  const float n = sqrtf(n2 == 0.f ? 1.f : n2);
+  float Y[SH::NY];
+  SH::sh(rx / n, ry / n, rz / n, Y);
+#pragma unroll
+  for (int l = 0; l <= SH::LMAX; ++l)
+#pragma unroll
+    for (int m = 0; m < 2 * l + 1; ++m) edge_attrs[e * SH::NY + l * l + m] = sc.f[l] * Y[l * l + m];
+}
+
+// node attributes = e3nn.scatter_mean of the edge attributes over the receivers (:64-74; empty rows -> 0),
+// plus the harmonics of the node velocities when steerable_velocities (:76-83).  perm: original edge id per CSR slot
+template <class SH>
+__global__ void steerable_node_kernel(const float* __restrict__ edge_attrs, const int32_t* __restrict__ rowptr,
+                                      const int32_t* __restrict__ perm, int n_nodes, const float* __restrict__ vel,
+                                      int ld_vel, ShScale sc, float* __restrict__ node_attrs) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= n_nodes) return;
+  float a[SH::NY];
+#pragma unroll
+  for (int i = 0; i < SH::NY; ++i) a[i] = 0.f;
+  const int p0 = rowptr[n], p1 = rowptr[n + 1];
+  for (int q = p0; q < p1; ++q) {
+    const float* row = edge_attrs + (size_t)perm[q] * SH::NY;
+#pragma unroll
+    for (int i = 0; i < SH::NY; ++i) a[i] += row[i];
+  }
+  const float cnt = (float)max(p1 - p0, 1);
+#pragma unroll
+  for (int i = 0; i < SH::NY; ++i) a[i] = a[i] / cnt;
+  if (vel) {
+    const float vx = vel[n * ld_vel], vy = vel[n * ld_vel + 1], vz = vel[n * ld_vel + 2];
+    const float n2 = vx * vx + vy * vy + vz * vz;
+    const float nn = sqrtf(n2 == 0.f ? 1.f : n2);
+    float Y[SH::NY];
+    SH::sh(vx / nn, vy / nn, vz / nn, Y);
+#pragma unroll
+    for (int l = 0; l <= SH::LMAX; ++l)
+#pragma unroll
+      for (int m = 0; m < 2 * l + 1; ++m) a[l * l + m] += sc.f[l] * Y[l * l + m];
+  }
+#pragma unroll
+  for (int i = 0; i < SH::NY; ++i) node_attrs[n * SH::NY + i] = a[i];
+}
+
+template <class SH>
+void launch_steerable(const float* pos, int ld_pos, const float* vel, int ld_vel, int B, int N, int E,
+                      const int32_t* senders, const int32_t* receivers, const int32_t* rowptr, const int32_t* perm,
+                      const Cell3& cl, const ShScale& sc, float* r_ij, float* edge_attrs, float* node_attrs,
+                      cudaStream_t st) {
+  const int64_t n_edges = (int64_t)B * E;
+  steerable_edge_kernel<SH><<<(unsigned)ceil_div64(n_edges, 256), 256, 0, st>>>(pos, ld_pos, N, E, n_edges, senders,
+                                                                                receivers, cl, sc, r_ij, edge_attrs);
+  steerable_node_kernel<SH><<<(unsigned)ceil_div64((int64_t)B * N, 256), 256, 0, st>>>(edge_attrs, rowptr, perm, B * N, vel,
+                                                                                     ld_vel, sc, node_attrs);
+}
+
 }  // namespace
 
 extern "C" int eqnn_egnn_geom_fwd(const float* pos, int ld_pos, int n_nodes, const int32_t* rowptr,
@@ -592,6 +668,31 @@ extern "C" int eqnn_copy_cols(const float* src, int ld_src, int col_src, int wid
   copy_cols_kernel<<<(unsigned)ceil_div64(n * width, 256), 256, 0, as_stream(stream)>>>(src, ld_src, col_src, width, n,
                                                                                        dst, ld_dst, col_dst);
   EQNN_CHECK_LAUNCH();
+  return EQNN_OK;
+}
+
+extern "C" int eqnn_steerable_attrs(const float* pos, int ld_pos, const float* vel, int ld_vel, int B, int N, int E,
+                                    const int32_t* senders, const int32_t* receivers, const int32_t* rowptr,
+                                    const int32_t* perm, const float* cell, const float* cell_inv, int lmax,
+                                    int sh_norm, float* r_ij, float* edge_attrs, float* node_attrs,
+                                    eqnn_stream_t stream) {
+  EQNN_CHECK_ARG(pos && senders && receivers && rowptr && perm && r_ij && edge_attrs && node_attrs && ld_pos >= 3,
+                 "steerable_attrs: bad argument");
+  EQNN_CHECK_ARG(lmax >= 1 && lmax <= 3, "steerable_attrs: lmax_attributes must be 1..3");
+  EQNN_CHECK_ARG(sh_norm >= 0 && sh_norm <= 2, "steerable_attrs: sh_norm must be 0 (norm), 1 (component) or 2 (integral)");
+  EQNN_CHECK_ARG(!vel || ld_vel >= 3, "steerable_attrs: bad velocity stride");
+  if (B <= 0 || N <= 0) return EQNN_OK;
+  Cell3 cl;
+  int rc = make_cell(cl, cell, cell_inv);
+  if (rc) return rc;
+  ShScale sc;
+  for (int l = 0; l < 5; ++l)
+    sc.f[l] = sh_norm == 0 ? 1.f : (sh_norm == 1 ? sqrtf(2.f * l + 1.f) : (float)sqrt((2.0 * l + 1.0) / (4.0 * 3.14159265358979323846)));
+  cudaStream_t st = as_stream(stream);
+  if (lmax == 1) launch_steerable<SH_1>(pos, ld_pos, vel, ld_vel, B, N, E, senders, receivers, rowptr, perm, cl, sc, r_ij, edge_attrs, node_attrs, st);
+  else if (lmax == 2) launch_steerable<SH_2>(pos, ld_pos, vel, ld_vel, B, N, E, senders, receivers, rowptr, perm, cl, sc, r_ij, edge_attrs, node_attrs, st);
+  else launch_steerable<SH_3>(pos, ld_pos, vel, ld_vel, B, N, E, senders, receivers, rowptr, perm, cl, sc, r_ij, edge_attrs, node_attrs, st);
+  EQNN_CHECK_LAUNCH_N(2);
   return EQNN_OK;
 }
 

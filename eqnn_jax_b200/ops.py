@@ -285,6 +285,19 @@ def egnn_sender_acc(dre, rowptr_s, perm_s, n_nodes, dpos):
           "egnn_sender_acc")
 
 
+def steerable_attrs(pos, ld_pos, vel, ld_vel, B, N, E, senders, receivers, rowptr, perm, cell, cell_inv, lmax, sh_norm):
+    """-> r_ij [B*E, 3], edge_attrs [B*E, (lmax+1)^2], node_attrs [B*N, (lmax+1)^2] (equivariant_graph_utils.py:27-83)."""
+    ny = (lmax + 1) ** 2
+    dev = pos.device
+    r_ij = torch.empty((B * E, 3), dtype=_F32, device=dev)
+    e_attr = torch.empty((B * E, ny), dtype=_F32, device=dev)
+    n_attr = torch.empty((B * N, ny), dtype=_F32, device=dev)
+    check(lib().eqnn_steerable_attrs(_ptr(pos), ld_pos, _ptr(vel), ld_vel, B, N, E, _ptr(senders), _ptr(receivers),
+                                     _ptr(rowptr), _ptr(perm), _c9(cell), _c9(cell_inv), lmax, sh_norm, _ptr(r_ij),
+                                     _ptr(e_attr), _ptr(n_attr), _stream()), "steerable_attrs")
+    return r_ij, e_attr, n_attr
+
+
 def egnn_edge_input_fwd(feats, nf, nodes, F, h_off, dh, rowptr, src, n_nodes, U):
     check(lib().eqnn_egnn_edge_input_fwd(_ptr(feats), nf, _off(nodes, h_off), F, dh, _ptr(rowptr), _ptr(src), n_nodes,
                                          _ptr(U), _stream()), "egnn_edge_input_fwd")

@@ -193,6 +193,18 @@ int eqnn_layernorm_bwd(const float* a, int da, const float* g, int dg, int B, co
 /* y[n] = sum_m x[m, n]  (bias gradients) */
 int eqnn_colsum(const float* x, int64_t M, int N, float* y, eqnn_stream_t stream);
 
+/* ---- steerable graph attributes (models/utils/equivariant_graph_utils.py:27-102, `get_equivariant_graph`) ----
+ * Edges in the reference's order (senders / receivers: [B, E] local ids; rowptr / perm: receiver-sorted CSR of
+ * eqnn_csr_build).  r_ij[e] = x[sender] - x[receiver], minimum image when cell != NULL, no EPS (:46-52);
+ * edge_attrs[e, (lmax+1)^2] = normalisation * Y_lm(r_ij / |r_ij|) (:56-61; sh_norm 0 "norm", 1 "component",
+ * 2 "integral"); node_attrs[n] = e3nn.scatter_mean of edge_attrs over the receivers (:64-74) + Y_lm(vel[n]) when
+ * vel != NULL (steerable_velocities, :76-83).  additional_messages (:85-90) = eqnn_edge_features(r_ij).
+ * cell / cell_inv: HOST pointers to 9 floats or NULL. */
+int eqnn_steerable_attrs(const float* pos, int ld_pos, const float* vel, int ld_vel, int B, int N, int E,
+                         const int32_t* senders, const int32_t* receivers, const int32_t* rowptr, const int32_t* perm,
+                         const float* cell, const float* cell_inv, int lmax, int sh_norm, float* r_ij,
+                         float* edge_attrs, float* node_attrs, eqnn_stream_t stream);
+
 /* ---- EGNN coordinate layer (models/egnn.py, positions-only) ---------------------------------------------
  * geometry (:82-90):  rij4[p] = (r_ij, |r_ij|), r_ij = x_s - x_r + 1e-7 then minimum image (cell may be NULL);
  *                     feats[p, :] = e3nn.bessel(|r_ij|, n_rb, r_max)  ([n_edges, 1] = |r_ij| if n_rb == 0)

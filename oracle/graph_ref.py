@@ -111,6 +111,55 @@ def build_graph(node_feats, global_feats, k, use_edges=True, apply_pbc=None, n_r
 
 
 # rotation helpers used by the reference's tests (graph_utils.py:334-364)
+class SteerableGraphsTuple(NamedTuple):
+    """models/utils/equivariant_graph_utils.py:14-24."""
+    nodes: object
+    edges: object
+    receivers: object
+    senders: object
+    additional_messages: object
+    steerable_node_attrs: object
+    steerable_edge_attrs: object
+    globals: object
+    n_node: object
+    n_edge: object
+
+
+def get_equivariant_graph(node_features, positions, velocities, senders, receivers, n_node, n_edge, edges, globals,
+                          lmax_attributes, additional_messages=None, steerable_velocities=False,
+                          spherical_harmonics_norm="integral", apply_pbc=None, n_radial_basis=0, r_max=1.0):
+    """equivariant_graph_utils.py:27-102 in numpy fp32 (test infrastructure only).
+
+    r_ij = x[senders] - x[receivers] (minimum image if apply_pbc; no EPS, :46-52); edge attributes = normalised
+    spherical harmonics up to lmax_attributes (:56-61); node attributes = e3nn.scatter_mean of the edge attributes
+    over the receivers, graph by graph (:64-74), plus the harmonics of the velocities if steerable_velocities
+    (:76-83); additional_messages = e3nn.bessel(|r_ij|) as n_rb x 0e or |r_ij| as 1x0e (:85-90)."""
+    from .so3 import spherical_harmonics
+    pos = np.asarray(positions, dtype=np.float32)
+    B, N = pos.shape[:2]
+    snd, rcv = np.asarray(senders), np.asarray(receivers)
+    bi = np.arange(B)[:, None]
+    r_ij = (pos[bi, snd] - pos[bi, rcv]).astype(np.float32)
+    if apply_pbc is not None:
+        r_ij = np.asarray(apply_pbc(r_ij), dtype=np.float32)
+    e_attr = spherical_harmonics(lmax_attributes, r_ij.astype(np.float64), True, spherical_harmonics_norm)
+    D = e_attr.shape[-1]
+    n_attr = np.zeros((B, N, D))
+    cnt = np.zeros((B, N))
+    for b in range(B):
+        np.add.at(n_attr[b], rcv[b], e_attr[b])
+        np.add.at(cnt[b], rcv[b], 1.0)
+    n_attr = n_attr / np.maximum(cnt, 1.0)[..., None]
+    if steerable_velocities:
+        n_attr = n_attr + spherical_harmonics(lmax_attributes, np.asarray(velocities, dtype=np.float64), True,
+                                              spherical_harmonics_norm)
+    d = np.sqrt((r_ij.astype(np.float32) ** 2).sum(-1, dtype=np.float32)).astype(np.float32)
+    add = bessel_np(d, n_radial_basis, r_max) if n_radial_basis > 0 else d[..., None]
+    return SteerableGraphsTuple(nodes=node_features, edges=edges, receivers=receivers, senders=senders,
+                                additional_messages=add, steerable_node_attrs=n_attr, steerable_edge_attrs=e_attr,
+                                globals=globals, n_node=n_node, n_edge=n_edge)
+
+
 def rotation_matrix(angle_deg, axis):
     a_rad = np.radians(angle_deg)
     axis = np.asarray(axis, dtype=np.float64)

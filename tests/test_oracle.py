@@ -194,6 +194,34 @@ def test_reference_egnn_equivariance_test_on_oracle(F, kw):
     np.testing.assert_allclose(o1, rot(o0), atol=2e-5 * max(1.0, np.abs(o0).max()))
 
 
+def test_steerable_attributes_on_oracle():
+    """equivariant_graph_utils.py:27-102 restated in oracle/graph_ref.py: the attributes are spherical tensors
+    (Y(R r) = D(R) Y(r)), the node attributes are receiver-side means, self-loop edges (r = 0) give (Y_0, 0, ...),
+    and the radial messages are rotation invariant."""
+    from oracle import so3
+    rng = np.random.default_rng(2)
+    x = rng.normal(size=(2, 20, 3)).astype(np.float32)
+    v = rng.normal(size=(2, 20, 3)).astype(np.float32)
+    R = G.rotation_matrix(33.0, np.array([0.3, -0.5, 0.81]) / np.linalg.norm([0.3, -0.5, 0.81]))
+    g = G.build_graph(x, None, 4)
+    kw = dict(steerable_velocities=True, spherical_harmonics_norm="integral", n_radial_basis=6, r_max=2.0)
+    a = G.get_equivariant_graph(None, x, v, g.senders, g.receivers, g.n_node, g.n_edge, None, None, 2, **kw)
+    b = G.get_equivariant_graph(None, (x @ R.T).astype(np.float32), (v @ R.T).astype(np.float32), g.senders, g.receivers,
+                                g.n_node, g.n_edge, None, None, 2, **kw)
+    D = so3.irreps_rotation_matrix(so3.Irreps.spherical_harmonics(2), R)
+    np.testing.assert_allclose(b.steerable_edge_attrs, a.steerable_edge_attrs @ D.T, atol=2e-6)
+    np.testing.assert_allclose(b.steerable_node_attrs, a.steerable_node_attrs @ D.T, atol=2e-6)
+    np.testing.assert_allclose(b.additional_messages, a.additional_messages, atol=2e-5)
+    self_loops = g.senders == g.receivers
+    assert self_loops.any()
+    y0 = 1.0 / np.sqrt(4 * np.pi)
+    np.testing.assert_allclose(a.steerable_edge_attrs[self_loops], np.array([y0] + [0.0] * 8)[None].repeat(self_loops.sum(), 0))
+    # node attribute of node 0 of graph 0 = mean over its incoming edges + Y(v)
+    inc = g.receivers[0] == 0
+    want = a.steerable_edge_attrs[0][inc].mean(0) + so3.spherical_harmonics(2, v[0, 0].astype(np.float64), True, "integral")
+    np.testing.assert_allclose(a.steerable_node_attrs[0, 0], want, atol=1e-12)
+
+
 def test_pbc_sanity_reference_tests():
     """tests/test_pbcs.py:8-33 and :35-62."""
     rng = np.random.default_rng(0)
