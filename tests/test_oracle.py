@@ -222,6 +222,66 @@ def test_steerable_attributes_on_oracle():
     np.testing.assert_allclose(a.steerable_node_attrs[0, 0], want, atol=1e-12)
 
 
+def _steerable(x, k=5):
+    from oracle.e3nn_ref import IrrepsArray
+    g = G.build_graph(x, None, k)
+    return G.get_equivariant_graph(IrrepsArray("1o+1o+1x0e", torch.tensor(x, dtype=torch.float64)), x[..., :3], x[..., 3:6],
+                                   g.senders, g.receivers, g.n_node, g.n_edge, None, None, 1)
+
+
+def test_segnn_param_count_matches_notebook():
+    """notebooks/examples.ipynb cells 8-9: 573 253 parameters (d_hidden 128, l_max 1, 3 x 3 layers, 64 radial)."""
+    from oracle import segnn_ref as S
+    from oracle.so3 import Irreps
+    cfg = S.SEGNNConfig(d_hidden=128, l_max_hidden=1, n_layers=3, message_passing_steps=3, task="graph",
+                        output_irreps="1x0e", message_passing_agg="mean", n_outputs=2, residual=False)
+    p = S.init_params(cfg, "1o", Irreps.spherical_harmonics(1), "64x0e")
+
+    def count(t):
+        return sum(count(v) if isinstance(v, dict) else int(np.prod(v.shape)) for v in t.values())
+    assert count(p) == 573253
+
+
+@pytest.mark.parametrize("task", ["node", "graph"])
+def test_reference_segnn_equivariance_tests_on_oracle(task):
+    """tests/test_equivariance.py:288-335 (SEGNN node: f(Rx) = R f(x); SEGNN graph: f(Rx) = f(x)), rtol 0.05."""
+    from oracle import segnn_ref as S
+    from oracle.so3 import Irreps
+    rng = np.random.default_rng(0)
+    x = rng.normal(size=(2, 5, 7)).astype(np.float32)
+    axis = np.array([0, 1 / np.sqrt(2), 1 / np.sqrt(2)])
+    xr = np.stack([G.rotate_representation(x[b], 45.0, axis) for b in range(2)]).astype(np.float32)
+    cfg = S.SEGNNConfig(message_passing_steps=2 if task == "node" else 3, d_hidden=32, task=task, residual=True,
+                        output_irreps="1o + 1o + 1x0e" if task == "node" else "1x0e")
+    p = NQ.to_torch(S.init_params(cfg, "1o+1o+1x0e", Irreps.spherical_harmonics(1), "1x0e", seed=0))
+    o1 = S.apply_batched(p, cfg, _steerable(x))
+    o2 = S.apply_batched(p, cfg, _steerable(xr))
+    if task == "node":
+        a, b = o1.array.numpy(), o2.array.numpy()
+        ar = np.stack([G.rotate_representation(a[i], 45.0, axis) for i in range(2)])
+        assert not np.allclose(a, b, rtol=0.05)
+        assert np.allclose(b, ar, rtol=0.05, atol=1e-6)
+        np.testing.assert_allclose(b, ar, atol=2e-5 * np.abs(a).max())
+    else:
+        np.testing.assert_allclose(o1.numpy(), o2.numpy(), rtol=1e-4, atol=1e-7)
+
+
+def test_segnn_discarded_node_layers_have_zero_gradient():
+    """segnn.py:84-89: the first n_layers-1 TPLGs of the node function own parameters but never reach the output."""
+    from oracle import segnn_ref as S
+    from oracle.so3 import Irreps
+    rng = np.random.default_rng(1)
+    x = rng.normal(size=(1, 6, 7)).astype(np.float32)
+    cfg = S.SEGNNConfig(message_passing_steps=1, d_hidden=16, n_layers=3, task="graph", output_irreps="1x0e")
+    p = NQ.to_torch(S.init_params(cfg, "1o+1o+1x0e", Irreps.spherical_harmonics(1), "1x0e", seed=0), requires_grad=True)
+    S.apply_batched(p, cfg, _steerable(x, 4)).sum().backward()
+    # creation order: embed (0), edge fn (1, 2, 3), node fn (4, 5 discarded; 6 used), read-out (7)
+    for name, dead in [("TensorProductLinearGate_4", True), ("TensorProductLinearGate_5", True),
+                       ("TensorProductLinearGate_6", False), ("TensorProductLinearGate_3", False)]:
+        g = max(float(w.grad.abs().max()) if w.grad is not None else 0.0 for w in p[name]["Linear_0"].values())
+        assert (g == 0.0) == dead, (name, g)
+
+
 def test_pbc_sanity_reference_tests():
     """tests/test_pbcs.py:8-33 and :35-62."""
     rng = np.random.default_rng(0)
