@@ -53,6 +53,10 @@ SIGNATURES: Dict[str, tuple] = {
     "eqnn_egnn_coord_fwd": (_i, [_p, _p, _i, _i, _p, _i, _p, _i, _p, _p, _p, _i, _p]),
     "eqnn_egnn_coord_bwd": (_i, [_p, _p, _i, _i, _p, _p, _i, _p, _i, _d, _p, _p, _p, _p, _p]),
     "eqnn_egnn_sender_acc": (_i, [_p, _p, _p, _i, _p, _p]),
+    "eqnn_segnn_ycontract": (_i, [_p, _p, _i, _p, _i, _i, _i64, _i, _i, _p, _p]),
+    "eqnn_segnn_yexpand": (_i, [_p, _p, _i, _i64, _i, _i, _p, _p]),
+    "eqnn_gather_rows": (_i, [_p, _p, _i64, _i, _p, _p]),
+    "eqnn_axpy": (_i, [_i64, _f, _p, _p, _p]),
     "eqnn_steerable_attrs": (_i, [_p, _i, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p]),
     "eqnn_egnn_edge_input_fwd": (_i, [_p, _i, _p, _i, _i, _p, _p, _i, _p, _p]),
     "eqnn_egnn_edge_input_bwd": (_i, [_p, _i, _i, _p, _p, _p, _p, _i, _p, _p, _p, _i, _p]),

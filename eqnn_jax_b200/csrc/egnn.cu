@@ -522,6 +522,48 @@ void launch_steerable(const float* pos, int ld_pos, const float* vel, int ld_vel
                                                                                      ld_vel, sc, node_attrs);
 }
 
+
+// ---- SEGNN TensorProductLinearGate (models/segnn.py:30-64), dense-lowered -----------------------------------
+// Linear(TP(x, y)) is bilinear in (x, y): z[r, o] = b[o] + sum_j y[r, j] * (x[r, :] @ M_j)[o].  The GEMM produces
+// Xbig[r, j * Do + o] = (x @ [M_0 | M_1 | ...])[r, j * Do + o]; these two kernels contract / expand the y axis.
+__global__ void segnn_ycontract_kernel(const float* __restrict__ Xbig, const float* __restrict__ y, int ld_y,
+                                       const float* __restrict__ bias, int bias_col, int n_bias, int64_t R, int Dy,
+                                       int Do, float* __restrict__ z) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R * Do) return;
+  const int64_t r = i / Do;
+  const int o = (int)(i - r * Do);
+  float a = (bias && o >= bias_col && o < bias_col + n_bias) ? bias[o - bias_col] : 0.f;
+  const float* xb = Xbig + r * (size_t)Dy * Do + o;
+  for (int j = 0; j < Dy; ++j) a = fmaf(y ? y[r * ld_y + j] : 1.f, xb[(size_t)j * Do], a);
+  z[i] = a;
+}
+
+__global__ void segnn_yexpand_kernel(const float* __restrict__ dz, const float* __restrict__ y, int ld_y, int64_t R,
+                                     int Dy, int Do, float* __restrict__ dXbig) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R * Dy * Do) return;
+  const int64_t r = i / ((int64_t)Dy * Do);
+  const int rem = (int)(i - r * (int64_t)Dy * Do);
+  const int j = rem / Do, o = rem - j * Do;
+  dXbig[i] = (y ? y[r * ld_y + j] : 1.f) * dz[r * Do + o];
+}
+
+// dst[p, :] = src[perm[p], :]
+__global__ void gather_rows_kernel(const float* __restrict__ src, const int32_t* __restrict__ perm, int64_t n, int w,
+                                   float* __restrict__ dst) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * w) return;
+  const int64_t p = i / w;
+  dst[i] = src[(size_t)perm[p] * w + (i - p * w)];
+}
+
+// y[i] += a * x[i]
+__global__ void axpy_kernel(int64_t n, float a, const float* __restrict__ x, float* __restrict__ y) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = fmaf(a, x[i], y[i]);
+}
+
 }  // namespace
 
 extern "C" int eqnn_egnn_geom_fwd(const float* pos, int ld_pos, int n_nodes, const int32_t* rowptr,
@@ -693,6 +735,43 @@ extern "C" int eqnn_steerable_attrs(const float* pos, int ld_pos, const float* v
   else if (lmax == 2) launch_steerable<SH_2>(pos, ld_pos, vel, ld_vel, B, N, E, senders, receivers, rowptr, perm, cl, sc, r_ij, edge_attrs, node_attrs, st);
   else launch_steerable<SH_3>(pos, ld_pos, vel, ld_vel, B, N, E, senders, receivers, rowptr, perm, cl, sc, r_ij, edge_attrs, node_attrs, st);
   EQNN_CHECK_LAUNCH_N(2);
+  return EQNN_OK;
+}
+
+extern "C" int eqnn_segnn_ycontract(const float* Xbig, const float* y, int ld_y, const float* bias, int bias_col,
+                                    int n_bias, int64_t R, int Dy, int Do, float* z, eqnn_stream_t stream) {
+  EQNN_CHECK_ARG(Xbig && z && Dy >= 1 && Do >= 1 && (y || Dy == 1) && (!y || ld_y >= Dy) && n_bias >= 0 && bias_col >= 0 &&
+                     bias_col + n_bias <= Do, "segnn_ycontract: bad argument");
+  if (R <= 0) return EQNN_OK;
+  segnn_ycontract_kernel<<<(unsigned)ceil_div64(R * Do, 256), 256, 0, as_stream(stream)>>>(Xbig, y, ld_y, bias, bias_col,
+                                                                                         n_bias, R, Dy, Do, z);
+  EQNN_CHECK_LAUNCH();
+  return EQNN_OK;
+}
+
+extern "C" int eqnn_segnn_yexpand(const float* dz, const float* y, int ld_y, int64_t R, int Dy, int Do, float* dXbig,
+                                  eqnn_stream_t stream) {
+  EQNN_CHECK_ARG(dz && dXbig && Dy >= 1 && Do >= 1 && (y || Dy == 1) && (!y || ld_y >= Dy), "segnn_yexpand: bad argument");
+  if (R <= 0) return EQNN_OK;
+  segnn_yexpand_kernel<<<(unsigned)ceil_div64(R * Dy * Do, 256), 256, 0, as_stream(stream)>>>(dz, y, ld_y, R, Dy, Do, dXbig);
+  EQNN_CHECK_LAUNCH();
+  return EQNN_OK;
+}
+
+extern "C" int eqnn_gather_rows(const float* src, const int32_t* perm, int64_t n, int width, float* dst,
+                                eqnn_stream_t stream) {
+  EQNN_CHECK_ARG(src && perm && dst && width >= 1, "gather_rows: bad argument");
+  if (n <= 0) return EQNN_OK;
+  gather_rows_kernel<<<(unsigned)ceil_div64(n * width, 256), 256, 0, as_stream(stream)>>>(src, perm, n, width, dst);
+  EQNN_CHECK_LAUNCH();
+  return EQNN_OK;
+}
+
+extern "C" int eqnn_axpy(int64_t n, float a, const float* x, float* y, eqnn_stream_t stream) {
+  EQNN_CHECK_ARG(x && y, "axpy: null pointer");
+  if (n <= 0) return EQNN_OK;
+  axpy_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, as_stream(stream)>>>(n, a, x, y);
+  EQNN_CHECK_LAUNCH();
   return EQNN_OK;
 }
 

@@ -285,6 +285,28 @@ def egnn_sender_acc(dre, rowptr_s, perm_s, n_nodes, dpos):
           "egnn_sender_acc")
 
 
+def segnn_ycontract(Xbig, y, ld_y, bias_buf, bias_off, bias_col, n_bias, R, Dy, Do, z, x_off=0, y_off=0, z_off=0):
+    check(lib().eqnn_segnn_ycontract(_off(Xbig, x_off), None if y is None else _off(y, y_off), ld_y,
+                                     None if bias_buf is None else _off(bias_buf, bias_off), bias_col, n_bias, R, Dy, Do,
+                                     _off(z, z_off), _stream()), "segnn_ycontract")
+
+
+def segnn_yexpand(dz, y, ld_y, R, Dy, Do, dXbig, dz_off=0, y_off=0):
+    check(lib().eqnn_segnn_yexpand(_off(dz, dz_off), None if y is None else _off(y, y_off), ld_y, R, Dy, Do, _ptr(dXbig),
+                                   _stream()), "segnn_yexpand")
+
+
+def gather_rows(src, perm, width):
+    n = perm.numel()
+    dst = torch.empty((n, width), dtype=_F32, device=src.device)
+    check(lib().eqnn_gather_rows(_ptr(src), _ptr(perm), n, width, _ptr(dst), _stream()), "gather_rows")
+    return dst
+
+
+def axpy(a, x, y):
+    check(lib().eqnn_axpy(x.numel(), float(a), _ptr(x), _ptr(y), _stream()), "axpy")
+
+
 def steerable_attrs(pos, ld_pos, vel, ld_vel, B, N, E, senders, receivers, rowptr, perm, cell, cell_inv, lmax, sh_norm):
     """-> r_ij [B*E, 3], edge_attrs [B*E, (lmax+1)^2], node_attrs [B*N, (lmax+1)^2] (equivariant_graph_utils.py:27-83)."""
     ny = (lmax + 1) ** 2

@@ -205,6 +205,22 @@ int eqnn_steerable_attrs(const float* pos, int ld_pos, const float* vel, int ld_
                          const float* cell, const float* cell_inv, int lmax, int sh_norm, float* r_ij,
                          float* edge_attrs, float* node_attrs, eqnn_stream_t stream);
 
+/* ---- SEGNN TensorProductLinearGate (models/segnn.py:30-64), dense-lowered ---------------------------------
+ * Linear(TP(x, y)) = sum_j y_j (x @ M_j) + b: the host lowers the e3nn Linear weights and the Clebsch-Gordan
+ * coefficients into M_cat = [M_0 | M_1 | ...] (Dx x Dy*Do, eqnn_weights_expand), eqnn_gemm_f32 forms
+ * Xbig = x @ M_cat, and these kernels contract / expand the attribute axis:
+ *   z[r, o] = bias[o - bias_col] (for bias_col <= o < bias_col + n_bias: the 0e block) + sum_j y[r, j] Xbig[r, j*Do + o]
+ *                                                                          (y NULL: Dy = 1, y = 1; segnn.py:35-36)
+ *   dXbig[r, j*Do + o] = y[r, j] dz[r, o]
+ * The gate (segnn.py:55-63) is eqnn_gate_fwd/bwd. */
+int eqnn_segnn_ycontract(const float* Xbig, const float* y, int ld_y, const float* bias, int bias_col, int n_bias,
+                         int64_t R, int Dy, int Do, float* z, eqnn_stream_t stream);
+int eqnn_segnn_yexpand(const float* dz, const float* y, int ld_y, int64_t R, int Dy, int Do, float* dXbig,
+                       eqnn_stream_t stream);
+/* dst[p, :] = src[perm[p], :]  (per-edge arrays into receiver-sorted order);  y += a * x */
+int eqnn_gather_rows(const float* src, const int32_t* perm, int64_t n, int width, float* dst, eqnn_stream_t stream);
+int eqnn_axpy(int64_t n, float a, const float* x, float* y, eqnn_stream_t stream);
+
 /* ---- EGNN coordinate layer (models/egnn.py, positions-only) ---------------------------------------------
  * geometry (:82-90):  rij4[p] = (r_ij, |r_ij|), r_ij = x_s - x_r + 1e-7 then minimum image (cell may be NULL);
  *                     feats[p, :] = e3nn.bessel(|r_ij|, n_rb, r_max)  ([n_edges, 1] = |r_ij| if n_rb == 0)
