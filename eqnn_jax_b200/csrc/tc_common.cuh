@@ -39,9 +39,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 
 // generic-proxy shared-memory writes -> visible to the async proxy (tensor core reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
-#ifndef EQNN_EXPERIMENT_NOFENCE
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-#endif
 }
 
 // ---- bulk asynchronous copies (TMA, non-tensor form): global -> shared, completion counted on an mbarrier ----

@@ -8,14 +8,19 @@
 // accumulating in fp32 in tensor memory.
 //
 // tc_rowgemm:  C[M x N] = epi( alpha * pro(A)[M x K] @ B[K x N] ),  M tiled by 128 rows.
-//   one persistent CTA per SM, warp-specialised:
-//     warps 5..12 (producers)  stream 128-row A chunks (32 k-columns) from HBM with 128-bit loads,
-//                              apply the activation prologue, split hi/lo, store into a ring of
-//                              128B-swizzled K-major shared-memory stages;
-//     warp  4     (MMA)        one elected thread issues 3 MMAs per 8-wide k-step, commits to mbarriers;
-//     warps 0..3  (epilogue)   tcgen05.ld the fp32 accumulator (double-buffered in TMEM),
-//                              apply alpha / activation-derivative epilogue, 128-bit stores.
+//   one persistent CTA per SM, 800 threads, warp-specialised:
+//     warps 0..7   (epilogue)  tcgen05.ld the fp32 accumulator (double-buffered in TMEM), apply alpha / bias /
+//                              activation-derivative epilogue in packed fp32x2 math, transpose through XOR-swizzled
+//                              shared memory so that every global store covers whole 128-byte lines;
+//     warp  8      (MMA)       one elected thread issues 3 MMAs per 8-wide k-step, commits to mbarriers;
+//     warps 9..24  (producers) stream 128-row A chunks (32 k-columns) from HBM with 128-bit loads three chunks
+//                              ahead (register ring) plus an L2 bulk prefetch of the next tile, apply the activation
+//                              prologue and the hi/lo split (packed fp32x2), store into a ring of 128B-swizzled
+//                              K-major shared-memory stages, one elected mbarrier arrival per warp.
 //   B (the <=128x128 weight matrix) is split once per CTA and stays resident in shared memory.
+// tc_wgrad:  dW = alpha * pro(X)^T @ G with the edge axis as K: a loader warp issues TMA bulk copies
+//   (cp.async.bulk + mbarrier complete_tx) of whole 32-edge chunks into a raw ring; transform warps split them into
+//   MN-major SWIZZLE_128B_BASE32B operands; registers are re-balanced between roles with setmaxnreg.
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <type_traits>
@@ -54,7 +59,6 @@ constexpr int RG_THREADS = (EPI_WARPS + 1 + RG_PROD_WARPS) * 32;   // 800
 #ifndef RG_L2_PREFETCH
 #define RG_L2_PREFETCH 1
 #endif
-constexpr int RG_DEPTH = 3;                                        // chunks of loads in flight per producer thread
 constexpr uint32_t STG_WARP = 32 * 128;                            // epilogue staging: 32 rows x 128 B per warp
 
 template <int K, int N, bool STAGED = true>
@@ -129,7 +133,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) tc_rowgemm_kernel(const RowGemm
 
   if (warp >= MMA_WARP + 1) {
     // =========================== producers ===========================
-    // RG_DEPTH chunks of 128-bit loads are in flight per thread (register ring): the stream is bound by
+    // three chunks of 128-bit loads are in flight per thread (register ring): the stream is bound by
     // HBM latency x bytes in flight (512 threads x 3 x 32 B = 48 KB per SM), not by the split arithmetic.
     const int pt = tid - (MMA_WARP + 1) * 32;
     const uint32_t my_tiles = (blockIdx.x < n_tiles) ? (uint32_t)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0u;
