@@ -172,3 +172,84 @@ def test_sh_norm_factors():
     for l in range(4):
         for n in ("norm", "component", "integral"):
             assert pso3.sh_norm_factor(l, n) == pytest.approx(so3.sh_normalization_factor(l, n))
+
+
+# --------------------------------------------------------------------------------------------------
+# SEGNN: parameter layout and dense lowering of TensorProductLinearGate (host logic, no GPU)
+# --------------------------------------------------------------------------------------------------
+def _leaves_(tree, pre=()):
+    for k, v in tree.items():
+        if isinstance(v, dict):
+            yield from _leaves_(v, pre + (k,))
+        else:
+            yield pre + (k,), v
+
+
+@pytest.mark.parametrize("kw,irr,lat,nadd", [
+    (dict(d_hidden=128, l_max_hidden=1, n_layers=3, message_passing_steps=3, task="graph", output_irreps="1x0e",
+          message_passing_agg="mean", n_outputs=2, residual=False), "1o", 1, 64),          # notebook cell 8: 573 253 parameters
+    (dict(d_hidden=32, message_passing_steps=2, task="node", output_irreps="1o + 1o + 1x0e"), "1o+1o+1x0e", 1, 1),
+    (dict(d_hidden=128, l_max_hidden=2, n_layers=3, message_passing_steps=3, task="node", output_irreps="1x1o"), "1o", 2, 1),
+])
+def test_segnn_plan_parameters_match_oracle(kw, irr, lat, nadd):
+    from eqnn_jax_b200.segnn import SEGNN, _Plan
+    from eqnn_jax_b200.irreps import Irreps
+    from oracle import segnn_ref as S
+    from oracle.so3 import Irreps as OI
+    plan = _Plan(SEGNN(**kw), Irreps(irr), lat, nadd)
+    tree = S.init_params(S.SEGNNConfig(**kw), irr, OI.spherical_harmonics(lat), f"{nadd}x0e")
+    want = {p: tuple(v.shape) for p, v in _leaves_(tree)}
+    got = {p: tuple(s) for p, s, _ in plan.layout}
+    assert want == got
+    if nadd == 64:
+        assert plan._n_params == 573253
+
+
+def test_segnn_dense_lowering_equals_oracle_tplg():
+    """(x (x) y) @ M_cat + b, with M_cat expanded on the host from the flat parameters, equals the oracle's
+    gate-less TensorProductLinearGate (Linear(TP(x, y)), segnn.py:48-54) -- the arithmetic the GPU path runs."""
+    import torch
+    from eqnn_jax_b200.segnn import SEGNN, _Plan
+    from eqnn_jax_b200.irreps import Irreps
+    from oracle import segnn_ref as S
+    from oracle.e3nn_ref import IrrepsArray as OIA
+    from oracle.so3 import Irreps as OI, spherical_harmonics
+    rng = np.random.default_rng(0)
+    kw = dict(d_hidden=32, l_max_hidden=2, n_layers=2, message_passing_steps=1, task="node", output_irreps="1o+1x0e")
+    irr, lat, nadd = "1o+2x0e", 2, 3
+    plan = _Plan(SEGNN(**kw), Irreps(irr), lat, nadd)
+    tree = S.init_params(S.SEGNNConfig(**kw), irr, OI.spherical_harmonics(lat), f"{nadd}x0e", seed=3)
+    theta = np.zeros((plan._n_params,))
+    for path, shape, off in plan.layout:
+        node = tree
+        for q in path:
+            node = node[q]
+        theta[off:off + node.size] = (node + (0.3 if path[-1].startswith("b[") else 0.0)).reshape(-1)
+    tab = plan._np
+    wexp = np.where(tab["exp_idx"] >= 0, tab["exp_scale"].astype(np.float64) * theta[np.maximum(tab["exp_idx"], 0)], 0.0)
+    checked = 0
+    for t, x_irreps in [(plan.embed, irr), (plan.steps[0]["edge"][0], None), (plan.steps[0]["node"], None),
+                        (plan.decode[0], None), (plan.decode[-1], None)]:
+        R = 5
+        x = rng.normal(size=(R, t.Dx))
+        y = spherical_harmonics(lat, rng.normal(size=(R, 3)), True, "integral") if t.has_y else np.ones((R, 1))
+        M = wexp[t.M_off:t.M_off + t.Dx * t.Dy * t.Do].reshape(t.Dx, t.Dy, t.Do)
+        z = np.einsum("ri,rj,ijo->ro", x, y, M)
+        if t.n_bias:
+            z[:, t.b_col:t.b_col + t.n_bias] += theta[t.b_off:t.b_off + t.n_bias]
+        # oracle: same parameters, x in its stored irreps layout
+        p = {k: torch.tensor(v + (0.3 if k.startswith("b[") else 0.0)) for k, v in tree[t.name]["Linear_0"].items()}
+        xi = OI(x_irreps) if x_irreps is not None else None
+        if xi is None:                                   # recover the stored input irreps from the plan
+            xi = {plan.steps[0]["edge"][0]: OI(f"{nadd}x0e") + OI(str(plan.embed.out_irreps)) + OI(str(plan.embed.out_irreps)),
+                  plan.steps[0]["node"]: OI(str(plan.embed.out_irreps)) + OI(str(plan.steps[0]["edge"][-1].out_irreps)),
+                  plan.decode[0]: OI(str(plan.h_irreps)), plan.decode[-1]: OI(str(plan.decode[-2].out_irreps))}[t]
+        yo = OIA(OI.spherical_harmonics(lat), torch.tensor(y)) if t.has_y else None
+        lin_out = S.tplg_linear_irreps(str(t.out_irreps) if not t.activation else str(plan.hidden), t.activation)
+        from oracle import e3nn_ref as E
+        yy = yo if yo is not None else OIA(S.ONE, torch.ones(R, 1, dtype=torch.float64))
+        want = E.linear_apply(p, E.tensor_product(OIA(xi, torch.tensor(x)), yy), lin_out, gradient_normalization=0.0).array
+        # the expand table stores the CG coefficients in fp32
+        np.testing.assert_allclose(z, want.numpy(), atol=1e-6 * max(1.0, np.abs(want.numpy()).max()))
+        checked += 1
+    assert checked == 5
