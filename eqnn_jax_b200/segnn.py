@@ -19,7 +19,8 @@ backward passes gather sender / receiver ends through the two CSRs (no atomics).
 the node function never reach the output (:84-89): they own parameters (exact zero gradients) and are not
 computed.  First correct path: fp32 CUDA-core GEMMs on the dense lowering (about 7x the FLOPs of the irrep-blocked
 form); the tensor-core version is next round's work.
-Not built: graph globals, max aggregation, activations other than gelu -> NotImplementedError, never a fallback.
+Graph globals (concatenated to the pooled scalars, LayerNorm, :282-286) are supported.
+Not built: max aggregation, activations other than gelu -> NotImplementedError, never a fallback.
 """
 from __future__ import annotations
 
@@ -132,7 +133,8 @@ class _TPLG:
 
 
 class _Plan:
-    def __init__(self, cfg: "SEGNN", irreps_in: Irreps, lmax_attr: int, n_add: int):
+    def __init__(self, cfg: "SEGNN", irreps_in: Irreps, lmax_attr: int, n_add: int, n_globals: int = 0):
+        self.n_globals = int(n_globals)
         self.layout: List[Tuple[Tuple[str, ...], Tuple[int, ...], int]] = []
         self._n_params = 0
         self._n_exp = 0
@@ -191,8 +193,13 @@ class _Plan:
             d = cfg.d_hidden
             self.pre = tplg(h_irreps, lmax_attr, Irreps([(d, 0, 1)]), False)
             self.dense = (self.add_param(("Dense_0", "kernel"), (d, d)), self.add_param(("Dense_0", "bias"), (d,)))
-            ws = [cfg.mlp_readout_widths[0] * d] + [w * d for w in cfg.mlp_readout_widths[1:]] + [cfg.n_outputs]
-            self.ro_mlp, fan = [], d
+            n_pool = d + self.n_globals                                              # globals + LayerNorm, :282-286
+            self.ln = None
+            if self.n_globals > 0:
+                self.ln = (self.add_param(("LayerNorm_0", "scale"), (n_pool,)),
+                           self.add_param(("LayerNorm_0", "bias"), (n_pool,)))
+            ws = [cfg.mlp_readout_widths[0] * n_pool] + [w * d for w in cfg.mlp_readout_widths[1:]] + [cfg.n_outputs]
+            self.ro_mlp, fan = [], n_pool
             for l, w in enumerate(ws):
                 self.ro_mlp.append((self.add_param(("MLP_0", f"Dense_{l}", "kernel"), (fan, w)),
                                     self.add_param(("MLP_0", f"Dense_{l}", "bias"), (w,)), fan, w))
@@ -269,25 +276,23 @@ class SEGNN:
         self._plans: Dict = {}
 
     # ---- plan / parameters ----------------------------------------------------------------------
-    @staticmethod
-    def _unpack(g: SteerableGraphsTuple):
+    def _unpack(self, g: SteerableGraphsTuple):
         for f in ("nodes", "steerable_node_attrs", "steerable_edge_attrs", "additional_messages"):
             if not isinstance(getattr(g, f), IrrepsArray):
                 raise TypeError(f"SEGNN expects st_graphs.{f} to be an IrrepsArray (reference: e3nn.IrrepsArray)")
-        if g.globals is not None:
-            raise NotImplementedError("graph globals are not on the B200 SEGNN path yet")
         nodes = g.nodes.array
         if not nodes.is_cuda:
             raise RuntimeError("SEGNN: expected CUDA tensors (this path has no CPU implementation)")
         lmax_attr = int(round(math.sqrt(g.steerable_edge_attrs.array.shape[-1]))) - 1
         if Irreps(g.steerable_edge_attrs.irreps) != Irreps.spherical_harmonics(lmax_attr):
             raise NotImplementedError("steerable attributes must be spherical harmonics 0..lmax (get_equivariant_graph)")
-        return Irreps(g.nodes.irreps), lmax_attr, int(g.additional_messages.array.shape[-1])
+        n_glob = 0 if (g.globals is None or self.task != "graph") else int(g.globals.shape[-1])
+        return Irreps(g.nodes.irreps), lmax_attr, int(g.additional_messages.array.shape[-1]), n_glob
 
-    def plan(self, irreps_in, lmax_attr: int, n_add: int) -> _Plan:
-        key = (Irreps(irreps_in), lmax_attr, n_add)
+    def plan(self, irreps_in, lmax_attr: int, n_add: int, n_globals: int = 0) -> _Plan:
+        key = (Irreps(irreps_in), lmax_attr, n_add, n_globals)
         if key not in self._plans:
-            self._plans[key] = _Plan(self, Irreps(irreps_in), lmax_attr, n_add)
+            self._plans[key] = _Plan(self, Irreps(irreps_in), lmax_attr, n_add, n_globals)
         return self._plans[key]
 
     def init(self, rng: Union[int, np.random.Generator], st_graphs: SteerableGraphsTuple) -> FlatParams:
@@ -301,6 +306,9 @@ class SEGNN:
             stds.update(t.init_std)
         for path, shape, off in plan.layout:
             n = int(np.prod(shape))
+            if path[0] == "LayerNorm_0":
+                host[off:off + n] = 1.0 if path[-1] == "scale" else 0.0
+                continue
             if path[-1] == "bias" or path[-1].startswith("b["):
                 continue
             if path[0].startswith("TensorProductLinearGate"):
@@ -315,7 +323,7 @@ class SEGNN:
 
     # ---- forward / backward ------------------------------------------------------------------------
     def _prepare(self, g: SteerableGraphsTuple):
-        irreps_in, lmax_attr, n_add = self._unpack(g)
+        irreps_in, lmax_attr, n_add, n_glob = self._unpack(g)
         nodes = g.nodes.array
         if nodes.dim() == 2:
             raise ValueError("SEGNN on B200 expects a leading batch axis (B, N, D)")
@@ -330,8 +338,13 @@ class SEGNN:
         y_node = f32c(g.steerable_node_attrs.array, ny)
         y_edge = ops.gather_rows(f32c(g.steerable_edge_attrs.array, ny), perm, ny)       # receiver-sorted order
         add = ops.gather_rows(f32c(g.additional_messages.array, n_add), perm, n_add)
-        plan = self.plan(irreps_in, lmax_attr, n_add)
-        return plan, f32c(nodes, D), B, N, E, (rowptr, perm, src, rowptr_s, perm_s), y_node, y_edge, add
+        plan = self.plan(irreps_in, lmax_attr, n_add, n_glob)
+        glob = None
+        if n_glob:
+            if not isinstance(g.globals, torch.Tensor) or not g.globals.is_cuda:
+                raise RuntimeError("st_graphs.globals must be a CUDA tensor (this path has no CPU implementation)")
+            glob = g.globals.reshape(B, n_glob).to(torch.float32).contiguous()
+        return plan, f32c(nodes, D), B, N, E, (rowptr, perm, src, rowptr_s, perm_s), y_node, y_edge, add, glob
 
     def forward_backward(self, params: FlatParams, st_graphs: SteerableGraphsTuple, grad_fn=None):
         """Forward (and, if ``grad_fn(out) -> dL/dout`` is given, backward into ``params.grad``).  Returns the raw
@@ -398,7 +411,7 @@ class SEGNN:
         return dx
 
     # -- whole model ------------------------------------------------------------------------------------
-    def _forward(self, theta, plan, nodes, B, N, E, csr, y_node, y_edge, add):
+    def _forward(self, theta, plan, nodes, B, N, E, csr, y_node, y_edge, add, glob=None):
         rowptr, perm, src, rowptr_s, perm_s = csr
         dev = theta.device
         f32 = dict(dtype=torch.float32, device=dev)
@@ -442,16 +455,22 @@ class SEGNN:
         _mm(Nt, d, d, 1.0, pre, 0, d, theta, plan.dense[0], d, pre2, 0, d, epi=1, aux=theta, aux_off=plan.dense[1])
         pooled = torch.empty((B, d), **f32)
         ops.pool_fwd(pre2, B, N, d, 1 if self.readout_agg == "mean" else 0, pooled)
-        zs, a, pro = [], pooled, 0
+        a, ln_stats = pooled, None
+        if plan.ln is not None:
+            a = torch.empty((B, d + plan.n_globals), **f32)
+            ln_stats = torch.empty((B, 2), **f32)
+            ops.layernorm_fwd(pooled, glob, theta, plan.ln[0], plan.ln[1], 1e-6, a, ln_stats)
+        ro_in = a
+        zs, pro = [], 0
         for (ko, bo, fan, w) in plan.ro_mlp:
             zl = torch.empty((B, w), **f32)
             _mm(B, w, fan, 1.0, a, 0, fan, theta, ko, w, zl, 0, w, pro=pro, pro_scale=1.0, epi=1, aux=theta, aux_off=bo)
             zs.append(zl)
             a, pro = zl, 1
-        saved.update(pre_out=pre, pooled=pooled, ro_z=zs)
+        saved.update(pre_out=pre, pooled=pooled, ro_z=zs, ro_in=ro_in, ln_stats=ln_stats)
         return zs[-1], saved
 
-    def _backward(self, theta, gtheta, saved, gout, plan, nodes, B, N, E, csr, y_node, y_edge, add):
+    def _backward(self, theta, gtheta, saved, gout, plan, nodes, B, N, E, csr, y_node, y_edge, add, glob=None):
         rowptr, perm, src, rowptr_s, perm_s = csr
         dev = theta.device
         f32 = dict(dtype=torch.float32, device=dev)
@@ -473,7 +492,7 @@ class SEGNN:
             dz = gout.reshape(B, -1).contiguous()
             for l in range(len(plan.ro_mlp) - 1, -1, -1):
                 ko, bo, fan, w = plan.ro_mlp[l]
-                a_prev = zs[l - 1] if l > 0 else saved["pooled"]
+                a_prev = zs[l - 1] if l > 0 else saved["ro_in"]
                 _mm(fan, w, B, 1.0, a_prev, 0, fan, dz, 0, w, gtheta, ko, w, ta=True, pro=1 if l > 0 else 0, pro_scale=1.0)
                 ops.colsum(dz, B, w, gtheta, y_off=bo)
                 dprev = torch.empty((B, fan), **f32)
@@ -483,6 +502,11 @@ class SEGNN:
                 else:
                     _mm(B, fan, w, 1.0, dz, 0, w, theta, ko, w, dprev, 0, fan, tb=True)
                 dz = dprev
+            if plan.ln is not None:
+                d_pool = torch.empty((B, d), **f32)
+                ops.layernorm_bwd(saved["pooled"], glob, theta, plan.ln[0], saved["ln_stats"], dz, d_pool, gtheta,
+                                  plan.ln[0], plan.ln[1])
+                dz = d_pool
             dpre2 = torch.empty((Nt, d), **f32)
             ops.pool_bwd(dz, B, N, d, 1 if self.readout_agg == "mean" else 0, dpre2)
             _mm(d, d, Nt, 1.0, saved["pre_out"], 0, d, dpre2, 0, d, gtheta, plan.dense[0], d, ta=True)     # Dense_0

@@ -30,7 +30,7 @@ def _close(got, want, what, rtol=RTOL, scale=None):
     assert err <= rtol * max(scale, 1e-30), f"{what}: max err {err:.3e} vs scale {scale:.3e} (rel {err / max(scale, 1e-30):.2e})"
 
 
-def _run(kw, irreps, x, k, lmax_attr, n_rb, pbc, vel):
+def _run(kw, irreps, x, k, lmax_attr, n_rb, pbc, vel, n_glob=0):
     from eqnn_jax_b200 import graph_utils as GU
     from eqnn_jax_b200.equivariant_graph_utils import get_equivariant_graph
     from eqnn_jax_b200.irreps import Irreps
@@ -42,12 +42,13 @@ def _run(kw, irreps, x, k, lmax_attr, n_rb, pbc, vel):
     gpbc = GU.get_apply_pbc(cell=cell) if pbc else None
     g = G.build_graph(x, None, k, apply_pbc=opbc)
     v = x[..., 3:6] if vel else None
+    glob = np.random.default_rng(11).normal(size=(B, n_glob)).astype(np.float32) if n_glob else None
     ost = G.get_equivariant_graph(OIA(irreps, torch.tensor(x, dtype=torch.float64)), x[..., :3], v, g.senders, g.receivers,
-                                  g.n_node, g.n_edge, None, None, lmax_attr, steerable_velocities=vel, apply_pbc=opbc,
+                                  g.n_node, g.n_edge, None, glob, lmax_attr, steerable_velocities=vel, apply_pbc=opbc,
                                   n_radial_basis=n_rb, r_max=1.5)
     cfg = S.SEGNNConfig(**kw)
     n_add = max(n_rb, 1)
-    tree = S.init_params(cfg, irreps, OI.spherical_harmonics(lmax_attr), f"{n_add}x0e", seed=1)
+    tree = S.init_params(cfg, irreps, OI.spherical_harmonics(lmax_attr), f"{n_add}x0e", seed=1, n_globals=n_glob)
     for _, w in _leaves(tree):                                         # non-zero biases: exercise their gradient path
         pass
     rng = np.random.default_rng(7)
@@ -63,7 +64,8 @@ def _run(kw, irreps, x, k, lmax_attr, n_rb, pbc, vel):
     xt = torch.tensor(x).cuda()
     gst = get_equivariant_graph(IrrepsArray(Irreps(irreps), xt), xt[..., :3].contiguous(),
                                 xt[..., 3:6].contiguous() if vel else None, torch.tensor(g.senders).cuda(),
-                                torch.tensor(g.receivers).cuda(), g.n_node, g.n_edge, None, None, lmax_attr,
+                                torch.tensor(g.receivers).cuda(), g.n_node, g.n_edge, None,
+                                None if glob is None else torch.tensor(glob).cuda(), lmax_attr,
                                 steerable_velocities=vel, apply_pbc=gpbc, n_radial_basis=n_rb, r_max=1.5)
     model = SEGNN(**kw)
     params = model.init(0, gst)
@@ -73,25 +75,28 @@ def _run(kw, irreps, x, k, lmax_attr, n_rb, pbc, vel):
     return got.cpu().numpy(), val.detach().numpy(), params, p
 
 
-@pytest.mark.parametrize("kw,irreps,F,lmax_attr,n_rb,pbc,vel", [
+@pytest.mark.parametrize("kw,irreps,F,lmax_attr,n_rb,pbc,vel,n_glob", [
     # tests/test_equivariance.py:288-310 (node) and :313-335 (graph): 7 features "1o+1o+1x0e", attributes l <= 1
     (dict(message_passing_steps=2, d_hidden=32, task="node", residual=True, output_irreps="1o + 1o + 1x0e"),
-     "1o+1o+1x0e", 7, 1, 0, False, True),
+     "1o+1o+1x0e", 7, 1, 0, False, True, 0),
     (dict(message_passing_steps=3, d_hidden=32, task="graph", residual=True, output_irreps="1x0e", n_outputs=2),
-     "1o+1o+1x0e", 7, 1, 0, False, True),
+     "1o+1o+1x0e", 7, 1, 0, False, True, 0),
     # cfg-3 shape (train_velocities.py:364-378,454-458): positions only, l_max_hidden 2, sum, node task -> 1x1o, PBC
     (dict(d_hidden=64, n_layers=3, message_passing_steps=2, message_passing_agg="sum", task="node", output_irreps="1x1o",
-          l_max_hidden=2, residual=True), "1o", 3, 1, 0, True, False),
+          l_max_hidden=2, residual=True), "1o", 3, 1, 0, True, False, 0),
     # train_cosmology.py:185 style: attributes l <= 2, Bessel messages, mean aggregation, graph read-out, no residual
     (dict(d_hidden=64, n_layers=2, message_passing_steps=2, message_passing_agg="mean", task="graph", output_irreps="1x0e",
-          l_max_hidden=2, n_outputs=2, residual=False), "1o", 3, 2, 8, True, False),
+          l_max_hidden=2, n_outputs=2, residual=False), "1o", 3, 2, 8, True, False, 0),
+    # graph globals (TPCF vector) -> concat + LayerNorm before the read-out MLP (segnn.py:282-286)
+    (dict(d_hidden=32, n_layers=2, message_passing_steps=1, message_passing_agg="mean", task="graph", output_irreps="1x0e",
+          n_outputs=2), "1o", 3, 1, 0, False, False, 12),
 ])
-def test_segnn_forward_and_gradients(kw, irreps, F, lmax_attr, n_rb, pbc, vel):
+def test_segnn_forward_and_gradients(kw, irreps, F, lmax_attr, n_rb, pbc, vel, n_glob):
     rng = np.random.default_rng(len(irreps) + lmax_attr)
     B, N, k = 2, 60, 6
     x = rng.normal(size=(B, N, F)).astype(np.float32)
     x[..., :3] = rng.uniform(0.0, 3.4, size=(B, N, 3))
-    got, want, params, p = _run(kw, irreps, x, k, lmax_attr, n_rb, pbc, vel)
+    got, want, params, p = _run(kw, irreps, x, k, lmax_attr, n_rb, pbc, vel, n_glob)
     _close(got, want, "output")
     gt = params.grad_tree
     scales = {}
