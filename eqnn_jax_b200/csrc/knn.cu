@@ -170,6 +170,217 @@ knn_kernel(const float* __restrict__ x, int ldx, int N, int k, Cell cell, int32_
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Cell-list search (periodic, diagonal cell): same distances, same order, far fewer pairs.
+//
+// Points are binned into G^3 cells of the periodic box and stored cell by cell.  A warp owns one query and
+// sweeps the (2R+1)^3 cells around it.  The result is accepted only if the k-th distance lies strictly inside
+// the searched region -- sqrt(D_k) < R*h - margin, h = cell width, margin covers fp32 binning and the +1e-7 of
+// the distance expression -- because then every point at distance <= D_k was a candidate; otherwise R grows
+// (up to the whole box = brute force).  Distances come from the same pair_dist as the dense sweep and the list
+// is ordered lexicographically by (distance, index), which is exactly the stable argsort of the reference, so the
+// output is bit-identical to the dense path whatever the visiting order.
+// ------------------------------------------------------------------------------------------------
+struct Grid {
+  int G;            // cells per axis
+  float h[3];       // cell width per axis (box length / G)
+  float margin[3];  // safety margin per axis
+};
+
+__device__ __forceinline__ int cell_coord(float x, float ci, int G) {
+  float u = x * ci;
+  u -= floorf(u);                       // [0, 1]
+  int c = (int)(u * (float)G);
+  return c >= G ? G - 1 : (c < 0 ? 0 : c);
+}
+
+__global__ void knn_bin_kernel(const float* __restrict__ x, int ldx, int N, Cell cl, Grid g, int32_t* __restrict__ cell_of,
+                               int32_t* __restrict__ count) {
+  const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const float* p = x + ((size_t)b * N + i) * ldx;
+  const int cx = cell_coord(p[0], cl.ci[0], g.G), cy = cell_coord(p[1], cl.ci[4], g.G), cz = cell_coord(p[2], cl.ci[8], g.G);
+  const int c = (cz * g.G + cy) * g.G + cx;
+  cell_of[(size_t)b * N + i] = c;
+  atomicAdd(count + (size_t)b * (g.G * g.G * g.G + 1) + c, 1);
+}
+
+// exclusive scan of the per-cell counts of one cloud (G^3 <= 4096 cells): one CTA per cloud
+__global__ void __launch_bounds__(1024) knn_scan_kernel(int32_t* __restrict__ count, int n_cells) {
+  __shared__ int sm[1024];
+  int32_t* c = count + (size_t)blockIdx.x * (n_cells + 1);
+  const int per = (n_cells + 1023) / 1024;
+  const int t = threadIdx.x, lo = t * per, hi = min(lo + per, n_cells);
+  int s = 0;
+  for (int i = lo; i < hi; ++i) s += c[i];
+  sm[t] = s;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    const int v = (t >= o) ? sm[t - o] : 0;
+    __syncthreads();
+    sm[t] += v;
+    __syncthreads();
+  }
+  int run = sm[t] - s;
+  for (int i = lo; i < hi; ++i) {
+    const int v = c[i];
+    c[i] = run;
+    run += v;
+  }
+  if (t == 1023) c[n_cells] = sm[1023];
+}
+
+// sorted[b][slot] = (x, y, z, original index); slot order inside a cell is arbitrary (the search does not depend on it)
+__global__ void knn_scatter_kernel(const float* __restrict__ x, int ldx, int N, int n_cells, const int32_t* __restrict__ cell_of,
+                                   const int32_t* __restrict__ start, int32_t* __restrict__ cursor,
+                                   float4* __restrict__ sorted) {
+  const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const int c = cell_of[(size_t)b * N + i];
+  const int slot = start[(size_t)b * (n_cells + 1) + c] + atomicAdd(cursor + (size_t)b * n_cells + c, 1);
+  const float* p = x + ((size_t)b * N + i) * ldx;
+  sorted[(size_t)b * N + slot] = make_float4(p[0], p[1], p[2], __int_as_float(i));
+}
+
+__device__ __forceinline__ bool lex_lt(float d, int j, float d2, int j2) { return d < d2 || (d == d2 && j < j2); }
+
+template <int R, bool FMA>
+__global__ void __launch_bounds__(WARPS * 32)
+knn_cell_kernel(const float4* __restrict__ sorted, const int32_t* __restrict__ start, int N, int k, Cell cell, Grid g,
+                int32_t* __restrict__ senders, int32_t* __restrict__ receivers, float* __restrict__ dr) {
+  const unsigned FULL = 0xffffffffu;
+  const float INF = __int_as_float(0x7f800000);
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int slot = blockIdx.x * WARPS + warp;
+  if (slot >= N) return;
+  const int G = g.G, n_cells = G * G * G;
+  const float4* pts = sorted + (size_t)b * N;
+  const int32_t* cs = start + (size_t)b * (n_cells + 1);
+  const float4 q = pts[slot];
+  const int qi = __float_as_int(q.w);
+  const int cx = cell_coord(q.x, cell.ci[0], G), cy = cell_coord(q.y, cell.ci[4], G), cz = cell_coord(q.z, cell.ci[8], G);
+  const int kr = (k - 1) >> 5, kl = (k - 1) & 31;
+  float ed[R];
+  int ej[R];
+  for (int Rr = 1;; ++Rr) {
+    float thr = INF;
+    int thrj = 0x7fffffff;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      ed[r] = INF;
+      ej[r] = 0x7fffffff;
+    }
+    const int span = min(2 * Rr + 1, G);                   // cells visited per axis (never the same cell twice)
+    const int z0 = (span == G) ? 0 : cz - Rr, y0 = (span == G) ? 0 : cy - Rr, x0 = (span == G) ? 0 : cx - Rr;
+    for (int dz = 0; dz < span; ++dz) {
+      const int zz = ((z0 + dz) % G + G) % G;
+      for (int dy = 0; dy < span; ++dy) {
+        const int yy = ((y0 + dy) % G + G) % G;
+        const int rowc = (zz * G + yy) * G;
+        // the x-run [x0, x0 + span) modulo G is one or two contiguous slot ranges
+        int xa = ((x0 % G) + G) % G, len = span;
+        while (len > 0) {
+          const int run = min(len, G - xa);
+          const int p0 = cs[rowc + xa], p1 = cs[rowc + xa + run];
+          for (int tb = p0; tb < p1; tb += 32) {
+            const int t = tb + lane;
+            const bool tv = t < p1;
+            const float4 c = pts[tv ? t : p0];
+            const int jc = __float_as_int(c.w);
+            const float D = pair_dist<true, true, FMA>(q.x, q.y, q.z, c.x, c.y, c.z, cell);
+            unsigned m = __ballot_sync(FULL, tv && lex_lt(D, jc, thr, thrj));
+            while (m) {
+              const int srcl = __ffs(m) - 1;
+              m &= m - 1;
+              const float Dn = __shfl_sync(FULL, D, srcl);
+              const int jn = __shfl_sync(FULL, jc, srcl);
+              if (!lex_lt(Dn, jn, thr, thrj)) continue;    // threshold moved since the ballot (warp-uniform)
+#pragma unroll
+              for (int r = R - 1; r >= 0; --r) {
+                float ld = __shfl_up_sync(FULL, ed[r], 1);
+                int lj = __shfl_up_sync(FULL, ej[r], 1);
+                if (r > 0) {
+                  const float wd = __shfl_sync(FULL, ed[r - 1], 31);
+                  const int wj = __shfl_sync(FULL, ej[r - 1], 31);
+                  if (lane == 0) { ld = wd; lj = wj; }
+                } else if (lane == 0) {
+                  ld = -INF;
+                  lj = -1;
+                }
+                if (r * 32 + lane < k) {
+                  if (lex_lt(Dn, jn, ld, lj)) { ed[r] = ld; ej[r] = lj; }
+                  else if (lex_lt(Dn, jn, ed[r], ej[r])) { ed[r] = Dn; ej[r] = jn; }
+                }
+              }
+              float tq = ed[0];
+              int tj = ej[0];
+              if (R > 1 && kr == 1) { tq = ed[R - 1]; tj = ej[R - 1]; }
+              thr = __shfl_sync(FULL, tq, kl);
+              thrj = __shfl_sync(FULL, tj, kl);
+            }
+          }
+          len -= run;
+          xa = 0;
+        }
+      }
+    }
+    if (span == G) break;                                  // the whole box was searched
+    // accept iff sqrt(D_k) < min over axes of (R h - margin)
+    float reach = INF;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) reach = fminf(reach, (float)Rr * g.h[c] - g.margin[c]);
+    if (thr < INF && reach > 0.f && thr < reach * reach) break;
+  }
+  const size_t ebase = ((size_t)b * N + qi) * k;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int e = r * 32 + lane;
+    if (e < k) {
+      const int j = ej[r];
+      senders[ebase + e] = qi;
+      receivers[ebase + e] = j;
+    }
+  }
+  (void)dr;   // displacements are written by knn_dr_kernel from the caller's coordinate array
+}
+
+// dr[e] = wrapped displacement of the selected pair, same expression as the dense path
+template <bool PBC, bool DIAG>
+__global__ void knn_dr_kernel(const float* __restrict__ x, int ldx, int N, int k, Cell cell,
+                              const int32_t* __restrict__ receivers, float* __restrict__ dr) {
+  const int b = blockIdx.y;
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (int64_t)N * k) return;
+  const int qi = (int)(e / k);
+  const float* xb = x + (size_t)b * N * ldx;
+  const int j = receivers[(size_t)b * N * k + e];
+  float o[3] = {0.f, 0.f, 0.f};
+  if (j >= 0 && j < N) {
+    const float* q = xb + (size_t)qi * ldx;
+    const float* p = xb + (size_t)j * ldx;
+    pair_dist<PBC, DIAG, false>(q[0], q[1], q[2], p[0], p[1], p[2], cell, o);
+  }
+  float* out = dr + ((size_t)b * N * k + e) * 3;
+  out[0] = o[0]; out[1] = o[1]; out[2] = o[2];
+}
+
+// cells per axis for a uniform-density estimate of the k-th neighbour distance r_k = L (3k / (4 pi N))^(1/3):
+// cell width >= 1.3 r_k so that R = 1 is accepted for almost every query.  0 = use the dense sweep.
+int grid_cells(int N, int k) {
+  if (N < 2048) return 0;
+  const double rk = cbrt(3.0 * k / (4.0 * 3.14159265358979323846 * N));
+  int G = (int)floor(1.0 / (1.3 * rk));
+  if (G > 16) G = 16;
+  return G >= 4 ? G : 0;
+}
+
+size_t cell_ws_bytes(int B, int N, int G) {
+  const size_t n_cells = (size_t)G * G * G;
+  return (size_t)B * N * 16 + (size_t)B * N * 4 + (size_t)B * (n_cells + 1) * 4 + (size_t)B * n_cells * 4 + 256;
+}
+
 template <int R>
 int launch_knn(const float* x, int ldx, int N, int k, const Cell& cell, bool pbc, bool diag, bool fma, int B,
                int32_t* s, int32_t* r, float* dr, cudaStream_t st) {
@@ -189,10 +400,13 @@ int launch_knn(const float* x, int ldx, int N, int k, const Cell& cell, bool pbc
 
 }  // namespace
 
-extern "C" size_t eqnn_knn_workspace_bytes(int, int, int) { return 0; }
+extern "C" size_t eqnn_knn_workspace_bytes(int B, int N, int k) {
+  const int G = grid_cells(N, k);
+  return G ? cell_ws_bytes(B, N, G) : 0;
+}
 
 extern "C" int eqnn_knn_pbc(const float* x, int ld_x, const float* cell, const float* cell_inv, int B, int N,
-                            int k, int flags, int32_t* senders, int32_t* receivers, float* dr, void*, size_t,
+                            int k, int flags, int32_t* senders, int32_t* receivers, float* dr, void* ws, size_t ws_bytes,
                             eqnn_stream_t stream) {
   EQNN_CHECK_ARG(x && senders && receivers, "knn: null pointer");
   EQNN_CHECK_ARG(B >= 0 && N >= 0 && ld_x >= 3, "knn: bad shape");
@@ -217,6 +431,44 @@ extern "C" int eqnn_knn_pbc(const float* x, int ld_x, const float* cell, const f
   }
   const bool fma = (flags & EQNN_KNN_FMA) != 0;
   cudaStream_t st = as_stream(stream);
+  // cell-list search: periodic diagonal cells, large clouds, and a caller-provided workspace; bit-identical output
+  const int G = (pbc && diag && !(flags & EQNN_KNN_DENSE)) ? grid_cells(N, k) : 0;
+  if (G && ws && ws_bytes >= cell_ws_bytes(B, N, G)) {
+    const int n_cells = G * G * G;
+    Grid g;
+    g.G = G;
+    for (int a = 0; a < 3; ++a) {
+      const float L = fabsf(c.c[4 * a]);
+      g.h[a] = L / (float)G;
+      g.margin[a] = 1e-4f * L + 4e-7f;
+    }
+    uint8_t* w = reinterpret_cast<uint8_t*>(ws);
+    float4* sorted = reinterpret_cast<float4*>(w);
+    int32_t* cell_of = reinterpret_cast<int32_t*>(w + (size_t)B * N * 16);
+    int32_t* start = cell_of + (size_t)B * N;
+    int32_t* cursor = start + (size_t)B * (n_cells + 1);
+    EQNN_CUDA(cudaMemsetAsync(start, 0, ((size_t)B * (n_cells + 1) + (size_t)B * n_cells) * 4, st));
+    dim3 gp((N + 255) / 256, B);
+    knn_bin_kernel<<<gp, 256, 0, st>>>(x, ld_x, N, c, g, cell_of, start);
+    knn_scan_kernel<<<B, 1024, 0, st>>>(start, n_cells);
+    knn_scatter_kernel<<<gp, 256, 0, st>>>(x, ld_x, N, n_cells, cell_of, start, cursor, sorted);
+    dim3 gq((N + WARPS - 1) / WARPS, B);
+    if (k <= 32) {
+      if (fma) knn_cell_kernel<1, true><<<gq, WARPS * 32, 0, st>>>(sorted, start, N, k, c, g, senders, receivers, dr);
+      else knn_cell_kernel<1, false><<<gq, WARPS * 32, 0, st>>>(sorted, start, N, k, c, g, senders, receivers, dr);
+    } else {
+      if (fma) knn_cell_kernel<2, true><<<gq, WARPS * 32, 0, st>>>(sorted, start, N, k, c, g, senders, receivers, dr);
+      else knn_cell_kernel<2, false><<<gq, WARPS * 32, 0, st>>>(sorted, start, N, k, c, g, senders, receivers, dr);
+    }
+    int n_launch = 4;
+    if (dr) {
+      dim3 gd((unsigned)(((int64_t)N * k + 255) / 256), B);
+      knn_dr_kernel<true, true><<<gd, 256, 0, st>>>(x, ld_x, N, k, c, receivers, dr);
+      ++n_launch;
+    }
+    EQNN_CHECK_LAUNCH_N(n_launch);
+    return EQNN_OK;
+  }
   if (k <= 32) return launch_knn<1>(x, ld_x, N, k, c, pbc, diag, fma, B, senders, receivers, dr, st);
   return launch_knn<2>(x, ld_x, N, k, c, pbc, diag, fma, B, senders, receivers, dr, st);
 }

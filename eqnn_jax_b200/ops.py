@@ -82,20 +82,32 @@ def tp_dims(tp_id: int) -> Tuple[int, int, int, int]:
 
 
 # ---------------------------------------------------------------- graph build
-def knn_pbc(x: torch.Tensor, k: int, cell=None, cell_inv=None, fma: bool = False, want_dr: bool = True):
-    """x [B, N, F>=3] -> senders [B,E], receivers [B,E] (int32), dr [B,E,3]."""
+_KNN_WS = None
+
+
+def knn_pbc(x: torch.Tensor, k: int, cell=None, cell_inv=None, fma: bool = False, want_dr: bool = True,
+            dense: bool = False):
+    """x [B, N, F>=3] -> senders [B,E], receivers [B,E] (int32), dr [B,E,3].
+    ``dense=True`` forces the N x N sweep; otherwise large periodic clouds use the cell list (same output)."""
+    global _KNN_WS
     _req(x, _F32, "x")
     B, N, F = x.shape
     E = N * k
     senders = torch.empty((B, E), dtype=_I32, device=x.device)
     receivers = torch.empty((B, E), dtype=_I32, device=x.device)
     dr = torch.empty((B, E, 3), dtype=_F32, device=x.device) if want_dr else None
-    flags = (1 if cell is not None else 0) | (2 if fma else 0)
+    flags = (1 if cell is not None else 0) | (2 if fma else 0) | (4 if dense else 0)
     c9 = (C.c_float * 9)(*[float(v) for v in cell.reshape(-1)]) if cell is not None else None
     ci9 = (C.c_float * 9)(*[float(v) for v in cell_inv.reshape(-1)]) if cell is not None else None
+    need = 0 if (dense or cell is None) else int(lib().eqnn_knn_workspace_bytes(B, N, k))
+    ws = None
+    if need:
+        if _KNN_WS is None:
+            _KNN_WS = GemmWorkspace()
+        ws, need = _KNN_WS.get(need, x.device)
     t0 = TIMER.begin() if TIMER else None
     check(lib().eqnn_knn_pbc(_ptr(x), F, c9, ci9, B, N, k, flags, _ptr(senders), _ptr(receivers), _ptr(dr),
-                             None, 0, _stream()), "knn_pbc")
+                             ws, need, _stream()), "knn_pbc")
     if TIMER:
         TIMER.end("knn_pbc", t0)
     return senders, receivers, dr

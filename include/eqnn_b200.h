@@ -63,8 +63,13 @@ int eqnn_tp_dims(int id, int* dxp, int* ny, int* n_live, int* d_live);
  *   receivers  [B, N*k] int32  = neighbour indices, local ids  (graph_utils.py:71)
  *   dr         [B, N*k, 3] fp32 = wrapped displacement of each selected pair (:72); may be NULL
  * flags: EQNN_KNN_PBC; EQNN_KNN_FMA contracts D_ij as fma(d2,d2,fma(d1,d1,d0*d0))
- *        (what an FMA-fusing CPU backend would produce; off by default).            */
-enum { EQNN_KNN_PBC = 1, EQNN_KNN_FMA = 2 };
+ *        (what an FMA-fusing CPU backend would produce; off by default);
+ *        EQNN_KNN_DENSE forces the dense N x N sweep.
+ * ws / ws_bytes: optional workspace of eqnn_knn_workspace_bytes(B, N, k) bytes.  With it, periodic diagonal cells
+ * and N >= 2048, the search runs on a cell list (points binned into G^3 cells, (2R+1)^3 cells swept per query, R
+ * grown until the k-th distance lies inside the searched region): same distance expression, list ordered by
+ * (distance, index) -- output bit-identical to the dense sweep.  Without it (NULL / too small) the dense sweep runs. */
+enum { EQNN_KNN_PBC = 1, EQNN_KNN_FMA = 2, EQNN_KNN_DENSE = 4 };
 size_t eqnn_knn_workspace_bytes(int B, int N, int k);
 int eqnn_knn_pbc(const float* x, int ld_x, const float* cell, const float* cell_inv, int B, int N, int k,
                  int flags, int32_t* senders, int32_t* receivers, float* dr, void* ws, size_t ws_bytes,

@@ -152,3 +152,32 @@ def test_edge_geometry_matches_reference_rounding():
     np.testing.assert_allclose(gm[:, :3], u, atol=1e-7)
     want = G.bessel_np(d, 16, 0.6)
     np.testing.assert_allclose(radial.cpu().numpy(), want, rtol=0, atol=4e-6 * np.abs(want).max())
+
+
+@pytest.mark.parametrize("N,k,kind", [(5000, 20, "uniform"), (6000, 32, "clustered"), (4096, 20, "duplicates"),
+                                      (20000, 32, "uniform"), (3000, 40, "uniform")])
+def test_cell_list_knn_is_bit_identical_to_dense_sweep(N, k, kind):
+    """The cell-list search (large periodic clouds) must return exactly the dense sweep's indices and displacements:
+    same fp32 distance expression, list ordered by (distance, index) = the reference's stable argsort.  Clustered
+    points force the search radius to grow; duplicated points create exact distance ties."""
+    from eqnn_jax_b200 import ops
+    rng = np.random.default_rng(N + k)
+    L = 3.4
+    if kind == "clustered":
+        centres = rng.uniform(-L / 2, L / 2, size=(12, 3))
+        x = centres[rng.integers(0, 12, size=N)] + 0.03 * rng.normal(size=(N, 3))
+        x[: N // 10] = rng.uniform(-L / 2, L / 2, size=(N // 10, 3))       # sparse background: far k-th neighbours
+    else:
+        x = rng.uniform(-L / 2, L / 2, size=(N, 3))
+    if kind == "duplicates":
+        x[N // 2:] = x[: N - N // 2]                                        # every point twice: exact ties
+    x = np.stack([x, np.roll(x, 1, axis=0)]).astype(np.float32)             # B = 2
+    cell = np.eye(3, dtype=np.float32) * L
+    cinv = np.linalg.inv(cell).astype(np.float32)
+    xt = torch.tensor(x).cuda()
+    assert ops.lib().eqnn_knn_workspace_bytes(2, N, k) > 0
+    s0, r0, d0 = ops.knn_pbc(xt, k, cell, cinv, dense=True)
+    s1, r1, d1 = ops.knn_pbc(xt, k, cell, cinv)
+    assert torch.equal(s0, s1)
+    assert torch.equal(r0, r1)
+    assert torch.equal(d0.view(torch.int32), d1.view(torch.int32))
