@@ -597,10 +597,12 @@ def _forward(model: NequIP, plan: _Plan, theta: torch.Tensor, pg: PreparedGraph,
     T0 = torch.empty((Nt, tpr.d_live), **f32)
     ops.node_tp_fwd(ro_id, hr, attrs, Nt, T0)
     dh = model.d_hidden
-    pre = torch.empty((Nt, dh), **f32)
-    _mm(Nt, dh, tpr.d_live, 1.0, T0, 0, tpr.d_live, wexp, plan.Wro.off, dh, pre, 0, dh)
+    # The Linear to d_hidden scalars and the sum / mean over the nodes commute (nequip.py:195-199): pool the
+    # D_live-wide tensor-product output first, then apply the Linear to B rows instead of B*N rows.
+    T0p = torch.empty((B, tpr.d_live), **f32)
+    ops.pool_fwd(T0, B, N, tpr.d_live, 1 if model.readout_agg == "mean" else 0, T0p)
     pooled = torch.empty((B, dh), **f32)
-    ops.pool_fwd(pre, B, N, dh, 1 if model.readout_agg == "mean" else 0, pooled)
+    _mm(B, dh, tpr.d_live, 1.0, T0p, 0, tpr.d_live, wexp, plan.Wro.off, dh, pooled, 0, dh)
     ln_stats = None
     a = pooled
     if plan.ln is not None:
@@ -617,7 +619,7 @@ def _forward(model: NequIP, plan: _Plan, theta: torch.Tensor, pg: PreparedGraph,
             aux_off=bo)
         zs.append(zl)
         a, pro = zl, 1
-    saved.update(attrs=attrs, hr=hr, T0=T0, pooled=pooled, ro_z=zs, ro_in=ro_in, ln_stats=ln_stats, globals=globals_)
+    saved.update(attrs=attrs, hr=hr, T0p=T0p, pooled=pooled, ro_z=zs, ro_in=ro_in, ln_stats=ln_stats, globals=globals_)
     return zs[-1], saved
 
 
@@ -672,12 +674,13 @@ def _backward(model: NequIP, plan: _Plan, theta: torch.Tensor, pg: PreparedGraph
             ops.layernorm_bwd(saved["pooled"], saved["globals"], theta, plan.ln[0], saved["ln_stats"], dz, d_pool,
                               gtheta, plan.ln[0], plan.ln[1])
             dz = d_pool
-        dpre = torch.empty((Nt, dhid), **f32)
-        ops.pool_bwd(dz, B, N, dhid, 1 if model.readout_agg == "mean" else 0, dpre)
-        T0 = saved["T0"]
-        _mm(tpr.d_live, dhid, Nt, 1.0, T0, 0, tpr.d_live, dpre, 0, dhid, gwexp, plan.Wro.off, dhid, ta=True)
+        # pooled = pool(T0) @ Wro: weight gradient and data gradient on B rows, then un-pool
+        T0p = saved["T0p"]
+        _mm(tpr.d_live, dhid, B, 1.0, T0p, 0, tpr.d_live, dz, 0, dhid, gwexp, plan.Wro.off, dhid, ta=True)
+        dT0p = torch.empty((B, tpr.d_live), **f32)
+        _mm(B, tpr.d_live, dhid, 1.0, dz, 0, dhid, wexp, plan.Wro.off, dhid, dT0p, 0, tpr.d_live, tb=True)
         dT0 = torch.empty((Nt, tpr.d_live), **f32)
-        _mm(Nt, tpr.d_live, dhid, 1.0, dpre, 0, dhid, wexp, plan.Wro.off, dhid, dT0, 0, tpr.d_live, tb=True)
+        ops.pool_bwd(dT0p, B, N, tpr.d_live, 1 if model.readout_agg == "mean" else 0, dT0)
         dhr = torch.empty((Nt, tpr.dxp), **f32)
         ops.node_tp_bwd(ro_id, saved["hr"], saved["attrs"], dT0, Nt, dhr)
         dh = torch.empty((Nt, D), **f32)
