@@ -299,6 +299,89 @@ struct SplitPlan {
   int64_t k_per_split;
 };
 
+
+// ------------------------------------------------------------------------------------------------
+// Skinny shapes: the node-level Linear layers have a handful of columns (7, 8, 18) and hundreds of thousands of
+// rows.  A 128-wide tile wastes >90% of its lanes on them, so they get two dedicated kernels.
+//   rows:   C[M x N] (+)= alpha * A[M x K] @ B[K x N],  K, N <= 32: one thread per row, B in shared memory
+//   wgrad:  C[Mi x N]  = alpha * sum_k A(m, k) B(k, n), Mi, N <= 32, K = #rows: per-CTA partials over row
+//           chunks (operands staged through shared memory), fixed-order reduction (deterministic)
+// ------------------------------------------------------------------------------------------------
+template <int NB>
+__global__ void __launch_bounds__(256) skinny_rows_kernel(const GemmP p) {
+  __shared__ float sB[32 * NB];
+  const int K = (int)p.K, N = (int)p.N;
+  for (int i = threadIdx.x; i < K * NB; i += 256) {
+    const int k = i / NB, n = i - k * NB;
+    sB[i] = n < N ? p.B[(int64_t)k * p.sbk + (int64_t)n * p.sbn] : 0.f;
+  }
+  __syncthreads();
+  const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (r >= p.M) return;
+  float acc[NB];
+#pragma unroll
+  for (int n = 0; n < NB; ++n) acc[n] = 0.f;
+  const float* a = p.A + r * p.sam;
+  for (int k = 0; k < K; ++k) {
+    const float v = a[(int64_t)k * p.sak];
+#pragma unroll
+    for (int n = 0; n < NB; ++n) acc[n] = fmaf(v, sB[k * NB + n], acc[n]);
+  }
+  float* c = p.C + r * p.scm;
+#pragma unroll
+  for (int n = 0; n < NB; ++n)
+    if (n < N) {
+      const float v = p.alpha * acc[n];
+      c[(int64_t)n * p.scn] = p.accumulate ? c[(int64_t)n * p.scn] + v : v;
+    }
+}
+
+constexpr int SKW_ROWS = 64;      // rows staged per step
+template <int MB>                  // Mi, N <= MB; thread = (m, n) pair
+__global__ void __launch_bounds__(MB * MB) skinny_wgrad_kernel(const GemmP p, int64_t rows_per_cta, float* __restrict__ partial) {
+  __shared__ float sA[SKW_ROWS][MB + 1];
+  __shared__ float sBt[SKW_ROWS][MB + 1];
+  const int Mi = (int)p.M, N = (int)p.N;
+  const int tid = threadIdx.x, m = tid / MB, n = tid - m * MB;
+  const int64_t k0 = (int64_t)blockIdx.x * rows_per_cta, k1 = min(p.K, k0 + rows_per_cta);
+  float acc = 0.f;
+  for (int64_t kb = k0; kb < k1; kb += SKW_ROWS) {
+    const int nr = (int)min((int64_t)SKW_ROWS, k1 - kb);
+    __syncthreads();
+    for (int i = tid; i < SKW_ROWS * MB; i += MB * MB) {
+      const int r = i / MB, c = i - r * MB;
+      sA[r][c] = (r < nr && c < Mi) ? p.A[(int64_t)c * p.sam + (kb + r) * p.sak] : 0.f;
+      sBt[r][c] = (r < nr && c < N) ? p.B[(kb + r) * p.sbk + (int64_t)c * p.sbn] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int r = 0; r < SKW_ROWS; ++r) acc = fmaf(sA[r][m], sBt[r][n], acc);
+  }
+  if (m < Mi && n < N) partial[((size_t)blockIdx.x * Mi + m) * N + n] = acc;
+}
+
+__global__ void skinny_wgrad_reduce_kernel(const GemmP p, int n_parts, const float* __restrict__ partial) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int Mi = (int)p.M, N = (int)p.N;
+  if (i >= Mi * N) return;
+  float s = 0.f;
+  for (int q = 0; q < n_parts; ++q) s += partial[(size_t)q * Mi * N + i];
+  const int m = i / N, n = i - m * N;
+  float* c = p.C + (int64_t)m * p.scm + (int64_t)n * p.scn;
+  *c = p.accumulate ? *c + p.alpha * s : p.alpha * s;
+}
+
+inline bool skinny_rows_ok(int64_t M, int64_t N, int64_t K, int pro, int epi) {
+  return pro == 0 && epi == 0 && M >= 4096 && K >= 1 && K <= 32 && N <= 32;
+}
+inline bool skinny_wgrad_ok(int64_t M, int64_t N, int64_t K, int pro, int epi) {
+  return pro == 0 && epi == 0 && K >= 4096 && M <= 32 && N <= 32;
+}
+inline int skinny_wgrad_parts(int64_t K) {
+  const int64_t want = ceil_div64(K, 4 * SKW_ROWS);
+  return (int)(want < 1184 ? want : 1184);
+}
+
 SplitPlan plan_split(int64_t M, int64_t N, int64_t K, int bm, int bn) {
   const int64_t tiles = ceil_div64(M, bm) * ceil_div64(N, bn);
   SplitPlan s{1, K};
@@ -345,7 +428,9 @@ extern "C" size_t eqnn_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K) {
   SplitPlan s = plan_split(M, N, K, 128, bn);
   const size_t simt = s.ksplit > 1 ? (size_t)s.ksplit * M * N * sizeof(float) : 0;
   const size_t tcw = eqnn_tc_wgrad_workspace_bytes(M, N, K);
-  return simt > tcw ? simt : tcw;
+  const size_t skw = skinny_wgrad_ok(M, N, K, 0, 0) ? (size_t)skinny_wgrad_parts(K) * M * N * sizeof(float) : 0;
+  size_t need = simt > tcw ? simt : tcw;
+  return need > skw ? need : skw;
 }
 
 extern "C" int eqnn_gemm_f32(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t sam,
@@ -379,6 +464,28 @@ extern "C" int eqnn_gemm_f32(int64_t M, int64_t N, int64_t K, float alpha, const
   p.accumulate = (flags & EQNN_GEMM_ACCUMULATE) ? 1 : 0;
   p.pro = pro; p.pro_scale = pro_scale;
   p.epi = epi; p.aux = aux; p.ld_aux = ld_aux; p.epi_scale = epi_scale;
+  cudaStream_t st = as_stream(stream);
+  if (skinny_rows_ok(M, N, K, pro, epi)) {
+    const unsigned grid = (unsigned)ceil_div64(M, 256);
+    if (N <= 8) skinny_rows_kernel<8><<<grid, 256, 0, st>>>(p);
+    else if (N <= 16) skinny_rows_kernel<16><<<grid, 256, 0, st>>>(p);
+    else skinny_rows_kernel<32><<<grid, 256, 0, st>>>(p);
+    EQNN_CHECK_LAUNCH();
+    return EQNN_OK;
+  }
+  if (skinny_wgrad_ok(M, N, K, pro, epi) && ws && ws_bytes >= (size_t)skinny_wgrad_parts(K) * M * N * sizeof(float)) {
+    const int parts = skinny_wgrad_parts(K);
+    const int64_t rows_per_cta = ceil_div64(ceil_div64(K, parts), SKW_ROWS) * SKW_ROWS;
+    const int used = (int)ceil_div64(K, rows_per_cta);
+    float* partial = reinterpret_cast<float*>(ws);
+    const int mx = (int)(M > N ? M : N);
+    if (mx <= 8) skinny_wgrad_kernel<8><<<used, 64, 0, st>>>(p, rows_per_cta, partial);
+    else if (mx <= 16) skinny_wgrad_kernel<16><<<used, 256, 0, st>>>(p, rows_per_cta, partial);
+    else skinny_wgrad_kernel<32><<<used, 1024, 0, st>>>(p, rows_per_cta, partial);
+    skinny_wgrad_reduce_kernel<<<(unsigned)ceil_div64(M * N, 128), 128, 0, st>>>(p, used, partial);
+    EQNN_CHECK_LAUNCH_N(2);
+    return EQNN_OK;
+  }
   const int bn = N <= 16 ? 16 : (N <= 32 ? 32 : 128);
   SplitPlan s = plan_split(M, N, K, 128, bn);
   p.ksplit = s.ksplit; p.k_per_split = s.k_per_split;
@@ -390,7 +497,6 @@ extern "C" int eqnn_gemm_f32(int64_t M, int64_t N, int64_t K, float alpha, const
   else if (sam == 1 && sak % 4 == 0 && aligned16(A)) amode = 2;
   if (sbn == 1 && sbk % 4 == 0 && aligned16(B)) bmode = 1;
   // float4 loads along K need every split to start on a multiple of 4 (k_per_split is a multiple of BK)
-  cudaStream_t st = as_stream(stream);
   if (bn == 16) launch<128, 16, 8, 1>(p, amode, bmode, st);
   else if (bn == 32) launch<128, 32, 8, 2>(p, amode, bmode, st);
   else launch<128, 128, 8, 8>(p, amode, bmode, st);

@@ -23,7 +23,8 @@ def _rel(got, want):
 
 
 @pytest.mark.parametrize("M,N,K", [(1, 1, 1), (8, 2, 256), (40000, 192, 33), (40000, 7, 170), (5000, 8, 7),
-                                   (70001, 128, 64), (30000, 128, 128), (30000, 11, 128), (300, 130, 50)])
+                                   (70001, 128, 64), (30000, 128, 128), (30000, 11, 128), (300, 130, 50),
+                                   (40001, 18, 30), (7, 8, 50000), (18, 30, 20001), (8, 7, 100001)])   # skinny kernels
 @pytest.mark.parametrize("ta,tb,tc", [(False, False, False), (True, False, False), (False, True, False),
                                       (True, True, True)])
 def test_gemm_layouts(M, N, K, ta, tb, tc):
@@ -76,6 +77,27 @@ def test_gemm_prologue_epilogue_accumulate_offsets():
     _mm(M, N, K, 2.0, A.float().cuda(), 0, K, buf, 5, N, C, 0, N, epi=2, aux=aux.float().cuda(), ld_aux=N,
         epi_scale=1.3, accumulate=True)
     assert _rel(C, C0 + 2.0 * (A @ B) * gelu_grad(aux) * 1.3) < 3e-6
+
+
+def test_gemm_skinny_kernels_accumulate_and_determinism():
+    """Node-level Linear shapes: N-row GEMM with a few columns, and its weight gradient (K = #rows)."""
+    from eqnn_jax_b200.nequip import _mm
+    g = torch.Generator().manual_seed(3)
+    M, N, K = 60000, 7, 8
+    A = torch.randn(M, K, generator=g, dtype=torch.float64)
+    B = torch.randn(K, N, generator=g, dtype=torch.float64)
+    C0 = torch.randn(M, N, generator=g, dtype=torch.float64)
+    C = C0.float().cuda()
+    _mm(M, N, K, 1.5, A.float().cuda(), 0, K, B.t().contiguous().float().cuda(), 0, K, C, 0, N, tb=True, accumulate=True)
+    assert _rel(C, C0 + 1.5 * (A @ B)) < 2e-6
+    G = torch.randn(M, N, generator=g, dtype=torch.float64)
+    outs = []
+    for _ in range(2):
+        W = torch.full((K, N), 2.0).cuda()
+        _mm(K, N, M, 0.5, A.float().cuda(), 0, K, G.float().cuda(), 0, N, W, 0, N, ta=True, accumulate=True)
+        outs.append(W.clone())
+    assert torch.equal(outs[0], outs[1])
+    assert _rel(outs[0], 2.0 + 0.5 * (A.t() @ G)) < 2e-6
 
 
 def test_gate_forward_backward():
