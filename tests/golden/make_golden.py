@@ -19,6 +19,14 @@ sys.path.insert(0, os.path.join(HERE, "..", ".."))
 
 from oracle import graph_ref as G          # noqa: E402
 from oracle import nequip_ref as NQ        # noqa: E402
+from oracle import egnn_ref as EG          # noqa: E402
+from oracle import segnn_ref as SG         # noqa: E402
+from oracle.e3nn_ref import IrrepsArray as OIA   # noqa: E402
+from oracle.so3 import Irreps as OI        # noqa: E402
+
+EGNN_KW = dict(message_passing_steps=2, d_hidden=32, n_layers=3, tanh_out=True, soft_edges=True, positions_only=False,
+               task="node", decouple_pos_vel_updates=True, n_radial_basis=8, r_max=2.0)
+SEGNN_KW = dict(message_passing_steps=2, d_hidden=32, task="node", residual=True, output_irreps="1o + 1o + 1x0e")
 
 IRR = "1o+1o+1x0e"
 
@@ -67,7 +75,29 @@ def nequip_fixture():
     np.savez_compressed(os.path.join(HERE, "nequip_small.npz"), **out)
 
 
+def egnn_segnn_fixture():
+    """EGNN on (x, v, h) nodes and SEGNN on "1o+1o+1x0e" nodes (the configurations of the reference's own
+    equivariance tests, tests/test_equivariance.py:224-310), oracle outputs in fp64."""
+    rng = np.random.default_rng(21)
+    B, N, k = 2, 20, 5
+    x = rng.normal(size=(B, N, 7)).astype(np.float32)
+    g = G.build_graph(x, None, k)
+    out = {"x": x, "k": np.array(k)}
+    cfg = EG.EGNNConfig(**EGNN_KW)
+    p = NQ.to_torch(EG.init_params(cfg, 7, seed=5))
+    out["egnn_out"] = EG.apply_batched(p, cfg, g._replace(nodes=torch.tensor(x, dtype=torch.float64))).nodes.numpy()
+    st = G.get_equivariant_graph(OIA(IRR, torch.tensor(x, dtype=torch.float64)), x[..., :3], x[..., 3:6], g.senders,
+                                 g.receivers, g.n_node, g.n_edge, None, None, 1)
+    scfg = SG.SEGNNConfig(**SEGNN_KW)
+    sp = NQ.to_torch(SG.init_params(scfg, IRR, OI.spherical_harmonics(1), "1x0e", seed=6))
+    out["segnn_out"] = SG.apply_batched(sp, scfg, st).array.numpy()
+    out["steerable_node_attrs"] = np.asarray(st.steerable_node_attrs)
+    out["steerable_edge_attrs"] = np.asarray(st.steerable_edge_attrs)
+    np.savez_compressed(os.path.join(HERE, "egnn_segnn_small.npz"), **out)
+
+
 if __name__ == "__main__":
     knn_fixture()
     nequip_fixture()
+    egnn_segnn_fixture()
     print("wrote", [f for f in os.listdir(HERE) if f.endswith(".npz")])

@@ -85,3 +85,60 @@ def test_gpu_nequip_matches_golden(neq, name):
     w = neq[f"{name}_grad_linear1"]
     got = np.concatenate([v.cpu().numpy().reshape(-1) for v in gt["Linear_1"].values()])
     assert np.abs(got - w).max() <= 1e-5 * np.abs(w).max()
+
+
+# ---- EGNN (x, v, h) and SEGNN: the configurations of the reference's own equivariance tests --------------------
+EGNN_KW = dict(message_passing_steps=2, d_hidden=32, n_layers=3, tanh_out=True, soft_edges=True, positions_only=False,
+               task="node", decouple_pos_vel_updates=True, n_radial_basis=8, r_max=2.0)
+SEGNN_KW = dict(message_passing_steps=2, d_hidden=32, task="node", residual=True, output_irreps="1o + 1o + 1x0e")
+
+
+@pytest.fixture(scope="module")
+def es():
+    return np.load(os.path.join(HERE, "golden", "egnn_segnn_small.npz"))
+
+
+def test_oracle_reproduces_egnn_segnn_golden(es):
+    from oracle import egnn_ref as EG, segnn_ref as SG
+    from oracle.e3nn_ref import IrrepsArray as OIA
+    from oracle.so3 import Irreps as OI
+    x = es["x"]
+    g = G.build_graph(x, None, int(es["k"]))
+    cfg = EG.EGNNConfig(**EGNN_KW)
+    o = EG.apply_batched(NQ.to_torch(EG.init_params(cfg, 7, seed=5)), cfg, g._replace(nodes=torch.tensor(x, dtype=torch.float64)))
+    np.testing.assert_allclose(o.nodes.numpy(), es["egnn_out"], rtol=1e-9, atol=1e-11)
+    st = G.get_equivariant_graph(OIA(IRR, torch.tensor(x, dtype=torch.float64)), x[..., :3], x[..., 3:6], g.senders,
+                                 g.receivers, g.n_node, g.n_edge, None, None, 1)
+    np.testing.assert_allclose(np.asarray(st.steerable_node_attrs), es["steerable_node_attrs"], rtol=1e-10, atol=1e-12)
+    scfg = SG.SEGNNConfig(**SEGNN_KW)
+    so = SG.apply_batched(NQ.to_torch(SG.init_params(scfg, IRR, OI.spherical_harmonics(1), "1x0e", seed=6)), scfg, st)
+    np.testing.assert_allclose(so.array.numpy(), es["segnn_out"], rtol=1e-9, atol=1e-11)
+
+
+@pytest.mark.gpu
+def test_gpu_egnn_segnn_match_golden(es):
+    from eqnn_jax_b200 import graph_utils as GU
+    from eqnn_jax_b200.egnn import EGNN
+    from eqnn_jax_b200.equivariant_graph_utils import get_equivariant_graph
+    from eqnn_jax_b200.irreps import Irreps
+    from eqnn_jax_b200.nequip import IrrepsArray
+    from eqnn_jax_b200.segnn import SEGNN
+    from oracle import egnn_ref as EG, segnn_ref as SG
+    from oracle.so3 import Irreps as OI
+    x = torch.tensor(es["x"]).cuda()
+    g = GU.build_graph(x, None, int(es["k"]))
+    model = EGNN(**EGNN_KW)
+    gg = g._replace(edges=None)
+    params = model.init(0, gg)
+    params.load_tree(EG.init_params(EG.EGNNConfig(**EGNN_KW), 7, seed=5))
+    got = model.forward_backward(params, gg).cpu().numpy().astype(np.float64)
+    assert np.abs(got - es["egnn_out"]).max() <= 1e-5 * np.abs(es["egnn_out"]).max()
+    st = get_equivariant_graph(IrrepsArray(Irreps(IRR), x), x[..., :3].contiguous(), x[..., 3:6].contiguous(), g.senders,
+                               g.receivers, g.n_node, g.n_edge, None, None, 1)
+    a = st.steerable_node_attrs.array.cpu().numpy().astype(np.float64)
+    assert np.abs(a - es["steerable_node_attrs"]).max() <= 1e-5 * np.abs(es["steerable_node_attrs"]).max()
+    smodel = SEGNN(**SEGNN_KW)
+    sparams = smodel.init(0, st)
+    sparams.load_tree(SG.init_params(SG.SEGNNConfig(**SEGNN_KW), IRR, OI.spherical_harmonics(1), "1x0e", seed=6))
+    sgot = smodel.forward_backward(sparams, st).cpu().numpy().astype(np.float64)
+    assert np.abs(sgot - es["segnn_out"]).max() <= 1e-5 * np.abs(es["segnn_out"]).max()
