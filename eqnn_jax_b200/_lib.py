@@ -58,14 +58,14 @@ SIGNATURES: Dict[str, tuple] = {
     "eqnn_gather_rows": (_i, [_p, _p, _i64, _i, _p, _p]),
     "eqnn_axpy": (_i, [_i64, _f, _p, _p, _p]),
     "eqnn_steerable_attrs": (_i, [_p, _i, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p]),
-    "eqnn_egnn_edge_input_fwd": (_i, [_p, _i, _p, _i, _i, _p, _p, _i, _p, _p]),
-    "eqnn_egnn_edge_input_bwd": (_i, [_p, _i, _i, _p, _p, _p, _p, _i, _p, _p, _p, _i, _p]),
+    "eqnn_egnn_edge_input_fwd": (_i, [_p, _i, _p, _i, _i, _p, _i, _i, _p, _p, _i, _p, _p]),
+    "eqnn_egnn_edge_input_bwd": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _i, _p, _p, _p, _i, _p]),
     "eqnn_egnn_xv_base": (_i, [_p, _i, _p, _p, _i64, _p, _p]),
     "eqnn_egnn_node_assemble": (_i, [_p, _i, _i, _p, _i64, _p, _p]),
     "eqnn_egnn_segment_rows_fwd": (_i, [_p, _i, _i, _p, _i, _i, _p, _i, _p]),
     "eqnn_egnn_segment_rows_bwd": (_i, [_p, _i, _i, _p, _i, _p, _i, _i, _p, _p]),
     "eqnn_egnn_xv_bwd": (_i, [_p, _i, _p, _p, _p, _i, _p, _i64, _p, _p, _p, _p]),
-    "eqnn_copy_cols": (_i, [_p, _i, _i, _i, _i64, _p, _i, _i, _p]),
+    "eqnn_copy_cols": (_i, [_p, _i, _i, _i, _i64, _i, _i, _p, _i, _i, _p]),
     "eqnn_softgate_fwd": (_i, [_p, _p, _i64, _p, _p]),
     "eqnn_softgate_bwd": (_i, [_p, _p, _p, _i64, _p, _p, _p]),
     "eqnn_colsum_workspace_bytes": (_sz, [_i]),

@@ -280,13 +280,16 @@ constexpr int COLSUM_PARTS = 296;
 // edge-MLP input U[p] = [feats[p] | h[sender(p)] | h[receiver(p)]] in receiver-sorted order: warp per receiver row
 __global__ void __launch_bounds__(256) egnn_edge_input_fwd_kernel(const float* __restrict__ feats, int nf,
                                                                   const float* __restrict__ h, int ld_h, int dh,
+                                                                  const float* __restrict__ glob, int n_glob,
+                                                                  int nodes_per_graph,
                                                                   const int32_t* __restrict__ rowptr,
                                                                   const int32_t* __restrict__ src, int n_nodes,
                                                                   float* __restrict__ U) {
   const int lane = threadIdx.x & 31;
   const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= n_nodes) return;
-  const int K0 = nf + 2 * dh;
+  const int K0 = nf + 2 * dh + n_glob;
+  const float* gl = n_glob ? glob + (size_t)(row / nodes_per_graph) * n_glob : nullptr;   // jraph broadcasts the globals
   const int p0 = rowptr[row], p1 = rowptr[row + 1];
   for (int64_t i = (int64_t)p0 * K0 + lane; i < (int64_t)p1 * K0; i += 32) {
     const int64_t p = i / K0;
@@ -294,14 +297,15 @@ __global__ void __launch_bounds__(256) egnn_edge_input_fwd_kernel(const float* _
     float v;
     if (c < nf) v = feats[p * nf + c];
     else if (c < nf + dh) v = h[(size_t)src[p] * ld_h + (c - nf)];
-    else v = h[(size_t)row * ld_h + (c - nf - dh)];
+    else if (c < nf + 2 * dh) v = h[(size_t)row * ld_h + (c - nf - dh)];
+    else v = gl[c - nf - 2 * dh];
     U[i] = v;
   }
 }
 
 // backward of the concatenation: dfeats (copy), receiver part summed over the row (+= into dh_out), sender part
 // stored at the ORIGINAL edge id for the sender-sorted gather that follows
-__global__ void __launch_bounds__(256) egnn_edge_input_bwd_kernel(const float* __restrict__ dU, int nf, int dh,
+__global__ void __launch_bounds__(256) egnn_edge_input_bwd_kernel(const float* __restrict__ dU, int nf, int dh, int n_glob,
                                                                   const int32_t* __restrict__ rowptr,
                                                                   const int32_t* __restrict__ perm, int n_nodes,
                                                                   float* __restrict__ dfeats, float* __restrict__ dhs_e,
@@ -309,7 +313,7 @@ __global__ void __launch_bounds__(256) egnn_edge_input_bwd_kernel(const float* _
   const int lane = threadIdx.x & 31;
   const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= n_nodes) return;
-  const int K0 = nf + 2 * dh;
+  const int K0 = nf + 2 * dh + n_glob;
   const int p0 = rowptr[row], p1 = rowptr[row + 1];
   if (dfeats)
     for (int64_t i = (int64_t)p0 * nf + lane; i < (int64_t)p1 * nf; i += 32) {
@@ -437,14 +441,17 @@ __global__ void egnn_xv_bwd_kernel(const float* __restrict__ nodes, int F, const
   }
 }
 
-// dst[n, c0d + j] = src[n, c0s + j], j < w  (strided column block copy)
-__global__ void copy_cols_kernel(const float* __restrict__ src, int ld_s, int c0s, int w, int64_t n,
-                                 float* __restrict__ dst, int ld_d, int c0d) {
+// dst[n, c0d + j] (+)= src[n / group, c0s + j], j < w  (strided column block copy; group > 1 broadcasts one source
+// row to `group` consecutive destination rows: graph globals -> nodes)
+__global__ void copy_cols_kernel(const float* __restrict__ src, int ld_s, int c0s, int w, int64_t n, int group,
+                                 int accumulate, float* __restrict__ dst, int ld_d, int c0d) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * w) return;
   const int64_t r = i / w;
   const int j = (int)(i - r * w);
-  dst[r * ld_d + c0d + j] = src[r * ld_s + c0s + j];
+  const float v = src[(r / group) * ld_s + c0s + j];
+  float* d = dst + r * ld_d + c0d + j;
+  *d = accumulate ? *d + v : v;
 }
 
 
@@ -624,18 +631,20 @@ extern "C" int eqnn_egnn_sender_acc(const float* dre, const int32_t* rowptr_s, c
   return EQNN_OK;
 }
 
-extern "C" int eqnn_egnn_edge_input_fwd(const float* feats, int nf, const float* h, int ld_h, int dh,
-                                        const int32_t* rowptr, const int32_t* src, int n_nodes, float* U,
-                                        eqnn_stream_t stream) {
-  EQNN_CHECK_ARG(feats && h && rowptr && src && U && nf >= 1 && dh >= 1 && ld_h >= dh, "egnn_edge_input_fwd: bad argument");
+extern "C" int eqnn_egnn_edge_input_fwd(const float* feats, int nf, const float* h, int ld_h, int dh, const float* glob,
+                                        int n_glob, int nodes_per_graph, const int32_t* rowptr, const int32_t* src,
+                                        int n_nodes, float* U, eqnn_stream_t stream) {
+  EQNN_CHECK_ARG(feats && rowptr && src && U && nf >= 1 && dh >= 0 && (dh == 0 || (h && ld_h >= dh)),
+                 "egnn_edge_input_fwd: bad argument");
+  EQNN_CHECK_ARG(n_glob >= 0 && (n_glob == 0 || (glob && nodes_per_graph >= 1)), "egnn_edge_input_fwd: bad globals");
   if (n_nodes <= 0) return EQNN_OK;
   egnn_edge_input_fwd_kernel<<<(unsigned)ceil_div64((int64_t)n_nodes * 32, 256), 256, 0, as_stream(stream)>>>(
-      feats, nf, h, ld_h, dh, rowptr, src, n_nodes, U);
+      feats, nf, h, ld_h, dh, glob, n_glob, nodes_per_graph, rowptr, src, n_nodes, U);
   EQNN_CHECK_LAUNCH();
   return EQNN_OK;
 }
 
-extern "C" int eqnn_egnn_edge_input_bwd(const float* dU, int nf, int dh, const int32_t* rowptr, const int32_t* perm,
+extern "C" int eqnn_egnn_edge_input_bwd(const float* dU, int nf, int dh, int n_glob, const int32_t* rowptr, const int32_t* perm,
                                         const int32_t* rowptr_s, const int32_t* perm_s, int n_nodes, float* dfeats,
                                         float* dhs_e, float* dh_out, int ld_dh, eqnn_stream_t stream) {
   EQNN_CHECK_ARG(dU && rowptr && perm && rowptr_s && perm_s && dhs_e && dh_out && nf >= 1 && dh >= 1 && ld_dh >= dh,
@@ -643,7 +652,7 @@ extern "C" int eqnn_egnn_edge_input_bwd(const float* dU, int nf, int dh, const i
   if (n_nodes <= 0) return EQNN_OK;
   cudaStream_t st = as_stream(stream);
   egnn_edge_input_bwd_kernel<<<(unsigned)ceil_div64((int64_t)n_nodes * 32, 256), 256, 0, st>>>(
-      dU, nf, dh, rowptr, perm, n_nodes, dfeats, dhs_e, dh_out, ld_dh);
+      dU, nf, dh, n_glob, rowptr, perm, n_nodes, dfeats, dhs_e, dh_out, ld_dh);
   egnn_segment_gather_add_kernel<<<(unsigned)ceil_div64((int64_t)n_nodes * dh, 256), 256, 0, st>>>(
       dhs_e, dh, rowptr_s, perm_s, n_nodes, dh_out, ld_dh);
   EQNN_CHECK_LAUNCH_N(2);
@@ -702,13 +711,14 @@ extern "C" int eqnn_egnn_xv_bwd(const float* nodes, int F, const float* sx, cons
   return EQNN_OK;
 }
 
-extern "C" int eqnn_copy_cols(const float* src, int ld_src, int col_src, int width, int64_t n, float* dst, int ld_dst,
-                              int col_dst, eqnn_stream_t stream) {
+extern "C" int eqnn_copy_cols(const float* src, int ld_src, int col_src, int width, int64_t n, int group, int accumulate,
+                              float* dst, int ld_dst, int col_dst, eqnn_stream_t stream) {
   EQNN_CHECK_ARG(src && dst && width >= 1 && col_src >= 0 && col_dst >= 0 && ld_src >= col_src + width &&
-                     ld_dst >= col_dst + width, "copy_cols: bad argument");
+                     ld_dst >= col_dst + width && group >= 1, "copy_cols: bad argument");
   if (n <= 0) return EQNN_OK;
   copy_cols_kernel<<<(unsigned)ceil_div64(n * width, 256), 256, 0, as_stream(stream)>>>(src, ld_src, col_src, width, n,
-                                                                                       dst, ld_dst, col_dst);
+                                                                                       group, accumulate, dst, ld_dst,
+                                                                                       col_dst);
   EQNN_CHECK_LAUNCH();
   return EQNN_OK;
 }

@@ -21,7 +21,9 @@ The (x, h) layout (``positions_only=True`` with scalar attributes: train_cosmolo
 aggregated messages: h' = h + phi_h([h, m_i]) (egnn.py:152-166), m_i = segment reduce of m_ij.  The (x, v) layout
 (6 features) feeds m_i to phi_v / phi_xx and returns (x', v, m_i): the node width grows to 6 + d_hidden and the
 following steps run as (x, v, h) with d_hidden scalars (egnn.py:171-196) -- all four layouts of the reference.
-Not built yet: graph globals, max aggregation -> NotImplementedError, never a silent fallback.
+Graph globals (broadcast to every edge and node by jraph, concatenated to the pooled features and LayerNorm-ed
+before the read-out, egnn.py:41-60,163-164,211-212,332-336) are supported for the (x), (x, h) and (x, v, h) layouts.
+Not built yet: globals with the (x, v) layout, max aggregation -> NotImplementedError, never a silent fallback.
 """
 from __future__ import annotations
 
@@ -79,7 +81,7 @@ class EGNN:
         if self.n_layers < 2:
             raise NotImplementedError("n_layers >= 2 expected")
 
-    def _layout(self, n_feat: int = 3):
+    def _layout(self, n_feat: int = 3, n_glob: int = 0):
         d, L = self.d_hidden, self.n_layers
         nf = self.n_radial_basis if self.n_radial_basis > 0 else 1
         layout: List[Tuple[Tuple[str, ...], Tuple[int, ...], int]] = []
@@ -104,7 +106,9 @@ class EGNN:
         for s in range(self.message_passing_steps):
             vel, dh = self._variant(Fs)
             st = {"phi_e": [], "phi_x": [], "F": Fs, "vel": vel, "dh": dh}
-            fan = nf + 2 * dh
+            if vel and dh == 0 and n_glob:
+                raise NotImplementedError("B200 EGNN: graph globals with the (x, v) layout are not built")
+            fan = nf + 2 * dh + n_glob                        # [bessel | h_s | h_r | globals], egnn.py:41-60,93-96
             for l in range(L):
                 st["phi_e"].append((add((f"MLP_{mi}", f"Dense_{l}", "kernel"), (fan, d)),
                                     add((f"MLP_{mi}", f"Dense_{l}", "bias"), (d,)), fan))
@@ -120,9 +124,9 @@ class EGNN:
                            add((f"MLP_{mi}", "Dense_0", "bias"), (d,))) if self.soft_edges else None
             mi += 1
             if not vel and dh > 0:                           # node function, egnn.py:159-166: phi_h([h_i, m_i])
-                st["phi_h"] = add_mlp(mi, dh + d, [d] * (L - 1) + [dh]); mi += 1
+                st["phi_h"] = add_mlp(mi, dh + d + n_glob, [d] * (L - 1) + [dh]); mi += 1
             if vel:                                          # node function, egnn.py:171-229
-                n_in = dh if dh > 0 else d                   # concats = h_i, or m_i when there are no scalars
+                n_in = (dh if dh > 0 else d) + n_glob        # concats = h_i, or m_i when there are no scalars (+ globals)
                 st["phi_v"] = add_mlp(mi, n_in, [d] * (L - 1) + [1]); mi += 1
                 st["phi_h"] = None
                 if dh > 0:
@@ -136,16 +140,24 @@ class EGNN:
             steps.append(st)
         readout = []
         if self.task == "graph":
-            ws = [self.mlp_readout_widths[0] * Fs] + [w * d for w in self.mlp_readout_widths[1:]] + [self.n_outputs]
-            readout = add_mlp(mi, Fs, ws)
+            n_pool = Fs + n_glob                              # globals + LayerNorm before the read-out, egnn.py:332-336
+            self._ln = None
+            if n_glob:
+                self._ln = (add(("LayerNorm_0", "scale"), (n_pool,)), add(("LayerNorm_0", "bias"), (n_pool,)))
+            ws = [self.mlp_readout_widths[0] * n_pool] + [w * d for w in self.mlp_readout_widths[1:]] + [self.n_outputs]
+            readout = add_mlp(mi, n_pool, ws)
         return layout, steps, readout, off
 
     def init(self, rng: Union[int, np.random.Generator], graphs: GraphsTuple) -> FlatParams:
         self._check(graphs.nodes.shape[-1])
-        layout, steps, readout, n = self._layout(graphs.nodes.shape[-1])
+        n_glob = 0 if graphs.globals is None else int(graphs.globals.shape[-1])
+        layout, steps, readout, n = self._layout(graphs.nodes.shape[-1], n_glob)
         rng = np.random.default_rng(rng) if not isinstance(rng, np.random.Generator) else rng
         host = np.zeros((n,), dtype=np.float32)
         for path, shape, off in layout:
+            if path[0] == "LayerNorm_0":
+                host[off:off + int(np.prod(shape))] = 1.0 if path[-1] == "scale" else 0.0
+                continue
             if path[-1] == "bias":
                 continue
             if path[0].startswith("Dense_"):       # variance_scaling(1e-2, fan_in, uniform), egnn.py:73-78
@@ -162,13 +174,16 @@ class EGNN:
             x = x.unsqueeze(0)
         B, N, F = x.shape
         self._check(F)
+        glob = None
         if graphs.globals is not None:
-            raise NotImplementedError("graph globals are not on the B200 EGNN path yet")
+            if not isinstance(graphs.globals, torch.Tensor) or not graphs.globals.is_cuda:
+                raise RuntimeError("graphs.globals must be a CUDA tensor (this path has no CPU implementation)")
+            glob = graphs.globals.reshape(B, -1).to(torch.float32).contiguous()
         senders = graphs.senders.reshape(B, -1).contiguous()
         receivers = graphs.receivers.reshape(B, -1).contiguous()
         rowptr, perm, src = ops.csr_build(senders, receivers, N)
         rowptr_s, perm_s, _ = ops.csr_build(receivers, senders, N)
-        return x.contiguous(), B, N, senders.shape[1], (rowptr, perm, src, rowptr_s, perm_s)
+        return x.contiguous(), B, N, senders.shape[1], (rowptr, perm, src, rowptr_s, perm_s, glob)
 
     def forward_backward(self, params: FlatParams, graphs: GraphsTuple, grad_fn=None):
         """Forward (and, if ``grad_fn(out) -> dL/dout`` is given, backward into ``params.grad``)."""
@@ -215,10 +230,11 @@ class EGNN:
                 _mm(M, fan, w, 1.0, dz, 0, w, theta, ko, w, t, off, ld, tb=True, accumulate=True, tag="egnn_node_mlp")
 
     def _forward(self, theta, x, B, N, E, csr):
-        rowptr, perm, src, rowptr_s, perm_s = csr
+        rowptr, perm, src, rowptr_s, perm_s, glob = csr
+        G_ = 0 if glob is None else glob.shape[1]
         dev = x.device
         f32 = dict(dtype=torch.float32, device=dev)
-        layout, steps, readout, _ = self._layout(x.shape[-1])
+        layout, steps, readout, _ = self._layout(x.shape[-1], G_)
         Nt, Et = B * N, B * E
         d = self.d_hidden
         nf = self.n_radial_basis if self.n_radial_basis > 0 else 1
@@ -230,15 +246,15 @@ class EGNN:
         saved = {"steps": []}
         for st in steps:
             F, vel, dh, F_out = st["F"], st["vel"], st["dh"], st["F_out"]
-            K0 = nf + 2 * dh
+            K0 = nf + 2 * dh + G_
             ho = 6 if vel else 3                             # first scalar-attribute column
             rij4 = torch.empty((Et, 4), **f32)
             feats = torch.empty((Et, nf), **f32)
             ops.egnn_geom_fwd(nodes, F, Nt, rowptr, src, cell, cinv, self.n_radial_basis, self.r_max, rij4, feats)
             U = feats
-            if dh > 0:                                       # [bessel | h_sender | h_receiver], egnn.py:47-60,93-96
+            if K0 != nf:                                     # [bessel | h_sender | h_receiver | globals], egnn.py:41-60,93-96
                 U = torch.empty((Et, K0), **f32)
-                ops.egnn_edge_input_fwd(feats, nf, nodes, F, ho, dh, rowptr, src, Nt, U)
+                ops.egnn_edge_input_fwd(feats, nf, nodes, F, ho, dh, rowptr, src, Nt, U, glob=glob, nodes_per_graph=N)
             acts, a, pro = [], U, 0
             Za = Mg = None
             nE = len(st["phi_e"])
@@ -266,15 +282,22 @@ class EGNN:
             if not vel:
                 ops.egnn_coord_fwd(rij4, t, self.tanh_out, agg, rowptr, Nt, nodes, F, cell, cinv, nodes_next, F)
                 if dh > 0:                                   # (x, h): h' = h + phi_h([h, m_i]), egnn.py:152-166
-                    Cc = torch.empty((Nt, dh + d), **f32)
-                    ops.copy_cols(nodes, F, 3, dh, Nt, Cc, dh + d, 0)
-                    ops.egnn_segment_rows_fwd(Mg if gated else acts[nE - 1], d, not gated, rowptr, Nt, agg, Cc, dh + d,
+                    wc = dh + d + G_                         # [h | m_i | globals]
+                    Cc = torch.empty((Nt, wc), **f32)
+                    ops.copy_cols(nodes, F, 3, dh, Nt, Cc, wc, 0)
+                    ops.egnn_segment_rows_fwd(Mg if gated else acts[nE - 1], d, not gated, rowptr, Nt, agg, Cc, wc,
                                               col_off=dh)
-                    zh = self._mlp_fwd(theta, st["phi_h"], Cc, 0, dh + d, Nt)
+                    if G_:
+                        ops.copy_cols(glob, G_, 0, G_, Nt, Cc, wc, dh + d, group=N)
+                    zh = self._mlp_fwd(theta, st["phi_h"], Cc, 0, wc, Nt)
                     ops.egnn_node_assemble(nodes, F, 3, zh[-1], Nt, nodes_next)
                     sv.update(Cc=Cc, zh=zh)
             else:
-                if dh > 0:                                   # concats = h_i (egnn.py:207)
+                if dh > 0 and G_:                            # concats = [h_i | globals] (egnn.py:207-212)
+                    cin, c_off, c_ld = torch.empty((Nt, dh + G_), **f32), 0, dh + G_
+                    ops.copy_cols(nodes, F, 6, dh, Nt, cin, dh + G_, 0)
+                    ops.copy_cols(glob, G_, 0, G_, Nt, cin, dh + G_, dh, group=N)
+                elif dh > 0:                                 # concats = h_i (egnn.py:207)
                     cin, c_off, c_ld = nodes, 6, F
                 else:                                        # concats = m_i (egnn.py:180), returned as new scalars
                     cin, c_off, c_ld = torch.empty((Nt, d), **f32), 0, d
@@ -298,20 +321,27 @@ class EGNN:
             return nodes.view(B, N, F), saved
         pooled = torch.empty((B, F), **f32)
         ops.pool_fwd(nodes, B, N, F, 1 if self.readout_agg == "mean" else 0, pooled)
-        zs, a, pro = [], pooled, 0
+        a, ln_stats = pooled, None
+        if G_:
+            a = torch.empty((B, F + G_), **f32)
+            ln_stats = torch.empty((B, 2), **f32)
+            ops.layernorm_fwd(pooled, glob, theta, self._ln[0], self._ln[1], 1e-6, a, ln_stats)
+        ro_in = a
+        zs, pro = [], 0
         for (ko, bo, fan, h) in readout:
             zl = torch.empty((B, h), **f32)
             _mm(B, h, fan, 1.0, a, 0, fan, theta, ko, h, zl, 0, h, pro=pro, pro_scale=1.0, epi=1, aux=theta, aux_off=bo)
             zs.append(zl)
             a, pro = zl, 1
-        saved.update(pooled=pooled, ro_z=zs)
+        saved.update(pooled=pooled, ro_z=zs, ro_in=ro_in, ln_stats=ln_stats)
         return zs[-1], saved
 
     def _backward(self, theta, gtheta, saved, gout, B, N, E, csr):
-        rowptr, perm, src, rowptr_s, perm_s = csr
+        rowptr, perm, src, rowptr_s, perm_s, glob = csr
+        G_ = 0 if glob is None else glob.shape[1]
         dev = theta.device
         f32 = dict(dtype=torch.float32, device=dev)
-        layout, steps, readout, _ = self._layout(saved["steps"][0]["nodes"].shape[-1])
+        layout, steps, readout, _ = self._layout(saved["steps"][0]["nodes"].shape[-1], G_)
         Nt, Et = B * N, B * E
         d = self.d_hidden
         nf = self.n_radial_basis if self.n_radial_basis > 0 else 1
@@ -326,7 +356,7 @@ class EGNN:
             dz = gout.reshape(B, -1).contiguous()
             for l in range(len(readout) - 1, -1, -1):
                 ko, bo, fan, h = readout[l]
-                a_prev = zs[l - 1] if l > 0 else saved["pooled"]
+                a_prev = zs[l - 1] if l > 0 else saved["ro_in"]
                 _mm(fan, h, B, 1.0, a_prev, 0, fan, dz, 0, h, gtheta, ko, h, ta=True, pro=1 if l > 0 else 0, pro_scale=1.0)
                 ops.colsum(dz, B, h, gtheta, y_off=bo)
                 dprev = torch.empty((B, fan), **f32)
@@ -336,6 +366,11 @@ class EGNN:
                 else:
                     _mm(B, fan, h, 1.0, dz, 0, h, theta, ko, h, dprev, 0, fan, tb=True)
                 dz = dprev
+            if G_:
+                d_pool = torch.empty((B, F), **f32)
+                ops.layernorm_bwd(saved["pooled"], glob, theta, self._ln[0], saved["ln_stats"], dz, d_pool, gtheta,
+                                  self._ln[0], self._ln[1])
+                dz = d_pool
             dN = torch.empty((Nt, F), **f32)
             ops.pool_bwd(dz, B, N, F, 1 if self.readout_agg == "mean" else 0, dN)
         dt = torch.empty((Et,), **f32)
@@ -344,7 +379,7 @@ class EGNN:
             st, sv = steps[si], saved["steps"][si]
             rij4, U, acts, t, nodes = sv["rij4"], sv["U"], sv["acts"], sv["t"], sv["nodes"]
             F, vel, dh, F_out = st["F"], st["vel"], st["dh"], st["F_out"]      # dN is (Nt, F_out) here
-            K0 = nf + 2 * dh
+            K0 = nf + 2 * dh + G_
             nE = len(st["phi_e"])
             g3 = dN
             if F_out != 3:                                   # dL/dx' as a dense (Nt, 3) array
@@ -365,14 +400,15 @@ class EGNN:
                 if zx is not None:
                     self._mlp_bwd(theta, gtheta, st["phi_xx"], zx, sv["cin"], 0, d, Nt, dsx, (dC, 0, d))
             if not vel and dh > 0:
-                dC_ld, dC_off = dh + d, dh
+                dC_ld, dC_off = dh + d + G_, dh
                 # (x, h) node function first: it yields dL/dm_i, which joins the message gradient below.
                 # dC starts as [dL/dh' | 0]; the MLP input gradient is accumulated on top: [dL/dh (so far) | dL/dm_i]
                 dph = torch.empty((Nt, dh), **f32)
                 ops.copy_cols(dN, F, 3, dh, Nt, dph, dh, 0)
-                dC = torch.zeros((Nt, dh + d), **f32)
-                ops.copy_cols(dN, F, 3, dh, Nt, dC, dh + d, 0)
-                self._mlp_bwd(theta, gtheta, st["phi_h"], sv["zh"], sv["Cc"], 0, dh + d, Nt, dph, (dC, 0, dh + d))
+                dC = torch.zeros((Nt, dh + d + G_), **f32)
+                ops.copy_cols(dN, F, 3, dh, Nt, dC, dh + d + G_, 0)
+                self._mlp_bwd(theta, gtheta, st["phi_h"], sv["zh"], sv["Cc"], 0, dh + d + G_, Nt, dph,
+                              (dC, 0, dh + d + G_))
             layers = st["phi_e"] + st["phi_x"]
             last = acts[-1]
             # t = gelu(U_last) @ k_last
@@ -421,7 +457,7 @@ class EGNN:
             mix = None
             if si > 0:
                 dfeats = dU
-                if dh > 0:
+                if K0 != nf:
                     dfeats = torch.empty((Et, nf), **f32)
                     ops.copy_cols(dU, K0, 0, nf, Et, dfeats, nf, 0)
                 mix = torch.empty((Nt, 3), **f32)
@@ -434,9 +470,9 @@ class EGNN:
                     continue
                 dN_in = torch.empty((Nt, F), **f32)
                 ops.copy_cols(mix, 3, 0, 3, Nt, dN_in, F, 0)
-                ops.copy_cols(dC, dh + d, 0, dh, Nt, dN_in, F, 3)
+                ops.copy_cols(dC, dh + d + G_, 0, dh, Nt, dN_in, F, 3)
                 dhs_e = torch.empty((Et, dh), **f32)
-                ops.egnn_edge_input_bwd(dU, nf, dh, rowptr, perm, rowptr_s, perm_s, Nt, None, dhs_e, dN_in, F, 3)
+                ops.egnn_edge_input_bwd(dU, nf, dh, rowptr, perm, rowptr_s, perm_s, Nt, None, dhs_e, dN_in, F, 3, n_glob=G_)
                 dN = dN_in
                 continue
             # ---- node function backward (egnn.py:171-229)
@@ -448,16 +484,24 @@ class EGNN:
             if dh == 0:                                      # (x, v): the MLPs were differentiated above; 6 columns only
                 dN = dN_in
                 continue
-            din = (dN_in, 6, F) if si > 0 else None
+            cin, c_off, c_ld = sv["cin"], sv["c_off"], sv["c_ld"]
+            din, dCv = None, None
             if si > 0:
                 dhs_e = torch.empty((Et, dh), **f32)
-                ops.egnn_edge_input_bwd(dU, nf, dh, rowptr, perm, rowptr_s, perm_s, Nt, None, dhs_e, dN_in, F, 6)
+                ops.egnn_edge_input_bwd(dU, nf, dh, rowptr, perm, rowptr_s, perm_s, Nt, None, dhs_e, dN_in, F, 6, n_glob=G_)
+                if G_:                                       # the MLPs read [h | globals]: gradient through a side buffer
+                    dCv = torch.zeros((Nt, dh + G_), **f32)
+                    din = (dCv, 0, dh + G_)
+                else:
+                    din = (dN_in, 6, F)
             dph = torch.empty((Nt, dh), **f32)
             ops.copy_cols(dN, F, 6, dh, Nt, dph, dh, 0)
-            self._mlp_bwd(theta, gtheta, st["phi_h"], zh, nodes, 6, F, Nt, dph, din)
-            self._mlp_bwd(theta, gtheta, st["phi_v"], zv, nodes, 6, F, Nt, dsv, din)
+            self._mlp_bwd(theta, gtheta, st["phi_h"], zh, cin, c_off, c_ld, Nt, dph, din)
+            self._mlp_bwd(theta, gtheta, st["phi_v"], zv, cin, c_off, c_ld, Nt, dsv, din)
             if zx is not None:
-                self._mlp_bwd(theta, gtheta, st["phi_xx"], zx, nodes, 6, F, Nt, dsx, din)
+                self._mlp_bwd(theta, gtheta, st["phi_xx"], zx, cin, c_off, c_ld, Nt, dsx, din)
+            if dCv is not None:
+                ops.copy_cols(dCv, dh + G_, 0, dh, Nt, dN_in, F, 6, accumulate=True)
             dN = dN_in
         return None
 

@@ -332,13 +332,15 @@ def steerable_attrs(pos, ld_pos, vel, ld_vel, B, N, E, senders, receivers, rowpt
     return r_ij, e_attr, n_attr
 
 
-def egnn_edge_input_fwd(feats, nf, nodes, F, h_off, dh, rowptr, src, n_nodes, U):
-    check(lib().eqnn_egnn_edge_input_fwd(_ptr(feats), nf, _off(nodes, h_off), F, dh, _ptr(rowptr), _ptr(src), n_nodes,
-                                         _ptr(U), _stream()), "egnn_edge_input_fwd")
+def egnn_edge_input_fwd(feats, nf, nodes, F, h_off, dh, rowptr, src, n_nodes, U, glob=None, nodes_per_graph=1):
+    n_glob = 0 if glob is None else glob.shape[1]
+    check(lib().eqnn_egnn_edge_input_fwd(_ptr(feats), nf, _off(nodes, h_off) if dh else None, F, dh, _ptr(glob), n_glob,
+                                         nodes_per_graph, _ptr(rowptr), _ptr(src), n_nodes, _ptr(U), _stream()),
+          "egnn_edge_input_fwd")
 
 
-def egnn_edge_input_bwd(dU, nf, dh, rowptr, perm, rowptr_s, perm_s, n_nodes, dfeats, dhs_e, dnodes, F, h_off):
-    check(lib().eqnn_egnn_edge_input_bwd(_ptr(dU), nf, dh, _ptr(rowptr), _ptr(perm), _ptr(rowptr_s), _ptr(perm_s), n_nodes,
+def egnn_edge_input_bwd(dU, nf, dh, rowptr, perm, rowptr_s, perm_s, n_nodes, dfeats, dhs_e, dnodes, F, h_off, n_glob=0):
+    check(lib().eqnn_egnn_edge_input_bwd(_ptr(dU), nf, dh, n_glob, _ptr(rowptr), _ptr(perm), _ptr(rowptr_s), _ptr(perm_s), n_nodes,
                                          _ptr(dfeats), _ptr(dhs_e), _off(dnodes, h_off), F, _stream()),
           "egnn_edge_input_bwd")
 
@@ -367,8 +369,10 @@ def egnn_xv_bwd(nodes, F, sx, sv, dnext, ld_dnext, mix, n, din, dsx, dsv):
                                  _ptr(dsx), _ptr(dsv), _stream()), "egnn_xv_bwd")
 
 
-def copy_cols(src, ld_src, col_src, width, n, dst, ld_dst, col_dst):
-    check(lib().eqnn_copy_cols(_ptr(src), ld_src, col_src, width, n, _ptr(dst), ld_dst, col_dst, _stream()), "copy_cols")
+def copy_cols(src, ld_src, col_src, width, n, dst, ld_dst, col_dst, group=1, accumulate=False):
+    """dst[r, col_dst:col_dst+width] (+)= src[r // group, col_src:col_src+width] for r < n."""
+    check(lib().eqnn_copy_cols(_ptr(src), ld_src, col_src, width, n, group, int(accumulate), _ptr(dst), ld_dst, col_dst,
+                               _stream()), "copy_cols")
 
 
 def softgate_fwd(z, za, m):

@@ -246,11 +246,13 @@ int eqnn_egnn_coord_bwd(const float* rij4, const float* t, int use_tanh, int agg
 int eqnn_egnn_sender_acc(const float* dre, const int32_t* rowptr_s, const int32_t* perm_s, int n_nodes, float* dpos,
                          eqnn_stream_t stream);
 /* node layout (x, v, h) with scalar attributes (egnn.py:47-60, 198-229):
- * edge-MLP input U[p] = [feats[p] (nf) | h[sender] (dh) | h[receiver] (dh)] in receiver-sorted order, and its backward
+ * edge-MLP input U[p] = [feats[p] (nf) | h[sender] (dh) | h[receiver] (dh) | globals[graph of p] (n_glob)] in
+ * receiver-sorted order (jraph broadcasts the graph globals to every edge, egnn.py:41,46,53,60), and its backward
  * (dfeats may be NULL; dh_out[n, :dh] += receiver row sums + sender-sorted gather; dhs_e: [n_edges, dh] scratch). */
-int eqnn_egnn_edge_input_fwd(const float* feats, int nf, const float* h, int ld_h, int dh, const int32_t* rowptr,
-                             const int32_t* src, int n_nodes, float* U, eqnn_stream_t stream);
-int eqnn_egnn_edge_input_bwd(const float* dU, int nf, int dh, const int32_t* rowptr, const int32_t* perm,
+int eqnn_egnn_edge_input_fwd(const float* feats, int nf, const float* h, int ld_h, int dh, const float* glob, int n_glob,
+                             int nodes_per_graph, const int32_t* rowptr, const int32_t* src, int n_nodes, float* U,
+                             eqnn_stream_t stream);
+int eqnn_egnn_edge_input_bwd(const float* dU, int nf, int dh, int n_glob, const int32_t* rowptr, const int32_t* perm,
                              const int32_t* rowptr_s, const int32_t* perm_s, int n_nodes, float* dfeats, float* dhs_e,
                              float* dh_out, int ld_dh, eqnn_stream_t stream);
 /* base[n] = sx[n] x[n] + sv[n] v[n] (sx NULL = 1): the coordinate layer then forms x' = wrap(base + agg)  (:213-227) */
@@ -272,9 +274,10 @@ int eqnn_egnn_segment_rows_bwd(const float* dmi, int ld_dmi, int d, const float*
  * returns 6 + d_hidden columns) */
 int eqnn_egnn_xv_bwd(const float* nodes, int F, const float* sx, const float* sv, const float* dnext, int ld_dnext,
                      const float* mix, int64_t n, float* din, float* dsx, float* dsv, eqnn_stream_t stream);
-/* dst[n, col_dst + j] = src[n, col_src + j], j < width */
-int eqnn_copy_cols(const float* src, int ld_src, int col_src, int width, int64_t n, float* dst, int ld_dst, int col_dst,
-                   eqnn_stream_t stream);
+/* dst[n, col_dst + j] (+)= src[n / group, col_src + j], j < width  (group > 1: one source row per `group` destination
+ * rows, e.g. graph globals broadcast to the nodes) */
+int eqnn_copy_cols(const float* src, int ld_src, int col_src, int width, int64_t n, int group, int accumulate, float* dst,
+                   int ld_dst, int col_dst, eqnn_stream_t stream);
 /* soft edges (egnn.py:101-105): m = gelu(z) * sigmoid(za); backward: dza = dm * gelu(z) * sigmoid'(za),
  * g1 = dm * sigmoid(za)  (g1 may alias dm) */
 int eqnn_softgate_fwd(const float* z, const float* za, int64_t n, float* m, eqnn_stream_t stream);

@@ -59,18 +59,19 @@ def _variant(cfg: EGNNConfig, F: int):
     return True, F - 6
 
 
-def init_params(cfg: EGNNConfig, n_feat: int, seed: int = 0) -> Dict:
-    """All four node-feature layouts of the reference: (x), (x, h), (x, v), (x, v, h); no graph globals.
+def init_params(cfg: EGNNConfig, n_feat: int, seed: int = 0, n_globals: int = 0) -> Dict:
+    """All four node-feature layouts of the reference: (x), (x, h), (x, v), (x, v, h), with optional graph globals
+    (broadcast to every edge and node by jraph; egnn.py:41,46,53,60,163-164,181-182,211-212,332-336).
     Flax auto-names follow construction order: phi_e, phi_x, [Dense], phi_a, then the node function's phi_v / phi_h /
     phi_xx (egnn.py:63-79,100,161,177-189,210-222)."""
     rng = np.random.default_rng(seed)
     p: Dict = {}
     d, L = cfg.d_hidden, cfg.n_layers
     n_msg = cfg.n_radial_basis if cfg.n_radial_basis > 0 else 1
-    mi, F = 0, n_feat
+    mi, F, G_ = 0, n_feat, n_globals
     for s in range(cfg.message_passing_steps):
         vel, dh = _variant(cfg, F)
-        p[f"MLP_{mi}"] = _mlp_init(rng, n_msg + 2 * dh, [d] * (L - 1) + [d]); mi += 1   # phi_e
+        p[f"MLP_{mi}"] = _mlp_init(rng, n_msg + 2 * dh + G_, [d] * (L - 1) + [d]); mi += 1   # phi_e
         p[f"MLP_{mi}"] = _mlp_init(rng, d, [d] * (L - 1)); mi += 1                      # phi_x
         lim = math.sqrt(3.0 * 1e-2 / d)                                                 # variance_scaling(1e-2, fan_in, uniform)
         p[f"Dense_{s}"] = {"kernel": rng.uniform(-lim, lim, size=(d, 1))}
@@ -79,19 +80,22 @@ def init_params(cfg: EGNNConfig, n_feat: int, seed: int = 0) -> Dict:
         mi += 1
         if not vel:
             if dh > 0:
-                p[f"MLP_{mi}"] = _mlp_init(rng, dh + d, [d] * (L - 1) + [dh]); mi += 1  # phi_h([h_i, m_i])
+                p[f"MLP_{mi}"] = _mlp_init(rng, dh + d + G_, [d] * (L - 1) + [dh]); mi += 1  # phi_h([h_i, m_i, globals])
         else:
-            n_in = d if dh == 0 else dh                                                 # concats = m_i | h_i
+            n_in = (d if dh == 0 else dh) + G_                                          # concats = [m_i | h_i (, globals)]
             p[f"MLP_{mi}"] = _mlp_init(rng, n_in, [d] * (L - 1) + [1]); mi += 1         # phi_v
             if dh > 0:
                 p[f"MLP_{mi}"] = _mlp_init(rng, n_in, [d] * (L - 1) + [dh]); mi += 1    # phi_h
             if cfg.decouple_pos_vel_updates:
                 p[f"MLP_{mi}"] = _mlp_init(rng, n_in, [d] * (L - 1) + [1]); mi += 1     # phi_xx
             if dh == 0:
-                F = 6 + d                                                               # returns [x', v, m_i] (:196)
+                F = 6 + d + G_                                                          # returns [x', v, concats] (:196)
     if cfg.task == "graph":
-        w = [cfg.mlp_readout_widths[0] * F] + [x * d for x in cfg.mlp_readout_widths[1:]] + [cfg.n_outputs]
-        p[f"MLP_{mi}"] = _mlp_init(rng, F, w)
+        n_pool = F + G_
+        if G_ > 0:
+            p["LayerNorm_0"] = {"scale": np.ones((n_pool,)), "bias": np.zeros((n_pool,))}
+        w = [cfg.mlp_readout_widths[0] * n_pool] + [x * d for x in cfg.mlp_readout_widths[1:]] + [cfg.n_outputs]
+        p[f"MLP_{mi}"] = _mlp_init(rng, n_pool, w)
     return p
 
 
@@ -112,6 +116,9 @@ def apply_single(params, cfg: EGNNConfig, graph: GraphsTuple):
         cell = torch.as_tensor(pbc.cell, dtype=dtype)
         cell_inv = torch.as_tensor(pbc.cell_inv, dtype=dtype)
     wrap = (lambda a: a - torch.round(a @ cell_inv) @ cell) if pbc is not None else (lambda a: a)
+    glob = None if graph.globals is None else torch.as_tensor(graph.globals, dtype=dtype).reshape(1, -1)   # :268-271
+    g_e = None if glob is None else glob.expand(senders.shape[0], -1)
+    g_n = None if glob is None else glob.expand(N, -1)
     mi = 0
     for s in range(cfg.message_passing_steps):
         vel, dh = _variant(cfg, nodes.shape[1])
@@ -125,6 +132,8 @@ def apply_single(params, cfg: EGNNConfig, graph: GraphsTuple):
             else d[:, None]
         if dh > 0:
             feats = torch.cat([feats, h[senders], h[receivers]], -1)
+        if g_e is not None:
+            feats = torch.cat([feats, g_e], -1)
         m = _mlp(params[f"MLP_{mi}"], feats, True); mi += 1
         phi_x = params[f"MLP_{mi}"]; mi += 1
         if cfg.soft_edges:
@@ -141,10 +150,13 @@ def apply_single(params, cfg: EGNNConfig, graph: GraphsTuple):
             if dh == 0:
                 nodes = x_p
             else:
-                h_p = h + _mlp(params[f"MLP_{mi}"], torch.cat([h, m_i], -1), False); mi += 1
+                c = torch.cat([h, m_i] + ([g_n] if g_n is not None else []), -1)
+                h_p = h + _mlp(params[f"MLP_{mi}"], c, False); mi += 1
                 nodes = torch.cat([x_p, h_p], -1)
         else:
             c = m_i if dh == 0 else h
+            if g_n is not None:
+                c = torch.cat([c, g_n], -1)
             v_p = _mlp(params[f"MLP_{mi}"], c, False) * v + agg_x; mi += 1
             if dh > 0:
                 h_p = h + _mlp(params[f"MLP_{mi}"], c, False); mi += 1
@@ -157,6 +169,11 @@ def apply_single(params, cfg: EGNNConfig, graph: GraphsTuple):
     if cfg.task == "node":
         return graph._replace(nodes=nodes)
     pooled = {"mean": nodes.mean(0), "sum": nodes.sum(0), "max": nodes.max(0).values}[cfg.readout_agg]
+    if glob is not None:                                                # :332-336
+        pooled = torch.cat([pooled, glob[0]])
+        mu = pooled.mean()
+        var = ((pooled - mu) ** 2).mean()
+        pooled = (pooled - mu) / torch.sqrt(var + 1e-6) * params["LayerNorm_0"]["scale"] + params["LayerNorm_0"]["bias"]
     return _mlp(params[f"MLP_{mi}"], pooled, False)
 
 
@@ -164,7 +181,7 @@ def apply_batched(params, cfg: EGNNConfig, graphs: GraphsTuple):
     outs = []
     for b in range(graphs.nodes.shape[0]):
         g = GraphsTuple(nodes=graphs.nodes[b], edges=None, receivers=graphs.receivers[b], senders=graphs.senders[b],
-                        globals=None, n_node=None, n_edge=None)
+                        globals=None if graphs.globals is None else graphs.globals[b], n_node=None, n_edge=None)
         outs.append(apply_single(params, cfg, g))
     if cfg.task == "node":
         return graphs._replace(nodes=torch.stack([o.nodes for o in outs]))

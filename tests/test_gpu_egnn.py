@@ -34,7 +34,7 @@ def _leaves(tree, pre=()):
             yield pre + (k,), v
 
 
-def _run(kw, B=2, N=256, k=8, pbc=False, seed=0, F=3):
+def _run(kw, B=2, N=256, k=8, pbc=False, seed=0, F=3, n_glob=0):
     from eqnn_jax_b200 import graph_utils as GU
     from eqnn_jax_b200.egnn import EGNN
     rng = np.random.default_rng(seed)
@@ -46,16 +46,18 @@ def _run(kw, B=2, N=256, k=8, pbc=False, seed=0, F=3):
     cell = np.eye(3, dtype=np.float32) * 3.4
     opbc = G.get_apply_pbc(cell=cell) if pbc else None
     gpbc = GU.get_apply_pbc(cell=cell) if pbc else None
-    g = G.build_graph(x, None, k, apply_pbc=opbc)
+    glob = rng.normal(size=(B, n_glob)).astype(np.float32) if n_glob else None
+    g = G.build_graph(x, glob, k, apply_pbc=opbc)
     cfg = EG.EGNNConfig(**kw, apply_pbc=opbc)
-    tree = EG.init_params(cfg, F, seed=seed + 1)
+    tree = EG.init_params(cfg, F, seed=seed + 1, n_globals=n_glob)
     # make the coordinate updates O(1e-3..1e-2) instead of O(1e-4) so that every path carries signal, without
     # turning the layer stack into a chaotic map (large moves amplify fp32 rounding through the Bessel phase)
     for s in range(cfg.message_passing_steps):
         tree[f"Dense_{s}"]["kernel"] = tree[f"Dense_{s}"]["kernel"] * (4.0 if cfg.message_passing_agg == "mean" else 0.5)
     model = EGNN(**kw, apply_pbc=gpbc)
     gg = GU.GraphsTuple(nodes=torch.tensor(x).cuda(), edges=None, receivers=torch.tensor(g.receivers).cuda(),
-                        senders=torch.tensor(g.senders).cuda(), globals=None, n_node=None, n_edge=None)
+                        senders=torch.tensor(g.senders).cuda(), globals=None if glob is None else torch.tensor(glob).cuda(),
+                        n_node=None, n_edge=None)
     params = model.init(0, gg)
     params.load_tree(tree)
     p = NQ.to_torch(tree, torch.float64, requires_grad=True)
@@ -116,32 +118,39 @@ def test_egnn_forward_and_gradients(kw, pbc):
 XVH = dict(positions_only=False, n_layers=3, r_max=0.6, message_passing_steps=2, n_outputs=2)
 
 
-@pytest.mark.parametrize("kw,pbc,F", [
+@pytest.mark.parametrize("kw,pbc,F,n_glob", [
+    # graph globals (TPCF vector, train_cosmology.py --use_tpcf): broadcast to edges and nodes, LayerNorm read-out
+    (dict(positions_only=True, soft_edges=False, n_layers=3, d_hidden=128, n_radial_basis=32, r_max=0.6,
+          message_passing_steps=2, message_passing_agg="mean", task="graph", n_outputs=2), True, 3, 10),
+    (dict(XVH, positions_only=True, soft_edges=True, d_hidden=32, n_radial_basis=8, message_passing_agg="mean",
+          task="graph"), False, 6, 4),
+    (dict(XVH, soft_edges=False, decouple_pos_vel_updates=True, d_hidden=32, n_radial_basis=8,
+          message_passing_agg="sum", task="graph"), False, 8, 5),
     (dict(XVH, soft_edges=True, tanh_out=True, decouple_pos_vel_updates=True, d_hidden=32, n_radial_basis=16,
-          message_passing_agg="mean", task="node", message_passing_steps=3), False, 7),   # tests/test_equivariance.py:224-250
+          message_passing_agg="mean", task="node", message_passing_steps=3), False, 7, 0),   # tests/test_equivariance.py:224-250
     (dict(XVH, soft_edges=False, decouple_pos_vel_updates=False, d_hidden=128, n_radial_basis=32,
-          message_passing_agg="mean", task="graph"), True, 9),                            # tensor-core edge MLPs
+          message_passing_agg="mean", task="graph"), True, 9, 0),                            # tensor-core edge MLPs
     (dict(XVH, soft_edges=True, tanh_out=True, decouple_pos_vel_updates=True, d_hidden=64, n_radial_basis=0,
-          message_passing_agg="sum", task="graph"), False, 8),
+          message_passing_agg="sum", task="graph"), False, 8, 0),
     # (x, h): train_cosmology.py --feats all with EGNN_PARAMS (positions_only=True, velocities as scalars)
     (dict(XVH, positions_only=True, soft_edges=False, d_hidden=128, n_radial_basis=32, message_passing_agg="mean",
-          task="graph"), True, 6),
+          task="graph"), True, 6, 0),
     (dict(XVH, positions_only=True, soft_edges=True, tanh_out=True, d_hidden=32, n_radial_basis=8,
-          message_passing_agg="sum", task="node", message_passing_steps=3), False, 5),
+          message_passing_agg="sum", task="node", message_passing_steps=3), False, 5, 0),
     # (x, v): train_cosmology.py --feats all with positions_only=False; the node width grows to 6 + d_hidden (egnn.py:196)
     (dict(XVH, soft_edges=False, decouple_pos_vel_updates=True, d_hidden=32, n_radial_basis=8,
-          message_passing_agg="mean", task="node", message_passing_steps=3), False, 6),
+          message_passing_agg="mean", task="node", message_passing_steps=3), False, 6, 0),
     (dict(XVH, soft_edges=True, tanh_out=True, decouple_pos_vel_updates=False, d_hidden=64, n_radial_basis=16,
-          message_passing_agg="sum", task="graph"), True, 6),
+          message_passing_agg="sum", task="graph"), True, 6, 0),
 ])
-def test_egnn_xvh_forward_and_gradients(kw, pbc, F):
+def test_egnn_xvh_forward_and_gradients(kw, pbc, F, n_glob):
     """(x, v, h) node layout, egnn.py:47-60 and :198-229; (x, h) layout, :42-46 and :152-166."""
-    got, want, params, p, x, p32 = _run(kw, pbc=pbc, F=F, seed=3)
+    got, want, params, p, x, p32 = _run(kw, pbc=pbc, F=F, seed=3, n_glob=n_glob)
     got = got.cpu().numpy()
     if kw["task"] == "node":
         _close(got, want, "nodes")
         _close(got[..., :3] - x[..., :3], want[..., :3] - x[..., :3], "coordinate update", rtol=1e-3)
-        if not kw["positions_only"]:
+        if not kw.get("positions_only", False):
             assert np.array_equal(got[..., 3:6], x[..., 3:6])                  # the old velocity is returned (:229)
     else:
         _close(got, want, "output")
