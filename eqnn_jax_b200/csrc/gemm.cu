@@ -371,6 +371,30 @@ __global__ void skinny_wgrad_reduce_kernel(const GemmP p, int n_parts, const flo
   *c = p.accumulate ? *c + p.alpha * s : p.alpha * s;
 }
 
+
+//   tiny:   problems with a few rows or a short reduction (the B-row read-out MLPs and their weight gradients):
+//           one thread per output element, threads along n so that B(k, n) is read coalesced; prologue and
+//           epilogue as in the tiled kernel
+__global__ void __launch_bounds__(256) tiny_gemm_kernel(const GemmP p) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= p.M * p.N) return;
+  const int64_t m = i / p.N, n = i - m * p.N;
+  const float* a = p.A + m * p.sam;
+  const float* b = p.B + n * p.sbn;
+  float acc0 = 0.f, acc1 = 0.f;
+  int64_t k = 0;
+  for (; k + 1 < p.K; k += 2) {
+    acc0 = fmaf(apply_pro(a[k * p.sak], p.pro, p.pro_scale), b[k * p.sbk], acc0);
+    acc1 = fmaf(apply_pro(a[(k + 1) * p.sak], p.pro, p.pro_scale), b[(k + 1) * p.sbk], acc1);
+  }
+  if (k < p.K) acc0 = fmaf(apply_pro(a[k * p.sak], p.pro, p.pro_scale), b[k * p.sbk], acc0);
+  store_out(p, m, n, p.alpha * (acc0 + acc1));
+}
+
+inline bool tiny_ok(int64_t M, int64_t N, int64_t K) {
+  return K <= 2048 && (M <= 64 || K <= 64) && M * N <= (int64_t)1 << 18 && M * N * K <= (int64_t)1 << 25;
+}
+
 inline bool skinny_rows_ok(int64_t M, int64_t N, int64_t K, int pro, int epi) {
   return pro == 0 && epi == 0 && M >= 4096 && K >= 1 && K <= 32 && N <= 32;
 }
@@ -465,6 +489,11 @@ extern "C" int eqnn_gemm_f32(int64_t M, int64_t N, int64_t K, float alpha, const
   p.pro = pro; p.pro_scale = pro_scale;
   p.epi = epi; p.aux = aux; p.ld_aux = ld_aux; p.epi_scale = epi_scale;
   cudaStream_t st = as_stream(stream);
+  if (tiny_ok(M, N, K)) {
+    tiny_gemm_kernel<<<(unsigned)ceil_div64(M * N, 256), 256, 0, st>>>(p);
+    EQNN_CHECK_LAUNCH();
+    return EQNN_OK;
+  }
   if (skinny_rows_ok(M, N, K, pro, epi)) {
     const unsigned grid = (unsigned)ceil_div64(M, 256);
     if (N <= 8) skinny_rows_kernel<8><<<grid, 256, 0, st>>>(p);
