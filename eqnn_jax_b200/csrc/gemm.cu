@@ -403,7 +403,7 @@ inline bool skinny_wgrad_ok(int64_t M, int64_t N, int64_t K, int pro, int epi) {
 }
 inline int skinny_wgrad_parts(int64_t K) {
   const int64_t want = ceil_div64(K, 4 * SKW_ROWS);
-  return (int)(want < 1184 ? want : 1184);
+  return (int)(want < 296 ? want : 296);
 }
 
 SplitPlan plan_split(int64_t M, int64_t N, int64_t K, int bm, int bn) {
