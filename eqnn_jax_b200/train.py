@@ -19,7 +19,11 @@ import torch.distributed as dist
 
 from . import graph_utils as GU
 from . import ops
+from .egnn import EGNN
+from .equivariant_graph_utils import get_equivariant_graph
+from .irreps import Irreps
 from .nequip import IrrepsArray, NequIP, NequIPParams
+from .segnn import SEGNN
 
 
 def cosine_decay_lr(step: int, init_value: float, decay_steps: int, alpha: float = 0.0) -> float:
@@ -30,7 +34,7 @@ def cosine_decay_lr(step: int, init_value: float, decay_steps: int, alpha: float
 
 @dataclasses.dataclass
 class TrainState:
-    model: NequIP
+    model: object                        # NequIP, EGNN or SEGNN (GraphWrapper of train_cosmology.py:136-212)
     params: NequIPParams
     learning_rate: float = 3e-4          # train_cosmology.py:645
     weight_decay: float = 1e-5           # :646
@@ -76,19 +80,37 @@ def wrap_nodes(halos: torch.Tensor) -> IrrepsArray:
     return IrrepsArray("1o + 1o + 1x0e", halos.contiguous())
 
 
+def wrap_graph(model, halo_batch: torch.Tensor, senders, receivers, k: int, apply_pbc=None, globals_=None,
+               n_radial_basis: int = 64, r_max: float = 0.6):
+    """``GraphWrapper.__call__`` of train_cosmology.py:143-212: the model-specific view of one batch of clouds."""
+    B, N = halo_batch.shape[:2]
+    n_node = torch.full((B, 1), N, dtype=torch.int32)
+    n_edge = torch.full((B, 1), k, dtype=torch.int32)
+    if isinstance(model, NequIP):                            # :192-208
+        return GU.GraphsTuple(nodes=wrap_nodes(halo_batch), edges=None, receivers=receivers, senders=senders,
+                              globals=globals_, n_node=n_node, n_edge=n_edge)
+    if isinstance(model, EGNN):                              # :150-151 (the model carries apply_pbc, :403-408)
+        return GU.GraphsTuple(nodes=halo_batch.contiguous(), edges=None, receivers=receivers, senders=senders,
+                              globals=globals_, n_node=n_node, n_edge=n_edge)
+    if isinstance(model, SEGNN):                             # :163-190
+        nodes = IrrepsArray(Irreps("1o" if halo_batch.shape[-1] == 3 else "1o + 1o"), halo_batch.contiguous())
+        return get_equivariant_graph(nodes, halo_batch[..., :3].contiguous(), None, senders, receivers, n_node, n_edge, None,
+                                     globals_, model.l_max_hidden, steerable_velocities=False, apply_pbc=apply_pbc,
+                                     n_radial_basis=n_radial_basis, r_max=r_max)
+    raise TypeError(f"no B200 path for model type {type(model).__name__}")
+
+
 def train_step(state: TrainState, halo_batch: torch.Tensor, y_batch: torch.Tensor, k: int,
-               apply_pbc: Optional[GU.ApplyPBC] = None, world_size: int = 1) -> torch.Tensor:
+               apply_pbc: Optional[GU.ApplyPBC] = None, world_size: int = 1, globals_=None) -> torch.Tensor:
     """One optimisation step on this rank's shard; returns the (device) mean loss over all ranks."""
     model, params = state.model, state.params
     n = params.flat.numel()
     # build_graph (train_cosmology.py:226-235) also expands |dr| in a Bessel basis into graph.edges, which the
-    # NequIP wrapper discards (edges=None, :201-208); under jax.jit XLA removes that dead computation, so only
+    # model wrappers discard (edges=None, :201-208); under jax.jit XLA removes that dead computation, so only
     # the neighbour search is run here.
-    B, N = halo_batch.shape[:2]
     senders, receivers, _ = ops.knn_pbc(halo_batch, k, None if apply_pbc is None else apply_pbc.cell,
                                         None if apply_pbc is None else apply_pbc.cell_inv, want_dr=False)
-    g = GU.GraphsTuple(nodes=wrap_nodes(halo_batch), edges=None, receivers=receivers, senders=senders, globals=None,
-                       n_node=torch.full((B, 1), N, dtype=torch.int32), n_edge=torch.full((B, 1), k, dtype=torch.int32))
+    g = wrap_graph(model, halo_batch, senders, receivers, k, apply_pbc, globals_)
     loss_slot = state.bucket[n:]
 
     def grad_fn(out: torch.Tensor) -> torch.Tensor:
