@@ -376,23 +376,24 @@ __global__ void skinny_wgrad_reduce_kernel(const GemmP p, int n_parts, const flo
 //           one thread per output element, threads along n so that B(k, n) is read coalesced; prologue and
 //           epilogue as in the tiled kernel
 __global__ void __launch_bounds__(256) tiny_gemm_kernel(const GemmP p) {
-  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  // one warp per output element: the 32 lanes split the reduction (these problems have few outputs and a
+  // reduction of up to a few hundred terms, so a thread per output would be a chain of dependent loads)
+  const int lane = threadIdx.x & 31;
+  const int64_t i = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5;
   if (i >= p.M * p.N) return;
   const int64_t m = i / p.N, n = i - m * p.N;
   const float* a = p.A + m * p.sam;
   const float* b = p.B + n * p.sbn;
-  float acc0 = 0.f, acc1 = 0.f;
-  int64_t k = 0;
-  for (; k + 1 < p.K; k += 2) {
-    acc0 = fmaf(apply_pro(a[k * p.sak], p.pro, p.pro_scale), b[k * p.sbk], acc0);
-    acc1 = fmaf(apply_pro(a[(k + 1) * p.sak], p.pro, p.pro_scale), b[(k + 1) * p.sbk], acc1);
-  }
-  if (k < p.K) acc0 = fmaf(apply_pro(a[k * p.sak], p.pro, p.pro_scale), b[k * p.sbk], acc0);
-  store_out(p, m, n, p.alpha * (acc0 + acc1));
+  float acc = 0.f;
+  for (int64_t k = lane; k < p.K; k += 32)
+    acc = fmaf(apply_pro(a[k * p.sak], p.pro, p.pro_scale), b[k * p.sbk], acc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) store_out(p, m, n, p.alpha * acc);
 }
 
 inline bool tiny_ok(int64_t M, int64_t N, int64_t K) {
-  return K <= 2048 && (M <= 64 || K <= 64) && M * N <= (int64_t)1 << 18 && M * N * K <= (int64_t)1 << 25;
+  return K <= 2048 && (M <= 64 || K <= 64) && M * N <= (int64_t)1 << 17 && M * N * K <= (int64_t)1 << 25;
 }
 
 inline bool skinny_rows_ok(int64_t M, int64_t N, int64_t K, int pro, int epi) {
@@ -490,7 +491,7 @@ extern "C" int eqnn_gemm_f32(int64_t M, int64_t N, int64_t K, float alpha, const
   p.epi = epi; p.aux = aux; p.ld_aux = ld_aux; p.epi_scale = epi_scale;
   cudaStream_t st = as_stream(stream);
   if (tiny_ok(M, N, K)) {
-    tiny_gemm_kernel<<<(unsigned)ceil_div64(M * N, 256), 256, 0, st>>>(p);
+    tiny_gemm_kernel<<<(unsigned)ceil_div64(M * N * 32, 256), 256, 0, st>>>(p);
     EQNN_CHECK_LAUNCH();
     return EQNN_OK;
   }
