@@ -55,6 +55,7 @@ SIGNATURES: Dict[str, tuple] = {
     "eqnn_egnn_sender_acc": (_i, [_p, _p, _p, _i, _p, _p]),
     "eqnn_segnn_ycontract": (_i, [_p, _p, _i, _p, _i, _i, _i64, _i, _i, _p, _p]),
     "eqnn_segnn_yexpand": (_i, [_p, _p, _i, _i64, _i, _i, _p, _p]),
+    "eqnn_segnn_cg_apply": (_i, [_p, _i, _i, _p, _i, _i, _p, _p, _p, _p, _i, _i, _i64, _i, _p, _i, _p]),
     "eqnn_gather_rows": (_i, [_p, _p, _i64, _i, _p, _p]),
     "eqnn_axpy": (_i, [_i64, _f, _p, _p, _p]),
     "eqnn_steerable_attrs": (_i, [_p, _i, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p]),

@@ -556,6 +556,39 @@ __global__ void segnn_yexpand_kernel(const float* __restrict__ dz, const float* 
   dXbig[i] = (y ? y[r * ld_y + j] : 1.f) * dz[r * Do + o];
 }
 
+// Irrep-blocked TensorProductLinearGate: out[r, o] = bias + sum_t coef[t] * y[r, idx[t] >> 24] * in[r, idx[t] & 0xFFFFFF]
+// over the CSR range ptr[o] .. ptr[o+1] (Clebsch-Gordan terms).  One warp per row: the input row and the attribute row
+// are staged in shared memory, each lane owns the outputs o = lane, lane + 32, ...  The same kernel runs the forward
+// (in = T, table sorted by Linear output) and the backward (in = dz, table sorted by T column).
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+segnn_cg_kernel(const float* __restrict__ in, int ld_in, int n_in, const float* __restrict__ y, int ld_y, int Dy,
+                const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx, const float* __restrict__ coef,
+                const float* __restrict__ bias, int bias_col, int n_bias, int64_t R, int n_out,
+                float* __restrict__ out, int ld_out) {
+  extern __shared__ float cg_sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* row = cg_sm + (size_t)warp * (n_in + 32);
+  float* yr = row + n_in;
+  for (int64_t r = (int64_t)blockIdx.x * WARPS + warp; r < R; r += (int64_t)gridDim.x * WARPS) {
+    const float* src = in + (size_t)r * ld_in;
+    for (int c = lane; c < n_in; c += 32) row[c] = __ldg(src + c);
+    if (lane < Dy) yr[lane] = y ? __ldg(y + (size_t)r * ld_y + lane) : 1.f;
+    __syncwarp();
+    float* dst = out + (size_t)r * ld_out;
+    for (int o = lane; o < n_out; o += 32) {
+      float acc = (bias != nullptr && o >= bias_col && o < bias_col + n_bias) ? __ldg(bias + (o - bias_col)) : 0.f;
+      const int t1 = __ldg(ptr + o + 1);
+      for (int t = __ldg(ptr + o); t < t1; ++t) {
+        const int q = __ldg(idx + t);
+        acc = fmaf(__ldg(coef + t) * yr[q >> 24], row[q & 0xFFFFFF], acc);
+      }
+      dst[o] = acc;
+    }
+    __syncwarp();
+  }
+}
+
 // dst[p, :] = src[perm[p], :]
 __global__ void gather_rows_kernel(const float* __restrict__ src, const int32_t* __restrict__ perm, int64_t n, int w,
                                    float* __restrict__ dst) {
@@ -764,6 +797,28 @@ extern "C" int eqnn_segnn_yexpand(const float* dz, const float* y, int ld_y, int
   EQNN_CHECK_ARG(dz && dXbig && Dy >= 1 && Do >= 1 && (y || Dy == 1) && (!y || ld_y >= Dy), "segnn_yexpand: bad argument");
   if (R <= 0) return EQNN_OK;
   segnn_yexpand_kernel<<<(unsigned)ceil_div64(R * Dy * Do, 256), 256, 0, as_stream(stream)>>>(dz, y, ld_y, R, Dy, Do, dXbig);
+  EQNN_CHECK_LAUNCH();
+  return EQNN_OK;
+}
+
+extern "C" int eqnn_segnn_cg_apply(const float* in, int ld_in, int n_in, const float* y, int ld_y, int Dy,
+                                   const int32_t* ptr, const int32_t* idx, const float* coef, const float* bias,
+                                   int bias_col, int n_bias, int64_t R, int n_out, float* out, int ld_out,
+                                   eqnn_stream_t stream) {
+  EQNN_CHECK_ARG(in && ptr && idx && coef && out && n_in >= 1 && n_in < (1 << 24) && ld_in >= n_in && n_out >= 1 &&
+                     ld_out >= n_out && Dy >= 1 && Dy <= 32 && (y || Dy == 1) && (!y || ld_y >= Dy) && n_bias >= 0 &&
+                     bias_col >= 0 && bias_col + n_bias <= n_out,
+                 "segnn_cg_apply: bad argument");
+  if (R <= 0) return EQNN_OK;
+  constexpr int WARPS = 8;
+  const size_t smem = (size_t)WARPS * (n_in + 32) * sizeof(float);
+  EQNN_CHECK_ARG(smem <= 200 * 1024, "segnn_cg_apply: input row too wide for shared memory");
+  if (smem > 48 * 1024)
+    EQNN_CUDA(cudaFuncSetAttribute(segnn_cg_kernel<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t want = ceil_div64(R, WARPS);
+  const unsigned grid = (unsigned)(want < 148 * 8 ? want : 148 * 8);
+  segnn_cg_kernel<WARPS><<<grid, WARPS * 32, smem, as_stream(stream)>>>(in, ld_in, n_in, y, ld_y, Dy, ptr, idx, coef, bias,
+                                                                         bias_col, n_bias, R, n_out, out, ld_out);
   EQNN_CHECK_LAUNCH();
   return EQNN_OK;
 }

@@ -308,6 +308,18 @@ def segnn_yexpand(dz, y, ld_y, R, Dy, Do, dXbig, dz_off=0, y_off=0):
                                    _stream()), "segnn_yexpand")
 
 
+def segnn_cg_apply(inp, ld_in, n_in, y, ld_y, Dy, ptr, idx, coef, bias_buf, bias_off, bias_col, n_bias, R, n_out, out,
+                   ld_out, in_off=0, y_off=0, out_off=0, ptr_off=0):
+    """out[r, o] = bias + sum_t coef[t] y[r, idx[t] >> 24] in[r, idx[t] & 0xFFFFFF] over ptr[o] .. ptr[o+1]."""
+    t0 = TIMER.begin() if TIMER else None
+    check(lib().eqnn_segnn_cg_apply(_off(inp, in_off), ld_in, n_in, None if y is None else _off(y, y_off), ld_y, Dy,
+                                    _off(ptr, ptr_off), _ptr(idx), _ptr(coef),
+                                    None if bias_buf is None else _off(bias_buf, bias_off), bias_col, n_bias, R, n_out,
+                                    _off(out, out_off), ld_out, _stream()), "segnn_cg_apply")
+    if TIMER:
+        TIMER.end("segnn_cg", t0)
+
+
 def gather_rows(src, perm, width):
     n = perm.numel()
     dst = torch.empty((n, width), dtype=_F32, device=src.device)

@@ -105,6 +105,9 @@ class _TPLG:
         self.D_out = self.d_g if activation else self.Do
         if not live:
             return
+        if owner.lowering == "blocked":
+            self._lower_blocked(owner, x_irreps, xin, in_map, x_off, paths, lin, out_off)
+            return
         # dense lowering: M_cat[x column, j * Do + o]
         self.M_off = owner.new_dense(self.Dx * self.Dy * self.Do)
         ncols = self.Dy * self.Do
@@ -132,9 +135,88 @@ class _TPLG:
             owner.add_entries(np.broadcast_to(dst, val.shape).ravel(), np.broadcast_to(par, val.shape).ravel(), val.ravel())
 
 
+    def _lower_blocked(self, owner, x_irreps, xin, in_map, x_off, paths, lin, out_off):
+        """Irrep-blocked lowering: the multiplicity contraction first, T[(path, w, m1)] = sum_u x[(u, m1)] W_path[u, w]
+        (one GEMM per run of stored x columns of one irrep type; ``runs``), then the Clebsch-Gordan terms
+        z[(w, m3)] += sqrt(2 l3 + 1) C[m1, m2, m3] y[m2] T[(path, w, m1)] from CSR tables (``cg_f`` by Linear output
+        for the forward, ``cg_b`` by T column for the backward)."""
+        row_in_chunk: Dict[Tuple[int, int], int] = {}
+        kept, DT = [], 0
+        for (i1, l2, l3, p3, m1) in paths:
+            key = (l3, p3)
+            r0 = row_in_chunk.get(key, 0)
+            row_in_chunk[key] = r0 + m1
+            i_out = next((i for i, (_, lo, po) in enumerate(lin) if (lo, po) == key), None)
+            if i_out is None:
+                continue
+            l1 = xin[i1][1]
+            cg = so3.real_cg(l1, l2, l3) * math.sqrt(2 * l3 + 1)
+            if not np.any(cg):
+                continue
+            mo = lin[i_out][0]
+            kept.append(dict(i1=i1, l1=l1, l2=l2, l3=l3, i_out=i_out, r0=r0, mo=mo, toff=DT, cg=cg))
+            DT += mo * (2 * l1 + 1)
+        self.DT = DT
+        t_lo = {i1: min(k["toff"] for k in kept if k["i1"] == i1) for i1 in {k["i1"] for k in kept}}
+        t_hi = {i1: max(k["toff"] + k["mo"] * (2 * k["l1"] + 1) for k in kept if k["i1"] == i1) for i1 in t_lo}
+        # runs of stored x columns of one irrep type
+        inv = np.empty((self.Dx,), dtype=np.int64)
+        inv[np.asarray(in_map, dtype=np.int64)] = np.arange(self.Dx)
+        type_of = {(l, p): i for i, (_, l, p) in enumerate(xin)}
+        stored, c = [], 0
+        for (m, l, p) in x_irreps:
+            w = m * (2 * l + 1)
+            if w:
+                if stored and stored[-1][0] == (l, p) and stored[-1][1] + stored[-1][2] == c:
+                    stored[-1][2] += w
+                else:
+                    stored.append([(l, p), c, w])
+            c += w
+        self.runs, seen, covered = [], set(), 0
+        for (l, p), c0, K in stored:
+            i1 = type_of[(l, p)]
+            if i1 not in t_lo:
+                continue                                          # no path from this irrep type reaches the Linear
+            d1 = 2 * l + 1
+            Nr = t_hi[i1] - t_lo[i1]
+            W_off = owner.new_dense(K * Nr)
+            comp = inv[c0:c0 + K] - x_off[i1]
+            u, m1 = comp // d1, comp % d1
+            for k in (k for k in kept if k["i1"] == i1):
+                wv = np.arange(k["mo"])[None, :]
+                dst = W_off + np.arange(K)[:, None] * Nr + (k["toff"] - t_lo[i1]) + wv * d1 + m1[:, None]
+                par = self.w_off[k["i_out"]] + (k["r0"] + u[:, None]) * k["mo"] + wv
+                owner.add_entries(dst.ravel(), par.ravel(), np.ones(dst.size))
+            self.runs.append((c0, K, t_lo[i1], Nr, W_off, i1 in seen))      # last: accumulate into T
+            seen.add(i1)
+            covered += K
+        self.dx_full = covered == self.Dx                         # else: uncovered dx columns are exact zeros
+        # Clebsch-Gordan terms
+        o_l, t_l, j_l, c_l = [], [], [], []
+        for k in kept:
+            a, b, cc = np.nonzero(k["cg"])
+            d1, d3 = 2 * k["l1"] + 1, 2 * k["l3"] + 1
+            wv = np.arange(k["mo"])[:, None]
+            o_l.append((out_off[k["i_out"]] + wv * d3 + cc[None, :]).ravel())
+            t_l.append((k["toff"] + wv * d1 + a[None, :]).ravel())
+            j_l.append(np.broadcast_to(k["l2"] ** 2 + b[None, :], (k["mo"], a.size)).ravel())
+            c_l.append(np.broadcast_to(k["cg"][a, b, cc][None, :], (k["mo"], a.size)).ravel())
+        o_a, t_a, j_a, c_a = (np.concatenate(v) for v in (o_l, t_l, j_l, c_l))
+        self.cg_f = owner.add_cg(o_a, t_a, j_a, c_a, self.Do)     # rows: Linear outputs, sources: T columns
+        self.cg_b = owner.add_cg(t_a, o_a, j_a, c_a, DT)          # rows: T columns, sources: Linear outputs
+
+
 class _Plan:
     def __init__(self, cfg: "SEGNN", irreps_in: Irreps, lmax_attr: int, n_add: int, n_globals: int = 0):
         self.n_globals = int(n_globals)
+        self.lowering = cfg.lowering
+        if self.lowering not in ("blocked", "dense"):
+            raise ValueError(f"lowering must be 'blocked' or 'dense', not {cfg.lowering!r}")
+        self._cg_ptr: List[np.ndarray] = []
+        self._cg_idx: List[np.ndarray] = []
+        self._cg_coef: List[np.ndarray] = []
+        self._n_cg_ptr = 0
+        self._n_cg = 0
         self.layout: List[Tuple[Tuple[str, ...], Tuple[int, ...], int]] = []
         self._n_params = 0
         self._n_exp = 0
@@ -220,6 +302,19 @@ class _Plan:
         self._n_exp += n
         return off
 
+    def add_cg(self, rows, src, j, coef, n_rows: int) -> int:
+        """Append one CSR table (sorted by row, stable) to the plan's Clebsch-Gordan tables; returns its ptr offset."""
+        order = np.argsort(rows, kind="stable")
+        counts = np.bincount(rows, minlength=n_rows)
+        ptr = self._n_cg + np.concatenate([[0], np.cumsum(counts)])
+        off = self._n_cg_ptr
+        self._cg_ptr.append(ptr.astype(np.int32))
+        self._cg_idx.append((src[order].astype(np.int64) | (j[order].astype(np.int64) << 24)).astype(np.int32))
+        self._cg_coef.append(coef[order].astype(np.float32))
+        self._n_cg_ptr += n_rows + 1
+        self._n_cg += rows.size
+        return off
+
     def add_entries(self, dst, par, val):
         self._dst.append(np.asarray(dst, dtype=np.int64))
         self._par.append(np.asarray(par, dtype=np.int64))
@@ -241,8 +336,11 @@ class _Plan:
         ptr = np.concatenate([start, [ps.size]]).astype(np.int32)
         self._np = dict(exp_idx=idx, exp_scale=scale, con_pidx=pidx.astype(np.int32), con_ptr=ptr,
                         con_tidx=dst[order].astype(np.int32), con_scale=val[order].astype(np.float32))
+        cat = lambda parts, dt: np.concatenate(parts).astype(dt) if parts else np.zeros((1,), dt)
+        self._np.update(cg_ptr=cat(self._cg_ptr, np.int32), cg_idx=cat(self._cg_idx, np.int32),
+                        cg_coef=cat(self._cg_coef, np.float32))
         self._dev: Dict[str, Dict[str, torch.Tensor]] = {}
-        del self._dst, self._par, self._val
+        del self._dst, self._par, self._val, self._cg_ptr, self._cg_idx, self._cg_coef
 
     def device_tables(self, device):
         key = str(device)
@@ -271,6 +369,10 @@ class SEGNN:
     l_max_hidden: int = 1
     hidden_irreps: Optional[Union[str, Irreps]] = None
     residual: bool = True
+    # not a reference field: "dense" = one GEMM on M_cat per layer; "blocked" = irrep-blocked lowering (multiplicity
+    # GEMMs per stored irrep block + Clebsch-Gordan table kernel): 4x fewer FLOPs, but its K <= 89 GEMMs run at
+    # 4-10 TFLOP/s on the CUDA-core kernel, so it is 14 % slower end to end today
+    lowering: str = "dense"
 
     def __post_init__(self):
         self._plans: Dict = {}
@@ -371,14 +473,25 @@ class SEGNN:
         dev = theta.device
         f32 = dict(dtype=torch.float32, device=dev)
         z = torch.empty((R, t.Do), **f32)
-        nc = t.Dy * t.Do
         blk = min(R, ROW_BLOCK)
-        Xbig = torch.empty((blk, nc), **f32)
-        for r0 in range(0, R, blk):
-            n = min(blk, R - r0)
-            _mm(n, nc, t.Dx, 1.0, x, r0 * ldx, ldx, wexp, t.M_off, nc, Xbig, 0, nc, tag="segnn_gemm")
-            ops.segnn_ycontract(Xbig, y if t.has_y else None, t.Dy, theta if t.n_bias else None, t.b_off or 0, t.b_col,
-                                t.n_bias, n, t.Dy, t.Do, z, y_off=r0 * t.Dy, z_off=r0 * t.Do)
+        if plan.lowering == "blocked":
+            tab = plan.device_tables(dev)
+            T = torch.empty((blk, t.DT), **f32)
+            for r0 in range(0, R, blk):
+                n = min(blk, R - r0)
+                for (c0, K, tb, Nr, W_off, acc) in t.runs:
+                    _mm(n, Nr, K, 1.0, x, r0 * ldx + c0, ldx, wexp, W_off, Nr, T, tb, t.DT, accumulate=acc, tag="segnn_gemm")
+                ops.segnn_cg_apply(T, t.DT, t.DT, y if t.has_y else None, t.Dy, t.Dy, tab["cg_ptr"], tab["cg_idx"],
+                                   tab["cg_coef"], theta if t.n_bias else None, t.b_off or 0, t.b_col, t.n_bias, n, t.Do,
+                                   z, t.Do, y_off=r0 * t.Dy, out_off=r0 * t.Do, ptr_off=t.cg_f)
+        else:
+            nc = t.Dy * t.Do
+            Xbig = torch.empty((blk, nc), **f32)
+            for r0 in range(0, R, blk):
+                n = min(blk, R - r0)
+                _mm(n, nc, t.Dx, 1.0, x, r0 * ldx, ldx, wexp, t.M_off, nc, Xbig, 0, nc, tag="segnn_gemm")
+                ops.segnn_ycontract(Xbig, y if t.has_y else None, t.Dy, theta if t.n_bias else None, t.b_off or 0, t.b_col,
+                                    t.n_bias, n, t.Dy, t.Do, z, y_off=r0 * t.Dy, z_off=r0 * t.Do)
         if not t.activation:
             return z, (x, ldx, y, z)
         g = torch.empty((R, t.d_g), **f32)
@@ -397,8 +510,26 @@ class SEGNN:
             tmp = torch.empty((t.Do,), **f32)
             ops.colsum_tall(dz, R, t.Do, tmp)
             gtheta[t.b_off:t.b_off + t.n_bias].copy_(tmp[t.b_col:t.b_col + t.n_bias])
-        nc = t.Dy * t.Do
         blk = min(R, ROW_BLOCK)
+        if plan.lowering == "blocked":
+            tab = plan.device_tables(dev)
+            dT = torch.empty((blk, t.DT), **f32)
+            dx = None
+            if need_dx:
+                dx = torch.empty((R, t.Dx), **f32) if t.dx_full else torch.zeros((R, t.Dx), **f32)
+            for r0 in range(0, R, blk):
+                n = min(blk, R - r0)
+                ops.segnn_cg_apply(dz, t.Do, t.Do, y if t.has_y else None, t.Dy, t.Dy, tab["cg_ptr"], tab["cg_idx"],
+                                   tab["cg_coef"], None, 0, 0, 0, n, t.DT, dT, t.DT, in_off=r0 * t.Do, y_off=r0 * t.Dy,
+                                   ptr_off=t.cg_b)
+                for (c0, K, tb, Nr, W_off, _) in t.runs:
+                    _mm(K, Nr, n, 1.0, x, r0 * ldx + c0, ldx, dT, tb, t.DT, gwexp, W_off, Nr, ta=True, accumulate=r0 > 0,
+                        tag="segnn_gemm")
+                    if need_dx:
+                        _mm(n, K, Nr, 1.0, dT, tb, t.DT, wexp, W_off, Nr, dx, r0 * t.Dx + c0, t.Dx, tb=True,
+                            tag="segnn_gemm")
+            return dx
+        nc = t.Dy * t.Do
         dXbig = torch.empty((blk, nc), **f32)
         dx = torch.empty((R, t.Dx), **f32) if need_dx else None
         for r0 in range(0, R, blk):

@@ -222,6 +222,16 @@ int eqnn_segnn_ycontract(const float* Xbig, const float* y, int ld_y, const floa
                          int64_t R, int Dy, int Do, float* z, eqnn_stream_t stream);
 int eqnn_segnn_yexpand(const float* dz, const float* y, int ld_y, int64_t R, int Dy, int Do, float* dXbig,
                        eqnn_stream_t stream);
+/* Irrep-blocked form of the same layer (the default of eqnn_jax_b200.segnn): the multiplicity contraction runs
+ * first, T[r, (path, w, m1)] = sum_u x[r, (u, m1)] W_path[u, w] (eqnn_gemm_f32 per stored irrep block of x), then
+ * the Clebsch-Gordan terms are applied from a CSR table (entries: idx = source column | attribute component << 24,
+ * coef = sqrt(2 l3 + 1) C[m1, m2, m3]):
+ *   out[r, o] = bias[o - bias_col] (0e block) + sum_{t in ptr[o] .. ptr[o+1]} coef[t] y[r, idx[t] >> 24] in[r, idx[t] & 0xFFFFFF]
+ * forward: in = T, rows of the table = Linear outputs; backward: in = dz, rows = T columns (bias NULL).
+ * y NULL: Dy = 1, y = 1.  Dy <= 32, n_in < 2^24. */
+int eqnn_segnn_cg_apply(const float* in, int ld_in, int n_in, const float* y, int ld_y, int Dy, const int32_t* ptr,
+                        const int32_t* idx, const float* coef, const float* bias, int bias_col, int n_bias, int64_t R,
+                        int n_out, float* out, int ld_out, eqnn_stream_t stream);
 /* dst[p, :] = src[perm[p], :]  (per-edge arrays into receiver-sorted order);  y += a * x */
 int eqnn_gather_rows(const float* src, const int32_t* perm, int64_t n, int width, float* dst, eqnn_stream_t stream);
 int eqnn_axpy(int64_t n, float a, const float* x, float* y, eqnn_stream_t stream);

@@ -1,5 +1,5 @@
 """SEGNN (BASELINE.json configs[2] / SURVEY cfg-3) forward+backward throughput on synthetic 5000-node PBC clouds.
-   python scripts/bench_segnn.py [graphs_per_gpu] [lmax_attributes]  -> one JSON line (edges/s), CUDA events, 3 warm-ups."""
+   python scripts/bench_segnn.py [graphs_per_gpu] [lmax_attributes] [blocked|dense]  -> one JSON line (edges/s), CUDA events, 3 warm-ups."""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -12,13 +12,14 @@ from eqnn_jax_b200.segnn import SEGNN
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 LMAX_ATTR = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+LOWERING = sys.argv[3] if len(sys.argv) > 3 else "blocked"
 N, K = bench.N_NODES, bench.K_NN
 halos, _ = bench.synth_batch(0, B)
 x = torch.from_numpy(halos[..., :3].copy()).cuda()
 pbc = GU.get_apply_pbc(std=(bench.STD[:3] / bench.BOX).astype(np.float32))
 # train_velocities.py:364-378,454-458: d_hidden 128, 3 x 3, sum, node task -> 1x1o, l_max_hidden 2, |r| messages, PBC
 model = SEGNN(d_hidden=128, n_layers=3, message_passing_steps=3, message_passing_agg="sum", task="node", output_irreps="1x1o",
-              l_max_hidden=2, residual=True)
+              l_max_hidden=2, residual=True, lowering=LOWERING)
 target = torch.randn(B, N, 3, device="cuda")
 
 
@@ -46,5 +47,5 @@ ops.TIMER = ops.KernelTimer(); step(params); prof = ops.TIMER.summary(); ops.TIM
 E = B * N * K
 print(json.dumps({"metric": "SEGNN fwd+bwd edges/sec", "value": E / (ms * 1e-3), "unit": "edges/s", "ms_per_step": ms,
                   "config": {"workload": "SEGNN l_max_hidden 2, 3 steps x 3 layers, 5000-node kNN-20 PBC clouds (cfg-3)",
-                             "graphs_per_gpu": B, "lmax_attributes": LMAX_ATTR, "gemm": "fp32 CUDA-core, dense-lowered TPLG"},
+                             "graphs_per_gpu": B, "lmax_attributes": LMAX_ATTR, "gemm": f"fp32 CUDA-core, {LOWERING} TPLG lowering"},
                   "breakdown_ms": {k: t for k, (n, t) in sorted(prof.items())}, "params": params.num_params()}))

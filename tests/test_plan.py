@@ -205,9 +205,22 @@ def test_segnn_plan_parameters_match_oracle(kw, irr, lat, nadd):
         assert plan._n_params == 573253
 
 
-def test_segnn_dense_lowering_equals_oracle_tplg():
-    """(x (x) y) @ M_cat + b, with M_cat expanded on the host from the flat parameters, equals the oracle's
-    gate-less TensorProductLinearGate (Linear(TP(x, y)), segnn.py:48-54) -- the arithmetic the GPU path runs."""
+def _cg_rows(tab, ptr_off, n_rows, src, y):
+    """Host statement of eqnn_segnn_cg_apply: out[r, o] = sum_t coef[t] y[r, idx[t] >> 24] src[r, idx[t] & 0xFFFFFF]."""
+    out = np.zeros((src.shape[0], n_rows))
+    ptr = tab["cg_ptr"][ptr_off:ptr_off + n_rows + 1]
+    for o in range(n_rows):
+        for t in range(ptr[o], ptr[o + 1]):
+            q = int(tab["cg_idx"][t])
+            out[:, o] += float(tab["cg_coef"][t]) * y[:, q >> 24] * src[:, q & 0xFFFFFF]
+    return out
+
+
+@pytest.mark.parametrize("lowering", ["blocked", "dense"])
+def test_segnn_dense_lowering_equals_oracle_tplg(lowering):
+    """Linear(TP(x, y)) + b evaluated on the host from the plan's tables -- dense: (x (x) y) @ M_cat; blocked: per-run
+    multiplicity GEMMs into T, then the Clebsch-Gordan CSR table (and its transpose against the forward one) --
+    equals the oracle's gate-less TensorProductLinearGate (segnn.py:48-54): the arithmetic the GPU path runs."""
     import torch
     from eqnn_jax_b200.segnn import SEGNN, _Plan
     from eqnn_jax_b200.irreps import Irreps
@@ -217,7 +230,7 @@ def test_segnn_dense_lowering_equals_oracle_tplg():
     rng = np.random.default_rng(0)
     kw = dict(d_hidden=32, l_max_hidden=2, n_layers=2, message_passing_steps=1, task="node", output_irreps="1o+1x0e")
     irr, lat, nadd = "1o+2x0e", 2, 3
-    plan = _Plan(SEGNN(**kw), Irreps(irr), lat, nadd)
+    plan = _Plan(SEGNN(lowering=lowering, **kw), Irreps(irr), lat, nadd)
     tree = S.init_params(S.SEGNNConfig(**kw), irr, OI.spherical_harmonics(lat), f"{nadd}x0e", seed=3)
     theta = np.zeros((plan._n_params,))
     for path, shape, off in plan.layout:
@@ -233,8 +246,26 @@ def test_segnn_dense_lowering_equals_oracle_tplg():
         R = 5
         x = rng.normal(size=(R, t.Dx))
         y = spherical_harmonics(lat, rng.normal(size=(R, 3)), True, "integral") if t.has_y else np.ones((R, 1))
-        M = wexp[t.M_off:t.M_off + t.Dx * t.Dy * t.Do].reshape(t.Dx, t.Dy, t.Do)
-        z = np.einsum("ri,rj,ijo->ro", x, y, M)
+        if lowering == "dense":
+            M = wexp[t.M_off:t.M_off + t.Dx * t.Dy * t.Do].reshape(t.Dx, t.Dy, t.Do)
+            z = np.einsum("ri,rj,ijo->ro", x, y, M)
+        else:
+            T = np.zeros((R, t.DT))
+            first = set()
+            for (c0, K, tb, Nr, W_off, acc) in t.runs:
+                assert acc == (tb in first)
+                first.add(tb)
+                T[:, tb:tb + Nr] += x[:, c0:c0 + K] @ wexp[W_off:W_off + K * Nr].reshape(K, Nr)
+            z = _cg_rows(tab, t.cg_f, t.Do, T, y)
+            # the backward table is the transpose of the forward one: <dz, cg_f(T)> == <cg_b(dz), T>
+            dz = rng.normal(size=z.shape)
+            dT = _cg_rows(tab, t.cg_b, t.DT, dz, y)
+            np.testing.assert_allclose((dz * z).sum(), (dT * T).sum(), rtol=1e-10)
+            if not t.dx_full:
+                cov = np.zeros(t.Dx, bool)
+                for (c0, K, *_r) in t.runs:
+                    cov[c0:c0 + K] = True
+                assert not cov.all()
         if t.n_bias:
             z[:, t.b_col:t.b_col + t.n_bias] += theta[t.b_off:t.b_off + t.n_bias]
         # oracle: same parameters, x in its stored irreps layout
