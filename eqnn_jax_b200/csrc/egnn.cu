@@ -548,12 +548,15 @@ __global__ void segnn_ycontract_kernel(const float* __restrict__ Xbig, const flo
 
 __global__ void segnn_yexpand_kernel(const float* __restrict__ dz, const float* __restrict__ y, int ld_y, int64_t R,
                                      int Dy, int Do, float* __restrict__ dXbig) {
+  // one thread per (row, output): dz is read once and fans out to the Dy attribute blocks (coalesced along o)
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= R * Dy * Do) return;
-  const int64_t r = i / ((int64_t)Dy * Do);
-  const int rem = (int)(i - r * (int64_t)Dy * Do);
-  const int j = rem / Do, o = rem - j * Do;
-  dXbig[i] = (y ? y[r * ld_y + j] : 1.f) * dz[r * Do + o];
+  if (i >= R * Do) return;
+  const int64_t r = i / Do;
+  const int o = (int)(i - r * Do);
+  const float v = dz[i];
+  float* dst = dXbig + (size_t)r * Dy * Do + o;
+  const float* yr = y ? y + (size_t)r * ld_y : nullptr;
+  for (int j = 0; j < Dy; ++j) dst[(size_t)j * Do] = (yr ? __ldg(yr + j) : 1.f) * v;
 }
 
 // Irrep-blocked TensorProductLinearGate: out[r, o] = bias + sum_t coef[t] * y[r, idx[t] >> 24] * in[r, idx[t] & 0xFFFFFF]
@@ -796,7 +799,7 @@ extern "C" int eqnn_segnn_yexpand(const float* dz, const float* y, int ld_y, int
                                   eqnn_stream_t stream) {
   EQNN_CHECK_ARG(dz && dXbig && Dy >= 1 && Do >= 1 && (y || Dy == 1) && (!y || ld_y >= Dy), "segnn_yexpand: bad argument");
   if (R <= 0) return EQNN_OK;
-  segnn_yexpand_kernel<<<(unsigned)ceil_div64(R * Dy * Do, 256), 256, 0, as_stream(stream)>>>(dz, y, ld_y, R, Dy, Do, dXbig);
+  segnn_yexpand_kernel<<<(unsigned)ceil_div64(R * Do, 256), 256, 0, as_stream(stream)>>>(dz, y, ld_y, R, Dy, Do, dXbig);
   EQNN_CHECK_LAUNCH();
   return EQNN_OK;
 }

@@ -448,13 +448,20 @@ int eqnn_tc_wgrad_try(int64_t M, int64_t N, int64_t K, float alpha, const float*
                       const float* B, int64_t sbk, int64_t sbn, float* C, int64_t scm, int64_t scn, int accumulate,
                       int pro, float pro_scale, int epi, void* ws, size_t ws_bytes, cudaStream_t st);
 
+size_t eqnn_tc_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K);
+int eqnn_tc_gemm_try(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t sam, int64_t sak,
+                     const float* B, int64_t sbk, int64_t sbn, float* C, int64_t scm, int64_t scn, int accumulate,
+                     int pro, int epi, void* ws, size_t ws_bytes, cudaStream_t st);
+
 extern "C" size_t eqnn_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K) {
   const int bn = N <= 16 ? 16 : (N <= 32 ? 32 : 128);
   SplitPlan s = plan_split(M, N, K, 128, bn);
   const size_t simt = s.ksplit > 1 ? (size_t)s.ksplit * M * N * sizeof(float) : 0;
   const size_t tcw = eqnn_tc_wgrad_workspace_bytes(M, N, K);
   const size_t skw = skinny_wgrad_ok(M, N, K, 0, 0) ? (size_t)skinny_wgrad_parts(K) * M * N * sizeof(float) : 0;
+  const size_t tcg = eqnn_tc_gemm_workspace_bytes(M, N, K);
   size_t need = simt > tcw ? simt : tcw;
+  need = need > tcg ? need : tcg;
   return need > skw ? need : skw;
 }
 
@@ -480,6 +487,12 @@ extern "C" int eqnn_gemm_f32(int64_t M, int64_t N, int64_t K, float alpha, const
                                     as_stream(stream));
     if (w == 1) return EQNN_OK;
     if (w < 0) return -w;
+    if (flags & EQNN_GEMM_TF32X3_ANY) {
+      const int g = eqnn_tc_gemm_try(M, N, K, alpha, A, sam, sak, B, sbk, sbn, C, scm, scn,
+                                     (flags & EQNN_GEMM_ACCUMULATE) ? 1 : 0, pro, epi, ws, ws_bytes, as_stream(stream));
+      if (g == 1) return EQNN_OK;
+      if (g < 0) return -g;
+    }
   }
   GemmP p;
   p.M = M; p.N = N; p.K = K; p.alpha = alpha;

@@ -1,0 +1,377 @@
+// General fp32 GEMM on the tcgen05 tensor cores with 3xTF32 operand splitting (fp32-class accuracy):
+//   C[m, n] (+)= alpha * sum_k A[m, k] B[k, n],   any M, N, K, element strides and alignment.
+// Used by the SEGNN dense-lowered TensorProductLinearGate (models/segnn.py:30-64): x @ M_cat (forward),
+// dXbig @ M_cat^T (data gradient) and x^T @ dXbig (weight gradient, split over K with a fixed-order reduction).
+//
+// One CTA computes one 128 x 128 tile of one K split:
+//   warp  0     MMA issuer first (one elected thread): per 32-wide k chunk 4 x 3 tcgen05.mma kind::tf32
+//               (A_hi B_hi + A_lo B_hi + A_hi B_lo), accumulator in TMEM
+//   warps 0-3   epilogue: TMEM -> registers -> (shared-memory transpose for row-major C) -> global
+//   warps 4-19  producers (4-11: A tile, 12-19: B tile): strided, predicated cp.async loads (zero fill past
+//               M / N / K) into a per-thread shared-memory FIFO three chunks deep, then hi/lo split (round to
+//               nearest TF32) and 16-byte stores into 128-byte-swizzled K-major operand tiles; threads run
+//               along whichever index is contiguous in global memory
+// Ring of NSTAGE operand stages with full/empty mbarriers; nothing is assumed about alignment, so the same kernel
+// serves row-major, transposed and offset operands.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace {
+using namespace tc;
+
+constexpr int GT_M = 128;
+// 20 warps: registers are allocated in groups of four warps, so a 21st warp would cost every thread 16 registers
+constexpr int GT_EPI_WARPS = 4, GT_MMA_WARP = 0, GT_PROD_WARPS = 16;
+constexpr int GT_THREADS = (GT_EPI_WARPS + GT_PROD_WARPS) * 32;       // 640
+
+// fp32 -> (hi, lo): hi = a rounded to nearest TF32 (cvt.rna), lo = a - hi exact, |lo| <= 2^-11 |a|.  Rounding instead
+// of truncating halves |lo|, which quarters both the dropped lo*lo term and the tensor core's truncation of lo.
+__device__ __forceinline__ void split_rna(float a, float& hi, float& lo) {
+  uint32_t h;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(a));
+  hi = __uint_as_float(h);
+  lo = a - hi;
+}
+
+struct TcGemmP {
+  const float* A; int64_t sam, sak;
+  const float* B; int64_t sbk, sbn;
+  float* C; int64_t scm, scn;
+  int64_t M, N, K;
+  float alpha;
+  int accumulate;
+  int ksplit;
+  int64_t k_per_split;
+  float* partial;      // [ksplit][M][N] when ksplit > 1
+};
+
+template <int BN>
+struct GtCfg {
+  static constexpr uint32_t A_HALF = GT_M * 128, B_HALF = BN * 128;
+  static constexpr uint32_t STAGE = 2 * A_HALF + 2 * B_HALF;
+  static constexpr int NSTAGE = 2;                                      // operand ring (hi/lo, swizzled)
+  static constexpr int NPT = GT_M / 16 + BN / 16;                       // fp32 elements per producer thread and chunk
+  static constexpr uint32_t RAW_SLOT = NPT * GT_PROD_WARPS * 32 * 4;    // raw fp32 landing zone of one chunk
+  static constexpr int RAW_D = 3;                                       // chunks in flight (cp.async)
+  static constexpr uint32_t SMEM = NSTAGE * STAGE + RAW_D * RAW_SLOT + 1024 /*align*/ + 256 /*barriers*/;
+  static_assert(SMEM <= 227 * 1024, "shared memory budget exceeded");
+};
+
+// 4-byte asynchronous global -> shared copy; src_bytes = 0 writes a zero without reading
+__device__ __forceinline__ void cp_async4(uint32_t dst, const float* src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const float* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+
+template <int BN>
+__global__ void __launch_bounds__(GT_THREADS, 1) tc_gemm_kernel(const TcGemmP p) {
+  using Cfg = GtCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bars = base + Cfg::NSTAGE * Cfg::STAGE + Cfg::RAW_D * Cfg::RAW_SLOT;
+  auto full = [&](int s) { return bars + 8u * s; };
+  auto empty = [&](int s) { return bars + 8u * (Cfg::NSTAGE + s); };
+  const uint32_t t_full = bars + 8u * (2 * Cfg::NSTAGE);
+  const uint32_t tmem_slot = t_full + 8u;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t n0 = (int64_t)blockIdx.x * BN, m0 = (int64_t)blockIdx.y * GT_M;
+  const int64_t kbeg = (int64_t)blockIdx.z * p.k_per_split;
+  const int64_t kend = (kbeg + p.k_per_split < p.K) ? kbeg + p.k_per_split : p.K;
+  const int nch = (int)((kend - kbeg + 31) / 32);
+
+  if (tid == 0) {
+    for (int s = 0; s < Cfg::NSTAGE; ++s) {
+      mbar_init(full(s), GT_PROD_WARPS);
+      mbar_init(empty(s), 1);
+    }
+    mbar_init(t_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == GT_MMA_WARP) tmem_alloc(tmem_slot, BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
+
+  if (warp >= GT_EPI_WARPS) {
+    // =========================== producers ===========================
+    // Warps 4-11 feed A, warps 12-19 feed B; both operands are 128-row x 32-k tiles stored K-major, so one code path
+    // serves them.  Every thread owns four groups of 4 consecutive k per chunk (16 elements):
+    //   k contiguous in global memory   : group q = (row t/8 + 32 q, k 4 (t%8) ..)   -- 8 threads read one 128-byte row
+    //   rows contiguous in global memory: group q = (row t%128, k 16 (t/128) + 4 q ..) -- a warp reads 32 consecutive rows
+    // Zero fill past M / N / K.  Each group becomes one hi and one lo 16-byte store into the swizzled tile
+    // (conflict-free in both maps).
+    static_assert(BN == GT_M, "the two producer teams assume equally sized operand tiles");
+    const int pt = tid - GT_EPI_WARPS * 32;
+    const int ot = pt & 255;
+    const bool is_b = pt >= 256;
+    const int64_t s_row = is_b ? p.sbn : p.sam, s_k = is_b ? p.sbk : p.sak;
+    const float* obase = is_b ? p.B + n0 * p.sbn + kbeg * p.sbk : p.A + m0 * p.sam + kbeg * p.sak;
+    const int64_t rows_avail = is_b ? p.N - n0 : p.M - m0;
+    const uint32_t st_off = is_b ? 2 * Cfg::A_HALF : 0u;
+    const bool kmode = s_k <= s_row;
+    const bool vec = kmode && s_k == 1 && (s_row & 3) == 0 && (reinterpret_cast<uintptr_t>(obase) & 15) == 0;
+    const float* gq[4];
+    uint32_t offq[4];
+    int kq[4];
+    bool rok[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int row = kmode ? (ot >> 3) + 32 * q : (ot & 127);
+      kq[q] = kmode ? (ot & 7) * 4 : (ot >> 7) * 16 + 4 * q;
+      gq[q] = obase + row * s_row + kq[q] * s_k;
+      offq[q] = st_off + sw128((uint32_t)row, (uint32_t)kq[q] >> 2);
+      rok[q] = row < rows_avail;
+    }
+    auto publish = [&](int c, const float4 (&g)[4]) {
+      const int s = c % Cfg::NSTAGE;
+      mbar_wait(empty(s), ((c / Cfg::NSTAGE) & 1u) ^ 1u);
+      uint8_t* stage = gen + s * Cfg::STAGE;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float4 hi, lo;
+        split_rna(g[q].x, hi.x, lo.x);
+        split_rna(g[q].y, hi.y, lo.y);
+        split_rna(g[q].z, hi.z, lo.z);
+        split_rna(g[q].w, hi.w, lo.w);
+        *reinterpret_cast<float4*>(stage + offq[q]) = hi;
+        *reinterpret_cast<float4*>(stage + Cfg::A_HALF + offq[q]) = lo;
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full(s));            // one arrival per producer warp
+    };
+    if (vec) {
+      // 16-byte cp.async copies into a per-thread FIFO in shared memory, RAW_D chunks deep: no registers are held
+      // while the loads are in flight, and the thread that issued a copy reads it back (wait_group is enough).
+      const uint32_t raw0 = base + Cfg::NSTAGE * Cfg::STAGE + pt * 16u;
+      constexpr uint32_t RAW_Q = GT_PROD_WARPS * 32 * 16;             // bytes between a thread's groups
+      auto issue = [&](int c) {
+        if (c < nch) {
+          const uint32_t slot = raw0 + (c % Cfg::RAW_D) * Cfg::RAW_SLOT;
+          const int64_t krem = (kend - kbeg) - 32 * (int64_t)c;       // k entries of this chunk that exist
+          const float* adv = obase + 32 * (int64_t)c;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            // a group is whole or absent except in the last chunk, where its tail is zero-filled by the byte count
+            const int64_t left = krem - kq[q];
+            const uint32_t bytes = !rok[q] || left <= 0 ? 0u : (left >= 4 ? 16u : 4u * (uint32_t)left);
+            cp_async16(slot + q * RAW_Q, bytes ? gq[q] + (adv - obase) : obase, bytes);
+          }
+        }
+        cp_async_commit();                            // always: keeps the group count uniform
+      };
+      for (int c = 0; c < Cfg::RAW_D; ++c) issue(c);
+      for (int c = 0; c < nch; ++c) {
+        cp_async_wait<Cfg::RAW_D - 1>();              // chunk c has landed
+        const uint8_t* raw = gen + (raw0 - base) + (c % Cfg::RAW_D) * Cfg::RAW_SLOT;
+        float4 g[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) g[q] = *reinterpret_cast<const float4*>(raw + q * RAW_Q);
+        publish(c, g);
+        issue(c + Cfg::RAW_D);                        // refill the slot just drained (after its values were used)
+      }
+      cp_async_wait<0>();
+    } else {
+      // scalar loads (unaligned rows, or rows contiguous instead of k): registers, two chunks ahead
+      auto ldg_chunk = [&](int c, float4 (&g)[4]) {
+        if (c >= nch) return;
+        const int64_t krem = (kend - kbeg) - 32 * (int64_t)c;
+        const int64_t adv = 32 * (int64_t)c * s_k;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float* src = gq[q] + adv;
+          const bool r = rok[q];
+          g[q].x = (r && kq[q] + 0 < krem) ? __ldg(src) : 0.f;
+          g[q].y = (r && kq[q] + 1 < krem) ? __ldg(src + s_k) : 0.f;
+          g[q].z = (r && kq[q] + 2 < krem) ? __ldg(src + 2 * s_k) : 0.f;
+          g[q].w = (r && kq[q] + 3 < krem) ? __ldg(src + 3 * s_k) : 0.f;
+        }
+      };
+      float4 g0[4], g1[4], g2[4];
+      ldg_chunk(0, g0);
+      ldg_chunk(1, g1);
+      for (int c = 0; c < nch; c += 3) {
+        ldg_chunk(c + 2, g2);
+        publish(c, g0);
+        if (c + 1 < nch) {
+          ldg_chunk(c + 3, g0);
+          publish(c + 1, g1);
+        }
+        if (c + 2 < nch) {
+          ldg_chunk(c + 4, g1);
+          publish(c + 2, g2);
+        }
+      }
+    }
+  } else {
+    // =========================== MMA issuer (warp 0, one thread), then epilogue ===========================
+    if (warp == GT_MMA_WARP && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(GT_M, BN, 0, 0);
+      for (int c = 0; c < nch; ++c) {
+        const int s = c % Cfg::NSTAGE;
+        mbar_wait(full(s), (c / Cfg::NSTAGE) & 1u);
+        tc_fence_after();
+        const uint32_t a_hi = base + s * Cfg::STAGE, a_lo = a_hi + Cfg::A_HALF;
+        const uint32_t b_hi = a_hi + 2 * Cfg::A_HALF, b_lo = b_hi + Cfg::B_HALF;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const uint64_t dah = make_desc(a_hi + kk * 32, 16, 1024), dal = make_desc(a_lo + kk * 32, 16, 1024);
+          const uint64_t dbh = make_desc(b_hi + kk * 32, 16, 1024), dbl = make_desc(b_lo + kk * 32, 16, 1024);
+          mma_tf32(tmem_base, dah, dbh, idesc, (c | kk) ? 1u : 0u);
+          mma_tf32(tmem_base, dal, dbh, idesc, 1u);
+          mma_tf32(tmem_base, dah, dbl, idesc, 1u);
+        }
+        mma_commit(empty(s));
+      }
+      mma_commit(t_full);
+    }
+    __syncwarp();
+    // thread = accumulator row (tcgen05.ld 32x32b); row-major destinations go through a 32 x 33 shared-memory
+    // transpose (the operand stages are dead once t_full fires) so that lanes run along n.
+    mbar_wait(t_full, 0);
+    tc_fence_after();
+    const int64_t m = m0 + warp * 32 + lane;
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    float* stg = reinterpret_cast<float*>(gen) + warp * (32 * 33);
+    const bool split = p.ksplit > 1;
+    float* dst = split ? p.partial + (size_t)blockIdx.z * p.M * p.N : p.C;
+    const int64_t dm = split ? p.N : p.scm, dn = split ? 1 : p.scn;
+    const bool acc = !split && p.accumulate;
+    const bool transpose = dn <= dm;
+#pragma unroll 1
+    for (int cb = 0; cb < BN / 32; ++cb) {
+      const int64_t nb = n0 + cb * 32;
+      if (nb >= p.N) break;                          // warp-uniform
+      float v[32];
+      tmem_ld32(taddr + cb * 32, v);
+      tmem_ld_wait();
+      if (transpose) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = v[j];
+        __syncwarp();
+        const int64_t n = nb + lane;
+        if (n < p.N) {
+          float* q = dst + (m0 + warp * 32) * dm + n * dn;
+          const int64_t left = p.M - (m0 + warp * 32);
+          const int rows = left < 32 ? (int)(left < 0 ? 0 : left) : 32;
+          if (acc) {                                   // all reads first: the loads are independent of the stores
+#pragma unroll
+            for (int r = 0; r < 32; ++r) v[r] = r < rows ? q[r * dm] : 0.f;
+#pragma unroll
+            for (int r = 0; r < 32; ++r)
+              if (r < rows) q[r * dm] = fmaf(p.alpha, stg[r * 33 + lane], v[r]);
+          } else {
+#pragma unroll 8
+            for (int r = 0; r < rows; ++r) q[r * dm] = p.alpha * stg[r * 33 + lane];
+          }
+        }
+        __syncwarp();
+      } else if (m < p.M) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (nb + j < p.N) {
+            float* q = dst + m * dm + (nb + j) * dn;
+            const float o = p.alpha * v[j];
+            *q = acc ? *q + o : o;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == GT_MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BN);
+  }
+}
+
+// C[m, n] (+)= sum_z partial[z][m][n], z ascending (deterministic)
+__global__ void tc_gemm_reduce_kernel(const TcGemmP p) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.M * p.N) return;
+  const int64_t m = i / p.N, n = i - m * p.N;
+  float s = 0.f;
+  for (int z = 0; z < p.ksplit; ++z) s += p.partial[(size_t)z * p.M * p.N + i];
+  float* q = p.C + m * p.scm + n * p.scn;
+  *q = p.accumulate ? *q + s : s;
+}
+
+struct GtPlan {
+  int bn, ksplit;
+  int64_t k_per_split;
+};
+
+GtPlan gt_plan(int64_t M, int64_t N, int64_t K) {
+  GtPlan g;
+  g.bn = 128;
+  const int64_t tiles = ((M + GT_M - 1) / GT_M) * ((N + g.bn - 1) / g.bn);
+  int64_t ks = 1;
+  if (tiles < 148 && K >= 1024) {
+    ks = (2 * 148) / tiles;
+    const int64_t most = K / 256;                  // at least 8 k chunks per split
+    if (ks > most) ks = most;
+    if (ks < 1) ks = 1;
+  }
+  int64_t per = (K + ks - 1) / ks;
+  per = (per + 31) / 32 * 32;
+  g.k_per_split = per;
+  g.ksplit = (int)((K + per - 1) / per);
+  return g;
+}
+
+bool gt_shape_ok(int64_t M, int64_t N, int64_t K) {
+  return M >= 32 && N >= 32 && K >= 16 && M * N >= (1 << 14) && M * N * K >= (1 << 24) && N < (1ll << 31) &&
+         (M + GT_M - 1) / GT_M <= 65535;
+}
+
+template <int BN>
+int launch_tc_gemm(const TcGemmP& p, cudaStream_t st) {
+  auto kern = tc_gemm_kernel<BN>;
+  static bool configured = false;
+  if (!configured) {
+    EQNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GtCfg<BN>::SMEM));
+    configured = true;
+  }
+  dim3 grid((unsigned)((p.N + BN - 1) / BN), (unsigned)((p.M + GT_M - 1) / GT_M), (unsigned)p.ksplit);
+  kern<<<grid, GT_THREADS, GtCfg<BN>::SMEM, st>>>(p);
+  if (p.ksplit > 1) tc_gemm_reduce_kernel<<<(unsigned)ceil_div64(p.M * p.N, 256), 256, 0, st>>>(p);
+  EQNN_CHECK_LAUNCH_N(p.ksplit > 1 ? 2 : 1);
+  return EQNN_OK;
+}
+
+}  // namespace
+
+size_t eqnn_tc_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K) {
+  if (!gt_shape_ok(M, N, K)) return 0;
+  const GtPlan g = gt_plan(M, N, K);
+  return g.ksplit > 1 ? (size_t)g.ksplit * M * N * sizeof(float) : 0;
+}
+
+// returns 1 when the GEMM was launched here, 0 when the shape is declined, < 0 on error (-status)
+int eqnn_tc_gemm_try(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t sam, int64_t sak,
+                     const float* B, int64_t sbk, int64_t sbn, float* C, int64_t scm, int64_t scn, int accumulate,
+                     int pro, int epi, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (pro != 0 || epi != 0 || !gt_shape_ok(M, N, K)) return 0;
+  const GtPlan g = gt_plan(M, N, K);
+  if (g.ksplit > 1 && (!ws || ws_bytes < (size_t)g.ksplit * M * N * sizeof(float))) return 0;
+  TcGemmP p;
+  p.A = A; p.sam = sam; p.sak = sak;
+  p.B = B; p.sbk = sbk; p.sbn = sbn;
+  p.C = C; p.scm = scm; p.scn = scn;
+  p.M = M; p.N = N; p.K = K;
+  p.alpha = alpha; p.accumulate = accumulate;
+  p.ksplit = g.ksplit; p.k_per_split = g.k_per_split;
+  p.partial = reinterpret_cast<float*>(ws);
+  const int rc = launch_tc_gemm<128>(p, st);
+  return rc ? -rc : 1;
+}

@@ -208,7 +208,7 @@ _GEMM_WS = GemmWorkspace()
 
 
 def gemm(M, N, K, alpha, A, sam, sak, B, sbk, sbn, Cm, scm, scn, accumulate=False, pro=0, pro_scale=1.0, epi=0,
-         aux=None, ld_aux=0, epi_scale=1.0, a_off=0, b_off=0, c_off=0, aux_off=0, tag="gemm", tf32x3=False):
+         aux=None, ld_aux=0, epi_scale=1.0, a_off=0, b_off=0, c_off=0, aux_off=0, tag="gemm", tf32x3=False, tc_any=False):
     """C[m,n] (+)= epi(alpha * sum_k pro(A[m,k]) B[k,n]); element strides; *_off = element offsets."""
     L = lib()
     need = L.eqnn_gemm_workspace_bytes(M, N, K)
@@ -219,7 +219,7 @@ def gemm(M, N, K, alpha, A, sam, sak, B, sbk, sbn, Cm, scm, scn, accumulate=Fals
     px = C.c_void_p(0 if aux is None else aux.data_ptr() + 4 * aux_off)
     t0 = TIMER.begin() if TIMER else None
     check(L.eqnn_gemm_f32(M, N, K, float(alpha), pa, sam, sak, pb, sbk, sbn, pc, scm, scn,
-                          (1 if accumulate else 0) | (2 if tf32x3 else 0), pro, float(pro_scale), epi, px, ld_aux, float(epi_scale), ws, ws_bytes, _stream()), "gemm")
+                          (1 if accumulate else 0) | (2 if (tf32x3 or tc_any) else 0) | (4 if tc_any else 0), pro, float(pro_scale), epi, px, ld_aux, float(epi_scale), ws, ws_bytes, _stream()), "gemm")
     if TIMER:
         TIMER.end(tag, t0)
 

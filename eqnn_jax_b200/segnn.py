@@ -373,6 +373,9 @@ class SEGNN:
     # GEMMs per stored irrep block + Clebsch-Gordan table kernel): 4x fewer FLOPs, but its K <= 89 GEMMs run at
     # 4-10 TFLOP/s on the CUDA-core kernel, so it is 14 % slower end to end today
     lowering: str = "dense"
+    # not a reference field: run the layer GEMMs on tcgen05 tensor cores with 3xTF32 operand splitting
+    # (fp32-class accuracy); False = fp32 FMA on the CUDA cores
+    tensor_cores: bool = True
 
     def __post_init__(self):
         self._plans: Dict = {}
@@ -480,7 +483,7 @@ class SEGNN:
             for r0 in range(0, R, blk):
                 n = min(blk, R - r0)
                 for (c0, K, tb, Nr, W_off, acc) in t.runs:
-                    _mm(n, Nr, K, 1.0, x, r0 * ldx + c0, ldx, wexp, W_off, Nr, T, tb, t.DT, accumulate=acc, tag="segnn_gemm")
+                    _mm(n, Nr, K, 1.0, x, r0 * ldx + c0, ldx, wexp, W_off, Nr, T, tb, t.DT, accumulate=acc, tag="segnn_gemm", tc_any=self.tensor_cores)
                 ops.segnn_cg_apply(T, t.DT, t.DT, y if t.has_y else None, t.Dy, t.Dy, tab["cg_ptr"], tab["cg_idx"],
                                    tab["cg_coef"], theta if t.n_bias else None, t.b_off or 0, t.b_col, t.n_bias, n, t.Do,
                                    z, t.Do, y_off=r0 * t.Dy, out_off=r0 * t.Do, ptr_off=t.cg_f)
@@ -489,7 +492,7 @@ class SEGNN:
             Xbig = torch.empty((blk, nc), **f32)
             for r0 in range(0, R, blk):
                 n = min(blk, R - r0)
-                _mm(n, nc, t.Dx, 1.0, x, r0 * ldx, ldx, wexp, t.M_off, nc, Xbig, 0, nc, tag="segnn_gemm")
+                _mm(n, nc, t.Dx, 1.0, x, r0 * ldx, ldx, wexp, t.M_off, nc, Xbig, 0, nc, tag="segnn_gemm", tc_any=self.tensor_cores)
                 ops.segnn_ycontract(Xbig, y if t.has_y else None, t.Dy, theta if t.n_bias else None, t.b_off or 0, t.b_col,
                                     t.n_bias, n, t.Dy, t.Do, z, y_off=r0 * t.Dy, z_off=r0 * t.Do)
         if not t.activation:
@@ -524,10 +527,10 @@ class SEGNN:
                                    ptr_off=t.cg_b)
                 for (c0, K, tb, Nr, W_off, _) in t.runs:
                     _mm(K, Nr, n, 1.0, x, r0 * ldx + c0, ldx, dT, tb, t.DT, gwexp, W_off, Nr, ta=True, accumulate=r0 > 0,
-                        tag="segnn_gemm")
+                        tag="segnn_gemm", tc_any=self.tensor_cores)
                     if need_dx:
                         _mm(n, K, Nr, 1.0, dT, tb, t.DT, wexp, W_off, Nr, dx, r0 * t.Dx + c0, t.Dx, tb=True,
-                            tag="segnn_gemm")
+                            tag="segnn_gemm", tc_any=self.tensor_cores)
             return dx
         nc = t.Dy * t.Do
         dXbig = torch.empty((blk, nc), **f32)
@@ -536,9 +539,9 @@ class SEGNN:
             n = min(blk, R - r0)
             ops.segnn_yexpand(dz, y if t.has_y else None, t.Dy, n, t.Dy, t.Do, dXbig, dz_off=r0 * t.Do, y_off=r0 * t.Dy)
             _mm(t.Dx, nc, n, 1.0, x, r0 * ldx, ldx, dXbig, 0, nc, gwexp, t.M_off, nc, ta=True, accumulate=r0 > 0,
-                tag="segnn_gemm")
+                tag="segnn_gemm", tc_any=self.tensor_cores)
             if need_dx:
-                _mm(n, t.Dx, nc, 1.0, dXbig, 0, nc, wexp, t.M_off, nc, dx, r0 * t.Dx, t.Dx, tb=True, tag="segnn_gemm")
+                _mm(n, t.Dx, nc, 1.0, dXbig, 0, nc, wexp, t.M_off, nc, dx, r0 * t.Dx, t.Dx, tb=True, tag="segnn_gemm", tc_any=self.tensor_cores)
         return dx
 
     # -- whole model ------------------------------------------------------------------------------------

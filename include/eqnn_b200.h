@@ -150,7 +150,10 @@ int eqnn_node_tp_bwd(int tp_id, const float* x, const float* y, const float* gT,
 /*   EQNN_GEMM_TF32X3: large-M problems with K, N <= 128 run on the tensor cores (tcgen05, TMEM) with every
  *   operand split into two TF32 halves and three MMAs per product (fp32-class accuracy, error ~2^-21);
  *   shapes the tensor-core kernels do not cover silently use the fp32 CUDA-core kernel.           */
-enum { EQNN_GEMM_ACCUMULATE = 1, EQNN_GEMM_TF32X3 = 2 };
+/*   EQNN_GEMM_TF32X3_ANY (with EQNN_GEMM_TF32X3): every other shape with pro = epi = 0 and M, N >= 32 also runs
+ *   on the tensor cores, through a general 128 x 128/256-tile 3xTF32 kernel (any strides and alignment, K split
+ *   over CTAs for short-and-wide outputs) -- the SEGNN dense-lowered layers (models/segnn.py:30-64).            */
+enum { EQNN_GEMM_ACCUMULATE = 1, EQNN_GEMM_TF32X3 = 2, EQNN_GEMM_TF32X3_ANY = 4 };
 size_t eqnn_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K);
 int eqnn_gemm_f32(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t sam, int64_t sak,
                   const float* B, int64_t sbk, int64_t sbn, float* C, int64_t scm, int64_t scn, int flags,

@@ -278,3 +278,48 @@ def test_tensor_core_3xtf32_gemm_matches_fp64(case, M):
     torch.cuda.synchronize()
     assert not torch.isnan(got).any()
     assert _rel(got, want) < 3e-6
+
+
+@pytest.mark.parametrize("case", ["fwd", "fwd_acc", "dgrad", "wgrad", "wgrad_acc", "small_k", "offsets"])
+def test_general_tensor_core_gemm_matches_fp64(case):
+    """General 3xTF32 tcgen05 GEMM (EQNN_GEMM_TF32X3_ANY; the SEGNN dense-lowered layers): unaligned leading
+    dimensions, row / column tails, transposed operands, K split over CTAs, accumulation -- against fp64."""
+    from eqnn_jax_b200.nequip import _mm
+    g = torch.Generator().manual_seed(len(case))
+    r64 = lambda *s: torch.randn(*s, generator=g, dtype=torch.float64)
+    dev = lambda t: t.float().cuda()
+    if case in ("fwd", "fwd_acc"):                       # x @ M_cat: lda 341 (not a multiple of 4), row tail
+        M, N, K = 3001, 768, 341
+        A, B, C0 = r64(M, K), r64(K, N), r64(M, N)
+        C = dev(C0)
+        _mm(M, N, K, 0.5, dev(A), 0, K, dev(B), 0, N, C, 0, N, accumulate=case == "fwd_acc", tc_any=True)
+        want = 0.5 * (A @ B) + (C0 if case == "fwd_acc" else 0.0)
+    elif case == "dgrad":                                # dXbig @ M_cat^T: B transposed, column tail (341)
+        M, N, K = 2500, 341, 768
+        A, W = r64(M, K), r64(N, K)
+        C = torch.full((M, N), float("nan")).cuda()
+        _mm(M, N, K, 1.0, dev(A), 0, K, dev(W), 0, K, C, 0, N, tb=True, tc_any=True)
+        want = A @ W.t()
+    elif case in ("wgrad", "wgrad_acc"):                 # x^T @ dXbig: A transposed, K = rows, split over CTAs
+        M, N, K = 170, 768, 20011
+        X, D, C0 = r64(K, M), r64(K, N), r64(M, N)
+        C = dev(C0)
+        _mm(M, N, K, 1.0, dev(X), 0, M, dev(D), 0, N, C, 0, N, ta=True, accumulate=case == "wgrad_acc", tc_any=True)
+        want = X.t() @ D + (C0 if case == "wgrad_acc" else 0.0)
+    elif case == "small_k":                              # K below one chunk, N below one tile
+        M, N, K = 70001, 40, 20
+        A, B = r64(M, K), r64(K, N)
+        C = torch.full((M, N), float("nan")).cuda()
+        _mm(M, N, K, 2.0, dev(A), 0, K, dev(B), 0, N, C, 0, N, tc_any=True)
+        want = 2.0 * (A @ B)
+    else:                                                # sub-blocks of wider buffers at odd element offsets
+        M, N, K = 1000, 130, 89
+        Ab, Bb, Cb = r64(M, 341), r64(K * 200 + 7), r64(M, 633)
+        C = dev(Cb)
+        _mm(M, N, K, 1.0, dev(Ab), 89, 341, dev(Bb), 3, 200, C, 125, 633, tc_any=True)
+        want = Cb.clone()
+        want[:, 125:125 + N] = Ab[:, 89:89 + K] @ Bb[3:3 + K * 200].reshape(K, 200)[:, :N]
+    torch.cuda.synchronize()
+    assert torch.isfinite(C).all()
+    err = (C.double().cpu() - want).abs().max().item()
+    assert err <= 1e-5 * want.abs().max().item(), (case, err, want.abs().max().item())

@@ -104,6 +104,7 @@ def test_segnn_forward_and_gradients(kw, irreps, F, lmax_attr, n_rb, pbc, vel, n
     for path, w in _leaves(p):
         scales[path[0]] = max(scales.get(path[0], 0.0), float(w.grad.abs().max()) if w.grad is not None else 0.0)
     n_dead = 0
+    gmax = max(scales.values())
     for path, w in _leaves(p):
         g = gt
         for q in path:
@@ -113,7 +114,11 @@ def test_segnn_forward_and_gradients(kw, irreps, F, lmax_attr, n_rb, pbc, vel, n
             assert float(g.abs().max()) == 0.0, path
             n_dead += 1
             continue
-        _close(g.cpu().numpy(), wn, "grad " + "/".join(path), scale=scales[path[0]])
+        # 1e-5 of the module's own gradient scale; modules whose gradients sit orders of magnitude below the dominant
+        # flow of the same backward pass inherit that flow's fp32 rounding (1e-7 of it), as in tests/test_gpu_egnn.py
+        err = np.abs(g.cpu().numpy().astype(np.float64) - wn).max()
+        assert err <= RTOL * scales[path[0]] + 1e-7 * gmax, \
+            f"grad {'/'.join(path)}: err {err:.3e}, module scale {scales[path[0]]:.3e}, largest gradient {gmax:.3e}"
     assert n_dead > 0
 
 
