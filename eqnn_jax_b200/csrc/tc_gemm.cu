@@ -7,10 +7,10 @@
 //   warp  0     MMA issuer first (one elected thread): per 32-wide k chunk 4 x 3 tcgen05.mma kind::tf32
 //               (A_hi B_hi + A_lo B_hi + A_hi B_lo), accumulator in TMEM
 //   warps 0-3   epilogue: TMEM -> registers -> (shared-memory transpose for row-major C) -> global
-//   warps 4-19  producers (4-11: A tile, 12-19: B tile): strided, predicated cp.async loads (zero fill past
-//               M / N / K) into a per-thread shared-memory FIFO three chunks deep, then hi/lo split (round to
-//               nearest TF32) and 16-byte stores into 128-byte-swizzled K-major operand tiles; threads run
-//               along whichever index is contiguous in global memory
+//   warps 4-19  producers (4-11: A tile, 12-19: B tile): strided, predicated loads (zero fill past M / N / K) held
+//               in registers two chunks ahead, hi/lo split (round to nearest TF32), 16-byte stores into
+//               128-byte-swizzled K-major operand tiles; threads run along whichever index is contiguous in
+//               global memory
 // Ring of NSTAGE operand stages with full/empty mbarriers; nothing is assumed about alignment, so the same kernel
 // serves row-major, transposed and offset operands.
 #include "common.cuh"
@@ -24,13 +24,26 @@ constexpr int GT_M = 128;
 constexpr int GT_EPI_WARPS = 4, GT_MMA_WARP = 0, GT_PROD_WARPS = 16;
 constexpr int GT_THREADS = (GT_EPI_WARPS + GT_PROD_WARPS) * 32;       // 640
 
-// fp32 -> (hi, lo): hi = a rounded to nearest TF32 (cvt.rna), lo = a - hi exact, |lo| <= 2^-11 |a|.  Rounding instead
-// of truncating halves |lo|, which quarters both the dropped lo*lo term and the tensor core's truncation of lo.
-__device__ __forceinline__ void split_rna(float a, float& hi, float& lo) {
-  uint32_t h;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(a));
-  hi = __uint_as_float(h);
-  lo = a - hi;
+// fp32 -> (hi, lo): hi = a rounded to the nearest TF32 (half away from zero, two integer instructions; cvt.rna.tf32
+// is emulated in ~5), lo = a - hi exact, |lo| <= 2^-11 |a|.  Rounding instead of truncating halves |lo|, which
+// quarters both the dropped lo*lo term and the tensor core's own truncation of lo.  (|a| within 2^-11 of FLT_MAX
+// would round to infinity; the operands here are activations and weights.)
+__device__ __forceinline__ float round_tf32(float a) {
+  return __uint_as_float((__float_as_uint(a) + 0x1000u) & 0xffffe000u);
+}
+__device__ __forceinline__ void split4(const float4& a, float4& hi, float4& lo) {
+  hi = make_float4(round_tf32(a.x), round_tf32(a.y), round_tf32(a.z), round_tf32(a.w));
+  const f32x2 neg1 = pk2(-1.f, -1.f);
+  upk2(fma2(pk2(hi.x, hi.y), neg1, pk2(a.x, a.y)), lo.x, lo.y);
+  upk2(fma2(pk2(hi.z, hi.w), neg1, pk2(a.z, a.w)), lo.z, lo.w);
+}
+
+// waits that are expected to be long back off, so the waiting warps do not eat the producers' issue slots
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity, unsigned ns) {
+  for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin) {
+    __nanosleep(ns);
+    if (spin > (1u << 24)) __trap();
+  }
 }
 
 struct TcGemmP {
@@ -49,25 +62,12 @@ template <int BN>
 struct GtCfg {
   static constexpr uint32_t A_HALF = GT_M * 128, B_HALF = BN * 128;
   static constexpr uint32_t STAGE = 2 * A_HALF + 2 * B_HALF;
-  static constexpr int NSTAGE = 2;                                      // operand ring (hi/lo, swizzled)
-  static constexpr int NPT = GT_M / 16 + BN / 16;                       // fp32 elements per producer thread and chunk
-  static constexpr uint32_t RAW_SLOT = NPT * GT_PROD_WARPS * 32 * 4;    // raw fp32 landing zone of one chunk
-  static constexpr int RAW_D = 3;                                       // chunks in flight (cp.async)
-  static constexpr uint32_t SMEM = NSTAGE * STAGE + RAW_D * RAW_SLOT + 1024 /*align*/ + 256 /*barriers*/;
+  // three stages: a stage is refilled only after its MMAs have completed, and the refill (wait, split, 16-byte
+  // stores, proxy fence, arrive) takes longer than one chunk of MMAs -- it needs two chunks of slack
+  static constexpr int NSTAGE = 3;
+  static constexpr uint32_t SMEM = NSTAGE * STAGE + 1024 /*align*/ + 256 /*barriers*/;
   static_assert(SMEM <= 227 * 1024, "shared memory budget exceeded");
 };
-
-// 4-byte asynchronous global -> shared copy; src_bytes = 0 writes a zero without reading
-__device__ __forceinline__ void cp_async4(uint32_t dst, const float* src, uint32_t src_bytes) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-__device__ __forceinline__ void cp_async16(uint32_t dst, const float* src, uint32_t src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
 
 template <int BN>
 __global__ void __launch_bounds__(GT_THREADS, 1) tc_gemm_kernel(const TcGemmP p) {
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) tc_gemm_kernel(const TcGemmP p)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t bars = base + Cfg::NSTAGE * Cfg::STAGE + Cfg::RAW_D * Cfg::RAW_SLOT;
+  const uint32_t bars = base + Cfg::NSTAGE * Cfg::STAGE;
   auto full = [&](int s) { return bars + 8u * s; };
   auto empty = [&](int s) { return bars + 8u * (Cfg::NSTAGE + s); };
   const uint32_t t_full = bars + 8u * (2 * Cfg::NSTAGE);
@@ -122,26 +122,23 @@ __global__ void __launch_bounds__(GT_THREADS, 1) tc_gemm_kernel(const TcGemmP p)
     const float* gq[4];
     uint32_t offq[4];
     int kq[4];
-    bool rok[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int row = kmode ? (ot >> 3) + 32 * q : (ot & 127);
       kq[q] = kmode ? (ot & 7) * 4 : (ot >> 7) * 16 + 4 * q;
-      gq[q] = obase + row * s_row + kq[q] * s_k;
+      // rows past the end of A / B re-read the last one: they only feed accumulator rows / columns never stored
+      const int64_t grow = row < rows_avail ? row : rows_avail - 1;
+      gq[q] = obase + grow * s_row + kq[q] * s_k;
       offq[q] = st_off + sw128((uint32_t)row, (uint32_t)kq[q] >> 2);
-      rok[q] = row < rows_avail;
     }
     auto publish = [&](int c, const float4 (&g)[4]) {
       const int s = c % Cfg::NSTAGE;
-      mbar_wait(empty(s), ((c / Cfg::NSTAGE) & 1u) ^ 1u);
+      mbar_wait_backoff(empty(s), ((c / Cfg::NSTAGE) & 1u) ^ 1u, 32);
       uint8_t* stage = gen + s * Cfg::STAGE;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         float4 hi, lo;
-        split_rna(g[q].x, hi.x, lo.x);
-        split_rna(g[q].y, hi.y, lo.y);
-        split_rna(g[q].z, hi.z, lo.z);
-        split_rna(g[q].w, hi.w, lo.w);
+        split4(g[q], hi, lo);
         *reinterpret_cast<float4*>(stage + offq[q]) = hi;
         *reinterpret_cast<float4*>(stage + Cfg::A_HALF + offq[q]) = lo;
       }
@@ -149,53 +146,35 @@ __global__ void __launch_bounds__(GT_THREADS, 1) tc_gemm_kernel(const TcGemmP p)
       __syncwarp();
       if (lane == 0) mbar_arrive(full(s));            // one arrival per producer warp
     };
-    if (vec) {
-      // 16-byte cp.async copies into a per-thread FIFO in shared memory, RAW_D chunks deep: no registers are held
-      // while the loads are in flight, and the thread that issued a copy reads it back (wait_group is enough).
-      const uint32_t raw0 = base + Cfg::NSTAGE * Cfg::STAGE + pt * 16u;
-      constexpr uint32_t RAW_Q = GT_PROD_WARPS * 32 * 16;             // bytes between a thread's groups
-      auto issue = [&](int c) {
-        if (c < nch) {
-          const uint32_t slot = raw0 + (c % Cfg::RAW_D) * Cfg::RAW_SLOT;
-          const int64_t krem = (kend - kbeg) - 32 * (int64_t)c;       // k entries of this chunk that exist
-          const float* adv = obase + 32 * (int64_t)c;
+    // loads go to registers, two chunks ahead of the one being published (16-byte loads when the operand allows it);
+    // only the last chunk of a K range can be partial, and only there are loads predicated (zero fill past K)
+    auto ldg_chunk = [&](int c, float4 (&g)[4]) {
+      if (c >= nch) return;
+      const int64_t krem = (kend - kbeg) - 32 * (int64_t)c;           // k entries of this chunk that exist
+      const int64_t adv = 32 * (int64_t)c * s_k;
+      if (krem >= 32) {
+        if (vec) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) g[q] = __ldg(reinterpret_cast<const float4*>(gq[q] + adv));
+        } else {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            // a group is whole or absent except in the last chunk, where its tail is zero-filled by the byte count
-            const int64_t left = krem - kq[q];
-            const uint32_t bytes = !rok[q] || left <= 0 ? 0u : (left >= 4 ? 16u : 4u * (uint32_t)left);
-            cp_async16(slot + q * RAW_Q, bytes ? gq[q] + (adv - obase) : obase, bytes);
+            const float* src = gq[q] + adv;
+            g[q] = make_float4(__ldg(src), __ldg(src + s_k), __ldg(src + 2 * s_k), __ldg(src + 3 * s_k));
           }
         }
-        cp_async_commit();                            // always: keeps the group count uniform
-      };
-      for (int c = 0; c < Cfg::RAW_D; ++c) issue(c);
-      for (int c = 0; c < nch; ++c) {
-        cp_async_wait<Cfg::RAW_D - 1>();              // chunk c has landed
-        const uint8_t* raw = gen + (raw0 - base) + (c % Cfg::RAW_D) * Cfg::RAW_SLOT;
-        float4 g[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) g[q] = *reinterpret_cast<const float4*>(raw + q * RAW_Q);
-        publish(c, g);
-        issue(c + Cfg::RAW_D);                        // refill the slot just drained (after its values were used)
-      }
-      cp_async_wait<0>();
-    } else {
-      // scalar loads (unaligned rows, or rows contiguous instead of k): registers, two chunks ahead
-      auto ldg_chunk = [&](int c, float4 (&g)[4]) {
-        if (c >= nch) return;
-        const int64_t krem = (kend - kbeg) - 32 * (int64_t)c;
-        const int64_t adv = 32 * (int64_t)c * s_k;
+      } else {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const float* src = gq[q] + adv;
-          const bool r = rok[q];
-          g[q].x = (r && kq[q] + 0 < krem) ? __ldg(src) : 0.f;
-          g[q].y = (r && kq[q] + 1 < krem) ? __ldg(src + s_k) : 0.f;
-          g[q].z = (r && kq[q] + 2 < krem) ? __ldg(src + 2 * s_k) : 0.f;
-          g[q].w = (r && kq[q] + 3 < krem) ? __ldg(src + 3 * s_k) : 0.f;
+          g[q].x = (kq[q] + 0 < krem) ? __ldg(src) : 0.f;
+          g[q].y = (kq[q] + 1 < krem) ? __ldg(src + s_k) : 0.f;
+          g[q].z = (kq[q] + 2 < krem) ? __ldg(src + 2 * s_k) : 0.f;
+          g[q].w = (kq[q] + 3 < krem) ? __ldg(src + 3 * s_k) : 0.f;
         }
-      };
+      }
+    };
+    {
       float4 g0[4], g1[4], g2[4];
       ldg_chunk(0, g0);
       ldg_chunk(1, g1);
@@ -237,7 +216,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) tc_gemm_kernel(const TcGemmP p)
     __syncwarp();
     // thread = accumulator row (tcgen05.ld 32x32b); row-major destinations go through a 32 x 33 shared-memory
     // transpose (the operand stages are dead once t_full fires) so that lanes run along n.
-    mbar_wait(t_full, 0);
+    mbar_wait_backoff(t_full, 0, 128);
     tc_fence_after();
     const int64_t m = m0 + warp * 32 + lane;
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
