@@ -46,6 +46,67 @@ __global__ void gate_fwd_kernel(const float* __restrict__ z, int64_t n, GateDesc
   out[i] = v;
 }
 
+// Tall inputs (per-edge SEGNN layers): thread = column, a block walks GATE_ROWS rows, so the column's role (which
+// gate, which components) is resolved once and no 64-bit division runs per element.  Same arithmetic as above.
+constexpr int GATE_ROWS = 16;
+__global__ void gate_fwd_rows_kernel(const float* __restrict__ z, int64_t n, GateDesc d, float* __restrict__ out) {
+  const int d_in = d.n_extra + d.n_gates + d.d_gated, d_out = d.n_extra + d.d_gated;
+  const int c = threadIdx.x;
+  if (c >= d_out) return;
+  const int j = c - d.n_extra;
+  const int src = c < d.n_extra ? c : d.n_extra + d.n_gates + j;
+  const int gate = c < d.n_extra ? 0 : d.n_extra + gate_index(d, j);
+  const int64_t r0 = (int64_t)blockIdx.x * GATE_ROWS;
+  const int64_t r1 = r0 + GATE_ROWS < n ? r0 + GATE_ROWS : n;
+  for (int64_t r = r0; r < r1; ++r) {
+    const float* zr = z + r * d_in;
+    const float x = zr[src];
+    out[r * d_out + c] = c < d.n_extra ? gelu_tanh(x) * d.inv_c_act : (sigmoid_acc(zr[gate]) * d.inv_c_gate) * x;
+  }
+}
+
+__global__ void gate_bwd_rows_kernel(const float* __restrict__ z, const float* __restrict__ gout, int64_t n, GateDesc d,
+                                     float* __restrict__ gz) {
+  const int d_in = d.n_extra + d.n_gates + d.d_gated, d_out = d.n_extra + d.d_gated;
+  const int c = threadIdx.x;
+  if (c >= d_in) return;
+  int kind = 0, off = 0, dim = 1, gate = 0;      // 0 activated scalar | 1 gate scalar | 2 gated component
+  if (c >= d.n_extra + d.n_gates) {
+    kind = 2;
+    off = c - d.n_extra - d.n_gates;
+    gate = d.n_extra + gate_index(d, off);
+  } else if (c >= d.n_extra) {
+    kind = 1;
+    int gi = c - d.n_extra;
+#pragma unroll
+    for (int k = 0; k < MAX_GATE_CHUNKS; ++k) {
+      if (k < d.n_chunks) {
+        if (gi >= 0 && gi < d.mul[k]) { off += gi * d.dim[k]; dim = d.dim[k]; gi = -1; }
+        else if (gi >= 0) { gi -= d.mul[k]; off += d.mul[k] * d.dim[k]; }
+      }
+    }
+  }
+  const int64_t r0 = (int64_t)blockIdx.x * GATE_ROWS;
+  const int64_t r1 = r0 + GATE_ROWS < n ? r0 + GATE_ROWS : n;
+  for (int64_t r = r0; r < r1; ++r) {
+    const float* zr = z + r * d_in;
+    const float* gr = gout + r * d_out;
+    float v;
+    if (kind == 0) {
+      v = gr[c] * gelu_tanh_grad(zr[c]) * d.inv_c_act;
+    } else if (kind == 1) {
+      float s = 0.f;
+      for (int q = 0; q < dim; ++q) s += gr[d.n_extra + off + q] * zr[d.n_extra + d.n_gates + off + q];
+      const float sg = sigmoid_acc(zr[c]);
+      v = s * sg * (1.f - sg) * d.inv_c_gate;
+    } else {
+      const float g = sigmoid_acc(zr[gate]) * d.inv_c_gate;
+      v = g * gr[d.n_extra + off];
+    }
+    gz[r * d_in + c] = v;
+  }
+}
+
 // one thread per input element of z; gates sum over their (2l+1) components
 __global__ void gate_bwd_kernel(const float* __restrict__ z, const float* __restrict__ gout, int64_t n, GateDesc d,
                                 float* __restrict__ gz) {
@@ -273,7 +334,11 @@ extern "C" int eqnn_gate_fwd(const float* z, int64_t n, int n_extra, int n_gates
   if (rc) return rc;
   const int64_t tot = n * (d.n_extra + d.d_gated);
   if (tot == 0) return EQNN_OK;
-  gate_fwd_kernel<<<(unsigned)ceil_div64(tot, 256), 256, 0, as_stream(stream)>>>(z, n, d, out);
+  const int d_out = d.n_extra + d.d_gated;
+  if (n >= 4096 && d_out <= 1024)
+    gate_fwd_rows_kernel<<<(unsigned)ceil_div64(n, GATE_ROWS), (d_out + 31) / 32 * 32, 0, as_stream(stream)>>>(z, n, d, out);
+  else
+    gate_fwd_kernel<<<(unsigned)ceil_div64(tot, 256), 256, 0, as_stream(stream)>>>(z, n, d, out);
   EQNN_CHECK_LAUNCH();
   return EQNN_OK;
 }
@@ -287,7 +352,11 @@ extern "C" int eqnn_gate_bwd(const float* z, const float* gout, int64_t n, int n
   if (rc) return rc;
   const int64_t tot = n * (d.n_extra + d.n_gates + d.d_gated);
   if (tot == 0) return EQNN_OK;
-  gate_bwd_kernel<<<(unsigned)ceil_div64(tot, 256), 256, 0, as_stream(stream)>>>(z, gout, n, d, gz);
+  const int d_in = d.n_extra + d.n_gates + d.d_gated;
+  if (n >= 4096 && d_in <= 1024)
+    gate_bwd_rows_kernel<<<(unsigned)ceil_div64(n, GATE_ROWS), (d_in + 31) / 32 * 32, 0, as_stream(stream)>>>(z, gout, n, d, gz);
+  else
+    gate_bwd_kernel<<<(unsigned)ceil_div64(tot, 256), 256, 0, as_stream(stream)>>>(z, gout, n, d, gz);
   EQNN_CHECK_LAUNCH();
   return EQNN_OK;
 }

@@ -100,10 +100,11 @@ def test_gemm_skinny_kernels_accumulate_and_determinism():
     assert _rel(outs[0], 2.0 + 0.5 * (A.t() @ G)) < 2e-6
 
 
-def test_gate_forward_backward():
+@pytest.mark.parametrize("n", [77, 5003])           # 5003: the tall-input kernels (thread = column, rows walked)
+def test_gate_forward_backward(n):
     from eqnn_jax_b200 import ops
     g = torch.Generator().manual_seed(2)
-    n, n_extra, mul, l = 77, 9, [3, 2], [1, 2]
+    n_extra, mul, l = 9, [3, 2], [1, 2]
     n_gates = sum(mul)
     dg = sum(m * (2 * ll + 1) for m, ll in zip(mul, l))
     z = torch.randn(n, n_extra + n_gates + dg, generator=g, dtype=torch.float64, requires_grad=True)
