@@ -226,6 +226,9 @@ __global__ void __launch_bounds__(GT_THREADS, 1) tc_gemm_kernel(const TcGemmP p)
     const int64_t dm = split ? p.N : p.scm, dn = split ? 1 : p.scn;
     const bool acc = !split && p.accumulate;
     const bool transpose = dn <= dm;
+    // row-major destination with 32-byte-aligned rows: every thread writes whole sectors of its own row with
+    // 256-bit stores -- four instructions per 32 columns instead of a shared-memory transpose and 32 scalar stores
+    const bool rows256 = dn == 1 && !acc && (dm & 7) == 0 && (reinterpret_cast<uintptr_t>(dst) & 31) == 0;
 #pragma unroll 1
     for (int cb = 0; cb < BN / 32; ++cb) {
       const int64_t nb = n0 + cb * 32;
@@ -233,7 +236,15 @@ __global__ void __launch_bounds__(GT_THREADS, 1) tc_gemm_kernel(const TcGemmP p)
       float v[32];
       tmem_ld32(taddr + cb * 32, v);
       tmem_ld_wait();
-      if (transpose) {
+      if (rows256 && nb + 32 <= p.N) {
+        if (m < p.M) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
+          float* q = dst + m * dm + nb;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) stg256(q + j, v + j);
+        }
+      } else if (transpose) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = v[j];
         __syncwarp();

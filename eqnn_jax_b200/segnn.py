@@ -17,8 +17,10 @@ Edges are processed in receiver-sorted order: ``eqnn_egnn_edge_input_fwd`` build
 h_r) (:112), ``eqnn_egnn_segment_rows_fwd`` is jraph's segment_sum / segment_mean over receivers (:218), and the
 backward passes gather sender / receiver ends through the two CSRs (no atomics).  The first n_layers-1 layers of
 the node function never reach the output (:84-89): they own parameters (exact zero gradients) and are not
-computed.  First correct path: fp32 CUDA-core GEMMs on the dense lowering (about 7x the FLOPs of the irrep-blocked
-form); the tensor-core version is next round's work.
+computed.  The layer GEMMs run on the tcgen05 tensor cores with 3xTF32 operand splitting (csrc/tc_gemm.cu, any
+strides / alignment, K split over CTAs for the weight gradients); ``tensor_cores=False`` keeps them on the fp32
+CUDA-core kernel.  ``lowering="blocked"`` is a second, irrep-blocked route (multiplicity GEMMs per stored irrep
+block + a Clebsch-Gordan table kernel, 4x fewer FLOPs but overhead-bound K <= 89 GEMMs).
 Graph globals (concatenated to the pooled scalars, LayerNorm, :282-286) are supported.
 Not built: max aggregation, activations other than gelu -> NotImplementedError, never a fallback.
 """
@@ -379,6 +381,7 @@ class SEGNN:
 
     def __post_init__(self):
         self._plans: Dict = {}
+        self._gemm_kw = dict(tag="segnn_gemm", tc_any=bool(self.tensor_cores))
 
     # ---- plan / parameters ----------------------------------------------------------------------
     def _unpack(self, g: SteerableGraphsTuple):
@@ -483,7 +486,7 @@ class SEGNN:
             for r0 in range(0, R, blk):
                 n = min(blk, R - r0)
                 for (c0, K, tb, Nr, W_off, acc) in t.runs:
-                    _mm(n, Nr, K, 1.0, x, r0 * ldx + c0, ldx, wexp, W_off, Nr, T, tb, t.DT, accumulate=acc, tag="segnn_gemm", tc_any=self.tensor_cores)
+                    _mm(n, Nr, K, 1.0, x, r0 * ldx + c0, ldx, wexp, W_off, Nr, T, tb, t.DT, accumulate=acc, **self._gemm_kw)
                 ops.segnn_cg_apply(T, t.DT, t.DT, y if t.has_y else None, t.Dy, t.Dy, tab["cg_ptr"], tab["cg_idx"],
                                    tab["cg_coef"], theta if t.n_bias else None, t.b_off or 0, t.b_col, t.n_bias, n, t.Do,
                                    z, t.Do, y_off=r0 * t.Dy, out_off=r0 * t.Do, ptr_off=t.cg_f)
@@ -492,7 +495,7 @@ class SEGNN:
             Xbig = torch.empty((blk, nc), **f32)
             for r0 in range(0, R, blk):
                 n = min(blk, R - r0)
-                _mm(n, nc, t.Dx, 1.0, x, r0 * ldx, ldx, wexp, t.M_off, nc, Xbig, 0, nc, tag="segnn_gemm", tc_any=self.tensor_cores)
+                _mm(n, nc, t.Dx, 1.0, x, r0 * ldx, ldx, wexp, t.M_off, nc, Xbig, 0, nc, **self._gemm_kw)
                 ops.segnn_ycontract(Xbig, y if t.has_y else None, t.Dy, theta if t.n_bias else None, t.b_off or 0, t.b_col,
                                     t.n_bias, n, t.Dy, t.Do, z, y_off=r0 * t.Dy, z_off=r0 * t.Do)
         if not t.activation:
@@ -527,10 +530,10 @@ class SEGNN:
                                    ptr_off=t.cg_b)
                 for (c0, K, tb, Nr, W_off, _) in t.runs:
                     _mm(K, Nr, n, 1.0, x, r0 * ldx + c0, ldx, dT, tb, t.DT, gwexp, W_off, Nr, ta=True, accumulate=r0 > 0,
-                        tag="segnn_gemm", tc_any=self.tensor_cores)
+                        **self._gemm_kw)
                     if need_dx:
                         _mm(n, K, Nr, 1.0, dT, tb, t.DT, wexp, W_off, Nr, dx, r0 * t.Dx + c0, t.Dx, tb=True,
-                            tag="segnn_gemm", tc_any=self.tensor_cores)
+                            **self._gemm_kw)
             return dx
         nc = t.Dy * t.Do
         dXbig = torch.empty((blk, nc), **f32)
@@ -539,9 +542,9 @@ class SEGNN:
             n = min(blk, R - r0)
             ops.segnn_yexpand(dz, y if t.has_y else None, t.Dy, n, t.Dy, t.Do, dXbig, dz_off=r0 * t.Do, y_off=r0 * t.Dy)
             _mm(t.Dx, nc, n, 1.0, x, r0 * ldx, ldx, dXbig, 0, nc, gwexp, t.M_off, nc, ta=True, accumulate=r0 > 0,
-                tag="segnn_gemm", tc_any=self.tensor_cores)
+                **self._gemm_kw)
             if need_dx:
-                _mm(n, t.Dx, nc, 1.0, dXbig, 0, nc, wexp, t.M_off, nc, dx, r0 * t.Dx, t.Dx, tb=True, tag="segnn_gemm", tc_any=self.tensor_cores)
+                _mm(n, t.Dx, nc, 1.0, dXbig, 0, nc, wexp, t.M_off, nc, dx, r0 * t.Dx, t.Dx, tb=True, **self._gemm_kw)
         return dx
 
     # -- whole model ------------------------------------------------------------------------------------

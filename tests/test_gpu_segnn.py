@@ -30,7 +30,7 @@ def _close(got, want, what, rtol=RTOL, scale=None):
     assert err <= rtol * max(scale, 1e-30), f"{what}: max err {err:.3e} vs scale {scale:.3e} (rel {err / max(scale, 1e-30):.2e})"
 
 
-def _run(kw, irreps, x, k, lmax_attr, n_rb, pbc, vel, n_glob=0, lowering="dense"):
+def _run(kw, irreps, x, k, lmax_attr, n_rb, pbc, vel, n_glob=0, lowering="dense", tc=True):
     from eqnn_jax_b200 import graph_utils as GU
     from eqnn_jax_b200.equivariant_graph_utils import get_equivariant_graph
     from eqnn_jax_b200.irreps import Irreps
@@ -67,7 +67,7 @@ def _run(kw, irreps, x, k, lmax_attr, n_rb, pbc, vel, n_glob=0, lowering="dense"
                                 torch.tensor(g.receivers).cuda(), g.n_node, g.n_edge, None,
                                 None if glob is None else torch.tensor(glob).cuda(), lmax_attr,
                                 steerable_velocities=vel, apply_pbc=gpbc, n_radial_basis=n_rb, r_max=1.5)
-    model = SEGNN(lowering=lowering, **kw)
+    model = SEGNN(lowering=lowering, tensor_cores=tc, **kw)
     params = model.init(0, gst)
     params.load_tree(tree)
     cott = torch.tensor(cot, dtype=torch.float32).cuda()
@@ -91,13 +91,13 @@ def _run(kw, irreps, x, k, lmax_attr, n_rb, pbc, vel, n_glob=0, lowering="dense"
     (dict(d_hidden=32, n_layers=2, message_passing_steps=1, message_passing_agg="mean", task="graph", output_irreps="1x0e",
           n_outputs=2), "1o", 3, 1, 0, False, False, 12),
 ])
-@pytest.mark.parametrize("lowering", ["dense", "blocked"])
-def test_segnn_forward_and_gradients(kw, irreps, F, lmax_attr, n_rb, pbc, vel, n_glob, lowering):
+@pytest.mark.parametrize("lowering,tc", [("dense", True), ("blocked", True), ("dense", False)])
+def test_segnn_forward_and_gradients(kw, irreps, F, lmax_attr, n_rb, pbc, vel, n_glob, lowering, tc):
     rng = np.random.default_rng(len(irreps) + lmax_attr)
     B, N, k = 2, 60, 6
     x = rng.normal(size=(B, N, F)).astype(np.float32)
     x[..., :3] = rng.uniform(0.0, 3.4, size=(B, N, 3))
-    got, want, params, p = _run(kw, irreps, x, k, lmax_attr, n_rb, pbc, vel, n_glob, lowering=lowering)
+    got, want, params, p = _run(kw, irreps, x, k, lmax_attr, n_rb, pbc, vel, n_glob, lowering=lowering, tc=tc)
     _close(got, want, "output")
     gt = params.grad_tree
     scales = {}
