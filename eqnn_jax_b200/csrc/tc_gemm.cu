@@ -312,6 +312,12 @@ GtPlan gt_plan(int64_t M, int64_t N, int64_t K) {
     if (ks > most) ks = most;
     if (ks < 1) ks = 1;
   }
+  // The tensor core adds into the fp32 accumulator without round-to-nearest, an error that grows with the number of
+  // products summed in TMEM (2e-5 of the result after 3000, measured): no split accumulates more than 1024 k
+  // entries, the partials are summed in fp32 registers by the reduction kernel.  (Bounded by 256 MB of partials.)
+  const int64_t for_accuracy = (K + 1023) / 1024;
+  const int64_t fits = (int64_t)(256u << 20) / (M * N * (int64_t)sizeof(float));
+  if (ks < for_accuracy) ks = for_accuracy < fits ? for_accuracy : (fits > ks ? fits : ks);
   int64_t per = (K + ks - 1) / ks;
   per = (per + 31) / 32 * 32;
   g.k_per_split = per;

@@ -281,7 +281,7 @@ def test_tensor_core_3xtf32_gemm_matches_fp64(case, M):
     assert _rel(got, want) < 3e-6
 
 
-@pytest.mark.parametrize("case", ["fwd", "fwd_acc", "dgrad", "wgrad", "wgrad_acc", "small_k", "offsets"])
+@pytest.mark.parametrize("case", ["fwd", "fwd_acc", "dgrad", "wgrad", "wgrad_acc", "wgrad_long", "small_k", "offsets"])
 def test_general_tensor_core_gemm_matches_fp64(case):
     """General 3xTF32 tcgen05 GEMM (EQNN_GEMM_TF32X3_ANY; the SEGNN dense-lowered layers): unaligned leading
     dimensions, row / column tails, transposed operands, K split over CTAs, accumulation -- against fp64."""
@@ -301,8 +301,8 @@ def test_general_tensor_core_gemm_matches_fp64(case):
         C = torch.full((M, N), float("nan")).cuda()
         _mm(M, N, K, 1.0, dev(A), 0, K, dev(W), 0, K, C, 0, N, tb=True, tc_any=True)
         want = A @ W.t()
-    elif case in ("wgrad", "wgrad_acc"):                 # x^T @ dXbig: A transposed, K = rows, split over CTAs
-        M, N, K = 170, 768, 20011
+    elif case in ("wgrad", "wgrad_acc", "wgrad_long"):   # x^T @ dXbig: A transposed, K = rows, split over CTAs
+        M, N, K = 170, 768, (70001 if case == "wgrad_long" else 20011)   # long: accumulation stays <= 1024 per split
         X, D, C0 = r64(K, M), r64(K, N), r64(M, N)
         C = dev(C0)
         _mm(M, N, K, 1.0, dev(X), 0, M, dev(D), 0, N, C, 0, N, ta=True, accumulate=case == "wgrad_acc", tc_any=True)
