@@ -160,6 +160,263 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------
+# the other model families on the path: SEGNN (cfg-3) and EGNN (cfg-4)
+# --------------------------------------------------------------------------------------
+SEGNN_KW = dict(d_hidden=128, n_layers=3, message_passing_steps=3, message_passing_agg="sum", task="node",
+                output_irreps="1x1o", l_max_hidden=2, residual=True)        # train_velocities.py:364-378,454-458
+SEGNN_LMAX_ATTR = 1
+EGNN_KW = dict(message_passing_steps=4, d_hidden=128, n_layers=3, activation="gelu", soft_edges=False,
+               positions_only=True, tanh_out=False, decouple_pos_vel_updates=True, message_passing_agg="mean",
+               readout_agg="mean", mlp_readout_widths=(4, 2, 2), task="graph", n_outputs=2, n_radial_basis=32,
+               r_max=0.6)                                                   # train_cosmology.py:67-81,403-408
+FAMILIES = {
+    "segnn": dict(metric="SEGNN fwd+bwd edges/sec", graphs=8, cpu_nodes=1000,
+                  name="SEGNN l_max_hidden 2, attributes l<=1, 3 steps x 3 layers, node task -> 1x1o, 5000-node kNN-20 "
+                       "PBC clouds (cfg-3)"),
+    "egnn": dict(metric="EGNN fwd+bwd edges/sec", graphs=32, cpu_nodes=5000,
+                 name="EGNN positions-only, 4 steps, graph regression, 5000-node kNN-20 PBC clouds (cfg-4)"),
+}
+
+
+def family_targets(kind, halos, y):
+    """Synthetic targets: SEGNN regresses per-node velocities (train_velocities.py), EGNN the 2 graph labels."""
+    return halos[..., 3:6].copy() if kind == "segnn" else y
+
+
+def cpu_family_step(kind, pos, target, tree, threads):
+    """One fwd+bwd of the oracle restatement (dense PBC kNN + steerable attributes + model + MSE grads) on the host."""
+    import torch
+    from oracle import graph_ref as G
+    torch.set_num_threads(threads)
+    pbc = G.get_apply_pbc((STD[:3] / BOX).astype(np.float32))
+    t0 = time.perf_counter()
+    g = G.build_graph(pos, None, K_NN, apply_pbc=pbc)
+    if kind == "segnn":
+        from oracle import nequip_ref as NQ, segnn_ref as S
+        from oracle.e3nn_ref import IrrepsArray as OIA
+        st = G.get_equivariant_graph(OIA("1o", torch.tensor(pos, dtype=torch.float32)), pos, None, g.senders, g.receivers,
+                                     g.n_node, g.n_edge, None, None, SEGNN_LMAX_ATTR, apply_pbc=pbc)
+        p = NQ.to_torch(tree, torch.float32, requires_grad=True)
+        out = S.apply_batched(p, S.SEGNNConfig(**SEGNN_KW), st, dtype=torch.float32).array
+    else:
+        from oracle import egnn_ref as EG, nequip_ref as NQ
+        p = NQ.to_torch(tree, torch.float32, requires_grad=True)
+        cfg = EG.EGNNConfig(**{**EGNN_KW, "apply_pbc": pbc})
+        out = EG.apply_batched(p, cfg, g._replace(nodes=torch.tensor(pos), edges=None))
+    loss = ((out - torch.tensor(target)) ** 2).mean()
+    loss.backward()
+    return time.perf_counter() - t0, float(loss.detach())
+
+
+def cpu_family_baseline(kind, n_nodes, reps, warm=1):
+    threads = os.cpu_count() or 1
+    halos, y = synth_batch(0, 1)
+    halos, y = halos[:, :n_nodes], y
+    pos, target = halos[..., :3].copy(), family_targets(kind, halos, y)
+    if kind == "segnn":
+        from oracle import segnn_ref as S
+        from oracle.so3 import Irreps as OI
+        tree = S.init_params(S.SEGNNConfig(**SEGNN_KW), "1o", OI.spherical_harmonics(SEGNN_LMAX_ATTR), "1x0e", seed=0)
+    else:
+        from oracle import egnn_ref as EG
+        tree = EG.init_params(EG.EGNNConfig(**EGNN_KW), 3, seed=0)
+    for _ in range(warm):
+        cpu_family_step(kind, pos, target, tree, threads)
+    ts = [cpu_family_step(kind, pos, target, tree, threads)[0] for _ in range(reps)]
+    edges = n_nodes * K_NN
+    return edges * len(ts) / sum(ts), 1e3 * sum(ts) / len(ts), threads, \
+        f"1 cloud of {n_nodes} nodes ({edges} edges) per step: dense PBC kNN + attributes + fwd + bwd, torch-CPU fp32 " \
+        f"restatement (JAX/e3nn-jax not installable in this image)"
+
+
+def run_family(args):
+    kind = args.workload
+    fam = FAMILIES[kind]
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return
+        val, ms, threads, sample = cpu_family_baseline(kind, fam["cpu_nodes"], max(args.steps, 1), max(args.warmup, 1))
+        print(json.dumps({"impl": "reference", "metric": fam["metric"], "value": val, "unit": "edges/s", "n_gpus": args.gpus,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": fam["name"], "graphs_per_step": 1},
+                          "cpu_baseline": {"value": val, "unit": "edges/s", "cores": threads, "kind": "port", "sample": sample},
+                          "e2e": {"value": val, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}),
+              flush=True)
+        return
+    import torch
+    import torch.distributed as dist
+    from eqnn_jax_b200 import _lib, graph_utils as GU, ops
+    from eqnn_jax_b200.train import TrainState, allreduce_mean_, cosine_decay_lr
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py --impl b200 needs a GPU (no CPU fallback exists for this path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+    B = args.graphs_per_gpu if "--graphs-per-gpu" in sys.argv else fam["graphs"]
+    E_step = B * N_NODES * K_NN
+    pbc = GU.get_apply_pbc(std=(STD[:3] / BOX).astype(np.float32))
+    host = []
+    for j in range(2):
+        h, y = synth_batch(1000 * rank + 100 * j, B)
+        host.append((torch.from_numpy(h[..., :3].copy()).pin_memory(),
+                     torch.from_numpy(np.ascontiguousarray(family_targets(kind, h, y))).pin_memory()))
+    resident = [(x.to(dev), t.to(dev)) for x, t in host]
+
+    if kind == "segnn":
+        from eqnn_jax_b200.equivariant_graph_utils import get_equivariant_graph
+        from eqnn_jax_b200.irreps import Irreps
+        from eqnn_jax_b200.nequip import IrrepsArray
+        from eqnn_jax_b200.segnn import SEGNN
+        model = SEGNN(**SEGNN_KW)
+
+        def make_graph(x, s, r):
+            return get_equivariant_graph(IrrepsArray(Irreps("1o"), x), x, None, s, r, None, None, None, None,
+                                         SEGNN_LMAX_ATTR, apply_pbc=pbc)
+    else:
+        from eqnn_jax_b200.egnn import EGNN
+        model = EGNN(apply_pbc=pbc, **EGNN_KW)
+
+        def make_graph(x, s, r):
+            return GU.GraphsTuple(nodes=x, edges=None, receivers=r, senders=s, globals=None, n_node=None, n_edge=None)
+
+    def graph_of(x):
+        s, r, _ = ops.knn_pbc(x, K_NN, pbc.cell, pbc.cell_inv, want_dr=False)
+        return make_graph(x, s, r)
+
+    params = model.init(0, graph_of(resident[0][0]))      # same seed on every rank = replicated parameters
+    state = TrainState(model, params)
+    n = params.flat.numel()
+    loss_slot = state.bucket[n:]
+
+    def train(x, t):
+        """kNN graph + attributes, forward, MSE, backward, gradient all-reduce, AdamW (the step of eqnn_jax_b200.train)."""
+        g = graph_of(x)
+
+        def grad_fn(out):
+            o2, t2 = out.reshape(-1, out.shape[-1]), t.reshape(-1, t.shape[-1])
+            if state._gpred is None or state._gpred.shape != o2.shape:
+                state._gpred = torch.empty_like(o2)
+            ops.mse_loss(o2, t2, 1.0, loss_slot, state._gpred)
+            return state._gpred.view(out.shape)
+
+        model.forward_backward(params, g, grad_fn)
+        allreduce_mean_(state.bucket, world)
+        state.step += 1
+        lr = cosine_decay_lr(state.step - 1, state.learning_rate, state.decay_steps)
+        ops.adamw(params.flat, params.grad, state.mu, state.nu, lr, 0.9, 0.999, 1e-8, state.weight_decay, state.step)
+        return loss_slot
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
+        e0.record()
+        for i in range(k):
+            fn(i)
+        e1.record()
+        barrier()
+        t1 = time.time()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), t0, t1
+
+    xbuf, tbuf = torch.empty_like(resident[0][0]), torch.empty_like(resident[0][1])
+    loss_host = torch.empty((1,), dtype=torch.float32).pin_memory()
+
+    def step_resident(i):
+        train(*resident[i % 2])
+
+    def step_e2e(i):
+        x, t = host[i % 2]
+        xbuf.copy_(x, non_blocking=True)
+        tbuf.copy_(t, non_blocking=True)
+        loss_host.copy_(train(xbuf, tbuf), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        step_resident(i)
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = L.eqnn_launch_count()
+    ms, t0, t1 = timed(step_resident, args.steps)
+    launches = L.eqnn_launch_count() - l0
+    clocks = sampler.stop(t0, t1) if sampler else None
+    for i in range(2):
+        step_e2e(i)
+    ms_e2e, _, _ = timed(step_e2e, args.steps)
+    ops.TIMER = ops.KernelTimer()
+    step_resident(0)
+    prof = ops.TIMER.summary()
+    ops.TIMER = None
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    if kind == "segnn":
+        plan = model.plan(Irreps("1o"), SEGNN_LMAX_ATTR, 1)
+        Nt, Et = B * N_NODES, E_step
+        edge_layers = {id(t) for st in plan.steps for t in st["edge"]}
+        flops = blocked = 0.0
+        for t in plan.tplgs:
+            if not t.live:
+                continue
+            rows = Et if id(t) in edge_layers else Nt
+            passes = 2 if t is plan.embed else 3                 # forward, weight gradient (+ data gradient)
+            flops += passes * 2.0 * rows * t.Dx * t.Dy * t.Do
+        n_g, ms_g = prof.get("segnn_gemm", (0, 0.0))
+        tf = flops / (ms_g * 1e-3) / 1e12 if ms_g > 0 else float("nan")
+        roof = {"kernel": "TensorProductLinearGate GEMMs fwd + dgrad + wgrad (tc_gemm_kernel: tcgen05 kind::tf32, 3 MMAs "
+                          "per product, any strides)", "bound": "tensor", "achieved": tf, "peak": pk["tf_sust"],
+                "unit": "TFLOP/s", "frac": tf / pk["tf_sust"], "traffic": None,
+                "peak_source": f"bf16_tflops_sustained of {pk['which']}", "launches_per_step": n_g, "ms_per_step": ms_g,
+                "flops_per_step": flops,
+                "note": "algorithmic flops = 2 Dx Dy Do per row and pass of the dense-lowered layer, 1 per product; the "
+                        "kernel issues 3 tf32 MMAs per product at half the bf16 rate, so its own ceiling is peak / 6"}
+    else:
+        per_edge_step = (128 + 512) + 4 * 1024 + 516 + (1028 + 4 * 1536 + 640) + (640 + 4 * 1024 + 516)
+        n_f, ms_f = prof.get("egnn_mlp_fwd", (0, 0.0))
+        n_b, ms_b = prof.get("egnn_mlp_bwd", (0, 0.0))
+        gbs = E_step * EGNN_KW["message_passing_steps"] * per_edge_step / ((ms_f + ms_b) * 1e-3) / 1e9 \
+            if ms_f + ms_b > 0 else float("nan")
+        roof = {"kernel": "edge / coordinate MLP GEMMs fwd + dgrad + wgrad (tc_rowgemm_kernel / tc_wgrad_kernel)",
+                "bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
+                "traffic": None, "peak_source": f"hbm_gbs of {pk['which']}", "bytes_per_edge_step": per_edge_step,
+                "launches_per_step": n_f + n_b, "ms_per_step": ms_f + ms_b,
+                "note": "algorithmic traffic of the 32 -> 128 -> (4x) 128 -> 1 per-edge chain: fwd 640 | 4x1024 | 516; "
+                        "dgrad 1028 | 4x1536 | 640; wgrad 640 | 4x1024 | 516 bytes per edge and message-passing step"}
+    line = {"metric": fam["metric"], "value": world * E_step * args.steps / (ms * 1e-3), "unit": "edges/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": fam["name"], "graphs_per_gpu": B, "edges_per_gpu_step": E_step,
+                       "step": "kNN graph build + attributes + forward + MSE + backward + grad all-reduce + AdamW",
+                       "l2": "inputs larger than L2 (per-step working set of several GB)", "parallelism": f"dp{world}"},
+            "e2e": {"value": world * E_step * args.steps / (ms_e2e * 1e-3), "unit": "edges/s",
+                    "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": int(xbuf.numel() * 4 + tbuf.numel() * 4), "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
+            "breakdown_ms_per_step": {k: t for k, (c, t) in sorted(prof.items())}}
+    if world == 1 and not args.no_cpu_baseline:
+        val, _, threads, sample = cpu_family_baseline(kind, fam["cpu_nodes"], 2)
+        line["cpu_baseline"] = {"value": val, "unit": "edges/s", "cores": threads, "kind": "port", "sample": sample}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------
 # B200 arm
 # --------------------------------------------------------------------------------------
 def main():
@@ -173,8 +430,11 @@ def main():
     ap.add_argument("--profile-steps", type=int, default=2)
     # cfg2 = the workload BASELINE.json quotes the metric on (default); cfg5 = its large-graph scaling case
     # (50 000-node clouds, k = 32, l_max = 3), 2 clouds per GPU unless --graphs-per-gpu is given
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg5"])
+    # segnn / egnn: the other model families of the path (BASELINE.json configs[2], configs[3]) through the same step
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg5", "segnn", "egnn"])
     args = ap.parse_args()
+    if args.workload in FAMILIES:
+        return run_family(args)
     global N_NODES, K_NN
     workload_name = "NequIP lmax=2, 5000-node kNN-20 PBC clouds, graph regression (cfg-2)"
     if args.workload == "cfg5":
