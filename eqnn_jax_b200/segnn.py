@@ -40,7 +40,7 @@ from .graph_utils import GraphsTuple
 from .irreps import Irreps, balanced_irreps
 from .nequip import IrrepsArray, NequIPParams as FlatParams, _mm, normalize_constant
 
-ROW_BLOCK = 1 << 16      # rows per Xbig block (bounds the (rows, Dy*Do) temporaries)
+ROW_BLOCK = 1 << 18      # rows per Xbig block: bounds the (rows, Dy*Do) temporaries (0.8 GB each at Dy*Do = 768)
 
 
 # --------------------------------------------------------------------------------------------------
