@@ -122,6 +122,30 @@ def test_segnn_forward_and_gradients(kw, irreps, F, lmax_attr, n_rb, pbc, vel, n
     assert n_dead > 0
 
 
+@pytest.mark.parametrize("lowering", ["dense", "blocked"])
+def test_segnn_row_blocks(monkeypatch, lowering):
+    """Edge rows are processed in blocks of ROW_BLOCK (weight gradients accumulate across blocks): same result with
+    blocks of 100 rows (8 blocks, a ragged last one) as the oracle."""
+    from eqnn_jax_b200 import segnn as SG
+    monkeypatch.setattr(SG, "ROW_BLOCK", 100)
+    rng = np.random.default_rng(5)
+    kw = dict(d_hidden=32, n_layers=2, message_passing_steps=1, message_passing_agg="sum", task="node",
+              output_irreps="1x1o", l_max_hidden=2, residual=True)
+    x = rng.uniform(0.0, 3.4, size=(2, 60, 3)).astype(np.float32)
+    got, want, params, p = _run(kw, "1o", x, 6, 1, 0, True, False, 0, lowering=lowering)
+    _close(got, want, "output")
+    gt = params.grad_tree
+    gmax = max(float(w.grad.abs().max()) for _, w in _leaves(p) if w.grad is not None)
+    for path, w in _leaves(p):
+        if w.grad is None or not path[0].startswith("TensorProductLinearGate"):
+            continue
+        g = gt
+        for q in path:
+            g = g[q]
+        err = np.abs(g.cpu().numpy().astype(np.float64) - w.grad.numpy()).max()
+        assert err <= RTOL * max(float(w.grad.abs().max()), 1e-30) + 1e-6 * gmax, ("/".join(path), err)
+
+
 def test_segnn_reference_equivariance_property():
     """tests/test_equivariance.py:288-310 on the B200 path: f(R x) = R f(x) for the 7-feature node task."""
     from eqnn_jax_b200.equivariant_graph_utils import get_equivariant_graph
