@@ -69,6 +69,8 @@ SIGNATURES: Dict[str, tuple] = {
     "eqnn_copy_cols": (_i, [_p, _i, _i, _i, _i64, _i, _i, _p, _i, _i, _p]),
     "eqnn_softgate_fwd": (_i, [_p, _p, _i64, _p, _p]),
     "eqnn_softgate_bwd": (_i, [_p, _p, _p, _i64, _p, _p, _p]),
+    "eqnn_dense_wgrad_workspace_bytes": (_sz, [_i64, _i64, _i64]),
+    "eqnn_dense_wgrad_f32": (_i, [_i64, _i64, _i64, _f, _p, _i64, _i, _f, _p, _i64, _p, _i64, _p, _i, _p, _sz, _p]),
     "eqnn_colsum_workspace_bytes": (_sz, [_i]),
     "eqnn_colsum_tall": (_i, [_p, _i64, _i, _p, _p, _sz, _p]),
     "eqnn_pool_fwd": (_i, [_p, _i, _i, _i, _i, _p, _p]),

@@ -446,7 +446,8 @@ int eqnn_tc_rowgemm_try(int64_t M, int64_t N, int64_t K, float alpha, const floa
 size_t eqnn_tc_wgrad_workspace_bytes(int64_t M, int64_t N, int64_t K);
 int eqnn_tc_wgrad_try(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t sam, int64_t sak,
                       const float* B, int64_t sbk, int64_t sbn, float* C, int64_t scm, int64_t scn, int accumulate,
-                      int pro, float pro_scale, int epi, void* ws, size_t ws_bytes, cudaStream_t st);
+                      int pro, float pro_scale, int epi, void* ws, size_t ws_bytes, cudaStream_t st,
+                      float* colsum_out = nullptr);
 
 size_t eqnn_tc_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K);
 int eqnn_tc_gemm_try(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t sam, int64_t sak,
@@ -546,4 +547,33 @@ extern "C" int eqnn_gemm_f32(int64_t M, int64_t N, int64_t K, float alpha, const
   if (s.ksplit > 1) splitk_reduce_kernel<<<(unsigned)ceil_div64(M * N, 256), 256, 0, st>>>(p);
   EQNN_CHECK_LAUNCH_N(s.ksplit > 1 ? 2 : 1);
   return EQNN_OK;
+}
+
+// ---- parameter gradients of a Dense layer over a tall batch: kernel and bias in one pass over G ----------------
+extern "C" size_t eqnn_colsum_workspace_bytes(int N);
+extern "C" int eqnn_colsum_tall(const float* x, int64_t M, int N, float* y, void* ws, size_t ws_bytes,
+                                eqnn_stream_t stream);
+
+extern "C" size_t eqnn_dense_wgrad_workspace_bytes(int64_t M, int64_t N, int64_t K) {
+  const size_t a = eqnn_gemm_workspace_bytes(M, N, K), b = eqnn_colsum_workspace_bytes((int)N);
+  return a > b ? a : b;
+}
+
+extern "C" int eqnn_dense_wgrad_f32(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t lda, int pro,
+                                    float pro_scale, const float* G, int64_t ldg, float* gW, int64_t ldw, float* gb,
+                                    int flags, void* ws, size_t ws_bytes, eqnn_stream_t stream) {
+  EQNN_CHECK_ARG(M >= 1 && N >= 1 && K >= 0 && A && G && gW && gb && lda >= M && ldg >= N && ldw >= N,
+                 "dense_wgrad: bad argument");
+  EQNN_CHECK_ARG(!(flags & EQNN_GEMM_ACCUMULATE), "dense_wgrad: accumulation is not supported");
+  if (flags & EQNN_GEMM_TF32X3) {
+    const int w = eqnn_tc_wgrad_try(M, N, K, alpha, A, 1, lda, G, ldg, 1, gW, ldw, 1, 0, pro, pro_scale, 0, ws, ws_bytes,
+                                    as_stream(stream), gb);
+    if (w == 1) return EQNN_OK;
+    if (w < 0) return -w;
+  }
+  int rc = eqnn_gemm_f32(M, N, K, alpha, A, 1, lda, G, ldg, 1, gW, ldw, 1, flags, pro, pro_scale, 0, nullptr, 0, 1.f, ws,
+                         ws_bytes, stream);
+  if (rc) return rc;
+  EQNN_CHECK_ARG((reinterpret_cast<uintptr_t>(G) & 15) == 0 && ldg == N, "dense_wgrad: G must be dense and 16-byte aligned");
+  return eqnn_colsum_tall(G, K, (int)N, gb, ws, ws_bytes, stream);
 }

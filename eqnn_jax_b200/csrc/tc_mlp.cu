@@ -396,6 +396,7 @@ struct WgradP {
   int64_t E;
   float pro_scale;
   float* partial;   // [gridDim.x][MI][NPAD]
+  float* colsum;    // [gridDim.x][N] per-CTA column sums of G (the bias gradient of a Dense layer), or NULL; GMODE 0
 };
 
 // wgrad thread layout (warpgroup-aligned so that registers can be re-balanced with setmaxnreg):
@@ -524,6 +525,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const WgradP p)
       *reinterpret_cast<float4*>(gen_base + off_lo) = lo;
     };
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    // Column sums of G ride along: thread pt always meets the same four columns (WG_PT is a multiple of N / 4), so
+    // they accumulate in one register quadruple -- the Dense bias gradient costs no second pass over G.
+    static_assert(GMODE != 0 || WG_PT % (N / 4) == 0, "a transform thread must keep its G columns across chunks");
+    const bool want_cs = (GMODE == 0) && p.colsum != nullptr;
+    float4 cs = zero4;
     for (uint32_t g = 0; g < total; ++g) {
       const int s = g % NSTAGE, rs = g % RAW_NS;
       const int64_t e0 = (c_beg + g) * 32;
@@ -553,6 +559,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const WgradP p)
             const float4 v = (row < rows) ? *reinterpret_cast<const float4*>(graw + (uint32_t)f * 16u) : zero4;
             const uint32_t off = (c4 >> 3) * 4096 + sw128_base32(row, c4 & 7);
             put(sb + off, sb + B_HALF_W + off, v, std::false_type{});
+            if (want_cs) {
+              cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w;
+            }
           }
         }
       } else if (pt < 128) {
@@ -573,6 +582,21 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const WgradP p)
       if (lane == 0) {
         mbar_arrive(a_full(s));       // operands published to the MMA warp
         mbar_arrive(r_empty(rs));     // raw slot may be refilled
+      }
+    }
+    if (GMODE == 0 && want_cs) {
+      // the raw ring is dead once every transform warp has left the loop: reduce the WG_PT / (N / 4) partial sums
+      // of every column through it, in a fixed order
+      constexpr int NQ = N / 4, NG = WG_PT / NQ;
+      float* scratch = reinterpret_cast<float*>(gen_base + (raw0 - base));
+      asm volatile("bar.sync 1, %0;" ::"n"(WG_PT) : "memory");
+      *reinterpret_cast<float4*>(scratch + (pt / NQ) * N + 4 * (pt % NQ)) = cs;
+      asm volatile("bar.sync 1, %0;" ::"n"(WG_PT) : "memory");
+      if (pt < N) {
+        float t = 0.f;
+#pragma unroll 4
+        for (int q = 0; q < NG; ++q) t += scratch[q * N + pt];
+        p.colsum[(size_t)blockIdx.x * N + pt] = t;
       }
     }
   } else if (warp == WG_MMA_WARP) {
@@ -677,6 +701,15 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
   }
 }
 
+// y[n] = sum over the per-CTA column sums, CTA order (deterministic)
+__global__ void colsum_parts_reduce_kernel(const float* __restrict__ parts, int n_parts, int N, float* __restrict__ y) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float t = 0.f;
+  for (int q = 0; q < n_parts; ++q) t += parts[(size_t)q * N + n];
+  y[n] = t;
+}
+
 template <int MI, int N, int GMODE, int PRO>
 int launch_wgrad(const WgradP& p, int grid, cudaStream_t st) {
   constexpr uint32_t SMEM = WgradCfg<MI, N, GMODE>::SMEM;
@@ -698,14 +731,17 @@ size_t eqnn_tc_wgrad_workspace_bytes(int64_t M, int64_t N, int64_t K) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  return (size_t)sms * 128 * 128 * sizeof(float);
+  return (size_t)sms * (128 * 128 + 128) * sizeof(float);      // weight partials + column-sum partials
 }
 
 // dW[M x N] = alpha * pro(X)^T @ G with the edge dimension as K.  Same return convention as below.
+// colsum_out (optional, row-major G with N = 128 only): y[n] = sum_k G[k, n], accumulated by the same pass over G.
 int eqnn_tc_wgrad_try(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t sam, int64_t sak,
                       const float* B, int64_t sbk, int64_t sbn, float* C, int64_t scm, int64_t scn, int accumulate,
-                      int pro, float pro_scale, int epi, void* ws, size_t ws_bytes, cudaStream_t st) {
+                      int pro, float pro_scale, int epi, void* ws, size_t ws_bytes, cudaStream_t st,
+                      float* colsum_out) {
   if (accumulate || epi != 0 || K < 4096 || scn != 1) return 0;
+  if (colsum_out && !(N == 128 && sbn == 1)) return 0;
   if (!(M == 32 || M == 64 || M == 128) || sam != 1 || sak % 4 != 0 || (reinterpret_cast<uintptr_t>(A) & 15)) return 0;
   if (reinterpret_cast<uintptr_t>(B) & 15) return 0;
   int dev = 0, sms = 148;
@@ -716,10 +752,12 @@ int eqnn_tc_wgrad_try(int64_t M, int64_t N, int64_t K, float alpha, const float*
   WgradP p;
   p.X = A; p.ldx = sak; p.G = B; p.E = K; p.pro_scale = pro_scale; p.n_valid = (int)N;
   p.partial = reinterpret_cast<float*>(ws);
+  p.colsum = nullptr;
   int rc = 0, npad = 0;
   if (N == 128 && sbn == 1 && sbk % 4 == 0) {
     npad = 128; p.ldg = sbk;
-    if (!ws || ws_bytes < (size_t)grid * M * npad * 4) return 0;
+    if (!ws || ws_bytes < (size_t)grid * (M * npad + (colsum_out ? npad : 0)) * 4) return 0;
+    if (colsum_out) p.colsum = p.partial + (size_t)grid * M * npad;
     if (M == 128) rc = pro ? launch_wgrad<128, 128, 0, 1>(p, grid, st) : launch_wgrad<128, 128, 0, 0>(p, grid, st);
     else if (M == 64) rc = pro ? launch_wgrad<64, 128, 0, 1>(p, grid, st) : launch_wgrad<64, 128, 0, 0>(p, grid, st);
     else rc = pro ? launch_wgrad<32, 128, 0, 1>(p, grid, st) : launch_wgrad<32, 128, 0, 0>(p, grid, st);
@@ -736,6 +774,10 @@ int eqnn_tc_wgrad_try(int64_t M, int64_t N, int64_t K, float alpha, const float*
   const int tot = (int)(M * N);
   wgrad_reduce_kernel<<<(tot + 31) / 32, 256, 0, st>>>(p.partial, grid, (int)M, npad, (int)N, alpha, C, scm);
   eqnn_count_launches(1);
+  if (p.colsum) {
+    colsum_parts_reduce_kernel<<<1, 128, 0, st>>>(p.colsum, grid, (int)N, colsum_out);
+    eqnn_count_launches(1);
+  }
   return 1;
 }
 

@@ -424,9 +424,8 @@ class EGNN:
                 gated = (l == nE and st["phi_a"] is not None)      # this layer's input is the soft-gated message
                 if gated:
                     a_prev, pro = sv["Mg"], 0
-                _mm(fan, d, Et, 1.0, a_prev, 0, fan, dZ, 0, d, gtheta, ko, d, ta=True, pro=pro, pro_scale=1.0,
-                    tag="egnn_mlp_bwd", tf32x3=tc)
-                ops.colsum_tall(dZ, Et, d, gtheta, y_off=bo)
+                ops.dense_wgrad(fan, d, Et, a_prev, 0, fan, dZ, d, gtheta, ko, d, gtheta, bo, pro=pro, pro_scale=1.0,
+                                tf32x3=tc, tag="egnn_mlp_bwd")            # kernel and bias gradients, one pass over dZ
                 if gated:
                     ka, ba = st["phi_a"]
                     ZL, Za = acts[l - 1], sv["Za"]
@@ -436,9 +435,8 @@ class EGNN:
                         ops.egnn_segment_rows_bwd(dC, dC_ld, dC_off, d, None, 0, rowptr, Nt, agg, dM)
                     dZa = torch.empty((Et, d), **f32)
                     ops.softgate_bwd(ZL, Za, dM, dZa, dM)           # dM <- dM * sigmoid(Za)  (first branch into Z_L)
-                    _mm(d, d, Et, 1.0, ZL, 0, d, dZa, 0, d, gtheta, ka, d, ta=True, pro=1, pro_scale=1.0,
-                        tag="egnn_mlp_bwd", tf32x3=tc)
-                    ops.colsum_tall(dZa, Et, d, gtheta, y_off=ba)
+                    ops.dense_wgrad(d, d, Et, ZL, 0, d, dZa, d, gtheta, ka, d, gtheta, ba, pro=1, pro_scale=1.0, tf32x3=tc,
+                                    tag="egnn_mlp_bwd")
                     # dZ_L = (dZa @ Ka^T + dM) * gelu'(Z_L): second branch accumulated in the epilogue (EPI 3)
                     _mm(Et, d, d, 1.0, dZa, 0, d, theta, ka, d, dM, 0, d, tb=True, epi=3, aux=ZL, ld_aux=d, epi_scale=1.0,
                         tag="egnn_mlp_bwd", tf32x3=tc)

@@ -398,6 +398,18 @@ def softgate_bwd(z, za, dm, dza, g1):
 _COLSUM_WS = GemmWorkspace()
 
 
+def dense_wgrad(M, N, K, A, a_off, lda, G, ldg, gW, w_off, ldw, gb, b_off, pro=0, pro_scale=1.0, tf32x3=False,
+                tag="dense_wgrad"):
+    """gW[M x N] = pro(A)^T G and gb[n] = sum_k G[k, n] in one pass over G (A: [K x M], G: [K x N], row-major)."""
+    L = lib()
+    ws, ws_bytes = _GEMM_WS.get(L.eqnn_dense_wgrad_workspace_bytes(M, N, K), gW.device)
+    t0 = TIMER.begin() if TIMER else None
+    check(L.eqnn_dense_wgrad_f32(M, N, K, 1.0, _off(A, a_off), lda, pro, float(pro_scale), _ptr(G), ldg, _off(gW, w_off),
+                                 ldw, _off(gb, b_off), 2 if tf32x3 else 0, ws, ws_bytes, _stream()), "dense_wgrad")
+    if TIMER:
+        TIMER.end(tag, t0)
+
+
 def colsum_tall(x, M, N, y, y_off=0):
     need = lib().eqnn_colsum_workspace_bytes(N)
     ws, ws_bytes = _COLSUM_WS.get(need, x.device)

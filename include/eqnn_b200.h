@@ -296,6 +296,15 @@ int eqnn_copy_cols(const float* src, int ld_src, int col_src, int width, int64_t
 int eqnn_softgate_fwd(const float* z, const float* za, int64_t n, float* m, eqnn_stream_t stream);
 int eqnn_softgate_bwd(const float* z, const float* za, const float* dm, int64_t n, float* dza, float* g1,
                       eqnn_stream_t stream);
+/* Parameter gradients of a Dense layer (models/mlp.py, egnn.py phi_e / phi_x / phi_h) over a tall batch, one pass
+ * over G:  gW[M x N] = alpha * pro(A)^T G,  gb[n] = sum_k G[k, n]   (A: [K x M] rows lda, G: [K x N] rows ldg).
+ * With EQNN_GEMM_TF32X3 and a shape the tcgen05 weight-gradient kernel covers (M in {32, 64, 128}, N = 128,
+ * K >= 4096) the column sums are accumulated by the warps that already stream G into the tensor-core operands;
+ * other shapes run eqnn_gemm_f32 followed by eqnn_colsum_tall (G dense and 16-byte aligned).  Fixed-order sums. */
+size_t eqnn_dense_wgrad_workspace_bytes(int64_t M, int64_t N, int64_t K);
+int eqnn_dense_wgrad_f32(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t lda, int pro,
+                         float pro_scale, const float* G, int64_t ldg, float* gW, int64_t ldw, float* gb, int flags,
+                         void* ws, size_t ws_bytes, eqnn_stream_t stream);
 /* y[n] = sum_m x[m, n] for tall x (bias gradients of the edge MLPs): two-stage, fixed order */
 size_t eqnn_colsum_workspace_bytes(int N);
 int eqnn_colsum_tall(const float* x, int64_t M, int N, float* y, void* ws, size_t ws_bytes, eqnn_stream_t stream);

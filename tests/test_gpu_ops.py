@@ -324,3 +324,25 @@ def test_general_tensor_core_gemm_matches_fp64(case):
     assert torch.isfinite(C).all()
     err = (C.double().cpu() - want).abs().max().item()
     assert err <= 1e-5 * want.abs().max().item(), (case, err, want.abs().max().item())
+
+
+@pytest.mark.parametrize("M,N,K,pro,tc", [(128, 128, 70001, 1, True), (32, 128, 20000, 0, True), (64, 128, 5000, 1, True),
+                                           (128, 128, 3000, 0, True), (48, 128, 9000, 1, True), (128, 128, 9000, 1, False)])
+def test_dense_wgrad_kernel_and_bias_in_one_pass(M, N, K, pro, tc):
+    """eqnn_dense_wgrad_f32: gW = pro(A)^T G and gb = colsum(G); on the tcgen05 weight-gradient kernel the column sums
+    ride along with the operand transform (first three cases), other shapes fall back to GEMM + column sum."""
+    from eqnn_jax_b200 import ops
+    g = torch.Generator().manual_seed(M + K)
+    A = torch.randn(K, M, generator=g, dtype=torch.float64) * (2.0 if pro else 1.0)
+    G = torch.randn(K, N, generator=g, dtype=torch.float64)
+    inv_c = 1.0 / 0.652
+    want_w = (gelu(A) * inv_c if pro else A).t() @ G
+    want_b = G.sum(0)
+    buf = torch.full((M * N + N + 5,), float("nan")).cuda()
+    ops.dense_wgrad(M, N, K, A.float().cuda(), 0, M, G.float().cuda(), N, buf, 3, N, buf, 3 + M * N, pro=pro, pro_scale=inv_c,
+                    tf32x3=tc)
+    got_w = buf[3:3 + M * N].view(M, N).double().cpu()
+    got_b = buf[3 + M * N:3 + M * N + N].double().cpu()
+    assert torch.isnan(buf[:3]).all() and torch.isnan(buf[3 + M * N + N:]).all()
+    assert (got_w - want_w).abs().max().item() <= 1e-5 * want_w.abs().max().item()
+    assert (got_b - want_b).abs().max().item() <= 1e-5 * max(want_b.abs().max().item(), K ** 0.5)
