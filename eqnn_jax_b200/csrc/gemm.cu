@@ -562,8 +562,13 @@ extern "C" size_t eqnn_dense_wgrad_workspace_bytes(int64_t M, int64_t N, int64_t
 extern "C" int eqnn_dense_wgrad_f32(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t lda, int pro,
                                     float pro_scale, const float* G, int64_t ldg, float* gW, int64_t ldw, float* gb,
                                     int flags, void* ws, size_t ws_bytes, eqnn_stream_t stream) {
-  EQNN_CHECK_ARG(M >= 1 && N >= 1 && K >= 0 && A && G && gW && gb && lda >= M && ldg >= N && ldw >= N,
-                 "dense_wgrad: bad argument");
+  EQNN_CHECK_ARG(M >= 1 && N >= 1 && K >= 0 && gW && gb && ldw >= N, "dense_wgrad: bad argument");
+  if (K == 0) {                                        // empty batch: both gradients are zero
+    EQNN_CUDA(cudaMemset2DAsync(gW, (size_t)ldw * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M, as_stream(stream)));
+    EQNN_CUDA(cudaMemsetAsync(gb, 0, (size_t)N * sizeof(float), as_stream(stream)));
+    return EQNN_OK;
+  }
+  EQNN_CHECK_ARG(A && G && lda >= M && ldg >= N, "dense_wgrad: bad argument");
   EQNN_CHECK_ARG(!(flags & EQNN_GEMM_ACCUMULATE), "dense_wgrad: accumulation is not supported");
   if (flags & EQNN_GEMM_TF32X3) {
     const int w = eqnn_tc_wgrad_try(M, N, K, alpha, A, 1, lda, G, ldg, 1, gW, ldw, 1, 0, pro, pro_scale, 0, ws, ws_bytes,
