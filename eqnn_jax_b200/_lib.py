@@ -53,6 +53,7 @@ SIGNATURES: Dict[str, tuple] = {
     "eqnn_egnn_coord_fwd": (_i, [_p, _p, _i, _i, _p, _i, _p, _i, _p, _p, _p, _i, _p]),
     "eqnn_egnn_coord_bwd": (_i, [_p, _p, _i, _i, _p, _p, _i, _p, _i, _d, _p, _p, _p, _p, _p]),
     "eqnn_egnn_sender_acc": (_i, [_p, _p, _p, _i, _p, _p]),
+    "eqnn_segnn_tplg_fwd": (_i, [_p, _i, _i, _p, _p, _i, _i, _i, _p, _i, _i, _i64, _p, _i, _p]),
     "eqnn_segnn_ycontract": (_i, [_p, _p, _i, _p, _i, _i, _i64, _i, _i, _p, _p]),
     "eqnn_segnn_yexpand": (_i, [_p, _p, _i, _i64, _i, _i, _p, _p]),
     "eqnn_segnn_cg_apply": (_i, [_p, _i, _i, _p, _i, _i, _p, _p, _p, _p, _i, _i, _i64, _i, _p, _i, _p]),

@@ -541,22 +541,22 @@ __global__ void segnn_ycontract_kernel(const float* __restrict__ Xbig, const flo
   const int64_t r = i / Do;
   const int o = (int)(i - r * Do);
   float a = (bias && o >= bias_col && o < bias_col + n_bias) ? bias[o - bias_col] : 0.f;
-  const float* xb = Xbig + r * (size_t)Dy * Do + o;
-  for (int j = 0; j < Dy; ++j) a = fmaf(y ? y[r * ld_y + j] : 1.f, xb[(size_t)j * Do], a);
+  const float* xb = Xbig + (r * (size_t)Do + o) * Dy;        // the Dy attribute components of one output are adjacent
+  for (int j = 0; j < Dy; ++j) a = fmaf(y ? y[r * ld_y + j] : 1.f, xb[j], a);
   z[i] = a;
 }
 
 __global__ void segnn_yexpand_kernel(const float* __restrict__ dz, const float* __restrict__ y, int ld_y, int64_t R,
                                      int Dy, int Do, float* __restrict__ dXbig) {
-  // one thread per (row, output): dz is read once and fans out to the Dy attribute blocks (coalesced along o)
+  // one thread per (row, output): dz is read once and fans out to the Dy adjacent attribute columns
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= R * Do) return;
   const int64_t r = i / Do;
   const int o = (int)(i - r * Do);
   const float v = dz[i];
-  float* dst = dXbig + (size_t)r * Dy * Do + o;
+  float* dst = dXbig + ((size_t)r * Do + o) * Dy;
   const float* yr = y ? y + (size_t)r * ld_y : nullptr;
-  for (int j = 0; j < Dy; ++j) dst[(size_t)j * Do] = (yr ? __ldg(yr + j) : 1.f) * v;
+  for (int j = 0; j < Dy; ++j) dst[j] = (yr ? __ldg(yr + j) : 1.f) * v;
 }
 
 // Irrep-blocked TensorProductLinearGate: out[r, o] = bias + sum_t coef[t] * y[r, idx[t] >> 24] * in[r, idx[t] & 0xFFFFFF]

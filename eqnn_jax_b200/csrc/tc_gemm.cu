@@ -56,6 +56,11 @@ struct TcGemmP {
   int ksplit;
   int64_t k_per_split;
   float* partial;      // [ksplit][M][N] when ksplit > 1
+  // fused attribute contraction (SEGNN forward): when yc_Dy > 0 the accumulator columns are (output o, attribute j)
+  // pairs, j fastest, and the epilogue stores z[m, o] = bias + sum_j yc_y[m, j] * acc[m, o * yc_Dy + j] into C
+  // (row stride scm) instead of the N-wide product; yc_Dy divides 32, no K split, no accumulation
+  const float* yc_y; const float* yc_bias;
+  int yc_ldy, yc_Dy, yc_bias_col, yc_nbias;
 };
 
 template <int BN>
@@ -68,6 +73,20 @@ struct GtCfg {
   static constexpr uint32_t SMEM = NSTAGE * STAGE + 1024 /*align*/ + 256 /*barriers*/;
   static_assert(SMEM <= 227 * 1024, "shared memory budget exceeded");
 };
+
+// zo[i] = sum_j yv[j] v[i * DY + j] for the 32 / DY outputs held in 32 accumulator columns (compile-time indices)
+template <int DY>
+__device__ __forceinline__ void contract_y(const float (&v)[32], const float (&yv)[8], float (&zo)[32]) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    float a = 0.f;
+    if (i < 32 / DY) {
+#pragma unroll
+      for (int j = 0; j < DY; ++j) a = fmaf(yv[j], v[i * DY + j], a);
+    }
+    zo[i] = a;
+  }
+}
 
 template <int BN>
 __global__ void __launch_bounds__(GT_THREADS, 1) tc_gemm_kernel(const TcGemmP p) {
@@ -193,6 +212,12 @@ __global__ void __launch_bounds__(GT_THREADS, 1) tc_gemm_kernel(const TcGemmP p)
     }
   } else {
     // =========================== MMA issuer (warp 0, one thread), then epilogue ===========================
+    const int64_t m = m0 + warp * 32 + lane;         // this thread's accumulator row (tcgen05.ld 32x32b)
+    float yv[8];                                     // its attributes (fused contraction, Dy <= 8): loaded up front so
+    if (p.yc_Dy > 0) {                               // that the latency hides behind the main loop
+#pragma unroll
+      for (int j = 0; j < 8; ++j) yv[j] = (j < p.yc_Dy && m < p.M) ? __ldg(p.yc_y + m * p.yc_ldy + j) : 0.f;
+    }
     if (warp == GT_MMA_WARP && lane == 0) {
       constexpr uint32_t idesc = make_idesc_tf32(GT_M, BN, 0, 0);
       for (int c = 0; c < nch; ++c) {
@@ -218,7 +243,6 @@ __global__ void __launch_bounds__(GT_THREADS, 1) tc_gemm_kernel(const TcGemmP p)
     // transpose (the operand stages are dead once t_full fires) so that lanes run along n.
     mbar_wait_backoff(t_full, 0, 128);
     tc_fence_after();
-    const int64_t m = m0 + warp * 32 + lane;
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
     float* stg = reinterpret_cast<float*>(gen) + warp * (32 * 33);
     const bool split = p.ksplit > 1;
@@ -236,7 +260,46 @@ __global__ void __launch_bounds__(GT_THREADS, 1) tc_gemm_kernel(const TcGemmP p)
       float v[32];
       tmem_ld32(taddr + cb * 32, v);
       tmem_ld_wait();
-      if (rows256 && nb + 32 <= p.N) {
+      if (p.yc_Dy > 0) {
+        // 32 accumulator columns = 32 / Dy whole outputs: contract with y, add the bias of the 0e block, and write
+        // the outputs of this row as one run
+        const int Dy = p.yc_Dy, per = 32 / Dy;
+        const int64_t o0 = nb / Dy, Do = p.N / Dy;
+        const bool has_bias = p.yc_bias != nullptr && o0 < p.yc_bias_col + p.yc_nbias && o0 + per > p.yc_bias_col;
+        if (Dy == 4 && o0 + 8 <= Do && (p.scm & 7) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 31) == 0) {
+          // attributes l <= 1: eight outputs per 32 columns, one 256-bit store per row
+          float zo[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            zo[i] = fmaf(yv[3], v[4 * i + 3], fmaf(yv[2], v[4 * i + 2], fmaf(yv[1], v[4 * i + 1], yv[0] * v[4 * i])));
+          if (has_bias) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int64_t o = o0 + i;
+              if (o >= p.yc_bias_col && o < p.yc_bias_col + p.yc_nbias) zo[i] += __ldg(p.yc_bias + (o - p.yc_bias_col));
+            }
+          }
+          if (m < p.M) stg256(p.C + m * p.scm + o0, zo);
+        } else {
+          float zo[32];
+          if (Dy == 4) contract_y<4>(v, yv, zo);
+          else if (Dy == 8) contract_y<8>(v, yv, zo);
+          else if (Dy == 2) contract_y<2>(v, yv, zo);
+          else contract_y<1>(v, yv, zo);
+          if (m < p.M) {
+            float* q = p.C + m * p.scm + o0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int64_t o = o0 + i;
+              if (i < per && o < Do) {
+                float t = zo[i];
+                if (has_bias && o >= p.yc_bias_col && o < p.yc_bias_col + p.yc_nbias) t += __ldg(p.yc_bias + (o - p.yc_bias_col));
+                q[i] = t;
+              }
+            }
+          }
+        }
+      } else if (rows256 && nb + 32 <= p.N) {
         if (m < p.M) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
@@ -368,6 +431,31 @@ int eqnn_tc_gemm_try(int64_t M, int64_t N, int64_t K, float alpha, const float* 
   p.alpha = alpha; p.accumulate = accumulate;
   p.ksplit = g.ksplit; p.k_per_split = g.k_per_split;
   p.partial = reinterpret_cast<float*>(ws);
+  p.yc_y = nullptr; p.yc_bias = nullptr; p.yc_ldy = p.yc_Dy = p.yc_bias_col = p.yc_nbias = 0;
   const int rc = launch_tc_gemm<128>(p, st);
   return rc ? -rc : 1;
+}
+
+// ---- SEGNN TensorProductLinearGate forward with the attribute contraction in the GEMM epilogue ----------------
+// z[r, o] = bias + sum_j y[r, j] (x @ M_cat)[r, o * Dy + j]: the (R x Do*Dy) product never leaves tensor memory.
+extern "C" int eqnn_segnn_tplg_fwd(const float* x, int ld_x, int Dx, const float* Mcat, const float* y, int ld_y, int Dy,
+                                   int Do, const float* bias, int bias_col, int n_bias, int64_t R, float* z, int ld_z,
+                                   eqnn_stream_t stream) {
+  if (R <= 0) return EQNN_OK;
+  const int64_t N = (int64_t)Dy * Do;
+  EQNN_CHECK_ARG(x && Mcat && y && z && Dx >= 1 && ld_x >= Dx && Do >= 1 && ld_z >= Do && ld_y >= Dy &&
+                     (Dy == 1 || Dy == 2 || Dy == 4 || Dy == 8) && n_bias >= 0 && bias_col >= 0 && bias_col + n_bias <= Do &&
+                     (n_bias == 0 || bias),
+                 "segnn_tplg_fwd: bad argument (Dy must be 1, 2, 4 or 8)");
+  EQNN_CHECK_ARG(gt_shape_ok(R, N, Dx), "segnn_tplg_fwd: shape not covered by the tensor-core kernel");
+  TcGemmP p;
+  p.A = x; p.sam = ld_x; p.sak = 1;
+  p.B = Mcat; p.sbk = N; p.sbn = 1;
+  p.C = z; p.scm = ld_z; p.scn = 1;
+  p.M = R; p.N = N; p.K = Dx;
+  p.alpha = 1.f; p.accumulate = 0;
+  p.ksplit = 1; p.k_per_split = ((int64_t)Dx + 31) / 32 * 32;
+  p.partial = nullptr;
+  p.yc_y = y; p.yc_bias = n_bias ? bias : nullptr; p.yc_ldy = ld_y; p.yc_Dy = Dy; p.yc_bias_col = bias_col; p.yc_nbias = n_bias;
+  return launch_tc_gemm<128>(p, as_stream(stream));
 }

@@ -297,6 +297,24 @@ def egnn_sender_acc(dre, rowptr_s, perm_s, n_nodes, dpos):
           "egnn_sender_acc")
 
 
+def segnn_fwd_fused_ok(R, Dx, Dy, Do):
+    """Shapes eqnn_segnn_tplg_fwd accepts (mirrors its argument checks)."""
+    N = Dy * Do
+    return Dy in (1, 2, 4, 8) and R >= 32 and N >= 32 and Dx >= 16 and R * N >= (1 << 14) and R * N * Dx >= (1 << 24) \
+        and R <= 128 * 65535
+
+
+def segnn_tplg_fwd(x, ld_x, Dx, mcat, m_off, y, Dy, Do, bias_buf, bias_off, bias_col, n_bias, R, z, x_off=0, y_off=0, z_off=0,
+                   tag="segnn_gemm"):
+    """z[r, o] = bias + sum_j y[r, j] (x @ M_cat)[r, o*Dy + j], contraction fused into the tensor-core GEMM epilogue."""
+    t0 = TIMER.begin() if TIMER else None
+    check(lib().eqnn_segnn_tplg_fwd(_off(x, x_off), ld_x, Dx, _off(mcat, m_off), _off(y, y_off), Dy, Dy, Do,
+                                    None if bias_buf is None else _off(bias_buf, bias_off), bias_col, n_bias, R,
+                                    _off(z, z_off), Do, _stream()), "segnn_tplg_fwd")
+    if TIMER:
+        TIMER.end(tag, t0)
+
+
 def segnn_ycontract(Xbig, y, ld_y, bias_buf, bias_off, bias_col, n_bias, R, Dy, Do, z, x_off=0, y_off=0, z_off=0):
     check(lib().eqnn_segnn_ycontract(_off(Xbig, x_off), None if y is None else _off(y, y_off), ld_y,
                                      None if bias_buf is None else _off(bias_buf, bias_off), bias_col, n_bias, R, Dy, Do,

@@ -6,12 +6,12 @@ names (``TensorProductLinearGate_i/Linear_0/w[i,j] ...``, ``Dense_0``, ``MLP_0``
 
 Every layer of the model is a ``TensorProductLinearGate`` (:21-64): ``gate(Linear(TP(x, y)))`` with y the steerable
 attributes (spherical harmonics, one copy per degree).  ``Linear(TP(x, y))`` is bilinear, so it is lowered at plan
-time into one dense matrix per attribute component, ``M_cat = [M_0 | M_1 | ...]`` (rows: components of x in their
-stored order; columns: attribute component x Linear output), whose entries are Clebsch-Gordan coefficients times
+time into one dense matrix per attribute component, ``M_cat`` (rows: components of x in their
+stored order; columns: Linear output x attribute component, attribute fastest), whose entries are Clebsch-Gordan coefficients times
 single Linear weights (``eqnn_weights_expand`` gathers them from the flat parameter buffer; the transposed table
 contracts dense gradients back).  Per layer and row block:
     Xbig = x @ M_cat                      eqnn_gemm_f32                              segnn.py:54  (TP + Linear)
-    z    = sum_j y_j Xbig[:, j] + b       eqnn_segnn_ycontract                        segnn.py:48-54 (biases on 0e)
+    z    = sum_j y_j Xbig[:, :, j] + b    eqnn_segnn_ycontract                        segnn.py:48-54 (biases on 0e)
     out  = e3nn.gate(z)                   eqnn_gate_fwd                              segnn.py:55-63
 Edges are processed in receiver-sorted order: ``eqnn_egnn_edge_input_fwd`` builds concat(additional_messages, h_s,
 h_r) (:112), ``eqnn_egnn_segment_rows_fwd`` is jraph's segment_sum / segment_mean over receivers (:218), and the
@@ -110,7 +110,8 @@ class _TPLG:
         if owner.lowering == "blocked":
             self._lower_blocked(owner, x_irreps, xin, in_map, x_off, paths, lin, out_off)
             return
-        # dense lowering: M_cat[x column, j * Do + o]
+        # dense lowering: M_cat[x column, o * Dy + j] (the Dy attribute components of one output are adjacent, so a
+        # GEMM tile holds whole outputs and the attribute contraction can run in its epilogue)
         self.M_off = owner.new_dense(self.Dx * self.Dy * self.Do)
         ncols = self.Dy * self.Do
         for (i1, l2, l3, p3, m1) in paths:
@@ -130,7 +131,7 @@ class _TPLG:
             w = np.arange(mo)[None, :, None]
             t = np.arange(a.size)[None, None, :]
             rows = np.asarray(in_map)[x_off[i1] + u * (2 * l1 + 1) + a[t]]
-            cols = (l2 * l2 + b[t]) * self.Do + out_off[i_out] + w * (2 * l3 + 1) + c[t]
+            cols = (out_off[i_out] + w * (2 * l3 + 1) + c[t]) * self.Dy + (l2 * l2 + b[t])
             dst = self.M_off + rows * ncols + cols
             par = self.w_off[i_out] + (r0 + u) * mo + w + 0 * t
             val = cg[a, b, c][t] + 0.0 * (u + w)
@@ -490,6 +491,10 @@ class SEGNN:
                 ops.segnn_cg_apply(T, t.DT, t.DT, y if t.has_y else None, t.Dy, t.Dy, tab["cg_ptr"], tab["cg_idx"],
                                    tab["cg_coef"], theta if t.n_bias else None, t.b_off or 0, t.b_col, t.n_bias, n, t.Do,
                                    z, t.Do, y_off=r0 * t.Dy, out_off=r0 * t.Do, ptr_off=t.cg_f)
+        elif self.tensor_cores and t.has_y and ops.segnn_fwd_fused_ok(R, t.Dx, t.Dy, t.Do):
+            # attribute contraction in the GEMM epilogue: x @ M_cat never leaves tensor memory, no row blocks
+            ops.segnn_tplg_fwd(x, ldx, t.Dx, wexp, t.M_off, y, t.Dy, t.Do, theta if t.n_bias else None, t.b_off or 0,
+                               t.b_col, t.n_bias, R, z)
         else:
             nc = t.Dy * t.Do
             Xbig = torch.empty((blk, nc), **f32)

@@ -215,12 +215,19 @@ int eqnn_steerable_attrs(const float* pos, int ld_pos, const float* vel, int ld_
 
 /* ---- SEGNN TensorProductLinearGate (models/segnn.py:30-64), dense-lowered ---------------------------------
  * Linear(TP(x, y)) = sum_j y_j (x @ M_j) + b: the host lowers the e3nn Linear weights and the Clebsch-Gordan
- * coefficients into M_cat = [M_0 | M_1 | ...] (Dx x Dy*Do, eqnn_weights_expand), eqnn_gemm_f32 forms
- * Xbig = x @ M_cat, and these kernels contract / expand the attribute axis:
- *   z[r, o] = bias[o - bias_col] (for bias_col <= o < bias_col + n_bias: the 0e block) + sum_j y[r, j] Xbig[r, j*Do + o]
+ * coefficients into M_cat (Dx x Do*Dy, column o*Dy + j = output o, attribute component j; eqnn_weights_expand),
+ * eqnn_gemm_f32 forms Xbig = x @ M_cat, and these kernels contract / expand the attribute axis:
+ *   z[r, o] = bias[o - bias_col] (for bias_col <= o < bias_col + n_bias: the 0e block) + sum_j y[r, j] Xbig[r, o*Dy + j]
  *                                                                          (y NULL: Dy = 1, y = 1; segnn.py:35-36)
- *   dXbig[r, j*Do + o] = y[r, j] dz[r, o]
+ *   dXbig[r, o*Dy + j] = y[r, j] dz[r, o]
  * The gate (segnn.py:55-63) is eqnn_gate_fwd/bwd. */
+/* Forward of the dense-lowered layer with the attribute contraction fused into the tensor-core GEMM's epilogue
+ * (tc_gemm.cu): z[r, o] = bias + sum_j y[r, j] (x @ M_cat)[r, o*Dy + j]; the (R x Do*Dy) product is reduced in
+ * registers straight out of tensor memory and never written.  Dy in {1, 2, 4, 8} (attributes l <= 1: Dy = 4), y != NULL,
+ * and a shape the kernel covers (R >= 32, Do*Dy >= 32, R*Do*Dy*Dx >= 2^24); anything else is an error and the caller
+ * keeps eqnn_gemm_f32 + eqnn_segnn_ycontract. */
+int eqnn_segnn_tplg_fwd(const float* x, int ld_x, int Dx, const float* Mcat, const float* y, int ld_y, int Dy, int Do,
+                        const float* bias, int bias_col, int n_bias, int64_t R, float* z, int ld_z, eqnn_stream_t stream);
 int eqnn_segnn_ycontract(const float* Xbig, const float* y, int ld_y, const float* bias, int bias_col, int n_bias,
                          int64_t R, int Dy, int Do, float* z, eqnn_stream_t stream);
 int eqnn_segnn_yexpand(const float* dz, const float* y, int ld_y, int64_t R, int Dy, int Do, float* dXbig,

@@ -347,3 +347,25 @@ def test_dense_wgrad_kernel_and_bias_in_one_pass(M, N, K, pro, tc):
     assert torch.isnan(buf[:3]).all() and torch.isnan(buf[3 + M * N + N:]).all()
     assert (got_w - want_w).abs().max().item() <= 1e-5 * max(want_w.abs().max().item(), 1e-30)
     assert (got_b - want_b).abs().max().item() <= 1e-5 * max(want_b.abs().max().item(), K ** 0.5)
+
+
+@pytest.mark.parametrize("R,Dx,Dy,Do,nb", [(3001, 341, 4, 192, 110), (70001, 170, 4, 170, 88), (4000, 170, 8, 30, 0),
+                                           (3000, 64, 1, 96, 96), (5000, 40, 2, 50, 7)])
+def test_segnn_fused_forward_matches_fp64(R, Dx, Dy, Do, nb):
+    """eqnn_segnn_tplg_fwd: z = bias + sum_j y_j (x @ M_cat)[:, o*Dy + j] with the contraction in the GEMM epilogue --
+    against fp64 (row tails, partial column tiles, unaligned z rows, every supported Dy)."""
+    from eqnn_jax_b200 import ops
+    g = torch.Generator().manual_seed(R + Do)
+    r64 = lambda *s: torch.randn(*s, generator=g, dtype=torch.float64)
+    x, y, M, b = r64(R, Dx + 1), r64(R, Dy), r64(Dx, Do * Dy), r64(max(nb, 1))
+    assert ops.segnn_fwd_fused_ok(R, Dx, Dy, Do)
+    dev = lambda t: t.float().cuda().contiguous()
+    z = torch.full((R, Do), float("nan")).cuda()
+    bcol = 3 if nb and nb + 3 <= Do else 0
+    ops.segnn_tplg_fwd(dev(x), Dx + 1, Dx, dev(M), 0, dev(y), Dy, Do, dev(b) if nb else None, 0, bcol, nb, R, z)
+    want = torch.einsum("rk,koj,rj->ro", x[:, :Dx], M.reshape(Dx, Do, Dy), y)
+    if nb:
+        want[:, bcol:bcol + nb] += b[:nb]
+    assert torch.isfinite(z).all(), int((~torch.isfinite(z)).sum())
+    err = (z.double().cpu() - want).abs().max().item()
+    assert err <= 1e-5 * want.abs().max().item(), (err, want.abs().max().item())

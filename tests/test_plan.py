@@ -247,8 +247,8 @@ def test_segnn_dense_lowering_equals_oracle_tplg(lowering):
         x = rng.normal(size=(R, t.Dx))
         y = spherical_harmonics(lat, rng.normal(size=(R, 3)), True, "integral") if t.has_y else np.ones((R, 1))
         if lowering == "dense":
-            M = wexp[t.M_off:t.M_off + t.Dx * t.Dy * t.Do].reshape(t.Dx, t.Dy, t.Do)
-            z = np.einsum("ri,rj,ijo->ro", x, y, M)
+            M = wexp[t.M_off:t.M_off + t.Dx * t.Dy * t.Do].reshape(t.Dx, t.Do, t.Dy)
+            z = np.einsum("ri,rj,ioj->ro", x, y, M)
         else:
             T = np.zeros((R, t.DT))
             first = set()
