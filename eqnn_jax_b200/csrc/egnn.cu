@@ -291,15 +291,19 @@ __global__ void __launch_bounds__(256) egnn_edge_input_fwd_kernel(const float* _
   const int K0 = nf + 2 * dh + n_glob;
   const float* gl = n_glob ? glob + (size_t)(row / nodes_per_graph) * n_glob : nullptr;   // jraph broadcasts the globals
   const int p0 = rowptr[row], p1 = rowptr[row + 1];
-  for (int64_t i = (int64_t)p0 * K0 + lane; i < (int64_t)p1 * K0; i += 32) {
-    const int64_t p = i / K0;
-    const int c = (int)(i - p * K0);
-    float v;
-    if (c < nf) v = feats[p * nf + c];
-    else if (c < nf + dh) v = h[(size_t)src[p] * ld_h + (c - nf)];
-    else if (c < nf + 2 * dh) v = h[(size_t)row * ld_h + (c - nf - dh)];
-    else v = gl[c - nf - 2 * dh];
-    U[i] = v;
+  const float* hr = h + (size_t)row * ld_h;
+  for (int p = p0; p < p1; ++p) {                      // lanes run along the columns of one edge row
+    const float* hs = h + (size_t)src[p] * ld_h;
+    const float* fp = feats + (size_t)p * nf;
+    float* u = U + (size_t)p * K0;
+    for (int c = lane; c < K0; c += 32) {
+      float v;
+      if (c < nf) v = fp[c];
+      else if (c < nf + dh) v = hs[c - nf];
+      else if (c < nf + 2 * dh) v = hr[c - nf - dh];
+      else v = gl[c - nf - 2 * dh];
+      u[c] = v;
+    }
   }
 }
 
@@ -315,21 +319,18 @@ __global__ void __launch_bounds__(256) egnn_edge_input_bwd_kernel(const float* _
   if (row >= n_nodes) return;
   const int K0 = nf + 2 * dh + n_glob;
   const int p0 = rowptr[row], p1 = rowptr[row + 1];
-  if (dfeats)
-    for (int64_t i = (int64_t)p0 * nf + lane; i < (int64_t)p1 * nf; i += 32) {
-      const int64_t p = i / nf;
-      dfeats[i] = dU[p * K0 + (i - p * nf)];
-    }
-  for (int64_t i = (int64_t)p0 * dh + lane; i < (int64_t)p1 * dh; i += 32) {
-    const int64_t p = i / dh;
-    dhs_e[(size_t)perm[p] * dh + (i - p * dh)] = dU[p * K0 + nf + (i - p * dh)];
+  // lanes run along the columns (coalesced row segments of dU), the row's edges are walked in order
+  for (int p = p0; p < p1; ++p) {
+    const float* u = dU + (size_t)p * K0;
+    if (dfeats)
+      for (int c = lane; c < nf; c += 32) dfeats[(size_t)p * nf + c] = u[c];
+    float* ds = dhs_e + (size_t)perm[p] * dh;
+    for (int c = lane; c < dh; c += 32) ds[c] = u[nf + c];
   }
-  for (int c = 0; c < dh; ++c) {                       // receiver end: lanes over the row's edges, shuffle reduce
+  for (int c = lane; c < dh; c += 32) {                // receiver end: fixed-order sum over the row's edges
     float a = 0.f;
-    for (int p = p0 + lane; p < p1; p += 32) a += dU[(size_t)p * K0 + nf + dh + c];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-    if (lane == 0) dh_out[(size_t)row * ld_dh + c] += a;
+    for (int p = p0; p < p1; ++p) a += dU[(size_t)p * K0 + nf + dh + c];
+    dh_out[(size_t)row * ld_dh + c] += a;
   }
 }
 
