@@ -593,6 +593,131 @@ segnn_cg_kernel(const float* __restrict__ in, int ld_in, int n_in, const float* 
   }
 }
 
+// ---- first edge layer of a SEGNN message-passing step, evaluated at the nodes ------------------------------------
+// Its input is concat(add[e], h[sender], h[receiver]) (segnn.py:111-113), so x @ M_cat splits into
+// add @ M_a + (h @ M_s)[sender] + (h @ M_r)[receiver]: the two big products are formed once per NODE (P_s, P_r:
+// [n_nodes][Do*Dy], 1/k of the per-edge work) and the per-edge part is a gather + attribute contraction:
+//   z[p, o] = bias + sum_j y[p, j] (P_r[row, o*Dy+j] + P_s[src[p], o*Dy+j] + sum_a add[p, a] M_a[a, o*Dy+j])
+// Warp per receiver row (edges in receiver-sorted order), lanes along the outputs o.
+__global__ void __launch_bounds__(256) segnn_edge0_fwd_kernel(const float* __restrict__ Ps, const float* __restrict__ Pr,
+                                                              const float* __restrict__ add, int n_add,
+                                                              const float* __restrict__ Ma, const float* __restrict__ y,
+                                                              int Dy, int Do, const float* __restrict__ bias, int bias_col,
+                                                              int n_bias, const int32_t* __restrict__ rowptr,
+                                                              const int32_t* __restrict__ src, int n_nodes,
+                                                              float* __restrict__ z) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= n_nodes) return;
+  const int nc = Do * Dy;
+  const int p0 = rowptr[row], p1 = rowptr[row + 1];
+  const float* pr = Pr + (size_t)row * nc;
+  if (Dy == 4 && ((reinterpret_cast<uintptr_t>(Ps) | reinterpret_cast<uintptr_t>(Pr) | reinterpret_cast<uintptr_t>(Ma) |
+                   reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
+    // attributes l <= 1: the four attribute columns of an output are one 16-byte load; the receiver's own row of
+    // P_r stays in registers while the row's edges are walked
+    for (int o = lane; o < Do; o += 32) {
+      const float b = (bias != nullptr && o >= bias_col && o < bias_col + n_bias) ? __ldg(bias + (o - bias_col)) : 0.f;
+      const float4 r4 = __ldg(reinterpret_cast<const float4*>(pr) + o);
+      for (int p = p0; p < p1; ++p) {
+        const float4 s4 = __ldg(reinterpret_cast<const float4*>(Ps + (size_t)src[p] * nc) + o);
+        const float4 y4 = __ldg(reinterpret_cast<const float4*>(y) + p);
+        float4 t = make_float4(r4.x + s4.x, r4.y + s4.y, r4.z + s4.z, r4.w + s4.w);
+        for (int a = 0; a < n_add; ++a) {
+          const float f = __ldg(add + (size_t)p * n_add + a);
+          const float4 m4 = __ldg(reinterpret_cast<const float4*>(Ma + (size_t)a * nc) + o);
+          t.x = fmaf(f, m4.x, t.x); t.y = fmaf(f, m4.y, t.y); t.z = fmaf(f, m4.z, t.z); t.w = fmaf(f, m4.w, t.w);
+        }
+        z[(size_t)p * Do + o] = fmaf(y4.w, t.w, fmaf(y4.z, t.z, fmaf(y4.y, t.y, fmaf(y4.x, t.x, b))));
+      }
+    }
+    return;
+  }
+  for (int p = p0; p < p1; ++p) {
+    const float* ps = Ps + (size_t)src[p] * nc;
+    const float* yp = y + (size_t)p * Dy;
+    const float* ap = add + (size_t)p * n_add;
+    for (int o = lane; o < Do; o += 32) {
+      float acc = (bias != nullptr && o >= bias_col && o < bias_col + n_bias) ? __ldg(bias + (o - bias_col)) : 0.f;
+      for (int j = 0; j < Dy; ++j) {
+        const int c = o * Dy + j;
+        float t = pr[c] + ps[c];
+        for (int a = 0; a < n_add; ++a) t = fmaf(__ldg(ap + a), __ldg(Ma + (size_t)a * nc + c), t);
+        acc = fmaf(__ldg(yp + j), t, acc);
+      }
+      z[(size_t)p * Do + o] = acc;
+    }
+  }
+}
+
+// its backward onto the node-level products: with G[p, o*Dy+j] = y[p, j] dz[p, o] (never written),
+//   dPr[n, c] = sum over the edges received by n of G[p, c],   dPs[n, c] = sum over the edges sent by n of G[spos[q], c]
+// (spos: sender-sorted position -> receiver-sorted position).  Thread per (node, column), fixed order.
+__global__ void segnn_edge0_bwd_kernel(const float* __restrict__ dz, const float* __restrict__ y, int Dy, int Do,
+                                       const int32_t* __restrict__ rowptr, const int32_t* __restrict__ rowptr_s,
+                                       const int32_t* __restrict__ spos, int n_nodes, float* __restrict__ dPs,
+                                       float* __restrict__ dPr) {
+  const int nc = Do * Dy;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)n_nodes * nc) return;
+  const int64_t n = i / nc;
+  const int c = (int)(i - n * nc);
+  const int o = c / Dy, j = c - o * Dy;
+  float a = 0.f;
+  for (int p = rowptr[n]; p < rowptr[n + 1]; ++p) a = fmaf(__ldg(y + (size_t)p * Dy + j), __ldg(dz + (size_t)p * Do + o), a);
+  dPr[i] = a;
+  a = 0.f;
+  for (int q = rowptr_s[n]; q < rowptr_s[n + 1]; ++q) {
+    const int p = spos[q];
+    a = fmaf(__ldg(y + (size_t)p * Dy + j), __ldg(dz + (size_t)p * Do + o), a);
+  }
+  dPs[i] = a;
+}
+
+// gMa[a, o*Dy+j] = sum_p add[p, a] y[p, j] dz[p, o]  (n_add <= 8): per-CTA partials over edge ranges, then a fixed-order sum
+constexpr int EDGE0_PARTS = 148 * 16;      // short edge ranges: the per-thread loop is a dependent chain of loads
+__global__ void __launch_bounds__(1024) segnn_edge0_wadd_partial_kernel(const float* __restrict__ add, int n_add,
+                                                                       const float* __restrict__ y, int Dy,
+                                                                       const float* __restrict__ dz, int Do, int64_t E,
+                                                                       int64_t per, float* __restrict__ part) {
+  const int nc = Do * Dy;
+  const int64_t e0 = (int64_t)blockIdx.x * per, e1 = (e0 + per < E) ? e0 + per : E;
+  for (int c = threadIdx.x; c < nc; c += blockDim.x) {
+    const int o = c / Dy, j = c - o * Dy;
+    float acc[8];
+#pragma unroll
+    for (int a = 0; a < 8; ++a) acc[a] = 0.f;
+#pragma unroll 4
+    for (int64_t p = e0; p < e1; ++p) {
+      const float g = __ldg(y + p * Dy + j) * __ldg(dz + p * Do + o);
+#pragma unroll
+      for (int a = 0; a < 8; ++a)
+        if (a < n_add) acc[a] = fmaf(__ldg(add + p * n_add + a), g, acc[a]);
+    }
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+      if (a < n_add) part[((size_t)blockIdx.x * n_add + a) * nc + c] = acc[a];
+  }
+}
+__global__ void segnn_edge0_wadd_final_kernel(const float* __restrict__ part, int parts, int n, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float t = 0.f;
+  for (int q = 0; q < parts; ++q) t += part[(size_t)q * n + i];
+  out[i] = t;
+}
+
+// inv[perm[p]] = p ; spos[q] = inv[perm_s[q]]
+__global__ void perm_invert_kernel(const int32_t* __restrict__ perm, int64_t n, int32_t* __restrict__ inv) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) inv[perm[i]] = (int32_t)i;
+}
+__global__ void perm_gather_kernel(const int32_t* __restrict__ inv, const int32_t* __restrict__ perm_s, int64_t n,
+                                   int32_t* __restrict__ spos) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) spos[i] = inv[perm_s[i]];
+}
+
 // dst[p, :] = src[perm[p], :]
 __global__ void gather_rows_kernel(const float* __restrict__ src, const int32_t* __restrict__ perm, int64_t n, int w,
                                    float* __restrict__ dst) {
@@ -824,6 +949,61 @@ extern "C" int eqnn_segnn_cg_apply(const float* in, int ld_in, int n_in, const f
   segnn_cg_kernel<WARPS><<<grid, WARPS * 32, smem, as_stream(stream)>>>(in, ld_in, n_in, y, ld_y, Dy, ptr, idx, coef, bias,
                                                                          bias_col, n_bias, R, n_out, out, ld_out);
   EQNN_CHECK_LAUNCH();
+  return EQNN_OK;
+}
+
+extern "C" int eqnn_segnn_edge0_fwd(const float* Ps, const float* Pr, const float* add, int n_add, const float* Ma,
+                                    const float* y, int Dy, int Do, const float* bias, int bias_col, int n_bias,
+                                    const int32_t* rowptr, const int32_t* src, int n_nodes, float* z, eqnn_stream_t stream) {
+  EQNN_CHECK_ARG(Ps && Pr && y && rowptr && src && z && Dy >= 1 && Do >= 1 && n_add >= 0 && (n_add == 0 || (add && Ma)) &&
+                     n_bias >= 0 && bias_col >= 0 && bias_col + n_bias <= Do && (n_bias == 0 || bias),
+                 "segnn_edge0_fwd: bad argument");
+  if (n_nodes <= 0) return EQNN_OK;
+  segnn_edge0_fwd_kernel<<<(unsigned)ceil_div64((int64_t)n_nodes * 32, 256), 256, 0, as_stream(stream)>>>(
+      Ps, Pr, add, n_add, Ma, y, Dy, Do, n_bias ? bias : nullptr, bias_col, n_bias, rowptr, src, n_nodes, z);
+  EQNN_CHECK_LAUNCH();
+  return EQNN_OK;
+}
+
+extern "C" int eqnn_segnn_edge0_bwd(const float* dz, const float* y, int Dy, int Do, const int32_t* rowptr,
+                                    const int32_t* rowptr_s, const int32_t* spos, int n_nodes, float* dPs, float* dPr,
+                                    eqnn_stream_t stream) {
+  EQNN_CHECK_ARG(dz && y && rowptr && rowptr_s && spos && dPs && dPr && Dy >= 1 && Do >= 1, "segnn_edge0_bwd: bad argument");
+  if (n_nodes <= 0) return EQNN_OK;
+  segnn_edge0_bwd_kernel<<<(unsigned)ceil_div64((int64_t)n_nodes * Do * Dy, 256), 256, 0, as_stream(stream)>>>(
+      dz, y, Dy, Do, rowptr, rowptr_s, spos, n_nodes, dPs, dPr);
+  EQNN_CHECK_LAUNCH();
+  return EQNN_OK;
+}
+
+extern "C" size_t eqnn_segnn_edge0_wadd_workspace_bytes(int n_add, int Dy, int Do) {
+  return (size_t)EDGE0_PARTS * n_add * Dy * Do * sizeof(float);
+}
+
+extern "C" int eqnn_segnn_edge0_wadd(const float* add, int n_add, const float* y, int Dy, const float* dz, int Do, int64_t E,
+                                     float* gMa, void* ws, size_t ws_bytes, eqnn_stream_t stream) {
+  EQNN_CHECK_ARG(add && y && dz && gMa && n_add >= 1 && n_add <= 8 && Dy >= 1 && Do >= 1 && E >= 0,
+                 "segnn_edge0_wadd: bad argument (1 <= n_add <= 8)");
+  EQNN_CHECK_ARG(ws && ws_bytes >= eqnn_segnn_edge0_wadd_workspace_bytes(n_add, Dy, Do), "segnn_edge0_wadd: workspace too small");
+  const int parts = (int)min((int64_t)EDGE0_PARTS, max((int64_t)1, (E + 63) / 64));
+  const int64_t per = (E + parts - 1) / parts;
+  const int n = n_add * Dy * Do;
+  cudaStream_t st = as_stream(stream);
+  const int nthr = (Dy * Do >= 1024) ? 1024 : (Dy * Do + 31) / 32 * 32;
+  segnn_edge0_wadd_partial_kernel<<<parts, nthr, 0, st>>>(add, n_add, y, Dy, dz, Do, E, per, reinterpret_cast<float*>(ws));
+  segnn_edge0_wadd_final_kernel<<<(n + 127) / 128, 128, 0, st>>>(reinterpret_cast<float*>(ws), parts, n, gMa);
+  EQNN_CHECK_LAUNCH_N(2);
+  return EQNN_OK;
+}
+
+extern "C" int eqnn_perm_compose(const int32_t* perm, const int32_t* perm_s, int64_t n, int32_t* inv, int32_t* spos,
+                                 eqnn_stream_t stream) {
+  EQNN_CHECK_ARG(perm && perm_s && inv && spos && n >= 0, "perm_compose: bad argument");
+  if (n == 0) return EQNN_OK;
+  cudaStream_t st = as_stream(stream);
+  perm_invert_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(perm, n, inv);
+  perm_gather_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(inv, perm_s, n, spos);
+  EQNN_CHECK_LAUNCH_N(2);
   return EQNN_OK;
 }
 

@@ -338,6 +338,42 @@ def segnn_cg_apply(inp, ld_in, n_in, y, ld_y, Dy, ptr, idx, coef, bias_buf, bias
         TIMER.end("segnn_cg", t0)
 
 
+def segnn_edge0_fwd(Ps, Pr, add, n_add, wexp, ma_off, y, Dy, Do, bias_buf, bias_off, bias_col, n_bias, rowptr, src, n_nodes, z):
+    t0 = TIMER.begin() if TIMER else None
+    check(lib().eqnn_segnn_edge0_fwd(_ptr(Ps), _ptr(Pr), _ptr(add), n_add, _off(wexp, ma_off), _ptr(y), Dy, Do,
+                                     None if bias_buf is None else _off(bias_buf, bias_off), bias_col, n_bias,
+                                     _ptr(rowptr), _ptr(src), n_nodes, _ptr(z), _stream()), "segnn_edge0_fwd")
+    if TIMER:
+        TIMER.end("segnn_edge0", t0)
+
+
+def segnn_edge0_bwd(dz, y, Dy, Do, rowptr, rowptr_s, spos, n_nodes, dPs, dPr):
+    t0 = TIMER.begin() if TIMER else None
+    check(lib().eqnn_segnn_edge0_bwd(_ptr(dz), _ptr(y), Dy, Do, _ptr(rowptr), _ptr(rowptr_s), _ptr(spos), n_nodes,
+                                     _ptr(dPs), _ptr(dPr), _stream()), "segnn_edge0_bwd")
+    if TIMER:
+        TIMER.end("segnn_edge0", t0)
+
+
+def segnn_edge0_wadd(add, n_add, y, Dy, dz, Do, E, gwexp, g_off):
+    L = lib()
+    ws, ws_bytes = _GEMM_WS.get(L.eqnn_segnn_edge0_wadd_workspace_bytes(n_add, Dy, Do), dz.device)
+    t0 = TIMER.begin() if TIMER else None
+    check(L.eqnn_segnn_edge0_wadd(_ptr(add), n_add, _ptr(y), Dy, _ptr(dz), Do, E, _off(gwexp, g_off), ws, ws_bytes,
+                                  _stream()), "segnn_edge0_wadd")
+    if TIMER:
+        TIMER.end("segnn_edge0", t0)
+
+
+def perm_compose(perm, perm_s):
+    """spos[q] = receiver-sorted position of the q-th sender-sorted edge."""
+    n = perm.numel()
+    inv = torch.empty_like(perm)
+    spos = torch.empty_like(perm)
+    check(lib().eqnn_perm_compose(_ptr(perm), _ptr(perm_s), n, _ptr(inv), _ptr(spos), _stream()), "perm_compose")
+    return spos
+
+
 def gather_rows(src, perm, width):
     n = perm.numel()
     dst = torch.empty((n, width), dtype=_F32, device=src.device)

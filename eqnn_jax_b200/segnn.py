@@ -442,6 +442,7 @@ class SEGNN:
         E = snd.shape[1]
         rowptr, perm, src = ops.csr_build(snd, rcv, N)
         rowptr_s, perm_s, _ = ops.csr_build(rcv, snd, N)
+        spos = ops.perm_compose(perm, perm_s)             # sender-sorted position -> receiver-sorted position
         ny = (lmax_attr + 1) ** 2
         f32c = lambda t, w: t.to(torch.float32).contiguous().reshape(-1, w)
         y_node = f32c(g.steerable_node_attrs.array, ny)
@@ -453,7 +454,7 @@ class SEGNN:
             if not isinstance(g.globals, torch.Tensor) or not g.globals.is_cuda:
                 raise RuntimeError("st_graphs.globals must be a CUDA tensor (this path has no CPU implementation)")
             glob = g.globals.reshape(B, n_glob).to(torch.float32).contiguous()
-        return plan, f32c(nodes, D), B, N, E, (rowptr, perm, src, rowptr_s, perm_s), y_node, y_edge, add, glob
+        return plan, f32c(nodes, D), B, N, E, (rowptr, perm, src, rowptr_s, perm_s, spos), y_node, y_edge, add, glob
 
     def forward_backward(self, params: FlatParams, st_graphs: SteerableGraphsTuple, grad_fn=None):
         """Forward (and, if ``grad_fn(out) -> dL/dout`` is given, backward into ``params.grad``).  Returns the raw
@@ -552,9 +553,55 @@ class SEGNN:
                 _mm(n, t.Dx, nc, 1.0, dXbig, 0, nc, wexp, t.M_off, nc, dx, r0 * t.Dx, t.Dx, tb=True, **self._gemm_kw)
         return dx
 
+    # -- first edge layer of a step, evaluated at the nodes ----------------------------------------------------
+    def _edge0_ok(self, plan, t: _TPLG, n_add: int) -> bool:
+        return plan.lowering == "dense" and t.has_y and 1 <= n_add <= 8
+
+    def _edge0_fwd(self, plan, t: _TPLG, theta, wexp, h, Dh, add, n_add, y, csr, Nt, Et):
+        """concat(add, h_s, h_r) @ M_cat = add @ M_a + (h @ M_s)[sender] + (h @ M_r)[receiver]: the two wide products
+        are formed per node (1/k of the per-edge rows), the per-edge part is a gather + attribute contraction."""
+        rowptr, _, src = csr[:3]
+        f32 = dict(dtype=torch.float32, device=theta.device)
+        nc = t.Dy * t.Do
+        P = torch.empty((2, Nt, nc), **f32)
+        Ms = t.M_off + n_add * nc
+        _mm(Nt, nc, Dh, 1.0, h, 0, Dh, wexp, Ms, nc, P, 0, nc, **self._gemm_kw)
+        _mm(Nt, nc, Dh, 1.0, h, 0, Dh, wexp, Ms + Dh * nc, nc, P, Nt * nc, nc, **self._gemm_kw)
+        z = torch.empty((Et, t.Do), **f32)
+        ops.segnn_edge0_fwd(P[0], P[1], add, n_add, wexp, t.M_off, y, t.Dy, t.Do, theta if t.n_bias else None, t.b_off or 0,
+                            t.b_col, t.n_bias, rowptr, src, Nt, z)
+        if not t.activation:
+            return z, (h, y, z)
+        g = torch.empty((Et, t.d_g), **f32)
+        ops.gate_fwd(z, Et, t.n_extra, t.n_gates, t.gate_mul, t.gate_l, plan.inv_c_act, plan.inv_c_gate, g)
+        return g, (h, y, z)
+
+    def _edge0_bwd(self, plan, t: _TPLG, theta, gtheta, wexp, gwexp, sv, dout, Dh, add, n_add, csr, Nt, Et, dh_prev):
+        """Parameter gradients of the layer and the gradient of h (accumulated into dh_prev) from dL/dout [Et, D_out]."""
+        h, y, z = sv
+        rowptr, _, _, rowptr_s, _, spos = csr
+        f32 = dict(dtype=torch.float32, device=theta.device)
+        dz = dout
+        if t.activation:
+            dz = torch.empty((Et, t.Do), **f32)
+            ops.gate_bwd(z, dout, Et, t.n_extra, t.n_gates, t.gate_mul, t.gate_l, plan.inv_c_act, plan.inv_c_gate, dz)
+        if t.n_bias:
+            tmp = torch.empty((t.Do,), **f32)
+            ops.colsum_tall(dz, Et, t.Do, tmp)
+            gtheta[t.b_off:t.b_off + t.n_bias].copy_(tmp[t.b_col:t.b_col + t.n_bias])
+        nc = t.Dy * t.Do
+        dP = torch.empty((2, Nt, nc), **f32)
+        ops.segnn_edge0_bwd(dz, y, t.Dy, t.Do, rowptr, rowptr_s, spos, Nt, dP[0], dP[1])
+        Ms = t.M_off + n_add * nc
+        for k in range(2):                                   # sender block, receiver block of M_cat
+            _mm(Dh, nc, Nt, 1.0, h, 0, Dh, dP, k * Nt * nc, nc, gwexp, Ms + k * Dh * nc, nc, ta=True, **self._gemm_kw)
+            _mm(Nt, Dh, nc, 1.0, dP, k * Nt * nc, nc, wexp, Ms + k * Dh * nc, nc, dh_prev, 0, Dh, tb=True, accumulate=True,
+                **self._gemm_kw)
+        ops.segnn_edge0_wadd(add, n_add, y, t.Dy, dz, t.Do, Et, gwexp, t.M_off)
+
     # -- whole model ------------------------------------------------------------------------------------
     def _forward(self, theta, plan, nodes, B, N, E, csr, y_node, y_edge, add, glob=None):
-        rowptr, perm, src, rowptr_s, perm_s = csr
+        rowptr, perm, src, rowptr_s, perm_s, spos = csr
         dev = theta.device
         f32 = dict(dtype=torch.float32, device=dev)
         Nt, Et = B * N, B * E
@@ -567,10 +614,17 @@ class SEGNN:
         h, saved["embed"] = self._tplg_fwd(plan, plan.embed, theta, wexp, nodes, nodes.shape[1], y_node, Nt)
         for st in plan.steps:
             Dh = st["h_irreps"].dim
-            U = torch.empty((Et, n_add + 2 * Dh), **f32)
-            ops.egnn_edge_input_fwd(add, n_add, h, Dh, 0, Dh, rowptr, src, Nt, U)          # concat(add, h_s, h_r) :112
-            m, ld, es = U, U.shape[1], []
-            for t in st["edge"]:
+            es = []
+            rest = st["edge"]
+            if self._edge0_ok(plan, rest[0], n_add):
+                m, s_ = self._edge0_fwd(plan, rest[0], theta, wexp, h, Dh, add, n_add, y_edge, csr, Nt, Et)
+                es.append(s_)
+                rest = rest[1:]
+            else:
+                m = torch.empty((Et, n_add + 2 * Dh), **f32)
+                ops.egnn_edge_input_fwd(add, n_add, h, Dh, 0, Dh, rowptr, src, Nt, m)       # concat(add, h_s, h_r) :112
+            ld = m.shape[1]
+            for t in rest:
                 m, s_ = self._tplg_fwd(plan, t, theta, wexp, m, ld, y_edge, Et)
                 ld = m.shape[1]
                 es.append(s_)
@@ -613,7 +667,7 @@ class SEGNN:
         return zs[-1], saved
 
     def _backward(self, theta, gtheta, saved, gout, plan, nodes, B, N, E, csr, y_node, y_edge, add, glob=None):
-        rowptr, perm, src, rowptr_s, perm_s = csr
+        rowptr, perm, src, rowptr_s, perm_s, spos = csr
         dev = theta.device
         f32 = dict(dtype=torch.float32, device=dev)
         Nt, Et = B * N, B * E
@@ -665,10 +719,16 @@ class SEGNN:
                 ops.axpy(1.0, dh, dh_prev)
             dm = torch.zeros((Et, Dm), **f32)
             ops.egnn_segment_rows_bwd(dC, Dh + Dm, Dh, Dm, None, 0, rowptr, Nt, agg, dm)
-            for t, s_ in zip(reversed(st["edge"]), reversed(sv["edge"])):
+            fast0 = self._edge0_ok(plan, st["edge"][0], n_add)
+            for t, s_ in zip(reversed(st["edge"][1:] if fast0 else st["edge"]),
+                             reversed(sv["edge"][1:] if fast0 else sv["edge"])):
                 dm = self._tplg_bwd(plan, t, theta, gtheta, wexp, gwexp, s_, dm, Et)
-            dhs_e = torch.empty((Et, Dh), **f32)                                           # dm is now dL/dU
-            ops.egnn_edge_input_bwd(dm, n_add, Dh, rowptr, perm, rowptr_s, perm_s, Nt, None, dhs_e, dh_prev, Dh, 0)
+            if fast0:
+                self._edge0_bwd(plan, st["edge"][0], theta, gtheta, wexp, gwexp, sv["edge"][0], dm, Dh, add, n_add, csr,
+                                Nt, Et, dh_prev)
+            else:
+                dhs_e = torch.empty((Et, Dh), **f32)                                       # dm is now dL/dU
+                ops.egnn_edge_input_bwd(dm, n_add, Dh, rowptr, perm, rowptr_s, perm_s, Nt, None, dhs_e, dh_prev, Dh, 0)
             dh = dh_prev
         self._tplg_bwd(plan, plan.embed, theta, gtheta, wexp, gwexp, saved["embed"], dh, Nt, need_dx=False)
         ops.weights_contract(gwexp, tab["con_pidx"], tab["con_ptr"], tab["con_tidx"], tab["con_scale"], gtheta)

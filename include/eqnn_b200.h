@@ -242,6 +242,26 @@ int eqnn_segnn_yexpand(const float* dz, const float* y, int ld_y, int64_t R, int
 int eqnn_segnn_cg_apply(const float* in, int ld_in, int n_in, const float* y, int ld_y, int Dy, const int32_t* ptr,
                         const int32_t* idx, const float* coef, const float* bias, int bias_col, int n_bias, int64_t R,
                         int n_out, float* out, int ld_out, eqnn_stream_t stream);
+/* First edge layer of a message-passing step, evaluated at the nodes (segnn.py:111-113: its input is
+ * concat(add[e], h[sender], h[receiver]), so x @ M_cat = add @ M_a + (h @ M_s)[sender] + (h @ M_r)[receiver]).
+ * The caller forms P_s = h @ M_s and P_r = h @ M_r with eqnn_gemm_f32 on the n_nodes rows (1/k of the per-edge
+ * work); edges are in receiver-sorted order (rowptr / src of eqnn_csr_build):
+ *   fwd : z[p, o] = bias + sum_j y[p, j] (P_r[row(p), o*Dy+j] + P_s[src[p], o*Dy+j] + sum_a add[p, a] M_a[a, o*Dy+j])
+ *   bwd : with G[p, o*Dy+j] = y[p, j] dz[p, o]:  dP_r[n, :] = sum of G over the edges received by n,
+ *         dP_s[n, :] = sum of G over the edges sent by n (rowptr_s: sender-sorted CSR; spos[q] = receiver-sorted
+ *         position of the q-th sender-sorted edge, from eqnn_perm_compose(perm, perm_s))
+ *   wadd: gM_a[a, o*Dy+j] = sum_p add[p, a] G[p, o*Dy+j]   (1 <= n_add <= 8; two-stage, fixed order)
+ * The remaining gradients (h, M_s, M_r) are node-level GEMMs on dP_s / dP_r. */
+int eqnn_segnn_edge0_fwd(const float* Ps, const float* Pr, const float* add, int n_add, const float* Ma, const float* y,
+                         int Dy, int Do, const float* bias, int bias_col, int n_bias, const int32_t* rowptr,
+                         const int32_t* src, int n_nodes, float* z, eqnn_stream_t stream);
+int eqnn_segnn_edge0_bwd(const float* dz, const float* y, int Dy, int Do, const int32_t* rowptr, const int32_t* rowptr_s,
+                         const int32_t* spos, int n_nodes, float* dPs, float* dPr, eqnn_stream_t stream);
+size_t eqnn_segnn_edge0_wadd_workspace_bytes(int n_add, int Dy, int Do);
+int eqnn_segnn_edge0_wadd(const float* add, int n_add, const float* y, int Dy, const float* dz, int Do, int64_t E,
+                          float* gMa, void* ws, size_t ws_bytes, eqnn_stream_t stream);
+int eqnn_perm_compose(const int32_t* perm, const int32_t* perm_s, int64_t n, int32_t* inv, int32_t* spos,
+                      eqnn_stream_t stream);
 /* dst[p, :] = src[perm[p], :]  (per-edge arrays into receiver-sorted order);  y += a * x */
 int eqnn_gather_rows(const float* src, const int32_t* perm, int64_t n, int width, float* dst, eqnn_stream_t stream);
 int eqnn_axpy(int64_t n, float a, const float* x, float* y, eqnn_stream_t stream);
