@@ -369,13 +369,18 @@ def run_family(args):
         plan = model.plan(Irreps("1o"), SEGNN_LMAX_ATTR, 1)
         Nt, Et = B * N_NODES, E_step
         edge_layers = {id(t) for st in plan.steps for t in st["edge"]}
-        flops = blocked = 0.0
+        # the first edge layer of a step runs its two wide products at the nodes (h @ M_s, h @ M_r: segnn._edge0_fwd)
+        at_nodes = {id(st["edge"][0]) for st in plan.steps if model._edge0_ok(plan, st["edge"][0], 1)}
+        flops = 0.0
         for t in plan.tplgs:
             if not t.live:
                 continue
             rows = Et if id(t) in edge_layers else Nt
             passes = 2 if t is plan.embed else 3                 # forward, weight gradient (+ data gradient)
-            flops += passes * 2.0 * rows * t.Dx * t.Dy * t.Do
+            if id(t) in at_nodes:
+                flops += 3 * 2.0 * Nt * (t.Dx - 1) * t.Dy * t.Do  # GEMM work as executed: node rows, h_s and h_r blocks
+            else:
+                flops += passes * 2.0 * rows * t.Dx * t.Dy * t.Do
         n_g, ms_g = prof.get("segnn_gemm", (0, 0.0))
         tf = flops / (ms_g * 1e-3) / 1e12 if ms_g > 0 else float("nan")
         roof = {"kernel": "TensorProductLinearGate GEMMs fwd + dgrad + wgrad (tc_gemm_kernel: tcgen05 kind::tf32, 3 MMAs "
@@ -383,8 +388,9 @@ def run_family(args):
                 "unit": "TFLOP/s", "frac": tf / pk["tf_sust"], "traffic": None,
                 "peak_source": f"bf16_tflops_sustained of {pk['which']}", "launches_per_step": n_g, "ms_per_step": ms_g,
                 "flops_per_step": flops,
-                "note": "algorithmic flops = 2 Dx Dy Do per row and pass of the dense-lowered layer, 1 per product; the "
-                        "kernel issues 3 tf32 MMAs per product at half the bf16 rate, so its own ceiling is peak / 6"}
+                "note": "flops = 2 Dx Dy Do per row and pass of the dense-lowered layer as executed (the first edge layer "
+                        "of every step at the node rows), 1 per product; the kernel issues 3 tf32 MMAs per product at half "
+                        "the bf16 rate, so its own ceiling is peak / 6"}
     else:
         per_edge_step = (128 + 512) + 4 * 1024 + 516 + (1028 + 4 * 1536 + 640) + (640 + 4 * 1024 + 516)
         n_f, ms_f = prof.get("egnn_mlp_fwd", (0, 0.0))

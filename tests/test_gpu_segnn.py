@@ -87,6 +87,10 @@ def _run(kw, irreps, x, k, lmax_attr, n_rb, pbc, vel, n_glob=0, lowering="dense"
     # train_cosmology.py:185 style: attributes l <= 2, Bessel messages, mean aggregation, graph read-out, no residual
     (dict(d_hidden=64, n_layers=2, message_passing_steps=2, message_passing_agg="mean", task="graph", output_irreps="1x0e",
           l_max_hidden=2, n_outputs=2, residual=False), "1o", 3, 2, 8, True, False, 0),
+    # 12 Bessel messages: more additional messages than the node-level first-edge-layer path takes (<= 8), so the
+    # concat(add, h_s, h_r) route runs
+    (dict(d_hidden=32, n_layers=2, message_passing_steps=2, message_passing_agg="sum", task="node", output_irreps="1x1o",
+          l_max_hidden=1, residual=True), "1o", 3, 1, 12, True, False, 0),
     # graph globals (TPCF vector) -> concat + LayerNorm before the read-out MLP (segnn.py:282-286)
     (dict(d_hidden=32, n_layers=2, message_passing_steps=1, message_passing_agg="mean", task="graph", output_irreps="1x0e",
           n_outputs=2), "1o", 3, 1, 0, False, False, 12),
