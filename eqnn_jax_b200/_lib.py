@@ -62,6 +62,10 @@ SIGNATURES: Dict[str, tuple] = {
     "eqnn_segnn_edge0_wadd_workspace_bytes": (_sz, [_i, _i, _i]),
     "eqnn_segnn_edge0_wadd": (_i, [_p, _i, _p, _i, _p, _i, _i64, _p, _p, _sz, _p]),
     "eqnn_perm_compose": (_i, [_p, _p, _i64, _p, _p]),
+    "eqnn_segnn_yagg_fwd": (_i, [_p, _i, _p, _i, _p, _i, _i, _p, _p]),
+    "eqnn_segnn_yagg_bwd": (_i, [_p, _i, _p, _i, _p, _i, _i, _p, _p]),
+    "eqnn_segnn_bias_deg_fwd": (_i, [_p, _i, _p, _i, _p, _i, _i, _p]),
+    "eqnn_segnn_bias_deg_bwd": (_i, [_p, _i, _p, _i, _i, _i, _p, _p]),
     "eqnn_gather_rows": (_i, [_p, _p, _i64, _i, _p, _p]),
     "eqnn_axpy": (_i, [_i64, _f, _p, _p, _p]),
     "eqnn_steerable_attrs": (_i, [_p, _i, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p]),

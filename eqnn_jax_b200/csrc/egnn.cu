@@ -718,6 +718,94 @@ __global__ void perm_gather_kernel(const int32_t* __restrict__ inv, const int32_
   if (i < n) spos[i] = inv[perm_s[i]];
 }
 
+// ---- last edge layer of a SEGNN message-passing step, evaluated at the nodes ------------------------------------
+// The last edge layer has no gate (segnn.py:66-77) and its output is only aggregated over the receivers (:218), so
+//   agg[n, o] = f sum_{p in n} (b[o] + sum_j y[p, j] (m[p] @ M_cat)[o*Dy+j]) = sum_j (S_j[n] @ M_j)[o] + b[o] w(n)
+// with S_j[n, k] = f sum_{p in n} y[p, j] m[p, k] (f = 1 for sum, 1/deg for mean; w(n) = f deg) and
+// M_j[k, o] = M_cat[k, o*Dy+j]: one y-weighted segment reduction per edge, the GEMMs run on the node rows.
+constexpr int YAGG_MAX_DY = 16;
+__global__ void __launch_bounds__(256) segnn_yagg_fwd_kernel(const float* __restrict__ m, int Dx, const float* __restrict__ y,
+                                                             int Dy, const int32_t* __restrict__ rowptr, int n_nodes, int agg,
+                                                             float* __restrict__ S) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= n_nodes) return;
+  const int p0 = rowptr[row], p1 = rowptr[row + 1];
+  const float inv = (agg == 1) ? 1.f / (float)max(p1 - p0, 1) : 1.f;
+  for (int k = lane; k < Dx; k += 32) {
+    float acc[YAGG_MAX_DY];
+#pragma unroll
+    for (int j = 0; j < YAGG_MAX_DY; ++j) acc[j] = 0.f;
+    for (int p = p0; p < p1; ++p) {
+      const float v = m[(size_t)p * Dx + k];
+      const float* yp = y + (size_t)p * Dy;
+#pragma unroll
+      for (int j = 0; j < YAGG_MAX_DY; ++j)
+        if (j < Dy) acc[j] = fmaf(__ldg(yp + j), v, acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < YAGG_MAX_DY; ++j)
+      if (j < Dy) S[((size_t)j * n_nodes + row) * Dx + k] = acc[j] * inv;
+  }
+}
+
+// dm[p, k] = f sum_j y[p, j] dS_j[n(p), k]
+__global__ void __launch_bounds__(256) segnn_yagg_bwd_kernel(const float* __restrict__ dS, int Dx, const float* __restrict__ y,
+                                                             int Dy, const int32_t* __restrict__ rowptr, int n_nodes, int agg,
+                                                             float* __restrict__ dm) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= n_nodes) return;
+  const int p0 = rowptr[row], p1 = rowptr[row + 1];
+  const float inv = (agg == 1) ? 1.f / (float)max(p1 - p0, 1) : 1.f;
+  for (int k = lane; k < Dx; k += 32) {
+    float g[YAGG_MAX_DY];
+#pragma unroll
+    for (int j = 0; j < YAGG_MAX_DY; ++j) g[j] = (j < Dy) ? dS[((size_t)j * n_nodes + row) * Dx + k] * inv : 0.f;
+    for (int p = p0; p < p1; ++p) {
+      const float* yp = y + (size_t)p * Dy;
+      float a = 0.f;
+#pragma unroll
+      for (int j = 0; j < YAGG_MAX_DY; ++j)
+        if (j < Dy) a = fmaf(__ldg(yp + j), g[j], a);
+      dm[(size_t)p * Dx + k] = a;
+    }
+  }
+}
+
+// out[n, c] += b[c] w(n) for the bias columns;  w(n) = deg (sum) or [deg > 0] (mean)
+__global__ void segnn_bias_deg_fwd_kernel(float* __restrict__ out, int ld, const float* __restrict__ bias, int n_bias,
+                                          const int32_t* __restrict__ rowptr, int n_nodes, int agg) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)n_nodes * n_bias) return;
+  const int64_t n = i / n_bias;
+  const int c = (int)(i - n * n_bias);
+  const int deg = rowptr[n + 1] - rowptr[n];
+  const float w = (agg == 1) ? (deg > 0 ? 1.f : 0.f) : (float)deg;
+  out[(size_t)n * ld + c] += __ldg(bias + c) * w;
+}
+
+// gb[c] = sum_n w(n) d[n, c]: one block per bias column, fixed-order tree
+__global__ void __launch_bounds__(256) segnn_bias_deg_bwd_kernel(const float* __restrict__ d, int ld,
+                                                                 const int32_t* __restrict__ rowptr, int n_nodes, int agg,
+                                                                 float* __restrict__ gb) {
+  __shared__ float red[256];
+  const int c = blockIdx.x;
+  float a = 0.f;
+  for (int n = threadIdx.x; n < n_nodes; n += 256) {
+    const int deg = rowptr[n + 1] - rowptr[n];
+    const float w = (agg == 1) ? (deg > 0 ? 1.f : 0.f) : (float)deg;
+    a = fmaf(w, d[(size_t)n * ld + c], a);
+  }
+  red[threadIdx.x] = a;
+  __syncthreads();
+  for (int s2 = 128; s2 > 0; s2 >>= 1) {
+    if ((int)threadIdx.x < s2) red[threadIdx.x] += red[threadIdx.x + s2];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) gb[c] = red[0];
+}
+
 // dst[p, :] = src[perm[p], :]
 __global__ void gather_rows_kernel(const float* __restrict__ src, const int32_t* __restrict__ perm, int64_t n, int w,
                                    float* __restrict__ dst) {
@@ -1004,6 +1092,48 @@ extern "C" int eqnn_perm_compose(const int32_t* perm, const int32_t* perm_s, int
   perm_invert_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(perm, n, inv);
   perm_gather_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(inv, perm_s, n, spos);
   EQNN_CHECK_LAUNCH_N(2);
+  return EQNN_OK;
+}
+
+extern "C" int eqnn_segnn_yagg_fwd(const float* m, int Dx, const float* y, int Dy, const int32_t* rowptr, int n_nodes,
+                                   int agg, float* S, eqnn_stream_t stream) {
+  EQNN_CHECK_ARG(m && y && rowptr && S && Dx >= 1 && Dy >= 1 && Dy <= YAGG_MAX_DY && (agg == 0 || agg == 1),
+                 "segnn_yagg_fwd: bad argument (Dy <= 16, agg 0 sum | 1 mean)");
+  if (n_nodes <= 0) return EQNN_OK;
+  segnn_yagg_fwd_kernel<<<(unsigned)ceil_div64((int64_t)n_nodes * 32, 256), 256, 0, as_stream(stream)>>>(m, Dx, y, Dy, rowptr,
+                                                                                                      n_nodes, agg, S);
+  EQNN_CHECK_LAUNCH();
+  return EQNN_OK;
+}
+
+extern "C" int eqnn_segnn_yagg_bwd(const float* dS, int Dx, const float* y, int Dy, const int32_t* rowptr, int n_nodes,
+                                   int agg, float* dm, eqnn_stream_t stream) {
+  EQNN_CHECK_ARG(dS && y && rowptr && dm && Dx >= 1 && Dy >= 1 && Dy <= YAGG_MAX_DY && (agg == 0 || agg == 1),
+                 "segnn_yagg_bwd: bad argument (Dy <= 16, agg 0 sum | 1 mean)");
+  if (n_nodes <= 0) return EQNN_OK;
+  segnn_yagg_bwd_kernel<<<(unsigned)ceil_div64((int64_t)n_nodes * 32, 256), 256, 0, as_stream(stream)>>>(dS, Dx, y, Dy, rowptr,
+                                                                                                      n_nodes, agg, dm);
+  EQNN_CHECK_LAUNCH();
+  return EQNN_OK;
+}
+
+extern "C" int eqnn_segnn_bias_deg_fwd(float* out, int ld, const float* bias, int n_bias, const int32_t* rowptr, int n_nodes,
+                                       int agg, eqnn_stream_t stream) {
+  EQNN_CHECK_ARG(out && bias && rowptr && n_bias >= 0 && ld >= n_bias && (agg == 0 || agg == 1), "segnn_bias_deg_fwd: bad argument");
+  if (n_nodes <= 0 || n_bias == 0) return EQNN_OK;
+  segnn_bias_deg_fwd_kernel<<<(unsigned)ceil_div64((int64_t)n_nodes * n_bias, 256), 256, 0, as_stream(stream)>>>(
+      out, ld, bias, n_bias, rowptr, n_nodes, agg);
+  EQNN_CHECK_LAUNCH();
+  return EQNN_OK;
+}
+
+extern "C" int eqnn_segnn_bias_deg_bwd(const float* d, int ld, const int32_t* rowptr, int n_nodes, int agg, int n_bias,
+                                       float* gb, eqnn_stream_t stream) {
+  EQNN_CHECK_ARG(d && rowptr && gb && n_bias >= 0 && ld >= n_bias && n_nodes >= 0 && (agg == 0 || agg == 1),
+                 "segnn_bias_deg_bwd: bad argument");
+  if (n_bias == 0) return EQNN_OK;
+  segnn_bias_deg_bwd_kernel<<<n_bias, 256, 0, as_stream(stream)>>>(d, ld, rowptr, n_nodes, agg, gb);
+  EQNN_CHECK_LAUNCH();
   return EQNN_OK;
 }
 

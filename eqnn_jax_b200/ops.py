@@ -365,6 +365,30 @@ def segnn_edge0_wadd(add, n_add, y, Dy, dz, Do, E, gwexp, g_off):
         TIMER.end("segnn_edge0", t0)
 
 
+def segnn_yagg_fwd(m, Dx, y, Dy, rowptr, n_nodes, agg, S):
+    t0 = TIMER.begin() if TIMER else None
+    check(lib().eqnn_segnn_yagg_fwd(_ptr(m), Dx, _ptr(y), Dy, _ptr(rowptr), n_nodes, agg, _ptr(S), _stream()), "segnn_yagg_fwd")
+    if TIMER:
+        TIMER.end("segnn_edgeL", t0)
+
+
+def segnn_yagg_bwd(dS, Dx, y, Dy, rowptr, n_nodes, agg, dm):
+    t0 = TIMER.begin() if TIMER else None
+    check(lib().eqnn_segnn_yagg_bwd(_ptr(dS), Dx, _ptr(y), Dy, _ptr(rowptr), n_nodes, agg, _ptr(dm), _stream()), "segnn_yagg_bwd")
+    if TIMER:
+        TIMER.end("segnn_edgeL", t0)
+
+
+def segnn_bias_deg_fwd(out, out_off, ld, bias_buf, bias_off, n_bias, rowptr, n_nodes, agg):
+    check(lib().eqnn_segnn_bias_deg_fwd(_off(out, out_off), ld, _off(bias_buf, bias_off), n_bias, _ptr(rowptr), n_nodes, agg,
+                                        _stream()), "segnn_bias_deg_fwd")
+
+
+def segnn_bias_deg_bwd(d, d_off, ld, rowptr, n_nodes, agg, n_bias, gb, gb_off):
+    check(lib().eqnn_segnn_bias_deg_bwd(_off(d, d_off), ld, _ptr(rowptr), n_nodes, agg, n_bias, _off(gb, gb_off), _stream()),
+          "segnn_bias_deg_bwd")
+
+
 def perm_compose(perm, perm_s):
     """spos[q] = receiver-sorted position of the q-th sender-sorted edge."""
     n = perm.numel()

@@ -599,6 +599,44 @@ class SEGNN:
                 **self._gemm_kw)
         ops.segnn_edge0_wadd(add, n_add, y, t.Dy, dz, t.Do, Et, gwexp, t.M_off)
 
+    # -- last edge layer of a step, evaluated at the nodes -----------------------------------------------------
+    def _edgeL_ok(self, plan, st) -> bool:
+        t = st["edge"][-1]
+        return plan.lowering == "dense" and len(st["edge"]) >= 2 and t.has_y and not t.activation and t.Dy <= 16
+
+    def _edgeL_fwd(self, plan, t: _TPLG, theta, wexp, m, y, rowptr, Nt, agg, Cc, ldc, col_off):
+        """The last edge layer has no gate and is only aggregated over the receivers, so the aggregation moves in front
+        of it: S_j[n] = f sum_{p in n} y[p, j] m[p] (one pass over the edges), agg[n] = sum_j S_j[n] @ M_j + b w(n)
+        (Dy GEMMs on the node rows, written straight into the node function's input Cc[:, col_off:])."""
+        f32 = dict(dtype=torch.float32, device=theta.device)
+        Dx, nc = t.Dx, t.Dy * t.Do
+        S = torch.empty((t.Dy, Nt, Dx), **f32)
+        ops.segnn_yagg_fwd(m, Dx, y, t.Dy, rowptr, Nt, agg, S)
+        for j in range(t.Dy):
+            ops.gemm(Nt, t.Do, Dx, 1.0, S, Dx, 1, wexp, nc, t.Dy, Cc, ldc, 1, accumulate=j > 0, a_off=j * Nt * Dx,
+                     b_off=t.M_off + j, c_off=col_off, **self._gemm_kw)
+        if t.n_bias:
+            ops.segnn_bias_deg_fwd(Cc, col_off + t.b_col, ldc, theta, t.b_off, t.n_bias, rowptr, Nt, agg)
+        return (S,)
+
+    def _edgeL_bwd(self, plan, t: _TPLG, theta, gtheta, wexp, gwexp, sv, dC, ldc, col_off, y, rowptr, Nt, Et, agg):
+        """-> dL/dm [Et, Dx] from dL/dagg = dC[:, col_off:col_off + Do]; parameter gradients on the node rows."""
+        (S,) = sv
+        f32 = dict(dtype=torch.float32, device=theta.device)
+        Dx, nc = t.Dx, t.Dy * t.Do
+        if t.n_bias:
+            ops.segnn_bias_deg_bwd(dC, col_off + t.b_col, ldc, rowptr, Nt, agg, t.n_bias, gtheta, t.b_off)
+        dS = torch.empty((t.Dy, Nt, Dx), **f32)
+        for j in range(t.Dy):
+            # dS_j = dagg @ M_j^T ;  gM_j = S_j^T @ dagg  (M_j[k, o] = M_cat[k, o*Dy + j])
+            ops.gemm(Nt, Dx, t.Do, 1.0, dC, ldc, 1, wexp, t.Dy, nc, dS, Dx, 1, a_off=col_off, b_off=t.M_off + j,
+                     c_off=j * Nt * Dx, **self._gemm_kw)
+            ops.gemm(Dx, t.Do, Nt, 1.0, S, 1, Dx, dC, ldc, 1, gwexp, nc, t.Dy, a_off=j * Nt * Dx, b_off=col_off,
+                     c_off=t.M_off + j, **self._gemm_kw)
+        dm = torch.empty((Et, Dx), **f32)
+        ops.segnn_yagg_bwd(dS, Dx, y, t.Dy, rowptr, Nt, agg, dm)
+        return dm
+
     # -- whole model ------------------------------------------------------------------------------------
     def _forward(self, theta, plan, nodes, B, N, E, csr, y_node, y_edge, add, glob=None):
         rowptr, perm, src, rowptr_s, perm_s, spos = csr
@@ -624,14 +662,18 @@ class SEGNN:
                 m = torch.empty((Et, n_add + 2 * Dh), **f32)
                 ops.egnn_edge_input_fwd(add, n_add, h, Dh, 0, Dh, rowptr, src, Nt, m)       # concat(add, h_s, h_r) :112
             ld = m.shape[1]
-            for t in rest:
+            fastL = self._edgeL_ok(plan, st)
+            for t in (rest[:-1] if fastL else rest):
                 m, s_ = self._tplg_fwd(plan, t, theta, wexp, m, ld, y_edge, Et)
                 ld = m.shape[1]
                 es.append(s_)
-            Dm = m.shape[1]
+            Dm = st["edge"][-1].D_out
             Cc = torch.empty((Nt, Dh + Dm), **f32)                                        # concat(h, agg) :79-81
             ops.copy_cols(h, Dh, 0, Dh, Nt, Cc, Dh + Dm, 0)
-            ops.egnn_segment_rows_fwd(m, Dm, 0, rowptr, Nt, agg, Cc, Dh + Dm, col_off=Dh)
+            if fastL:
+                es.append(self._edgeL_fwd(plan, st["edge"][-1], theta, wexp, m, y_edge, rowptr, Nt, agg, Cc, Dh + Dm, Dh))
+            else:
+                ops.egnn_segment_rows_fwd(m, Dm, 0, rowptr, Nt, agg, Cc, Dh + Dm, col_off=Dh)
             new, ns = self._tplg_fwd(plan, st["node"], theta, wexp, Cc, Dh + Dm, y_node, Nt)
             if self.residual:
                 ops.axpy(1.0, h, new)
@@ -717,11 +759,16 @@ class SEGNN:
             ops.copy_cols(dC, Dh + Dm, 0, Dh, Nt, dh_prev, Dh, 0)
             if self.residual:
                 ops.axpy(1.0, dh, dh_prev)
-            dm = torch.zeros((Et, Dm), **f32)
-            ops.egnn_segment_rows_bwd(dC, Dh + Dm, Dh, Dm, None, 0, rowptr, Nt, agg, dm)
             fast0 = self._edge0_ok(plan, st["edge"][0], n_add)
-            for t, s_ in zip(reversed(st["edge"][1:] if fast0 else st["edge"]),
-                             reversed(sv["edge"][1:] if fast0 else sv["edge"])):
+            fastL = self._edgeL_ok(plan, st)
+            lo, hi = (1 if fast0 else 0), len(st["edge"]) - (1 if fastL else 0)
+            if fastL:
+                dm = self._edgeL_bwd(plan, st["edge"][-1], theta, gtheta, wexp, gwexp, sv["edge"][-1], dC, Dh + Dm, Dh, y_edge,
+                                     rowptr, Nt, Et, agg)
+            else:
+                dm = torch.zeros((Et, Dm), **f32)
+                ops.egnn_segment_rows_bwd(dC, Dh + Dm, Dh, Dm, None, 0, rowptr, Nt, agg, dm)
+            for t, s_ in zip(reversed(st["edge"][lo:hi]), reversed(sv["edge"][lo:hi])):
                 dm = self._tplg_bwd(plan, t, theta, gtheta, wexp, gwexp, s_, dm, Et)
             if fast0:
                 self._edge0_bwd(plan, st["edge"][0], theta, gtheta, wexp, gwexp, sv["edge"][0], dm, Dh, add, n_add, csr,

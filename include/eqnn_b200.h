@@ -262,6 +262,21 @@ int eqnn_segnn_edge0_wadd(const float* add, int n_add, const float* y, int Dy, c
                           float* gMa, void* ws, size_t ws_bytes, eqnn_stream_t stream);
 int eqnn_perm_compose(const int32_t* perm, const int32_t* perm_s, int64_t n, int32_t* inv, int32_t* spos,
                       eqnn_stream_t stream);
+/* Last edge layer of a message-passing step, evaluated at the nodes: it has no gate (segnn.py:66-77) and its output
+ * is only aggregated over the receivers (:218), so with f = 1 (sum) or 1/deg (mean), w(n) = f deg:
+ *   agg[n, o] = sum_j (S_j[n] @ M_j)[o] + b[o] w(n),   S_j[n, k] = f sum_{p in n} y[p, j] m[p, k],  M_j[k, o] = M_cat[k, o*Dy+j]
+ *   yagg_fwd: S [Dy][n_nodes][Dx] from the per-edge inputs m [E][Dx] (receiver-sorted, rowptr);  the caller runs the
+ *             Dy node-level GEMMs (eqnn_gemm_f32 with strides Do*Dy, Dy on M_cat);  bias_deg_fwd adds b w(n) in place
+ *   yagg_bwd: dm[p, k] = f sum_j y[p, j] dS_j[n(p), k];   bias_deg_bwd: gb[c] = sum_n w(n) d[n, c]
+ * agg: 0 sum | 1 mean.  Dy <= 16. */
+int eqnn_segnn_yagg_fwd(const float* m, int Dx, const float* y, int Dy, const int32_t* rowptr, int n_nodes, int agg,
+                        float* S, eqnn_stream_t stream);
+int eqnn_segnn_yagg_bwd(const float* dS, int Dx, const float* y, int Dy, const int32_t* rowptr, int n_nodes, int agg,
+                        float* dm, eqnn_stream_t stream);
+int eqnn_segnn_bias_deg_fwd(float* out, int ld, const float* bias, int n_bias, const int32_t* rowptr, int n_nodes, int agg,
+                            eqnn_stream_t stream);
+int eqnn_segnn_bias_deg_bwd(const float* d, int ld, const int32_t* rowptr, int n_nodes, int agg, int n_bias, float* gb,
+                            eqnn_stream_t stream);
 /* dst[p, :] = src[perm[p], :]  (per-edge arrays into receiver-sorted order);  y += a * x */
 int eqnn_gather_rows(const float* src, const int32_t* perm, int64_t n, int width, float* dst, eqnn_stream_t stream);
 int eqnn_axpy(int64_t n, float a, const float* x, float* y, eqnn_stream_t stream);
