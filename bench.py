@@ -371,14 +371,17 @@ def run_family(args):
         edge_layers = {id(t) for st in plan.steps for t in st["edge"]}
         # the first edge layer of a step runs its two wide products at the nodes (h @ M_s, h @ M_r: segnn._edge0_fwd)
         at_nodes = {id(st["edge"][0]) for st in plan.steps if model._edge0_ok(plan, st["edge"][0], 1)}
+        # ... and so does the last one (no gate, only aggregated: segnn._edgeL_fwd)
+        last_at_nodes = {id(st["edge"][-1]) for st in plan.steps if model._edgeL_ok(plan, st)}
         flops = 0.0
         for t in plan.tplgs:
             if not t.live:
                 continue
             rows = Et if id(t) in edge_layers else Nt
             passes = 2 if t is plan.embed else 3                 # forward, weight gradient (+ data gradient)
-            if id(t) in at_nodes:
-                flops += 3 * 2.0 * Nt * (t.Dx - 1) * t.Dy * t.Do  # GEMM work as executed: node rows, h_s and h_r blocks
+            if id(t) in at_nodes or id(t) in last_at_nodes:
+                # GEMM work as executed: node rows (first layer: the h_s and h_r blocks; last layer: Dy GEMMs on S_j)
+                flops += 3 * 2.0 * Nt * (t.Dx - (1 if id(t) in at_nodes else 0)) * t.Dy * t.Do
             else:
                 flops += passes * 2.0 * rows * t.Dx * t.Dy * t.Do
         n_g, ms_g = prof.get("segnn_gemm", (0, 0.0))
@@ -388,8 +391,8 @@ def run_family(args):
                 "unit": "TFLOP/s", "frac": tf / pk["tf_sust"], "traffic": None,
                 "peak_source": f"bf16_tflops_sustained of {pk['which']}", "launches_per_step": n_g, "ms_per_step": ms_g,
                 "flops_per_step": flops,
-                "note": "flops = 2 Dx Dy Do per row and pass of the dense-lowered layer as executed (the first edge layer "
-                        "of every step at the node rows), 1 per product; the kernel issues 3 tf32 MMAs per product at half "
+                "note": "flops = 2 Dx Dy Do per row and pass of the dense-lowered layer as executed (the first and the "
+                        "last edge layer of every step at the node rows), 1 per product; the kernel issues 3 tf32 MMAs per product at half "
                         "the bf16 rate, so its own ceiling is peak / 6"}
     else:
         per_edge_step = (128 + 512) + 4 * 1024 + 516 + (1028 + 4 * 1536 + 640) + (640 + 4 * 1024 + 516)

@@ -699,6 +699,42 @@ __global__ void __launch_bounds__(1024) segnn_edge0_wadd_partial_kernel(const fl
       if (a < n_add) part[((size_t)blockIdx.x * n_add + a) * nc + c] = acc[a];
   }
 }
+// Dy <= 4: thread per output o keeps all n_add x Dy accumulators, so dz is read once per edge (coalesced) and the
+// attribute / message values are warp-wide broadcasts
+__global__ void __launch_bounds__(256) segnn_edge0_wadd_partial4_kernel(const float* __restrict__ add, int n_add,
+                                                                        const float* __restrict__ y, int Dy,
+                                                                        const float* __restrict__ dz, int Do, int64_t E,
+                                                                        int64_t per, float* __restrict__ part) {
+  const int nc = Do * Dy;
+  const int64_t e0 = (int64_t)blockIdx.x * per, e1 = (e0 + per < E) ? e0 + per : E;
+  for (int o = threadIdx.x; o < Do; o += blockDim.x) {
+    float acc[8][4];
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[a][j] = 0.f;
+#pragma unroll 2
+    for (int64_t p = e0; p < e1; ++p) {
+      const float d = __ldg(dz + p * Do + o);
+      float g[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) g[j] = (j < Dy) ? __ldg(y + p * Dy + j) * d : 0.f;
+#pragma unroll
+      for (int a = 0; a < 8; ++a) {
+        if (a < n_add) {
+          const float f = __ldg(add + p * n_add + a);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[a][j] = fmaf(f, g[j], acc[a][j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (a < n_add && j < Dy) part[((size_t)blockIdx.x * n_add + a) * nc + o * Dy + j] = acc[a][j];
+  }
+}
 __global__ void segnn_edge0_wadd_final_kernel(const float* __restrict__ part, int parts, int n, float* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -1073,12 +1109,18 @@ extern "C" int eqnn_segnn_edge0_wadd(const float* add, int n_add, const float* y
   EQNN_CHECK_ARG(add && y && dz && gMa && n_add >= 1 && n_add <= 8 && Dy >= 1 && Do >= 1 && E >= 0,
                  "segnn_edge0_wadd: bad argument (1 <= n_add <= 8)");
   EQNN_CHECK_ARG(ws && ws_bytes >= eqnn_segnn_edge0_wadd_workspace_bytes(n_add, Dy, Do), "segnn_edge0_wadd: workspace too small");
-  const int parts = (int)min((int64_t)EDGE0_PARTS, max((int64_t)1, (E + 63) / 64));
+  // the Dy <= 4 kernel keeps every load coalesced or broadcast: a quarter of the partials is enough to fill the GPU
+  const int cap = (Dy <= 4) ? EDGE0_PARTS / 4 : EDGE0_PARTS;
+  const int parts = (int)min((int64_t)cap, max((int64_t)1, (E + 63) / 64));
   const int64_t per = (E + parts - 1) / parts;
   const int n = n_add * Dy * Do;
   cudaStream_t st = as_stream(stream);
   const int nthr = (Dy * Do >= 1024) ? 1024 : (Dy * Do + 31) / 32 * 32;
-  segnn_edge0_wadd_partial_kernel<<<parts, nthr, 0, st>>>(add, n_add, y, Dy, dz, Do, E, per, reinterpret_cast<float*>(ws));
+  if (Dy <= 4)
+    segnn_edge0_wadd_partial4_kernel<<<parts, Do >= 256 ? 256 : (Do + 31) / 32 * 32, 0, st>>>(
+        add, n_add, y, Dy, dz, Do, E, per, reinterpret_cast<float*>(ws));
+  else
+    segnn_edge0_wadd_partial_kernel<<<parts, nthr, 0, st>>>(add, n_add, y, Dy, dz, Do, E, per, reinterpret_cast<float*>(ws));
   segnn_edge0_wadd_final_kernel<<<(n + 127) / 128, 128, 0, st>>>(reinterpret_cast<float*>(ws), parts, n, gMa);
   EQNN_CHECK_LAUNCH_N(2);
   return EQNN_OK;
