@@ -21,6 +21,11 @@ computed.  The layer GEMMs run on the tcgen05 tensor cores with 3xTF32 operand s
 strides / alignment, K split over CTAs for the weight gradients); ``tensor_cores=False`` keeps them on the fp32
 CUDA-core kernel.  ``lowering="blocked"`` is a second, irrep-blocked route (multiplicity GEMMs per stored irrep
 block + a Clebsch-Gordan table kernel, 4x fewer FLOPs but overhead-bound K <= 89 GEMMs).
+Two of the three edge layers of a message-passing step do not run per edge: the first one takes
+concat(add_e, h_sender, h_receiver), so its wide products are formed per node and gathered (``_edge0_fwd``); the last
+one has no gate and is only aggregated over the receivers, so the aggregation is pulled in front of it and its GEMMs
+run on the node rows (``_edgeL_fwd``).  With attributes l <= 1 the forward GEMM of the remaining layers contracts the
+attribute axis in its epilogue (``eqnn_segnn_tplg_fwd``).
 Graph globals (concatenated to the pooled scalars, LayerNorm, :282-286) are supported.
 Not built: max aggregation, activations other than gelu -> NotImplementedError, never a fallback.
 """

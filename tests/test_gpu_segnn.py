@@ -150,6 +150,50 @@ def test_segnn_row_blocks(monkeypatch, lowering):
         assert err <= RTOL * max(float(w.grad.abs().max()), 1e-30) + 1e-6 * gmax, ("/".join(path), err)
 
 
+def test_segnn_routes_agree_at_cloud_size(monkeypatch):
+    """A 3000-node kNN-20 PBC cloud (too large for the oracle in a test): the default route (dense lowering on tensor
+    cores, first and last edge layer of every step at the nodes) against the plain per-edge route on the CUDA cores and
+    against the irrep-blocked lowering -- outputs and every parameter gradient."""
+    from eqnn_jax_b200 import graph_utils as GU, ops
+    from eqnn_jax_b200 import segnn as SG
+    from eqnn_jax_b200.equivariant_graph_utils import get_equivariant_graph
+    from eqnn_jax_b200.irreps import Irreps
+    from eqnn_jax_b200.nequip import IrrepsArray
+    rng = np.random.default_rng(3)
+    B, N, k = 1, 3000, 20
+    x = torch.tensor(rng.uniform(0.0, 1.0, size=(B, N, 3)).astype(np.float32)).cuda()
+    pbc = GU.get_apply_pbc(cell=np.eye(3, dtype=np.float32))
+    s, r, _ = ops.knn_pbc(x, k, pbc.cell, pbc.cell_inv, want_dr=False)
+    g = get_equivariant_graph(IrrepsArray(Irreps("1o"), x), x, None, s, r, None, None, None, None, 1, apply_pbc=pbc)
+    kw = dict(d_hidden=64, n_layers=3, message_passing_steps=2, message_passing_agg="mean", task="node",
+              output_irreps="1x1o", l_max_hidden=2, residual=True)
+    cot = torch.tensor(rng.normal(size=(B, N, 3)).astype(np.float32)).cuda()
+
+    def run(per_edge=False, **extra):
+        model = SG.SEGNN(**kw, **extra)
+        if per_edge:
+            monkeypatch.setattr(SG.SEGNN, "_edge0_ok", lambda self, *a: False)
+            monkeypatch.setattr(SG.SEGNN, "_edgeL_ok", lambda self, *a: False)
+        params = model.init(0, g)
+        out = model.forward_backward(params, g, lambda o: cot)
+        monkeypatch.undo()
+        return out.double().cpu().numpy(), params.grad.double().cpu().numpy(), params
+
+    out0, g0, params = run()
+    scale = {}
+    for path, shape, off in params.layout:
+        n = int(np.prod(shape))
+        scale[path[0]] = max(scale.get(path[0], 0.0), float(np.abs(g0[off:off + n]).max()))
+    gmax = max(scale.values())
+    for what, (out1, g1, _) in {"per-edge, CUDA cores": run(per_edge=True, tensor_cores=False),
+                                "blocked lowering": run(lowering="blocked")}.items():
+        assert np.abs(out1 - out0).max() <= 2e-5 * np.abs(out0).max(), what
+        for path, shape, off in params.layout:
+            n = int(np.prod(shape))
+            err = np.abs(g1[off:off + n] - g0[off:off + n]).max()
+            assert err <= 2e-5 * scale[path[0]] + 2e-7 * gmax, (what, "/".join(path), err, scale[path[0]], gmax)
+
+
 def test_segnn_reference_equivariance_property():
     """tests/test_equivariance.py:288-310 on the B200 path: f(R x) = R f(x) for the 7-feature node task."""
     from eqnn_jax_b200.equivariant_graph_utils import get_equivariant_graph
