@@ -760,6 +760,7 @@ __global__ void perm_gather_kernel(const int32_t* __restrict__ inv, const int32_
 // with S_j[n, k] = f sum_{p in n} y[p, j] m[p, k] (f = 1 for sum, 1/deg for mean; w(n) = f deg) and
 // M_j[k, o] = M_cat[k, o*Dy+j]: one y-weighted segment reduction per edge, the GEMMs run on the node rows.
 constexpr int YAGG_MAX_DY = 16;
+template <int YAGG_DY>      // attribute slots kept in registers: 4 (l <= 1), 9 (l <= 2) or 16 (l <= 3); Dy <= YAGG_DY
 __global__ void __launch_bounds__(256) segnn_yagg_fwd_kernel(const float* __restrict__ m, int Dx, const float* __restrict__ y,
                                                              int Dy, const int32_t* __restrict__ rowptr, int n_nodes, int agg,
                                                              float* __restrict__ S) {
@@ -769,23 +770,24 @@ __global__ void __launch_bounds__(256) segnn_yagg_fwd_kernel(const float* __rest
   const int p0 = rowptr[row], p1 = rowptr[row + 1];
   const float inv = (agg == 1) ? 1.f / (float)max(p1 - p0, 1) : 1.f;
   for (int k = lane; k < Dx; k += 32) {
-    float acc[YAGG_MAX_DY];
+    float acc[YAGG_DY];
 #pragma unroll
-    for (int j = 0; j < YAGG_MAX_DY; ++j) acc[j] = 0.f;
+    for (int j = 0; j < YAGG_DY; ++j) acc[j] = 0.f;
     for (int p = p0; p < p1; ++p) {
       const float v = m[(size_t)p * Dx + k];
       const float* yp = y + (size_t)p * Dy;
 #pragma unroll
-      for (int j = 0; j < YAGG_MAX_DY; ++j)
+      for (int j = 0; j < YAGG_DY; ++j)
         if (j < Dy) acc[j] = fmaf(__ldg(yp + j), v, acc[j]);
     }
 #pragma unroll
-    for (int j = 0; j < YAGG_MAX_DY; ++j)
+    for (int j = 0; j < YAGG_DY; ++j)
       if (j < Dy) S[((size_t)j * n_nodes + row) * Dx + k] = acc[j] * inv;
   }
 }
 
 // dm[p, k] = f sum_j y[p, j] dS_j[n(p), k]
+template <int YAGG_DY>
 __global__ void __launch_bounds__(256) segnn_yagg_bwd_kernel(const float* __restrict__ dS, int Dx, const float* __restrict__ y,
                                                              int Dy, const int32_t* __restrict__ rowptr, int n_nodes, int agg,
                                                              float* __restrict__ dm) {
@@ -795,14 +797,14 @@ __global__ void __launch_bounds__(256) segnn_yagg_bwd_kernel(const float* __rest
   const int p0 = rowptr[row], p1 = rowptr[row + 1];
   const float inv = (agg == 1) ? 1.f / (float)max(p1 - p0, 1) : 1.f;
   for (int k = lane; k < Dx; k += 32) {
-    float g[YAGG_MAX_DY];
+    float g[YAGG_DY];
 #pragma unroll
-    for (int j = 0; j < YAGG_MAX_DY; ++j) g[j] = (j < Dy) ? dS[((size_t)j * n_nodes + row) * Dx + k] * inv : 0.f;
+    for (int j = 0; j < YAGG_DY; ++j) g[j] = (j < Dy) ? dS[((size_t)j * n_nodes + row) * Dx + k] * inv : 0.f;
     for (int p = p0; p < p1; ++p) {
       const float* yp = y + (size_t)p * Dy;
       float a = 0.f;
 #pragma unroll
-      for (int j = 0; j < YAGG_MAX_DY; ++j)
+      for (int j = 0; j < YAGG_DY; ++j)
         if (j < Dy) a = fmaf(__ldg(yp + j), g[j], a);
       dm[(size_t)p * Dx + k] = a;
     }
@@ -1142,8 +1144,10 @@ extern "C" int eqnn_segnn_yagg_fwd(const float* m, int Dx, const float* y, int D
   EQNN_CHECK_ARG(m && y && rowptr && S && Dx >= 1 && Dy >= 1 && Dy <= YAGG_MAX_DY && (agg == 0 || agg == 1),
                  "segnn_yagg_fwd: bad argument (Dy <= 16, agg 0 sum | 1 mean)");
   if (n_nodes <= 0) return EQNN_OK;
-  segnn_yagg_fwd_kernel<<<(unsigned)ceil_div64((int64_t)n_nodes * 32, 256), 256, 0, as_stream(stream)>>>(m, Dx, y, Dy, rowptr,
-                                                                                                      n_nodes, agg, S);
+  const unsigned grid = (unsigned)ceil_div64((int64_t)n_nodes * 32, 256);
+  if (Dy <= 4) segnn_yagg_fwd_kernel<4><<<grid, 256, 0, as_stream(stream)>>>(m, Dx, y, Dy, rowptr, n_nodes, agg, S);
+  else if (Dy <= 9) segnn_yagg_fwd_kernel<9><<<grid, 256, 0, as_stream(stream)>>>(m, Dx, y, Dy, rowptr, n_nodes, agg, S);
+  else segnn_yagg_fwd_kernel<16><<<grid, 256, 0, as_stream(stream)>>>(m, Dx, y, Dy, rowptr, n_nodes, agg, S);
   EQNN_CHECK_LAUNCH();
   return EQNN_OK;
 }
@@ -1153,8 +1157,10 @@ extern "C" int eqnn_segnn_yagg_bwd(const float* dS, int Dx, const float* y, int 
   EQNN_CHECK_ARG(dS && y && rowptr && dm && Dx >= 1 && Dy >= 1 && Dy <= YAGG_MAX_DY && (agg == 0 || agg == 1),
                  "segnn_yagg_bwd: bad argument (Dy <= 16, agg 0 sum | 1 mean)");
   if (n_nodes <= 0) return EQNN_OK;
-  segnn_yagg_bwd_kernel<<<(unsigned)ceil_div64((int64_t)n_nodes * 32, 256), 256, 0, as_stream(stream)>>>(dS, Dx, y, Dy, rowptr,
-                                                                                                      n_nodes, agg, dm);
+  const unsigned grid = (unsigned)ceil_div64((int64_t)n_nodes * 32, 256);
+  if (Dy <= 4) segnn_yagg_bwd_kernel<4><<<grid, 256, 0, as_stream(stream)>>>(dS, Dx, y, Dy, rowptr, n_nodes, agg, dm);
+  else if (Dy <= 9) segnn_yagg_bwd_kernel<9><<<grid, 256, 0, as_stream(stream)>>>(dS, Dx, y, Dy, rowptr, n_nodes, agg, dm);
+  else segnn_yagg_bwd_kernel<16><<<grid, 256, 0, as_stream(stream)>>>(dS, Dx, y, Dy, rowptr, n_nodes, agg, dm);
   EQNN_CHECK_LAUNCH();
   return EQNN_OK;
 }

@@ -58,6 +58,7 @@ __global__ void gate_fwd_rows_kernel(const float* __restrict__ z, int64_t n, Gat
   const int gate = c < d.n_extra ? 0 : d.n_extra + gate_index(d, j);
   const int64_t r0 = (int64_t)blockIdx.x * GATE_ROWS;
   const int64_t r1 = r0 + GATE_ROWS < n ? r0 + GATE_ROWS : n;
+#pragma unroll 4
   for (int64_t r = r0; r < r1; ++r) {
     const float* zr = z + r * d_in;
     const float x = zr[src];
@@ -88,6 +89,7 @@ __global__ void gate_bwd_rows_kernel(const float* __restrict__ z, const float* _
   }
   const int64_t r0 = (int64_t)blockIdx.x * GATE_ROWS;
   const int64_t r1 = r0 + GATE_ROWS < n ? r0 + GATE_ROWS : n;
+#pragma unroll 4
   for (int64_t r = r0; r < r1; ++r) {
     const float* zr = z + r * d_in;
     const float* gr = gout + r * d_out;
