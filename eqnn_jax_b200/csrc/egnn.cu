@@ -674,6 +674,37 @@ __global__ void segnn_edge0_bwd_kernel(const float* __restrict__ dz, const float
   dPs[i] = a;
 }
 
+// Dy = 4: warp per node, lanes along the outputs o; dz is read once per (edge, o) and the four attribute values of the
+// edge are one broadcast 16-byte load; the four columns of an output are written as one 16-byte store
+__global__ void __launch_bounds__(256) segnn_edge0_bwd4_kernel(const float* __restrict__ dz, const float* __restrict__ y,
+                                                               int Do, const int32_t* __restrict__ rowptr,
+                                                               const int32_t* __restrict__ rowptr_s,
+                                                               const int32_t* __restrict__ spos, int n_nodes,
+                                                               float* __restrict__ dPs, float* __restrict__ dPr) {
+  const int lane = threadIdx.x & 31;
+  const int64_t n = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (n >= n_nodes) return;
+  const int p0 = rowptr[n], p1 = rowptr[n + 1], q0 = rowptr_s[n], q1 = rowptr_s[n + 1];
+  const float4* y4 = reinterpret_cast<const float4*>(y);
+  for (int o = lane; o < Do; o += 32) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int p = p0; p < p1; ++p) {
+      const float d = __ldg(dz + (size_t)p * Do + o);
+      const float4 yy = __ldg(y4 + p);
+      a.x = fmaf(yy.x, d, a.x); a.y = fmaf(yy.y, d, a.y); a.z = fmaf(yy.z, d, a.z); a.w = fmaf(yy.w, d, a.w);
+    }
+    reinterpret_cast<float4*>(dPr + (size_t)n * Do * 4)[o] = a;
+    a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int q = q0; q < q1; ++q) {
+      const int p = spos[q];
+      const float d = __ldg(dz + (size_t)p * Do + o);
+      const float4 yy = __ldg(y4 + p);
+      a.x = fmaf(yy.x, d, a.x); a.y = fmaf(yy.y, d, a.y); a.z = fmaf(yy.z, d, a.z); a.w = fmaf(yy.w, d, a.w);
+    }
+    reinterpret_cast<float4*>(dPs + (size_t)n * Do * 4)[o] = a;
+  }
+}
+
 // gMa[a, o*Dy+j] = sum_p add[p, a] y[p, j] dz[p, o]  (n_add <= 8): per-CTA partials over edge ranges, then a fixed-order sum
 constexpr int EDGE0_PARTS = 148 * 16;      // short edge ranges: the per-thread loop is a dependent chain of loads
 __global__ void __launch_bounds__(1024) segnn_edge0_wadd_partial_kernel(const float* __restrict__ add, int n_add,
@@ -1096,8 +1127,12 @@ extern "C" int eqnn_segnn_edge0_bwd(const float* dz, const float* y, int Dy, int
                                     eqnn_stream_t stream) {
   EQNN_CHECK_ARG(dz && y && rowptr && rowptr_s && spos && dPs && dPr && Dy >= 1 && Do >= 1, "segnn_edge0_bwd: bad argument");
   if (n_nodes <= 0) return EQNN_OK;
-  segnn_edge0_bwd_kernel<<<(unsigned)ceil_div64((int64_t)n_nodes * Do * Dy, 256), 256, 0, as_stream(stream)>>>(
-      dz, y, Dy, Do, rowptr, rowptr_s, spos, n_nodes, dPs, dPr);
+  if (Dy == 4 && ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(dPs) | reinterpret_cast<uintptr_t>(dPr)) & 15) == 0)
+    segnn_edge0_bwd4_kernel<<<(unsigned)ceil_div64((int64_t)n_nodes * 32, 256), 256, 0, as_stream(stream)>>>(
+        dz, y, Do, rowptr, rowptr_s, spos, n_nodes, dPs, dPr);
+  else
+    segnn_edge0_bwd_kernel<<<(unsigned)ceil_div64((int64_t)n_nodes * Do * Dy, 256), 256, 0, as_stream(stream)>>>(
+        dz, y, Dy, Do, rowptr, rowptr_s, spos, n_nodes, dPs, dPr);
   EQNN_CHECK_LAUNCH();
   return EQNN_OK;
 }
