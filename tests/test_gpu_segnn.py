@@ -91,6 +91,9 @@ def _run(kw, irreps, x, k, lmax_attr, n_rb, pbc, vel, n_glob=0, lowering="dense"
     # concat(add, h_s, h_r) route runs
     (dict(d_hidden=32, n_layers=2, message_passing_steps=2, message_passing_agg="sum", task="node", output_irreps="1x1o",
           l_max_hidden=1, residual=True), "1o", 3, 1, 12, True, False, 0),
+    # attributes up to l = 3 (16 components): the widest attribute slot of the node-level edge-layer kernels
+    (dict(d_hidden=32, n_layers=2, message_passing_steps=1, message_passing_agg="mean", task="node", output_irreps="1x1o",
+          l_max_hidden=2, residual=True), "1o", 3, 3, 0, False, False, 0),
     # graph globals (TPCF vector) -> concat + LayerNorm before the read-out MLP (segnn.py:282-286)
     (dict(d_hidden=32, n_layers=2, message_passing_steps=1, message_passing_agg="mean", task="graph", output_irreps="1x0e",
           n_outputs=2), "1o", 3, 1, 0, False, False, 12),
