@@ -284,3 +284,47 @@ def test_segnn_dense_lowering_equals_oracle_tplg(lowering):
         np.testing.assert_allclose(z, want.numpy(), atol=1e-6 * max(1.0, np.abs(want.numpy()).max()))
         checked += 1
     assert checked == 5
+
+
+def test_segnn_node_level_edge_layer_identities():
+    """The algebra behind segnn._edge0_fwd / _edgeL_fwd on the host, from the plan's own tables: (1) the first edge layer
+    on concat(add, h_s, h_r) equals add @ M_a + (h @ M_s)[sender] + (h @ M_r)[receiver] contracted with y; (2) the last
+    edge layer followed by the receiver aggregation equals sum_j S_j @ M_j + b w(n) with S_j[n] = f sum_p y[p, j] m[p]."""
+    from eqnn_jax_b200.segnn import SEGNN, _Plan
+    from eqnn_jax_b200.irreps import Irreps
+    rng = np.random.default_rng(1)
+    kw = dict(d_hidden=16, l_max_hidden=1, n_layers=3, message_passing_steps=1, task="node", output_irreps="1o")
+    nadd, lat = 2, 1
+    plan = _Plan(SEGNN(**kw), Irreps("1o"), lat, nadd)
+    theta = rng.normal(size=(plan._n_params,))
+    tab = plan._np
+    wexp = np.where(tab["exp_idx"] >= 0, tab["exp_scale"].astype(np.float64) * theta[np.maximum(tab["exp_idx"], 0)], 0.0)
+    N, k = 7, 3
+    snd = rng.integers(0, N, size=(N * k,))
+    rcv = np.repeat(np.arange(N), k)
+    Dy = (lat + 1) ** 2
+    y = rng.normal(size=(N * k, Dy))
+    # (1) first edge layer
+    t = plan.steps[0]["edge"][0]
+    Dh = (t.Dx - nadd) // 2
+    h, add = rng.normal(size=(N, Dh)), rng.normal(size=(N * k, nadd))
+    M = wexp[t.M_off:t.M_off + t.Dx * t.Dy * t.Do].reshape(t.Dx, t.Do, t.Dy)
+    U = np.concatenate([add, h[snd], h[rcv]], axis=1)
+    want = np.einsum("ek,koj,ej->eo", U, M, y)
+    Ps, Pr = np.einsum("nk,koj->noj", h, M[nadd:nadd + Dh]), np.einsum("nk,koj->noj", h, M[nadd + Dh:])
+    got = np.einsum("eoj,ej->eo", np.einsum("ea,aoj->eoj", add, M[:nadd]) + Ps[snd] + Pr[rcv], y)
+    np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-12)
+    # (2) last edge layer + aggregation (sum and mean), bias on the 0e block
+    t = plan.steps[0]["edge"][-1]
+    assert not t.activation
+    M = wexp[t.M_off:t.M_off + t.Dx * t.Dy * t.Do].reshape(t.Dx, t.Do, t.Dy)
+    b = np.zeros(t.Do)
+    b[t.b_col:t.b_col + t.n_bias] = theta[t.b_off:t.b_off + t.n_bias]
+    m = rng.normal(size=(N * k, t.Dx))
+    z = np.einsum("ek,koj,ej->eo", m, M, y) + b
+    for mean in (False, True):
+        f = 1.0 / k if mean else 1.0
+        want = f * np.add.reduceat(z, np.arange(0, N * k, k), axis=0)
+        S = f * np.add.reduceat(y[:, :, None] * m[:, None, :], np.arange(0, N * k, k), axis=0)      # [n, j, k]
+        got = np.einsum("njk,koj->no", S, M) + b * (f * k)
+        np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-12)
