@@ -14,7 +14,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libeqnn_b200.so")
-SOURCES = ["knn.cu", "csr.cu", "tpconv.cu", "gemm.cu", "elementwise.cu", "tc_mlp.cu", "tc_gemm.cu", "node.cu", "egnn.cu"]
+SOURCES = ["knn.cu", "csr.cu", "tpconv.cu", "gemm.cu", "elementwise.cu", "tc_mlp.cu", "rmlp.cu", "tc_gemm.cu", "node.cu", "egnn.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
@@ -39,7 +39,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     gen = os.path.join(CSRC, "gen", "tp_gen.cuh")
     codegen.generate(gen)
     headers = [os.path.join(CSRC, "common.cuh"), gen, os.path.join(HERE, "..", "include", "eqnn_b200.h"),
-               os.path.join(CSRC, "tc_common.cuh")]
+               os.path.join(CSRC, "tc_common.cuh"), os.path.join(CSRC, "rmlp_common.cuh")]
     objdir = os.path.join(CSRC, "build")
     os.makedirs(objdir, exist_ok=True)
     nvcc = _nvcc()

@@ -121,6 +121,7 @@ __global__ void geom_kernel(const float* __restrict__ pos, int ld, int n_nodes, 
     geom[p] = make_float4(__fdiv_rn(rx, dn), __fdiv_rn(ry, dn), __fdiv_rn(rz, dn), d);
     if (radial && n_rb == 0) radial[p] = d;
   }
+  __syncwarp();   // the Bessel loop reads geom[p].w written by other lanes of this warp
   if (radial && n_rb > 0) {
     // e3nn.bessel: sqrt(2/c) * sin(j*pi/c * x)/x with the fp32 rounding points of the reference.  Lanes own
     // basis indices j (coalesced stores of each edge's n_rb values); edge lengths are re-read (L1 hits).

@@ -4,7 +4,46 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 namespace tc {
+
+// ---- host side: per-device launch configuration ------------------------------------------
+// cudaFuncAttributeMaxDynamicSharedMemorySize belongs to the (function, device) pair, and one process may drive
+// several devices from several host threads (jax.pmap: one thread per device).  Every kernel instantiation owns one
+// DeviceOnce: the attribute is set the first time the instantiation is launched on a device; concurrent first
+// launches may both set it (idempotent), later launches cost one relaxed atomic load.
+constexpr int kMaxDevices = 64;
+struct DeviceOnce {
+  std::atomic<unsigned char> done[kMaxDevices];
+};
+template <typename Kernel>
+inline cudaError_t configure_smem(DeviceOnce& once, Kernel kern, int smem_bytes, int* device_out = nullptr) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (device_out) *device_out = dev;
+  if (dev < 0 || dev >= kMaxDevices || !once.done[dev].load(std::memory_order_acquire)) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < kMaxDevices) once.done[dev].store(1, std::memory_order_release);
+  }
+  return cudaSuccess;
+}
+// SM count of the current device, cached per device (cudaDeviceGetAttribute is a driver round trip)
+inline int sm_count() {
+  static std::atomic<int> cache[kMaxDevices];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev >= 0 && dev < kMaxDevices) {
+    const int c = cache[dev].load(std::memory_order_relaxed);
+    if (c > 0) return c;
+  }
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (dev >= 0 && dev < kMaxDevices) cache[dev].store(sms, std::memory_order_relaxed);
+  return sms;
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

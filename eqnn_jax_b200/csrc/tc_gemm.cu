@@ -396,11 +396,8 @@ bool gt_shape_ok(int64_t M, int64_t N, int64_t K) {
 template <int BN>
 int launch_tc_gemm(const TcGemmP& p, cudaStream_t st) {
   auto kern = tc_gemm_kernel<BN>;
-  static bool configured = false;
-  if (!configured) {
-    EQNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GtCfg<BN>::SMEM));
-    configured = true;
-  }
+  static tc::DeviceOnce once;   // one per kernel instantiation; the attribute is per device
+  EQNN_CUDA(tc::configure_smem(once, kern, (int)GtCfg<BN>::SMEM));
   dim3 grid((unsigned)((p.N + BN - 1) / BN), (unsigned)((p.M + GT_M - 1) / GT_M), (unsigned)p.ksplit);
   kern<<<grid, GT_THREADS, GtCfg<BN>::SMEM, st>>>(p);
   if (p.ksplit > 1) tc_gemm_reduce_kernel<<<(unsigned)ceil_div64(p.M * p.N, 256), 256, 0, st>>>(p);

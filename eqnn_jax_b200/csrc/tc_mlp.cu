@@ -365,14 +365,9 @@ template <int K, int N, int AMODE, int PRO, int EPI, int CMODE>
 int launch_rowgemm(const RowGemmP& p, cudaStream_t st) {
   using Cfg = RowCfg<K, N, AMODE == 0>;
   auto kern = tc_rowgemm_kernel<K, N, AMODE, PRO, EPI, CMODE>;
-  static bool configured = false;   // attribute is per function; setting it again is harmless
-  if (!configured) {
-    EQNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-    configured = true;
-  }
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  static DeviceOnce once;           // one per kernel instantiation; the attribute is per device
+  EQNN_CUDA(configure_smem(once, kern, (int)Cfg::SMEM));
+  const int sms = sm_count();
   const int64_t n_tiles = (p.M + TILE_M - 1) / TILE_M;
   const unsigned grid = (unsigned)(n_tiles < sms ? n_tiles : sms);
   kern<<<grid, RG_THREADS, Cfg::SMEM, st>>>(p);
@@ -714,11 +709,8 @@ template <int MI, int N, int GMODE, int PRO>
 int launch_wgrad(const WgradP& p, int grid, cudaStream_t st) {
   constexpr uint32_t SMEM = WgradCfg<MI, N, GMODE>::SMEM;
   auto kern = tc_wgrad_kernel<MI, N, GMODE, PRO>;
-  static bool configured = false;
-  if (!configured) {
-    EQNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-    configured = true;
-  }
+  static DeviceOnce once;
+  EQNN_CUDA(configure_smem(once, kern, (int)SMEM));
   kern<<<grid, WG_THREADS, SMEM, st>>>(p);
   EQNN_CHECK_LAUNCH();
   return EQNN_OK;
@@ -728,9 +720,7 @@ int launch_wgrad(const WgradP& p, int grid, cudaStream_t st) {
 
 size_t eqnn_tc_wgrad_workspace_bytes(int64_t M, int64_t N, int64_t K) {
   if (K < 4096 || M > 128 || N > 128) return 0;
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = sm_count();
   return (size_t)sms * (128 * 128 + 128) * sizeof(float);      // weight partials + column-sum partials
 }
 
@@ -744,9 +734,7 @@ int eqnn_tc_wgrad_try(int64_t M, int64_t N, int64_t K, float alpha, const float*
   if (colsum_out && !(N == 128 && sbn == 1)) return 0;
   if (!(M == 32 || M == 64 || M == 128) || sam != 1 || sak % 4 != 0 || (reinterpret_cast<uintptr_t>(A) & 15)) return 0;
   if (reinterpret_cast<uintptr_t>(B) & 15) return 0;
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = sm_count();
   const int64_t n_chunks = (K + 31) / 32;
   const int grid = (int)(n_chunks < sms ? n_chunks : sms);
   WgradP p;

@@ -224,6 +224,30 @@ def gemm(M, N, K, alpha, A, sam, sak, B, sbk, sbn, Cm, scm, scn, accumulate=Fals
         TIMER.end(tag, t0)
 
 
+def radial_mlp_supported(n_rb: int, d_hidden: int, n_hidden: int, n_out: int) -> bool:
+    return bool(lib().eqnn_radial_mlp_supported(n_rb, d_hidden, n_hidden, n_out))
+
+
+def _weight_ptrs(weights):
+    """[(tensor, element offset, leading dimension)] -> host arrays of device pointers / leading dimensions."""
+    n = len(weights)
+    ptrs = (C.c_void_p * n)(*[t.data_ptr() + 4 * off for t, off, _ in weights])
+    lds = (C.c_int64 * n)(*[ld for _, _, ld in weights])
+    return ptrs, lds
+
+
+def radial_mlp_fwd(geom, n_rb, r_cut, weights, n_out, act_scale, w_t):
+    """geom [E, 4] (r_hat, d) -> w_t [n_out, E]; weights = [(tensor, offset, ld)] for the hidden layers + the output layer."""
+    E = geom.shape[0]
+    ptrs, lds = _weight_ptrs(weights)
+    t0 = TIMER.begin() if TIMER else None
+    check(lib().eqnn_radial_mlp_fwd(C.c_void_p(geom.data_ptr() + 12), 4, E, n_rb, float(r_cut), len(weights) - 1, 128,
+                                    ptrs, lds, n_out, float(act_scale), _ptr(w_t), w_t.shape[1], _stream()),
+          "radial_mlp_fwd")
+    if TIMER:
+        TIMER.end("radial_mlp_fwd", t0)
+
+
 def _int_arr(v: Sequence[int]):
     return (C.c_int * max(len(v), 1))(*v)
 

@@ -351,6 +351,23 @@ int eqnn_dense_wgrad_f32(int64_t M, int64_t N, int64_t K, float alpha, const flo
 size_t eqnn_colsum_workspace_bytes(int N);
 int eqnn_colsum_tall(const float* x, int64_t M, int N, float* y, void* ws, size_t ws_bytes, eqnn_stream_t stream);
 
+/* ---- fused radial MLP (models/nequip.py:55-68: e3nn.bessel -> e3nn.flax.MultiLayerPerceptron) -------------
+ * w_t[c, e] = ( act(...act(bessel(d_e) @ W_0 / sqrt(n_rb)) ... @ W_{n_hidden-1} / sqrt(128)) @ W_out / sqrt(128) )[c]
+ * with act(x) = gelu_tanh(x) * act_scale (e3nn.normalize_function).  ONE kernel from the edge length to the radial
+ * weights: the Bessel basis is evaluated in-kernel (fp32 rounding points of the reference: phase fl(fl(j*pi/r_cut)*d)),
+ * every weight matrix is resident in shared memory, activations stay in tensor memory between layers (tcgen05.mma with
+ * the A operand in TMEM); per edge the kernel reads d (4 bytes) and writes n_out floats.  Arithmetic: operands split
+ * into fp16 (hi, lo) pairs, three tensor-core products each, fp32 accumulation (error ~2^-21, like EQNN_GEMM_TF32X3).
+ *   dist[e * dist_stride]  edge length (e.g. geom + 3 with stride 4)
+ *   weights  HOST array of n_hidden + 1 device pointers; weights[l][k * ldw[l] + n]; ldw HOST array
+ *   the last matrix has n_out <= 16 columns (the live message columns, SH normalisation folded in)
+ *   w_t [n_out][ld_wt] column-major (the layout eqnn_tpconv_fwd reads)
+ * eqnn_radial_mlp_supported: 1 if the shape is covered (n_rb in {16,32,64}, d_hidden = 128, 1 <= n_hidden <= 3). */
+int eqnn_radial_mlp_supported(int n_rb, int d_hidden, int n_hidden, int n_out);
+int eqnn_radial_mlp_fwd(const float* dist, int64_t dist_stride, int64_t n_edges, int n_rb, double r_cut, int n_hidden,
+                        int d_hidden, const float* const* weights, const int64_t* ldw, int n_out, float act_scale,
+                        float* w_t, int64_t ld_wt, eqnn_stream_t stream);
+
 /* ---- parameter plumbing ----------------------------------------------------------------
  * dst[t] = idx[t] < 0 ? 0 : scale[t] * params[idx[t]]     (Linear -> dense matrix, live columns)
  * grads[pidx[j]] = sum_{t in [ptr[j], ptr[j+1])} scale_t[t] * ddst[tidx[t]]               */
