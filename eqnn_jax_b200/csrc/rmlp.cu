@@ -55,12 +55,19 @@ __host__ inline uint32_t rm_smem_bytes(const RmlpP& p) {
   return b + 1024 /*align*/ + 256 /*bessel frequencies*/ + 64 /*barriers*/;
 }
 
-// alpha * acc -> gelu * act_scale -> (hi, lo) words, 32 accumulator columns of one row
-__device__ __forceinline__ void act_split32(const float* v, float alpha, float act_scale, uint32_t* hiw, uint32_t* low) {
-  const f32x2 al2 = pk2(alpha, alpha), sc2 = pk2(act_scale, act_scale);
+// The scalar factors of the MLP are folded into the weight images: image l holds W_l * alpha_l (* act_scale for
+// l >= 1, the factor of the activation that feeds it), so an accumulator IS the pre-activation z_l and the operand
+// written back is the bare gelu_tanh(z_l).
+__host__ __device__ inline float rm_wscale(const float* alpha, float act_scale, int l) {
+  return l == 0 ? alpha[0] : alpha[l] * act_scale;
+}
+
+// z -> gelu_tanh(z) -> (hi, lo) words, 32 accumulator columns of one row
+__device__ __forceinline__ void act_split32(const float* v, uint32_t* hiw, uint32_t* low) {
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
-    const f32x2 a = gelu2(mul2(pk2(v[2 * j], v[2 * j + 1]), al2), sc2);
+    const f32x2 x = pk2(v[2 * j], v[2 * j + 1]);
+    const f32x2 a = mul2(x, gelu_sigmoid2(x, mul2(x, x)));
     float a0, a1;
     upk2(a, a0, a1);
     split_h2(a0, a1, hiw[j], low[j]);
@@ -103,7 +110,7 @@ __global__ void __launch_bounds__(RM_THREADS, 1) rmlp_fwd_kernel(const RmlpP p) 
   if (warp == RM_MMA_WARP) tmem_alloc(tmem_slot, 512);
   for (int l = 0; l < F; ++l)
     fill_weight_image(gen + w_off[l], gen + w_off[l] + w_half[l], p.W[l], p.ldw[l], rm_K(p, l), rm_N(p, l),
-                      l == F - 1 ? p.n_out : 128, 1.0f, tid, RM_THREADS);
+                      l == F - 1 ? p.n_out : 128, rm_wscale(p.alpha, p.act_scale, l), tid, RM_THREADS);
   if (tid < p.n_rb) wfreq[tid] = __fdiv_rn(__fmul_rn((float)(tid + 1), 3.14159265358979323846f), p.r_cut);
   fence_proxy_async_smem();
   tc_fence_before();
@@ -163,7 +170,7 @@ __global__ void __launch_bounds__(RM_THREADS, 1) rmlp_fwd_kernel(const RmlpP p) 
           tmem_ld32(t, v);
           tmem_ld_wait();
           uint32_t hiw[16], low[16];
-          act_split32(v, p.alpha[l - 1], p.act_scale, hiw, low);
+          act_split32(v, hiw, low);
           tmem_st16(t, hiw);
           tmem_st16(t + 16, low);
           tmem_st_wait();
@@ -185,7 +192,7 @@ __global__ void __launch_bounds__(RM_THREADS, 1) rmlp_fwd_kernel(const RmlpP p) 
           if (e < p.E) {
 #pragma unroll
             for (int c = 0; c < 16; ++c)
-              if (c < p.n_out) p.w_t[(int64_t)c * p.ld_wt + e] = p.alpha[F - 1] * v[c];
+              if (c < p.n_out) p.w_t[(int64_t)c * p.ld_wt + e] = v[c];
           }
         }
       }
@@ -215,6 +222,333 @@ __global__ void __launch_bounds__(RM_THREADS, 1) rmlp_fwd_kernel(const RmlpP p) 
           }
           mma_commit(acc_full(x));
         }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == RM_MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// Backward chain: per 128-edge tile, recompute the forward activations from d, then run the data-gradient chain
+//   g_H = (dw @ W_out^T) * gelu'(z_H);  g_{l-1} = (g_l @ W_l^T) * gelu'(z_{l-1})        (weight images already carry
+// the alpha / act_scale factors, which are linear and therefore the same in both directions), everything in tensor
+// memory.  The kernel emits what the weight gradients need: the basis a_0, the activations gelu(z_l) and the
+// gradients g_l = dL/dz_l (fp32, row-major).  One tile is in flight: it owns all four 128-column regions --
+// two for the ping-pong chain (accumulator / operand in place, as in the forward kernel) and two that stash
+// gelu'(z_1), gelu'(z_2) from the recompute phase (the sigmoid is evaluated once per pre-activation).
+// Gradients are brought into fp16 range by one power-of-two scale per launch (from max |dw|): only sums over edges
+// are ever formed from them, so what matters is the error relative to the LARGEST rows, which keeps 22 bits.
+// ------------------------------------------------------------------------------------------------------------------
+struct RmlpBwdP {
+  RmlpP f;                   // forward description (f.w_t unused)
+  const float* dw;           // dL/dw_t, [n_out][ld_dw] column-major
+  int64_t ld_dw;
+  const uint32_t* absmax;    // bit pattern of max |dw| (absmax_kernel)
+  float* act[RM_MAXL];       // act[0] = bessel basis [E][n_rb]; act[l] = gelu(z_l) [E][128], l = 1..H
+  float* grad[RM_MAXL];      // grad[l] = dL/dz_l [E][128], l = 1..H
+  // 1: emit in the blocked chunk layout of tc_mlp.cu's weight-gradient kernel -- per 32-edge chunk
+  // [16-byte column group][row][4 floats]: a warp (one row per lane) writes 512 contiguous bytes per store;
+  // 0: plain row-major (small problems that take the CUDA-core GEMM)
+  // blk[l] is the layout of the two operands of layer l's weight gradient, act[l] and grad[l + 1]
+  int blk[RM_MAXL];
+};
+
+constexpr uint32_t RM_GSLAB = 128 * 128;   // dw operand: 128 rows x 128 B (16 halves used), K-major, 128B swizzle
+
+__global__ void absmax_kernel(const float* __restrict__ x, int64_t ld, int rows, int64_t cols, uint32_t* __restrict__ out) {
+  uint32_t m = 0;
+  for (int r = 0; r < rows; ++r)
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cols; i += (int64_t)gridDim.x * blockDim.x) {
+      const uint32_t b = __float_as_uint(__ldg(x + (int64_t)r * ld + i)) & 0x7fffffffu;
+      m = b > m ? b : m;
+    }
+  m = __reduce_max_sync(0xffffffffu, m);
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
+// x pair -> gelu_tanh(x), gelu_tanh'(x) from one sigmoid
+__device__ __forceinline__ void gelu_both2(f32x2 x, f32x2& g, f32x2& gp) {
+  constexpr float D0 = 2.0f * 0.7978845608028654f, D1 = D0 * 3.0f * 0.044715f;
+  const f32x2 xx = mul2(x, x);
+  const f32x2 sg = gelu_sigmoid2(x, xx);
+  g = mul2(x, sg);
+  const f32x2 w = mul2(x, fma2(xx, pk2(D1, D1), pk2(D0, D0)));
+  const f32x2 q = mul2(sg, fma2(sg, pk2(-1.f, -1.f), pk2(1.f, 1.f)));
+  gp = fma2(q, w, sg);
+}
+
+// NV values of row e, columns [c0, c0 + NV) of a [E][ncols] matrix
+template <int NV>
+__device__ __forceinline__ void emit_cols(float* basep, int blocked, int64_t e, int ncols, int c0, const float* v) {
+  if (blocked) {
+    float* dst = basep + (e >> 5) * (int64_t)(32 * ncols) + (int64_t)(c0 >> 2) * 128 + (e & 31) * 4;
+#pragma unroll
+    for (int i = 0; i < NV / 4; ++i)
+      *reinterpret_cast<float4*>(dst + i * 128) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  } else {
+    float* dst = basep + e * ncols + c0;
+#pragma unroll
+    for (int i = 0; i < NV / 4; ++i)
+      *reinterpret_cast<float4*>(dst + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  }
+}
+
+__global__ void __launch_bounds__(RM_THREADS, 1) rmlp_bwd_kernel(const RmlpBwdP p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const RmlpP& f = p.f;
+  const int F = f.n_layers, H = F - 1;
+
+  // shared-memory map: weight images | dw operand slabs (hi, lo) | bessel frequencies | barriers
+  uint32_t w_off[RM_MAXL], w_half[RM_MAXL];
+  uint32_t off = 0;
+#pragma unroll
+  for (int l = 0; l < RM_MAXL; ++l) {
+    if (l < F) {
+      w_off[l] = off;
+      w_half[l] = w_half_bytes(rm_K(f, l), rm_N(f, l));
+      off += 2 * w_half[l];
+    } else {
+      w_off[l] = w_half[l] = 0;
+    }
+  }
+  const uint32_t gslab = off;
+  off += 2 * RM_GSLAB;
+  float* wfreq = reinterpret_cast<float*>(gen + off);
+  const uint32_t bars = base + off + 256;
+  const uint32_t opnd_full = bars, acc_full = bars + 8, mma_done = bars + 16, tmem_slot = bars + 24;
+
+  if (tid == 0) {
+    mbar_init(opnd_full, RM_CT);
+    mbar_init(acc_full, 1);
+    mbar_init(mma_done, 1);
+    mbar_fence_init();
+  }
+  if (warp == RM_MMA_WARP) tmem_alloc(tmem_slot, 512);
+  for (int l = 0; l < F; ++l)
+    fill_weight_image(gen + w_off[l], gen + w_off[l] + w_half[l], f.W[l], f.ldw[l], rm_K(f, l), rm_N(f, l),
+                      l == F - 1 ? f.n_out : 128, rm_wscale(f.alpha, f.act_scale, l), tid, RM_THREADS);
+  for (uint32_t o = tid * 16; o < 2 * RM_GSLAB; o += RM_THREADS * 16)
+    *reinterpret_cast<float4*>(gen + gslab + o) = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (tid < f.n_rb) wfreq[tid] = __fdiv_rn(__fmul_rn((float)(tid + 1), 3.14159265358979323846f), f.r_cut);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
+
+  const int64_t n_tiles = (f.E + RM_TILE - 1) / RM_TILE;
+  auto region = [&](int r) { return tmem_base + (uint32_t)((r & 1) * 128); };     // chain ping-pong
+  auto stash = [&](int l) { return tmem_base + 256u + (uint32_t)((l - 1) * 128); };   // gelu'(z_l), l = 1, 2
+
+  // gradient scale: max |dw| * S in [4, 8)
+  const uint32_t mbits = __ldg(p.absmax);
+  const int mexp = (int)((mbits >> 23) & 0xffu);
+  int sexp = 127 + 2 - (mexp - 127);
+  sexp = sexp < 1 ? 1 : (sexp > 254 ? 254 : sexp);
+  const float gS0 = (mexp == 0) ? 1.f : __uint_as_float((uint32_t)sexp << 23);
+  const float gSinv0 = (mexp == 0) ? 1.f : __uint_as_float((uint32_t)(254 - sexp) << 23);
+
+  if (warp < RM_CW) {
+    // =========================== compute warps ===========================
+    const int q = warp & 3, cg = warp >> 2;
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    const int row = q * 32 + lane;
+    uint32_t n_acc = 0;
+    auto wait_acc = [&]() {
+      mbar_wait(acc_full, n_acc & 1u);
+      ++n_acc;
+      tc_fence_after();
+    };
+    auto publish = [&]() {
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(opnd_full);
+    };
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int64_t e = tile * RM_TILE + row;
+      const bool live = e < f.E;
+      // The tensor core's fp32 accumulation truncates: every accumulator carries a small bias of one sign, which the
+      // weight-gradient sums over millions of edges would add up coherently (measured: error growing with the edge
+      // count).  Odd tiles therefore run the whole (linear) gradient chain on -g and flip the sign back when they
+      // emit: the bias changes sign with the tile parity and cancels in the sums.
+      const float gS = (tile & 1) ? -gS0 : gS0, gSinv = (tile & 1) ? -gSinv0 : gSinv0;
+      // ---- c0: Bessel basis -> operand of layer 1 (k-step s of the basis sits at column 32 s of region 1) ----
+      if (16 * cg < f.n_rb) {
+        const float d = live ? __ldg(f.dist + e * f.dist_stride) : 0.f;
+        const float inv_d = (d == 0.f) ? 0.f : __fdiv_rn(1.0f, d);
+        uint32_t hiw[8], low[8];
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float w = wfreq[16 * cg + j];
+          const float sn = sin_reduced(__fmul_rn(w, d)) * inv_d;
+          v[j] = __fmul_rn(f.pref, (d == 0.f) ? w : sn);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) split_h2(v[2 * j], v[2 * j + 1], hiw[j], low[j]);
+        const uint32_t t = region(1) + lane_sel + (uint32_t)(32 * cg);
+        tmem_st8(t, hiw);
+        tmem_st8(t + 16, low);
+        if (live) emit_cols<16>(p.act[0], p.blk[0], e, f.n_rb, 16 * cg, v);
+      }
+      if (cg == 0) {
+        // dw row (scaled) -> K-major operand slab: 16 halves = chunks 0, 1 of this row's 128-byte line
+        float g[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) g[c] = (live && c < f.n_out) ? gS * __ldg(p.dw + (int64_t)c * p.ld_dw + e) : 0.f;
+        uint32_t hiw[8], low[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) split_h2(g[2 * j], g[2 * j + 1], hiw[j], low[j]);
+        uint8_t* sl = gen + gslab;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const uint32_t o = sw128((uint32_t)row, (uint32_t)c);
+          *reinterpret_cast<uint4*>(sl + o) = make_uint4(hiw[4 * c], hiw[4 * c + 1], hiw[4 * c + 2], hiw[4 * c + 3]);
+          *reinterpret_cast<uint4*>(sl + RM_GSLAB + o) = make_uint4(low[4 * c], low[4 * c + 1], low[4 * c + 2], low[4 * c + 3]);
+        }
+        fence_proxy_async_smem();
+      }
+      publish();
+      // ---- recompute: z_l -> gelu (operand, in place) and gelu' (stash); the last hidden layer meets the gradient ----
+      for (int l = 1; l <= H; ++l) {
+        wait_acc();
+        const uint32_t tz = region(l - 1) + lane_sel + (uint32_t)(32 * cg);
+        float z[32], a[32], gp[32];
+        tmem_ld32(tz, z);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          f32x2 g2, gp2;
+          gelu_both2(pk2(z[2 * j], z[2 * j + 1]), g2, gp2);
+          upk2(g2, a[2 * j], a[2 * j + 1]);
+          upk2(gp2, gp[2 * j], gp[2 * j + 1]);
+        }
+        if (live) emit_cols<32>(p.act[l], p.blk[l], e, 128, 32 * cg, a);
+        if (l < H) {
+          uint32_t hiw[16], low[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) split_h2(a[2 * j], a[2 * j + 1], hiw[j], low[j]);
+          tmem_st16(tz, hiw);
+          tmem_st16(tz + 16, low);
+          tmem_st32(stash(l) + lane_sel + (uint32_t)(32 * cg), reinterpret_cast<const uint32_t*>(gp));
+          publish();
+        } else {
+          // g_H = (dw @ W_out^T) * gelu'(z_H): the product sits in the other region
+          const uint32_t tg = region(l) + lane_sel + (uint32_t)(32 * cg);
+          float pre[32];
+          tmem_ld32(tg, pre);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) pre[j] *= gp[j];
+          if (H >= 2) {
+            uint32_t hiw[16], low[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) split_h2(pre[2 * j], pre[2 * j + 1], hiw[j], low[j]);
+            tmem_st16(tg, hiw);
+            tmem_st16(tg + 16, low);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) pre[j] *= gSinv;
+          if (live) emit_cols<32>(p.grad[l], p.blk[l - 1], e, 128, 32 * cg, pre);
+          if (H >= 2) publish();
+        }
+      }
+      // ---- data-gradient chain: g_l = (g_{l+1} @ W_{l+1}^T) * gelu'(z_l), l = H-1 .. 1 ----
+      for (int l = H - 1; l >= 1; --l) {
+        wait_acc();
+        // g_H sits in region(H); every product lands in the other region: g_l in region(H + (H - l))
+        const uint32_t tg = region(2 * H - l) + lane_sel + (uint32_t)(32 * cg);
+        float pre[32], gp[32];
+        tmem_ld32(tg, pre);
+        tmem_ld32(stash(l) + lane_sel + (uint32_t)(32 * cg), gp);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) pre[j] *= gp[j];
+        if (l >= 2) {
+          uint32_t hiw[16], low[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) split_h2(pre[2 * j], pre[2 * j + 1], hiw[j], low[j]);
+          tmem_st16(tg, hiw);
+          tmem_st16(tg + 16, low);
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) pre[j] *= gSinv;
+        if (live) emit_cols<32>(p.grad[l], p.blk[l - 1], e, 128, 32 * cg, pre);
+        if (l >= 2) publish();
+      }
+    }
+  } else if (lane == 0) {
+    // =========================== MMA issuer ===========================
+    uint32_t n_op = 0, n_done = 0;
+    auto wait_opnd = [&]() {
+      mbar_wait(opnd_full, n_op & 1u);
+      ++n_op;
+      tc_fence_after();
+    };
+    // forward layer l (1-based): D = region(l-1), A = region(l) [basis: k-step s at column 32 s], B = image l-1 (K-major)
+    auto issue_fwd = [&](int l) {
+      const int K = rm_K(f, l - 1);
+      const uint32_t idesc = make_idesc_f16(128, 128, 0, 0);
+      const uint32_t b_hi = base + w_off[l - 1], b_lo = b_hi + w_half[l - 1];
+      const uint32_t d_tmem = region(l - 1), a_reg = region(l);
+      for (int s = 0; s < K / 16; ++s) {
+        const uint32_t a_hi = a_reg + (l == 1 ? (uint32_t)(32 * s) : (uint32_t)(32 * (s >> 1) + 8 * (s & 1))), a_lo = a_hi + 16;
+        const uint32_t boff = (uint32_t)(s >> 2) * 128u * 128u + (uint32_t)(s & 3) * 32u;
+        const uint64_t dbh = make_desc(b_hi + boff, 16, 1024), dbl = make_desc(b_lo + boff, 16, 1024);
+        mma_f16_ts(d_tmem, a_hi, dbh, idesc, s ? 1u : 0u);
+        mma_f16_ts(d_tmem, a_lo, dbh, idesc, 1u);
+        mma_f16_ts(d_tmem, a_hi, dbl, idesc, 1u);
+      }
+    };
+    // data gradient through layer l (1-based, 2 <= l <= H): D (N = 128 inputs k) = A (g_l, K = 128 outputs n) x image l-1
+    // read MN-major: k-step s = rows n = 16 s .. 16 s + 15 of both 64-k slabs (LBO = slab stride, SBO = 8 rows)
+    auto issue_dgrad = [&](int l, uint32_t a_reg, uint32_t d_tmem) {
+      const uint32_t idesc = make_idesc_f16(128, 128, 0, 1);
+      const uint32_t b_hi = base + w_off[l - 1], b_lo = b_hi + w_half[l - 1];
+      for (int s = 0; s < 8; ++s) {
+        const uint32_t a_hi = a_reg + (uint32_t)(32 * (s >> 1) + 8 * (s & 1)), a_lo = a_hi + 16;
+        const uint64_t dbh = make_desc(b_hi + s * 2048u, 128u * 128u, 1024), dbl = make_desc(b_lo + s * 2048u, 128u * 128u, 1024);
+        mma_f16_ts(d_tmem, a_hi, dbh, idesc, s ? 1u : 0u);
+        mma_f16_ts(d_tmem, a_lo, dbh, idesc, 1u);
+        mma_f16_ts(d_tmem, a_hi, dbl, idesc, 1u);
+      }
+    };
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int l = 1; l <= H; ++l) {
+        wait_opnd();
+        issue_fwd(l);
+        if (l < H) {
+          mma_commit(acc_full);
+        } else {
+          // the output layer's data gradient overwrites region(H), which layer H is still reading: wait for it
+          mma_commit(mma_done);
+          mbar_wait(mma_done, n_done & 1u);
+          ++n_done;
+          tc_fence_after();
+          const uint32_t idesc = make_idesc_f16(128, 128, 0, 1);
+          const uint32_t g_hi = base + gslab, g_lo = g_hi + RM_GSLAB;
+          const uint32_t b_hi = base + w_off[F - 1], b_lo = b_hi + w_half[F - 1];
+          const uint64_t dah = make_desc(g_hi, 16, 1024), dal = make_desc(g_lo, 16, 1024);
+          const uint64_t dbh = make_desc(b_hi, 16u * 128u, 1024), dbl = make_desc(b_lo, 16u * 128u, 1024);
+          mma_f16_ss(region(H), dah, dbh, idesc, 0u);
+          mma_f16_ss(region(H), dal, dbh, idesc, 1u);
+          mma_f16_ss(region(H), dah, dbl, idesc, 1u);
+          mma_commit(acc_full);
+        }
+      }
+      for (int l = H; l >= 2; --l) {
+        wait_opnd();
+        issue_dgrad(l, region(2 * H - l), region(2 * H - l + 1));
+        mma_commit(acc_full);
       }
     }
   }
@@ -265,5 +599,117 @@ extern "C" int eqnn_radial_mlp_fwd(const float* dist, int64_t dist_stride, int64
   const unsigned grid = (unsigned)(n_tiles < sms ? n_tiles : sms);
   rmlp_fwd_kernel<<<grid, RM_THREADS, smem, as_stream(stream)>>>(p);
   EQNN_CHECK_LAUNCH();
+  return EQNN_OK;
+}
+
+int eqnn_tc_wgrad_try(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t sam, int64_t sak,
+                      const float* B, int64_t sbk, int64_t sbn, float* C, int64_t scm, int64_t scn, int accumulate,
+                      int pro, float pro_scale, int epi, void* ws, size_t ws_bytes, cudaStream_t st,
+                      float* colsum_out, int blocked);
+
+// workspace: [absmax 256 B | bessel basis E*n_rb | n_hidden x gelu(z_l) E*128 | n_hidden x g_l E*128 | GEMM workspace]
+static size_t rm_bwd_gemm_ws(int64_t n_edges) {
+  size_t a = eqnn_gemm_workspace_bytes(128, 128, n_edges), b = eqnn_gemm_workspace_bytes(64, 128, n_edges);
+  size_t c = eqnn_gemm_workspace_bytes(128, 16, n_edges);
+  a = a > b ? a : b;
+  return a > c ? a : c;
+}
+extern "C" size_t eqnn_radial_mlp_bwd_workspace_bytes(int64_t n_edges, int n_rb, int n_hidden) {
+  const size_t ep = align_up((size_t)n_edges, 128);   // whole 32-edge chunks (blocked layout)
+  return 256 + ep * n_rb * 4 + 2 * (size_t)n_hidden * ep * 512 + align_up(rm_bwd_gemm_ws(n_edges), 256);
+}
+
+extern "C" int eqnn_radial_mlp_bwd(const float* dist, int64_t dist_stride, int64_t n_edges, int n_rb, double r_cut,
+                                   int n_hidden, int d_hidden, const float* const* weights, const int64_t* ldw,
+                                   int n_out, float act_scale, const float* dw_t, int64_t ld_dwt,
+                                   float* const* grad_weights, void* ws, size_t ws_bytes, eqnn_stream_t stream) {
+  EQNN_CHECK_ARG(dist && weights && ldw && dw_t && grad_weights && n_edges >= 0 && dist_stride >= 1, "radial_mlp_bwd: bad argument");
+  EQNN_CHECK_ARG(eqnn_radial_mlp_supported(n_rb, d_hidden, n_hidden, n_out), "radial_mlp_bwd: unsupported shape");
+  EQNN_CHECK_ARG(r_cut > 0.0 && ld_dwt >= n_edges, "radial_mlp_bwd: bad r_cut / ld_dwt");
+  EQNN_CHECK_ARG(sqrt(2.0 / r_cut) * n_rb * 3.14159265358979323846 / r_cut < 60000.0, "radial_mlp_bwd: r_cut too small for the fp16 operand split");
+  if (ws_bytes < eqnn_radial_mlp_bwd_workspace_bytes(n_edges, n_rb, n_hidden) || !ws) return eqnn_fail(EQNN_ERR_WORKSPACE, "radial_mlp_bwd: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  const int F = n_hidden + 1;
+  RmlpBwdP p;
+  RmlpP& f = p.f;
+  f.dist = dist; f.dist_stride = dist_stride; f.E = n_edges;
+  f.r_cut = (float)r_cut; f.pref = (float)sqrt(2.0 / r_cut);
+  f.n_rb = n_rb; f.n_layers = F; f.n_out = n_out;
+  for (int l = 0; l < RM_MAXL; ++l) {
+    f.W[l] = nullptr; f.ldw[l] = 0; f.alpha[l] = 0.f;
+    p.act[l] = nullptr; p.grad[l] = nullptr;
+  }
+  for (int l = 0; l < F; ++l) {
+    EQNN_CHECK_ARG(weights[l] != nullptr && grad_weights[l] != nullptr, "radial_mlp_bwd: null weight");
+    f.W[l] = weights[l]; f.ldw[l] = ldw[l];
+    f.alpha[l] = (float)(1.0 / sqrt((double)rm_K(f, l)));
+  }
+  f.act_scale = act_scale; f.w_t = nullptr; f.ld_wt = 0;
+  p.dw = dw_t; p.ld_dw = ld_dwt;
+  char* w = reinterpret_cast<char*>(ws);
+  uint32_t* absmax = reinterpret_cast<uint32_t*>(w);
+  w += 256;
+  p.absmax = absmax;
+  const size_t ep = align_up((size_t)n_edges, 128);
+  p.act[0] = reinterpret_cast<float*>(w);
+  w += ep * n_rb * 4;
+  for (int l = 1; l <= n_hidden; ++l) {
+    p.act[l] = reinterpret_cast<float*>(w);
+    w += ep * 512;
+  }
+  for (int l = 1; l <= n_hidden; ++l) {
+    p.grad[l] = reinterpret_cast<float*>(w);
+    w += ep * 512;
+  }
+  void* gws = w;
+  const size_t gws_bytes = rm_bwd_gemm_ws(n_edges);
+  // the tensor-core weight-gradient kernel (tc_mlp.cu) takes layers with 32 / 64 / 128 inputs from 4096 edges on; the
+  // output layer reads dw_t column-major and needs 16-byte aligned columns.  Other layers: row-major + CUDA-core GEMM.
+  for (int l = 0; l < RM_MAXL; ++l) p.blk[l] = 0;
+  for (int l = 0; l < F; ++l) {
+    const int K = rm_K(f, l);
+    bool ok = n_edges >= 4096 && (K == 32 || K == 64 || K == 128);
+    if (l == F - 1) ok = ok && ld_dwt % 4 == 0 && (reinterpret_cast<uintptr_t>(dw_t) & 15) == 0;
+    p.blk[l] = ok ? 1 : 0;
+  }
+  if (n_edges == 0) {
+    for (int l = 0; l < F; ++l) {
+      const int K = rm_K(f, l), N = l == F - 1 ? n_out : 128;
+      for (int k = 0; k < K; ++k) EQNN_CUDA(cudaMemsetAsync(grad_weights[l] + (int64_t)k * ldw[l], 0, (size_t)N * 4, st));
+    }
+    return EQNN_OK;
+  }
+  EQNN_CUDA(cudaMemsetAsync(absmax, 0, 4, st));
+  {
+    const int64_t want = (n_edges + 255) / 256;
+    const unsigned grid = (unsigned)(want < 1184 ? want : 1184);
+    absmax_kernel<<<grid, 256, 0, st>>>(dw_t, ld_dwt, n_out, n_edges, absmax);
+  }
+  uint32_t smem = rm_smem_bytes(f) + 2 * RM_GSLAB;
+  static DeviceOnce once;
+  EQNN_CUDA(configure_smem(once, rmlp_bwd_kernel, 227 * 1024));
+  const int64_t n_tiles = (n_edges + RM_TILE - 1) / RM_TILE;
+  const int sms = sm_count();
+  const unsigned grid = (unsigned)(n_tiles < sms ? n_tiles : sms);
+  rmlp_bwd_kernel<<<grid, RM_THREADS, smem, st>>>(p);
+  EQNN_CHECK_LAUNCH_N(2);
+  // weight gradients: dW_l = alpha_l * c_l * gelu(z_{l-1})^T g_l (c_l = act_scale for l >= 1: the emitted activations are bare)
+  for (int l = 0; l < F; ++l) {
+    const int K = rm_K(f, l);
+    const float al = rm_wscale(f.alpha, f.act_scale, l);
+    int rc = 0;
+    const float* G = l < F - 1 ? p.grad[l + 1] : dw_t;
+    const int64_t N = l < F - 1 ? 128 : n_out, sbk = l < F - 1 ? 128 : 1, sbn = l < F - 1 ? 1 : ld_dwt;
+    if (p.blk[l]) {
+      const int w = eqnn_tc_wgrad_try(K, N, n_edges, al, p.act[l], 1, K, G, sbk, sbn, grad_weights[l], ldw[l], 1, 0, 0, 1.f,
+                                      0, gws, gws_bytes, st, nullptr, l < F - 1 ? 3 : 1);
+      if (w < 0) return -w;
+      if (w != 1) return eqnn_fail(EQNN_ERR_ARG, "radial_mlp_bwd: weight-gradient shape not covered by the tensor-core kernel");
+      continue;
+    }
+    rc = eqnn_gemm_f32(K, N, n_edges, al, p.act[l], 1, K, G, sbk, sbn, grad_weights[l], ldw[l], 1, 0, 0, 1.f, 0, nullptr, 0,
+                       1.f, gws, gws_bytes, stream);
+    if (rc) return rc;
+  }
   return EQNN_OK;
 }

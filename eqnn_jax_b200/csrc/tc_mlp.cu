@@ -392,6 +392,10 @@ struct WgradP {
   float pro_scale;
   float* partial;   // [gridDim.x][MI][NPAD]
   float* colsum;    // [gridDim.x][N] per-CTA column sums of G (the bias gradient of a Dense layer), or NULL; GMODE 0
+  // "blocked" operands (written by the fused radial-MLP chain kernel, rmlp.cu): every 32-edge chunk is one contiguous
+  // block laid out [16-byte column group c4][row][4 floats] instead of [row][column], so that the producer's lanes
+  // (one row each) write 512 contiguous bytes per store; the buffer is padded to whole chunks.
+  int x_blocked, g_blocked;
 };
 
 // wgrad thread layout (warpgroup-aligned so that registers can be re-balanced with setmaxnreg):
@@ -490,16 +494,18 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const WgradP p)
       const uint32_t rows = (uint32_t)((p.E - e0 < 32) ? (p.E - e0) : 32);
       const uint32_t xdst = raw0 + rs * Cfg::RAW_STAGE, gdst = xdst + Cfg::XRAW;
       const uint32_t gbytes = (GMODE == 0) ? rows * N * 4u : (uint32_t)p.n_valid * rows * 4u;
-      if (lane == 0) mbar_expect_tx(r_full(rs), rows * MI * 4u + gbytes);
+      const uint32_t xbytes = p.x_blocked ? 32u * MI * 4u : rows * MI * 4u;
+      const uint32_t gbytes_c = (GMODE == 0 && p.g_blocked) ? 32u * N * 4u : gbytes;
+      if (lane == 0) mbar_expect_tx(r_full(rs), xbytes + gbytes_c);
       __syncwarp();
       if (x_dense) {
-        if (lane == 0) bulk_g2s(xdst, p.X + e0 * p.ldx, rows * MI * 4u, r_full(rs));
+        if (lane == 0) bulk_g2s(xdst, p.X + e0 * p.ldx, xbytes, r_full(rs));
       } else if ((uint32_t)lane < rows) {
         bulk_g2s(xdst + lane * MI * 4u, p.X + (e0 + lane) * p.ldx, MI * 4u, r_full(rs));
       }
       if (GMODE == 0) {
         if (g_dense) {
-          if (lane == 0) bulk_g2s(gdst, p.G + e0 * p.ldg, rows * N * 4u, r_full(rs));
+          if (lane == 0) bulk_g2s(gdst, p.G + e0 * p.ldg, gbytes_c, r_full(rs));
         } else if ((uint32_t)lane < rows) {
           bulk_g2s(gdst + lane * N * 4u, p.G + (e0 + lane) * p.ldg, N * 4u, r_full(rs));
         }
@@ -538,7 +544,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const WgradP p)
       for (int i = 0; i < XI; ++i) {
         const int f = pt + i * WG_PT;
         if (f < 8 * MI) {
-          const int row = f / (MI / 4), c4 = f % (MI / 4);
+          const int row = p.x_blocked ? (f & 31) : f / (MI / 4), c4 = p.x_blocked ? (f >> 5) : f % (MI / 4);
           const float4 v = (row < rows) ? *reinterpret_cast<const float4*>(xraw + (uint32_t)f * 16u) : zero4;
           // MN-major slab [m-block of 32][32 k-rows]: 4-row atoms, 32-byte-chunk swizzle
           const uint32_t off = (c4 >> 3) * 4096 + sw128_base32(row, c4 & 7);
@@ -550,7 +556,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const WgradP p)
         for (int i = 0; i < GI; ++i) {
           const int f = pt + i * WG_PT;
           if (f < 8 * N) {
-            const int row = f / (N / 4), c4 = f % (N / 4);
+            const int row = p.g_blocked ? (f & 31) : f / (N / 4), c4 = p.g_blocked ? (f >> 5) : f % (N / 4);
             const float4 v = (row < rows) ? *reinterpret_cast<const float4*>(graw + (uint32_t)f * 16u) : zero4;
             const uint32_t off = (c4 >> 3) * 4096 + sw128_base32(row, c4 & 7);
             put(sb + off, sb + B_HALF_W + off, v, std::false_type{});
@@ -729,9 +735,10 @@ size_t eqnn_tc_wgrad_workspace_bytes(int64_t M, int64_t N, int64_t K) {
 int eqnn_tc_wgrad_try(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t sam, int64_t sak,
                       const float* B, int64_t sbk, int64_t sbn, float* C, int64_t scm, int64_t scn, int accumulate,
                       int pro, float pro_scale, int epi, void* ws, size_t ws_bytes, cudaStream_t st,
-                      float* colsum_out) {
+                      float* colsum_out, int blocked) {
+  // blocked: bit 0 = A (X) in the blocked chunk layout, bit 1 = B (G); see WgradP
   if (accumulate || epi != 0 || K < 4096 || scn != 1) return 0;
-  if (colsum_out && !(N == 128 && sbn == 1)) return 0;
+  if (colsum_out && !(N == 128 && sbn == 1 && !(blocked & 2))) return 0;
   if (!(M == 32 || M == 64 || M == 128) || sam != 1 || sak % 4 != 0 || (reinterpret_cast<uintptr_t>(A) & 15)) return 0;
   if (reinterpret_cast<uintptr_t>(B) & 15) return 0;
   const int sms = sm_count();
@@ -739,17 +746,19 @@ int eqnn_tc_wgrad_try(int64_t M, int64_t N, int64_t K, float alpha, const float*
   const int grid = (int)(n_chunks < sms ? n_chunks : sms);
   WgradP p;
   p.X = A; p.ldx = sak; p.G = B; p.E = K; p.pro_scale = pro_scale; p.n_valid = (int)N;
+  p.x_blocked = blocked & 1; p.g_blocked = (blocked >> 1) & 1;
+  if (p.x_blocked && sak != M) return 0;
   p.partial = reinterpret_cast<float*>(ws);
   p.colsum = nullptr;
   int rc = 0, npad = 0;
-  if (N == 128 && sbn == 1 && sbk % 4 == 0) {
+  if (N == 128 && sbn == 1 && sbk % 4 == 0 && (!p.g_blocked || sbk == 128)) {
     npad = 128; p.ldg = sbk;
     if (!ws || ws_bytes < (size_t)grid * (M * npad + (colsum_out ? npad : 0)) * 4) return 0;
     if (colsum_out) p.colsum = p.partial + (size_t)grid * M * npad;
     if (M == 128) rc = pro ? launch_wgrad<128, 128, 0, 1>(p, grid, st) : launch_wgrad<128, 128, 0, 0>(p, grid, st);
     else if (M == 64) rc = pro ? launch_wgrad<64, 128, 0, 1>(p, grid, st) : launch_wgrad<64, 128, 0, 0>(p, grid, st);
     else rc = pro ? launch_wgrad<32, 128, 0, 1>(p, grid, st) : launch_wgrad<32, 128, 0, 0>(p, grid, st);
-  } else if (N <= 16 && sbk == 1 && sbn % 4 == 0) {
+  } else if (N <= 16 && sbk == 1 && sbn % 4 == 0 && !p.g_blocked) {
     npad = 16; p.ldg = sbn;
     if (!ws || ws_bytes < (size_t)grid * M * npad * 4) return 0;
     if (M == 128) rc = pro ? launch_wgrad<128, 16, 1, 1>(p, grid, st) : launch_wgrad<128, 16, 1, 0>(p, grid, st);

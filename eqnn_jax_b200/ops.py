@@ -248,6 +248,25 @@ def radial_mlp_fwd(geom, n_rb, r_cut, weights, n_out, act_scale, w_t):
         TIMER.end("radial_mlp_fwd", t0)
 
 
+_RMLP_WS = GemmWorkspace()
+
+
+def radial_mlp_bwd(geom, n_rb, r_cut, weights, n_out, act_scale, dw_t, grad_weights):
+    """Weight gradients of the radial MLP from dw_t [n_out, E]; grad_weights = [(tensor, offset, ld)] like weights."""
+    E = geom.shape[0]
+    ptrs, lds = _weight_ptrs(weights)
+    gptrs, glds = _weight_ptrs(grad_weights)
+    assert list(lds) == list(glds)
+    need = lib().eqnn_radial_mlp_bwd_workspace_bytes(E, n_rb, len(weights) - 1)
+    ws, ws_bytes = _RMLP_WS.get(need, geom.device)
+    t0 = TIMER.begin() if TIMER else None
+    check(lib().eqnn_radial_mlp_bwd(C.c_void_p(geom.data_ptr() + 12), 4, E, n_rb, float(r_cut), len(weights) - 1, 128,
+                                    ptrs, lds, n_out, float(act_scale), _ptr(dw_t), dw_t.shape[1], gptrs, ws, ws_bytes,
+                                    _stream()), "radial_mlp_bwd")
+    if TIMER:
+        TIMER.end("radial_mlp_bwd", t0)
+
+
 def _int_arr(v: Sequence[int]):
     return (C.c_int * max(len(v), 1))(*v)
 

@@ -364,6 +364,18 @@ int eqnn_colsum_tall(const float* x, int64_t M, int N, float* y, void* ws, size_
  *   w_t [n_out][ld_wt] column-major (the layout eqnn_tpconv_fwd reads)
  * eqnn_radial_mlp_supported: 1 if the shape is covered (n_rb in {16,32,64}, d_hidden = 128, 1 <= n_hidden <= 3). */
 int eqnn_radial_mlp_supported(int n_rb, int d_hidden, int n_hidden, int n_out);
+/* Backward of the same MLP w.r.t. its weights (the only gradient the reference takes: jax.value_and_grad w.r.t.
+ * params, train_cosmology.py:245; edge lengths carry no gradient).  dw_t [n_out][ld_dwt] = dL/dw_t.
+ * grad_weights: HOST array of n_hidden + 1 device pointers with the shapes / leading dimensions of `weights`
+ * (overwritten).  A chain kernel recomputes the activations from d in tensor memory and runs the data-gradient
+ * chain dL/dz_l = (dL/dz_{l+1} @ W_{l+1}^T) * gelu'(z_l) without leaving the SM; it emits gelu(z_l) and dL/dz_l once
+ * (the operands of the weight-gradient GEMMs, which run on the tcgen05 weight-gradient kernel with the edge axis as K).
+ * Nothing is kept from the forward pass.  ws: eqnn_radial_mlp_bwd_workspace_bytes. */
+size_t eqnn_radial_mlp_bwd_workspace_bytes(int64_t n_edges, int n_rb, int n_hidden);
+int eqnn_radial_mlp_bwd(const float* dist, int64_t dist_stride, int64_t n_edges, int n_rb, double r_cut, int n_hidden,
+                        int d_hidden, const float* const* weights, const int64_t* ldw, int n_out, float act_scale,
+                        const float* dw_t, int64_t ld_dwt, float* const* grad_weights, void* ws, size_t ws_bytes,
+                        eqnn_stream_t stream);
 int eqnn_radial_mlp_fwd(const float* dist, int64_t dist_stride, int64_t n_edges, int n_rb, double r_cut, int n_hidden,
                         int d_hidden, const float* const* weights, const int64_t* ldw, int n_out, float act_scale,
                         float* w_t, int64_t ld_wt, eqnn_stream_t stream);

@@ -70,3 +70,42 @@ def test_radial_mlp_fwd_rejects_unsupported_shapes():
     assert not ops.radial_mlp_supported(64, 64, 3, 8)
     assert not ops.radial_mlp_supported(64, 128, 4, 8)
     assert not ops.radial_mlp_supported(64, 128, 3, 17)
+
+
+@pytest.mark.parametrize("E,n_rb,n_hidden,n_out,gmag", [
+    (128 * 148 + 77, 64, 3, 8, 1e-6),     # cfg-2 model; tiny gradients exercise the power-of-two scale
+    (4096, 64, 3, 8, 1.0),
+    (5000, 32, 2, 11, 3e3),
+    (4200, 16, 1, 16, 1e-3),
+    (300, 64, 3, 8, 1.0),                  # below the tensor-core weight-gradient threshold (CUDA-core GEMMs)
+])
+def test_radial_mlp_bwd_matches_oracle(E, n_rb, n_hidden, n_out, gmag):
+    from eqnn_jax_b200 import ops
+    from eqnn_jax_b200.nequip import normalize_constant
+    r_cut = 0.6
+    act_scale = 1.0 / normalize_constant("gelu")
+    d, Ws = _inputs(E, n_rb, n_hidden, n_out, seed=7 + E % 1000)
+    rng = np.random.default_rng(E)
+    # heavy-tailed cotangent: a few edges carry most of the gradient, most are orders of magnitude smaller
+    dw = (rng.normal(size=(n_out, E)) * np.exp(rng.normal(size=(1, E)) * 2.0) * gmag).astype(np.float32)
+    geom = torch.zeros((E, 4), dtype=torch.float32, device="cuda")
+    geom[:, 3] = torch.tensor(d, device="cuda")
+    Wd = [torch.tensor(W, device="cuda") for W in Ws]
+    gW = [torch.full_like(W, float("nan")) for W in Wd]
+    ops.radial_mlp_bwd(geom, n_rb, r_cut, [(W, 0, W.shape[1]) for W in Wd], n_out, act_scale,
+                       torch.tensor(dw, device="cuda"), [(g, 0, g.shape[1]) for g in gW])
+    torch.cuda.synchronize()
+    # oracle: autograd through the fp64 restatement
+    from oracle import e3nn_ref as R
+    Wt = [torch.tensor(W, dtype=torch.float64, requires_grad=True) for W in Ws]
+    a = R.bessel(torch.tensor(d, dtype=torch.float64), n_rb, r_cut)
+    for l, W in enumerate(Wt):
+        a = a @ W / math.sqrt(W.shape[0])
+        if l < len(Wt) - 1:
+            a = R.gelu_tanh(a) * act_scale
+    (a * torch.tensor(dw, dtype=torch.float64).T).sum().backward()
+    for l, (g, W) in enumerate(zip(gW, Wt)):
+        got, want = g.double().cpu(), W.grad
+        assert torch.isfinite(got).all(), f"layer {l}: non-finite gradient"
+        err = float((got - want).abs().max() / want.abs().max())
+        assert err < TOL, f"radial MLP weight gradient, layer {l}: {err:.2e}"
