@@ -18,6 +18,8 @@
 #include "common.cuh"
 #include "rmlp_common.cuh"
 
+#include <stdlib.h>
+
 namespace {
 
 using namespace rmlp;
@@ -44,6 +46,9 @@ struct RmlpP {
   float act_scale;          // 1 / c of e3nn.normalize_function(gelu)
   float* w_t;               // [n_out][ld_wt] column-major radial weights
   int64_t ld_wt;
+  // optional stash of the pre-activations for eqnn_radial_mlp_bwd: z_stash[l - 1] = z_l, l = 1..n_hidden, each
+  // [ceil(E/32)] chunks of [32 column groups][32 rows][4 floats] (the blocked chunk layout of tc_mlp.cu's WgradP)
+  float* z_stash[RM_MAXL];
 };
 
 __host__ __device__ inline int rm_K(const RmlpP& p, int l) { return l == 0 ? p.n_rb : 128; }
@@ -71,6 +76,22 @@ __device__ __forceinline__ void act_split32(const float* v, uint32_t* hiw, uint3
     float a0, a1;
     upk2(a, a0, a1);
     split_h2(a0, a1, hiw[j], low[j]);
+  }
+}
+
+// NV values of row e, columns [c0, c0 + NV) of a [E][ncols] matrix
+template <int NV>
+__device__ __forceinline__ void emit_cols(float* basep, int blocked, int64_t e, int ncols, int c0, const float* v) {
+  if (blocked) {
+    float* dst = basep + (e >> 5) * (int64_t)(32 * ncols) + (int64_t)(c0 >> 2) * 128 + (e & 31) * 4;
+#pragma unroll
+    for (int i = 0; i < NV / 4; ++i)
+      *reinterpret_cast<float4*>(dst + i * 128) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  } else {
+    float* dst = basep + e * ncols + c0;
+#pragma unroll
+    for (int i = 0; i < NV / 4; ++i)
+      *reinterpret_cast<float4*>(dst + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
   }
 }
 
@@ -169,6 +190,10 @@ __global__ void __launch_bounds__(RM_THREADS, 1) rmlp_fwd_kernel(const RmlpP p) 
           float v[32];
           tmem_ld32(t, v);
           tmem_ld_wait();
+          if (p.z_stash[l - 1]) {
+            const int64_t e = (blockIdx.x + (2 * pr + x) * (int64_t)gridDim.x) * RM_TILE + row;
+            if (e < p.E) emit_cols<32>(p.z_stash[l - 1], 1, e, 128, 32 * cg, v);
+          }
           uint32_t hiw[16], low[16];
           act_split32(v, hiw, low);
           tmem_st16(t, hiw);
@@ -212,14 +237,20 @@ __global__ void __launch_bounds__(RM_THREADS, 1) rmlp_fwd_kernel(const RmlpP p) 
           tc_fence_after();
           const uint32_t d_tmem = region(x, (l - 1) & 1) + (l == F ? RM_FINAL_COL : 0u);
           const uint32_t a_reg = region(x, l & 1);
-          for (int s = 0; s < K / 16; ++s) {
-            const uint32_t a_hi = a_reg + (uint32_t)(32 * (s >> 1) + 8 * (s & 1)), a_lo = a_hi + 16;
-            const uint32_t boff = (uint32_t)(s >> 2) * (uint32_t)N * 128u + (uint32_t)(s & 3) * 32u;
-            const uint64_t dbh = make_desc(b_hi + boff, 16, 1024), dbl = make_desc(b_lo + boff, 16, 1024);
-            mma_f16_ts(d_tmem, a_hi, dbh, idesc, s ? 1u : 0u);
-            mma_f16_ts(d_tmem, a_lo, dbh, idesc, 1u);
-            mma_f16_ts(d_tmem, a_hi, dbl, idesc, 1u);
-          }
+          // The accumulator in tensor memory truncates on every update, in proportion to its current magnitude: the
+          // small cross terms (lo*hi, hi*lo) go first, the hi*hi terms that carry the value go last (pass 0 / pass 1).
+          for (int pass = 0; pass < 2; ++pass)
+            for (int s = 0; s < K / 16; ++s) {
+              const uint32_t a_hi = a_reg + (uint32_t)(32 * (s >> 1) + 8 * (s & 1)), a_lo = a_hi + 16;
+              const uint32_t boff = (uint32_t)(s >> 2) * (uint32_t)N * 128u + (uint32_t)(s & 3) * 32u;
+              const uint64_t dbh = make_desc(b_hi + boff, 16, 1024), dbl = make_desc(b_lo + boff, 16, 1024);
+              if (pass == 0) {
+                mma_f16_ts(d_tmem, a_lo, dbh, idesc, s ? 1u : 0u);
+                mma_f16_ts(d_tmem, a_hi, dbl, idesc, 1u);
+              } else {
+                mma_f16_ts(d_tmem, a_hi, dbh, idesc, 1u);
+              }
+            }
           mma_commit(acc_full(x));
         }
       }
@@ -281,22 +312,6 @@ __device__ __forceinline__ void gelu_both2(f32x2 x, f32x2& g, f32x2& gp) {
   const f32x2 w = mul2(x, fma2(xx, pk2(D1, D1), pk2(D0, D0)));
   const f32x2 q = mul2(sg, fma2(sg, pk2(-1.f, -1.f), pk2(1.f, 1.f)));
   gp = fma2(q, w, sg);
-}
-
-// NV values of row e, columns [c0, c0 + NV) of a [E][ncols] matrix
-template <int NV>
-__device__ __forceinline__ void emit_cols(float* basep, int blocked, int64_t e, int ncols, int c0, const float* v) {
-  if (blocked) {
-    float* dst = basep + (e >> 5) * (int64_t)(32 * ncols) + (int64_t)(c0 >> 2) * 128 + (e & 31) * 4;
-#pragma unroll
-    for (int i = 0; i < NV / 4; ++i)
-      *reinterpret_cast<float4*>(dst + i * 128) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-  } else {
-    float* dst = basep + e * ncols + c0;
-#pragma unroll
-    for (int i = 0; i < NV / 4; ++i)
-      *reinterpret_cast<float4*>(dst + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-  }
 }
 
 __global__ void __launch_bounds__(RM_THREADS, 1) rmlp_bwd_kernel(const RmlpBwdP p) {
@@ -376,11 +391,7 @@ __global__ void __launch_bounds__(RM_THREADS, 1) rmlp_bwd_kernel(const RmlpBwdP 
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int64_t e = tile * RM_TILE + row;
       const bool live = e < f.E;
-      // The tensor core's fp32 accumulation truncates: every accumulator carries a small bias of one sign, which the
-      // weight-gradient sums over millions of edges would add up coherently (measured: error growing with the edge
-      // count).  Odd tiles therefore run the whole (linear) gradient chain on -g and flip the sign back when they
-      // emit: the bias changes sign with the tile parity and cancels in the sums.
-      const float gS = (tile & 1) ? -gS0 : gS0, gSinv = (tile & 1) ? -gSinv0 : gSinv0;
+      const float gS = gS0, gSinv = gSinv0;
       // ---- c0: Bessel basis -> operand of layer 1 (k-step s of the basis sits at column 32 s of region 1) ----
       if (16 * cg < f.n_rb) {
         const float d = live ? __ldg(f.dist + e * f.dist_stride) : 0.f;
@@ -500,27 +511,35 @@ __global__ void __launch_bounds__(RM_THREADS, 1) rmlp_bwd_kernel(const RmlpBwdP 
       const uint32_t idesc = make_idesc_f16(128, 128, 0, 0);
       const uint32_t b_hi = base + w_off[l - 1], b_lo = b_hi + w_half[l - 1];
       const uint32_t d_tmem = region(l - 1), a_reg = region(l);
-      for (int s = 0; s < K / 16; ++s) {
-        const uint32_t a_hi = a_reg + (l == 1 ? (uint32_t)(32 * s) : (uint32_t)(32 * (s >> 1) + 8 * (s & 1))), a_lo = a_hi + 16;
-        const uint32_t boff = (uint32_t)(s >> 2) * 128u * 128u + (uint32_t)(s & 3) * 32u;
-        const uint64_t dbh = make_desc(b_hi + boff, 16, 1024), dbl = make_desc(b_lo + boff, 16, 1024);
-        mma_f16_ts(d_tmem, a_hi, dbh, idesc, s ? 1u : 0u);
-        mma_f16_ts(d_tmem, a_lo, dbh, idesc, 1u);
-        mma_f16_ts(d_tmem, a_hi, dbl, idesc, 1u);
-      }
+      for (int pass = 0; pass < 2; ++pass)     // cross terms first, hi*hi last (see rmlp_fwd_kernel)
+        for (int s = 0; s < K / 16; ++s) {
+          const uint32_t a_hi = a_reg + (l == 1 ? (uint32_t)(32 * s) : (uint32_t)(32 * (s >> 1) + 8 * (s & 1))), a_lo = a_hi + 16;
+          const uint32_t boff = (uint32_t)(s >> 2) * 128u * 128u + (uint32_t)(s & 3) * 32u;
+          const uint64_t dbh = make_desc(b_hi + boff, 16, 1024), dbl = make_desc(b_lo + boff, 16, 1024);
+          if (pass == 0) {
+            mma_f16_ts(d_tmem, a_lo, dbh, idesc, s ? 1u : 0u);
+            mma_f16_ts(d_tmem, a_hi, dbl, idesc, 1u);
+          } else {
+            mma_f16_ts(d_tmem, a_hi, dbh, idesc, 1u);
+          }
+        }
     };
     // data gradient through layer l (1-based, 2 <= l <= H): D (N = 128 inputs k) = A (g_l, K = 128 outputs n) x image l-1
     // read MN-major: k-step s = rows n = 16 s .. 16 s + 15 of both 64-k slabs (LBO = slab stride, SBO = 8 rows)
     auto issue_dgrad = [&](int l, uint32_t a_reg, uint32_t d_tmem) {
       const uint32_t idesc = make_idesc_f16(128, 128, 0, 1);
       const uint32_t b_hi = base + w_off[l - 1], b_lo = b_hi + w_half[l - 1];
-      for (int s = 0; s < 8; ++s) {
-        const uint32_t a_hi = a_reg + (uint32_t)(32 * (s >> 1) + 8 * (s & 1)), a_lo = a_hi + 16;
-        const uint64_t dbh = make_desc(b_hi + s * 2048u, 128u * 128u, 1024), dbl = make_desc(b_lo + s * 2048u, 128u * 128u, 1024);
-        mma_f16_ts(d_tmem, a_hi, dbh, idesc, s ? 1u : 0u);
-        mma_f16_ts(d_tmem, a_lo, dbh, idesc, 1u);
-        mma_f16_ts(d_tmem, a_hi, dbl, idesc, 1u);
-      }
+      for (int pass = 0; pass < 2; ++pass)
+        for (int s = 0; s < 8; ++s) {
+          const uint32_t a_hi = a_reg + (uint32_t)(32 * (s >> 1) + 8 * (s & 1)), a_lo = a_hi + 16;
+          const uint64_t dbh = make_desc(b_hi + s * 2048u, 128u * 128u, 1024), dbl = make_desc(b_lo + s * 2048u, 128u * 128u, 1024);
+          if (pass == 0) {
+            mma_f16_ts(d_tmem, a_lo, dbh, idesc, s ? 1u : 0u);
+            mma_f16_ts(d_tmem, a_hi, dbl, idesc, 1u);
+          } else {
+            mma_f16_ts(d_tmem, a_hi, dbh, idesc, 1u);
+          }
+        }
     };
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       for (int l = 1; l <= H; ++l) {
@@ -539,9 +558,9 @@ __global__ void __launch_bounds__(RM_THREADS, 1) rmlp_bwd_kernel(const RmlpBwdP 
           const uint32_t b_hi = base + w_off[F - 1], b_lo = b_hi + w_half[F - 1];
           const uint64_t dah = make_desc(g_hi, 16, 1024), dal = make_desc(g_lo, 16, 1024);
           const uint64_t dbh = make_desc(b_hi, 16u * 128u, 1024), dbl = make_desc(b_lo, 16u * 128u, 1024);
-          mma_f16_ss(region(H), dah, dbh, idesc, 0u);
-          mma_f16_ss(region(H), dal, dbh, idesc, 1u);
+          mma_f16_ss(region(H), dal, dbh, idesc, 0u);
           mma_f16_ss(region(H), dah, dbl, idesc, 1u);
+          mma_f16_ss(region(H), dah, dbh, idesc, 1u);
           mma_commit(acc_full);
         }
       }
@@ -560,6 +579,213 @@ __global__ void __launch_bounds__(RM_THREADS, 1) rmlp_bwd_kernel(const RmlpBwdP 
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Backward chain from stashed pre-activations (the default): the forward kernel has written z_1 .. z_H once; this
+// kernel runs only the data-gradient chain, g_H = (dw @ W_out^T) * gelu'(z_H), g_{l-1} = (g_l @ W_l^T) * gelu'(z_{l-1}),
+// with the structure of the forward kernel: accumulator and operand in place in tensor memory, two tiles in flight
+// (no stash regions are needed: gelu'(z_l) is formed from the z_l rows loaded straight into registers, prefetched
+// before the accumulator barrier).  It emits g_l for the weight-gradient kernel.
+// ------------------------------------------------------------------------------------------------------------------
+struct RmlpDgradP {
+  RmlpP f;
+  const float* dw;
+  int64_t ld_dw;
+  const uint32_t* absmax;
+  const float* z[RM_MAXL];   // z[l] = z_l, l = 1..H, blocked chunk layout
+  float* grad[RM_MAXL];      // grad[l] = dL/dz_l, l = 1..H
+  int blk[RM_MAXL];          // blk[l - 1]: layout of grad[l] (1 blocked, 0 row-major)
+};
+
+__device__ __forceinline__ void load_blocked32(const float* basep, int64_t e, int c0, float* v) {
+  const float* src = basep + (e >> 5) * (int64_t)(32 * 128) + (int64_t)(c0 >> 2) * 128 + (e & 31) * 4;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(src + i * 128));
+    v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+  }
+}
+
+__global__ void __launch_bounds__(RM_THREADS, 1) rmlp_dgrad_kernel(const RmlpDgradP p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const RmlpP& f = p.f;
+  const int F = f.n_layers, H = F - 1;
+
+  // shared-memory map: weight images of layers 2..F (layer 1 is not differentiated through) | barriers
+  uint32_t w_off[RM_MAXL], w_half[RM_MAXL];
+  uint32_t off = 0;
+#pragma unroll
+  for (int l = 0; l < RM_MAXL; ++l) {
+    if (l >= 1 && l < F) {
+      w_off[l] = off;
+      w_half[l] = w_half_bytes(rm_K(f, l), rm_N(f, l));
+      off += 2 * w_half[l];
+    } else {
+      w_off[l] = w_half[l] = 0;
+    }
+  }
+  const uint32_t bars = base + off;
+  auto opnd_full = [&](int x) { return bars + 8u * x; };
+  auto acc_full = [&](int x) { return bars + 8u * (2 + x); };
+  const uint32_t tmem_slot = bars + 32;
+
+  if (tid == 0) {
+    for (int x = 0; x < 2; ++x) {
+      mbar_init(opnd_full(x), RM_CT);
+      mbar_init(acc_full(x), 1);
+    }
+    mbar_fence_init();
+  }
+  if (warp == RM_MMA_WARP) tmem_alloc(tmem_slot, 512);
+  for (int l = 1; l < F; ++l)
+    fill_weight_image(gen + w_off[l], gen + w_off[l] + w_half[l], f.W[l], f.ldw[l], rm_K(f, l), rm_N(f, l),
+                      l == F - 1 ? f.n_out : 128, rm_wscale(f.alpha, f.act_scale, l), tid, RM_THREADS);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
+
+  const int64_t n_tiles = (f.E + RM_TILE - 1) / RM_TILE;
+  const int64_t my_tiles = (blockIdx.x < n_tiles) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int64_t n_pairs = (my_tiles + 1) / 2;
+  auto region = [&](int x, int r) { return tmem_base + (uint32_t)(x * 256 + (r & 1) * 128); };
+
+  const uint32_t mbits = __ldg(p.absmax);
+  const int mexp = (int)((mbits >> 23) & 0xffu);
+  int sexp = 127 + 2 - (mexp - 127);
+  sexp = sexp < 1 ? 1 : (sexp > 254 ? 254 : sexp);
+  const float gS0 = (mexp == 0) ? 1.f : __uint_as_float((uint32_t)sexp << 23);
+  const float gSinv0 = (mexp == 0) ? 1.f : __uint_as_float((uint32_t)(254 - sexp) << 23);
+
+  if (warp < RM_CW) {
+    // =========================== compute warps ===========================
+    const int q = warp & 3, cg = warp >> 2;
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    const int row = q * 32 + lane;
+    uint32_t n_acc[2] = {0u, 0u};
+    for (int64_t pr = 0; pr < n_pairs; ++pr) {
+      const int nx = (2 * pr + 1 < my_tiles) ? 2 : 1;
+      // ---- dw row (scaled) -> operand in region 1, columns [0, 8) + [16, 24) ----
+      for (int x = 0; x < nx; ++x) {
+        const int64_t tile = blockIdx.x + (2 * pr + x) * (int64_t)gridDim.x;
+        const int64_t e = tile * RM_TILE + row;
+        if (cg == 0) {
+          const float gS = gS0;
+          float g[16];
+#pragma unroll
+          for (int c = 0; c < 16; ++c) g[c] = (e < f.E && c < f.n_out) ? gS * __ldg(p.dw + (int64_t)c * p.ld_dw + e) : 0.f;
+          uint32_t hiw[8], low[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) split_h2(g[2 * j], g[2 * j + 1], hiw[j], low[j]);
+          const uint32_t t = region(x, 1) + lane_sel;
+          tmem_st8(t, hiw);
+          tmem_st8(t + 16, low);
+          tmem_st_wait();
+        }
+        tc_fence_before();
+        mbar_arrive(opnd_full(x));
+      }
+      // ---- g_l = product * gelu'(z_l), l = H .. 1; g_l sits in region (H - l) ----
+      for (int l = H; l >= 1; --l) {
+        for (int x = 0; x < nx; ++x) {
+          const int64_t tile = blockIdx.x + (2 * pr + x) * (int64_t)gridDim.x;
+          const int64_t e = tile * RM_TILE + row;
+          const bool live = e < f.E;
+          float z[32];
+          if (live) {
+            load_blocked32(p.z[l], e, 32 * cg, z);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) z[j] = 0.f;
+          }
+          mbar_wait(acc_full(x), n_acc[x] & 1u);
+          ++n_acc[x];
+          tc_fence_after();
+          const uint32_t t = region(x, H - l) + lane_sel + (uint32_t)(32 * cg);
+          float pre[32];
+          tmem_ld32(t, pre);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const f32x2 g2 = mul2(pk2(pre[2 * j], pre[2 * j + 1]), gelu_grad2(pk2(z[2 * j], z[2 * j + 1])));
+            upk2(g2, pre[2 * j], pre[2 * j + 1]);
+          }
+          if (l >= 2) {
+            uint32_t hiw[16], low[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) split_h2(pre[2 * j], pre[2 * j + 1], hiw[j], low[j]);
+            tmem_st16(t, hiw);
+            tmem_st16(t + 16, low);
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(opnd_full(x));
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) pre[j] *= gSinv0;
+          if (live) emit_cols<32>(p.grad[l], p.blk[l - 1], e, 128, 32 * cg, pre);
+        }
+      }
+    }
+  } else if (lane == 0) {
+    // =========================== MMA issuer ===========================
+    uint32_t n_op[2] = {0u, 0u};
+    const uint32_t idesc = make_idesc_f16(128, 128, 0, 1);
+    for (int64_t pr = 0; pr < n_pairs; ++pr) {
+      const int nx = (2 * pr + 1 < my_tiles) ? 2 : 1;
+      for (int l = F; l >= 2; --l) {
+        // data gradient through layer l (1-based): A = g_l (the dw rows for l = F), B = image of layer l read MN-major
+        const uint32_t b_hi = base + w_off[l - 1], b_lo = b_hi + w_half[l - 1];
+        for (int x = 0; x < nx; ++x) {
+          mbar_wait(opnd_full(x), n_op[x] & 1u);
+          ++n_op[x];
+          tc_fence_after();
+          if (l == F) {
+            const uint64_t dbh = make_desc(b_hi, 16u * 128u, 1024), dbl = make_desc(b_lo, 16u * 128u, 1024);
+            const uint32_t a_hi = region(x, 1), a_lo = a_hi + 16, d_tmem = region(x, 0);
+            mma_f16_ts(d_tmem, a_lo, dbh, idesc, 0u);
+            mma_f16_ts(d_tmem, a_hi, dbl, idesc, 1u);
+            mma_f16_ts(d_tmem, a_hi, dbh, idesc, 1u);
+          } else {
+            const uint32_t a_reg = region(x, H - l), d_tmem = region(x, H - l + 1);
+            for (int pass = 0; pass < 2; ++pass)     // cross terms first, hi*hi last (see rmlp_fwd_kernel)
+              for (int s = 0; s < 8; ++s) {
+                const uint32_t a_hi = a_reg + (uint32_t)(32 * (s >> 1) + 8 * (s & 1)), a_lo = a_hi + 16;
+                const uint64_t dbh = make_desc(b_hi + s * 2048u, 128u * 128u, 1024), dbl = make_desc(b_lo + s * 2048u, 128u * 128u, 1024);
+                if (pass == 0) {
+                  mma_f16_ts(d_tmem, a_lo, dbh, idesc, s ? 1u : 0u);
+                  mma_f16_ts(d_tmem, a_hi, dbl, idesc, 1u);
+                } else {
+                  mma_f16_ts(d_tmem, a_hi, dbh, idesc, 1u);
+                }
+              }
+          }
+          mma_commit(acc_full(x));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == RM_MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// blocked [chunk][c4][row][4] -> row-major [E][128] (small problems only)
+__global__ void unblock_kernel(const float* __restrict__ src, int64_t n_edges, float* __restrict__ dst) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // float4 index of the row-major matrix
+  if (i >= n_edges * 32) return;
+  const int64_t e = i >> 5;
+  const int c4 = (int)(i & 31);
+  reinterpret_cast<float4*>(dst)[i] =
+      __ldg(reinterpret_cast<const float4*>(src + (e >> 5) * (int64_t)(32 * 128) + (int64_t)c4 * 128 + (e & 31) * 4));
+}
+
 }  // namespace
 
 // Shapes the fused kernels cover: 128-wide hidden layers, 1..3 of them, a Bessel basis of 16, 32 or 64 functions,
@@ -569,9 +795,16 @@ extern "C" int eqnn_radial_mlp_supported(int n_rb, int d_hidden, int n_hidden, i
          n_out <= 16;
 }
 
+// one layer of the z stash: whole 128-edge tiles of 128 floats
+static size_t rm_stash_layer_floats(int64_t n_edges) { return align_up((size_t)n_edges, 128) * 128; }
+extern "C" size_t eqnn_radial_mlp_stash_bytes(int64_t n_edges, int n_hidden) {
+  return (size_t)n_hidden * rm_stash_layer_floats(n_edges) * sizeof(float);
+}
+
 extern "C" int eqnn_radial_mlp_fwd(const float* dist, int64_t dist_stride, int64_t n_edges, int n_rb, double r_cut,
                                    int n_hidden, int d_hidden, const float* const* weights, const int64_t* ldw,
-                                   int n_out, float act_scale, float* w_t, int64_t ld_wt, eqnn_stream_t stream) {
+                                   int n_out, float act_scale, float* w_t, int64_t ld_wt, float* z_stash,
+                                   eqnn_stream_t stream) {
   EQNN_CHECK_ARG(dist && weights && ldw && w_t && n_edges >= 0 && dist_stride >= 1, "radial_mlp_fwd: bad argument");
   EQNN_CHECK_ARG(eqnn_radial_mlp_supported(n_rb, d_hidden, n_hidden, n_out), "radial_mlp_fwd: unsupported shape");
   EQNN_CHECK_ARG(r_cut > 0.0 && ld_wt >= n_edges, "radial_mlp_fwd: bad r_cut / ld_wt");
@@ -591,6 +824,9 @@ extern "C" int eqnn_radial_mlp_fwd(const float* dist, int64_t dist_stride, int64
     p.alpha[l] = (float)(1.0 / sqrt((double)rm_K(p, l)));
   }
   p.act_scale = act_scale; p.w_t = w_t; p.ld_wt = ld_wt;
+  EQNN_CHECK_ARG(!z_stash || (reinterpret_cast<uintptr_t>(z_stash) & 15) == 0, "radial_mlp_fwd: z_stash must be 16-byte aligned");
+  for (int l = 0; l < RM_MAXL; ++l)
+    p.z_stash[l] = (z_stash && l < n_hidden) ? z_stash + (size_t)l * rm_stash_layer_floats(n_edges) : nullptr;
   const uint32_t smem = rm_smem_bytes(p);
   static DeviceOnce once;
   EQNN_CUDA(configure_smem(once, rmlp_fwd_kernel, 227 * 1024));
@@ -619,10 +855,120 @@ extern "C" size_t eqnn_radial_mlp_bwd_workspace_bytes(int64_t n_edges, int n_rb,
   return 256 + ep * n_rb * 4 + 2 * (size_t)n_hidden * ep * 512 + align_up(rm_bwd_gemm_ws(n_edges), 256);
 }
 
+
+// Backward from the forward kernel's z stash: absmax -> data-gradient chain kernel -> weight gradients on the tcgen05
+// weight-gradient kernel (X = z_{l-1} with the gelu prologue, or the Bessel basis for the first layer; G = g_l).
+// workspace: [absmax 256 B | n_hidden x g_l | (bessel basis when radial == NULL) | GEMM workspace]
+static int rm_bwd_from_stash(const float* dist, int64_t dist_stride, int64_t n_edges, int n_rb, double r_cut, int n_hidden,
+                             int d_hidden, const float* const* weights, const int64_t* ldw, int n_out, float act_scale,
+                             const float* dw_t, int64_t ld_dwt, const float* z_stash, const float* radial,
+                             float* const* grad_weights, void* ws, size_t ws_bytes, eqnn_stream_t stream) {
+  EQNN_CHECK_ARG(dist && weights && ldw && dw_t && grad_weights && n_edges >= 0 && dist_stride >= 1, "radial_mlp_bwd: bad argument");
+  EQNN_CHECK_ARG(eqnn_radial_mlp_supported(n_rb, d_hidden, n_hidden, n_out), "radial_mlp_bwd: unsupported shape");
+  EQNN_CHECK_ARG(r_cut > 0.0 && ld_dwt >= n_edges, "radial_mlp_bwd: bad r_cut / ld_dwt");
+  EQNN_CHECK_ARG(radial != nullptr, "radial_mlp_bwd: the stash variant needs the Bessel basis (eqnn_edge_geom's radial)");
+  EQNN_CHECK_ARG((reinterpret_cast<uintptr_t>(z_stash) & 15) == 0, "radial_mlp_bwd: z_stash must be 16-byte aligned");
+  if (ws_bytes < eqnn_radial_mlp_bwd_workspace_bytes(n_edges, n_rb, n_hidden) || !ws) return eqnn_fail(EQNN_ERR_WORKSPACE, "radial_mlp_bwd: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  const int F = n_hidden + 1;
+  RmlpDgradP p;
+  RmlpP& f = p.f;
+  f.dist = dist; f.dist_stride = dist_stride; f.E = n_edges;
+  f.r_cut = (float)r_cut; f.pref = (float)sqrt(2.0 / r_cut);
+  f.n_rb = n_rb; f.n_layers = F; f.n_out = n_out;
+  for (int l = 0; l < RM_MAXL; ++l) {
+    f.W[l] = nullptr; f.ldw[l] = 0; f.alpha[l] = 0.f; f.z_stash[l] = nullptr;
+    p.z[l] = nullptr; p.grad[l] = nullptr; p.blk[l] = 0;
+  }
+  for (int l = 0; l < F; ++l) {
+    EQNN_CHECK_ARG(weights[l] != nullptr && grad_weights[l] != nullptr, "radial_mlp_bwd: null weight");
+    f.W[l] = weights[l]; f.ldw[l] = ldw[l];
+    f.alpha[l] = (float)(1.0 / sqrt((double)rm_K(f, l)));
+  }
+  f.act_scale = act_scale; f.w_t = nullptr; f.ld_wt = 0;
+  p.dw = dw_t; p.ld_dw = ld_dwt;
+  char* w = reinterpret_cast<char*>(ws);
+  uint32_t* absmax = reinterpret_cast<uint32_t*>(w);
+  w += 256;
+  p.absmax = absmax;
+  const size_t ep = align_up((size_t)n_edges, 128);
+  for (int l = 1; l <= n_hidden; ++l) {
+    p.z[l] = z_stash + (size_t)(l - 1) * rm_stash_layer_floats(n_edges);
+    p.grad[l] = reinterpret_cast<float*>(w);
+    w += ep * 512;
+  }
+  w += ep * n_rb * 4 + (size_t)n_hidden * ep * 512;   // (the recompute variant's activations live here)
+  void* gws = w;
+  const size_t gws_bytes = rm_bwd_gemm_ws(n_edges);
+  if (n_edges == 0) {
+    for (int l = 0; l < F; ++l) {
+      const int K = rm_K(f, l), N = l == F - 1 ? n_out : 128;
+      for (int k = 0; k < K; ++k) EQNN_CUDA(cudaMemsetAsync(grad_weights[l] + (int64_t)k * ldw[l], 0, (size_t)N * 4, st));
+    }
+    return EQNN_OK;
+  }
+  // layer l's weight gradient (0-based): X = radial (l = 0, row-major) or z_l (blocked), G = grad[l + 1] or dw_t
+  bool tc_ok[RM_MAXL];
+  for (int l = 0; l < F; ++l) {
+    const int K = rm_K(f, l);
+    bool ok = n_edges >= 4096 && (K == 32 || K == 64 || K == 128) && !getenv("EQNN_RMLP_NO_TC_WGRAD");
+    if (l == 0) ok = ok && (reinterpret_cast<uintptr_t>(radial) & 15) == 0;
+    if (l == F - 1) ok = ok && ld_dwt % 4 == 0 && (reinterpret_cast<uintptr_t>(dw_t) & 15) == 0;
+    tc_ok[l] = ok;
+    if (l < F - 1) p.blk[l] = ok ? 1 : 0;     // layout of grad[l + 1]
+  }
+  EQNN_CUDA(cudaMemsetAsync(absmax, 0, 4, st));
+  {
+    const int64_t want = (n_edges + 255) / 256;
+    const unsigned grid = (unsigned)(want < 1184 ? want : 1184);
+    absmax_kernel<<<grid, 256, 0, st>>>(dw_t, ld_dwt, n_out, n_edges, absmax);
+  }
+  uint32_t smem = 1024 + 64;
+  for (int l = 1; l < F; ++l) smem += 2 * w_half_bytes(rm_K(f, l), rm_N(f, l));
+  static DeviceOnce once;
+  EQNN_CUDA(configure_smem(once, rmlp_dgrad_kernel, 227 * 1024));
+  const int64_t n_tiles = (n_edges + RM_TILE - 1) / RM_TILE;
+  const int sms = sm_count();
+  const unsigned grid = (unsigned)(n_tiles < sms ? n_tiles : sms);
+  rmlp_dgrad_kernel<<<grid, RM_THREADS, smem, st>>>(p);
+  EQNN_CHECK_LAUNCH_N(2);
+  for (int l = 0; l < F; ++l) {
+    const int K = rm_K(f, l);
+    const float* X = l == 0 ? radial : p.z[l];
+    const int pro = l == 0 ? 0 : 1;
+    const float* G = l < F - 1 ? p.grad[l + 1] : dw_t;
+    const int64_t N = l < F - 1 ? 128 : n_out, sbk = l < F - 1 ? 128 : 1, sbn = l < F - 1 ? 1 : ld_dwt;
+    if (tc_ok[l]) {
+      const int blocked = (l > 0 ? 1 : 0) | (l < F - 1 ? 2 : 0);
+      const int r = eqnn_tc_wgrad_try(K, N, n_edges, f.alpha[l], X, 1, K, G, sbk, sbn, grad_weights[l], ldw[l], 1, 0, pro,
+                                      act_scale, 0, gws, gws_bytes, st, nullptr, blocked);
+      if (r < 0) return -r;
+      if (r != 1) return eqnn_fail(EQNN_ERR_ARG, "radial_mlp_bwd: weight-gradient shape not covered by the tensor-core kernel");
+      continue;
+    }
+    // small problems: CUDA-core GEMM on row-major operands; a blocked z_l is first copied out row-major
+    const float* Xr = X;
+    if (l > 0) {
+      float* tmp = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + 256 + (size_t)n_hidden * ep * 512);
+      unblock_kernel<<<(unsigned)ceil_div64(n_edges * 32, 256), 256, 0, st>>>(X, n_edges, tmp);
+      EQNN_CHECK_LAUNCH();
+      Xr = tmp;
+    }
+    const int rc = eqnn_gemm_f32(K, N, n_edges, f.alpha[l], Xr, 1, K, G, sbk, sbn, grad_weights[l], ldw[l], 1, 0, pro,
+                                 act_scale, 0, nullptr, 0, 1.f, gws, gws_bytes, stream);
+    if (rc) return rc;
+  }
+  return EQNN_OK;
+}
+
 extern "C" int eqnn_radial_mlp_bwd(const float* dist, int64_t dist_stride, int64_t n_edges, int n_rb, double r_cut,
                                    int n_hidden, int d_hidden, const float* const* weights, const int64_t* ldw,
                                    int n_out, float act_scale, const float* dw_t, int64_t ld_dwt,
-                                   float* const* grad_weights, void* ws, size_t ws_bytes, eqnn_stream_t stream) {
+                                   const float* z_stash, const float* radial, float* const* grad_weights, void* ws,
+                                   size_t ws_bytes, eqnn_stream_t stream) {
+  if (z_stash)
+    return rm_bwd_from_stash(dist, dist_stride, n_edges, n_rb, r_cut, n_hidden, d_hidden, weights, ldw, n_out, act_scale,
+                             dw_t, ld_dwt, z_stash, radial, grad_weights, ws, ws_bytes, stream);
   EQNN_CHECK_ARG(dist && weights && ldw && dw_t && grad_weights && n_edges >= 0 && dist_stride >= 1, "radial_mlp_bwd: bad argument");
   EQNN_CHECK_ARG(eqnn_radial_mlp_supported(n_rb, d_hidden, n_hidden, n_out), "radial_mlp_bwd: unsupported shape");
   EQNN_CHECK_ARG(r_cut > 0.0 && ld_dwt >= n_edges, "radial_mlp_bwd: bad r_cut / ld_dwt");
@@ -645,6 +991,7 @@ extern "C" int eqnn_radial_mlp_bwd(const float* dist, int64_t dist_stride, int64
     f.alpha[l] = (float)(1.0 / sqrt((double)rm_K(f, l)));
   }
   f.act_scale = act_scale; f.w_t = nullptr; f.ld_wt = 0;
+  for (int l = 0; l < RM_MAXL; ++l) f.z_stash[l] = nullptr;
   p.dw = dw_t; p.ld_dw = ld_dwt;
   char* w = reinterpret_cast<char*>(ws);
   uint32_t* absmax = reinterpret_cast<uint32_t*>(w);

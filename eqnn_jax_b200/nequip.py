@@ -394,6 +394,13 @@ class NequIP:
     tensor_cores: bool = True
     # not a reference field: Linear + self-connection + gate + re-projection as one fused N-row kernel
     fuse_node_update: bool = True
+    # not a reference field: the whole radial MLP (Bessel basis -> n_layers Dense + gelu -> radial weights) as ONE
+    # tcgen05 kernel per direction with the activations in tensor memory (eqnn_radial_mlp_fwd / _bwd); shapes the
+    # fused kernels do not cover (d_hidden != 128, n_radial_basis not in {16, 32, 64}, n_layers > 3, more than 16 live
+    # message columns) keep the per-layer GEMMs.  "stash": the forward kernel keeps the pre-activations for the
+    # backward pass (1.5 KB per edge and step); "recompute": nothing is kept, the backward recomputes them from d.
+    fuse_radial_mlp: bool = True
+    radial_mlp_backward: str = "stash"
 
     def __post_init__(self):
         self._plans: Dict[Irreps, _Plan] = {}
@@ -515,6 +522,23 @@ def _n_edge_of(graphs: GraphsTuple) -> float:
     return float(v[0])
 
 
+def _fused_radial_ok(model: "NequIP", plan: _Plan) -> bool:
+    """The fused radial-MLP kernels cover this model (tensor-core path requested, supported shape)."""
+    if not (model.fuse_radial_mlp and model.tensor_cores):
+        return False
+    if model.radial_mlp_backward not in ("stash", "recompute"):
+        raise ValueError("radial_mlp_backward must be 'stash' or 'recompute'")
+    return ops.radial_mlp_supported(model.n_radial_basis, model.d_hidden, model.n_layers, plan.tp.n_live)
+
+
+def _radial_weights(theta: torch.Tensor, wexp: torch.Tensor, st: Dict, n_live: int):
+    """[(buffer, element offset, leading dimension)] of the radial MLP's Dense kernels: the hidden layers are Flax
+    parameters in the flat buffer, the output layer is its live-column expansion (works for the gradient buffers too)."""
+    ws = [(theta, koff, hdim) for (koff, fan, hdim) in st["mlp"][:-1]]
+    ws.append((wexp, st["W4L"].off, n_live))
+    return ws
+
+
 class _NequIPFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, theta, model, plan, pg, nodes, k, globals_=None):
@@ -549,16 +573,25 @@ def _forward(model: NequIP, plan: _Plan, theta: torch.Tensor, pg: PreparedGraph,
         xt = torch.empty((Nt, dxp), **f32)
         _mm(Nt, dxp, D, 1.0, h, 0, D, wexp, st["W0x"].off, dxp, xt, 0, dxp)
         Zs, a, fan_prev, pro = [], pg.radial, plan.n_rad_in, 0
-        for (koff, fan, hdim) in st["mlp"][:-1]:
+        fused = _fused_radial_ok(model, plan)
+        stash = None
+        if fused:
+            w_t = torch.empty((n_live, Et), **f32)
+            if save and model.radial_mlp_backward == "stash":
+                stash = ops.radial_mlp_stash(Et, len(st["mlp"]) - 1, dev)
+            ops.radial_mlp_fwd(pg.geom, model.n_radial_basis, model.r_cutoff, _radial_weights(theta, wexp, st, n_live),
+                               n_live, plan.inv_c_act, w_t, z_stash=stash)
+        for (koff, fan, hdim) in ([] if fused else st["mlp"][:-1]):
             Z = torch.empty((Et, hdim), **f32)
             _mm(Et, hdim, fan, 1.0 / math.sqrt(fan), a, 0, fan, theta, koff, hdim, Z, 0, hdim,
                 pro=pro, pro_scale=plan.inv_c_act, tag="radial_mlp_fwd", tf32x3=model.tensor_cores)
             Zs.append(Z)
             a, pro = Z, 1
         _, fan, _ = st["mlp"][-1]
-        w_t = torch.empty((n_live, Et), **f32)
-        _mm(Et, n_live, fan, 1.0 / math.sqrt(fan), a, 0, fan, wexp, st["W4L"].off, n_live, w_t, 0, Et, tc=True,
-            pro=pro, pro_scale=plan.inv_c_act, tag="radial_mlp_fwd", tf32x3=model.tensor_cores)
+        if not fused:
+            w_t = torch.empty((n_live, Et), **f32)
+            _mm(Et, n_live, fan, 1.0 / math.sqrt(fan), a, 0, fan, wexp, st["W4L"].off, n_live, w_t, 0, Et, tc=True,
+                pro=pro, pro_scale=plan.inv_c_act, tag="radial_mlp_fwd", tf32x3=model.tensor_cores)
         A = torch.empty((Nt, d_live), **f32)
         ops.tpconv_fwd(tp_id, pg.rowptr, pg.src, pg.geom, w_t, xt, Nt, agg, A, d_live)
         z = torch.empty((Nt, plan.d_z), **f32)
@@ -577,7 +610,7 @@ def _forward(model: NequIP, plan: _Plan, theta: torch.Tensor, pg: PreparedGraph,
                          plan.inv_c_gate, g)
             _mm(Nt, D, plan.d_g, 1.0, g, 0, plan.d_g, wexp, st["W3"].off, D, hn, 0, D)
         if save:
-            saved["steps"].append(dict(h=h, xt=xt, Zs=Zs, w_t=w_t, A=A, z=z, g=g))
+            saved["steps"].append(dict(h=h, xt=xt, Zs=Zs, w_t=w_t, A=A, z=z, g=g, stash=stash))
         h = hn
     saved["h_final"] = h
     if model.task == "node":
@@ -721,11 +754,17 @@ def _backward(model: NequIP, plan: _Plan, theta: torch.Tensor, pg: PreparedGraph
         nh = len(mlp) - 1
         _, fan, _ = mlp[-1]
         al = 1.0 / math.sqrt(fan)
-        a_last, pro_last = (Zs[-1], 1) if nh > 0 else (pg.radial, 0)
+        fused = _fused_radial_ok(model, plan)
+        if fused:
+            ops.radial_mlp_bwd(pg.geom, model.n_radial_basis, model.r_cutoff, _radial_weights(theta, wexp, st, n_live),
+                               n_live, plan.inv_c_act, dw_t, _radial_weights(gtheta, gwexp, st, n_live),
+                               z_stash=sv["stash"], radial=pg.radial if sv["stash"] is not None else None)
+        a_last, pro_last = (Zs[-1], 1) if nh > 0 and not fused else (pg.radial, 0)
         # dW4L = al * act(Z_last)^T @ dw_t^T
-        _mm(fan, n_live, Et, al, a_last, 0, fan, dw_t, 0, Et, gwexp, st["W4L"].off, n_live, ta=True, tb=True,
-            pro=pro_last, pro_scale=plan.inv_c_act, tag="radial_mlp_bwd", tf32x3=model.tensor_cores)
-        if nh > 0:
+        if not fused:
+            _mm(fan, n_live, Et, al, a_last, 0, fan, dw_t, 0, Et, gwexp, st["W4L"].off, n_live, ta=True, tb=True,
+                pro=pro_last, pro_scale=plan.inv_c_act, tag="radial_mlp_bwd", tf32x3=model.tensor_cores)
+        if nh > 0 and not fused:
             dZ = torch.empty((Et, fan), **f32)
             _mm(Et, fan, n_live, al, dw_t, 0, Et, wexp, st["W4L"].off, n_live, dZ, 0, fan, ta=True, tb=True,
                 epi=2, aux=Zs[-1], ld_aux=fan, epi_scale=plan.inv_c_act, tag="radial_mlp_bwd", tf32x3=model.tensor_cores)

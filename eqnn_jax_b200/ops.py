@@ -236,14 +236,19 @@ def _weight_ptrs(weights):
     return ptrs, lds
 
 
-def radial_mlp_fwd(geom, n_rb, r_cut, weights, n_out, act_scale, w_t):
+def radial_mlp_stash(n_edges, n_hidden, device):
+    """Buffer for the pre-activations the forward kernel keeps for the backward pass."""
+    return torch.empty((lib().eqnn_radial_mlp_stash_bytes(n_edges, n_hidden) // 4,), dtype=_F32, device=device)
+
+
+def radial_mlp_fwd(geom, n_rb, r_cut, weights, n_out, act_scale, w_t, z_stash=None):
     """geom [E, 4] (r_hat, d) -> w_t [n_out, E]; weights = [(tensor, offset, ld)] for the hidden layers + the output layer."""
     E = geom.shape[0]
     ptrs, lds = _weight_ptrs(weights)
     t0 = TIMER.begin() if TIMER else None
     check(lib().eqnn_radial_mlp_fwd(C.c_void_p(geom.data_ptr() + 12), 4, E, n_rb, float(r_cut), len(weights) - 1, 128,
-                                    ptrs, lds, n_out, float(act_scale), _ptr(w_t), w_t.shape[1], _stream()),
-          "radial_mlp_fwd")
+                                    ptrs, lds, n_out, float(act_scale), _ptr(w_t), w_t.shape[1], _ptr(z_stash),
+                                    _stream()), "radial_mlp_fwd")
     if TIMER:
         TIMER.end("radial_mlp_fwd", t0)
 
@@ -251,8 +256,9 @@ def radial_mlp_fwd(geom, n_rb, r_cut, weights, n_out, act_scale, w_t):
 _RMLP_WS = GemmWorkspace()
 
 
-def radial_mlp_bwd(geom, n_rb, r_cut, weights, n_out, act_scale, dw_t, grad_weights):
-    """Weight gradients of the radial MLP from dw_t [n_out, E]; grad_weights = [(tensor, offset, ld)] like weights."""
+def radial_mlp_bwd(geom, n_rb, r_cut, weights, n_out, act_scale, dw_t, grad_weights, z_stash=None, radial=None):
+    """Weight gradients of the radial MLP from dw_t [n_out, E]; grad_weights = [(tensor, offset, ld)] like weights.
+    With z_stash (from radial_mlp_fwd) and radial (edge_geom) the activations are not recomputed."""
     E = geom.shape[0]
     ptrs, lds = _weight_ptrs(weights)
     gptrs, glds = _weight_ptrs(grad_weights)
@@ -261,8 +267,8 @@ def radial_mlp_bwd(geom, n_rb, r_cut, weights, n_out, act_scale, dw_t, grad_weig
     ws, ws_bytes = _RMLP_WS.get(need, geom.device)
     t0 = TIMER.begin() if TIMER else None
     check(lib().eqnn_radial_mlp_bwd(C.c_void_p(geom.data_ptr() + 12), 4, E, n_rb, float(r_cut), len(weights) - 1, 128,
-                                    ptrs, lds, n_out, float(act_scale), _ptr(dw_t), dw_t.shape[1], gptrs, ws, ws_bytes,
-                                    _stream()), "radial_mlp_bwd")
+                                    ptrs, lds, n_out, float(act_scale), _ptr(dw_t), dw_t.shape[1], _ptr(z_stash),
+                                    _ptr(radial), gptrs, ws, ws_bytes, _stream()), "radial_mlp_bwd")
     if TIMER:
         TIMER.end("radial_mlp_bwd", t0)
 

@@ -370,15 +370,21 @@ int eqnn_radial_mlp_supported(int n_rb, int d_hidden, int n_hidden, int n_out);
  * (overwritten).  A chain kernel recomputes the activations from d in tensor memory and runs the data-gradient
  * chain dL/dz_l = (dL/dz_{l+1} @ W_{l+1}^T) * gelu'(z_l) without leaving the SM; it emits gelu(z_l) and dL/dz_l once
  * (the operands of the weight-gradient GEMMs, which run on the tcgen05 weight-gradient kernel with the edge axis as K).
- * Nothing is kept from the forward pass.  ws: eqnn_radial_mlp_bwd_workspace_bytes. */
+ * Two variants: with z_stash (written by eqnn_radial_mlp_fwd) and radial (the Bessel basis [n_edges][n_rb] of
+ * eqnn_edge_geom) only the data-gradient chain runs, two tiles in flight like the forward kernel; with z_stash = NULL
+ * nothing is kept from the forward pass and the activations are recomputed from d (radial is then unused).
+ * ws: eqnn_radial_mlp_bwd_workspace_bytes. */
 size_t eqnn_radial_mlp_bwd_workspace_bytes(int64_t n_edges, int n_rb, int n_hidden);
 int eqnn_radial_mlp_bwd(const float* dist, int64_t dist_stride, int64_t n_edges, int n_rb, double r_cut, int n_hidden,
                         int d_hidden, const float* const* weights, const int64_t* ldw, int n_out, float act_scale,
-                        const float* dw_t, int64_t ld_dwt, float* const* grad_weights, void* ws, size_t ws_bytes,
-                        eqnn_stream_t stream);
+                        const float* dw_t, int64_t ld_dwt, const float* z_stash, const float* radial,
+                        float* const* grad_weights, void* ws, size_t ws_bytes, eqnn_stream_t stream);
 int eqnn_radial_mlp_fwd(const float* dist, int64_t dist_stride, int64_t n_edges, int n_rb, double r_cut, int n_hidden,
                         int d_hidden, const float* const* weights, const int64_t* ldw, int n_out, float act_scale,
-                        float* w_t, int64_t ld_wt, eqnn_stream_t stream);
+                        float* w_t, int64_t ld_wt, float* z_stash, eqnn_stream_t stream);
+/* z_stash (optional, eqnn_radial_mlp_stash_bytes, 16-byte aligned): the forward kernel also writes the n_hidden
+ * pre-activation matrices z_l for the backward pass (opaque blocked layout; 512 bytes per edge and hidden layer). */
+size_t eqnn_radial_mlp_stash_bytes(int64_t n_edges, int n_hidden);
 
 /* ---- parameter plumbing ----------------------------------------------------------------
  * dst[t] = idx[t] < 0 ? 0 : scale[t] * params[idx[t]]     (Linear -> dense matrix, live columns)

@@ -45,16 +45,16 @@ def main():
     fl = 2.0 * sum(dims[i] * dims[i + 1] for i in range(len(dims) - 1)) * E
     print(f"radial_mlp_fwd: {ms:.3f} ms for {E} edges  ({E / ms / 1e6:.2f} G edges/s, {fl / ms / 1e9:.1f} TFLOP/s algorithmic, "
           f"{3 * fl / ms / 1e9:.1f} executed fp16)")
-    if True:
-        dw_t = torch.randn((n_out, E), device="cuda", generator=g) * 1e-4
-        gw = [(torch.empty_like(W), 0, W.shape[1]) for W in Ws]
-        ms = timeit(lambda: ops.radial_mlp_bwd(geom, n_rb, r_cut, wl, n_out, act, dw_t, gw), flush=flush)
-        print(f"radial_mlp_bwd: {ms:.3f} ms for {E} edges")
-        ops.TIMER = None
-        import ctypes as C
-        from eqnn_jax_b200._lib import lib
-        # the chain kernel alone: time the whole call minus the GEMMs is not separable here; use the launch counter + events
-
+    dw_t = torch.randn((n_out, E), device="cuda", generator=g) * 1e-4
+    gw = [(torch.empty_like(W), 0, W.shape[1]) for W in Ws]
+    stash = ops.radial_mlp_stash(E, n_hidden, geom.device)
+    ms = timeit(lambda: ops.radial_mlp_fwd(geom, n_rb, r_cut, wl, n_out, act, w_t, z_stash=stash), flush=flush)
+    print(f"radial_mlp_fwd + z stash: {ms:.3f} ms")
+    radial = ops.edge_features(torch.cat([geom[:, 3:4], torch.zeros_like(geom[:, :2])], dim=1).contiguous(), n_rb, r_cut)
+    ms = timeit(lambda: ops.radial_mlp_bwd(geom, n_rb, r_cut, wl, n_out, act, dw_t, gw, z_stash=stash, radial=radial), flush=flush)
+    print(f"radial_mlp_bwd (stash): {ms:.3f} ms for {E} edges")
+    ms = timeit(lambda: ops.radial_mlp_bwd(geom, n_rb, r_cut, wl, n_out, act, dw_t, gw), flush=flush)
+    print(f"radial_mlp_bwd (recompute): {ms:.3f} ms for {E} edges")
 
 
 if __name__ == "__main__":

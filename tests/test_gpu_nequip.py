@@ -331,3 +331,90 @@ def test_train_step_runs_for_every_model_family(family):
     losses = [float(train_step(state, x, y, k, pbc).item()) for _ in range(12)]
     assert np.isfinite(losses).all()
     assert losses[-1] < losses[0]
+
+
+# --------------------------------------------------------------------------------------------------------------
+# The benchmarked models on the route bench.py times: d_hidden 128, 64 Bessel functions, 3 radial layers,
+# 4 message-passing steps (train_cosmology.py:123-134), enough edges for every tensor-core kernel to engage.
+# Tolerance contract: max|got - want| <= 1e-5 * scale + 4 * floor per tensor, where scale is
+# the largest magnitude in the tensor's Flax module (a 1x1 weight whose gradient is a cancelling sum is judged
+# against its module, as in the tests above) and the per-tensor numbers are written to a report; floor =
+# max|oracle_fp32 - oracle_fp64| of that tensor is what a plain fp32 evaluation of the reference's own
+# arithmetic deviates from exact arithmetic (self-loop edges drive the first radial layer to |z| ~ 1e3, where
+# gelu' turns rounding of z into relative errors far above 1e-5 in ANY fp32 implementation).
+# --------------------------------------------------------------------------------------------------------------
+def _floor32(cfg, tree, g, irreps, cot):
+    p = NQ.to_torch(tree, torch.float32, requires_grad=True)
+    gt = g._replace(nodes=torch.tensor(g.nodes, dtype=torch.float32))
+    out = NQ.apply_batched(p, cfg, gt, irreps)
+    val = out.nodes if cfg.task == "node" else out
+    (val * torch.tensor(cot, dtype=torch.float32)).sum().backward()
+    return val.detach().double().numpy(), p
+
+
+@pytest.mark.parametrize("lmax,N,k,task,backward", [
+    (2, 512, 20, "graph", "stash"),        # cfg-2 model (bench.py MODEL_KW)
+    (2, 512, 20, "graph", "recompute"),
+    (3, 256, 32, "graph", "stash"),        # cfg-5 model
+    (2, 300, 16, "node", "stash"),
+])
+def test_bench_model_on_fused_tensor_core_route(lmax, N, k, task, backward):
+    import os
+    from eqnn_jax_b200 import ops
+    from eqnn_jax_b200.nequip import NequIP
+    rng = np.random.default_rng(100 * lmax + N)
+    B = 2
+    x = rng.normal(size=(B, N, 7)).astype(np.float32)
+    x[..., :3] = rng.uniform(-1.7, 1.7, size=(B, N, 3))
+    kw = dict(d_hidden=128, l_max=lmax, sphharm_norm="integral", message_passing_steps=4, n_layers=3, n_outputs=2,
+              n_radial_basis=64, r_cutoff=0.6, message_passing_agg="mean", task=task)
+    cfg, tree, g, model, gg, params = _setup(kw, x, k, seed=7)
+    model = NequIP(**kw, radial_mlp_backward=backward)
+    assert B * N * k >= 4096
+    cot = rng.normal(size=(B, N, 7) if task == "node" else (B, 2))
+    want, grads = _oracle(cfg, tree, g, IRR, cot)
+    want32, grads32 = _floor32(cfg, tree, g, IRR, cot)
+    ops.TIMER = ops.KernelTimer()
+    try:
+        out = model.forward_backward(params, gg, lambda o: torch.tensor(cot, dtype=torch.float32).cuda().reshape(o.shape))
+        tags = ops.TIMER.summary()
+    finally:
+        ops.TIMER = None
+    # the route: one fused radial-MLP kernel per message-passing step and direction, no per-layer radial GEMM
+    assert tags.get("radial_mlp_fwd", (0, 0))[0] == 4 and tags.get("radial_mlp_bwd", (0, 0))[0] == 4, tags
+    got = out.reshape(want.shape).cpu().numpy()
+    rows = []
+
+    def check(name, a, b, b32, mscale=None):
+        scale = np.abs(b).max()
+        floor = np.abs(b32 - b).max()
+        err = np.abs(a - b).max()
+        mscale = scale if mscale is None else mscale
+        rows.append(f"{name:60s} max|want| {scale:9.3e}  err/max|want| {err / max(scale, 1e-300):8.2e}  "
+                    f"err/module-scale {err / max(mscale, 1e-300):8.2e}  fp32-floor/max|want| {floor / max(scale, 1e-300):8.2e}")
+        return err <= RTOL * mscale + 4 * floor, name
+
+    bad = []
+    ok, nm = check("output", got, want, want32)
+    if not ok:
+        bad.append(nm)
+    gt = params.grad_tree
+    leaves32 = dict(_leaves(grads32))
+    ms = _module_scales(grads)
+    for path, w in _leaves(grads):
+        a = gt
+        for q_ in path:
+            a = a[q_]
+        wn = w.grad.numpy()
+        if np.abs(wn).max() == 0:
+            assert float(a.abs().max()) == 0.0, path
+            continue
+        ok, nm = check("grad " + "/".join(path), a.cpu().numpy().astype(np.float64), wn, leaves32[path].grad.double().numpy(),
+                       ms[path[0]])
+        if not ok:
+            bad.append(nm)
+    report = "\n".join(rows)
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open(f"gpurun_out/parity_nequip_lmax{lmax}_N{N}_k{k}_{task}_{backward}.txt", "w") as fh:
+        fh.write(report + "\n")
+    assert not bad, "tensors outside the contract: " + ", ".join(bad) + "\n" + report

@@ -1,6 +1,7 @@
 """Fused radial MLP (eqnn_radial_mlp_fwd / _bwd) against the fp64 oracle restatement of models/nequip.py:55-68.
 
-Tolerance: 1e-5 of the largest magnitude of each output tensor (north_star: fp32 features within 1e-5 relative)."""
+Tolerance: 1e-5 of the largest magnitude of each output tensor (north_star: fp32 features within 1e-5 relative);
+gradients additionally get 4x the deviation of a plain fp32 evaluation from fp64."""
 import math
 
 import numpy as np
@@ -73,13 +74,14 @@ def test_radial_mlp_fwd_rejects_unsupported_shapes():
 
 
 @pytest.mark.parametrize("E,n_rb,n_hidden,n_out,gmag", [
-    (128 * 148 + 77, 64, 3, 8, 1e-6),     # cfg-2 model; tiny gradients exercise the power-of-two scale
+    (128 * 148 * 2 + 77, 64, 3, 8, 1e-6), # cfg-2 model; tiny gradients exercise the power-of-two scale
     (4096, 64, 3, 8, 1.0),
     (5000, 32, 2, 11, 3e3),
     (4200, 16, 1, 16, 1e-3),
     (300, 64, 3, 8, 1.0),                  # below the tensor-core weight-gradient threshold (CUDA-core GEMMs)
 ])
-def test_radial_mlp_bwd_matches_oracle(E, n_rb, n_hidden, n_out, gmag):
+@pytest.mark.parametrize("variant", ["stash", "recompute"])
+def test_radial_mlp_bwd_matches_oracle(E, n_rb, n_hidden, n_out, gmag, variant):
     from eqnn_jax_b200 import ops
     from eqnn_jax_b200.nequip import normalize_constant
     r_cut = 0.6
@@ -92,8 +94,16 @@ def test_radial_mlp_bwd_matches_oracle(E, n_rb, n_hidden, n_out, gmag):
     geom[:, 3] = torch.tensor(d, device="cuda")
     Wd = [torch.tensor(W, device="cuda") for W in Ws]
     gW = [torch.full_like(W, float("nan")) for W in Wd]
-    ops.radial_mlp_bwd(geom, n_rb, r_cut, [(W, 0, W.shape[1]) for W in Wd], n_out, act_scale,
-                       torch.tensor(dw, device="cuda"), [(g, 0, g.shape[1]) for g in gW])
+    wl = [(W, 0, W.shape[1]) for W in Wd]
+    stash = radial = None
+    if variant == "stash":
+        # what the forward pass leaves behind: the pre-activations (fused kernel) and the Bessel basis (eqnn_edge_geom)
+        stash = ops.radial_mlp_stash(E, n_hidden, geom.device)
+        w_t = torch.empty((n_out, E), dtype=torch.float32, device="cuda")
+        ops.radial_mlp_fwd(geom, n_rb, r_cut, wl, n_out, act_scale, w_t, z_stash=stash)
+        radial = ops.edge_features(torch.cat([geom[:, 3:4], torch.zeros_like(geom[:, :2])], dim=1).contiguous(), n_rb, r_cut)
+    ops.radial_mlp_bwd(geom, n_rb, r_cut, wl, n_out, act_scale, torch.tensor(dw, device="cuda"),
+                       [(g, 0, g.shape[1]) for g in gW], z_stash=stash, radial=radial)
     torch.cuda.synchronize()
     # oracle: autograd through the fp64 restatement
     from oracle import e3nn_ref as R
@@ -104,8 +114,20 @@ def test_radial_mlp_bwd_matches_oracle(E, n_rb, n_hidden, n_out, gmag):
         if l < len(Wt) - 1:
             a = R.gelu_tanh(a) * act_scale
     (a * torch.tensor(dw, dtype=torch.float64).T).sum().backward()
-    for l, (g, W) in enumerate(zip(gW, Wt)):
+    # conditioning floor: the same arithmetic in plain fp32.  The d = 0 and small-d rows of the basis reach 1e2..1e3,
+    # so the pre-activations do too, and gelu' turns their rounding into gradient errors above 1e-5 in any fp32 code.
+    W32 = [torch.tensor(W, dtype=torch.float32, requires_grad=True) for W in Ws]
+    a = R.bessel(torch.tensor(d, dtype=torch.float32), n_rb, r_cut)
+    for l, W in enumerate(W32):
+        a = a @ W / math.sqrt(W.shape[0])
+        if l < len(W32) - 1:
+            a = R.gelu_tanh(a) * act_scale
+    (a * torch.tensor(dw, dtype=torch.float32).T).sum().backward()
+    for l, (g, W, w32) in enumerate(zip(gW, Wt, W32)):
         got, want = g.double().cpu(), W.grad
         assert torch.isfinite(got).all(), f"layer {l}: non-finite gradient"
-        err = float((got - want).abs().max() / want.abs().max())
-        assert err < TOL, f"radial MLP weight gradient, layer {l}: {err:.2e}"
+        scale = float(want.abs().max())
+        err = float((got - want).abs().max())
+        floor = float((w32.grad.double() - want).abs().max())
+        assert err <= TOL * scale + 4 * floor, \
+            f"radial MLP weight gradient, layer {l}: err {err / scale:.2e}, fp32 floor {floor / scale:.2e} (of max|want|)"
