@@ -28,7 +28,9 @@ __device__ __forceinline__ uint32_t cvt_h2(float a0, float a1) {
 __device__ __forceinline__ void split_h2(float a0, float a1, uint32_t& hi, uint32_t& lo) {
   hi = cvt_h2(a0, a1);
   const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
-  lo = cvt_h2(a0 - hf.x, a1 - hf.y);
+  float l0, l1;
+  upk2(fma2(pk2(hf.x, hf.y), pk2(-1.f, -1.f), pk2(a0, a1)), l0, l1);   // a - hi: exact in fp32
+  lo = cvt_h2(l0, l1);
 }
 
 // ---- tensor memory stores: thread i of the warp writes lane (warp % 4) * 32 + i, N consecutive columns -------
@@ -122,6 +124,50 @@ __device__ __forceinline__ float sin_reduced(float x) {
   c = fmaf(c, z, 1.0f);
   float v = (q & 1) ? c : s;
   return (q & 2) ? -v : v;
+}
+
+// the same for a pair of arguments, on packed fp32x2 arithmetic (the reduction and both polynomials are FMA chains)
+__device__ __forceinline__ void sin_reduced2(f32x2 x, float& s0, float& s1) {
+  const f32x2 magic = pk2(12582912.0f, 12582912.0f);
+  const f32x2 t = fma2(x, pk2(0.636619747f, 0.636619747f), magic);
+  float tq0, tq1;
+  upk2(t, tq0, tq1);
+  const f32x2 n = add2(t, pk2(-12582912.0f, -12582912.0f));
+  f32x2 r = fma2(n, pk2(-1.57079601e+00f, -1.57079601e+00f), x);
+  r = fma2(n, pk2(-3.13916473e-07f, -3.13916473e-07f), r);
+  r = fma2(n, pk2(-5.39030253e-15f, -5.39030253e-15f), r);
+  const f32x2 z = mul2(r, r);
+  f32x2 s = fma2(pk2(-1.95152959e-4f, -1.95152959e-4f), z, pk2(8.33216087e-3f, 8.33216087e-3f));
+  s = fma2(s, z, pk2(-1.66666546e-1f, -1.66666546e-1f));
+  s = fma2(mul2(s, z), r, r);
+  f32x2 c = fma2(pk2(2.44331571e-5f, 2.44331571e-5f), z, pk2(-1.38873163e-3f, -1.38873163e-3f));
+  c = fma2(c, z, pk2(4.16666457e-2f, 4.16666457e-2f));
+  c = fma2(c, z, pk2(-0.5f, -0.5f));
+  c = fma2(c, z, pk2(1.0f, 1.0f));
+  float sa, sb, ca, cb;
+  upk2(s, sa, sb);
+  upk2(c, ca, cb);
+  const int q0 = __float_as_int(tq0), q1 = __float_as_int(tq1);
+  const float v0 = (q0 & 1) ? ca : sa, v1 = (q1 & 1) ? cb : sb;
+  s0 = (q0 & 2) ? -v0 : v0;
+  s1 = (q1 & 2) ? -v1 : v1;
+}
+
+// 16 basis functions j0 + 1 .. j0 + 16 of one edge: pref * sin(fl(w_j d)) / d (w_j at d = 0), as fp32 values
+__device__ __forceinline__ void bessel16(const float* __restrict__ wfreq, int j0, float d, float pref, float* v) {
+  const float inv_d = (d == 0.f) ? 0.f : __fdiv_rn(1.0f, d);
+  const f32x2 d2 = pk2(d, d), sc = pk2(pref * inv_d, pref * inv_d);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float w0 = wfreq[j0 + 2 * j], w1 = wfreq[j0 + 2 * j + 1];
+    float s0, s1;
+    sin_reduced2(mul2(pk2(w0, w1), d2), s0, s1);            // mul.rn: the reference's fp32-rounded phase
+    upk2(mul2(pk2(s0, s1), sc), v[2 * j], v[2 * j + 1]);
+    if (d == 0.f) {
+      v[2 * j] = __fmul_rn(pref, w0);
+      v[2 * j + 1] = __fmul_rn(pref, w1);
+    }
+  }
 }
 
 }  // namespace rmlp
