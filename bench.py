@@ -60,9 +60,30 @@ def peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, which="fallback")
 
 
-# measured with `ncu --set full` on this code (profiles/r1c_*_raw.csv): DRAM read + write bytes per edge and step
-NCU_MLP_DRAM_BYTES = 10788       # algorithmic: 10848
-NCU_TPCONV_DRAM_BYTES = 150.6    # fwd 55.9 + bwd 94.7; algorithmic: 45.6 + 79.0 (the 32-byte dL/dx_t records are re-read)
+def ncu_traffic():
+    """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum of `ncu --set full`) per edge of the kernels of one
+    message-passing step, from the committed capture profiles/ncu_traffic.json (written by profiles/traffic.py from an
+    .ncu-rep of THIS bench command).  The file records the tree it was taken on; bench.py reports it next to the
+    number and returns None when the capture is missing -- nothing is hard-coded."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return None
+    return json.load(open(p))
+
+
+def traffic_of(tr, workload, patterns, edges):
+    """Sum over the kernels whose name contains one of `patterns`: bytes per edge (all launches of one message-passing
+    step) and the number of launches; None when the capture does not cover the workload."""
+    if tr is None or workload not in tr.get("workloads", {}):
+        return None
+    w = tr["workloads"][workload]
+    tot, n = 0.0, 0
+    for k, v in w["kernels"].items():
+        if any(pt in k for pt in patterns):
+            tot += v["dram_bytes_per_edge_step"]
+            n += v["launches_per_step"]
+    return {"bytes_per_edge_step": tot, "launches_per_step": n, "per_launch": tot * edges / max(n, 1),
+            "source": f"profiles/ncu_traffic.json ({w['capture']}, tree {tr.get('tree', '?')})"} if n else None
 
 
 def algorithmic(n_live, d_live, d_in=7, k=K_NN, n_rb=64, H=128, L=3):
@@ -170,6 +191,8 @@ EGNN_KW = dict(message_passing_steps=4, d_hidden=128, n_layers=3, activation="ge
                readout_agg="mean", mlp_readout_widths=(4, 2, 2), task="graph", n_outputs=2, n_radial_basis=32,
                r_max=0.6)                                                   # train_cosmology.py:67-81,403-408
 FAMILIES = {
+    # cpu_nodes: the CPU arm's cloud; the SEGNN restatement needs minutes per step at 5000 nodes, so it runs 1000-node
+    # clouds (edges/s is per-edge normalised) and the line says so (same_config false)
     "segnn": dict(metric="SEGNN fwd+bwd edges/sec", graphs=8, cpu_nodes=1000,
                   name="SEGNN l_max_hidden 2, attributes l<=1, 3 steps x 3 layers, node task -> 1x1o, 5000-node kNN-20 "
                        "PBC clouds (cfg-3)"),
@@ -419,7 +442,8 @@ def run_family(args):
             "breakdown_ms_per_step": {k: t for k, (c, t) in sorted(prof.items())}}
     if world == 1 and not args.no_cpu_baseline:
         val, _, threads, sample = cpu_family_baseline(kind, fam["cpu_nodes"], 2)
-        line["cpu_baseline"] = {"value": val, "unit": "edges/s", "cores": threads, "kind": "port", "sample": sample}
+        line["cpu_baseline"] = {"value": val, "unit": "edges/s", "cores": threads, "kind": "port", "sample": sample,
+                                "same_config": fam["cpu_nodes"] == N_NODES}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -436,7 +460,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--graphs-per-gpu", type=int, default=32)   # train_cosmology.py:648 batch_size
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--profile-steps", type=int, default=2)
+    ap.add_argument("--profile-steps", type=int, default=2)     # 0: skip the instrumented pass (ncu captures)
     # cfg2 = the workload BASELINE.json quotes the metric on (default); cfg5 = its large-graph scaling case
     # (50 000-node clouds, k = 32, l_max = 3), 2 clouds per GPU unless --graphs-per-gpu is given
     # segnn / egnn: the other model families of the path (BASELINE.json configs[2], configs[3]) through the same step
@@ -542,6 +566,14 @@ def main():
         step_resident(i)
     prof = ops.TIMER.summary()
     ops.TIMER = None
+    if args.profile_steps == 0:          # capture runs: the plain line only
+        if rank == 0:
+            print(json.dumps({"metric": "NequIP fwd+bwd edges/sec", "value": world * E_step * args.steps / (ms * 1e-3),
+                              "unit": "edges/s", "ms_per_step": ms / args.steps, "gpu_launches": int(launches),
+                              "edges_per_gpu_step": E_step, "note": "capture run (--profile-steps 0)"}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -561,9 +593,24 @@ def main():
     mlp_ms_step = (n_f * ms_mf + n_b * ms_mb) / args.profile_steps
     mlp_flops_step = E_step * steps_mp * (f_fwd + f_bwd)
     mlp_tf = mlp_flops_step / (mlp_ms_step * 1e-3) / 1e12 if mlp_ms_step > 0 else float("nan")
-    mlp_bytes = (256 + 512) + 2 * 1024 + (512 + 4 * n_live) + (4 * n_live + 1024) + 2 * 1536 + \
-                (512 + 4 * n_live) + 2 * 1024 + (256 + 512)
+    fused = model.fuse_radial_mlp and ops.radial_mlp_supported(MODEL_KW["n_radial_basis"], MODEL_KW["d_hidden"],
+                                                               MODEL_KW["n_layers"], n_live)
+    stash = fused and model.radial_mlp_backward == "stash"
+    H = MODEL_KW["n_layers"]
+    if fused:
+        # bytes the present design moves per edge and message-passing step:
+        #   forward  d (4) + w_t (4 n) [+ z stash 512 H]
+        #   backward dw (4 n) + z stash in / g out (2 x 512 H) | recompute: activations + gradients out (256 + 1024 H)
+        #   weight gradients: basis 256 + z (or activations) 512 H + g 512 H + dw 4 n
+        mlp_bytes = (4 + 4 * n_live + (512 * H if stash else 0)) + (4 * n_live + (1024 * H if stash else 256 + 1024 * H)) + \
+                    (256 + 1024 * H + 4 * n_live)
+    else:
+        mlp_bytes = (256 + 512) + 2 * 1024 + (512 + 4 * n_live) + (4 * n_live + 1024) + 2 * 1536 + \
+                    (512 + 4 * n_live) + 2 * 1024 + (256 + 512)
     mlp_gbs = E_step * steps_mp * mlp_bytes / (mlp_ms_step * 1e-3) / 1e9 if mlp_ms_step > 0 else float("nan")
+    tr = ncu_traffic()
+    tr_mlp = traffic_of(tr, args.workload, ("rmlp_", "tc_wgrad", "tc_rowgemm", "absmax", "wgrad_reduce"), E_step)
+    tr_tp = traffic_of(tr, args.workload, ("tpconv_fwd", "tpconv_bwd", "sender_reduce", "segment_gather"), E_step)
     _, ms_tf = per_launch("tpconv_fwd")
     _, ms_tb = per_launch("tpconv_bwd")
     tp_gbs = E_step * (b_fwd + b_bwd) / ((ms_tf + ms_tb) * 1e-3) / 1e9
@@ -585,30 +632,36 @@ def main():
                 "h2d_bytes_per_step": int(hbuf.numel() * 4 + ybuf.numel() * 4), "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        # dominant kernels = the per-edge radial MLP GEMMs.  Their arithmetic intensity (3 tf32 MMAs per product:
-        # 3*(f_fwd+f_bwd)/mlp_bytes ~ 65 flop/B) is below the tf32 ridge of a B200 (~1100 TF/s / 7.7 TB/s ~ 143
-        # flop/B), so the bound is HBM; the tensor-pipe view of the same launches is kept beside it.
-        "roofline": {"kernel": "radial MLP GEMMs fwd+dgrad+wgrad (tc_rowgemm_kernel / tc_wgrad_kernel, tcgen05 "
-                               "kind::tf32 x3): stream the per-edge activations layer by layer", "bound": "hbm",
-                     "achieved": mlp_gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": mlp_gbs / pk["hbm"],
-                     # DRAM bytes (read + write) of the same kernels under `ncu --set full`, per edge and step, summed over
-                     # the 11 GEMMs of one message-passing step (profiles/r1c_tc_microbench_raw.csv; that capture aliases the
-                     # dgrad kernel's aux operand with A, so its 512 B/edge are added); given per average launch
-                     "traffic": NCU_MLP_DRAM_BYTES * E_step * steps_mp / max((n_f + n_b) / args.profile_steps, 1),
-                     "traffic_bytes_per_edge_step": NCU_MLP_DRAM_BYTES, "peak_source": f"hbm_gbs of {pk['which']}",
-                     "bytes_per_edge_step": mlp_bytes, "launches_per_step": (n_f + n_b) / args.profile_steps,
-                     "ms_per_step": mlp_ms_step,
-                     "note": "algorithmic traffic: fwd 256+512 | 2x(512+512) | 512+4n ; dgrad 4n+512+512 | "
-                             "2x(3x512) ; wgrad 512+4n | 2x1024 | 256+512 bytes per edge"},
-        "roofline_mlp_tensor": {"kernel": "same launches, tensor-pipe view (algorithmic flops, 1 per product)",
-                                "bound": "tensor", "achieved": mlp_tf, "peak": pk["tf_sust"], "unit": "TFLOP/s",
-                                "frac": mlp_tf / pk["tf_sust"], "traffic": None,
-                                "peak_source": f"bf16_tflops_sustained of {pk['which']}",
-                                "flops_per_edge_step": f_fwd + f_bwd},
+        # dominant kernels = the radial MLP (tensor-core bound dense contraction).  `achieved` counts
+        # the ALGORITHMIC flops (one per product: 2 (n_rb H + (L-1) H^2 + H n_live) forward, twice that minus the first
+        # layer's data gradient backward); the kernels issue three fp16 MMAs per product (hi*hi + lo*hi + hi*lo, fp32-class
+        # accuracy), so their own ceiling is peak / 3.  The HBM view of the same launches is kept beside it.
+        "roofline": {"kernel": ("fused radial MLP: rmlp_fwd_kernel (Bessel + all layers, activations in tensor memory) + "
+                                "rmlp_dgrad_kernel (data-gradient chain) + tc_wgrad_kernel x4; tcgen05 kind::f16 / kind::tf32, "
+                                "3 MMAs per product") if fused else
+                               "radial MLP GEMMs fwd+dgrad+wgrad (tc_rowgemm_kernel / tc_wgrad_kernel, tcgen05 kind::tf32 x3)",
+                     "bound": "tensor", "achieved": mlp_tf, "peak": pk["tf_sust"], "unit": "TFLOP/s",
+                     "frac": mlp_tf / pk["tf_sust"],
+                     "traffic": tr_mlp["per_launch"] if tr_mlp else None,
+                     "traffic_source": tr_mlp["source"] if tr_mlp else "no ncu capture of this workload committed",
+                     "traffic_bytes_per_edge_step": tr_mlp["bytes_per_edge_step"] if tr_mlp else None,
+                     "peak_source": f"bf16_tflops_sustained of {pk['which']}",
+                     "flops_per_edge_step": f_fwd + f_bwd, "executed_mma_per_product": 3,
+                     "launches_per_step": (n_f + n_b) / args.profile_steps, "ms_per_step": mlp_ms_step,
+                     "ms_fwd_per_launch": ms_mf, "ms_bwd_per_call": ms_mb,
+                     "note": "flops per SURVEY.md 8(d).2 with the live output columns; time = CUDA events around "
+                             "every eqnn_radial_mlp_fwd / _bwd call of the instrumented pass"},
+        "roofline_mlp_hbm": {"kernel": "same launches, HBM view (bytes the design moves: forward d + w_t + z stash; "
+                                       "backward z + dw in, g out; weight gradients basis + z + g in)",
+                             "bound": "hbm", "achieved": mlp_gbs, "peak": pk["hbm"], "unit": "GB/s",
+                             "frac": mlp_gbs / pk["hbm"], "bytes_per_edge_step": mlp_bytes,
+                             "traffic": tr_mlp["per_launch"] if tr_mlp else None,
+                             "peak_source": f"hbm_gbs of {pk['which']}"},
         "roofline_tpconv": {"kernel": "tpconv_fwd + tpconv_bwd", "bound": "hbm", "achieved": tp_gbs, "peak": pk["hbm"],
                             "unit": "GB/s", "frac": tp_gbs / pk["hbm"],
-                            "traffic": NCU_TPCONV_DRAM_BYTES * E_step / 2,   # per launch (fwd and bwd averaged), ncu
-                            "traffic_bytes_per_edge_step": NCU_TPCONV_DRAM_BYTES,
+                            "traffic": tr_tp["per_launch"] if tr_tp else None,
+                            "traffic_source": tr_tp["source"] if tr_tp else "no ncu capture of this workload committed",
+                            "traffic_bytes_per_edge_step": tr_tp["bytes_per_edge_step"] if tr_tp else None,
                             "bytes_per_edge_step": b_fwd + b_bwd, "ms_fwd": ms_tf, "ms_bwd": ms_tb,
                             "n_live": n_live, "d_live": d_live, "peak_source": f"hbm_gbs of {pk['which']}"},
         "breakdown_ms_per_step": {k: t / args.profile_steps for k, (n, t) in sorted(prof.items())},
