@@ -67,5 +67,27 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_xla_shim(verbose: bool = False):
+    """Compiles jax_binding/xla_ffi_shim.cc against jaxlib's XLA FFI headers WHEN THEY EXIST (they do not in the
+    build image: returns None there).  The shim links against libeqnn_b200.so and lands next to ffi.py."""
+    try:
+        import jaxlib
+    except Exception:
+        return None
+    inc = os.path.join(os.path.dirname(jaxlib.__file__), "include")
+    if not os.path.exists(os.path.join(inc, "xla", "ffi", "api", "ffi.h")):
+        return None
+    src = os.path.join(HERE, "jax_binding", "xla_ffi_shim.cc")
+    out = os.path.join(HERE, "jax_binding", "libeqnn_xla.so")
+    if _stale(out, [src, LIB]):
+        cmd = ["g++", "-std=c++17", "-O2", "-shared", "-fPIC", "-I" + inc, "-I/usr/local/cuda/include",
+               "-I" + os.path.join(HERE, "..", "include"), src, "-L" + HERE, "-leqnn_b200", "-Wl,-rpath,$ORIGIN/..", "-o", out]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"xla_ffi_shim build failed:\n{r.stdout}\n{r.stderr}")
+    return out
+
+
 if __name__ == "__main__":
     print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print("xla shim:", build_xla_shim() or "skipped (no jaxlib headers)")
