@@ -465,6 +465,12 @@ def main():
     # (50 000-node clouds, k = 32, l_max = 3), 2 clouds per GPU unless --graphs-per-gpu is given
     # segnn / egnn: the other model families of the path (BASELINE.json configs[2], configs[3]) through the same step
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg5", "segnn", "egnn"])
+    # weak: --graphs-per-gpu clouds on every GPU (the driver's scaling runs); strong: the reference's regime, a GLOBAL
+    # batch of --graphs-per-gpu clouds split over the GPUs (train_cosmology.py:283-298: batch 32 over the devices)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    # the rank-local part of the step (graph build, forward, loss, backward) is captured once in a CUDA graph and
+    # replayed -- what jax.jit gives the reference; --no-cuda-graph launches the ~130 kernels one by one
+    ap.add_argument("--no-cuda-graph", action="store_true")
     args = ap.parse_args()
     if args.workload in FAMILIES:
         return run_family(args)
@@ -483,7 +489,7 @@ def main():
     import torch.distributed as dist
     from eqnn_jax_b200 import _lib, graph_utils as GU, ops
     from eqnn_jax_b200.nequip import NequIP
-    from eqnn_jax_b200.train import TrainState, train_step, wrap_nodes
+    from eqnn_jax_b200.train import GraphedTrainStep, TrainState, train_step, wrap_nodes
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -496,6 +502,10 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()
     B = args.graphs_per_gpu
+    if args.scaling == "strong":
+        if B % world:
+            raise SystemExit(f"--scaling strong: a global batch of {B} clouds does not split over {world} GPUs")
+        B //= world
     E_step = B * N_NODES * K_NN
 
     # inputs: two different host batches per rank (pinned), cycled
@@ -533,9 +543,22 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), t0, t1
 
+    graphed, graph_note = None, "off (--no-cuda-graph)"
+    if not args.no_cuda_graph:
+        try:
+            graphed = GraphedTrainStep(state, resident[0][0].shape, resident[0][1].shape, K_NN, apply_pbc, world)
+            graphed.capture(*resident[0])
+            graph_note = "rank-local part of the step replayed from one CUDA graph"
+        except Exception as e:      # keep the measurement: fall back to launching kernel by kernel
+            graphed, graph_note = None, f"capture failed ({type(e).__name__}: {e}); eager launches"
+            torch.cuda.synchronize()
+
+    def run_step(h, y):
+        return graphed(h, y) if graphed is not None else train_step(state, h, y, K_NN, apply_pbc, world)
+
     def step_resident(i):
         h, y = resident[i % 2]
-        train_step(state, h, y, K_NN, apply_pbc, world)
+        run_step(h, y)
 
     hbuf = torch.empty_like(resident[0][0])
     ybuf = torch.empty_like(resident[0][1])
@@ -543,9 +566,12 @@ def main():
 
     def step_e2e(i):
         h, y = host[i % 2]
-        hbuf.copy_(h, non_blocking=True)
-        ybuf.copy_(y, non_blocking=True)
-        loss = train_step(state, hbuf, ybuf, K_NN, apply_pbc, world)
+        if graphed is not None:                         # pinned host memory straight into the graph's input buffers
+            loss = graphed(h, y)
+        else:
+            hbuf.copy_(h, non_blocking=True)
+            ybuf.copy_(y, non_blocking=True)
+            loss = train_step(state, hbuf, ybuf, K_NN, apply_pbc, world)
         loss_host.copy_(loss, non_blocking=True)
         torch.cuda.current_stream().synchronize()      # the reference reads the loss every step (:468)
 
@@ -559,17 +585,24 @@ def main():
     for i in range(2):
         step_e2e(i)
     ms_e2e, _, _ = timed(step_e2e, args.steps)
+    if graphed is not None:
+        # a replayed graph does not pass through the library's launch counter: count one eager step of the same code
+        # (the kernels the graph holds) and add the per-step AdamW launch that stays outside the graph
+        l1 = L.eqnn_launch_count()
+        train_step(state, *resident[0], K_NN, apply_pbc, world)
+        launches = (L.eqnn_launch_count() - l1) * args.steps
 
-    # instrumented pass: per-kernel CUDA-event durations on the launching stream
+    # instrumented pass: per-kernel CUDA-event durations on the launching stream (eager launches)
     ops.TIMER = ops.KernelTimer()
     for i in range(args.profile_steps):
-        step_resident(i)
+        train_step(state, *resident[i % 2], K_NN, apply_pbc, world)
     prof = ops.TIMER.summary()
     ops.TIMER = None
     if args.profile_steps == 0:          # capture runs: the plain line only
         if rank == 0:
             print(json.dumps({"metric": "NequIP fwd+bwd edges/sec", "value": world * E_step * args.steps / (ms * 1e-3),
                               "unit": "edges/s", "ms_per_step": ms / args.steps, "gpu_launches": int(launches),
+                              "n_gpus": world, "scaling": args.scaling, "graphs_per_gpu": B, "cuda_graph": graph_note,
                               "edges_per_gpu_step": E_step, "note": "capture run (--profile-steps 0)"}), flush=True)
         if world > 1:
             dist.destroy_process_group()
@@ -622,9 +655,10 @@ def main():
     line = {
         "metric": "NequIP fwd+bwd edges/sec", "value": value, "unit": "edges/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name,
                    "graphs_per_gpu": B, "edges_per_gpu_step": E_step, "message_passing_steps": steps_mp,
+                   "cuda_graph": graph_note,
                    "step": "kNN graph build + CSR/geometry + forward + MSE + backward + grad all-reduce + AdamW",
                    "l2": "inputs larger than L2 (per-step working set of several GB)",
                    "parallelism": f"dp{world}"},

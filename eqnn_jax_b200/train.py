@@ -100,9 +100,10 @@ def wrap_graph(model, halo_batch: torch.Tensor, senders, receivers, k: int, appl
     raise TypeError(f"no B200 path for model type {type(model).__name__}")
 
 
-def train_step(state: TrainState, halo_batch: torch.Tensor, y_batch: torch.Tensor, k: int,
-               apply_pbc: Optional[GU.ApplyPBC] = None, world_size: int = 1, globals_=None) -> torch.Tensor:
-    """One optimisation step on this rank's shard; returns the (device) mean loss over all ranks."""
+def local_gradients(state: TrainState, halo_batch: torch.Tensor, y_batch: torch.Tensor, k: int,
+                    apply_pbc: Optional[GU.ApplyPBC] = None, globals_=None) -> torch.Tensor:
+    """The rank-local part of a step: kNN graph, forward, MSE, backward.  Gradients and the loss land in state.bucket.
+    No host synchronisation, no host-dependent launch parameter: capturable in a CUDA graph (GraphedTrainStep)."""
     model, params = state.model, state.params
     n = params.flat.numel()
     # build_graph (train_cosmology.py:226-235) also expands |dr| in a Bessel basis into graph.edges, which the
@@ -120,8 +121,63 @@ def train_step(state: TrainState, halo_batch: torch.Tensor, y_batch: torch.Tenso
         return state._gpred
 
     model.forward_backward(params, g, grad_fn)
+    return loss_slot
+
+
+def apply_update(state: TrainState, world_size: int = 1) -> torch.Tensor:
+    """pmean of gradients + loss (one NCCL all-reduce of the flat bucket), then optax.adamw with cosine decay."""
+    params = state.params
+    n = params.flat.numel()
+    loss_slot = state.bucket[n:]
     allreduce_mean_(state.bucket, world_size)
     state.step += 1
     lr = cosine_decay_lr(state.step - 1, state.learning_rate, state.decay_steps)
     ops.adamw(params.flat, params.grad, state.mu, state.nu, lr, 0.9, 0.999, 1e-8, state.weight_decay, state.step)
     return loss_slot
+
+
+def train_step(state: TrainState, halo_batch: torch.Tensor, y_batch: torch.Tensor, k: int,
+               apply_pbc: Optional[GU.ApplyPBC] = None, world_size: int = 1, globals_=None) -> torch.Tensor:
+    """One optimisation step on this rank's shard; returns the (device) mean loss over all ranks."""
+    local_gradients(state, halo_batch, y_batch, k, apply_pbc, globals_)
+    return apply_update(state, world_size)
+
+
+class GraphedTrainStep:
+    """The same step with the rank-local part (about 130 kernel launches for NequIP cfg-2) captured once in a CUDA
+    graph and replayed: one graph launch + the all-reduce + the AdamW launch per step.  What the reference gets from
+    jax.jit (train_cosmology.py:219: the whole step is one XLA executable).  Inputs are copied into static buffers
+    (device-to-device or from pinned host memory); shapes are fixed at construction, like a jitted function's."""
+
+    def __init__(self, state: TrainState, halo_shape, y_shape, k: int, apply_pbc: Optional[GU.ApplyPBC] = None,
+                 world_size: int = 1, warmup: int = 2):
+        self.state, self.k, self.apply_pbc, self.world_size = state, k, apply_pbc, world_size
+        dev = state.params.flat.device
+        self.halos = torch.zeros(tuple(halo_shape), dtype=torch.float32, device=dev)
+        self.y = torch.zeros(tuple(y_shape), dtype=torch.float32, device=dev)
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self._warmup = warmup
+
+    def capture(self, halo_batch: torch.Tensor, y_batch: torch.Tensor) -> None:
+        """Warm up eagerly on a side stream (workspaces reach their final size), then capture."""
+        self.halos.copy_(halo_batch)
+        self.y.copy_(y_batch)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(self._warmup):
+                local_gradients(self.state, self.halos, self.y, self.k, self.apply_pbc)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            local_gradients(self.state, self.halos, self.y, self.k, self.apply_pbc)
+        self.graph = g
+
+    def __call__(self, halo_batch: torch.Tensor, y_batch: torch.Tensor) -> torch.Tensor:
+        if self.graph is None:
+            self.capture(halo_batch, y_batch)
+        self.halos.copy_(halo_batch, non_blocking=True)
+        self.y.copy_(y_batch, non_blocking=True)
+        self.graph.replay()
+        return apply_update(self.state, self.world_size)
