@@ -32,8 +32,8 @@ SIGNATURES: Dict[str, tuple] = {
     "eqnn_csr_workspace_bytes": (_sz, [_i, _i, _i]),
     "eqnn_csr_build": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p, _sz, _p]),
     "eqnn_edge_geom": (_i, [_p, _i, _i, _p, _p, _i, _d, _p, _p, _p]),
-    "eqnn_tpconv_fwd": (_i, [_i, _p, _p, _p, _p, _i64, _p, _i, _i, _p, _i, _p]),
-    "eqnn_tpconv_bwd": (_i, [_i, _p, _p, _p, _p, _p, _i64, _p, _i, _i, _p, _i, _p, _p, _p]),
+    "eqnn_tpconv_fwd": (_i, [_i, _p, _p, _p, _p, _i64, _p, _i, _i, _p, _i, _p, _p]),
+    "eqnn_tpconv_bwd": (_i, [_i, _p, _p, _p, _p, _p, _i64, _p, _i, _i, _p, _i, _p, _p, _p, _p]),
     "eqnn_sender_reduce": (_i, [_p, _i, _i, _i, _p, _p]),
     "eqnn_segment_gather_sum": (_i, [_p, _p, _p, _i, _i, _p, _p]),
     "eqnn_sh_scatter": (_i, [_i, _p, _p, _i, _f, _p, _p]),
@@ -43,10 +43,10 @@ SIGNATURES: Dict[str, tuple] = {
     "eqnn_gemm_f32": (_i, [_i64, _i64, _i64, _f, _p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _i, _i, _f, _i,
                            _p, _i64, _f, _p, _sz, _p]),
     "eqnn_radial_mlp_supported": (_i, [_i, _i, _i, _i]),
-    "eqnn_radial_mlp_fwd": (_i, [_p, _i64, _i64, _i, _d, _i, _i, _p, _p, _i, _f, _p, _i64, _p, _p]),
+    "eqnn_radial_mlp_fwd": (_i, [_p, _i64, _i64, _i, _d, _i, _i, _p, _p, _i, _i, _f, _p, _i64, _p, _p]),
     "eqnn_radial_mlp_stash_bytes": (_sz, [_i64, _i]),
     "eqnn_radial_mlp_bwd_workspace_bytes": (_sz, [_i64, _i, _i]),
-    "eqnn_radial_mlp_bwd": (_i, [_p, _i64, _i64, _i, _d, _i, _i, _p, _p, _i, _f, _p, _i64, _p, _p, _p, _p, _sz, _p]),
+    "eqnn_radial_mlp_bwd": (_i, [_p, _i64, _i64, _i, _d, _i, _i, _p, _p, _i, _i, _f, _p, _i64, _p, _p, _p, _p, _sz, _p]),
     "eqnn_gate_fwd": (_i, [_p, _i64, _i, _i, _i, _p, _p, _f, _f, _p, _p]),
     "eqnn_gate_bwd": (_i, [_p, _p, _i64, _i, _i, _i, _p, _p, _f, _f, _p, _p]),
     "eqnn_node_update_workspace_bytes": (_sz, [_i, _i, _i, _i]),

@@ -43,7 +43,8 @@ struct RmlpP {
   const float* W[RM_MAXL];  // W[l]: element (k, n) at W[l][k * ldw[l] + n]
   int64_t ldw[RM_MAXL];
   float alpha[RM_MAXL];     // 1 / sqrt(fan_in) of layer l
-  float act_scale;          // 1 / c of e3nn.normalize_function(gelu)
+  float act_scale;          // 1 / c of e3nn.normalize_function(activation)
+  int act_kind;             // 0 gelu (tanh form), 1 silu
   float* w_t;               // [n_out][ld_wt] column-major radial weights
   int64_t ld_wt;
   // optional stash of the pre-activations for eqnn_radial_mlp_bwd: z_stash[l - 1] = z_l, l = 1..n_hidden, each
@@ -70,11 +71,11 @@ __host__ __device__ inline float rm_wscale(const float* alpha, float act_scale, 
 // z -> gelu_tanh(z) -> (hi, lo) words, 32 accumulator columns of one row.  (A variant with one reciprocal shared by
 // four sigmoids -- 5 instead of 8 MUFU per four values -- measured 3.5 % slower: the kernel is bound by issue slots
 // and latency, not by the special-function unit.)
-__device__ __forceinline__ void act_split32(const float* v, uint32_t* hiw, uint32_t* low) {
+__device__ __forceinline__ void act_split32(const float* v, const ActC& ac, uint32_t* hiw, uint32_t* low) {
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
     const f32x2 x = pk2(v[2 * j], v[2 * j + 1]);
-    const f32x2 a = mul2(x, gelu_sigmoid2(x, mul2(x, x)));
+    const f32x2 a = mul2(x, act_sigmoid2(x, mul2(x, x), ac));
     float a0, a1;
     upk2(a, a0, a1);
     split_h2(a0, a1, hiw[j], low[j]);
@@ -103,6 +104,7 @@ __global__ void __launch_bounds__(RM_THREADS, 1) rmlp_fwd_kernel(const RmlpP p) 
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int F = p.n_layers;
+  const ActC ac = act_constants(p.act_kind);
 
   // shared-memory map: weight images | bessel frequencies | barriers
   uint32_t w_off[RM_MAXL], w_half[RM_MAXL];
@@ -189,7 +191,7 @@ __global__ void __launch_bounds__(RM_THREADS, 1) rmlp_fwd_kernel(const RmlpP p) 
             if (e < p.E) emit_cols<32>(p.z_stash[l - 1], 1, e, 128, 32 * cg, v);
           }
           uint32_t hiw[16], low[16];
-          act_split32(v, hiw, low);
+          act_split32(v, ac, hiw, low);
           tmem_st16(t, hiw);
           tmem_st16(t + 16, low);
           tmem_st_wait();
@@ -297,17 +299,6 @@ __global__ void absmax_kernel(const float* __restrict__ x, int64_t ld, int rows,
   if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
 }
 
-// x pair -> gelu_tanh(x), gelu_tanh'(x) from one sigmoid
-__device__ __forceinline__ void gelu_both2(f32x2 x, f32x2& g, f32x2& gp) {
-  constexpr float D0 = 2.0f * 0.7978845608028654f, D1 = D0 * 3.0f * 0.044715f;
-  const f32x2 xx = mul2(x, x);
-  const f32x2 sg = gelu_sigmoid2(x, xx);
-  g = mul2(x, sg);
-  const f32x2 w = mul2(x, fma2(xx, pk2(D1, D1), pk2(D0, D0)));
-  const f32x2 q = mul2(sg, fma2(sg, pk2(-1.f, -1.f), pk2(1.f, 1.f)));
-  gp = fma2(q, w, sg);
-}
-
 __global__ void __launch_bounds__(RM_THREADS, 1) rmlp_bwd_kernel(const RmlpBwdP p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -315,6 +306,7 @@ __global__ void __launch_bounds__(RM_THREADS, 1) rmlp_bwd_kernel(const RmlpBwdP 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const RmlpP& f = p.f;
   const int F = f.n_layers, H = F - 1;
+  const ActC ac = act_constants(f.act_kind);
 
   // shared-memory map: weight images | dw operand slabs (hi, lo) | bessel frequencies | barriers
   uint32_t w_off[RM_MAXL], w_half[RM_MAXL];
@@ -427,7 +419,7 @@ __global__ void __launch_bounds__(RM_THREADS, 1) rmlp_bwd_kernel(const RmlpBwdP 
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           f32x2 g2, gp2;
-          gelu_both2(pk2(z[2 * j], z[2 * j + 1]), g2, gp2);
+          act_both2(pk2(z[2 * j], z[2 * j + 1]), ac, g2, gp2);
           upk2(g2, a[2 * j], a[2 * j + 1]);
           upk2(gp2, gp[2 * j], gp[2 * j + 1]);
         }
@@ -601,6 +593,7 @@ __global__ void __launch_bounds__(RM_THREADS, 1) rmlp_dgrad_kernel(const RmlpDgr
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const RmlpP& f = p.f;
   const int F = f.n_layers, H = F - 1;
+  const ActC ac = act_constants(f.act_kind);
 
   // shared-memory map: weight images of layers 2..F (layer 1 is not differentiated through) | barriers
   uint32_t w_off[RM_MAXL], w_half[RM_MAXL];
@@ -699,7 +692,7 @@ __global__ void __launch_bounds__(RM_THREADS, 1) rmlp_dgrad_kernel(const RmlpDgr
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const f32x2 g2 = mul2(pk2(pre[2 * j], pre[2 * j + 1]), gelu_grad2(pk2(z[2 * j], z[2 * j + 1])));
+            const f32x2 g2 = mul2(pk2(pre[2 * j], pre[2 * j + 1]), act_grad2(pk2(z[2 * j], z[2 * j + 1]), ac));
             upk2(g2, pre[2 * j], pre[2 * j + 1]);
           }
           if (l >= 2) {
@@ -791,8 +784,9 @@ extern "C" size_t eqnn_radial_mlp_stash_bytes(int64_t n_edges, int n_hidden) {
 
 extern "C" int eqnn_radial_mlp_fwd(const float* dist, int64_t dist_stride, int64_t n_edges, int n_rb, double r_cut,
                                    int n_hidden, int d_hidden, const float* const* weights, const int64_t* ldw,
-                                   int n_out, float act_scale, float* w_t, int64_t ld_wt, float* z_stash,
+                                   int n_out, int activation, float act_scale, float* w_t, int64_t ld_wt, float* z_stash,
                                    eqnn_stream_t stream) {
+  EQNN_CHECK_ARG(activation == EQNN_ACT_GELU || activation == EQNN_ACT_SILU, "radial_mlp_fwd: unknown activation");
   EQNN_CHECK_ARG(dist && weights && ldw && w_t && n_edges >= 0 && dist_stride >= 1, "radial_mlp_fwd: bad argument");
   EQNN_CHECK_ARG(eqnn_radial_mlp_supported(n_rb, d_hidden, n_hidden, n_out), "radial_mlp_fwd: unsupported shape");
   EQNN_CHECK_ARG(r_cut > 0.0 && ld_wt >= n_edges, "radial_mlp_fwd: bad r_cut / ld_wt");
@@ -811,7 +805,7 @@ extern "C" int eqnn_radial_mlp_fwd(const float* dist, int64_t dist_stride, int64
     p.W[l] = weights[l]; p.ldw[l] = ldw[l];
     p.alpha[l] = (float)(1.0 / sqrt((double)rm_K(p, l)));
   }
-  p.act_scale = act_scale; p.w_t = w_t; p.ld_wt = ld_wt;
+  p.act_scale = act_scale; p.act_kind = activation; p.w_t = w_t; p.ld_wt = ld_wt;
   EQNN_CHECK_ARG(!z_stash || (reinterpret_cast<uintptr_t>(z_stash) & 15) == 0, "radial_mlp_fwd: z_stash must be 16-byte aligned");
   for (int l = 0; l < RM_MAXL; ++l)
     p.z_stash[l] = (z_stash && l < n_hidden) ? z_stash + (size_t)l * rm_stash_layer_floats(n_edges) : nullptr;
@@ -848,9 +842,12 @@ extern "C" size_t eqnn_radial_mlp_bwd_workspace_bytes(int64_t n_edges, int n_rb,
 // weight-gradient kernel (X = z_{l-1} with the gelu prologue, or the Bessel basis for the first layer; G = g_l).
 // workspace: [absmax 256 B | n_hidden x g_l | (bessel basis when radial == NULL) | GEMM workspace]
 static int rm_bwd_from_stash(const float* dist, int64_t dist_stride, int64_t n_edges, int n_rb, double r_cut, int n_hidden,
-                             int d_hidden, const float* const* weights, const int64_t* ldw, int n_out, float act_scale,
-                             const float* dw_t, int64_t ld_dwt, const float* z_stash, const float* radial,
+                             int d_hidden, const float* const* weights, const int64_t* ldw, int n_out, int activation,
+                             float act_scale, const float* dw_t, int64_t ld_dwt, const float* z_stash, const float* radial,
                              float* const* grad_weights, void* ws, size_t ws_bytes, eqnn_stream_t stream) {
+  // the weight-gradient kernel's prologue (tc_mlp.cu) evaluates gelu on the stashed pre-activations: other activations
+  // take the recompute variant, which hands it bare activations
+  EQNN_CHECK_ARG(activation == EQNN_ACT_GELU, "radial_mlp_bwd: the z-stash variant supports gelu only (pass z_stash = NULL)");
   EQNN_CHECK_ARG(dist && weights && ldw && dw_t && grad_weights && n_edges >= 0 && dist_stride >= 1, "radial_mlp_bwd: bad argument");
   EQNN_CHECK_ARG(eqnn_radial_mlp_supported(n_rb, d_hidden, n_hidden, n_out), "radial_mlp_bwd: unsupported shape");
   EQNN_CHECK_ARG(r_cut > 0.0 && ld_dwt >= n_edges, "radial_mlp_bwd: bad r_cut / ld_dwt");
@@ -873,7 +870,7 @@ static int rm_bwd_from_stash(const float* dist, int64_t dist_stride, int64_t n_e
     f.W[l] = weights[l]; f.ldw[l] = ldw[l];
     f.alpha[l] = (float)(1.0 / sqrt((double)rm_K(f, l)));
   }
-  f.act_scale = act_scale; f.w_t = nullptr; f.ld_wt = 0;
+  f.act_scale = act_scale; f.act_kind = activation; f.w_t = nullptr; f.ld_wt = 0;
   p.dw = dw_t; p.ld_dw = ld_dwt;
   char* w = reinterpret_cast<char*>(ws);
   uint32_t* absmax = reinterpret_cast<uint32_t*>(w);
@@ -951,12 +948,13 @@ static int rm_bwd_from_stash(const float* dist, int64_t dist_stride, int64_t n_e
 
 extern "C" int eqnn_radial_mlp_bwd(const float* dist, int64_t dist_stride, int64_t n_edges, int n_rb, double r_cut,
                                    int n_hidden, int d_hidden, const float* const* weights, const int64_t* ldw,
-                                   int n_out, float act_scale, const float* dw_t, int64_t ld_dwt,
+                                   int n_out, int activation, float act_scale, const float* dw_t, int64_t ld_dwt,
                                    const float* z_stash, const float* radial, float* const* grad_weights, void* ws,
                                    size_t ws_bytes, eqnn_stream_t stream) {
+  EQNN_CHECK_ARG(activation == EQNN_ACT_GELU || activation == EQNN_ACT_SILU, "radial_mlp_bwd: unknown activation");
   if (z_stash)
-    return rm_bwd_from_stash(dist, dist_stride, n_edges, n_rb, r_cut, n_hidden, d_hidden, weights, ldw, n_out, act_scale,
-                             dw_t, ld_dwt, z_stash, radial, grad_weights, ws, ws_bytes, stream);
+    return rm_bwd_from_stash(dist, dist_stride, n_edges, n_rb, r_cut, n_hidden, d_hidden, weights, ldw, n_out, activation,
+                             act_scale, dw_t, ld_dwt, z_stash, radial, grad_weights, ws, ws_bytes, stream);
   EQNN_CHECK_ARG(dist && weights && ldw && dw_t && grad_weights && n_edges >= 0 && dist_stride >= 1, "radial_mlp_bwd: bad argument");
   EQNN_CHECK_ARG(eqnn_radial_mlp_supported(n_rb, d_hidden, n_hidden, n_out), "radial_mlp_bwd: unsupported shape");
   EQNN_CHECK_ARG(r_cut > 0.0 && ld_dwt >= n_edges, "radial_mlp_bwd: bad r_cut / ld_dwt");
@@ -978,7 +976,7 @@ extern "C" int eqnn_radial_mlp_bwd(const float* dist, int64_t dist_stride, int64
     f.W[l] = weights[l]; f.ldw[l] = ldw[l];
     f.alpha[l] = (float)(1.0 / sqrt((double)rm_K(f, l)));
   }
-  f.act_scale = act_scale; f.w_t = nullptr; f.ld_wt = 0;
+  f.act_scale = act_scale; f.act_kind = activation; f.w_t = nullptr; f.ld_wt = 0;
   for (int l = 0; l < RM_MAXL; ++l) f.z_stash[l] = nullptr;
   p.dw = dw_t; p.ld_dw = ld_dwt;
   char* w = reinterpret_cast<char*>(ws);

@@ -33,6 +33,41 @@ __device__ __forceinline__ void split_h2(float a0, float a1, uint32_t& hi, uint3
   lo = cvt_h2(l0, l1);
 }
 
+// ---- activation: x * sigma(x) with sigma = 1 / (1 + 2^(x (C0 + C1 x^2))) -------------------------------------------
+// gelu_tanh (flax.linen.gelu default): C0 = -2 sqrt(2/pi) log2(e), C1 = 0.044715 C0;  silu: C0 = -log2(e), C1 = 0.
+// The derivative is s + x s (1 - s) (D0 + D1 x^2) with D0 = -ln(2) C0, D1 = -3 ln(2) C1.
+struct ActC {
+  float c0, c1, d0, d1;
+};
+__host__ __device__ inline ActC act_constants(int kind) {
+  const float c0 = kind == 0 ? -2.0f * 0.7978845608028654f * 1.4426950408889634f : -1.4426950408889634f;
+  const float c1 = kind == 0 ? c0 * 0.044715f : 0.f;
+  return ActC{c0, c1, -0.6931471805599453f * c0, -3.0f * 0.6931471805599453f * c1};
+}
+__device__ __forceinline__ f32x2 act_sigmoid2(f32x2 x, f32x2 xx, const ActC& a) {
+  const f32x2 t = mul2(fma2(xx, pk2(a.c1, a.c1), pk2(a.c0, a.c0)), x);
+  float t0, t1;
+  upk2(t, t0, t1);
+  const f32x2 d = add2(pk2(ex2_ftz(t0), ex2_ftz(t1)), pk2(1.f, 1.f));
+  float d0, d1;
+  upk2(d, d0, d1);
+  return pk2(rcp_ftz(d0), rcp_ftz(d1));
+}
+// x pair -> act(x) and act'(x) from one sigmoid
+__device__ __forceinline__ void act_both2(f32x2 x, const ActC& a, f32x2& g, f32x2& gp) {
+  const f32x2 xx = mul2(x, x);
+  const f32x2 sg = act_sigmoid2(x, xx, a);
+  g = mul2(x, sg);
+  const f32x2 w = mul2(x, fma2(xx, pk2(a.d1, a.d1), pk2(a.d0, a.d0)));
+  const f32x2 q = mul2(sg, fma2(sg, pk2(-1.f, -1.f), pk2(1.f, 1.f)));
+  gp = fma2(q, w, sg);
+}
+__device__ __forceinline__ f32x2 act_grad2(f32x2 x, const ActC& a) {
+  f32x2 g, gp;
+  act_both2(x, a, g, gp);
+  return gp;
+}
+
 // ---- tensor memory stores: thread i of the warp writes lane (warp % 4) * 32 + i, N consecutive columns -------
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),

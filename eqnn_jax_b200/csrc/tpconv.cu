@@ -35,11 +35,16 @@ __device__ __forceinline__ void load_x(const float* __restrict__ xt, int s, floa
   }
 }
 
-template <class TP>
+// AMAX: jraph.segment_max (message_passing_agg = "max", models/nequip.py:118-120): the running value is the maximum
+// over the row's edges and the CSR position of the FIRST edge that attains it is recorded, so that the backward
+// pass can route the gradient to that edge alone (ties are measure-zero for real messages; the self-loop's exact
+// zeros in the l > 0 components can tie only with another exact zero).
+template <class TP, bool AMAX>
 __global__ void __launch_bounds__(TPC_THREADS)
 tpconv_fwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src,
                   const float4* __restrict__ geom, const float* __restrict__ w_t, int64_t n_edges,
-                  const float* __restrict__ xt, int n_nodes, int agg, float* __restrict__ A, int ld_a) {
+                  const float* __restrict__ xt, int n_nodes, int agg, float* __restrict__ A, int ld_a,
+                  int32_t* __restrict__ argmax) {
   constexpr int DL = TP::DLIVE;
   constexpr int STRIDE = DL | 1;
   constexpr int ITEMS = (TPC_ROWS * DL + TPC_THREADS - 1) / TPC_THREADS;
@@ -52,8 +57,12 @@ tpconv_fwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
   __syncthreads();
   const int p0 = s_rowptr[0], p1 = s_rowptr[nr];
   float acc[ITEMS];
+  int amax[ITEMS];
 #pragma unroll
-  for (int it = 0; it < ITEMS; ++it) acc[it] = 0.f;
+  for (int it = 0; it < ITEMS; ++it) {
+    acc[it] = AMAX ? -INFINITY : 0.f;
+    amax[it] = -1;
+  }
 
   for (int base = p0; base < p1; base += TPC_THREADS) {
     const int p = base + tid;
@@ -80,6 +89,17 @@ tpconv_fwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
         float a = acc[it];
         const float* col = sm + comp;
         int q = lo;
+        if (AMAX) {
+          int am = amax[it];
+          for (; q < hi; ++q) {
+            const float v = col[q * STRIDE];
+            if (v > a) {
+              a = v;
+              am = base + q;
+            }
+          }
+          amax[it] = am;
+        }
         for (; q + 3 < hi; q += 4) {                 // same ascending order, a quarter of the loop overhead
           const float v0 = col[q * STRIDE], v1 = col[(q + 1) * STRIDE], v2 = col[(q + 2) * STRIDE],
                       v3 = col[(q + 3) * STRIDE];
@@ -101,21 +121,26 @@ tpconv_fwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
         const int deg = s_rowptr[row + 1] - s_rowptr[row];
         a = a / (float)max(deg, 1);
       }
+      if (AMAX) {
+        if (amax[it] < 0) a = 0.f;                   // receiver without incoming edges (cannot happen with self-loops)
+        argmax[(size_t)(r0 + row) * DL + comp] = amax[it];
+      }
       A[(size_t)(r0 + row) * ld_a + comp] = a;
     }
   }
 }
 
-template <class TP>
+template <class TP, bool AMAX>
 __global__ void __launch_bounds__(TPC_THREADS)
 tpconv_bwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src,
                   const int32_t* __restrict__ perm, const float4* __restrict__ geom,
                   const float* __restrict__ w_t, int64_t n_edges, const float* __restrict__ xt, int n_nodes,
                   int agg, const float* __restrict__ gA, int ld_ga, float* __restrict__ dw_t,
-                  float* __restrict__ dxe) {
+                  float* __restrict__ dxe, const int32_t* __restrict__ argmax) {
   constexpr int DL = TP::DLIVE;
   constexpr int GS = DL | 1;
   __shared__ float sG[TPC_ROWS * GS];
+  __shared__ int sArg[AMAX ? TPC_ROWS * GS : 1];
   __shared__ int s_rowptr[TPC_ROWS + 1];
   const int tid = threadIdx.x;
   const int r0 = blockIdx.x * TPC_ROWS;
@@ -130,6 +155,7 @@ tpconv_bwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
       g = g / (float)max(deg, 1);
     }
     sG[row * GS + comp] = g;
+    if (AMAX) sArg[row * GS + comp] = argmax[(size_t)(r0 + row) * DL + comp];
   }
   __syncthreads();
   const int p0 = s_rowptr[0], p1 = s_rowptr[nr];
@@ -145,7 +171,7 @@ tpconv_bwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
 #pragma unroll
     for (int c = 0; c < TP::NLIVE; ++c) w[c] = w_t[(size_t)c * n_edges + p];
 #pragma unroll
-    for (int i = 0; i < DL; ++i) g[i] = sG[row * GS + i];
+    for (int i = 0; i < DL; ++i) g[i] = (!AMAX || sArg[row * GS + i] == p) ? sG[row * GS + i] : 0.f;
     TP::sh(gm.x, gm.y, gm.z, Y);
     TP::bwd(x, Y, w, g, dw, dx);
 #pragma unroll
@@ -272,16 +298,21 @@ extern "C" int eqnn_tp_dims(int id, int* dxp, int* ny, int* n_live, int* d_live)
 
 extern "C" int eqnn_tpconv_fwd(int tp_id, const int32_t* rowptr, const int32_t* src, const float* geom,
                                const float* w_t, int64_t n_edges, const float* xt, int n_nodes, int agg, float* A,
-                               int ld_a, eqnn_stream_t stream) {
+                               int ld_a, int32_t* argmax, eqnn_stream_t stream) {
   EQNN_CHECK_ARG(rowptr && src && geom && w_t && xt && A, "tpconv_fwd: null pointer");
-  EQNN_CHECK_ARG(agg == 0 || agg == 1, "tpconv_fwd: agg must be 0 (sum) or 1 (mean)");
+  EQNN_CHECK_ARG(agg >= 0 && agg <= 2, "tpconv_fwd: agg must be 0 (sum), 1 (mean) or 2 (max)");
+  EQNN_CHECK_ARG(agg != 2 || argmax, "tpconv_fwd: max aggregation needs the argmax buffer");
   EQNN_CHECK_ARG(((uintptr_t)geom & 15) == 0 && ((uintptr_t)xt & 15) == 0, "tpconv_fwd: geom/xt must be 16-byte aligned");
   if (n_nodes <= 0) return EQNN_OK;
   const unsigned grid = (unsigned)((n_nodes + TPC_ROWS - 1) / TPC_ROWS);
   EQNN_TP_DISPATCH(tp_id, {
     EQNN_CHECK_ARG(ld_a >= TP::DLIVE, "tpconv_fwd: ld_a smaller than live width");
-    tpconv_fwd_kernel<TP><<<grid, TPC_THREADS, 0, as_stream(stream)>>>(
-        rowptr, src, reinterpret_cast<const float4*>(geom), w_t, n_edges, xt, n_nodes, agg, A, ld_a);
+    if (agg == 2)
+      tpconv_fwd_kernel<TP, true><<<grid, TPC_THREADS, 0, as_stream(stream)>>>(
+          rowptr, src, reinterpret_cast<const float4*>(geom), w_t, n_edges, xt, n_nodes, agg, A, ld_a, argmax);
+    else
+      tpconv_fwd_kernel<TP, false><<<grid, TPC_THREADS, 0, as_stream(stream)>>>(
+          rowptr, src, reinterpret_cast<const float4*>(geom), w_t, n_edges, xt, n_nodes, agg, A, ld_a, nullptr);
   });
   EQNN_CHECK_LAUNCH();
   return EQNN_OK;
@@ -290,18 +321,24 @@ extern "C" int eqnn_tpconv_fwd(int tp_id, const int32_t* rowptr, const int32_t* 
 extern "C" int eqnn_tpconv_bwd(int tp_id, const int32_t* rowptr, const int32_t* src, const int32_t* perm,
                                const float* geom, const float* w_t, int64_t n_edges, const float* xt, int n_nodes,
                                int agg, const float* gA, int ld_ga, float* dw_t, float* dxe,
-                               eqnn_stream_t stream) {
+                               const int32_t* argmax, eqnn_stream_t stream) {
   EQNN_CHECK_ARG(rowptr && src && perm && geom && w_t && xt && gA && dw_t && dxe, "tpconv_bwd: null pointer");
-  EQNN_CHECK_ARG(agg == 0 || agg == 1, "tpconv_bwd: agg must be 0 (sum) or 1 (mean)");
+  EQNN_CHECK_ARG(agg >= 0 && agg <= 2, "tpconv_bwd: agg must be 0 (sum), 1 (mean) or 2 (max)");
+  EQNN_CHECK_ARG(agg != 2 || argmax, "tpconv_bwd: max aggregation needs the argmax buffer of the forward pass");
   EQNN_CHECK_ARG(((uintptr_t)geom & 15) == 0 && ((uintptr_t)xt & 15) == 0 && ((uintptr_t)dxe & 15) == 0,
                  "tpconv_bwd: geom/xt/dxe must be 16-byte aligned");
   if (n_nodes <= 0) return EQNN_OK;
   const unsigned grid = (unsigned)((n_nodes + TPC_ROWS - 1) / TPC_ROWS);
   EQNN_TP_DISPATCH(tp_id, {
     EQNN_CHECK_ARG(ld_ga >= TP::DLIVE, "tpconv_bwd: ld_ga smaller than live width");
-    tpconv_bwd_kernel<TP><<<grid, TPC_THREADS, 0, as_stream(stream)>>>(
-        rowptr, src, perm, reinterpret_cast<const float4*>(geom), w_t, n_edges, xt, n_nodes, agg, gA, ld_ga, dw_t,
-        dxe);
+    if (agg == 2)
+      tpconv_bwd_kernel<TP, true><<<grid, TPC_THREADS, 0, as_stream(stream)>>>(
+          rowptr, src, perm, reinterpret_cast<const float4*>(geom), w_t, n_edges, xt, n_nodes, agg, gA, ld_ga, dw_t,
+          dxe, argmax);
+    else
+      tpconv_bwd_kernel<TP, false><<<grid, TPC_THREADS, 0, as_stream(stream)>>>(
+          rowptr, src, perm, reinterpret_cast<const float4*>(geom), w_t, n_edges, xt, n_nodes, agg, gA, ld_ga, dw_t,
+          dxe, nullptr);
   });
   EQNN_CHECK_LAUNCH();
   return EQNN_OK;

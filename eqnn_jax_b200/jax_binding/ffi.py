@@ -77,7 +77,8 @@ def _radial_fwd(geom, radial, kernels, n_rb, r_cut, act_scale):
     stash = int(_core.eqnn_radial_mlp_stash_bytes(E, H)) // 4
     out = (_S((wout.shape[1], E), _f32), _S((stash,), _f32))
     w_t, z = jax.ffi.ffi_call("eqnn_radial_mlp_fwd", out)(geom, *hidden, wout, n_hidden=np.int32(H), n_rb=np.int32(n_rb),
-                                                           r_cut=float(r_cut), act_scale=np.float32(act_scale))
+                                                           r_cut=float(r_cut), activation=np.int32(0),
+                                                           act_scale=np.float32(act_scale))
     return w_t, (geom, radial, z, kernels)
 
 
@@ -88,7 +89,7 @@ def _radial_bwd(n_rb, r_cut, act_scale, res, dw_t):
     ws = int(_core.eqnn_radial_mlp_bwd_workspace_bytes(E, n_rb, H))
     out = tuple(_S(h.shape, _f32) for h in hidden) + (_S(wout.shape, _f32), _S((ws,), _u8))
     *g, _ = jax.ffi.ffi_call("eqnn_radial_mlp_bwd", out)(geom, radial, z, *hidden, wout, dw_t, n_hidden=np.int32(H),
-                                                          n_rb=np.int32(n_rb), r_cut=float(r_cut),
+                                                          n_rb=np.int32(n_rb), r_cut=float(r_cut), activation=np.int32(0),
                                                           act_scale=np.float32(act_scale))
     return None, None, list(g[:H]) + [g[3]]      # edge lengths carry no gradient (params only, train_cosmology.py:245)
 
@@ -98,18 +99,20 @@ radial_mlp.defvjp(_radial_fwd, _radial_bwd)
 
 @functools.partial(jax.custom_vjp, nondiff_argnums=(6, 7, 8))
 def tpconv(xt, w_t, rowptr, src, perm, geom, tp_id, agg, d_live):
-    out = _S((xt.shape[0], d_live), _f32)
-    return jax.ffi.ffi_call("eqnn_tpconv_fwd", out)(rowptr, src, geom, w_t, xt, tp_id=np.int32(tp_id), agg=np.int32(agg))
+    return _tp_fwd(xt, w_t, rowptr, src, perm, geom, tp_id, agg, d_live)[0]
 
 
 def _tp_fwd(xt, w_t, rowptr, src, perm, geom, tp_id, agg, d_live):
-    return tpconv(xt, w_t, rowptr, src, perm, geom, tp_id, agg, d_live), (xt, w_t, rowptr, src, perm, geom)
+    """agg: 0 sum, 1 mean, 2 max (the arg-max of every component is kept for the backward pass)."""
+    out = (_S((xt.shape[0], d_live), _f32), _S((xt.shape[0], d_live) if agg == 2 else (0,), _i32))
+    A, amax = jax.ffi.ffi_call("eqnn_tpconv_fwd", out)(rowptr, src, geom, w_t, xt, tp_id=np.int32(tp_id), agg=np.int32(agg))
+    return A, (xt, w_t, rowptr, src, perm, geom, amax)
 
 
 def _tp_bwd(tp_id, agg, d_live, res, gA):
-    xt, w_t, rowptr, src, perm, geom = res
+    xt, w_t, rowptr, src, perm, geom, amax = res
     out = (_S(w_t.shape, _f32), _S((src.shape[0], xt.shape[1]), _f32))
-    dw_t, dxe = jax.ffi.ffi_call("eqnn_tpconv_bwd", out)(rowptr, src, perm, geom, w_t, xt, gA, tp_id=np.int32(tp_id),
+    dw_t, dxe = jax.ffi.ffi_call("eqnn_tpconv_bwd", out)(rowptr, src, perm, geom, w_t, xt, gA, amax, tp_id=np.int32(tp_id),
                                                           agg=np.int32(agg))
     dxt = dxe.reshape(xt.shape[0], -1, xt.shape[1]).sum(1)      # kNN graphs: k contiguous edges per sender
     return dxt, dw_t, None, None, None, None

@@ -64,7 +64,7 @@ ffi::Error EdgeGeom(cudaStream_t stream, F32 pos, S32 rowptr, S32 src, int32_t n
 // ---- fused radial MLP, models/nequip.py:55-68 (hidden kernels W0..W2 [fan_in, 128], output kernel [128, n_out]) ----
 // Hidden kernels arrive as w0, w1, w2 (the unused trailing ones as zero-size arrays when n_hidden < 3).
 ffi::Error RadialMlpFwd(cudaStream_t stream, F32 geom, F32 w0, F32 w1, F32 w2, F32 wout, int32_t n_hidden, int32_t n_rb,
-                        double r_cut, float act_scale, RF32 w_t, RF32 z_stash) {
+                        double r_cut, int32_t activation, float act_scale, RF32 w_t, RF32 z_stash) {
   const float* hidden[3] = {w0.typed_data(), w1.typed_data(), w2.typed_data()};
   const float* W[4];
   int64_t ldw[4];
@@ -73,12 +73,12 @@ ffi::Error RadialMlpFwd(cudaStream_t stream, F32 geom, F32 w0, F32 w1, F32 w2, F
   ldw[n_hidden] = (int64_t)wout.dimensions()[1];
   const int64_t n_edges = geom.dimensions()[0];
   return status(eqnn_radial_mlp_fwd(geom.typed_data() + 3, 4, n_edges, n_rb, r_cut, n_hidden, 128, W, ldw,
-                                    (int)wout.dimensions()[1], act_scale, w_t->typed_data(), n_edges,
+                                    (int)wout.dimensions()[1], activation, act_scale, w_t->typed_data(), n_edges,
                                     z_stash->element_count() ? z_stash->typed_data() : nullptr, stream));
 }
 ffi::Error RadialMlpBwd(cudaStream_t stream, F32 geom, F32 radial, F32 z_stash, F32 w0, F32 w1, F32 w2, F32 wout, F32 dw_t,
-                        int32_t n_hidden, int32_t n_rb, double r_cut, float act_scale, RF32 g0, RF32 g1, RF32 g2, RF32 gout,
-                        RU8 ws) {
+                        int32_t n_hidden, int32_t n_rb, double r_cut, int32_t activation, float act_scale, RF32 g0, RF32 g1,
+                        RF32 g2, RF32 gout, RU8 ws) {
   const float* hidden[3] = {w0.typed_data(), w1.typed_data(), w2.typed_data()};
   float* ghidden[3] = {g0->typed_data(), g1->typed_data(), g2->typed_data()};
   const float* W[4];
@@ -90,22 +90,25 @@ ffi::Error RadialMlpBwd(cudaStream_t stream, F32 geom, F32 radial, F32 z_stash, 
   ldw[n_hidden] = (int64_t)wout.dimensions()[1];
   const int64_t n_edges = geom.dimensions()[0];
   return status(eqnn_radial_mlp_bwd(geom.typed_data() + 3, 4, n_edges, n_rb, r_cut, n_hidden, 128, W, ldw,
-                                    (int)wout.dimensions()[1], act_scale, dw_t.typed_data(), n_edges,
+                                    (int)wout.dimensions()[1], activation, act_scale, dw_t.typed_data(), n_edges,
                                     z_stash.element_count() ? z_stash.typed_data() : nullptr, radial.typed_data(), G,
                                     ws->untyped_data(), ws->size_bytes(), stream));
 }
 
 // ---- interaction kernel: SH + Clebsch-Gordan TP + radial weights + receiver reduction, models/nequip.py:46-52,68,118-120 ----
-ffi::Error TpconvFwd(cudaStream_t stream, S32 rowptr, S32 src, F32 geom, F32 w_t, F32 xt, int32_t tp_id, int32_t agg, RF32 A) {
+// argmax: [n_nodes, d_live] for agg == 2 (segment_max), a zero-size array otherwise
+ffi::Error TpconvFwd(cudaStream_t stream, S32 rowptr, S32 src, F32 geom, F32 w_t, F32 xt, int32_t tp_id, int32_t agg, RF32 A,
+                     RS32 argmax) {
   return status(eqnn_tpconv_fwd(tp_id, rowptr.typed_data(), src.typed_data(), geom.typed_data(), w_t.typed_data(),
                                 (int64_t)src.element_count(), xt.typed_data(), (int)xt.dimensions()[0], agg, A->typed_data(),
-                                (int)A->dimensions()[1], stream));
+                                (int)A->dimensions()[1], argmax->element_count() ? argmax->typed_data() : nullptr, stream));
 }
-ffi::Error TpconvBwd(cudaStream_t stream, S32 rowptr, S32 src, S32 perm, F32 geom, F32 w_t, F32 xt, F32 gA, int32_t tp_id,
-                     int32_t agg, RF32 dw_t, RF32 dxe) {
+ffi::Error TpconvBwd(cudaStream_t stream, S32 rowptr, S32 src, S32 perm, F32 geom, F32 w_t, F32 xt, F32 gA, S32 argmax,
+                     int32_t tp_id, int32_t agg, RF32 dw_t, RF32 dxe) {
   return status(eqnn_tpconv_bwd(tp_id, rowptr.typed_data(), src.typed_data(), perm.typed_data(), geom.typed_data(),
                                 w_t.typed_data(), (int64_t)src.element_count(), xt.typed_data(), (int)xt.dimensions()[0], agg,
-                                gA.typed_data(), (int)gA.dimensions()[1], dw_t->typed_data(), dxe->typed_data(), stream));
+                                gA.typed_data(), (int)gA.dimensions()[1], dw_t->typed_data(), dxe->typed_data(),
+                                argmax.element_count() ? argmax.typed_data() : nullptr, stream));
 }
 
 // ---- fused node update: Linear + self-connection + gate + re-projection, models/nequip.py:80-90,162 ----
@@ -147,18 +150,19 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(eqnn_edge_geom_ffi, EdgeGeom,
                                   .Attr<double>("r_cut").Ret<F32>().Ret<F32>());
 XLA_FFI_DEFINE_HANDLER_SYMBOL(eqnn_radial_mlp_fwd_ffi, RadialMlpFwd,
                               ffi::Ffi::Bind().EQNN_STREAM.Arg<F32>().Arg<F32>().Arg<F32>().Arg<F32>().Arg<F32>()
-                                  .Attr<int32_t>("n_hidden").Attr<int32_t>("n_rb").Attr<double>("r_cut").Attr<float>("act_scale")
-                                  .Ret<F32>().Ret<F32>());
+                                  .Attr<int32_t>("n_hidden").Attr<int32_t>("n_rb").Attr<double>("r_cut").Attr<int32_t>("activation")
+                                  .Attr<float>("act_scale").Ret<F32>().Ret<F32>());
 XLA_FFI_DEFINE_HANDLER_SYMBOL(eqnn_radial_mlp_bwd_ffi, RadialMlpBwd,
                               ffi::Ffi::Bind().EQNN_STREAM.Arg<F32>().Arg<F32>().Arg<F32>().Arg<F32>().Arg<F32>().Arg<F32>()
                                   .Arg<F32>().Arg<F32>().Attr<int32_t>("n_hidden").Attr<int32_t>("n_rb").Attr<double>("r_cut")
-                                  .Attr<float>("act_scale").Ret<F32>().Ret<F32>().Ret<F32>().Ret<F32>().Ret<U8>());
+                                  .Attr<int32_t>("activation").Attr<float>("act_scale").Ret<F32>().Ret<F32>().Ret<F32>().Ret<F32>()
+                                  .Ret<U8>());
 XLA_FFI_DEFINE_HANDLER_SYMBOL(eqnn_tpconv_fwd_ffi, TpconvFwd,
                               ffi::Ffi::Bind().EQNN_STREAM.Arg<S32>().Arg<S32>().Arg<F32>().Arg<F32>().Arg<F32>()
-                                  .Attr<int32_t>("tp_id").Attr<int32_t>("agg").Ret<F32>());
+                                  .Attr<int32_t>("tp_id").Attr<int32_t>("agg").Ret<F32>().Ret<S32>());
 XLA_FFI_DEFINE_HANDLER_SYMBOL(eqnn_tpconv_bwd_ffi, TpconvBwd,
                               ffi::Ffi::Bind().EQNN_STREAM.Arg<S32>().Arg<S32>().Arg<S32>().Arg<F32>().Arg<F32>().Arg<F32>()
-                                  .Arg<F32>().Attr<int32_t>("tp_id").Attr<int32_t>("agg").Ret<F32>().Ret<F32>());
+                                  .Arg<F32>().Arg<S32>().Attr<int32_t>("tp_id").Attr<int32_t>("agg").Ret<F32>().Ret<F32>());
 XLA_FFI_DEFINE_HANDLER_SYMBOL(eqnn_node_update_fwd_ffi, NodeUpdateFwd,
                               ffi::Ffi::Bind().EQNN_STREAM.Arg<F32>().Arg<F32>().Arg<F32>().Arg<F32>().Arg<F32>()
                                   .Attr<float>("alpha1").Attr<int32_t>("n_extra").Attr<int32_t>("n_gates")

@@ -48,6 +48,8 @@ def normalize_constant(name: str) -> float:
         y = 0.5 * x * (1.0 + torch.tanh(math.sqrt(2.0 / math.pi) * (x + 0.044715 * x ** 3)))
     elif name == "sigmoid":
         y = torch.sigmoid(x)
+    elif name == "silu":
+        y = x * torch.sigmoid(x)
     else:
         raise NotImplementedError(f"activation {name!r} has no B200 kernel on this path")
     return float(torch.sqrt(torch.mean(y * y)))
@@ -115,10 +117,10 @@ class _Plan:
         D = irreps_in.dim
         if len(irreps_in) == 0 or irreps_in[0][1] != 1:
             raise ValueError("the first irrep of the node features must be a vector (positions), nequip.py:129-132")
-        if cfg.activation != "gelu":
-            raise NotImplementedError("only activation='gelu' has a B200 kernel on this path")
-        if cfg.message_passing_agg not in ("sum", "mean"):
-            raise NotImplementedError("message_passing_agg must be 'sum' or 'mean' on the B200 path")
+        if cfg.activation not in ("gelu", "silu"):
+            raise NotImplementedError("activation must be 'gelu' or 'silu' on the B200 path (models/nequip.py:61)")
+        if cfg.message_passing_agg not in ("sum", "mean", "max"):
+            raise ValueError(f"Invalid message_passing_agg {cfg.message_passing_agg}")
         if cfg.task == "graph" and cfg.readout_agg not in ("sum", "mean"):
             raise NotImplementedError("readout_agg must be 'sum' or 'mean' on the B200 path")
         hidden = balanced_irreps(cfg.l_max, cfg.d_hidden, True)
@@ -178,6 +180,8 @@ class _Plan:
         self.d_in = D
         self.n_rad_in = cfg.n_radial_basis if cfg.n_radial_basis > 0 else 1
         self.shn = [so3.sh_norm_factor(l, cfg.sphharm_norm) for l in range(cfg.l_max + 1)]
+        # the radial MLP uses `activation` (nequip.py:61); e3nn.gate keeps its defaults, gelu / sigmoid (nequip.py:88-90)
+        self.inv_c_mlp = 1.0 / normalize_constant(cfg.activation)
         self.inv_c_act = 1.0 / normalize_constant("gelu")
         self.inv_c_gate = 1.0 / normalize_constant("sigmoid")
 
@@ -525,10 +529,16 @@ def _n_edge_of(graphs: GraphsTuple) -> float:
 def _fused_radial_ok(model: "NequIP", plan: _Plan) -> bool:
     """The fused radial-MLP kernels cover this model (tensor-core path requested, supported shape)."""
     if not (model.fuse_radial_mlp and model.tensor_cores):
+        if model.activation != "gelu":
+            raise NotImplementedError("activation='silu' runs on the fused radial-MLP kernels only")
         return False
     if model.radial_mlp_backward not in ("stash", "recompute"):
         raise ValueError("radial_mlp_backward must be 'stash' or 'recompute'")
-    return ops.radial_mlp_supported(model.n_radial_basis, model.d_hidden, model.n_layers, plan.tp.n_live)
+    ok = ops.radial_mlp_supported(model.n_radial_basis, model.d_hidden, model.n_layers, plan.tp.n_live)
+    if not ok and model.activation != "gelu":
+        raise NotImplementedError("activation='silu' needs a radial MLP the fused kernels cover "
+                                  "(d_hidden 128, n_radial_basis 16/32/64, n_layers <= 3)")
+    return ok
 
 
 def _radial_weights(theta: torch.Tensor, wexp: torch.Tensor, st: Dict, n_live: int):
@@ -565,7 +575,7 @@ def _forward(model: NequIP, plan: _Plan, theta: torch.Tensor, pg: PreparedGraph,
     ops.weights_expand(theta, tab["exp_idx"], tab["exp_scale"], wexp)
     tp_id = ops.tp_lookup(plan.tp_sig)
     dxp, n_live, d_live = plan.tp.dxp, plan.tp.n_live, plan.tp.d_live
-    agg = 1 if model.message_passing_agg == "mean" else 0
+    agg = ops.AGG[model.message_passing_agg]
     inv_sqrt_k = 1.0 / math.sqrt(k)
     h = nodes.reshape(Nt, D)
     saved = {"steps": [], "wexp": wexp}
@@ -577,10 +587,10 @@ def _forward(model: NequIP, plan: _Plan, theta: torch.Tensor, pg: PreparedGraph,
         stash = None
         if fused:
             w_t = torch.empty((n_live, Et), **f32)
-            if save and model.radial_mlp_backward == "stash":
+            if save and model.radial_mlp_backward == "stash" and model.activation == "gelu":
                 stash = ops.radial_mlp_stash(Et, len(st["mlp"]) - 1, dev)
             ops.radial_mlp_fwd(pg.geom, model.n_radial_basis, model.r_cutoff, _radial_weights(theta, wexp, st, n_live),
-                               n_live, plan.inv_c_act, w_t, z_stash=stash)
+                               n_live, plan.inv_c_mlp, w_t, z_stash=stash, activation=model.activation)
         for (koff, fan, hdim) in ([] if fused else st["mlp"][:-1]):
             Z = torch.empty((Et, hdim), **f32)
             _mm(Et, hdim, fan, 1.0 / math.sqrt(fan), a, 0, fan, theta, koff, hdim, Z, 0, hdim,
@@ -593,7 +603,8 @@ def _forward(model: NequIP, plan: _Plan, theta: torch.Tensor, pg: PreparedGraph,
             _mm(Et, n_live, fan, 1.0 / math.sqrt(fan), a, 0, fan, wexp, st["W4L"].off, n_live, w_t, 0, Et, tc=True,
                 pro=pro, pro_scale=plan.inv_c_act, tag="radial_mlp_fwd", tf32x3=model.tensor_cores)
         A = torch.empty((Nt, d_live), **f32)
-        ops.tpconv_fwd(tp_id, pg.rowptr, pg.src, pg.geom, w_t, xt, Nt, agg, A, d_live)
+        amax = torch.empty((Nt, d_live), dtype=torch.int32, device=dev) if agg == 2 else None   # segment_max winners
+        ops.tpconv_fwd(tp_id, pg.rowptr, pg.src, pg.geom, w_t, xt, Nt, agg, A, d_live, amax)
         z = torch.empty((Nt, plan.d_z), **f32)
         hn = torch.empty((Nt, D), **f32)
         g = None
@@ -610,7 +621,7 @@ def _forward(model: NequIP, plan: _Plan, theta: torch.Tensor, pg: PreparedGraph,
                          plan.inv_c_gate, g)
             _mm(Nt, D, plan.d_g, 1.0, g, 0, plan.d_g, wexp, st["W3"].off, D, hn, 0, D)
         if save:
-            saved["steps"].append(dict(h=h, xt=xt, Zs=Zs, w_t=w_t, A=A, z=z, g=g, stash=stash))
+            saved["steps"].append(dict(h=h, xt=xt, Zs=Zs, w_t=w_t, A=A, z=z, g=g, stash=stash, amax=amax))
         h = hn
     saved["h_final"] = h
     if model.task == "node":
@@ -669,7 +680,7 @@ def _backward(model: NequIP, plan: _Plan, theta: torch.Tensor, pg: PreparedGraph
     gtheta.zero_()
     tp_id = ops.tp_lookup(plan.tp_sig)
     dxp, n_live, d_live = plan.tp.dxp, plan.tp.n_live, plan.tp.d_live
-    agg = 1 if model.message_passing_agg == "mean" else 0
+    agg = ops.AGG[model.message_passing_agg]
     inv_sqrt_k = 1.0 / math.sqrt(k)
     h_final = saved["h_final"]
 
@@ -748,7 +759,7 @@ def _backward(model: NequIP, plan: _Plan, theta: torch.Tensor, pg: PreparedGraph
             else:
                 dh_prev.zero_()
         # interaction block
-        ops.tpconv_bwd(tp_id, pg.rowptr, pg.src, pg.perm, pg.geom, w_t, xt, Nt, agg, dA, d_live, dw_t, dxe)
+        ops.tpconv_bwd(tp_id, pg.rowptr, pg.src, pg.perm, pg.geom, w_t, xt, Nt, agg, dA, d_live, dw_t, dxe, sv["amax"])
         # radial MLP backward
         mlp = st["mlp"]
         nh = len(mlp) - 1
@@ -757,8 +768,9 @@ def _backward(model: NequIP, plan: _Plan, theta: torch.Tensor, pg: PreparedGraph
         fused = _fused_radial_ok(model, plan)
         if fused:
             ops.radial_mlp_bwd(pg.geom, model.n_radial_basis, model.r_cutoff, _radial_weights(theta, wexp, st, n_live),
-                               n_live, plan.inv_c_act, dw_t, _radial_weights(gtheta, gwexp, st, n_live),
-                               z_stash=sv["stash"], radial=pg.radial if sv["stash"] is not None else None)
+                               n_live, plan.inv_c_mlp, dw_t, _radial_weights(gtheta, gwexp, st, n_live),
+                               z_stash=sv["stash"], radial=pg.radial if sv["stash"] is not None else None,
+                               activation=model.activation)
         a_last, pro_last = (Zs[-1], 1) if nh > 0 and not fused else (pg.radial, 0)
         # dW4L = al * act(Z_last)^T @ dw_t^T
         if not fused:

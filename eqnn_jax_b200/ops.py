@@ -150,18 +150,21 @@ def edge_geom(pos: torch.Tensor, ld_pos: int, n_nodes: int, rowptr, src, n_rb: i
 
 
 # ---------------------------------------------------------------- interaction block
-def tpconv_fwd(tp_id, rowptr, src, geom, w_t, xt, n_nodes, agg, out, ld_out):
+AGG = {"sum": 0, "mean": 1, "max": 2}
+
+
+def tpconv_fwd(tp_id, rowptr, src, geom, w_t, xt, n_nodes, agg, out, ld_out, argmax=None):
     t0 = TIMER.begin() if TIMER else None
     check(lib().eqnn_tpconv_fwd(tp_id, _ptr(rowptr), _ptr(src), _ptr(geom), _ptr(w_t), src.numel(), _ptr(xt),
-                                n_nodes, agg, _ptr(out), ld_out, _stream()), "tpconv_fwd")
+                                n_nodes, agg, _ptr(out), ld_out, _ptr(argmax), _stream()), "tpconv_fwd")
     if TIMER:
         TIMER.end("tpconv_fwd", t0)
 
 
-def tpconv_bwd(tp_id, rowptr, src, perm, geom, w_t, xt, n_nodes, agg, gA, ld_ga, dw_t, dxe):
+def tpconv_bwd(tp_id, rowptr, src, perm, geom, w_t, xt, n_nodes, agg, gA, ld_ga, dw_t, dxe, argmax=None):
     t0 = TIMER.begin() if TIMER else None
     check(lib().eqnn_tpconv_bwd(tp_id, _ptr(rowptr), _ptr(src), _ptr(perm), _ptr(geom), _ptr(w_t), src.numel(),
-                                _ptr(xt), n_nodes, agg, _ptr(gA), ld_ga, _ptr(dw_t), _ptr(dxe), _stream()),
+                                _ptr(xt), n_nodes, agg, _ptr(gA), ld_ga, _ptr(dw_t), _ptr(dxe), _ptr(argmax), _stream()),
           "tpconv_bwd")
     if TIMER:
         TIMER.end("tpconv_bwd", t0)
@@ -241,14 +244,17 @@ def radial_mlp_stash(n_edges, n_hidden, device):
     return torch.empty((lib().eqnn_radial_mlp_stash_bytes(n_edges, n_hidden) // 4,), dtype=_F32, device=device)
 
 
-def radial_mlp_fwd(geom, n_rb, r_cut, weights, n_out, act_scale, w_t, z_stash=None):
+ACT = {"gelu": 0, "silu": 1}
+
+
+def radial_mlp_fwd(geom, n_rb, r_cut, weights, n_out, act_scale, w_t, z_stash=None, activation="gelu"):
     """geom [E, 4] (r_hat, d) -> w_t [n_out, E]; weights = [(tensor, offset, ld)] for the hidden layers + the output layer."""
     E = geom.shape[0]
     ptrs, lds = _weight_ptrs(weights)
     t0 = TIMER.begin() if TIMER else None
     check(lib().eqnn_radial_mlp_fwd(C.c_void_p(geom.data_ptr() + 12), 4, E, n_rb, float(r_cut), len(weights) - 1, 128,
-                                    ptrs, lds, n_out, float(act_scale), _ptr(w_t), w_t.shape[1], _ptr(z_stash),
-                                    _stream()), "radial_mlp_fwd")
+                                    ptrs, lds, n_out, ACT[activation], float(act_scale), _ptr(w_t), w_t.shape[1],
+                                    _ptr(z_stash), _stream()), "radial_mlp_fwd")
     if TIMER:
         TIMER.end("radial_mlp_fwd", t0)
 
@@ -256,7 +262,8 @@ def radial_mlp_fwd(geom, n_rb, r_cut, weights, n_out, act_scale, w_t, z_stash=No
 _RMLP_WS = GemmWorkspace()
 
 
-def radial_mlp_bwd(geom, n_rb, r_cut, weights, n_out, act_scale, dw_t, grad_weights, z_stash=None, radial=None):
+def radial_mlp_bwd(geom, n_rb, r_cut, weights, n_out, act_scale, dw_t, grad_weights, z_stash=None, radial=None,
+                   activation="gelu"):
     """Weight gradients of the radial MLP from dw_t [n_out, E]; grad_weights = [(tensor, offset, ld)] like weights.
     With z_stash (from radial_mlp_fwd) and radial (edge_geom) the activations are not recomputed."""
     E = geom.shape[0]
@@ -267,8 +274,8 @@ def radial_mlp_bwd(geom, n_rb, r_cut, weights, n_out, act_scale, dw_t, grad_weig
     ws, ws_bytes = _RMLP_WS.get(need, geom.device)
     t0 = TIMER.begin() if TIMER else None
     check(lib().eqnn_radial_mlp_bwd(C.c_void_p(geom.data_ptr() + 12), 4, E, n_rb, float(r_cut), len(weights) - 1, 128,
-                                    ptrs, lds, n_out, float(act_scale), _ptr(dw_t), dw_t.shape[1], _ptr(z_stash),
-                                    _ptr(radial), gptrs, ws, ws_bytes, _stream()), "radial_mlp_bwd")
+                                    ptrs, lds, n_out, ACT[activation], float(act_scale), _ptr(dw_t), dw_t.shape[1],
+                                    _ptr(z_stash), _ptr(radial), gptrs, ws, ws_bytes, _stream()), "radial_mlp_bwd")
     if TIMER:
         TIMER.end("radial_mlp_bwd", t0)
 

@@ -108,12 +108,14 @@ int eqnn_edge_geom(const float* pos, int ld_pos, int n_nodes, const int32_t* row
  *   tp_id  signature id (x irreps, lmax, live set)
  *   xt     [n_nodes, DXP] regrouped + padded sender record (Linear of :43 applied)
  *   w_t    [NLIVE, n_edges] column-major radial weights in CSR order
- *   agg    0 = sum, 1 = mean (divide by max(in-degree, 1))
+ *   agg    0 = sum, 1 = mean (divide by max(in-degree, 1)), 2 = max (jraph.segment_max)
  *   A      [n_nodes, ld_a], first DLIVE columns written
+ *   argmax [n_nodes, DLIVE] int32, agg == 2 only (else NULL): CSR position of the first edge attaining the
+ *          maximum of each component; the backward pass routes dL/dA to that edge alone
  * Harmonics are unit-norm ("norm"); the caller folds the e3nn normalisation factor
  * of each l into the weights that produce w_t.                                       */
 int eqnn_tpconv_fwd(int tp_id, const int32_t* rowptr, const int32_t* src, const float* geom, const float* w_t,
-                    int64_t n_edges, const float* xt, int n_nodes, int agg, float* A, int ld_a,
+                    int64_t n_edges, const float* xt, int n_nodes, int agg, float* A, int ld_a, int32_t* argmax,
                     eqnn_stream_t stream);
 /* Backward of the above w.r.t. w_t and xt (the custom_vjp rule):
  *   gA    [n_nodes, ld_ga]  dL/dA
@@ -122,7 +124,7 @@ int eqnn_tpconv_fwd(int tp_id, const int32_t* rowptr, const int32_t* src, const 
  *                           (perm) so that senders' k edges are contiguous            */
 int eqnn_tpconv_bwd(int tp_id, const int32_t* rowptr, const int32_t* src, const int32_t* perm, const float* geom,
                     const float* w_t, int64_t n_edges, const float* xt, int n_nodes, int agg, const float* gA,
-                    int ld_ga, float* dw_t, float* dxe, eqnn_stream_t stream);
+                    int ld_ga, float* dw_t, float* dxe, const int32_t* argmax, eqnn_stream_t stream);
 /* dxt[s, :] = sum_{j<k} dxe[s*k + j, :]   (sender-major fixed out-degree k, graph_utils.py:70) */
 int eqnn_sender_reduce(const float* dxe, int n_nodes, int k, int dxp, float* dxt, eqnn_stream_t stream);
 /* general out-degree: dxt[s, :] = sum over row s of a SENDER-sorted CSR (eqnn_csr_build with the roles of
@@ -353,7 +355,7 @@ int eqnn_colsum_tall(const float* x, int64_t M, int N, float* y, void* ws, size_
 
 /* ---- fused radial MLP (models/nequip.py:55-68: e3nn.bessel -> e3nn.flax.MultiLayerPerceptron) -------------
  * w_t[c, e] = ( act(...act(bessel(d_e) @ W_0 / sqrt(n_rb)) ... @ W_{n_hidden-1} / sqrt(128)) @ W_out / sqrt(128) )[c]
- * with act(x) = gelu_tanh(x) * act_scale (e3nn.normalize_function).  ONE kernel from the edge length to the radial
+ * with act(x) = activation(x) * act_scale (e3nn.normalize_function; activation EQNN_ACT_GELU or EQNN_ACT_SILU).  ONE kernel from the edge length to the radial
  * weights: the Bessel basis is evaluated in-kernel (fp32 rounding points of the reference: phase fl(fl(j*pi/r_cut)*d)),
  * every weight matrix is resident in shared memory, activations stay in tensor memory between layers (tcgen05.mma with
  * the A operand in TMEM); per edge the kernel reads d (4 bytes) and writes n_out floats.  Arithmetic: operands split
@@ -363,6 +365,7 @@ int eqnn_colsum_tall(const float* x, int64_t M, int N, float* y, void* ws, size_
  *   the last matrix has n_out <= 16 columns (the live message columns, SH normalisation folded in)
  *   w_t [n_out][ld_wt] column-major (the layout eqnn_tpconv_fwd reads)
  * eqnn_radial_mlp_supported: 1 if the shape is covered (n_rb in {16,32,64}, d_hidden = 128, 1 <= n_hidden <= 3). */
+enum { EQNN_ACT_GELU = 0, EQNN_ACT_SILU = 1 };   /* models/nequip.py:61 getattr(nn, activation); gelu = tanh form */
 int eqnn_radial_mlp_supported(int n_rb, int d_hidden, int n_hidden, int n_out);
 /* Backward of the same MLP w.r.t. its weights (the only gradient the reference takes: jax.value_and_grad w.r.t.
  * params, train_cosmology.py:245; edge lengths carry no gradient).  dw_t [n_out][ld_dwt] = dL/dw_t.
@@ -376,12 +379,12 @@ int eqnn_radial_mlp_supported(int n_rb, int d_hidden, int n_hidden, int n_out);
  * ws: eqnn_radial_mlp_bwd_workspace_bytes. */
 size_t eqnn_radial_mlp_bwd_workspace_bytes(int64_t n_edges, int n_rb, int n_hidden);
 int eqnn_radial_mlp_bwd(const float* dist, int64_t dist_stride, int64_t n_edges, int n_rb, double r_cut, int n_hidden,
-                        int d_hidden, const float* const* weights, const int64_t* ldw, int n_out, float act_scale,
-                        const float* dw_t, int64_t ld_dwt, const float* z_stash, const float* radial,
+                        int d_hidden, const float* const* weights, const int64_t* ldw, int n_out, int activation,
+                        float act_scale, const float* dw_t, int64_t ld_dwt, const float* z_stash, const float* radial,
                         float* const* grad_weights, void* ws, size_t ws_bytes, eqnn_stream_t stream);
 int eqnn_radial_mlp_fwd(const float* dist, int64_t dist_stride, int64_t n_edges, int n_rb, double r_cut, int n_hidden,
-                        int d_hidden, const float* const* weights, const int64_t* ldw, int n_out, float act_scale,
-                        float* w_t, int64_t ld_wt, float* z_stash, eqnn_stream_t stream);
+                        int d_hidden, const float* const* weights, const int64_t* ldw, int n_out, int activation,
+                        float act_scale, float* w_t, int64_t ld_wt, float* z_stash, eqnn_stream_t stream);
 /* z_stash (optional, eqnn_radial_mlp_stash_bytes, 16-byte aligned): the forward kernel also writes the n_hidden
  * pre-activation matrices z_l for the backward pass (opaque blocked layout; 512 bytes per edge and hidden layer). */
 size_t eqnn_radial_mlp_stash_bytes(int64_t n_edges, int n_hidden);

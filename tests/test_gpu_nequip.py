@@ -418,3 +418,60 @@ def test_bench_model_on_fused_tensor_core_route(lmax, N, k, task, backward):
     with open(f"gpurun_out/parity_nequip_lmax{lmax}_N{N}_k{k}_{task}_{backward}.txt", "w") as fh:
         fh.write(report + "\n")
     assert not bad, "tensors outside the contract: " + ", ".join(bad) + "\n" + report
+
+
+def _check_all(model, params, gg, cfg, tree, g, cot, rtol=RTOL, floor_factor=4.0):
+    """forward + every gradient against the fp64 oracle: 1e-5 of the module scale + floor_factor x the fp32 floor."""
+    want, grads = _oracle(cfg, tree, g, IRR, cot)
+    want32, grads32 = _floor32(cfg, tree, g, IRR, cot)
+    out = model.forward_backward(params, gg, lambda o: torch.tensor(cot, dtype=torch.float32).cuda().reshape(o.shape))
+    got = out.reshape(want.shape).cpu().numpy().astype(np.float64)
+    assert np.abs(got - want).max() <= rtol * np.abs(want).max() + floor_factor * np.abs(want32 - want).max(), "output"
+    gt, ms, l32 = params.grad_tree, _module_scales(grads), dict(_leaves(grads32))
+    for path, w in _leaves(grads):
+        a = gt
+        for q_ in path:
+            a = a[q_]
+        wn = w.grad.numpy()
+        if np.abs(wn).max() == 0:
+            assert float(a.abs().max()) == 0.0, path
+            continue
+        err = np.abs(a.cpu().numpy().astype(np.float64) - wn).max()
+        floor = np.abs(l32[path].grad.double().numpy() - wn).max()
+        assert err <= rtol * ms[path[0]] + floor_factor * floor, f"grad {'/'.join(path)}: {err / ms[path[0]]:.2e}"
+
+
+@pytest.mark.parametrize("lmax,task", [(1, "node"), (2, "graph")])
+def test_max_aggregation(lmax, task):
+    """message_passing_agg = "max" (jraph.segment_max, models/nequip.py:118-120): forward picks the maximum of every
+    message component over a receiver's edges, the backward routes the gradient to the winning edge."""
+    rng = np.random.default_rng(31 + lmax)
+    B, N, k = 2, 140, 9
+    x = rng.normal(size=(B, N, 7)).astype(np.float32)
+    x[..., :3] = rng.uniform(-1.7, 1.7, size=(B, N, 3))
+    kw = dict(d_hidden=64, l_max=lmax, sphharm_norm="integral", message_passing_steps=2, n_layers=2, n_outputs=2,
+              n_radial_basis=16, r_cutoff=0.6, message_passing_agg="max", task=task)
+    cfg, tree, g, model, gg, params = _setup(kw, x, k, seed=3)
+    cot = rng.normal(size=(B, N, 7) if task == "node" else (B, 2))
+    _check_all(model, params, gg, cfg, tree, g, cot)
+
+
+def test_silu_radial_mlp_on_fused_route():
+    """activation = "silu" (models/nequip.py:61 getattr(nn, activation)): the fused kernels evaluate x sigma(x) with the
+    silu constants; the backward takes the recompute variant."""
+    from eqnn_jax_b200 import ops
+    rng = np.random.default_rng(77)
+    B, N, k = 2, 300, 16
+    x = rng.normal(size=(B, N, 7)).astype(np.float32)
+    x[..., :3] = rng.uniform(-1.7, 1.7, size=(B, N, 3))
+    kw = dict(d_hidden=128, l_max=2, sphharm_norm="integral", message_passing_steps=2, n_layers=2, n_outputs=2,
+              n_radial_basis=32, r_cutoff=0.6, message_passing_agg="mean", task="graph", activation="silu")
+    cfg, tree, g, model, gg, params = _setup(kw, x, k, seed=5)
+    cot = rng.normal(size=(B, 2))
+    ops.TIMER = ops.KernelTimer()
+    try:
+        _check_all(model, params, gg, cfg, tree, g, cot)
+        tags = ops.TIMER.summary()
+    finally:
+        ops.TIMER = None
+    assert tags.get("radial_mlp_fwd", (0, 0))[0] == 2 and tags.get("radial_mlp_bwd", (0, 0))[0] == 2, tags
