@@ -125,6 +125,32 @@ def lib() -> C.CDLL:
     return _lib
 
 
+def reload() -> C.CDLL:
+    """Loads the library again after a rebuild (new tensor-product signature).  dlopen caches by path, so the rebuilt
+    file is opened through a fresh hard link; the old image stays mapped but is no longer used."""
+    global _lib, _generation
+    _generation += 1
+    link = f"{LIB_PATH}.{os.getpid()}.{_generation}.so"
+    if os.path.exists(link):
+        os.remove(link)
+    try:
+        os.link(LIB_PATH, link)
+    except OSError:
+        import shutil
+        shutil.copy(LIB_PATH, link)
+    L = C.CDLL(link)
+    os.remove(link)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return _lib
+
+
+_generation = 0
+
+
 def check(status: int, what: str = "") -> None:
     if status != 0:
         msg = lib().eqnn_last_error_string().decode()

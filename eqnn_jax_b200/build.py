@@ -33,11 +33,38 @@ def _stale(target: str, deps) -> bool:
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
+EXTRA_SIGS = os.path.join(CSRC, "gen", "extra_signatures.json")
+
+
+def extra_signatures():
+    """Tensor-product signatures beyond codegen.PREBUILT, added on first use (add_tp_signature): [x irreps, lmax, live]."""
+    import json
+    if not os.path.exists(EXTRA_SIGS):
+        return []
+    return [tuple(t) for t in json.load(open(EXTRA_SIGS))]
+
+
+def add_tp_signature(x_irreps: str, lmax: int, live: str) -> bool:
+    """models/nequip.py:124 accepts any node irreps; the interaction kernels are generated per (x irreps, lmax, live
+    irreps) signature.  Registers a new one, regenerates csrc/gen/tp_gen.cuh and rebuilds the library (nvcc, well under a
+    minute).  Returns True if the library changed; the caller reloads it (_lib.reload)."""
+    import json
+    sigs = extra_signatures()
+    key = (str(x_irreps), int(lmax), str(live))
+    if key in sigs:
+        return False
+    sigs.append(key)
+    os.makedirs(os.path.dirname(EXTRA_SIGS), exist_ok=True)
+    json.dump([list(t) for t in sigs], open(EXTRA_SIGS, "w"))
+    build_library()
+    return True
+
+
 def build_library(force: bool = False, verbose: bool = False) -> str:
     from . import codegen
 
     gen = os.path.join(CSRC, "gen", "tp_gen.cuh")
-    codegen.generate(gen)
+    codegen.generate(gen, list(codegen.PREBUILT) + extra_signatures())
     headers = [os.path.join(CSRC, "common.cuh"), gen, os.path.join(HERE, "..", "include", "eqnn_b200.h"),
                os.path.join(CSRC, "tc_common.cuh"), os.path.join(CSRC, "rmlp_common.cuh")]
     objdir = os.path.join(CSRC, "build")

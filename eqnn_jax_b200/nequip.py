@@ -137,8 +137,11 @@ class _Plan:
         # their messages, gates and weights cannot influence outputs, and their gradients are exact zeros
         # in the reference as well.
         # (0e is always kept: scalar messages feed the gate scalars of the surviving l>0 irreps.)
-        self.tp = make_tp_plan(irreps_in, cfg.l_max, upd.filter(keep=irreps_in + Irreps("1x0e")))
+        live = upd.filter(keep=irreps_in + Irreps("1x0e"))
+        self.tp = make_tp_plan(irreps_in, cfg.l_max, live)
         self.tp_sig = self.tp.signature
+        # (x irreps, lmax, live irreps): lets a signature outside codegen.PREBUILT be generated and compiled on first use
+        self.tp_spec = (str(irreps_in), cfg.l_max, str(live))
         self.upd = upd
         scal = [(m, l, p) for m, l, p in upd if l == 0]
         gated = [(m, l, p) for m, l, p in upd if l > 0]
@@ -242,6 +245,7 @@ class _Plan:
                 self.d_out = D
         elif cfg.task == "graph":
             self.tp_ro = make_tp_plan(irreps_in, cfg.l_max, "0e")
+            self.tp_ro_spec = (str(irreps_in), cfg.l_max, "0e")
             # constant regroup + pad matrix  h (stored) -> x (regrouped, padded)
             self.P = self._new_dense(D, self.tp_ro.dxp)
             for r, s_off in enumerate(irreps_in.regroup_index_map()):
@@ -573,7 +577,7 @@ def _forward(model: NequIP, plan: _Plan, theta: torch.Tensor, pg: PreparedGraph,
     tab = plan.device_tables(dev)
     wexp = torch.empty((plan._n_exp,), **f32)
     ops.weights_expand(theta, tab["exp_idx"], tab["exp_scale"], wexp)
-    tp_id = ops.tp_lookup(plan.tp_sig)
+    tp_id = ops.tp_lookup(plan.tp_sig, plan.tp_spec)
     dxp, n_live, d_live = plan.tp.dxp, plan.tp.n_live, plan.tp.d_live
     agg = ops.AGG[model.message_passing_agg]
     inv_sqrt_k = 1.0 / math.sqrt(k)
@@ -633,7 +637,7 @@ def _forward(model: NequIP, plan: _Plan, theta: torch.Tensor, pg: PreparedGraph,
         return o.view(B, N, -1), saved
     # ---- graph read-out (nequip.py:172-214)
     tpr = plan.tp_ro
-    ro_id = ops.tp_lookup(tpr.signature)
+    ro_id = ops.tp_lookup(tpr.signature, plan.tp_ro_spec)
     attrs = torch.empty((Nt, tpr.ny), **f32)
     ops.sh_scatter(model.l_max, pg.rowptr, pg.geom, Nt, 1.0 / k, attrs)
     hr = torch.empty((Nt, tpr.dxp), **f32)

@@ -65,8 +65,15 @@ def _req(t: torch.Tensor, dtype, name: str, contiguous: bool = True) -> torch.Te
 
 
 # ---------------------------------------------------------------- signatures
-def tp_lookup(signature: str) -> int:
+def tp_lookup(signature: str, spec=None) -> int:
+    """Id of a compiled tensor-product signature.  spec = (x irreps, lmax, live irreps) lets an unknown signature be
+    generated, compiled and loaded on first use (eqnn_jax_b200.build.add_tp_signature)."""
     i = lib().eqnn_tp_lookup(signature.encode())
+    if i < 0 and spec is not None:
+        from . import _lib as L, build
+        build.add_tp_signature(*spec)
+        L.reload()
+        i = lib().eqnn_tp_lookup(signature.encode())
     if i < 0:
         have = [lib().eqnn_tp_signature(j).decode() for j in range(lib().eqnn_tp_signature_count())]
         raise RuntimeError(

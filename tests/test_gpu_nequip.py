@@ -6,6 +6,7 @@ The oracle runs in float64 with the reference's fp32 rounding points on the ill-
 inputs (edge length, Bessel phase), see oracle/e3nn_ref.py:bessel.
 """
 import dataclasses
+import os
 
 import numpy as np
 import pytest
@@ -475,3 +476,42 @@ def test_silu_radial_mlp_on_fused_route():
     finally:
         ops.TIMER = None
     assert tags.get("radial_mlp_fwd", (0, 0))[0] == 2 and tags.get("radial_mlp_bwd", (0, 0))[0] == 2, tags
+
+
+def test_other_input_irreps_are_compiled_on_first_use():
+    """models/nequip.py:124 takes any node irreps whose first chunk is a vector.  The interaction kernels are generated
+    per signature: one outside codegen.PREBUILT is generated, compiled (nvcc) and loaded the first time it is used."""
+    import shutil
+    if shutil.which("nvcc") is None and not os.path.exists("/usr/local/cuda/bin/nvcc"):
+        pytest.skip("no nvcc on this machine: new tensor-product signatures cannot be compiled")
+    from eqnn_jax_b200 import graph_utils as GU
+    from eqnn_jax_b200.irreps import Irreps
+    from eqnn_jax_b200.nequip import IrrepsArray, NequIP
+    irr = "1o+2x0e"
+    rng = np.random.default_rng(9)
+    B, N, k = 2, 90, 8
+    x = rng.normal(size=(B, N, 5)).astype(np.float32)
+    kw = dict(d_hidden=64, l_max=2, sphharm_norm="integral", message_passing_steps=2, n_layers=2, n_outputs=2,
+              n_radial_basis=16, r_cutoff=0.6, message_passing_agg="mean", task="graph")
+    g = G.build_graph(x, None, k)
+    cfg = NQ.NequIPConfig(**kw)
+    tree = NQ.init_params(cfg, irr, seed=4)
+    model = NequIP(**kw)
+    gg = GU.GraphsTuple(nodes=IrrepsArray(Irreps(irr), torch.tensor(x).cuda()), edges=None,
+                        receivers=torch.tensor(g.receivers).cuda(), senders=torch.tensor(g.senders).cuda(),
+                        globals=None, n_node=torch.tensor(g.n_node), n_edge=torch.tensor(g.n_edge))
+    params = model.init(0, gg)
+    params.load_tree(tree)
+    cot = rng.normal(size=(B, 2))
+    want, grads = _oracle(cfg, tree, g, irr, cot)
+    out = model.forward_backward(params, gg, lambda o: torch.tensor(cot, dtype=torch.float32).cuda())
+    _close(out.cpu().numpy(), want, "output")
+    gt, ms = params.grad_tree, _module_scales(grads)
+    for path, w in _leaves(grads):
+        a = gt
+        for q_ in path:
+            a = a[q_]
+        if np.abs(w.grad.numpy()).max() == 0:
+            assert float(a.abs().max()) == 0.0
+            continue
+        _close(a.cpu().numpy(), w.grad.numpy(), "grad " + "/".join(path), scale=ms[path[0]])
