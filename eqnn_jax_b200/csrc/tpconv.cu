@@ -21,6 +21,9 @@ namespace {
 
 constexpr int TPC_THREADS = 128;
 constexpr int TPC_ROWS = 6;
+#ifndef TPC_BWD_MIN_CTAS
+#define TPC_BWD_MIN_CTAS 12
+#endif
 
 template <class TP>
 __device__ __forceinline__ void load_x(const float* __restrict__ xt, int s, float* x) {
@@ -39,6 +42,13 @@ __device__ __forceinline__ void load_x(const float* __restrict__ xt, int s, floa
 // over the row's edges and the CSR position of the FIRST edge that attains it is recorded, so that the backward
 // pass can route the gradient to that edge alone (ties are measure-zero for real messages; the self-loop's exact
 // zeros in the l > 0 components can tie only with another exact zero).
+// message row stride in floats: a multiple of 4 with an odd number of 16-byte groups, so that the 128-bit stores of 8
+// consecutive lanes (one per edge) fall into 8 distinct bank groups
+__host__ __device__ constexpr int tpc_stride(int dl) {
+  int s = (dl + 3) / 4 * 4;
+  return ((s / 4) & 1) ? s : s + 4;
+}
+
 template <class TP, bool AMAX>
 __global__ void __launch_bounds__(TPC_THREADS)
 tpconv_fwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src,
@@ -46,9 +56,10 @@ tpconv_fwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
                   const float* __restrict__ xt, int n_nodes, int agg, float* __restrict__ A, int ld_a,
                   int32_t* __restrict__ argmax) {
   constexpr int DL = TP::DLIVE;
-  constexpr int STRIDE = DL | 1;
-  constexpr int ITEMS = (TPC_ROWS * DL + TPC_THREADS - 1) / TPC_THREADS;
-  __shared__ float sm[TPC_THREADS * STRIDE];
+  constexpr int S = tpc_stride(DL), S4 = S / 4;
+  constexpr int NQ = (DL + 3) / 4;                      // component quads per row
+  constexpr int ITEMS = (TPC_ROWS * NQ + TPC_THREADS - 1) / TPC_THREADS;
+  __shared__ __align__(16) float sm[TPC_THREADS * S];
   __shared__ int s_rowptr[TPC_ROWS + 1];
   const int tid = threadIdx.x;
   const int r0 = blockIdx.x * TPC_ROWS;
@@ -56,12 +67,13 @@ tpconv_fwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
   if (tid <= nr) s_rowptr[tid] = rowptr[r0 + tid];
   __syncthreads();
   const int p0 = s_rowptr[0], p1 = s_rowptr[nr];
-  float acc[ITEMS];
-  int amax[ITEMS];
+  float4 acc[ITEMS];
+  int4 amax[ITEMS];
 #pragma unroll
   for (int it = 0; it < ITEMS; ++it) {
-    acc[it] = AMAX ? -INFINITY : 0.f;
-    amax[it] = -1;
+    const float v0 = AMAX ? -INFINITY : 0.f;
+    acc[it] = make_float4(v0, v0, v0, v0);
+    amax[it] = make_int4(-1, -1, -1, -1);
   }
 
   for (int base = p0; base < p1; base += TPC_THREADS) {
@@ -69,43 +81,52 @@ tpconv_fwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
     if (p < p1) {
       const int s = src[p];
       const float4 g = geom[p];
-      float x[TP::DXP], w[TP::NLIVE], Y[TP::NY], m[DL];
+      float x[TP::DXP], w[TP::NLIVE], Y[TP::NY];
+      __align__(16) float m[S];
       load_x<TP>(xt, s, x);
 #pragma unroll
       for (int c = 0; c < TP::NLIVE; ++c) w[c] = w_t[(size_t)c * n_edges + p];
       TP::sh(g.x, g.y, g.z, Y);
-      TP::fwd(x, Y, w, m);
 #pragma unroll
-      for (int i = 0; i < DL; ++i) sm[tid * STRIDE + i] = m[i];
+      for (int i = DL; i < S; ++i) m[i] = 0.f;
+      TP::fwd(x, Y, w, m);
+      float4* dst = reinterpret_cast<float4*>(sm + tid * S);
+#pragma unroll
+      for (int i = 0; i < NQ; ++i) dst[i] = make_float4(m[4 * i], m[4 * i + 1], m[4 * i + 2], m[4 * i + 3]);
     }
     __syncthreads();
 #pragma unroll
     for (int it = 0; it < ITEMS; ++it) {
       const int item = tid + it * TPC_THREADS;
-      if (item < nr * DL) {
-        const int row = item / DL, comp = item - row * DL;
+      if (item < nr * NQ) {
+        const int row = item / NQ, quad = item - row * NQ;
         const int lo = max(s_rowptr[row], base) - base;
         const int hi = min(s_rowptr[row + 1], base + TPC_THREADS) - base;
-        float a = acc[it];
-        const float* col = sm + comp;
+        float4 a = acc[it];
+        const float4* col = reinterpret_cast<const float4*>(sm + 4 * quad);
         int q = lo;
         if (AMAX) {
-          int am = amax[it];
+          int4 am = amax[it];
           for (; q < hi; ++q) {
-            const float v = col[q * STRIDE];
-            if (v > a) {
-              a = v;
-              am = base + q;
-            }
+            const float4 v = col[q * S4];
+            if (v.x > a.x) { a.x = v.x; am.x = base + q; }
+            if (v.y > a.y) { a.y = v.y; am.y = base + q; }
+            if (v.z > a.z) { a.z = v.z; am.z = base + q; }
+            if (v.w > a.w) { a.w = v.w; am.w = base + q; }
           }
           amax[it] = am;
         }
-        for (; q + 3 < hi; q += 4) {                 // same ascending order, a quarter of the loop overhead
-          const float v0 = col[q * STRIDE], v1 = col[(q + 1) * STRIDE], v2 = col[(q + 2) * STRIDE],
-                      v3 = col[(q + 3) * STRIDE];
-          a = (((a + v0) + v1) + v2) + v3;
+        for (; q + 1 < hi; q += 2) {                   // ascending order: the order of a sequential scatter-add
+          const float4 v0 = col[q * S4], v1 = col[(q + 1) * S4];
+          a.x = (a.x + v0.x) + v1.x;
+          a.y = (a.y + v0.y) + v1.y;
+          a.z = (a.z + v0.z) + v1.z;
+          a.w = (a.w + v0.w) + v1.w;
         }
-        for (; q < hi; ++q) a += col[q * STRIDE];
+        if (q < hi) {
+          const float4 v = col[q * S4];
+          a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
         acc[it] = a;
       }
     }
@@ -114,24 +135,30 @@ tpconv_fwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
 #pragma unroll
   for (int it = 0; it < ITEMS; ++it) {
     const int item = tid + it * TPC_THREADS;
-    if (item < nr * DL) {
-      const int row = item / DL, comp = item - row * DL;
-      float a = acc[it];
-      if (agg == 1) {
-        const int deg = s_rowptr[row + 1] - s_rowptr[row];
-        a = a / (float)max(deg, 1);
+    if (item < nr * NQ) {
+      const int row = item / NQ, quad = item - row * NQ;
+      const float a[4] = {acc[it].x, acc[it].y, acc[it].z, acc[it].w};
+      const int am[4] = {amax[it].x, amax[it].y, amax[it].z, amax[it].w};
+      const float deg = (float)max(s_rowptr[row + 1] - s_rowptr[row], 1);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int comp = 4 * quad + j;
+        if (comp < DL) {
+          float v = a[j];
+          if (agg == 1) v = v / deg;
+          if (AMAX) {
+            if (am[j] < 0) v = 0.f;                    // receiver without incoming edges (cannot happen with self-loops)
+            argmax[(size_t)(r0 + row) * DL + comp] = am[j];
+          }
+          A[(size_t)(r0 + row) * ld_a + comp] = v;
+        }
       }
-      if (AMAX) {
-        if (amax[it] < 0) a = 0.f;                   // receiver without incoming edges (cannot happen with self-loops)
-        argmax[(size_t)(r0 + row) * DL + comp] = amax[it];
-      }
-      A[(size_t)(r0 + row) * ld_a + comp] = a;
     }
   }
 }
 
 template <class TP, bool AMAX>
-__global__ void __launch_bounds__(TPC_THREADS)
+__global__ void __launch_bounds__(TPC_THREADS, (TP::DLIVE <= 24 ? TPC_BWD_MIN_CTAS : 8))
 tpconv_bwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src,
                   const int32_t* __restrict__ perm, const float4* __restrict__ geom,
                   const float* __restrict__ w_t, int64_t n_edges, const float* __restrict__ xt, int n_nodes,
@@ -344,10 +371,68 @@ extern "C" int eqnn_tpconv_bwd(int tp_id, const int32_t* rowptr, const int32_t* 
   return EQNN_OK;
 }
 
+// 128-bit variants (dxp a multiple of 4, 16-byte aligned buffers): one thread per (sender, component quad); the
+// threads of a sender read whole 32-byte sectors of its records
+__global__ void sender_reduce4_kernel(const float4* __restrict__ dxe, int n_nodes, int k, int q4, float4* __restrict__ dxt) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)n_nodes * q4) return;
+  const int64_t s = i / q4;
+  const int c = (int)(i - s * q4);
+  const float4* p = dxe + (size_t)s * k * q4 + c;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  int j = 0;
+  for (; j + 3 < k; j += 4) {                     // four independent loads in flight, summed in ascending edge order
+    const float4 v0 = __ldg(p + (size_t)j * q4), v1 = __ldg(p + (size_t)(j + 1) * q4), v2 = __ldg(p + (size_t)(j + 2) * q4),
+                 v3 = __ldg(p + (size_t)(j + 3) * q4);
+    a.x = (((a.x + v0.x) + v1.x) + v2.x) + v3.x;
+    a.y = (((a.y + v0.y) + v1.y) + v2.y) + v3.y;
+    a.z = (((a.z + v0.z) + v1.z) + v2.z) + v3.z;
+    a.w = (((a.w + v0.w) + v1.w) + v2.w) + v3.w;
+  }
+  for (; j < k; ++j) {
+    const float4 v = __ldg(p + (size_t)j * q4);
+    a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+  }
+  dxt[i] = a;
+}
+__global__ void segment_gather_sum4_kernel(const float4* __restrict__ dxe, const int32_t* __restrict__ rowptr_s,
+                                           const int32_t* __restrict__ perm_s, int n_nodes, int q4,
+                                           float4* __restrict__ dxt) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)n_nodes * q4) return;
+  const int64_t s = i / q4;
+  const int c = (int)(i - s * q4);
+  const int q1 = rowptr_s[s + 1];
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  int q = rowptr_s[s];
+  for (; q + 3 < q1; q += 4) {
+    const int e0 = perm_s[q], e1 = perm_s[q + 1], e2 = perm_s[q + 2], e3 = perm_s[q + 3];
+    const float4 v0 = __ldg(dxe + (size_t)e0 * q4 + c), v1 = __ldg(dxe + (size_t)e1 * q4 + c),
+                 v2 = __ldg(dxe + (size_t)e2 * q4 + c), v3 = __ldg(dxe + (size_t)e3 * q4 + c);
+    a.x = (((a.x + v0.x) + v1.x) + v2.x) + v3.x;
+    a.y = (((a.y + v0.y) + v1.y) + v2.y) + v3.y;
+    a.z = (((a.z + v0.z) + v1.z) + v2.z) + v3.z;
+    a.w = (((a.w + v0.w) + v1.w) + v2.w) + v3.w;
+  }
+  for (; q < q1; ++q) {
+    const float4 v = __ldg(dxe + (size_t)perm_s[q] * q4 + c);
+    a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+  }
+  dxt[i] = a;
+}
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 extern "C" int eqnn_sender_reduce(const float* dxe, int n_nodes, int k, int dxp, float* dxt,
                                   eqnn_stream_t stream) {
   EQNN_CHECK_ARG(dxe && dxt && k >= 1 && dxp >= 1, "sender_reduce: bad argument");
   if (n_nodes <= 0) return EQNN_OK;
+  if ((dxp & 3) == 0 && aligned16(dxe) && aligned16(dxt)) {
+    const int64_t n4 = (int64_t)n_nodes * (dxp / 4);
+    sender_reduce4_kernel<<<(unsigned)ceil_div64(n4, 128), 128, 0, as_stream(stream)>>>(
+        reinterpret_cast<const float4*>(dxe), n_nodes, k, dxp / 4, reinterpret_cast<float4*>(dxt));
+    EQNN_CHECK_LAUNCH();
+    return EQNN_OK;
+  }
   const int64_t n = (int64_t)n_nodes * dxp;
   sender_reduce_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, as_stream(stream)>>>(dxe, n_nodes, k, dxp, dxt);
   EQNN_CHECK_LAUNCH();
@@ -358,6 +443,13 @@ extern "C" int eqnn_segment_gather_sum(const float* dxe, const int32_t* rowptr_s
                                        int n_nodes, int dxp, float* dxt, eqnn_stream_t stream) {
   EQNN_CHECK_ARG(dxe && rowptr_s && perm_s && dxt && dxp >= 1, "segment_gather_sum: bad argument");
   if (n_nodes <= 0) return EQNN_OK;
+  if ((dxp & 3) == 0 && aligned16(dxe) && aligned16(dxt)) {
+    const int64_t n4 = (int64_t)n_nodes * (dxp / 4);
+    segment_gather_sum4_kernel<<<(unsigned)ceil_div64(n4, 128), 128, 0, as_stream(stream)>>>(
+        reinterpret_cast<const float4*>(dxe), rowptr_s, perm_s, n_nodes, dxp / 4, reinterpret_cast<float4*>(dxt));
+    EQNN_CHECK_LAUNCH();
+    return EQNN_OK;
+  }
   const int64_t n = (int64_t)n_nodes * dxp;
   segment_gather_sum_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, as_stream(stream)>>>(dxe, rowptr_s, perm_s,
                                                                                         n_nodes, dxp, dxt);

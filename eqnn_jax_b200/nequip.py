@@ -764,6 +764,10 @@ def _backward(model: NequIP, plan: _Plan, theta: torch.Tensor, pg: PreparedGraph
                 dh_prev.zero_()
         # interaction block
         ops.tpconv_bwd(tp_id, pg.rowptr, pg.src, pg.perm, pg.geom, w_t, xt, Nt, agg, dA, d_live, dw_t, dxe, sv["amax"])
+        # sender side: dxt = sum over each sender's edges -- right behind the kernel that wrote dxe, while the tail of
+        # it is still in L2 (the radial-MLP backward in between streams gigabytes)
+        dxt = torch.empty((Nt, dxp), **f32)
+        ops.segment_gather_sum(dxe, pg.rowptr_s, pg.perm_s, Nt, dxp, dxt)
         # radial MLP backward
         mlp = st["mlp"]
         nh = len(mlp) - 1
@@ -795,9 +799,7 @@ def _backward(model: NequIP, plan: _Plan, theta: torch.Tensor, pg: PreparedGraph
                     _mm(Et, fan_l, hdim, al, dZ, 0, hdim, theta, koff, hdim, dZp, 0, fan_l, tb=True,
                         epi=2, aux=Zs[l - 1], ld_aux=fan_l, epi_scale=plan.inv_c_act, tag="radial_mlp_bwd", tf32x3=model.tensor_cores)
                     dZ = dZp
-        # sender side: dxt = sum over each sender's edges, then through W0x
-        dxt = torch.empty((Nt, dxp), **f32)
-        ops.segment_gather_sum(dxe, pg.rowptr_s, pg.perm_s, Nt, dxp, dxt)
+        # sender side, through W0x
         _mm(Nt, D, dxp, 1.0, dxt, 0, dxp, wexp, st["W0x"].off, dxp, dh_prev, 0, D, tb=True, accumulate=True)
         _mm(D, dxp, Nt, 1.0, h, 0, D, dxt, 0, dxp, gwexp, st["W0x"].off, dxp, ta=True)
         dh = dh_prev

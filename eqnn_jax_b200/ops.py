@@ -182,8 +182,11 @@ def sender_reduce(dxe, n_nodes, k, dxp, dxt):
 
 
 def segment_gather_sum(dxe, rowptr_s, perm_s, n_nodes, dxp, dxt):
+    t0 = TIMER.begin() if TIMER else None
     check(lib().eqnn_segment_gather_sum(_ptr(dxe), _ptr(rowptr_s), _ptr(perm_s), n_nodes, dxp, _ptr(dxt), _stream()),
           "segment_gather_sum")
+    if TIMER:
+        TIMER.end("sender_reduce", t0)
 
 
 def sh_scatter(lmax, rowptr, geom, n_nodes, scale, attrs):
