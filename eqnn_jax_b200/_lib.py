@@ -49,6 +49,8 @@ SIGNATURES: Dict[str, tuple] = {
     "eqnn_radial_mlp_bwd": (_i, [_p, _i64, _i64, _i, _d, _i, _i, _p, _p, _i, _i, _f, _p, _i64, _p, _p, _p, _p, _sz, _p]),
     "eqnn_gate_fwd": (_i, [_p, _i64, _i, _i, _i, _p, _p, _f, _f, _p, _p]),
     "eqnn_gate_bwd": (_i, [_p, _p, _i64, _i, _i, _i, _p, _p, _f, _f, _p, _p]),
+    "eqnn_gate_act_fwd": (_i, [_p, _i64, _i, _i, _i, _p, _p, _i, _f, _f, _p, _p]),
+    "eqnn_gate_act_bwd": (_i, [_p, _p, _i64, _i, _i, _i, _p, _p, _i, _f, _f, _p, _p]),
     "eqnn_node_update_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "eqnn_node_update_fwd": (_i, [_p, _i, _i, _p, _i, _p, _f, _p, _i, _i, _i, _p, _p, _f, _f, _p, _p, _i, _i64, _p, _p,
                                   _p, _p]),
@@ -88,8 +90,11 @@ SIGNATURES: Dict[str, tuple] = {
     "eqnn_dense_wgrad_f32": (_i, [_i64, _i64, _i64, _f, _p, _i64, _i, _f, _p, _i64, _p, _i64, _p, _i, _p, _sz, _p]),
     "eqnn_colsum_workspace_bytes": (_sz, [_i]),
     "eqnn_colsum_tall": (_i, [_p, _i64, _i, _p, _p, _sz, _p]),
+    "eqnn_tp_messages": (_i, [_i, _p, _p, _p, _p, _i, _p, _p, _p, _i64, _p, _i, _p]),
     "eqnn_pool_fwd": (_i, [_p, _i, _i, _i, _i, _p, _p]),
     "eqnn_pool_bwd": (_i, [_p, _i, _i, _i, _i, _p, _p]),
+    "eqnn_pool_max_fwd": (_i, [_p, _i, _i, _i, _p, _p, _p]),
+    "eqnn_pool_max_bwd": (_i, [_p, _p, _i, _i, _i, _p, _p]),
     "eqnn_colsum": (_i, [_p, _i64, _i, _p, _p]),
     "eqnn_layernorm_fwd": (_i, [_p, _i, _p, _i, _i, _p, _p, _f, _p, _p, _p]),
     "eqnn_layernorm_bwd": (_i, [_p, _i, _p, _i, _i, _p, _p, _p, _p, _p, _p, _p]),

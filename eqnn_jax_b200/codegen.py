@@ -12,19 +12,20 @@ Run at build time by ``__graft_entry__.build()``; output: csrc/gen/tp_gen.cuh.
 from __future__ import annotations
 
 import os
-from typing import Dict, Iterable, List, Tuple
+from typing import Dict, Iterable, List, Optional, Tuple
 
 from . import so3
 from .plan import TPPlan, make_tp_plan
 
 # Signatures compiled into the library: (x irreps, lmax, live irreps or None)
 _HIDDEN_LIVE = {1: "0e+1o", 2: "0e+1o+2e", 3: "0e+1o+2e+3o"}
-PREBUILT: List[Tuple[str, int, str]] = []
+PREBUILT: List[Tuple[str, int, Optional[str]]] = []
 for _x in ("1o+1o+1x0e", "1o"):
     for _l in (1, 2, 3):
         PREBUILT.append((_x, _l, _HIDDEN_LIVE[_l]))   # interaction block (nequip.py:52), all hidden irreps
         PREBUILT.append((_x, _l, "0e+1o"))            # interaction block, irreps that survive nequip.py:162
         PREBUILT.append((_x, _l, "0e"))               # invariant read-out (nequip.py:197)
+        PREBUILT.append((_x, _l, None))               # every message column: the node task's `edges` output (:154-171)
 
 
 def _f(v: float) -> str:

@@ -7,9 +7,19 @@ namespace {
 constexpr int MAX_GATE_CHUNKS = 8;
 struct GateDesc {
   int n_extra, n_gates, n_chunks, d_gated;
+  int act;                 // scalar activation: EQNN_ACT_GELU (tanh form) or EQNN_ACT_SILU (models/segnn.py:27,56)
   int mul[MAX_GATE_CHUNKS], dim[MAX_GATE_CHUNKS];
   float inv_c_act, inv_c_gate;
 };
+
+__device__ __forceinline__ float gate_act(float x, int kind) { return kind == EQNN_ACT_SILU ? x * sigmoid_acc(x) : gelu_tanh(x); }
+__device__ __forceinline__ float gate_act_grad(float x, int kind) {
+  if (kind == EQNN_ACT_SILU) {
+    const float sg = sigmoid_acc(x);
+    return sg + x * sg * (1.f - sg);
+  }
+  return gelu_tanh_grad(x);
+}
 
 // gated component j -> index of its gate
 __device__ __forceinline__ int gate_index(const GateDesc& d, int j) {
@@ -37,7 +47,7 @@ __global__ void gate_fwd_kernel(const float* __restrict__ z, int64_t n, GateDesc
   const float* zr = z + row * d_in;
   float v;
   if (c < d.n_extra) {
-    v = gelu_tanh(zr[c]) * d.inv_c_act;
+    v = gate_act(zr[c], d.act) * d.inv_c_act;
   } else {
     const int j = c - d.n_extra;
     const float g = sigmoid_acc(zr[d.n_extra + gate_index(d, j)]) * d.inv_c_gate;
@@ -62,7 +72,7 @@ __global__ void gate_fwd_rows_kernel(const float* __restrict__ z, int64_t n, Gat
   for (int64_t r = r0; r < r1; ++r) {
     const float* zr = z + r * d_in;
     const float x = zr[src];
-    out[r * d_out + c] = c < d.n_extra ? gelu_tanh(x) * d.inv_c_act : (sigmoid_acc(zr[gate]) * d.inv_c_gate) * x;
+    out[r * d_out + c] = c < d.n_extra ? gate_act(x, d.act) * d.inv_c_act : (sigmoid_acc(zr[gate]) * d.inv_c_gate) * x;
   }
 }
 
@@ -95,7 +105,7 @@ __global__ void gate_bwd_rows_kernel(const float* __restrict__ z, const float* _
     const float* gr = gout + r * d_out;
     float v;
     if (kind == 0) {
-      v = gr[c] * gelu_tanh_grad(zr[c]) * d.inv_c_act;
+      v = gr[c] * gate_act_grad(zr[c], d.act) * d.inv_c_act;
     } else if (kind == 1) {
       float s = 0.f;
       for (int q = 0; q < dim; ++q) s += gr[d.n_extra + off + q] * zr[d.n_extra + d.n_gates + off + q];
@@ -121,7 +131,7 @@ __global__ void gate_bwd_kernel(const float* __restrict__ z, const float* __rest
   const float* gr = gout + row * d_out;
   float v;
   if (c < d.n_extra) {
-    v = gr[c] * gelu_tanh_grad(zr[c]) * d.inv_c_act;
+    v = gr[c] * gate_act_grad(zr[c], d.act) * d.inv_c_act;
   } else if (c < d.n_extra + d.n_gates) {
     // gate number gi: find its chunk and component range
     int gi = c - d.n_extra, off = 0, dim = 1;
@@ -146,6 +156,7 @@ __global__ void gate_bwd_kernel(const float* __restrict__ z, const float* __rest
 
 int make_gate_desc(GateDesc& d, int n_extra, int n_gates, int n_chunks, const int* mul, const int* l,
                    float inv_c_act, float inv_c_gate) {
+  d.act = EQNN_ACT_GELU;
   EQNN_CHECK_ARG(n_chunks >= 0 && n_chunks <= MAX_GATE_CHUNKS, "gate: too many gated chunks");
   EQNN_CHECK_ARG(n_chunks == 0 || (mul && l), "gate: null chunk arrays");
   d.n_extra = n_extra; d.n_gates = n_gates; d.n_chunks = n_chunks; d.d_gated = 0;
@@ -186,6 +197,54 @@ __global__ void pool_bwd_kernel(const float* __restrict__ gout, int B, int N, in
   const int c = (int)(i % D);
   const int64_t b = i / ((int64_t)N * D);
   gx[i] = gout[b * D + c] * scale;
+}
+
+// jnp.max over the nodes of a graph (readout_agg = "max", models/nequip.py:195-199): value and the index of the FIRST
+// node attaining it (the gradient is routed to that node alone)
+__global__ void pool_max_fwd_kernel(const float* __restrict__ x, int B, int N, int D, float* __restrict__ out,
+                                    int32_t* __restrict__ arg) {
+  __shared__ float sv[8][33];
+  __shared__ int si[8][33];
+  const int b = blockIdx.y, c = blockIdx.x * 32 + threadIdx.x;
+  float a = -INFINITY;
+  int ia = -1;
+  if (c < D)
+    for (int n = threadIdx.y; n < N; n += 8) {
+      const float v = x[((size_t)b * N + n) * D + c];
+      if (v > a || ia < 0) {
+        a = v;
+        ia = n;
+      }
+    }
+  sv[threadIdx.y][threadIdx.x] = a;
+  si[threadIdx.y][threadIdx.x] = ia;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < D) {
+    float m = sv[0][threadIdx.x];
+    int im = si[0][threadIdx.x];
+#pragma unroll
+    for (int q = 1; q < 8; ++q) {
+      const float v = sv[q][threadIdx.x];
+      const int iv = si[q][threadIdx.x];
+      if (iv >= 0 && (im < 0 || v > m || (v == m && iv < im))) {
+        m = v;
+        im = iv;
+      }
+    }
+    out[(size_t)b * D + c] = m;
+    arg[(size_t)b * D + c] = im;
+  }
+}
+
+__global__ void pool_max_bwd_kernel(const float* __restrict__ gout, const int32_t* __restrict__ arg, int B, int N, int D,
+                                    float* __restrict__ gx) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)B * N * D) return;
+  const int c = (int)(i % D);
+  const int64_t bn = i / D;
+  const int64_t b = bn / N;
+  const int n = (int)(bn - b * N);
+  gx[i] = (arg[b * D + c] == n) ? gout[b * D + c] : 0.f;
 }
 
 __global__ void colsum_kernel(const float* __restrict__ x, int64_t M, int N, float* __restrict__ y) {
@@ -328,12 +387,15 @@ __global__ void layernorm_wgrad_kernel(const float* __restrict__ a, int da, cons
 
 }  // namespace
 
-extern "C" int eqnn_gate_fwd(const float* z, int64_t n, int n_extra, int n_gates, int n_chunks, const int* mul,
-                             const int* l, float inv_c_act, float inv_c_gate, float* out, eqnn_stream_t stream) {
+extern "C" int eqnn_gate_act_fwd(const float* z, int64_t n, int n_extra, int n_gates, int n_chunks, const int* mul,
+                                 const int* l, int activation, float inv_c_act, float inv_c_gate, float* out,
+                                 eqnn_stream_t stream) {
   EQNN_CHECK_ARG(z && out && n >= 0, "gate_fwd: bad argument");
+  EQNN_CHECK_ARG(activation == EQNN_ACT_GELU || activation == EQNN_ACT_SILU, "gate_fwd: unknown activation");
   GateDesc d;
   int rc = make_gate_desc(d, n_extra, n_gates, n_chunks, mul, l, inv_c_act, inv_c_gate);
   if (rc) return rc;
+  d.act = activation;
   const int64_t tot = n * (d.n_extra + d.d_gated);
   if (tot == 0) return EQNN_OK;
   const int d_out = d.n_extra + d.d_gated;
@@ -345,13 +407,15 @@ extern "C" int eqnn_gate_fwd(const float* z, int64_t n, int n_extra, int n_gates
   return EQNN_OK;
 }
 
-extern "C" int eqnn_gate_bwd(const float* z, const float* gout, int64_t n, int n_extra, int n_gates, int n_chunks,
-                             const int* mul, const int* l, float inv_c_act, float inv_c_gate, float* gz,
-                             eqnn_stream_t stream) {
+extern "C" int eqnn_gate_act_bwd(const float* z, const float* gout, int64_t n, int n_extra, int n_gates, int n_chunks,
+                                 const int* mul, const int* l, int activation, float inv_c_act, float inv_c_gate, float* gz,
+                                 eqnn_stream_t stream) {
   EQNN_CHECK_ARG(z && gout && gz && n >= 0, "gate_bwd: bad argument");
+  EQNN_CHECK_ARG(activation == EQNN_ACT_GELU || activation == EQNN_ACT_SILU, "gate_bwd: unknown activation");
   GateDesc d;
   int rc = make_gate_desc(d, n_extra, n_gates, n_chunks, mul, l, inv_c_act, inv_c_gate);
   if (rc) return rc;
+  d.act = activation;
   const int64_t tot = n * (d.n_extra + d.n_gates + d.d_gated);
   if (tot == 0) return EQNN_OK;
   const int d_in = d.n_extra + d.n_gates + d.d_gated;
@@ -361,6 +425,16 @@ extern "C" int eqnn_gate_bwd(const float* z, const float* gout, int64_t n, int n
     gate_bwd_kernel<<<(unsigned)ceil_div64(tot, 256), 256, 0, as_stream(stream)>>>(z, gout, n, d, gz);
   EQNN_CHECK_LAUNCH();
   return EQNN_OK;
+}
+
+extern "C" int eqnn_gate_fwd(const float* z, int64_t n, int n_extra, int n_gates, int n_chunks, const int* mul,
+                             const int* l, float inv_c_act, float inv_c_gate, float* out, eqnn_stream_t stream) {
+  return eqnn_gate_act_fwd(z, n, n_extra, n_gates, n_chunks, mul, l, EQNN_ACT_GELU, inv_c_act, inv_c_gate, out, stream);
+}
+extern "C" int eqnn_gate_bwd(const float* z, const float* gout, int64_t n, int n_extra, int n_gates, int n_chunks,
+                             const int* mul, const int* l, float inv_c_act, float inv_c_gate, float* gz,
+                             eqnn_stream_t stream) {
+  return eqnn_gate_act_bwd(z, gout, n, n_extra, n_gates, n_chunks, mul, l, EQNN_ACT_GELU, inv_c_act, inv_c_gate, gz, stream);
 }
 
 extern "C" int eqnn_layernorm_fwd(const float* a, int da, const float* g, int dg, int B, const float* scale,
@@ -399,6 +473,23 @@ extern "C" int eqnn_pool_bwd(const float* gout, int B, int N, int D, int mode, f
   const int64_t tot = (int64_t)B * N * D;
   pool_bwd_kernel<<<(unsigned)ceil_div64(tot, 256), 256, 0, as_stream(stream)>>>(gout, B, N, D,
                                                                                 mode == 1 ? 1.f / (float)N : 1.f, gx);
+  EQNN_CHECK_LAUNCH();
+  return EQNN_OK;
+}
+
+extern "C" int eqnn_pool_max_fwd(const float* x, int B, int N, int D, float* out, int32_t* argmax, eqnn_stream_t stream) {
+  EQNN_CHECK_ARG(x && out && argmax && B >= 1 && N >= 1 && D >= 1, "pool_max_fwd: bad argument");
+  dim3 grid((D + 31) / 32, B), block(32, 8);
+  pool_max_fwd_kernel<<<grid, block, 0, as_stream(stream)>>>(x, B, N, D, out, argmax);
+  EQNN_CHECK_LAUNCH();
+  return EQNN_OK;
+}
+
+extern "C" int eqnn_pool_max_bwd(const float* gout, const int32_t* argmax, int B, int N, int D, float* gx,
+                                 eqnn_stream_t stream) {
+  EQNN_CHECK_ARG(gout && argmax && gx && B >= 1 && N >= 1 && D >= 1, "pool_max_bwd: bad argument");
+  const int64_t tot = (int64_t)B * N * D;
+  pool_max_bwd_kernel<<<(unsigned)ceil_div64(tot, 256), 256, 0, as_stream(stream)>>>(gout, argmax, B, N, D, gx);
   EQNN_CHECK_LAUNCH();
   return EQNN_OK;
 }

@@ -267,6 +267,32 @@ __global__ void __launch_bounds__(256) sh_scatter_kernel(const int32_t* __restri
   }
 }
 
+// Per-edge messages W_e * TP(xt[src], Y(r_hat_e)) written at the ORIGINAL edge id: the `edges` field the reference's
+// node task returns (the last step's update_edge_fn output, models/nequip.py:154-171).  w_rows holds one row of radial-MLP
+// outputs per CSR position; column c of the signature reads MLP column col[c] scaled by scale[c] (SH normalisation).
+struct TpMsgCols {
+  int col[32];
+  float scale[32];
+};
+template <class TP>
+__global__ void __launch_bounds__(128)
+tp_messages_kernel(const int32_t* __restrict__ src, const int32_t* __restrict__ perm, const float4* __restrict__ geom,
+                   const float* __restrict__ w_rows, int ld_w, TpMsgCols cols, const float* __restrict__ xt,
+                   int64_t n_edges, float* __restrict__ out, int ld_out) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_edges) return;
+  const float4 g = geom[p];
+  float x[TP::DXP], w[TP::NLIVE], Y[TP::NY], m[TP::DLIVE];
+  load_x<TP>(xt, src[p], x);
+#pragma unroll
+  for (int c = 0; c < TP::NLIVE; ++c) w[c] = w_rows[p * ld_w + cols.col[c]] * cols.scale[c];
+  TP::sh(g.x, g.y, g.z, Y);
+  TP::fwd(x, Y, w, m);
+  float* o = out + (size_t)perm[p] * ld_out;
+#pragma unroll
+  for (int i = 0; i < TP::DLIVE; ++i) o[i] = m[i];
+}
+
 template <class TP>
 __global__ void node_tp_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y, int64_t n,
                                    float* __restrict__ T) {
@@ -334,12 +360,17 @@ extern "C" int eqnn_tpconv_fwd(int tp_id, const int32_t* rowptr, const int32_t* 
   const unsigned grid = (unsigned)((n_nodes + TPC_ROWS - 1) / TPC_ROWS);
   EQNN_TP_DISPATCH(tp_id, {
     EQNN_CHECK_ARG(ld_a >= TP::DLIVE, "tpconv_fwd: ld_a smaller than live width");
-    if (agg == 2)
-      tpconv_fwd_kernel<TP, true><<<grid, TPC_THREADS, 0, as_stream(stream)>>>(
-          rowptr, src, reinterpret_cast<const float4*>(geom), w_t, n_edges, xt, n_nodes, agg, A, ld_a, argmax);
-    else
-      tpconv_fwd_kernel<TP, false><<<grid, TPC_THREADS, 0, as_stream(stream)>>>(
-          rowptr, src, reinterpret_cast<const float4*>(geom), w_t, n_edges, xt, n_nodes, agg, A, ld_a, nullptr);
+    // the widest signatures (every message column at l_max 3: eqnn_tp_messages only) do not fit the message transpose
+    if constexpr (tpc_stride(TP::DLIVE) * TPC_THREADS * 4 <= 40 * 1024) {
+      if (agg == 2)
+        tpconv_fwd_kernel<TP, true><<<grid, TPC_THREADS, 0, as_stream(stream)>>>(
+            rowptr, src, reinterpret_cast<const float4*>(geom), w_t, n_edges, xt, n_nodes, agg, A, ld_a, argmax);
+      else
+        tpconv_fwd_kernel<TP, false><<<grid, TPC_THREADS, 0, as_stream(stream)>>>(
+            rowptr, src, reinterpret_cast<const float4*>(geom), w_t, n_edges, xt, n_nodes, agg, A, ld_a, nullptr);
+    } else {
+      return eqnn_fail(EQNN_ERR_ARG, "tpconv_fwd: this signature is wider than the reduction kernel covers");
+    }
   });
   EQNN_CHECK_LAUNCH();
   return EQNN_OK;
@@ -421,6 +452,28 @@ __global__ void segment_gather_sum4_kernel(const float4* __restrict__ dxe, const
   dxt[i] = a;
 }
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+extern "C" int eqnn_tp_messages(int tp_id, const int32_t* src, const int32_t* perm, const float* geom, const float* w_rows,
+                                int ld_w, const int* col, const float* scale, const float* xt, int64_t n_edges, float* out,
+                                int ld_out, eqnn_stream_t stream) {
+  EQNN_CHECK_ARG(src && perm && geom && w_rows && col && scale && xt && out, "tp_messages: null pointer");
+  EQNN_CHECK_ARG(((uintptr_t)geom & 15) == 0 && ((uintptr_t)xt & 15) == 0, "tp_messages: geom/xt must be 16-byte aligned");
+  if (n_edges <= 0) return EQNN_OK;
+  EQNN_TP_DISPATCH(tp_id, {
+    EQNN_CHECK_ARG(TP::NLIVE <= 32, "tp_messages: more than 32 message columns");
+    EQNN_CHECK_ARG(ld_out >= TP::DLIVE, "tp_messages: ld_out smaller than the message width");
+    TpMsgCols c;
+    for (int i = 0; i < 32; ++i) {
+      c.col[i] = i < TP::NLIVE ? col[i] : 0;
+      c.scale[i] = i < TP::NLIVE ? scale[i] : 0.f;
+      EQNN_CHECK_ARG(c.col[i] >= 0 && c.col[i] < ld_w, "tp_messages: column index outside w_rows");
+    }
+    tp_messages_kernel<TP><<<(unsigned)ceil_div64(n_edges, 128), 128, 0, as_stream(stream)>>>(
+        src, perm, reinterpret_cast<const float4*>(geom), w_rows, ld_w, c, xt, n_edges, out, ld_out);
+  });
+  EQNN_CHECK_LAUNCH();
+  return EQNN_OK;
+}
 
 extern "C" int eqnn_sender_reduce(const float* dxe, int n_nodes, int k, int dxp, float* dxt,
                                   eqnn_stream_t stream) {

@@ -121,10 +121,13 @@ class _Plan:
             raise NotImplementedError("activation must be 'gelu' or 'silu' on the B200 path (models/nequip.py:61)")
         if cfg.message_passing_agg not in ("sum", "mean", "max"):
             raise ValueError(f"Invalid message_passing_agg {cfg.message_passing_agg}")
-        if cfg.task == "graph" and cfg.readout_agg not in ("sum", "mean"):
-            raise NotImplementedError("readout_agg must be 'sum' or 'mean' on the B200 path")
+        if cfg.task == "graph" and cfg.readout_agg not in ("sum", "mean", "max"):
+            raise ValueError(f"Invalid global aggregation function {cfg.readout_agg}")    # models/nequip.py:174-177
         hidden = balanced_irreps(cfg.l_max, cfg.d_hidden, True)
         tp_full = make_tp_plan(irreps_in, cfg.l_max, None)
+        self.tp_full = tp_full
+        self.tp_full_spec = (str(irreps_in), cfg.l_max,
+                             "+".join(f"{l}{'e' if p > 0 else 'o'}" for l, p in tp_full.live_types))
         msg = tp_full.irreps_msg
         irr = hidden.filter(keep=msg)
         n_gated = irr.num_irreps - irr.count("0e")
@@ -409,6 +412,10 @@ class NequIP:
     # backward pass (1.5 KB per edge and step); "recompute": nothing is kept, the backward recomputes them from d.
     fuse_radial_mlp: bool = True
     radial_mlp_backward: str = "stash"
+    # not a reference field: the reference's node task returns the processed GraphsTuple, whose `edges` are the last
+    # step's messages (models/nequip.py:154-171); no caller reads them, so they are only computed on request (every message
+    # column, un-reduced, (B, E, D_msg) in the reference's edge order; not differentiated through)
+    return_edges: bool = False
 
     def __post_init__(self):
         self._plans: Dict[Irreps, _Plan] = {}
@@ -477,12 +484,16 @@ class NequIP:
         plan = self.plan(irreps_in, _n_globals_of(graphs))
         pg = prepared if prepared is not None else self.prepare(graphs)
         k = _n_edge_of(graphs)
-        out = _NequIPFunction.apply(params.flat, self, plan, pg, arr.contiguous(), k, _globals_of(graphs, arr.shape[0]))
+        out, edges = _NequIPFunction.apply(params.flat, self, plan, pg, arr.contiguous(), k,
+                                           _globals_of(graphs, arr.shape[0]))
         if self.task == "graph":
             return out[0] if unbatched else out
         nodes = out[0] if unbatched else out
-        return graphs._replace(nodes=IrrepsArray(plan.irreps_out if plan.Wout is None else
-                                                 Irreps(self.irreps_out).filter(keep=irreps_in), nodes))
+        res = graphs._replace(nodes=IrrepsArray(plan.irreps_out if plan.Wout is None else
+                                                Irreps(self.irreps_out).filter(keep=irreps_in), nodes))
+        if self.return_edges:                                       # models/nequip.py:154-171: the last step's messages
+            res = res._replace(edges=IrrepsArray(plan.tp_full.irreps_msg, edges[0] if unbatched else edges))
+        return res
 
     __call__ = apply
 
@@ -553,16 +564,47 @@ def _radial_weights(theta: torch.Tensor, wexp: torch.Tensor, st: Dict, n_live: i
     return ws
 
 
+def _edge_messages(model: "NequIP", plan: _Plan, theta: torch.Tensor, pg: PreparedGraph, st: Dict, xt: torch.Tensor):
+    """models/nequip.py:39-71 for every edge and EVERY message column, un-reduced: what jraph.GraphNetwork leaves in
+    `edges` after the last step (:154-171).  The radial MLP runs layer by layer here (the fused kernel emits at most 16
+    columns); (B, E, D_msg) in the reference's edge order."""
+    if model.activation != "gelu":
+        raise NotImplementedError("return_edges: the layer-by-layer radial MLP has the gelu kernels only")
+    dev = theta.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    Et = pg.B * pg.E
+    a, pro = pg.radial, 0
+    for (koff, fan, hdim) in st["mlp"][:-1]:
+        Z = torch.empty((Et, hdim), **f32)
+        _mm(Et, hdim, fan, 1.0 / math.sqrt(fan), a, 0, fan, theta, koff, hdim, Z, 0, hdim, pro=pro,
+            pro_scale=plan.inv_c_act, tf32x3=model.tensor_cores)
+        a, pro = Z, 1
+    koff, fan, n_irr = st["mlp"][-1]
+    w_rows = torch.empty((Et, n_irr), **f32)
+    _mm(Et, n_irr, fan, 1.0 / math.sqrt(fan), a, 0, fan, theta, koff, n_irr, w_rows, 0, n_irr, pro=pro,
+        pro_scale=plan.inv_c_act)
+    tpf = plan.tp_full
+    tp_id = ops.tp_lookup(tpf.signature, plan.tp_full_spec)
+    out = torch.empty((Et, tpf.irreps_msg.dim), **f32)
+    ops.tp_messages(tp_id, pg.src, pg.perm, pg.geom, w_rows, [c.col for c in tpf.columns],
+                    [plan.shn[c.l2] for c in tpf.columns], xt, out)
+    return out.view(pg.B, pg.E, -1)
+
+
 class _NequIPFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, theta, model, plan, pg, nodes, k, globals_=None):
         out, saved = _forward(model, plan, theta.detach(), pg, nodes, k, save=True, globals_=globals_)
         ctx.model, ctx.plan, ctx.pg, ctx.saved, ctx.k = model, plan, pg, saved, k
         ctx.theta = theta.detach()
-        return out
+        edges = saved.pop("edges", None)
+        if edges is None:
+            edges = out.new_empty((0,))
+        ctx.mark_non_differentiable(edges)
+        return out, edges
 
     @staticmethod
-    def backward(ctx, gout):
+    def backward(ctx, gout, _gedges):
         g = torch.zeros_like(ctx.theta)
         _backward(ctx.model, ctx.plan, ctx.theta, ctx.pg, ctx.saved, gout.contiguous(), ctx.k, g)
         return g, None, None, None, None, None, None
@@ -626,6 +668,8 @@ def _forward(model: NequIP, plan: _Plan, theta: torch.Tensor, pg: PreparedGraph,
             _mm(Nt, D, plan.d_g, 1.0, g, 0, plan.d_g, wexp, st["W3"].off, D, hn, 0, D)
         if save:
             saved["steps"].append(dict(h=h, xt=xt, Zs=Zs, w_t=w_t, A=A, z=z, g=g, stash=stash, amax=amax))
+        if model.return_edges and model.task == "node" and st is plan.steps[-1]:
+            saved["edges"] = _edge_messages(model, plan, theta, pg, st, xt)
         h = hn
     saved["h_final"] = h
     if model.task == "node":
@@ -647,10 +691,19 @@ def _forward(model: NequIP, plan: _Plan, theta: torch.Tensor, pg: PreparedGraph,
     dh = model.d_hidden
     # The Linear to d_hidden scalars and the sum / mean over the nodes commute (nequip.py:195-199): pool the
     # D_live-wide tensor-product output first, then apply the Linear to B rows instead of B*N rows.
-    T0p = torch.empty((B, tpr.d_live), **f32)
-    ops.pool_fwd(T0, B, N, tpr.d_live, 1 if model.readout_agg == "mean" else 0, T0p)
     pooled = torch.empty((B, dh), **f32)
-    _mm(B, dh, tpr.d_live, 1.0, T0p, 0, tpr.d_live, wexp, plan.Wro.off, dh, pooled, 0, dh)
+    ro_arg = None
+    if model.readout_agg == "max":
+        # jnp.max does not commute with the Linear: per-node scalars first, then value + arg-max over the nodes
+        T0p = torch.empty((Nt, dh), **f32)
+        _mm(Nt, dh, tpr.d_live, 1.0, T0, 0, tpr.d_live, wexp, plan.Wro.off, dh, T0p, 0, dh)
+        ro_arg = torch.empty((B, dh), dtype=torch.int32, device=dev)
+        ops.pool_max_fwd(T0p, B, N, dh, pooled, ro_arg)
+        T0p = T0                                       # the weight gradient's left operand
+    else:
+        T0p = torch.empty((B, tpr.d_live), **f32)
+        ops.pool_fwd(T0, B, N, tpr.d_live, 1 if model.readout_agg == "mean" else 0, T0p)
+        _mm(B, dh, tpr.d_live, 1.0, T0p, 0, tpr.d_live, wexp, plan.Wro.off, dh, pooled, 0, dh)
     ln_stats = None
     a = pooled
     if plan.ln is not None:
@@ -667,7 +720,8 @@ def _forward(model: NequIP, plan: _Plan, theta: torch.Tensor, pg: PreparedGraph,
             aux_off=bo)
         zs.append(zl)
         a, pro = zl, 1
-    saved.update(attrs=attrs, hr=hr, T0p=T0p, pooled=pooled, ro_z=zs, ro_in=ro_in, ln_stats=ln_stats, globals=globals_)
+    saved.update(attrs=attrs, hr=hr, T0p=T0p, pooled=pooled, ro_z=zs, ro_in=ro_in, ln_stats=ln_stats, globals=globals_,
+                 ro_arg=ro_arg)
     return zs[-1], saved
 
 
@@ -724,11 +778,18 @@ def _backward(model: NequIP, plan: _Plan, theta: torch.Tensor, pg: PreparedGraph
             dz = d_pool
         # pooled = pool(T0) @ Wro: weight gradient and data gradient on B rows, then un-pool
         T0p = saved["T0p"]
-        _mm(tpr.d_live, dhid, B, 1.0, T0p, 0, tpr.d_live, dz, 0, dhid, gwexp, plan.Wro.off, dhid, ta=True)
-        dT0p = torch.empty((B, tpr.d_live), **f32)
-        _mm(B, tpr.d_live, dhid, 1.0, dz, 0, dhid, wexp, plan.Wro.off, dhid, dT0p, 0, tpr.d_live, tb=True)
         dT0 = torch.empty((Nt, tpr.d_live), **f32)
-        ops.pool_bwd(dT0p, B, N, tpr.d_live, 1 if model.readout_agg == "mean" else 0, dT0)
+        if model.readout_agg == "max":
+            # the gradient of every pooled scalar goes to the node that attained the maximum
+            dL = torch.empty((Nt, dhid), **f32)
+            ops.pool_max_bwd(dz, saved["ro_arg"], B, N, dhid, dL)
+            _mm(tpr.d_live, dhid, Nt, 1.0, T0p, 0, tpr.d_live, dL, 0, dhid, gwexp, plan.Wro.off, dhid, ta=True)
+            _mm(Nt, tpr.d_live, dhid, 1.0, dL, 0, dhid, wexp, plan.Wro.off, dhid, dT0, 0, tpr.d_live, tb=True)
+        else:
+            _mm(tpr.d_live, dhid, B, 1.0, T0p, 0, tpr.d_live, dz, 0, dhid, gwexp, plan.Wro.off, dhid, ta=True)
+            dT0p = torch.empty((B, tpr.d_live), **f32)
+            _mm(B, tpr.d_live, dhid, 1.0, dz, 0, dhid, wexp, plan.Wro.off, dhid, dT0p, 0, tpr.d_live, tb=True)
+            ops.pool_bwd(dT0p, B, N, tpr.d_live, 1 if model.readout_agg == "mean" else 0, dT0)
         dhr = torch.empty((Nt, tpr.dxp), **f32)
         ops.node_tp_bwd(ro_id, saved["hr"], saved["attrs"], dT0, Nt, dhr)
         dh = torch.empty((Nt, D), **f32)

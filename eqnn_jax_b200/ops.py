@@ -177,6 +177,13 @@ def tpconv_bwd(tp_id, rowptr, src, perm, geom, w_t, xt, n_nodes, agg, gA, ld_ga,
         TIMER.end("tpconv_bwd", t0)
 
 
+def tp_messages(tp_id, src, perm, geom, w_rows, cols, scales, xt, out):
+    """Un-reduced per-edge messages in the reference's edge order (node-task `edges`, models/nequip.py:154-171)."""
+    fa = (C.c_float * len(scales))(*[float(v) for v in scales])
+    check(lib().eqnn_tp_messages(tp_id, _ptr(src), _ptr(perm), _ptr(geom), _ptr(w_rows), w_rows.shape[1], _int_arr(cols),
+                                 fa, _ptr(xt), src.numel(), _ptr(out), out.shape[1], _stream()), "tp_messages")
+
+
 def sender_reduce(dxe, n_nodes, k, dxp, dxt):
     check(lib().eqnn_sender_reduce(_ptr(dxe), n_nodes, k, dxp, _ptr(dxt), _stream()), "sender_reduce")
 
@@ -294,14 +301,17 @@ def _int_arr(v: Sequence[int]):
     return (C.c_int * max(len(v), 1))(*v)
 
 
-def gate_fwd(z, n, n_extra, n_gates, mul, l, inv_c_act, inv_c_gate, out):
-    check(lib().eqnn_gate_fwd(_ptr(z), n, n_extra, n_gates, len(mul), _int_arr(mul), _int_arr(l), inv_c_act,
-                              inv_c_gate, _ptr(out), _stream()), "gate_fwd")
+ACT = {"gelu": 0, "silu": 1}     # EQNN_ACT_GELU / EQNN_ACT_SILU
 
 
-def gate_bwd(z, gout, n, n_extra, n_gates, mul, l, inv_c_act, inv_c_gate, gz):
-    check(lib().eqnn_gate_bwd(_ptr(z), _ptr(gout), n, n_extra, n_gates, len(mul), _int_arr(mul), _int_arr(l),
-                              inv_c_act, inv_c_gate, _ptr(gz), _stream()), "gate_bwd")
+def gate_fwd(z, n, n_extra, n_gates, mul, l, inv_c_act, inv_c_gate, out, activation="gelu"):
+    check(lib().eqnn_gate_act_fwd(_ptr(z), n, n_extra, n_gates, len(mul), _int_arr(mul), _int_arr(l), ACT[activation],
+                                  inv_c_act, inv_c_gate, _ptr(out), _stream()), "gate_fwd")
+
+
+def gate_bwd(z, gout, n, n_extra, n_gates, mul, l, inv_c_act, inv_c_gate, gz, activation="gelu"):
+    check(lib().eqnn_gate_act_bwd(_ptr(z), _ptr(gout), n, n_extra, n_gates, len(mul), _int_arr(mul), _int_arr(l),
+                                  ACT[activation], inv_c_act, inv_c_gate, _ptr(gz), _stream()), "gate_bwd")
 
 
 _NODE_WS = GemmWorkspace()
@@ -567,6 +577,14 @@ def pool_fwd(x, B, N, D, mode, out):
 
 def pool_bwd(gout, B, N, D, mode, gx):
     check(lib().eqnn_pool_bwd(_ptr(gout), B, N, D, mode, _ptr(gx), _stream()), "pool_bwd")
+
+
+def pool_max_fwd(x, B, N, D, out, argmax):
+    check(lib().eqnn_pool_max_fwd(_ptr(x), B, N, D, _ptr(out), _ptr(argmax), _stream()), "pool_max_fwd")
+
+
+def pool_max_bwd(gout, argmax, B, N, D, gx):
+    check(lib().eqnn_pool_max_bwd(_ptr(gout), _ptr(argmax), B, N, D, _ptr(gx), _stream()), "pool_max_bwd")
 
 
 def layernorm_fwd(a, g, scale_buf, scale_off, bias_off, eps, y, stats):

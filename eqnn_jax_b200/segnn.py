@@ -27,7 +27,7 @@ one has no gate and is only aggregated over the receivers, so the aggregation is
 run on the node rows (``_edgeL_fwd``).  With attributes l <= 1 the forward GEMM of the remaining layers contracts the
 attribute axis in its epilogue (``eqnn_segnn_tplg_fwd``).
 Graph globals (concatenated to the pooled scalars, LayerNorm, :282-286) are supported.
-Not built: max aggregation, activations other than gelu -> NotImplementedError, never a fallback.
+Scalar activations: gelu and silu (models/segnn.py:27,56).  Not built: max aggregation -> NotImplementedError, never a fallback.
 """
 from __future__ import annotations
 
@@ -231,15 +231,16 @@ class _Plan:
         self._dst: List[np.ndarray] = []
         self._par: List[np.ndarray] = []
         self._val: List[np.ndarray] = []
-        if cfg.scalar_activation != "gelu":
-            raise NotImplementedError("only scalar_activation='gelu' has a B200 kernel on this path")
+        if cfg.scalar_activation not in ("gelu", "silu"):
+            raise NotImplementedError("scalar_activation must be 'gelu' or 'silu' on the B200 path (models/segnn.py:27,56)")
         if cfg.message_passing_agg not in ("sum", "mean") or (cfg.task == "graph" and cfg.readout_agg not in ("sum", "mean")):
             raise NotImplementedError("aggregations must be 'sum' or 'mean' on the B200 path")
         hidden = Irreps(cfg.hidden_irreps) if cfg.hidden_irreps is not None else \
             balanced_irreps(cfg.l_max_hidden, cfg.d_hidden, True)
         self.hidden, self.irreps_in = hidden, irreps_in
         self.out_irreps = Irreps(cfg.output_irreps) if cfg.output_irreps is not None else irreps_in
-        self.inv_c_act = 1.0 / normalize_constant("gelu")
+        self.act = cfg.scalar_activation
+        self.inv_c_act = 1.0 / normalize_constant(cfg.scalar_activation)
         self.inv_c_gate = 1.0 / normalize_constant("sigmoid")
         ti = 0
 
@@ -512,7 +513,7 @@ class SEGNN:
         if not t.activation:
             return z, (x, ldx, y, z)
         g = torch.empty((R, t.d_g), **f32)
-        ops.gate_fwd(z, R, t.n_extra, t.n_gates, t.gate_mul, t.gate_l, plan.inv_c_act, plan.inv_c_gate, g)
+        ops.gate_fwd(z, R, t.n_extra, t.n_gates, t.gate_mul, t.gate_l, plan.inv_c_act, plan.inv_c_gate, g, plan.act)
         return g, (x, ldx, y, z)
 
     def _tplg_bwd(self, plan, t: _TPLG, theta, gtheta, wexp, gwexp, sv, dout, R, need_dx=True):
@@ -522,7 +523,7 @@ class SEGNN:
         dz = dout
         if t.activation:
             dz = torch.empty((R, t.Do), **f32)
-            ops.gate_bwd(z, dout, R, t.n_extra, t.n_gates, t.gate_mul, t.gate_l, plan.inv_c_act, plan.inv_c_gate, dz)
+            ops.gate_bwd(z, dout, R, t.n_extra, t.n_gates, t.gate_mul, t.gate_l, plan.inv_c_act, plan.inv_c_gate, dz, plan.act)
         if t.n_bias:
             tmp = torch.empty((t.Do,), **f32)
             ops.colsum_tall(dz, R, t.Do, tmp)
@@ -578,7 +579,7 @@ class SEGNN:
         if not t.activation:
             return z, (h, y, z)
         g = torch.empty((Et, t.d_g), **f32)
-        ops.gate_fwd(z, Et, t.n_extra, t.n_gates, t.gate_mul, t.gate_l, plan.inv_c_act, plan.inv_c_gate, g)
+        ops.gate_fwd(z, Et, t.n_extra, t.n_gates, t.gate_mul, t.gate_l, plan.inv_c_act, plan.inv_c_gate, g, plan.act)
         return g, (h, y, z)
 
     def _edge0_bwd(self, plan, t: _TPLG, theta, gtheta, wexp, gwexp, sv, dout, Dh, add, n_add, csr, Nt, Et, dh_prev):
@@ -589,7 +590,7 @@ class SEGNN:
         dz = dout
         if t.activation:
             dz = torch.empty((Et, t.Do), **f32)
-            ops.gate_bwd(z, dout, Et, t.n_extra, t.n_gates, t.gate_mul, t.gate_l, plan.inv_c_act, plan.inv_c_gate, dz)
+            ops.gate_bwd(z, dout, Et, t.n_extra, t.n_gates, t.gate_mul, t.gate_l, plan.inv_c_act, plan.inv_c_gate, dz, plan.act)
         if t.n_bias:
             tmp = torch.empty((t.Do,), **f32)
             ops.colsum_tall(dz, Et, t.Do, tmp)

@@ -69,6 +69,7 @@ int eqnn_tp_dims(int id, int* dxp, int* ny, int* n_live, int* d_live);
  * and N >= 2048, the search runs on a cell list (points binned into G^3 cells, (2R+1)^3 cells swept per query, R
  * grown until the k-th distance lies inside the searched region): same distance expression, list ordered by
  * (distance, index) -- output bit-identical to the dense sweep.  Without it (NULL / too small) the dense sweep runs. */
+enum { EQNN_ACT_GELU = 0, EQNN_ACT_SILU = 1 };   /* models/nequip.py:61 getattr(nn, activation); gelu = tanh form */
 enum { EQNN_KNN_PBC = 1, EQNN_KNN_FMA = 2, EQNN_KNN_DENSE = 4 };
 size_t eqnn_knn_workspace_bytes(int B, int N, int k);
 int eqnn_knn_pbc(const float* x, int ld_x, const float* cell, const float* cell_inv, int B, int N, int k,
@@ -125,6 +126,16 @@ int eqnn_tpconv_fwd(int tp_id, const int32_t* rowptr, const int32_t* src, const 
 int eqnn_tpconv_bwd(int tp_id, const int32_t* rowptr, const int32_t* src, const int32_t* perm, const float* geom,
                     const float* w_t, int64_t n_edges, const float* xt, int n_nodes, int agg, const float* gA,
                     int ld_ga, float* dw_t, float* dxe, const int32_t* argmax, eqnn_stream_t stream);
+
+/* Per-edge messages of one interaction step, un-reduced (the `edges` field of the node task's output,
+ * models/nequip.py:154-171: jraph.GraphNetwork stores the update_edge_fn result):
+ *     out[perm[p], :] = (w_rows[p, col[c]] * scale[c])_c (x) CG( xt[src(p)], Y_lm(r_hat_p) )
+ *   tp_id   a signature whose live set is every message column (NLIVE <= 32)
+ *   w_rows  [n_edges, ld_w] radial-MLP outputs per CSR position, row-major; col / scale: HOST arrays of NLIVE entries
+ *   out     [n_edges, ld_out] in the reference's (sender-major) edge order                                       */
+int eqnn_tp_messages(int tp_id, const int32_t* src, const int32_t* perm, const float* geom, const float* w_rows, int ld_w,
+                     const int* col, const float* scale, const float* xt, int64_t n_edges, float* out, int ld_out,
+                     eqnn_stream_t stream);
 /* dxt[s, :] = sum_{j<k} dxe[s*k + j, :]   (sender-major fixed out-degree k, graph_utils.py:70) */
 int eqnn_sender_reduce(const float* dxe, int n_nodes, int k, int dxp, float* dxt, eqnn_stream_t stream);
 /* general out-degree: dxt[s, :] = sum over row s of a SENDER-sorted CSR (eqnn_csr_build with the roles of
@@ -171,6 +182,13 @@ int eqnn_gate_fwd(const float* z, int64_t n, int n_extra, int n_gates, int n_chu
 int eqnn_gate_bwd(const float* z, const float* gout, int64_t n, int n_extra, int n_gates, int n_chunks,
                   const int* mul, const int* l, float inv_c_act, float inv_c_gate, float* gz,
                   eqnn_stream_t stream);
+/* the same with the scalar activation chosen by the caller (models/segnn.py:27,56 scalar_activation: EQNN_ACT_GELU or
+ * EQNN_ACT_SILU, inv_c_act = 1 / e3nn.normalize_function constant of that activation); gates stay sigmoid */
+int eqnn_gate_act_fwd(const float* z, int64_t n, int n_extra, int n_gates, int n_chunks, const int* mul, const int* l,
+                      int activation, float inv_c_act, float inv_c_gate, float* out, eqnn_stream_t stream);
+int eqnn_gate_act_bwd(const float* z, const float* gout, int64_t n, int n_extra, int n_gates, int n_chunks,
+                      const int* mul, const int* l, int activation, float inv_c_act, float inv_c_gate, float* gz,
+                      eqnn_stream_t stream);
 
 /* Fused node update of one interaction step (models/nequip.py:80-90 and :162):
  *     z = alpha1 * A @ W1 + h @ W2 ;  h_out = gate(z) @ W3 ;  xt_out = h_out @ W0n (optional, next step's :43)
@@ -193,6 +211,10 @@ int eqnn_node_update_bwd(const float* A, int ld_a, int d_a, const float* h, int 
 /* out[b, :] = reduce_n x[b, n, :]   (mode 0 sum, 1 mean; nequip.py:196-199) and its backward */
 int eqnn_pool_fwd(const float* x, int B, int N, int D, int mode, float* out, eqnn_stream_t stream);
 int eqnn_pool_bwd(const float* gout, int B, int N, int D, int mode, float* gx, eqnn_stream_t stream);
+/* readout_agg = "max" (jnp.max over the nodes, models/nequip.py:195-199): out [B, D], argmax [B, D] = first node
+ * attaining the maximum; the backward pass routes gout[b, c] to gx[b, argmax[b, c], c] and writes zeros elsewhere */
+int eqnn_pool_max_fwd(const float* x, int B, int N, int D, float* out, int32_t* argmax, eqnn_stream_t stream);
+int eqnn_pool_max_bwd(const float* gout, const int32_t* argmax, int B, int N, int D, float* gx, eqnn_stream_t stream);
 /* LayerNorm over x[b, :] = concat(a[b, :da], g[b, :dg]) (pooled node scalars | graph globals), nequip.py:201-205:
  * y = (x - mean) * rsqrt(var + eps) * scale + bias, flax.linen.LayerNorm defaults (eps = 1e-6).  stats[b] = (mean,
  * rstd) is kept for the backward, which returns d_a (B x da; the globals are data), dscale and dbias (da + dg). */
@@ -365,7 +387,6 @@ int eqnn_colsum_tall(const float* x, int64_t M, int N, float* y, void* ws, size_
  *   the last matrix has n_out <= 16 columns (the live message columns, SH normalisation folded in)
  *   w_t [n_out][ld_wt] column-major (the layout eqnn_tpconv_fwd reads)
  * eqnn_radial_mlp_supported: 1 if the shape is covered (n_rb in {16,32,64}, d_hidden = 128, 1 <= n_hidden <= 3). */
-enum { EQNN_ACT_GELU = 0, EQNN_ACT_SILU = 1 };   /* models/nequip.py:61 getattr(nn, activation); gelu = tanh form */
 int eqnn_radial_mlp_supported(int n_rb, int d_hidden, int n_hidden, int n_out);
 /* Backward of the same MLP w.r.t. its weights (the only gradient the reference takes: jax.value_and_grad w.r.t.
  * params, train_cosmology.py:245; edge lengths carry no gradient).  dw_t [n_out][ld_dwt] = dL/dw_t.

@@ -457,6 +457,44 @@ def test_max_aggregation(lmax, task):
     _check_all(model, params, gg, cfg, tree, g, cot)
 
 
+@pytest.mark.parametrize("agg", ["max", "sum"])
+def test_readout_aggregation(agg):
+    """readout_agg (models/nequip.py:173-199): "max" = jnp.max over the nodes of the per-node scalars (value + arg-max,
+    gradient routed to the winning node), "sum" = the pooled route without the 1/N."""
+    rng = np.random.default_rng(41)
+    B, N, k = 3, 130, 10
+    x = rng.normal(size=(B, N, 7)).astype(np.float32)
+    x[..., :3] = rng.uniform(-1.7, 1.7, size=(B, N, 3))
+    kw = dict(d_hidden=64, l_max=2, sphharm_norm="integral", message_passing_steps=2, n_layers=2, n_outputs=2,
+              n_radial_basis=16, r_cutoff=0.6, message_passing_agg="mean", task="graph", readout_agg=agg)
+    cfg, tree, g, model, gg, params = _setup(kw, x, k, seed=6)
+    cot = rng.normal(size=(B, 2))
+    _check_all(model, params, gg, cfg, tree, g, cot)
+
+
+@pytest.mark.parametrize("lmax,d_hidden,n_rb", [(1, 32, 4), (2, 128, 32), (3, 64, 16)])
+def test_node_task_returns_last_messages_as_edges(lmax, d_hidden, n_rb):
+    """models/nequip.py:154-171: the node task returns the processed GraphsTuple, whose `edges` are the last step's
+    messages (every irrep column, un-reduced, in the reference's edge order).  Computed on request (return_edges)."""
+    rng = np.random.default_rng(50 + lmax)
+    B, N, k = 2, 110, 9
+    x = rng.normal(size=(B, N, 7)).astype(np.float32)
+    x[..., :3] = rng.uniform(-1.7, 1.7, size=(B, N, 3))
+    kw = dict(d_hidden=d_hidden, l_max=lmax, sphharm_norm="integral", message_passing_steps=2, n_layers=2,
+              n_radial_basis=n_rb, r_cutoff=0.6, message_passing_agg="mean", task="node")
+    cfg, tree, g, model, gg, params = _setup(kw, x, k, seed=8)
+    model.return_edges = True
+    p = NQ.to_torch(tree, torch.float64, requires_grad=False)
+    want = NQ.apply_batched(p, cfg, g._replace(nodes=torch.tensor(g.nodes, dtype=torch.float64)), IRR)
+    out = model.apply(params, gg)
+    _close(out.nodes.array.detach().cpu().numpy(), want.nodes.numpy(), "nodes")
+    assert out.edges.array.shape == tuple(want.edges.shape)
+    assert str(out.edges.irreps) == str(model.plan(IRR).tp_full.irreps_msg)
+    _close(out.edges.array.cpu().numpy(), want.edges.numpy(), "edges (last-step messages)")
+    model.return_edges = False
+    assert model.apply(params, gg).edges is None
+
+
 def test_silu_radial_mlp_on_fused_route():
     """activation = "silu" (models/nequip.py:61 getattr(nn, activation)): the fused kernels evaluate x sigma(x) with the
     silu constants; the backward takes the recompute variant."""

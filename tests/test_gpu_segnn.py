@@ -94,6 +94,9 @@ def _run(kw, irreps, x, k, lmax_attr, n_rb, pbc, vel, n_glob=0, lowering="dense"
     # attributes up to l = 3 (16 components): the widest attribute slot of the node-level edge-layer kernels
     (dict(d_hidden=32, n_layers=2, message_passing_steps=1, message_passing_agg="mean", task="node", output_irreps="1x1o",
           l_max_hidden=2, residual=True), "1o", 3, 3, 0, False, False, 0),
+    # scalar_activation = "silu": the class default of TensorProductLinearGate (segnn.py:27), e3nn-normalised
+    (dict(d_hidden=32, n_layers=2, message_passing_steps=2, message_passing_agg="mean", task="node", output_irreps="1x1o",
+          l_max_hidden=1, residual=True, scalar_activation="silu"), "1o", 3, 1, 4, True, False, 0),
     # graph globals (TPCF vector) -> concat + LayerNorm before the read-out MLP (segnn.py:282-286)
     (dict(d_hidden=32, n_layers=2, message_passing_steps=1, message_passing_agg="mean", task="graph", output_irreps="1x0e",
           n_outputs=2), "1o", 3, 1, 0, False, False, 12),
