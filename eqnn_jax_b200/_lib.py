@@ -91,6 +91,8 @@ SIGNATURES: Dict[str, tuple] = {
     "eqnn_colsum_workspace_bytes": (_sz, [_i]),
     "eqnn_colsum_tall": (_i, [_p, _i64, _i, _p, _p, _sz, _p]),
     "eqnn_tp_messages": (_i, [_i, _p, _p, _p, _p, _i, _p, _p, _p, _i64, _p, _i, _p]),
+    "eqnn_radius_graph": (_i, [_p, _i, _p, _p, _i, _i, _f, _i, _p, _p, _p, _p, _p, _p]),
+    "eqnn_exclusive_scan_i32": (_i, [_p, _i64, _p, _p]),
     "eqnn_pool_fwd": (_i, [_p, _i, _i, _i, _i, _p, _p]),
     "eqnn_pool_bwd": (_i, [_p, _i, _i, _i, _i, _p, _p]),
     "eqnn_pool_max_fwd": (_i, [_p, _i, _i, _i, _p, _p, _p]),

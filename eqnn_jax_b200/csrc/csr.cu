@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(1024) scan_kernel(const int32_t* __restrict__ 
     for (int j = 0; j < SCAN_PER_THREAD; ++j) {
       if (i0 + j < n) {
         rowptr[i0 + j] = excl;
-        cursor[i0 + j] = excl;
+        if (cursor) cursor[i0 + j] = excl;
       }
       excl += v[j];
     }
@@ -190,6 +190,14 @@ extern "C" int eqnn_edge_features(const float* dr, int64_t n_edges, int n_rb, do
   const float pref = n_rb > 0 ? (float)sqrt(2.0 / r_max) : 1.f;
   edge_feat_kernel<<<(unsigned)ceil_div64(n_edges, 256), 256, 0, as_stream(stream)>>>(dr, n_edges, n_rb, (float)r_max,
                                                                                      pref, out);
+  EQNN_CHECK_LAUNCH();
+  return EQNN_OK;
+}
+
+// out[i] = sum_{j < i} count[j], i = 0..n (n + 1 outputs): the row pointers of a ragged edge list
+extern "C" int eqnn_exclusive_scan_i32(const int32_t* count, int64_t n, int32_t* out, eqnn_stream_t stream) {
+  EQNN_CHECK_ARG(count && out && n >= 0, "exclusive_scan: bad argument");
+  scan_kernel<<<1, 1024, 0, as_stream(stream)>>>(count, n, out, nullptr);
   EQNN_CHECK_LAUNCH();
   return EQNN_OK;
 }

@@ -20,12 +20,16 @@ struct Cell {
   float ci[9];  // inverse cell
 };
 
-template <bool PBC, bool DIAG, bool FMA>
+// EPS: nearest_neighbors adds 1e-7 to the difference (graph_utils.py:55); compute_distances (:223) does not
+template <bool PBC, bool DIAG, bool FMA, bool EPS = true>
 __device__ __forceinline__ float pair_dist(float xi, float yi, float zi, float xj, float yj, float zj,
                                            const Cell& cl, float* out3 = nullptr) {
-  float d0 = __fadd_rn(__fsub_rn(xi, xj), KNN_EPS);
-  float d1 = __fadd_rn(__fsub_rn(yi, yj), KNN_EPS);
-  float d2 = __fadd_rn(__fsub_rn(zi, zj), KNN_EPS);
+  float d0 = __fsub_rn(xi, xj), d1 = __fsub_rn(yi, yj), d2 = __fsub_rn(zi, zj);
+  if (EPS) {
+    d0 = __fadd_rn(d0, KNN_EPS);
+    d1 = __fadd_rn(d1, KNN_EPS);
+    d2 = __fadd_rn(d2, KNN_EPS);
+  }
   if (PBC) {
     if (DIAG) {
       float n0 = rintf(__fmul_rn(d0, cl.ci[0]));
@@ -398,7 +402,90 @@ int launch_knn(const float* x, int ldx, int N, int k, const Cell& cell, bool pbc
   return EQNN_OK;
 }
 
+// ---- radius graph (the radius branch of build_graph, graph_utils.py:266-277, as it evidently means to work) ----
+// edges (i -> j) of one graph: 0 < |apply_pbc(x_i - x_j)| < radius, in np.where order (i ascending, then j ascending);
+// the distance is compute_distances' sqrt(sum(dr^2)) (:209-226), every fp32 operation rounded separately.
+// One warp per query point i; FILL = false counts the row, FILL = true writes it behind the row pointer.
+template <bool PBC, bool DIAG, bool FILL>
+__global__ void __launch_bounds__(256)
+radius_kernel(const float* __restrict__ x, int ldx, int N, Cell cell, float radius, int32_t* __restrict__ count,
+              const int32_t* __restrict__ rowptr, int32_t* __restrict__ senders, int32_t* __restrict__ receivers,
+              float* __restrict__ dist) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  const int i = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (i >= N) return;
+  const float* xb = x + (size_t)b * N * ldx;
+  const float xi = xb[(size_t)i * ldx], yi = xb[(size_t)i * ldx + 1], zi = xb[(size_t)i * ldx + 2];
+  int n = 0;
+  int64_t base = FILL ? rowptr[(size_t)b * N + i] : 0;
+  for (int j0 = 0; j0 < N; j0 += 32) {
+    const int j = j0 + lane;
+    bool hit = false;
+    float d = 0.f;
+    if (j < N) {
+      const float* pj = xb + (size_t)j * ldx;
+      d = __fsqrt_rn(pair_dist<PBC, DIAG, false, false>(xi, yi, zi, pj[0], pj[1], pj[2], cell));
+      hit = d < radius && d > 0.f;
+    }
+    const unsigned m = __ballot_sync(FULL, hit);
+    if (FILL && hit) {
+      const int64_t o = base + __popc(m & ((1u << lane) - 1u));
+      senders[o] = i;
+      receivers[o] = j;
+      dist[o] = d;
+    }
+    n += __popc(m);
+    base += __popc(m);
+  }
+  if (!FILL && lane == 0) count[(size_t)b * N + i] = n;
+}
+
 }  // namespace
+
+static int radius_cell(const float* cell, const float* cell_inv, int flags, Cell& c, bool& pbc, bool& diag) {
+  pbc = (flags & EQNN_KNN_PBC) != 0;
+  diag = true;
+  for (int i = 0; i < 9; ++i) {
+    c.c[i] = (i % 4 == 0) ? 1.f : 0.f;
+    c.ci[i] = c.c[i];
+  }
+  if (pbc) {
+    EQNN_CHECK_ARG(cell && cell_inv, "radius_graph: PBC requested without cell / cell_inv");
+    for (int i = 0; i < 9; ++i) {
+      c.c[i] = cell[i];
+      c.ci[i] = cell_inv[i];
+      if (i % 4 != 0 && (cell[i] != 0.f || cell_inv[i] != 0.f)) diag = false;
+    }
+  }
+  return EQNN_OK;
+}
+
+extern "C" int eqnn_radius_graph(const float* x, int ld_x, const float* cell, const float* cell_inv, int B, int N,
+                                 float radius, int flags, int32_t* count, const int32_t* rowptr, int32_t* senders,
+                                 int32_t* receivers, float* dist, eqnn_stream_t stream) {
+  EQNN_CHECK_ARG(x && B >= 0 && N >= 0 && ld_x >= 3, "radius_graph: bad argument");
+  const bool fill = rowptr != nullptr;
+  EQNN_CHECK_ARG(fill ? (senders && receivers && dist) : (count != nullptr), "radius_graph: null output");
+  if (B == 0 || N == 0) return EQNN_OK;
+  Cell c;
+  bool pbc, diag;
+  if (int rc = radius_cell(cell, cell_inv, flags, c, pbc, diag)) return rc;
+  dim3 grid((unsigned)(((int64_t)N * 32 + 255) / 256), B);
+  cudaStream_t st = as_stream(stream);
+#define EQNN_RADIUS(P, D)                                                                                            \
+  do {                                                                                                               \
+    if (fill) radius_kernel<P, D, true><<<grid, 256, 0, st>>>(x, ld_x, N, c, radius, count, rowptr, senders, receivers, dist); \
+    else radius_kernel<P, D, false><<<grid, 256, 0, st>>>(x, ld_x, N, c, radius, count, rowptr, senders, receivers, dist);     \
+  } while (0)
+  if (!pbc) EQNN_RADIUS(false, true);
+  else if (diag) EQNN_RADIUS(true, true);
+  else EQNN_RADIUS(true, false);
+#undef EQNN_RADIUS
+  EQNN_CHECK_LAUNCH();
+  return EQNN_OK;
+}
 
 extern "C" size_t eqnn_knn_workspace_bytes(int B, int N, int k) {
   const int G = grid_cells(N, k);

@@ -68,13 +68,14 @@ def build_graph(node_feats: torch.Tensor, global_feats, k: int, use_edges: bool 
     """graph_utils.py:248-324 (kNN branch).  node_feats [B, N, F] fp32 on the GPU."""
     if use_invariant_edges and n_radial_basis > 0:
         raise ValueError("Cannot use both invariant edges and radial basis functions!")
-    if radius is not None:
-        raise NotImplementedError("radius graphs are broken upstream (graph_utils.py:277 reads an undefined name)")
     if use_invariant_edges:
         raise NotImplementedError("use_invariant_edges is not on the equivariant hot path")
     B, N, _ = node_feats.shape
     node_feats = node_feats.contiguous()
     dev = node_feats.device
+    if radius is not None:
+        return _build_radius_graph(node_feats, global_feats, float(radius), use_edges, apply_pbc, n_radial_basis, r_max,
+                                   use_3d_distances)
     senders, receivers, dr = ops.knn_pbc(node_feats, k, None if apply_pbc is None else apply_pbc.cell,
                                          None if apply_pbc is None else apply_pbc.cell_inv)
     n_node = torch.full((B, 1), N, dtype=torch.int32)                  # host-side metadata, like jraph
@@ -90,3 +91,28 @@ def build_graph(node_feats: torch.Tensor, global_feats, k: int, use_edges: bool 
         raise AttributeError("'NoneType' object has no attribute 'shape'")  # the reference fails at :305 too
     return GraphsTuple(nodes=node_feats, edges=edges, receivers=receivers, senders=senders, globals=global_feats,
                        n_node=n_node, n_edge=n_edge)
+
+
+def _build_radius_graph(node_feats, global_feats, radius, use_edges, apply_pbc, n_radial_basis, r_max, use_3d_distances):
+    """The ``radius is not None`` branch of build_graph (graph_utils.py:266-277).  Upstream it cannot run (``x`` is
+    undefined at :277, np.where of the batched mask yields three arrays, the distances are already scalars at :298); this
+    is what it evidently means: every pair with 0 < |apply_pbc(x_i - x_j)| < radius, compute_distances' arithmetic
+    (:209-226, no EPS), in np.where order.  The edge list is ragged, so -- unlike the kNN branch -- senders / receivers
+    are flat (n_total,) arrays of per-graph LOCAL node ids, graph b owning the next n_edge[b] entries, and ``edges`` is
+    (1, n_total, 1 | n_radial_basis) as :319-320 leaves it.  The batched models of this package take equal-sized graphs
+    (kNN); the radius graph is a graph-construction utility."""
+    if use_3d_distances:
+        raise NotImplementedError("radius graphs carry scalar distances (compute_distances, graph_utils.py:209-226)")
+    B, N, _ = node_feats.shape
+    senders, receivers, dist, n_edge = ops.radius_graph(node_feats, radius, None if apply_pbc is None else apply_pbc.cell,
+                                                        None if apply_pbc is None else apply_pbc.cell_inv)
+    if not use_edges:
+        raise AttributeError("'NoneType' object has no attribute 'shape'")  # the reference fails at :319 too
+    if dist.numel() == 0:
+        edges = torch.empty((1, 0, max(n_radial_basis, 1)), dtype=torch.float32, device=dist.device)
+    else:
+        d3 = torch.zeros((dist.numel(), 3), dtype=torch.float32, device=dist.device)
+        d3[:, 0] = dist                                                # |(d, 0, 0)| = d exactly
+        edges = ops.edge_features(d3, n_radial_basis, r_max).unsqueeze(0)
+    return GraphsTuple(nodes=node_feats, edges=edges, receivers=receivers, senders=senders, globals=global_feats,
+                       n_node=torch.full((B, 1), N, dtype=torch.int32), n_edge=n_edge.to(torch.int32))

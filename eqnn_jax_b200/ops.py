@@ -120,6 +120,31 @@ def knn_pbc(x: torch.Tensor, k: int, cell=None, cell_inv=None, fma: bool = False
     return senders, receivers, dr
 
 
+def radius_graph(x: torch.Tensor, radius: float, cell=None, cell_inv=None):
+    """x [B, N, F>=3] -> (senders, receivers [n_total] int32 local ids, dist [n_total], n_edge [B] int64 on the host):
+    every pair with 0 < |apply_pbc(x_i - x_j)| < radius, in np.where order (graph, i, j).  The edge list is ragged,
+    so its length is read back once (one host synchronisation) before the fill pass."""
+    _req(x, _F32, "x")
+    B, N, F = x.shape
+    flags = 1 if cell is not None else 0
+    c9 = (C.c_float * 9)(*[float(v) for v in cell.reshape(-1)]) if cell is not None else None
+    ci9 = (C.c_float * 9)(*[float(v) for v in cell_inv.reshape(-1)]) if cell is not None else None
+    count = torch.empty((B * N,), dtype=_I32, device=x.device)
+    rowptr = torch.empty((B * N + 1,), dtype=_I32, device=x.device)
+    check(lib().eqnn_radius_graph(_ptr(x), F, c9, ci9, B, N, float(radius), flags, _ptr(count), None, None, None, None,
+                                  _stream()), "radius_graph (count)")
+    check(lib().eqnn_exclusive_scan_i32(_ptr(count), B * N, _ptr(rowptr), _stream()), "exclusive_scan")
+    offs = rowptr[::N].cpu().to(torch.int64)                       # B + 1 graph offsets (the host sync)
+    total = int(offs[-1])
+    senders = torch.empty((total,), dtype=_I32, device=x.device)
+    receivers = torch.empty((total,), dtype=_I32, device=x.device)
+    dist = torch.empty((total,), dtype=_F32, device=x.device)
+    if total:
+        check(lib().eqnn_radius_graph(_ptr(x), F, c9, ci9, B, N, float(radius), flags, None, _ptr(rowptr), _ptr(senders),
+                                      _ptr(receivers), _ptr(dist), _stream()), "radius_graph (fill)")
+    return senders, receivers, dist, offs[1:] - offs[:-1]
+
+
 def edge_features(dr: torch.Tensor, n_rb: int, r_max: float) -> torch.Tensor:
     """dr [..., 3] -> |dr| [..., 1] (n_rb == 0) or bessel basis [..., n_rb]."""
     _req(dr, _F32, "dr")

@@ -76,6 +76,18 @@ int eqnn_knn_pbc(const float* x, int ld_x, const float* cell, const float* cell_
                  int flags, int32_t* senders, int32_t* receivers, float* dr, void* ws, size_t ws_bytes,
                  eqnn_stream_t stream);
 
+/* Radius graph: the `radius is not None` branch of build_graph (models/utils/graph_utils.py:266-277) as it evidently
+ * means to work (upstream it cannot run: `x` is undefined at :277 and np.where of the batched mask returns three arrays).
+ * Edges i -> j of every graph with 0 < |apply_pbc(x_i - x_j)| < radius (compute_distances, :209-226: no EPS), in np.where
+ * order (i, then j ascending).  Two passes over the same kernel:
+ *   rowptr == NULL: count[b * N + i] = number of edges leaving i;
+ *   rowptr given (eqnn_exclusive_scan_i32 of count, B * N + 1 entries): senders / receivers (local ids) and dist are
+ *   written at rowptr[b * N + i] ...  -- a ragged edge list, graph b owning [rowptr[b N], rowptr[(b + 1) N]).     */
+int eqnn_radius_graph(const float* x, int ld_x, const float* cell, const float* cell_inv, int B, int N, float radius,
+                      int flags, int32_t* count, const int32_t* rowptr, int32_t* senders, int32_t* receivers, float* dist,
+                      eqnn_stream_t stream);
+int eqnn_exclusive_scan_i32(const int32_t* count, int64_t n, int32_t* out, eqnn_stream_t stream);
+
 /* GraphsTuple.edges of build_graph (models/utils/graph_utils.py:298-302):
  *   n_rb == 0: out [n_edges, 1] = |dr|;  n_rb > 0: out [n_edges, n_rb] = e3nn.bessel(|dr|, n_rb, r_max) */
 int eqnn_edge_features(const float* dr, int64_t n_edges, int n_rb, double r_max, float* out, eqnn_stream_t stream);

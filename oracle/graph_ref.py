@@ -73,6 +73,30 @@ def nearest_neighbors(x, k: int, apply_pbc: Optional[Callable] = None):
     return sources, targets, dr[sources, targets]
 
 
+def compute_distances(x, apply_pbc: Optional[Callable] = None):
+    """graph_utils.py:209-226: pairwise distances of one graph, no EPS."""
+    x = np.asarray(x, dtype=np.float32)
+    dr = x[:, None, :] - x[None, :, :]
+    if apply_pbc is not None:
+        dr = apply_pbc(dr)
+    sq = dr * dr
+    return np.sqrt((sq[..., 0] + sq[..., 1]) + sq[..., 2]).astype(np.float32)
+
+
+def radius_graph(x, radius: float, apply_pbc: Optional[Callable] = None):
+    """The `radius is not None` branch of build_graph (graph_utils.py:266-277) as it evidently means to work (upstream:
+    `x` undefined at :277, np.where of the batched mask returns three arrays): per graph, mask = (d < radius) & (d > 0),
+    sources, targets = np.where(mask), distances[sources, targets]; concatenated over the batch with per-graph counts."""
+    x = np.asarray(x, dtype=np.float32)
+    src, dst, dist, n_edge = [], [], [], []
+    for b in range(x.shape[0]):
+        d = compute_distances(x[b, :, :3], apply_pbc)
+        mask = (d < np.float32(radius)) & (d > 0)
+        s, t = np.where(mask)
+        src.append(s.astype(np.int32)); dst.append(t.astype(np.int32)); dist.append(d[s, t]); n_edge.append(int(mask.sum()))
+    return np.concatenate(src), np.concatenate(dst), np.concatenate(dist), np.array(n_edge)
+
+
 def bessel_np(x, n, x_max):
     x = np.asarray(x, dtype=np.float32)[..., None]
     j = np.arange(1, n + 1, dtype=np.float32)

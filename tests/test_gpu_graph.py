@@ -181,3 +181,41 @@ def test_cell_list_knn_is_bit_identical_to_dense_sweep(N, k, kind):
     assert torch.equal(s0, s1)
     assert torch.equal(r0, r1)
     assert torch.equal(d0.view(torch.int32), d1.view(torch.int32))
+
+
+@pytest.mark.parametrize("pbc", [None, "diag", "triclinic"])
+def test_radius_graph_matches_the_oracle_bit_for_bit(pbc):
+    """The radius branch of build_graph (graph_utils.py:266-277; cannot run upstream): pairs with 0 < d < radius in
+    np.where order, compute_distances' arithmetic.  Indices, counts and distances must be identical to the oracle."""
+    from eqnn_jax_b200 import graph_utils as GU
+    rng = np.random.default_rng(3)
+    B, N, radius = 3, 300, 0.21
+    x = rng.uniform(0.0, 1.0, size=(B, N, 3)).astype(np.float32)
+    x[1, 7] = x[1, 3]                                   # a duplicate: distance exactly 0 is excluded
+    cell = None
+    if pbc == "diag":
+        cell = np.diag([1.0, 0.9, 1.1]).astype(np.float32)
+    elif pbc == "triclinic":
+        cell = np.array([[1.0, 0.0, 0.0], [0.2, 0.9, 0.0], [0.1, 0.3, 1.1]], dtype=np.float32)
+    o_pbc = G.get_apply_pbc(cell=cell) if cell is not None else None
+    g_pbc = GU.get_apply_pbc(cell=cell) if cell is not None else None
+    ws, wt, wd, wn = G.radius_graph(x, radius, o_pbc)
+    g = GU.build_graph(torch.tensor(x).cuda(), None, k=0, radius=radius, apply_pbc=g_pbc)
+    assert np.array_equal(g.n_edge.cpu().numpy(), wn)
+    assert np.array_equal(g.senders.cpu().numpy(), ws) and np.array_equal(g.receivers.cpu().numpy(), wt)
+    assert g.edges.shape == (1, len(wd), 1)
+    assert np.array_equal(g.edges.cpu().numpy()[0, :, 0], wd)
+    assert wn.sum() > 0 and not np.any(ws == wt)
+    # Bessel edge features of the same graph (graph_utils.py:300-302)
+    gb = GU.build_graph(torch.tensor(x).cuda(), None, k=0, radius=radius, apply_pbc=g_pbc, n_radial_basis=8, r_max=0.3)
+    want = G.bessel_np(wd[:, None], 8, 0.3).reshape(len(wd), 8)
+    np.testing.assert_allclose(gb.edges.cpu().numpy()[0], want, rtol=1e-5, atol=1e-5 * np.abs(want).max())
+
+
+def test_radius_graph_empty_and_full():
+    from eqnn_jax_b200 import graph_utils as GU
+    x = torch.tensor(np.random.default_rng(0).uniform(0, 1, size=(2, 40, 3)).astype(np.float32)).cuda()
+    g = GU.build_graph(x, None, k=0, radius=1e-6)
+    assert int(g.n_edge.sum()) == 0 and g.senders.numel() == 0
+    g = GU.build_graph(x, None, k=0, radius=10.0)
+    assert g.n_edge.tolist() == [40 * 39, 40 * 39]

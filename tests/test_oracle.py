@@ -304,3 +304,30 @@ def test_knn_self_is_first_and_ties_are_stable():
     s, t, dr = G.nearest_neighbors(x, 3)
     assert t.reshape(6, 3).tolist() == [[0, 1, 2]] * 3 + [[3, 4, 5]] * 3
     assert s.tolist() == np.repeat(np.arange(6), 3).tolist()
+
+
+def test_radius_graph_restatement_properties():
+    """oracle.graph_ref.radius_graph (graph_utils.py:266-277, the branch that cannot run upstream): symmetric pairs, no
+    self loops, counts equal to a brute-force count in float64 away from the cut-off, np.where ordering."""
+    from oracle import graph_ref as G
+    rng = np.random.default_rng(1)
+    x = rng.uniform(0, 1, size=(2, 60, 3)).astype(np.float32)
+    cell = np.diag([1.0, 1.0, 1.0]).astype(np.float32)
+    s, t, d, n = G.radius_graph(x, 0.3, G.get_apply_pbc(cell=cell))
+    assert n.sum() == len(s) == len(t) == len(d)
+    off = 0
+    for b in range(2):
+        sb, tb = s[off:off + n[b]], t[off:off + n[b]]
+        pairs = set(zip(sb.tolist(), tb.tolist()))
+        assert all((j, i) in pairs for i, j in pairs) and all(i != j for i, j in pairs)
+        assert np.all(np.diff(sb.astype(np.int64) * 60 + tb) > 0)           # np.where order: row-major, strictly increasing
+        dr = x[b, :, None, :].astype(np.float64) - x[b, None, :, :]
+        dr -= np.round(dr)
+        d64 = np.sqrt((dr ** 2).sum(-1))
+        sure = (np.abs(d64 - 0.3) > 1e-5)
+        want = (d64 < 0.3) & (d64 > 0)
+        got = np.zeros_like(want)
+        got[sb, tb] = True
+        assert np.array_equal(got[sure], want[sure])
+        off += n[b]
+    assert np.all((d > 0) & (d < 0.3))
