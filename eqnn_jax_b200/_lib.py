@@ -57,8 +57,8 @@ SIGNATURES: Dict[str, tuple] = {
     "eqnn_node_update_bwd": (_i, [_p, _i, _i, _p, _i, _p, _f, _p, _i, _i, _i, _p, _p, _f, _f, _p, _p, _p, _i64, _p, _p,
                                   _p, _p, _p, _p, _sz, _p]),
     "eqnn_egnn_geom_fwd": (_i, [_p, _i, _i, _p, _p, _p, _p, _i, _d, _p, _p, _p]),
-    "eqnn_egnn_coord_fwd": (_i, [_p, _p, _i, _i, _p, _i, _p, _i, _p, _p, _p, _i, _p]),
-    "eqnn_egnn_coord_bwd": (_i, [_p, _p, _i, _i, _p, _p, _i, _p, _i, _d, _p, _p, _p, _p, _p]),
+    "eqnn_egnn_coord_fwd": (_i, [_p, _p, _i, _i, _p, _i, _p, _i, _p, _p, _p, _i, _p, _p]),
+    "eqnn_egnn_coord_bwd": (_i, [_p, _p, _i, _i, _p, _p, _i, _p, _i, _d, _p, _p, _p, _p, _p, _p]),
     "eqnn_egnn_sender_acc": (_i, [_p, _p, _p, _i, _p, _p]),
     "eqnn_segnn_tplg_fwd": (_i, [_p, _i, _i, _p, _p, _i, _i, _i, _p, _i, _i, _i64, _p, _i, _p]),
     "eqnn_segnn_ycontract": (_i, [_p, _p, _i, _p, _i, _i, _i64, _i, _i, _p, _p]),
@@ -80,8 +80,8 @@ SIGNATURES: Dict[str, tuple] = {
     "eqnn_egnn_edge_input_bwd": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _i, _p, _p, _p, _i, _p]),
     "eqnn_egnn_xv_base": (_i, [_p, _i, _p, _p, _i64, _p, _p]),
     "eqnn_egnn_node_assemble": (_i, [_p, _i, _i, _p, _i64, _p, _p]),
-    "eqnn_egnn_segment_rows_fwd": (_i, [_p, _i, _i, _p, _i, _i, _p, _i, _p]),
-    "eqnn_egnn_segment_rows_bwd": (_i, [_p, _i, _i, _p, _i, _p, _i, _i, _p, _p]),
+    "eqnn_egnn_segment_rows_fwd": (_i, [_p, _i, _i, _p, _i, _i, _p, _i, _p, _p]),
+    "eqnn_egnn_segment_rows_bwd": (_i, [_p, _i, _i, _p, _i, _p, _i, _i, _p, _p, _p]),
     "eqnn_egnn_xv_bwd": (_i, [_p, _i, _p, _p, _p, _i, _p, _i64, _p, _p, _p, _p]),
     "eqnn_copy_cols": (_i, [_p, _i, _i, _i, _i64, _i, _i, _p, _i, _i, _p]),
     "eqnn_softgate_fwd": (_i, [_p, _p, _i64, _p, _p]),

@@ -69,25 +69,63 @@ __global__ void __launch_bounds__(256) egnn_coord_fwd_kernel(const float4* __res
                                                              const float* __restrict__ t, int use_tanh, int agg,
                                                              const int32_t* __restrict__ rowptr, int n_nodes,
                                                              const float* __restrict__ pos, int ld, Cell3 cl,
-                                                             float* __restrict__ pos_out, int ld_out) {
+                                                             float* __restrict__ pos_out, int ld_out,
+                                                             int32_t* __restrict__ argmax) {
   const int lane = threadIdx.x & 31;
   const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= n_nodes) return;
   const int p0 = rowptr[row], p1 = rowptr[row + 1];
   float ax = 0.f, ay = 0.f, az = 0.f;
-  for (int p = p0 + lane; p < p1; p += 32) {
-    const float4 r = rij4[p];
-    float tt = t[p];
-    if (use_tanh) tt = tanhf(tt);
-    ax += fminf(fmaxf(r.x * tt, -100.f), 100.f);
-    ay += fminf(fmaxf(r.y * tt, -100.f), 100.f);
-    az += fminf(fmaxf(r.z * tt, -100.f), 100.f);
-  }
+  if (agg == 2) {
+    // jraph.segment_max of the clipped translations, component by component; the first edge attaining a maximum wins
+    float m[3] = {-INFINITY, -INFINITY, -INFINITY};
+    int am[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff};
+    for (int p = p0 + lane; p < p1; p += 32) {
+      const float4 r = rij4[p];
+      float tt = t[p];
+      if (use_tanh) tt = tanhf(tt);
+      const float v[3] = {fminf(fmaxf(r.x * tt, -100.f), 100.f), fminf(fmaxf(r.y * tt, -100.f), 100.f),
+                          fminf(fmaxf(r.z * tt, -100.f), 100.f)};
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    ax += __shfl_xor_sync(0xffffffffu, ax, o);
-    ay += __shfl_xor_sync(0xffffffffu, ay, o);
-    az += __shfl_xor_sync(0xffffffffu, az, o);
+      for (int c = 0; c < 3; ++c)
+        if (v[c] > m[c] || am[c] == 0x7fffffff) {
+          m[c] = v[c];
+          am[c] = p;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float mo = __shfl_xor_sync(0xffffffffu, m[c], o);
+        const int ao = __shfl_xor_sync(0xffffffffu, am[c], o);
+        if (ao != 0x7fffffff && (am[c] == 0x7fffffff || mo > m[c] || (mo == m[c] && ao < am[c]))) {
+          m[c] = mo;
+          am[c] = ao;
+        }
+      }
+    if (lane == 0) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) argmax[(size_t)row * 3 + c] = am[c] == 0x7fffffff ? -1 : am[c];
+    }
+    ax = am[0] == 0x7fffffff ? 0.f : m[0];
+    ay = am[1] == 0x7fffffff ? 0.f : m[1];
+    az = am[2] == 0x7fffffff ? 0.f : m[2];
+  } else {
+    for (int p = p0 + lane; p < p1; p += 32) {
+      const float4 r = rij4[p];
+      float tt = t[p];
+      if (use_tanh) tt = tanhf(tt);
+      ax += fminf(fmaxf(r.x * tt, -100.f), 100.f);
+      ay += fminf(fmaxf(r.y * tt, -100.f), 100.f);
+      az += fminf(fmaxf(r.z * tt, -100.f), 100.f);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ax += __shfl_xor_sync(0xffffffffu, ax, o);
+      ay += __shfl_xor_sync(0xffffffffu, ay, o);
+      az += __shfl_xor_sync(0xffffffffu, az, o);
+    }
   }
   if (lane == 0) {
     const float inv = (agg == 1) ? 1.f / (float)max(p1 - p0, 1) : 1.f;
@@ -113,7 +151,8 @@ __global__ void __launch_bounds__(256) egnn_coord_bwd_kernel(const float4* __res
                                                              const float* __restrict__ dpos_out, int n_rb, float r_max,
                                                              float pref, const float* __restrict__ dfeats, int mode,
                                                              float* __restrict__ dt, float4* __restrict__ dre,
-                                                             float* __restrict__ dpos_in) {
+                                                             float* __restrict__ dpos_in,
+                                                             const int32_t* __restrict__ argmax) {
   const int lane = threadIdx.x & 31;
   const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= n_nodes) return;
@@ -133,8 +172,13 @@ __global__ void __launch_bounds__(256) egnn_coord_bwd_kernel(const float4* __res
       tt = t[p];
       tp = use_tanh ? tanhf(tt) : tt;
     }
-    const float mx = (fabsf(r.x * tp) <= 100.f) ? 1.f : 0.f, my = (fabsf(r.y * tp) <= 100.f) ? 1.f : 0.f,
-                mz = (fabsf(r.z * tp) <= 100.f) ? 1.f : 0.f;
+    float mx = (fabsf(r.x * tp) <= 100.f) ? 1.f : 0.f, my = (fabsf(r.y * tp) <= 100.f) ? 1.f : 0.f,
+          mz = (fabsf(r.z * tp) <= 100.f) ? 1.f : 0.f;
+    if (agg == 2) {                                   // segment_max: only the winning edge of a component sees its gradient
+      if (argmax[(size_t)row * 3] != p) mx = 0.f;
+      if (argmax[(size_t)row * 3 + 1] != p) my = 0.f;
+      if (argmax[(size_t)row * 3 + 2] != p) mz = 0.f;
+    }
     if (mode == 0) {
       if (on) {
         float d = r.x * gx * mx + r.y * gy * my + r.z * gz * mz;
@@ -375,13 +419,30 @@ __global__ void egnn_node_assemble_kernel(const float* __restrict__ nodes, int F
 // read by the (x, h) and (x, v) node functions): warp per receiver row, lanes over the d columns, edges in CSR order
 __global__ void __launch_bounds__(256) egnn_segment_rows_fwd_kernel(const float* __restrict__ rows, int d, int act,
                                                                     const int32_t* __restrict__ rowptr, int n_nodes,
-                                                                    int agg, float* __restrict__ out, int ld_out) {
+                                                                    int agg, float* __restrict__ out, int ld_out,
+                                                                    int32_t* __restrict__ argmax) {
   const int lane = threadIdx.x & 31;
   const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= n_nodes) return;
   const int p0 = rowptr[row], p1 = rowptr[row + 1];
   const float inv = (agg == 1) ? 1.f / (float)max(p1 - p0, 1) : 1.f;
   for (int c = lane; c < d; c += 32) {
+    if (agg == 2) {
+      // jraph.segment_max: the maximum and the CSR position of the first edge attaining it (gradient routing)
+      float a = -INFINITY;
+      int am = -1;
+      for (int p = p0; p < p1; ++p) {
+        float v = rows[(size_t)p * d + c];
+        if (act) v = gelu_tanh(v);
+        if (v > a || am < 0) {
+          a = v;
+          am = p;
+        }
+      }
+      out[(size_t)row * ld_out + c] = am < 0 ? 0.f : a;
+      argmax[(size_t)row * d + c] = am;
+      continue;
+    }
     float a = 0.f;
     for (int p = p0; p < p1; ++p) {
       const float v = rows[(size_t)p * d + c];
@@ -395,7 +456,8 @@ __global__ void __launch_bounds__(256) egnn_segment_rows_fwd_kernel(const float*
 __global__ void __launch_bounds__(256) egnn_segment_rows_bwd_kernel(const float* __restrict__ dmi, int ld_dmi, int d,
                                                                     const float* __restrict__ z, int act,
                                                                     const int32_t* __restrict__ rowptr, int n_nodes,
-                                                                    int agg, float* __restrict__ target) {
+                                                                    int agg, float* __restrict__ target,
+                                                                    const int32_t* __restrict__ argmax) {
   const int lane = threadIdx.x & 31;
   const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= n_nodes) return;
@@ -403,6 +465,14 @@ __global__ void __launch_bounds__(256) egnn_segment_rows_bwd_kernel(const float*
   const float inv = (agg == 1) ? 1.f / (float)max(p1 - p0, 1) : 1.f;
   for (int c = lane; c < d; c += 32) {
     const float g = dmi[(size_t)row * ld_dmi + c] * inv;
+    if (agg == 2) {                                   // segment_max: the winning edge takes the whole gradient
+      const int p = argmax[(size_t)row * d + c];
+      if (p >= 0) {
+        const size_t i = (size_t)p * d + c;
+        target[i] += act ? g * gelu_tanh_grad(z[i]) : g;
+      }
+      continue;
+    }
     for (int p = p0; p < p1; ++p) {
       const size_t i = (size_t)p * d + c;
       target[i] += act ? g * gelu_tanh_grad(z[i]) : g;
@@ -911,31 +981,32 @@ extern "C" int eqnn_egnn_geom_fwd(const float* pos, int ld_pos, int n_nodes, con
 
 extern "C" int eqnn_egnn_coord_fwd(const float* rij4, const float* t, int use_tanh, int agg, const int32_t* rowptr,
                                    int n_nodes, const float* pos, int ld_pos, const float* cell, const float* cell_inv,
-                                   float* pos_out, int ld_out, eqnn_stream_t stream) {
+                                   float* pos_out, int ld_out, int32_t* argmax, eqnn_stream_t stream) {
   EQNN_CHECK_ARG(rij4 && t && rowptr && pos && pos_out && ld_pos >= 3 && ld_out >= 3, "egnn_coord_fwd: bad argument");
-  EQNN_CHECK_ARG(agg == 0 || agg == 1, "egnn_coord_fwd: agg must be 0 (sum) or 1 (mean)");
+  EQNN_CHECK_ARG(agg >= 0 && agg <= 2 && (agg != 2 || argmax), "egnn_coord_fwd: agg must be 0 (sum), 1 (mean) or 2 (max, with the argmax buffer)");
   if (n_nodes <= 0) return EQNN_OK;
   Cell3 cl;
   int rc = make_cell(cl, cell, cell_inv);
   if (rc) return rc;
   egnn_coord_fwd_kernel<<<(unsigned)ceil_div64((int64_t)n_nodes * 32, 256), 256, 0, as_stream(stream)>>>(
-      reinterpret_cast<const float4*>(rij4), t, use_tanh, agg, rowptr, n_nodes, pos, ld_pos, cl, pos_out, ld_out);
+      reinterpret_cast<const float4*>(rij4), t, use_tanh, agg, rowptr, n_nodes, pos, ld_pos, cl, pos_out, ld_out, argmax);
   EQNN_CHECK_LAUNCH();
   return EQNN_OK;
 }
 
 extern "C" int eqnn_egnn_coord_bwd(const float* rij4, const float* t, int use_tanh, int agg, const int32_t* rowptr,
                                    const int32_t* perm, int n_nodes, const float* dpos_out, int n_rb, double r_max,
-                                   const float* dfeats, float* dt, float* dre, float* dpos_in, eqnn_stream_t stream) {
+                                   const float* dfeats, float* dt, float* dre, float* dpos_in, const int32_t* argmax,
+                                   eqnn_stream_t stream) {
   EQNN_CHECK_ARG(rij4 && t && rowptr && dpos_out, "egnn_coord_bwd: bad argument");
-  EQNN_CHECK_ARG(agg == 0 || agg == 1, "egnn_coord_bwd: agg must be 0 (sum) or 1 (mean)");
+  EQNN_CHECK_ARG(agg >= 0 && agg <= 2 && (agg != 2 || argmax), "egnn_coord_bwd: agg must be 0 (sum), 1 (mean) or 2 (max, with the argmax buffer)");
   const int mode = dfeats ? 1 : 0;
   EQNN_CHECK_ARG(mode == 1 ? (perm && dre && dpos_in) : (dt != nullptr), "egnn_coord_bwd: missing output for this phase");
   if (n_nodes <= 0) return EQNN_OK;
   const float pref = n_rb > 0 ? (float)sqrt(2.0 / r_max) : 1.f;
   egnn_coord_bwd_kernel<<<(unsigned)ceil_div64((int64_t)n_nodes * 32, 256), 256, 0, as_stream(stream)>>>(
       reinterpret_cast<const float4*>(rij4), t, use_tanh, agg, rowptr, perm, n_nodes, dpos_out, n_rb, (float)r_max, pref,
-      dfeats, mode, dt, reinterpret_cast<float4*>(dre), dpos_in);
+      dfeats, mode, dt, reinterpret_cast<float4*>(dre), dpos_in, argmax);
   EQNN_CHECK_LAUNCH();
   return EQNN_OK;
 }
@@ -998,23 +1069,24 @@ extern "C" int eqnn_egnn_node_assemble(const float* nodes, int F, int h_off, con
 }
 
 extern "C" int eqnn_egnn_segment_rows_fwd(const float* rows, int d, int act, const int32_t* rowptr, int n_nodes, int agg,
-                                          float* out, int ld_out, eqnn_stream_t stream) {
-  EQNN_CHECK_ARG(rows && rowptr && out && d >= 1 && ld_out >= d && (agg == 0 || agg == 1), "egnn_segment_rows_fwd: bad argument");
+                                          float* out, int ld_out, int32_t* argmax, eqnn_stream_t stream) {
+  EQNN_CHECK_ARG(rows && rowptr && out && d >= 1 && ld_out >= d && agg >= 0 && agg <= 2 && (agg != 2 || argmax),
+                 "egnn_segment_rows_fwd: bad argument");
   if (n_nodes <= 0) return EQNN_OK;
   egnn_segment_rows_fwd_kernel<<<(unsigned)ceil_div64((int64_t)n_nodes * 32, 256), 256, 0, as_stream(stream)>>>(
-      rows, d, act, rowptr, n_nodes, agg, out, ld_out);
+      rows, d, act, rowptr, n_nodes, agg, out, ld_out, argmax);
   EQNN_CHECK_LAUNCH();
   return EQNN_OK;
 }
 
 extern "C" int eqnn_egnn_segment_rows_bwd(const float* dmi, int ld_dmi, int d, const float* z, int act,
                                           const int32_t* rowptr, int n_nodes, int agg, float* target,
-                                          eqnn_stream_t stream) {
-  EQNN_CHECK_ARG(dmi && rowptr && target && d >= 1 && ld_dmi >= d && (agg == 0 || agg == 1) && (z || !act),
-                 "egnn_segment_rows_bwd: bad argument");
+                                          const int32_t* argmax, eqnn_stream_t stream) {
+  EQNN_CHECK_ARG(dmi && rowptr && target && d >= 1 && ld_dmi >= d && agg >= 0 && agg <= 2 && (z || !act) &&
+                     (agg != 2 || argmax), "egnn_segment_rows_bwd: bad argument");
   if (n_nodes <= 0) return EQNN_OK;
   egnn_segment_rows_bwd_kernel<<<(unsigned)ceil_div64((int64_t)n_nodes * 32, 256), 256, 0, as_stream(stream)>>>(
-      dmi, ld_dmi, d, z, act, rowptr, n_nodes, agg, target);
+      dmi, ld_dmi, d, z, act, rowptr, n_nodes, agg, target, argmax);
   EQNN_CHECK_LAUNCH();
   return EQNN_OK;
 }

@@ -23,7 +23,8 @@ aggregated messages: h' = h + phi_h([h, m_i]) (egnn.py:152-166), m_i = segment r
 following steps run as (x, v, h) with d_hidden scalars (egnn.py:171-196) -- all four layouts of the reference.
 Graph globals (broadcast to every edge and node by jraph, concatenated to the pooled features and LayerNorm-ed
 before the read-out, egnn.py:41-60,163-164,211-212,332-336) are supported for the (x), (x, h) and (x, v, h) layouts.
-Not built yet: globals with the (x, v) layout, max aggregation -> NotImplementedError, never a silent fallback.
+Aggregations: sum, mean and max (jraph.segment_max with the gradient routed to the winning edge; jnp.max read-out).
+Not built yet: globals with the (x, v) layout -> NotImplementedError, never a silent fallback.
 """
 from __future__ import annotations
 
@@ -76,8 +77,8 @@ class EGNN:
         self._variant(n_feat)
         if self.activation != "gelu":
             raise NotImplementedError("only activation='gelu' has a B200 kernel on this path")
-        if self.message_passing_agg not in ("sum", "mean") or self.readout_agg not in ("sum", "mean"):
-            raise NotImplementedError("aggregations must be 'sum' or 'mean' on the B200 path")
+        if self.message_passing_agg not in ("sum", "mean", "max") or self.readout_agg not in ("sum", "mean", "max"):
+            raise ValueError("aggregations must be 'sum', 'mean' or 'max' (models/egnn.py:282-284,326)")
         if self.n_layers < 2:
             raise NotImplementedError("n_layers >= 2 expected")
 
@@ -240,7 +241,7 @@ class EGNN:
         nf = self.n_radial_basis if self.n_radial_basis > 0 else 1
         cell = None if self.apply_pbc is None else self.apply_pbc.cell
         cinv = None if self.apply_pbc is None else self.apply_pbc.cell_inv
-        agg = 1 if self.message_passing_agg == "mean" else 0
+        agg = ops.AGG[self.message_passing_agg]
         tc = self.tensor_cores
         nodes = x.reshape(Nt, x.shape[-1])
         saved = {"steps": []}
@@ -277,16 +278,19 @@ class EGNN:
             _mm(Et, 1, d, 1.0, a, 0, d, theta, st["k_last"], 1, t, 0, Et, tc=True, pro=1, pro_scale=1.0,
                 tag="egnn_mlp_fwd", tf32x3=tc)
             nodes_next = torch.empty((Nt, F_out), **f32)
-            sv = dict(rij4=rij4, U=U, acts=acts, t=t, Za=Za, Mg=Mg, nodes=nodes)
+            # jraph.segment_max (egnn.py:282-284): winners of the translations (3 components) and of the messages
+            ax3 = torch.empty((Nt, 3), dtype=torch.int32, device=dev) if agg == 2 else None
+            am = torch.empty((Nt, d), dtype=torch.int32, device=dev) if agg == 2 else None
+            sv = dict(rij4=rij4, U=U, acts=acts, t=t, Za=Za, Mg=Mg, nodes=nodes, ax3=ax3, am=am)
             gated = st["phi_a"] is not None
             if not vel:
-                ops.egnn_coord_fwd(rij4, t, self.tanh_out, agg, rowptr, Nt, nodes, F, cell, cinv, nodes_next, F)
+                ops.egnn_coord_fwd(rij4, t, self.tanh_out, agg, rowptr, Nt, nodes, F, cell, cinv, nodes_next, F, argmax=ax3)
                 if dh > 0:                                   # (x, h): h' = h + phi_h([h, m_i]), egnn.py:152-166
                     wc = dh + d + G_                         # [h | m_i | globals]
                     Cc = torch.empty((Nt, wc), **f32)
                     ops.copy_cols(nodes, F, 3, dh, Nt, Cc, wc, 0)
                     ops.egnn_segment_rows_fwd(Mg if gated else acts[nE - 1], d, not gated, rowptr, Nt, agg, Cc, wc,
-                                              col_off=dh)
+                                              col_off=dh, argmax=am)
                     if G_:
                         ops.copy_cols(glob, G_, 0, G_, Nt, Cc, wc, dh + d, group=N)
                     zh = self._mlp_fwd(theta, st["phi_h"], Cc, 0, wc, Nt)
@@ -301,13 +305,13 @@ class EGNN:
                     cin, c_off, c_ld = nodes, 6, F
                 else:                                        # concats = m_i (egnn.py:180), returned as new scalars
                     cin, c_off, c_ld = torch.empty((Nt, d), **f32), 0, d
-                    ops.egnn_segment_rows_fwd(Mg if gated else acts[nE - 1], d, not gated, rowptr, Nt, agg, cin, d)
+                    ops.egnn_segment_rows_fwd(Mg if gated else acts[nE - 1], d, not gated, rowptr, Nt, agg, cin, d, argmax=am)
                 zv = self._mlp_fwd(theta, st["phi_v"], cin, c_off, c_ld, Nt)
                 zh = self._mlp_fwd(theta, st["phi_h"], cin, c_off, c_ld, Nt) if dh > 0 else None
                 zx = self._mlp_fwd(theta, st["phi_xx"], cin, c_off, c_ld, Nt) if st["phi_xx"] is not None else None
                 base = torch.empty((Nt, 3), **f32)
                 ops.egnn_xv_base(nodes, F, None if zx is None else zx[-1], zv[-1], Nt, base)
-                ops.egnn_coord_fwd(rij4, t, self.tanh_out, agg, rowptr, Nt, base, 3, cell, cinv, nodes_next, F_out)
+                ops.egnn_coord_fwd(rij4, t, self.tanh_out, agg, rowptr, Nt, base, 3, cell, cinv, nodes_next, F_out, argmax=ax3)
                 if dh > 0:
                     ops.egnn_node_assemble(nodes, F, 6, zh[-1], Nt, nodes_next)
                 else:
@@ -320,7 +324,12 @@ class EGNN:
         if self.task == "node":
             return nodes.view(B, N, F), saved
         pooled = torch.empty((B, F), **f32)
-        ops.pool_fwd(nodes, B, N, F, 1 if self.readout_agg == "mean" else 0, pooled)
+        ro_arg = None
+        if self.readout_agg == "max":                        # jnp.max over the nodes (egnn.py:326): value + arg-max
+            ro_arg = torch.empty((B, F), dtype=torch.int32, device=dev)
+            ops.pool_max_fwd(nodes, B, N, F, pooled, ro_arg)
+        else:
+            ops.pool_fwd(nodes, B, N, F, 1 if self.readout_agg == "mean" else 0, pooled)
         a, ln_stats = pooled, None
         if G_:
             a = torch.empty((B, F + G_), **f32)
@@ -333,7 +342,7 @@ class EGNN:
             _mm(B, h, fan, 1.0, a, 0, fan, theta, ko, h, zl, 0, h, pro=pro, pro_scale=1.0, epi=1, aux=theta, aux_off=bo)
             zs.append(zl)
             a, pro = zl, 1
-        saved.update(pooled=pooled, ro_z=zs, ro_in=ro_in, ln_stats=ln_stats)
+        saved.update(pooled=pooled, ro_z=zs, ro_in=ro_in, ln_stats=ln_stats, ro_arg=ro_arg)
         return zs[-1], saved
 
     def _backward(self, theta, gtheta, saved, gout, B, N, E, csr):
@@ -346,7 +355,7 @@ class EGNN:
         d = self.d_hidden
         nf = self.n_radial_basis if self.n_radial_basis > 0 else 1
         F = steps[-1]["F_out"]                               # width of the final node features
-        agg = 1 if self.message_passing_agg == "mean" else 0
+        agg = ops.AGG[self.message_passing_agg]
         tc = self.tensor_cores
         gtheta.zero_()
         if self.task == "node":
@@ -372,7 +381,10 @@ class EGNN:
                                   self._ln[0], self._ln[1])
                 dz = d_pool
             dN = torch.empty((Nt, F), **f32)
-            ops.pool_bwd(dz, B, N, F, 1 if self.readout_agg == "mean" else 0, dN)
+            if self.readout_agg == "max":
+                ops.pool_max_bwd(dz, saved["ro_arg"], B, N, F, dN)
+            else:
+                ops.pool_bwd(dz, B, N, F, 1 if self.readout_agg == "mean" else 0, dN)
         dt = torch.empty((Et,), **f32)
         dre = torch.empty((Et, 4), **f32)
         for si in range(len(steps) - 1, -1, -1):
@@ -386,7 +398,7 @@ class EGNN:
                 g3 = torch.empty((Nt, 3), **f32)
                 ops.copy_cols(dN, F_out, 0, 3, Nt, g3, 3, 0)
             ops.egnn_coord_bwd(rij4, t, self.tanh_out, agg, rowptr, perm, Nt, g3, self.n_radial_basis, self.r_max,
-                               None, dt, None, None)
+                               None, dt, None, None, argmax=sv["ax3"])
             dC, dC_ld, dC_off = None, 0, 0                    # dL/dm_i lives in dC[:, dC_off:], row stride dC_ld
             if vel and dh == 0:
                 # (x, v) node function first: m_i feeds phi_v / phi_xx and is returned as the new scalar attributes
@@ -432,7 +444,7 @@ class EGNN:
                     dM = torch.empty((Et, d), **f32)
                     _mm(Et, d, d, 1.0, dZ, 0, d, theta, ko, d, dM, 0, d, tb=True, tag="egnn_mlp_bwd", tf32x3=tc)
                     if dC is not None:                              # + dL/dm_i / deg on the gated message
-                        ops.egnn_segment_rows_bwd(dC, dC_ld, dC_off, d, None, 0, rowptr, Nt, agg, dM)
+                        ops.egnn_segment_rows_bwd(dC, dC_ld, dC_off, d, None, 0, rowptr, Nt, agg, dM, argmax=sv["am"])
                     dZa = torch.empty((Et, d), **f32)
                     ops.softgate_bwd(ZL, Za, dM, dZa, dM)           # dM <- dM * sigmoid(Za)  (first branch into Z_L)
                     ops.dense_wgrad(d, d, Et, ZL, 0, d, dZa, d, gtheta, ka, d, gtheta, ba, pro=1, pro_scale=1.0, tf32x3=tc,
@@ -447,7 +459,7 @@ class EGNN:
                     _mm(Et, fan, d, 1.0, dZ, 0, d, theta, ko, d, dZp, 0, fan, tb=True, epi=2, aux=acts[l - 1], ld_aux=fan,
                         epi_scale=1.0, tag="egnn_mlp_bwd", tf32x3=tc)
                     if dC is not None and l == nE:                  # message = gelu(Z_L): + dL/dm_i / deg * gelu'(Z_L)
-                        ops.egnn_segment_rows_bwd(dC, dC_ld, dC_off, d, acts[l - 1], 1, rowptr, Nt, agg, dZp)
+                        ops.egnn_segment_rows_bwd(dC, dC_ld, dC_off, d, acts[l - 1], 1, rowptr, Nt, agg, dZp, argmax=sv["am"])
                     dZ = dZp
                 elif si > 0:
                     dU = torch.empty((Et, fan), **f32)
@@ -460,7 +472,7 @@ class EGNN:
                     ops.copy_cols(dU, K0, 0, nf, Et, dfeats, nf, 0)
                 mix = torch.empty((Nt, 3), **f32)
                 ops.egnn_coord_bwd(rij4, t, self.tanh_out, agg, rowptr, perm, Nt, g3, self.n_radial_basis, self.r_max,
-                                   dfeats, None, dre, mix)
+                                   dfeats, None, dre, mix, argmax=sv["ax3"])
                 ops.egnn_sender_acc(dre, rowptr_s, perm_s, Nt, mix)
             if not vel:
                 if dh == 0 or si == 0:

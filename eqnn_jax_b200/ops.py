@@ -382,15 +382,17 @@ def egnn_geom_fwd(pos, ld_pos, n_nodes, rowptr, src, cell, cell_inv, n_rb, r_max
                                    float(r_max), _ptr(rij4), _ptr(feats), _stream()), "egnn_geom_fwd")
 
 
-def egnn_coord_fwd(rij4, t, use_tanh, agg, rowptr, n_nodes, pos, ld_pos, cell, cell_inv, pos_out, ld_out):
+def egnn_coord_fwd(rij4, t, use_tanh, agg, rowptr, n_nodes, pos, ld_pos, cell, cell_inv, pos_out, ld_out, argmax=None):
     check(lib().eqnn_egnn_coord_fwd(_ptr(rij4), _ptr(t), int(use_tanh), agg, _ptr(rowptr), n_nodes, _ptr(pos), ld_pos,
-                                    _c9(cell), _c9(cell_inv), _ptr(pos_out), ld_out, _stream()), "egnn_coord_fwd")
+                                    _c9(cell), _c9(cell_inv), _ptr(pos_out), ld_out, _ptr(argmax), _stream()),
+          "egnn_coord_fwd")
 
 
-def egnn_coord_bwd(rij4, t, use_tanh, agg, rowptr, perm, n_nodes, dpos_out, n_rb, r_max, dfeats, dt, dre, dpos_in):
+def egnn_coord_bwd(rij4, t, use_tanh, agg, rowptr, perm, n_nodes, dpos_out, n_rb, r_max, dfeats, dt, dre, dpos_in,
+                   argmax=None):
     check(lib().eqnn_egnn_coord_bwd(_ptr(rij4), _ptr(t), int(use_tanh), agg, _ptr(rowptr), _ptr(perm), n_nodes,
                                     _ptr(dpos_out), n_rb, float(r_max), _ptr(dfeats), _ptr(dt), _ptr(dre),
-                                    _ptr(dpos_in), _stream()), "egnn_coord_bwd")
+                                    _ptr(dpos_in), _ptr(argmax), _stream()), "egnn_coord_bwd")
 
 
 def egnn_sender_acc(dre, rowptr_s, perm_s, n_nodes, dpos):
@@ -545,14 +547,15 @@ def egnn_node_assemble(nodes, F, h_off, ph, n, nodes_next):
           "egnn_node_assemble")
 
 
-def egnn_segment_rows_fwd(rows, d, act, rowptr, n_nodes, agg, out, ld_out, col_off=0):
+def egnn_segment_rows_fwd(rows, d, act, rowptr, n_nodes, agg, out, ld_out, col_off=0, argmax=None):
+    """agg 2 = jraph.segment_max: argmax [n_nodes, d] int32 receives the winning CSR positions."""
     check(lib().eqnn_egnn_segment_rows_fwd(_ptr(rows), d, int(act), _ptr(rowptr), n_nodes, agg, _off(out, col_off), ld_out,
-                                           _stream()), "egnn_segment_rows_fwd")
+                                           _ptr(argmax), _stream()), "egnn_segment_rows_fwd")
 
 
-def egnn_segment_rows_bwd(dmi, ld_dmi, col_off, d, z, act, rowptr, n_nodes, agg, target):
+def egnn_segment_rows_bwd(dmi, ld_dmi, col_off, d, z, act, rowptr, n_nodes, agg, target, argmax=None):
     check(lib().eqnn_egnn_segment_rows_bwd(_off(dmi, col_off), ld_dmi, d, _ptr(z), int(act), _ptr(rowptr), n_nodes, agg,
-                                           _ptr(target), _stream()), "egnn_segment_rows_bwd")
+                                           _ptr(target), _ptr(argmax), _stream()), "egnn_segment_rows_bwd")
 
 
 def egnn_xv_bwd(nodes, F, sx, sv, dnext, ld_dnext, mix, n, din, dsx, dsv):

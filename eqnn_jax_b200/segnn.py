@@ -27,7 +27,8 @@ one has no gate and is only aggregated over the receivers, so the aggregation is
 run on the node rows (``_edgeL_fwd``).  With attributes l <= 1 the forward GEMM of the remaining layers contracts the
 attribute axis in its epilogue (``eqnn_segnn_tplg_fwd``).
 Graph globals (concatenated to the pooled scalars, LayerNorm, :282-286) are supported.
-Scalar activations: gelu and silu (models/segnn.py:27,56).  Not built: max aggregation -> NotImplementedError, never a fallback.
+Scalar activations: gelu and silu (models/segnn.py:27,56).  Aggregations: sum, mean, max (jraph.segment_max; the node-level evaluation of the last edge layer needs a linear
+aggregation and is skipped for max).
 """
 from __future__ import annotations
 
@@ -233,8 +234,9 @@ class _Plan:
         self._val: List[np.ndarray] = []
         if cfg.scalar_activation not in ("gelu", "silu"):
             raise NotImplementedError("scalar_activation must be 'gelu' or 'silu' on the B200 path (models/segnn.py:27,56)")
-        if cfg.message_passing_agg not in ("sum", "mean") or (cfg.task == "graph" and cfg.readout_agg not in ("sum", "mean")):
-            raise NotImplementedError("aggregations must be 'sum' or 'mean' on the B200 path")
+        if cfg.message_passing_agg not in ("sum", "mean", "max") or (cfg.task == "graph" and
+                                                                      cfg.readout_agg not in ("sum", "mean", "max")):
+            raise ValueError("aggregations must be 'sum', 'mean' or 'max' (models/segnn.py:155,218,265-270)")
         hidden = Irreps(cfg.hidden_irreps) if cfg.hidden_irreps is not None else \
             balanced_irreps(cfg.l_max_hidden, cfg.d_hidden, True)
         self.hidden, self.irreps_in = hidden, irreps_in
@@ -608,7 +610,9 @@ class SEGNN:
     # -- last edge layer of a step, evaluated at the nodes -----------------------------------------------------
     def _edgeL_ok(self, plan, st) -> bool:
         t = st["edge"][-1]
-        return plan.lowering == "dense" and len(st["edge"]) >= 2 and t.has_y and not t.activation and t.Dy <= 16
+        # (moving the aggregation in front of the layer needs a linear aggregation: sum or mean, not max)
+        return plan.lowering == "dense" and len(st["edge"]) >= 2 and t.has_y and not t.activation and t.Dy <= 16 and \
+            self.message_passing_agg != "max"
 
     def _edgeL_fwd(self, plan, t: _TPLG, theta, wexp, m, y, rowptr, Nt, agg, Cc, ldc, col_off):
         """The last edge layer has no gate and is only aggregated over the receivers, so the aggregation moves in front
@@ -652,7 +656,7 @@ class SEGNN:
         tab = plan.device_tables(dev)
         wexp = torch.empty((plan._n_exp,), **f32)
         ops.weights_expand(theta, tab["exp_idx"], tab["exp_scale"], wexp)
-        agg = 1 if self.message_passing_agg == "mean" else 0
+        agg = ops.AGG[self.message_passing_agg]
         n_add = add.shape[1]
         saved = {"wexp": wexp, "steps": []}
         h, saved["embed"] = self._tplg_fwd(plan, plan.embed, theta, wexp, nodes, nodes.shape[1], y_node, Nt)
@@ -679,11 +683,12 @@ class SEGNN:
             if fastL:
                 es.append(self._edgeL_fwd(plan, st["edge"][-1], theta, wexp, m, y_edge, rowptr, Nt, agg, Cc, Dh + Dm, Dh))
             else:
-                ops.egnn_segment_rows_fwd(m, Dm, 0, rowptr, Nt, agg, Cc, Dh + Dm, col_off=Dh)
+                amax = torch.empty((Nt, Dm), dtype=torch.int32, device=dev) if agg == 2 else None   # segment_max winners
+                ops.egnn_segment_rows_fwd(m, Dm, 0, rowptr, Nt, agg, Cc, Dh + Dm, col_off=Dh, argmax=amax)
             new, ns = self._tplg_fwd(plan, st["node"], theta, wexp, Cc, Dh + Dm, y_node, Nt)
             if self.residual:
                 ops.axpy(1.0, h, new)
-            saved["steps"].append(dict(edge=es, node=ns, Dh=Dh, Dm=Dm))
+            saved["steps"].append(dict(edge=es, node=ns, Dh=Dh, Dm=Dm, amax=None if fastL else amax))
             h = new
         if self.task == "node":
             x, ld, ds = h, h.shape[1], []
@@ -698,7 +703,12 @@ class SEGNN:
         pre2 = torch.empty((Nt, d), **f32)
         _mm(Nt, d, d, 1.0, pre, 0, d, theta, plan.dense[0], d, pre2, 0, d, epi=1, aux=theta, aux_off=plan.dense[1])
         pooled = torch.empty((B, d), **f32)
-        ops.pool_fwd(pre2, B, N, d, 1 if self.readout_agg == "mean" else 0, pooled)
+        ro_arg = None
+        if self.readout_agg == "max":                        # jnp.max over the nodes: value + arg-max (gradient routing)
+            ro_arg = torch.empty((B, d), dtype=torch.int32, device=dev)
+            ops.pool_max_fwd(pre2, B, N, d, pooled, ro_arg)
+        else:
+            ops.pool_fwd(pre2, B, N, d, 1 if self.readout_agg == "mean" else 0, pooled)
         a, ln_stats = pooled, None
         if plan.ln is not None:
             a = torch.empty((B, d + plan.n_globals), **f32)
@@ -711,7 +721,7 @@ class SEGNN:
             _mm(B, w, fan, 1.0, a, 0, fan, theta, ko, w, zl, 0, w, pro=pro, pro_scale=1.0, epi=1, aux=theta, aux_off=bo)
             zs.append(zl)
             a, pro = zl, 1
-        saved.update(pre_out=pre, pooled=pooled, ro_z=zs, ro_in=ro_in, ln_stats=ln_stats)
+        saved.update(pre_out=pre, pooled=pooled, ro_z=zs, ro_in=ro_in, ln_stats=ln_stats, ro_arg=ro_arg)
         return zs[-1], saved
 
     def _backward(self, theta, gtheta, saved, gout, plan, nodes, B, N, E, csr, y_node, y_edge, add, glob=None):
@@ -723,7 +733,7 @@ class SEGNN:
         wexp = saved["wexp"]
         gwexp = torch.zeros((plan._n_exp,), **f32)
         gtheta.zero_()
-        agg = 1 if self.message_passing_agg == "mean" else 0
+        agg = ops.AGG[self.message_passing_agg]
         n_add = add.shape[1]
         if self.task == "node":
             dx = gout.reshape(Nt, -1).contiguous()
@@ -752,7 +762,10 @@ class SEGNN:
                                   plan.ln[0], plan.ln[1])
                 dz = d_pool
             dpre2 = torch.empty((Nt, d), **f32)
-            ops.pool_bwd(dz, B, N, d, 1 if self.readout_agg == "mean" else 0, dpre2)
+            if self.readout_agg == "max":
+                ops.pool_max_bwd(dz, saved["ro_arg"], B, N, d, dpre2)
+            else:
+                ops.pool_bwd(dz, B, N, d, 1 if self.readout_agg == "mean" else 0, dpre2)
             _mm(d, d, Nt, 1.0, saved["pre_out"], 0, d, dpre2, 0, d, gtheta, plan.dense[0], d, ta=True)     # Dense_0
             ops.colsum_tall(dpre2, Nt, d, gtheta, y_off=plan.dense[1])
             dpre = torch.empty((Nt, d), **f32)
@@ -773,7 +786,7 @@ class SEGNN:
                                      rowptr, Nt, Et, agg)
             else:
                 dm = torch.zeros((Et, Dm), **f32)
-                ops.egnn_segment_rows_bwd(dC, Dh + Dm, Dh, Dm, None, 0, rowptr, Nt, agg, dm)
+                ops.egnn_segment_rows_bwd(dC, Dh + Dm, Dh, Dm, None, 0, rowptr, Nt, agg, dm, argmax=sv["amax"])
             for t, s_ in zip(reversed(st["edge"][lo:hi]), reversed(sv["edge"][lo:hi])):
                 dm = self._tplg_bwd(plan, t, theta, gtheta, wexp, gwexp, s_, dm, Et)
             if fast0:

@@ -324,16 +324,19 @@ int eqnn_axpy(int64_t n, float a, const float* x, float* y, eqnn_stream_t stream
  *                     pos_out[r] = wrap( pos[r] + agg_{e->r} clip(r_ij * [tanh](t_e), +-100) )
  * backward, two phases around the edge-MLP backward:  dfeats == NULL -> dt[p];  dfeats given -> dre (per-edge
  * dL/dr_ij stored at the ORIGINAL edge id) and dpos_in (identity + receiver end); eqnn_egnn_sender_acc adds the
- * sender end from the sender-sorted CSR.  cell / cell_inv: HOST pointers to 9 floats or NULL.                  */
+ * sender end from the sender-sorted CSR.  cell / cell_inv: HOST pointers to 9 floats or NULL.
+ * agg: 0 sum, 1 mean, 2 max (jraph.segment_max, egnn.py:282-284): argmax [n_nodes, 3] = CSR position of the first edge
+ * attaining each component's maximum, written by the forward pass and read by the backward pass (NULL otherwise). */
 int eqnn_egnn_geom_fwd(const float* pos, int ld_pos, int n_nodes, const int32_t* rowptr, const int32_t* src,
                        const float* cell, const float* cell_inv, int n_rb, double r_max, float* rij4, float* feats,
                        eqnn_stream_t stream);
 int eqnn_egnn_coord_fwd(const float* rij4, const float* t, int use_tanh, int agg, const int32_t* rowptr, int n_nodes,
                         const float* pos, int ld_pos, const float* cell, const float* cell_inv, float* pos_out,
-                        int ld_out, eqnn_stream_t stream);
+                        int ld_out, int32_t* argmax, eqnn_stream_t stream);
 int eqnn_egnn_coord_bwd(const float* rij4, const float* t, int use_tanh, int agg, const int32_t* rowptr,
                         const int32_t* perm, int n_nodes, const float* dpos_out, int n_rb, double r_max,
-                        const float* dfeats, float* dt, float* dre, float* dpos_in, eqnn_stream_t stream);
+                        const float* dfeats, float* dt, float* dre, float* dpos_in, const int32_t* argmax,
+                        eqnn_stream_t stream);
 int eqnn_egnn_sender_acc(const float* dre, const int32_t* rowptr_s, const int32_t* perm_s, int n_nodes, float* dpos,
                          eqnn_stream_t stream);
 /* node layout (x, v, h) with scalar attributes (egnn.py:47-60, 198-229):
@@ -355,11 +358,12 @@ int eqnn_egnn_node_assemble(const float* nodes, int F, int h_off, const float* p
                             eqnn_stream_t stream);
 /* aggregated messages (jraph segment_sum / segment_mean of m_ij; read by the (x, h) and (x, v) node functions,
  * egnn.py:161-166,180-196): out[r, :d] = agg_{e->r} act(rows[e, :]) with act 1 = gelu (messages kept as
- * pre-activations) and its backward target[e, :] += dmi[r(e), :] / deg * act'(z[e, :]) */
+ * pre-activations) and its backward target[e, :] += dmi[r(e), :] / deg * act'(z[e, :]);  agg = 2 (segment_max):
+ * argmax [n_nodes, d] = CSR position of the winning edge, which alone receives the gradient (NULL for sum / mean) */
 int eqnn_egnn_segment_rows_fwd(const float* rows, int d, int act, const int32_t* rowptr, int n_nodes, int agg, float* out,
-                               int ld_out, eqnn_stream_t stream);
+                               int ld_out, int32_t* argmax, eqnn_stream_t stream);
 int eqnn_egnn_segment_rows_bwd(const float* dmi, int ld_dmi, int d, const float* z, int act, const int32_t* rowptr,
-                               int n_nodes, int agg, float* target, eqnn_stream_t stream);
+                               int n_nodes, int agg, float* target, const int32_t* argmax, eqnn_stream_t stream);
 /* backward of the node update: dsx = g.x, dsv = g.v, din = (sx g + (mix - g), sv g + dnext_v, dnext_h); mix = g +
  * geometry gradient (NULL: none); din may be NULL (first step); dnext has row stride ld_dnext >= F (the (x, v) layout
  * returns 6 + d_hidden columns) */

@@ -86,6 +86,11 @@ def _run(kw, B=2, N=256, k=8, pbc=False, seed=0, F=3, n_glob=0):
           message_passing_steps=3, message_passing_agg="mean", task="graph", n_outputs=2, tanh_out=True), False),  # notebook cell 14
     (dict(positions_only=True, soft_edges=True, n_layers=3, d_hidden=32, n_radial_basis=8, r_max=0.6,
           message_passing_steps=2, message_passing_agg="mean", task="node", tanh_out=True), True),    # CUDA-core path
+    # jraph.segment_max of the translations + jnp.max read-out (egnn.py:282-284,326): arg-max routed backward
+    (dict(positions_only=True, soft_edges=False, n_layers=3, d_hidden=128, n_radial_basis=32, r_max=0.6,
+          message_passing_steps=2, message_passing_agg="max", readout_agg="max", task="graph", n_outputs=2), True),
+    (dict(positions_only=True, soft_edges=True, n_layers=3, d_hidden=32, n_radial_basis=8, r_max=0.6,
+          message_passing_steps=2, message_passing_agg="max", task="node", tanh_out=True), False),
 ])
 def test_egnn_forward_and_gradients(kw, pbc):
     got, want, params, p, x, p32 = _run(kw, pbc=pbc)
@@ -142,6 +147,13 @@ XVH = dict(positions_only=False, n_layers=3, r_max=0.6, message_passing_steps=2,
           message_passing_agg="mean", task="node", message_passing_steps=3), False, 6, 0),
     (dict(XVH, soft_edges=True, tanh_out=True, decouple_pos_vel_updates=False, d_hidden=64, n_radial_basis=16,
           message_passing_agg="sum", task="graph"), True, 6, 0),
+    # segment_max of the messages m_i (read by the (x, h), (x, v) and (x, v, h) node functions) and of the translations
+    (dict(XVH, positions_only=True, soft_edges=True, d_hidden=32, n_radial_basis=8, message_passing_agg="max",
+          readout_agg="max", task="graph"), False, 6, 0),
+    (dict(XVH, soft_edges=False, decouple_pos_vel_updates=True, d_hidden=32, n_radial_basis=8,
+          message_passing_agg="max", task="node", message_passing_steps=3), False, 6, 0),
+    (dict(XVH, soft_edges=True, tanh_out=True, decouple_pos_vel_updates=True, d_hidden=32, n_radial_basis=16,
+          message_passing_agg="max", task="graph"), True, 7, 0),
 ])
 def test_egnn_xvh_forward_and_gradients(kw, pbc, F, n_glob):
     """(x, v, h) node layout, egnn.py:47-60 and :198-229; (x, h) layout, :42-46 and :152-166."""
@@ -230,5 +242,5 @@ def test_egnn_unsupported_variants_fail_loudly():
     from eqnn_jax_b200.egnn import EGNN
     with pytest.raises(NotImplementedError):
         EGNN(positions_only=True, activation="relu").init(0, type("G", (), {"nodes": torch.zeros(1, 4, 3).cuda()})())
-    with pytest.raises(NotImplementedError):
-        EGNN(positions_only=True, message_passing_agg="max").init(0, type("G", (), {"nodes": torch.zeros(1, 4, 3).cuda()})())
+    with pytest.raises(ValueError):
+        EGNN(positions_only=True, message_passing_agg="median").init(0, type("G", (), {"nodes": torch.zeros(1, 4, 3).cuda()})())

@@ -97,6 +97,11 @@ def _run(kw, irreps, x, k, lmax_attr, n_rb, pbc, vel, n_glob=0, lowering="dense"
     # scalar_activation = "silu": the class default of TensorProductLinearGate (segnn.py:27), e3nn-normalised
     (dict(d_hidden=32, n_layers=2, message_passing_steps=2, message_passing_agg="mean", task="node", output_irreps="1x1o",
           l_max_hidden=1, residual=True, scalar_activation="silu"), "1o", 3, 1, 4, True, False, 0),
+    # jraph.segment_max over the receivers + jnp.max read-out (segnn.py:155,218,265-270): arg-max routed backward
+    (dict(d_hidden=32, n_layers=2, message_passing_steps=2, message_passing_agg="max", readout_agg="max", task="graph",
+          output_irreps="1x0e", l_max_hidden=1, n_outputs=2, residual=True), "1o", 3, 1, 4, True, False, 0),
+    (dict(d_hidden=32, n_layers=3, message_passing_steps=2, message_passing_agg="max", task="node", output_irreps="1x1o",
+          l_max_hidden=2, residual=True), "1o", 3, 2, 0, False, False, 0),
     # graph globals (TPCF vector) -> concat + LayerNorm before the read-out MLP (segnn.py:282-286)
     (dict(d_hidden=32, n_layers=2, message_passing_steps=1, message_passing_agg="mean", task="graph", output_irreps="1x0e",
           n_outputs=2), "1o", 3, 1, 0, False, False, 12),
@@ -232,6 +237,6 @@ def test_segnn_unsupported_fails_loudly():
     from eqnn_jax_b200.segnn import SEGNN, _Plan
     from eqnn_jax_b200.irreps import Irreps
     with pytest.raises(NotImplementedError):
-        _Plan(SEGNN(scalar_activation="silu"), Irreps("1o"), 1, 1)
-    with pytest.raises(NotImplementedError):
-        _Plan(SEGNN(message_passing_agg="max"), Irreps("1o"), 1, 1)
+        _Plan(SEGNN(scalar_activation="relu"), Irreps("1o"), 1, 1)
+    with pytest.raises(ValueError):
+        _Plan(SEGNN(message_passing_agg="median"), Irreps("1o"), 1, 1)
