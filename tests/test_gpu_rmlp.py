@@ -80,9 +80,12 @@ def test_radial_mlp_fwd_rejects_unsupported_shapes():
     (4200, 16, 1, 16, 1e-3),
     (300, 64, 3, 8, 1.0),                  # below the tensor-core weight-gradient threshold (CUDA-core GEMMs)
 ])
-@pytest.mark.parametrize("variant", ["stash", "recompute"])
-def test_radial_mlp_bwd_matches_oracle(E, n_rb, n_hidden, n_out, gmag, variant):
+@pytest.mark.parametrize("variant", ["stash", "recompute", "stash-chain"])
+def test_radial_mlp_bwd_matches_oracle(E, n_rb, n_hidden, n_out, gmag, variant, monkeypatch):
     from eqnn_jax_b200 import ops
+    if variant == "stash-chain":             # the chain kernel + separate weight gradients instead of rmlp_lbwd_kernel
+        monkeypatch.setenv("EQNN_RMLP_NO_LBWD", "1")
+        variant = "stash"
     from eqnn_jax_b200.nequip import normalize_constant
     r_cut = 0.6
     act_scale = 1.0 / normalize_constant("gelu")
