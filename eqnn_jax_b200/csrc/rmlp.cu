@@ -770,7 +770,7 @@ __global__ void __launch_bounds__(RM_THREADS, 1) rmlp_dgrad_kernel(const RmlpDgr
 //            the blocked layout, so a pass is ONE 4 KB bulk copy into the warp's landing buffer):
 //            g_l -> (hi, lo) -> G tile in shared memory AND in place into OP                           [publish g]
 //            (l = H: g_H = OP * gelu'(z_H) with OP = dw @ W_out^T from a small prologue MMA issued one tile ahead)
-//   MMA (lane 0 of warp 16):  PRE = OP @ W_l^T (24 MMAs);  ACC += A^T G (24 MMAs)
+//   MMA (lane 0 of warp 0, issued where the a path waits for PRE):  PRE = OP @ W_l^T (24 MMAs);  ACC += A^T G (24 MMAs)
 //   a path (warps 0..15, 32 columns of one row per thread, z_{l-1} prefetched into registers one tile ahead):
 //            gelu(z_{l-1}) -> (hi, lo) -> A tile in shared memory, gelu' kept in registers              [publish a]
 //            g_{l-1} = PRE * gelu'(z_{l-1}) -> global (blocked layout) while the weight-gradient MMAs run.
@@ -807,7 +807,7 @@ constexpr uint32_t RM_LBWD_SEG = 8;          // tiles per tensor-memory accumula
 constexpr uint32_t RM_OPT = 2 * 128 * 128; // one (hi or lo) half of a 128-edge x 128-column fp16 operand tile: 2 slabs of 16 KB
 
 constexpr int LB_GW0 = RM_CW;                    // warps 16..19: the g path (one warp per tensor-memory lane quarter);
-                                                 // lane 0 of warp 16 also issues the MMAs (20 warps keep 96 registers/thread)
+                                                 // lane 0 of warp 0 also issues the MMAs (20 warps keep 96 registers/thread)
 constexpr int LB_THREADS = (LB_GW0 + 4) * 32;    // 640
 
 __device__ __forceinline__ void sts_chunks(uint8_t* tile, uint32_t row, uint32_t chunk0, const uint32_t* hiw, const uint32_t* low) {
@@ -872,6 +872,59 @@ __global__ void __launch_bounds__(LB_THREADS, 1) rmlp_lbwd_kernel(const RmlpLbwd
   const float gS = (mexp == 0) ? 1.f : __uint_as_float((uint32_t)sexp << 23);
   const float gSinv = (mexp == 0) ? 1.f : __uint_as_float((uint32_t)(254 - sexp) << 23);
 
+// ---- MMA issue: lane 0 of a-path warp 0, in the gap where the a path waits for the data-gradient product ----
+const bool issuer = tid == 0;
+  const uint32_t idesc_d = make_idesc_f16(128, 128, 0, 1);      // A in tensor memory, B = weight image read MN-major
+  const uint32_t idesc_w = make_idesc_f16(128, 128, 1, 1);      // both operands edge-major shared memory (MN-major)
+  const uint32_t b_hi = base + o_w, b_lo = b_hi + w_half;
+  const uint32_t a_hi_s = base + o_a, a_lo_s = a_hi_s + RM_OPT, g_hi_s = base + o_g, g_lo_s = g_hi_s + RM_OPT;
+  // pre-activation gradient of the last hidden layer, (dw @ W_out^T), for tile `it` -> OP
+  auto prologue = [&](uint32_t it) {
+    mbar_wait(opnd0_full, it & 1u);
+    tc_fence_after();
+    const uint32_t wo_hi = base + o_wo, wo_lo = wo_hi + wo_half;
+    const uint64_t dbh = make_desc(wo_hi, 16u * 128u, 1024), dbl = make_desc(wo_lo, 16u * 128u, 1024);
+    const uint32_t a_hi = T_X, a_lo = a_hi + 16;
+    mma_f16_ts(T_OP, a_lo, dbh, idesc_d, 0u);
+    mma_f16_ts(T_OP, a_hi, dbl, idesc_d, 1u);
+    mma_f16_ts(T_OP, a_hi, dbh, idesc_d, 1u);
+    mma_commit(pro_full);
+  };
+  auto issue_dgrad = [&](uint32_t it) {
+    mbar_wait(opnd_g, it & 1u);
+    tc_fence_after();
+    for (int pass = 0; pass < 2; ++pass)       // cross terms first, hi*hi last (see rmlp_fwd_kernel)
+      for (int s = 0; s < 8; ++s) {
+        const uint32_t a_hi = T_OP + (uint32_t)(32 * (s >> 1) + 8 * (s & 1)), a_lo = a_hi + 16;
+        const uint64_t dbh = make_desc(b_hi + s * 2048u, 128u * 128u, 1024), dbl = make_desc(b_lo + s * 2048u, 128u * 128u, 1024);
+        if (pass == 0) {
+          mma_f16_ts(T_PRE, a_lo, dbh, idesc_d, s ? 1u : 0u);
+          mma_f16_ts(T_PRE, a_hi, dbl, idesc_d, 1u);
+        } else {
+          mma_f16_ts(T_PRE, a_hi, dbh, idesc_d, 1u);
+        }
+      }
+    mma_commit(pre_full);
+  };
+  // weight gradient of a tile: D[k][n] += sum_e a[e][k] g[e][n]; k-step s = edges 16 s .. 16 s + 15
+  auto issue_wgrad = [&](uint32_t it) {
+    mbar_wait(opnd_g, it & 1u);
+    mbar_wait(opnd_a, it & 1u);
+    tc_fence_after();
+    const uint32_t fresh = (it % RM_LBWD_SEG) == 0 ? 0u : 1u;
+    for (int pass = 0; pass < 2; ++pass)
+      for (int s = 0; s < 8; ++s) {
+        const uint64_t dah = make_desc(a_hi_s + s * 2048u, 16384u, 1024), dal = make_desc(a_lo_s + s * 2048u, 16384u, 1024);
+        const uint64_t dgh = make_desc(g_hi_s + s * 2048u, 16384u, 1024), dgl = make_desc(g_lo_s + s * 2048u, 16384u, 1024);
+        if (pass == 0) {
+          mma_f16_ss(T_ACC, dal, dgh, idesc_w, s ? 1u : fresh);
+          mma_f16_ss(T_ACC, dah, dgl, idesc_w, 1u);
+        } else {
+          mma_f16_ss(T_ACC, dah, dgh, idesc_w, 1u);
+        }
+      }
+    mma_commit(wg_done);
+  };
   if (warp < RM_CW) {
     // ============ a path (16 warps): gelu(z_{l-1}) -> A tile, then g_{l-1} = PRE * gelu'(z_{l-1}) -> global ============
     const int q = warp & 3, cg = warp >> 2;
@@ -907,6 +960,10 @@ __global__ void __launch_bounds__(LB_THREADS, 1) rmlp_lbwd_kernel(const RmlpLbwd
     };
     float z[32];
     if (my_tiles > 0) load_z(0, z);
+    if (p.first && my_tiles > 0) {
+      if (issuer) prologue(0);
+      __syncwarp();
+    }
     for (uint32_t it = 0; it < my_tiles; ++it) {
       const uint32_t par = it & 1u;
       const int64_t e = (blockIdx.x + (int64_t)it * gridDim.x) * RM_TILE + row;
@@ -934,6 +991,13 @@ __global__ void __launch_bounds__(LB_THREADS, 1) rmlp_lbwd_kernel(const RmlpLbwd
       mbar_arrive(opnd_a);
       // next tile's z_{l-1}: in flight across the wait below
       if (it + 1 < my_tiles) load_z(it + 1, z);
+      if (issuer) {
+        issue_dgrad(it);
+        // the next tile's prologue: OP is free (the data-gradient MMAs above precede it in the tensor pipe)
+        if (p.first && it + 1 < my_tiles) prologue(it + 1);
+      }
+      if (issuer_w) issue_wgrad(it);
+      __syncwarp();
       mbar_wait(pre_full, par);
       tc_fence_after();
 #pragma unroll
@@ -962,57 +1026,6 @@ __global__ void __launch_bounds__(LB_THREADS, 1) rmlp_lbwd_kernel(const RmlpLbwd
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
     const int row = q * 32 + lane;
     const float* gsrc = p.first ? p.z_l : p.g_in;
-    const bool issuer = (warp == LB_GW0) && (lane == 0);
-    // ---- MMA issue (one thread) ----
-    const uint32_t idesc_d = make_idesc_f16(128, 128, 0, 1);      // A in tensor memory, B = weight image read MN-major
-    const uint32_t idesc_w = make_idesc_f16(128, 128, 1, 1);      // both operands edge-major shared memory (MN-major)
-    const uint32_t b_hi = base + o_w, b_lo = b_hi + w_half;
-    const uint32_t a_hi_s = base + o_a, a_lo_s = a_hi_s + RM_OPT, g_hi_s = base + o_g, g_lo_s = g_hi_s + RM_OPT;
-    // pre-activation gradient of the last hidden layer, (dw @ W_out^T), for tile `it` -> OP
-    auto prologue = [&](uint32_t it) {
-      mbar_wait(opnd0_full, it & 1u);
-      tc_fence_after();
-      const uint32_t wo_hi = base + o_wo, wo_lo = wo_hi + wo_half;
-      const uint64_t dbh = make_desc(wo_hi, 16u * 128u, 1024), dbl = make_desc(wo_lo, 16u * 128u, 1024);
-      const uint32_t a_hi = T_X, a_lo = a_hi + 16;
-      mma_f16_ts(T_OP, a_lo, dbh, idesc_d, 0u);
-      mma_f16_ts(T_OP, a_hi, dbl, idesc_d, 1u);
-      mma_f16_ts(T_OP, a_hi, dbh, idesc_d, 1u);
-      mma_commit(pro_full);
-    };
-    auto issue_tile = [&](uint32_t it) {
-      const uint32_t par = it & 1u;
-      mbar_wait(opnd_g, par);
-      tc_fence_after();
-      for (int pass = 0; pass < 2; ++pass)       // cross terms first, hi*hi last (see rmlp_fwd_kernel)
-        for (int s = 0; s < 8; ++s) {
-          const uint32_t a_hi = T_OP + (uint32_t)(32 * (s >> 1) + 8 * (s & 1)), a_lo = a_hi + 16;
-          const uint64_t dbh = make_desc(b_hi + s * 2048u, 128u * 128u, 1024), dbl = make_desc(b_lo + s * 2048u, 128u * 128u, 1024);
-          if (pass == 0) {
-            mma_f16_ts(T_PRE, a_lo, dbh, idesc_d, s ? 1u : 0u);
-            mma_f16_ts(T_PRE, a_hi, dbl, idesc_d, 1u);
-          } else {
-            mma_f16_ts(T_PRE, a_hi, dbh, idesc_d, 1u);
-          }
-        }
-      mma_commit(pre_full);
-      // weight gradient of this tile: D[k][n] += sum_e a[e][k] g[e][n]; k-step s = edges 16 s .. 16 s + 15
-      mbar_wait(opnd_a, par);
-      tc_fence_after();
-      const uint32_t fresh = (it % RM_LBWD_SEG) == 0 ? 0u : 1u;
-      for (int pass = 0; pass < 2; ++pass)
-        for (int s = 0; s < 8; ++s) {
-          const uint64_t dah = make_desc(a_hi_s + s * 2048u, 16384u, 1024), dal = make_desc(a_lo_s + s * 2048u, 16384u, 1024);
-          const uint64_t dgh = make_desc(g_hi_s + s * 2048u, 16384u, 1024), dgl = make_desc(g_lo_s + s * 2048u, 16384u, 1024);
-          if (pass == 0) {
-            mma_f16_ss(T_ACC, dal, dgh, idesc_w, s ? 1u : fresh);
-            mma_f16_ss(T_ACC, dah, dgl, idesc_w, 1u);
-          } else {
-            mma_f16_ss(T_ACC, dah, dgh, idesc_w, 1u);
-          }
-        }
-      mma_commit(wg_done);
-    };
     auto publish_dw = [&](const float* d) {  // a dw row (scaled here) -> A operand of the prologue MMA (T_X)
       uint32_t hiw[8], low[8];
 #pragma unroll
@@ -1048,8 +1061,6 @@ __global__ void __launch_bounds__(LB_THREADS, 1) rmlp_lbwd_kernel(const RmlpLbwd
     if (p.first && my_tiles > 0) {
       load_dw(0);
       publish_dw(dnext);
-      if (issuer) prologue(0);
-      __syncwarp();
     }
     for (uint32_t it = 0; it < my_tiles; ++it) {
       const uint32_t par = it & 1u;
@@ -1060,9 +1071,10 @@ __global__ void __launch_bounds__(LB_THREADS, 1) rmlp_lbwd_kernel(const RmlpLbwd
         mbar_wait(pro_full, par);
         tc_fence_after();
       }
-      // the G tile and OP are free once the previous tile's MMAs have completed
+      // the G tile and OP are free once the previous tile's MMAs (weight gradient, data gradient) have completed
       if (it > 0) {
         mbar_wait(wg_done, (it - 1) & 1u);
+        mbar_wait(pre_full, (it - 1) & 1u);
         tc_fence_after();
       }
 #pragma unroll 1
@@ -1103,14 +1115,7 @@ __global__ void __launch_bounds__(LB_THREADS, 1) rmlp_lbwd_kernel(const RmlpLbwd
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(opnd_g);
-      if (issuer) issue_tile(it);
-      __syncwarp();
-      if (p.first && it + 1 < my_tiles) {
-        publish_dw(dnext);                     // T_X is free: the prologue of this tile completed before its passes
-        // the next tile's prologue: OP is free (the data-gradient MMAs above precede it in the tensor pipe)
-        if (issuer) prologue(it + 1);
-        __syncwarp();
-      }
+      if (p.first && it + 1 < my_tiles) publish_dw(dnext);   // T_X is free: this tile's prologue completed before its passes
     }
   }
   tc_fence_before();
