@@ -637,12 +637,17 @@ def main():
         #   weight gradients: basis 256 + z (or activations) 512 H + g 512 H + dw 4 n
         mlp_bytes = (4 + 4 * n_live + (512 * H if stash else 0)) + (4 * n_live + (1024 * H if stash else 256 + 1024 * H)) + \
                     (256 + 1024 * H + 4 * n_live)
+        if stash and H >= 2 and not os.environ.get("EQNN_RMLP_NO_LBWD"):
+            # fused per-layer backward (rmlp_lbwd_kernel): max|dw| pass 4 n | layer H: z_H + z_{H-1} + dw in, g_{H-1} out |
+            # layers H-1..2: z_{l-1} + g_l in, g_{l-1} out | first layer's weight gradient: basis + g_1 | output layer's: z_H + dw
+            mlp_bytes = (4 + 4 * n_live + 512 * H) + 4 * n_live + (1024 + 4 * n_live + 512) + (H - 2) * 1536 + \
+                        (256 + 512) + (512 + 4 * n_live)
     else:
         mlp_bytes = (256 + 512) + 2 * 1024 + (512 + 4 * n_live) + (4 * n_live + 1024) + 2 * 1536 + \
                     (512 + 4 * n_live) + 2 * 1024 + (256 + 512)
     mlp_gbs = E_step * steps_mp * mlp_bytes / (mlp_ms_step * 1e-3) / 1e9 if mlp_ms_step > 0 else float("nan")
     tr = ncu_traffic()
-    tr_mlp = traffic_of(tr, args.workload, ("rmlp_", "tc_wgrad", "tc_rowgemm", "absmax", "wgrad_reduce"), E_step)
+    tr_mlp = traffic_of(tr, args.workload, ("rmlp_", "tc_wgrad", "tc_rowgemm", "absmax", "wgrad_reduce", "lbwd_reduce"), E_step)
     tr_tp = traffic_of(tr, args.workload, ("tpconv_fwd", "tpconv_bwd", "sender_reduce", "segment_gather"), E_step)
     _, ms_tf = per_launch("tpconv_fwd")
     _, ms_tb = per_launch("tpconv_bwd")
@@ -673,8 +678,8 @@ def main():
         # layer's data gradient backward); the kernels issue three fp16 MMAs per product (hi*hi + lo*hi + hi*lo, fp32-class
         # accuracy), so their own ceiling is peak / 3.  The HBM view of the same launches is kept beside it.
         "roofline": {"kernel": ("fused radial MLP: rmlp_fwd_kernel (Bessel + all layers, activations in tensor memory) + "
-                                "rmlp_dgrad_kernel (data-gradient chain) + tc_wgrad_kernel x4; tcgen05 kind::f16 / kind::tf32, "
-                                "3 MMAs per product") if fused else
+                                "rmlp_lbwd_kernel per hidden layer (data gradient + weight gradient in one pass) + tc_wgrad_kernel x2; "
+                                "tcgen05 kind::f16 / kind::tf32, 3 MMAs per product") if fused else
                                "radial MLP GEMMs fwd+dgrad+wgrad (tc_rowgemm_kernel / tc_wgrad_kernel, tcgen05 kind::tf32 x3)",
                      "bound": "tensor", "achieved": mlp_tf, "peak": pk["tf_sust"], "unit": "TFLOP/s",
                      "frac": mlp_tf / pk["tf_sust"],
@@ -687,8 +692,8 @@ def main():
                      "ms_fwd_per_launch": ms_mf, "ms_bwd_per_call": ms_mb,
                      "note": "flops per SURVEY.md 8(d).2 with the live output columns; time = CUDA events around "
                              "every eqnn_radial_mlp_fwd / _bwd call of the instrumented pass"},
-        "roofline_mlp_hbm": {"kernel": "same launches, HBM view (bytes the design moves: forward d + w_t + z stash; "
-                                       "backward z + dw in, g out; weight gradients basis + z + g in)",
+        "roofline_mlp_hbm": {"kernel": "same launches, HBM view (bytes the design moves: forward d + w_t + z stash; backward per hidden "
+                                       "layer z_{l-1} + g_l in, g_{l-1} out; first / output layer weight gradients basis + g_1, z_H + dw)",
                              "bound": "hbm", "achieved": mlp_gbs, "peak": pk["hbm"], "unit": "GB/s",
                              "frac": mlp_gbs / pk["hbm"], "bytes_per_edge_step": mlp_bytes,
                              "traffic": tr_mlp["per_launch"] if tr_mlp else None,

@@ -872,8 +872,9 @@ __global__ void __launch_bounds__(LB_THREADS, 1) rmlp_lbwd_kernel(const RmlpLbwd
   const float gS = (mexp == 0) ? 1.f : __uint_as_float((uint32_t)sexp << 23);
   const float gSinv = (mexp == 0) ? 1.f : __uint_as_float((uint32_t)(254 - sexp) << 23);
 
-// ---- MMA issue: lane 0 of a-path warp 0, in the gap where the a path waits for the data-gradient product ----
-const bool issuer = tid == 0;
+  // ---- MMA issue: lanes 0 of a-path warps 0 and 1, in the gap where the a path waits for the data-gradient product ----
+  const bool issuer = tid == 0;          // prologue + data-gradient MMAs
+  const bool issuer_w = tid == 32;       // weight-gradient MMAs (independent of the former: other operands, other accumulator)
   const uint32_t idesc_d = make_idesc_f16(128, 128, 0, 1);      // A in tensor memory, B = weight image read MN-major
   const uint32_t idesc_w = make_idesc_f16(128, 128, 1, 1);      // both operands edge-major shared memory (MN-major)
   const uint32_t b_hi = base + o_w, b_lo = b_hi + w_half;
@@ -1213,6 +1214,8 @@ int eqnn_tc_wgrad_try(int64_t M, int64_t N, int64_t K, float alpha, const float*
                       const float* B, int64_t sbk, int64_t sbn, float* C, int64_t scm, int64_t scn, int accumulate,
                       int pro, float pro_scale, int epi, void* ws, size_t ws_bytes, cudaStream_t st,
                       float* colsum_out, int blocked);
+int eqnn_tc_wgrad_bessel_try(int n_rb, int64_t E, float alpha, const float* geom, double r_cut, const float* G, int g_blocked,
+                             float* C, int64_t scm, void* ws, size_t ws_bytes, cudaStream_t st);
 
 // workspace: [absmax 256 B | bessel basis E*n_rb | n_hidden x gelu(z_l) E*128 | n_hidden x g_l E*128 | GEMM workspace]
 static size_t rm_bwd_gemm_ws(int64_t n_edges) {
@@ -1240,7 +1243,16 @@ static int rm_bwd_from_stash(const float* dist, int64_t dist_stride, int64_t n_e
   EQNN_CHECK_ARG(dist && weights && ldw && dw_t && grad_weights && n_edges >= 0 && dist_stride >= 1, "radial_mlp_bwd: bad argument");
   EQNN_CHECK_ARG(eqnn_radial_mlp_supported(n_rb, d_hidden, n_hidden, n_out), "radial_mlp_bwd: unsupported shape");
   EQNN_CHECK_ARG(r_cut > 0.0 && ld_dwt >= n_edges, "radial_mlp_bwd: bad r_cut / ld_dwt");
-  EQNN_CHECK_ARG(radial != nullptr, "radial_mlp_bwd: the stash variant needs the Bessel basis (eqnn_edge_geom's radial)");
+  // The first layer's weight gradient can generate the Bessel basis itself (tc_wgrad_kernel PRO = 2) when the edge lengths
+  // sit in (r_hat, d) records (dist = geom + 3, stride 4): taken when no radial array is given, or on request
+  // (EQNN_RMLP_BESSEL_WGRAD=1).  Measured at 3.2 M edges: 0.68 ms against 0.52 ms reading eqnn_edge_geom's radial -- the
+  // transform warps pay 64 sines per edge four times per training step, more than the 256 B / edge they save -- so
+  // callers that hold the basis anyway (NequIP: one array per batch) pass it.
+  const bool bessel_ok = dist_stride == 4 && (n_rb == 32 || n_rb == 64) && n_edges >= 4096 &&
+                         (reinterpret_cast<uintptr_t>(dist - 3) & 15) == 0 && !getenv("EQNN_RMLP_NO_TC_WGRAD");
+  const bool bessel_wgrad = bessel_ok && (radial == nullptr || getenv("EQNN_RMLP_BESSEL_WGRAD"));
+  EQNN_CHECK_ARG(radial != nullptr || bessel_wgrad || n_edges == 0,
+                 "radial_mlp_bwd: this shape needs the Bessel basis (eqnn_edge_geom's radial) for the first layer's weight gradient");
   EQNN_CHECK_ARG((reinterpret_cast<uintptr_t>(z_stash) & 15) == 0, "radial_mlp_bwd: z_stash must be 16-byte aligned");
   if (ws_bytes < eqnn_radial_mlp_bwd_workspace_bytes(n_edges, n_rb, n_hidden) || !ws) return eqnn_fail(EQNN_ERR_WORKSPACE, "radial_mlp_bwd: workspace too small");
   cudaStream_t st = as_stream(stream);
@@ -1286,7 +1298,7 @@ static int rm_bwd_from_stash(const float* dist, int64_t dist_stride, int64_t n_e
   for (int l = 0; l < F; ++l) {
     const int K = rm_K(f, l);
     bool ok = n_edges >= 4096 && (K == 32 || K == 64 || K == 128) && !getenv("EQNN_RMLP_NO_TC_WGRAD");
-    if (l == 0) ok = ok && (reinterpret_cast<uintptr_t>(radial) & 15) == 0;
+    if (l == 0) ok = ok && (bessel_wgrad || (radial && (reinterpret_cast<uintptr_t>(radial) & 15) == 0));
     if (l == F - 1) ok = ok && ld_dwt % 4 == 0 && (reinterpret_cast<uintptr_t>(dw_t) & 15) == 0;
     tc_ok[l] = ok;
     if (l < F - 1) p.blk[l] = ok ? 1 : 0;     // layout of grad[l + 1]
@@ -1340,6 +1352,12 @@ static int rm_bwd_from_stash(const float* dist, int64_t dist_stride, int64_t n_e
     const int pro = l == 0 ? 0 : 1;
     const float* G = l < F - 1 ? p.grad[l + 1] : dw_t;
     const int64_t N = l < F - 1 ? 128 : n_out, sbk = l < F - 1 ? 128 : 1, sbn = l < F - 1 ? 1 : ld_dwt;
+    if (tc_ok[l] && l == 0 && bessel_wgrad && F >= 2) {
+      const int r = eqnn_tc_wgrad_bessel_try(n_rb, n_edges, f.alpha[0], dist - 3, r_cut, G, 1, grad_weights[0], ldw[0], gws, gws_bytes, st);
+      if (r < 0) return -r;
+      if (r == 1) continue;
+      if (!radial) return eqnn_fail(EQNN_ERR_ARG, "radial_mlp_bwd: first-layer weight gradient not covered and no radial given");
+    }
     if (tc_ok[l]) {
       const int blocked = (l > 0 ? 1 : 0) | (l < F - 1 ? 2 : 0);
       const int r = eqnn_tc_wgrad_try(K, N, n_edges, f.alpha[l], X, 1, K, G, sbk, sbn, grad_weights[l], ldw[l], 1, 0, pro,

@@ -23,6 +23,7 @@
 //   MN-major SWIZZLE_128B_BASE32B operands; registers are re-balanced between roles with setmaxnreg.
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "rmlp_common.cuh"
 #include <type_traits>
 
 namespace {
@@ -396,6 +397,11 @@ struct WgradP {
   // block laid out [16-byte column group c4][row][4 floats] instead of [row][column], so that the producer's lanes
   // (one row each) write 512 contiguous bytes per store; the buffer is padded to whole chunks.
   int x_blocked, g_blocked;
+  // PRO == 2: X is not read at all -- it is the Bessel basis of the edge length (e3nn.bessel, the first radial layer's
+  // input, models/nequip.py:57), generated by the transform warps from the 32 edge records (r_hat, d) of a chunk:
+  // 512 bytes per chunk cross HBM instead of 32 * MI * 4.  geom = [E][4] floats, d in component 3.
+  const float* geom;
+  float r_cut, pref;
 };
 
 // wgrad thread layout (warpgroup-aligned so that registers can be re-balanced with setmaxnreg):
@@ -418,12 +424,12 @@ struct WgradCfg {
   static constexpr uint32_t XRAW = 32 * MI * 4;               // one 32-edge chunk of X, as it lies in HBM
   static constexpr uint32_t GRAW = (GMODE == 0) ? 32 * N * 4 : 16 * 128;
   static constexpr uint32_t RAW_STAGE = XRAW + GRAW;
-  static constexpr int RAW_NS = (NSTAGE * STAGE_W + 4 * RAW_STAGE + 2048 <= SMEM_LIMIT) ? 4 : 3;   // raw ring depth
-  static constexpr uint32_t SMEM = NSTAGE * STAGE_W + RAW_NS * RAW_STAGE + 1024 + 256;
+  static constexpr int RAW_NS = (NSTAGE * STAGE_W + 4 * RAW_STAGE + 2560 <= SMEM_LIMIT) ? 4 : 3;   // raw ring depth
+  static constexpr uint32_t SMEM = NSTAGE * STAGE_W + RAW_NS * RAW_STAGE + 1024 + 256 + 512 /* bessel frequencies */;
   static_assert(SMEM <= SMEM_LIMIT, "shared memory budget exceeded");
 };
 
-template <int MI, int N, int GMODE, int PRO>   // GMODE 0: G row-major [E][N]; 1: G column-major [n][E], N = 16
+template <int MI, int N, int GMODE, int PRO>   // GMODE 0: G row-major [E][N]; 1: G column-major [n][E], N = 16; PRO 0 none, 1 gelu, 2 bessel(d)
 __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const WgradP p) {
   using Cfg = WgradCfg<MI, N, GMODE>;
   constexpr uint32_t A_HALF_W = Cfg::A_HALF_W, B_HALF_W = Cfg::B_HALF_W, STAGE_W = Cfg::STAGE_W;
@@ -448,6 +454,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const WgradP p)
   const uint32_t tmem_slot = bars + 8u * (2 * NSTAGE + 4 + 2 * RAW_NS);
   uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float* wfreq = reinterpret_cast<float*>(gen_base + (bars - base) + 256);   // PRO == 2: j * pi / r_cut, j = 1..MI
+  if (PRO == 2 && tid < MI) wfreq[tid] = __fdiv_rn(__fmul_rn((float)(tid + 1), 3.14159265358979323846f), p.r_cut);
 
   const int64_t n_chunks = (p.E + 31) / 32;
   const int64_t per = (n_chunks + gridDim.x - 1) / gridDim.x;
@@ -494,11 +502,13 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const WgradP p)
       const uint32_t rows = (uint32_t)((p.E - e0 < 32) ? (p.E - e0) : 32);
       const uint32_t xdst = raw0 + rs * Cfg::RAW_STAGE, gdst = xdst + Cfg::XRAW;
       const uint32_t gbytes = (GMODE == 0) ? rows * N * 4u : (uint32_t)p.n_valid * rows * 4u;
-      const uint32_t xbytes = p.x_blocked ? 32u * MI * 4u : rows * MI * 4u;
+      const uint32_t xbytes = PRO == 2 ? rows * 16u : (p.x_blocked ? 32u * MI * 4u : rows * MI * 4u);
       const uint32_t gbytes_c = (GMODE == 0 && p.g_blocked) ? 32u * N * 4u : gbytes;
       if (lane == 0) mbar_expect_tx(r_full(rs), xbytes + gbytes_c);
       __syncwarp();
-      if (x_dense) {
+      if (PRO == 2) {
+        if (lane == 0) bulk_g2s(xdst, p.geom + e0 * 4, xbytes, r_full(rs));     // 32 edge records (r_hat, d)
+      } else if (x_dense) {
         if (lane == 0) bulk_g2s(xdst, p.X + e0 * p.ldx, xbytes, r_full(rs));
       } else if ((uint32_t)lane < rows) {
         bulk_g2s(xdst + lane * MI * 4u, p.X + (e0 + lane) * p.ldx, MI * 4u, r_full(rs));
@@ -544,8 +554,25 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const WgradP p)
       for (int i = 0; i < XI; ++i) {
         const int f = pt + i * WG_PT;
         if (f < 8 * MI) {
-          const int row = p.x_blocked ? (f & 31) : f / (MI / 4), c4 = p.x_blocked ? (f >> 5) : f % (MI / 4);
-          const float4 v = (row < rows) ? *reinterpret_cast<const float4*>(xraw + (uint32_t)f * 16u) : zero4;
+          const int row = (p.x_blocked || PRO == 2) ? (f & 31) : f / (MI / 4), c4 = (p.x_blocked || PRO == 2) ? (f >> 5) : f % (MI / 4);
+          float4 v = zero4;
+          if (PRO == 2) {
+            // basis functions 4 c4 + 1 .. 4 c4 + 4 of edge `row`: the forward kernel's arithmetic (rmlp::bessel16)
+            if (row < rows) {
+              const float d = *reinterpret_cast<const float*>(xraw + (uint32_t)row * 16u + 12u);
+              const float inv_d = (d == 0.f) ? 0.f : __fdiv_rn(1.0f, d);
+              const float w0 = wfreq[4 * c4], w1 = wfreq[4 * c4 + 1], w2 = wfreq[4 * c4 + 2], w3 = wfreq[4 * c4 + 3];
+              const f32x2 d2 = pk2(d, d), sc = pk2(p.pref * inv_d, p.pref * inv_d);
+              float s0, s1, s2, s3;
+              rmlp::sin_reduced2(mul2(pk2(w0, w1), d2), s0, s1);
+              rmlp::sin_reduced2(mul2(pk2(w2, w3), d2), s2, s3);
+              upk2(mul2(pk2(s0, s1), sc), v.x, v.y);
+              upk2(mul2(pk2(s2, s3), sc), v.z, v.w);
+              if (d == 0.f) v = make_float4(__fmul_rn(p.pref, w0), __fmul_rn(p.pref, w1), __fmul_rn(p.pref, w2), __fmul_rn(p.pref, w3));
+            }
+          } else if (row < rows) {
+            v = *reinterpret_cast<const float4*>(xraw + (uint32_t)f * 16u);
+          }
           // MN-major slab [m-block of 32][32 k-rows]: 4-row atoms, 32-byte-chunk swizzle
           const uint32_t off = (c4 >> 3) * 4096 + sw128_base32(row, c4 & 7);
           put(sa + off, sa + A_HALF_W + off, v, std::integral_constant<bool, PRO == 1>{});
@@ -747,6 +774,7 @@ int eqnn_tc_wgrad_try(int64_t M, int64_t N, int64_t K, float alpha, const float*
   WgradP p;
   p.X = A; p.ldx = sak; p.G = B; p.E = K; p.pro_scale = pro_scale; p.n_valid = (int)N;
   p.x_blocked = blocked & 1; p.g_blocked = (blocked >> 1) & 1;
+  p.geom = nullptr; p.r_cut = 1.f; p.pref = 0.f;
   if (p.x_blocked && sak != M) return 0;
   p.partial = reinterpret_cast<float*>(ws);
   p.colsum = nullptr;
@@ -775,6 +803,31 @@ int eqnn_tc_wgrad_try(int64_t M, int64_t N, int64_t K, float alpha, const float*
     colsum_parts_reduce_kernel<<<1, 128, 0, st>>>(p.colsum, grid, (int)N, colsum_out);
     eqnn_count_launches(1);
   }
+  return 1;
+}
+
+// First radial layer's weight gradient with the Bessel basis generated in the kernel (PRO = 2):
+//   dW[n_rb x 128] = alpha * bessel(d)^T @ G,  d = geom[e][3], G = [E][128] row-major or blocked.
+// Same return convention as eqnn_tc_wgrad_try.
+int eqnn_tc_wgrad_bessel_try(int n_rb, int64_t E, float alpha, const float* geom, double r_cut, const float* G, int g_blocked,
+                             float* C, int64_t scm, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (!(n_rb == 32 || n_rb == 64) || E < 4096 || !geom || (reinterpret_cast<uintptr_t>(geom) & 15) ||
+      (reinterpret_cast<uintptr_t>(G) & 15))
+    return 0;
+  const int sms = sm_count();
+  const int64_t n_chunks = (E + 31) / 32;
+  const int grid = (int)(n_chunks < sms ? n_chunks : sms);
+  if (!ws || ws_bytes < (size_t)grid * n_rb * 128 * 4) return 0;
+  WgradP p;
+  p.X = nullptr; p.ldx = n_rb; p.G = G; p.ldg = 128; p.E = E; p.pro_scale = 1.f; p.n_valid = 128;
+  p.x_blocked = 0; p.g_blocked = g_blocked ? 1 : 0;
+  p.partial = reinterpret_cast<float*>(ws);
+  p.colsum = nullptr;
+  p.geom = geom; p.r_cut = (float)r_cut; p.pref = (float)sqrt(2.0 / r_cut);
+  const int rc = n_rb == 64 ? launch_wgrad<64, 128, 0, 2>(p, grid, st) : launch_wgrad<32, 128, 0, 2>(p, grid, st);
+  if (rc) return -rc;
+  wgrad_reduce_kernel<<<(n_rb * 128 + 31) / 32, 256, 0, st>>>(p.partial, grid, n_rb, 128, 128, alpha, C, scm);
+  eqnn_count_launches(1);
   return 1;
 }
 

@@ -410,9 +410,12 @@ int eqnn_radial_mlp_supported(int n_rb, int d_hidden, int n_hidden, int n_out);
  * (overwritten).  A chain kernel recomputes the activations from d in tensor memory and runs the data-gradient
  * chain dL/dz_l = (dL/dz_{l+1} @ W_{l+1}^T) * gelu'(z_l) without leaving the SM; it emits gelu(z_l) and dL/dz_l once
  * (the operands of the weight-gradient GEMMs, which run on the tcgen05 weight-gradient kernel with the edge axis as K).
- * Two variants: with z_stash (written by eqnn_radial_mlp_fwd) and radial (the Bessel basis [n_edges][n_rb] of
- * eqnn_edge_geom) only the data-gradient chain runs, two tiles in flight like the forward kernel; with z_stash = NULL
- * nothing is kept from the forward pass and the activations are recomputed from d (radial is then unused).
+ * Two variants.  With z_stash (written by eqnn_radial_mlp_fwd): every hidden layer l >= 2 runs as ONE kernel that forms
+ * dL/dz_{l-1} and dL/dW_l in a single pass over the edges (both weight-gradient operands edge-major in shared memory; the
+ * layer fed by dw forms dL/dz_H itself), the first and the output layer's weight gradients run on the tcgen05
+ * weight-gradient kernel; radial = the Bessel basis [n_edges][n_rb] of eqnn_edge_geom (may be NULL for n_rb 32 / 64,
+ * n_edges >= 4096, dist_stride 4: the basis is then regenerated inside the weight-gradient kernel, slower).
+ * With z_stash = NULL nothing is kept from the forward pass: the activations are recomputed from d (radial unused).
  * ws: eqnn_radial_mlp_bwd_workspace_bytes. */
 size_t eqnn_radial_mlp_bwd_workspace_bytes(int64_t n_edges, int n_rb, int n_hidden);
 int eqnn_radial_mlp_bwd(const float* dist, int64_t dist_stride, int64_t n_edges, int n_rb, double r_cut, int n_hidden,

@@ -80,9 +80,12 @@ def test_radial_mlp_fwd_rejects_unsupported_shapes():
     (4200, 16, 1, 16, 1e-3),
     (300, 64, 3, 8, 1.0),                  # below the tensor-core weight-gradient threshold (CUDA-core GEMMs)
 ])
-@pytest.mark.parametrize("variant", ["stash", "recompute", "stash-chain"])
+@pytest.mark.parametrize("variant", ["stash", "recompute", "stash-chain", "stash-bessel"])
 def test_radial_mlp_bwd_matches_oracle(E, n_rb, n_hidden, n_out, gmag, variant, monkeypatch):
     from eqnn_jax_b200 import ops
+    no_radial = variant == "stash-bessel"    # first layer's weight gradient generates the Bessel basis in the kernel
+    if no_radial:
+        variant = "stash"
     if variant == "stash-chain":             # the chain kernel + separate weight gradients instead of rmlp_lbwd_kernel
         monkeypatch.setenv("EQNN_RMLP_NO_LBWD", "1")
         variant = "stash"
@@ -105,6 +108,10 @@ def test_radial_mlp_bwd_matches_oracle(E, n_rb, n_hidden, n_out, gmag, variant, 
         w_t = torch.empty((n_out, E), dtype=torch.float32, device="cuda")
         ops.radial_mlp_fwd(geom, n_rb, r_cut, wl, n_out, act_scale, w_t, z_stash=stash)
         radial = ops.edge_features(torch.cat([geom[:, 3:4], torch.zeros_like(geom[:, :2])], dim=1).contiguous(), n_rb, r_cut)
+        if no_radial:
+            if E < 4096 or n_rb not in (32, 64):
+                pytest.skip("the in-kernel basis covers n_rb 32 / 64 from 4096 edges on")
+            radial = None
     ops.radial_mlp_bwd(geom, n_rb, r_cut, wl, n_out, act_scale, torch.tensor(dw, device="cuda"),
                        [(g, 0, g.shape[1]) for g in gW], z_stash=stash, radial=radial)
     torch.cuda.synchronize()
