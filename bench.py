@@ -640,7 +640,8 @@ def main():
         if stash and H >= 2 and not os.environ.get("EQNN_RMLP_NO_LBWD"):
             # fused per-layer backward (rmlp_lbwd_kernel): max|dw| pass 4 n | layer H: z_H + z_{H-1} + dw in, g_{H-1} out |
             # layers H-1..2: z_{l-1} + g_l in, g_{l-1} out | first layer's weight gradient: basis + g_1 | output layer's: z_H + dw
-            mlp_bytes = (4 + 4 * n_live + 512 * H) + 4 * n_live + (1024 + 4 * n_live + 512) + (H - 2) * 1536 + \
+            # (the forward stash holds z_1 .. z_{H-1}, gelu(z_H), gelu'(z_H): H + 1 matrices)
+            mlp_bytes = (4 + 4 * n_live + 512 * (H + 1)) + 4 * n_live + (1024 + 4 * n_live + 512) + (H - 2) * 1536 + \
                         (256 + 512) + (512 + 4 * n_live)
     else:
         mlp_bytes = (256 + 512) + 2 * 1024 + (512 + 4 * n_live) + (4 * n_live + 1024) + 2 * 1536 + \

@@ -47,7 +47,8 @@ struct RmlpP {
   int act_kind;             // 0 gelu (tanh form), 1 silu
   float* w_t;               // [n_out][ld_wt] column-major radial weights
   int64_t ld_wt;
-  // optional stash of the pre-activations for eqnn_radial_mlp_bwd: z_stash[l - 1] = z_l, l = 1..n_hidden, each
+  // optional stash for eqnn_radial_mlp_bwd: z_stash[l - 1] = z_l for l = 1..n_hidden-1; the last hidden layer stores
+  // z_stash[n_hidden - 1] = gelu(z_H) and z_stash[n_hidden] = gelu'(z_H) instead of z_H (see the kernel); each
   // [ceil(E/32)] chunks of [32 column groups][32 rows][4 floats] (the blocked chunk layout of tc_mlp.cu's WgradP)
   float* z_stash[RM_MAXL];
 };
@@ -186,12 +187,35 @@ __global__ void __launch_bounds__(RM_THREADS, 1) rmlp_fwd_kernel(const RmlpP p) 
           float v[32];
           tmem_ld32(t, v);
           tmem_ld_wait();
-          if (p.z_stash[l - 1]) {
-            const int64_t e = (blockIdx.x + (2 * pr + x) * (int64_t)gridDim.x) * RM_TILE + row;
-            if (e < p.E) emit_cols<32>(p.z_stash[l - 1], 1, e, 128, 32 * cg, v);
-          }
           uint32_t hiw[16], low[16];
-          act_split32(v, ac, hiw, low);
+          if (p.z_stash[l - 1] && l == F - 1) {
+            // last hidden layer: the backward pass needs gelu(z_H) (output layer's weight gradient) and gelu'(z_H)
+            // (g_H = (dw @ W_out^T) * gelu'(z_H)) and never z_H itself: both come out of the sigmoid evaluated here anyway
+            const int64_t e = (blockIdx.x + (2 * pr + x) * (int64_t)gridDim.x) * RM_TILE + row;
+            float* da = p.z_stash[l - 1] + (e >> 5) * (int64_t)(32 * 128) + (int64_t)(8 * cg) * 128 + (e & 31) * 4;
+            float* dg = p.z_stash[l] + (e >> 5) * (int64_t)(32 * 128) + (int64_t)(8 * cg) * 128 + (e & 31) * 4;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              f32x2 a01, g01, a23, g23;
+              act_both2(pk2(v[4 * i], v[4 * i + 1]), ac, a01, g01);
+              act_both2(pk2(v[4 * i + 2], v[4 * i + 3]), ac, a23, g23);
+              float4 a4, g4;
+              upk2(a01, a4.x, a4.y); upk2(a23, a4.z, a4.w);
+              upk2(g01, g4.x, g4.y); upk2(g23, g4.z, g4.w);
+              if (e < p.E) {
+                *reinterpret_cast<float4*>(da + i * 128) = a4;
+                *reinterpret_cast<float4*>(dg + i * 128) = g4;
+              }
+              split_h2(a4.x, a4.y, hiw[2 * i], low[2 * i]);
+              split_h2(a4.z, a4.w, hiw[2 * i + 1], low[2 * i + 1]);
+            }
+          } else {
+            if (p.z_stash[l - 1]) {
+              const int64_t e = (blockIdx.x + (2 * pr + x) * (int64_t)gridDim.x) * RM_TILE + row;
+              if (e < p.E) emit_cols<32>(p.z_stash[l - 1], 1, e, 128, 32 * cg, v);
+            }
+            act_split32(v, ac, hiw, low);
+          }
           tmem_st16(t, hiw);
           tmem_st16(t + 16, low);
           tmem_st_wait();
@@ -572,7 +596,7 @@ struct RmlpDgradP {
   const float* dw;
   int64_t ld_dw;
   const uint32_t* absmax;
-  const float* z[RM_MAXL];   // z[l] = z_l, l = 1..H, blocked chunk layout
+  const float* z[RM_MAXL];   // z[l] = z_l, l = 1..H-1, and z[H] = gelu'(z_H); blocked chunk layout
   float* grad[RM_MAXL];      // grad[l] = dL/dz_l, l = 1..H
   int blk[RM_MAXL];          // blk[l - 1]: layout of grad[l] (1 blocked, 0 row-major)
 };
@@ -692,7 +716,8 @@ __global__ void __launch_bounds__(RM_THREADS, 1) rmlp_dgrad_kernel(const RmlpDgr
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const f32x2 g2 = mul2(pk2(pre[2 * j], pre[2 * j + 1]), act_grad2(pk2(z[2 * j], z[2 * j + 1]), ac));
+            const f32x2 zz = pk2(z[2 * j], z[2 * j + 1]);
+            const f32x2 g2 = mul2(pk2(pre[2 * j], pre[2 * j + 1]), l == H ? zz : act_grad2(zz, ac));   // z[H] holds gelu'(z_H)
             upk2(g2, pre[2 * j], pre[2 * j + 1]);
           }
           if (l >= 2) {
@@ -795,7 +820,7 @@ struct RmlpLbwdP {
   const float* dw;           // [n_out][ld_dw] column-major
   int64_t ld_dw;
   const uint32_t* absmax;
-  const float* z_l;          // first = 1: z_H (blocked chunk layout)
+  const float* z_l;          // first = 1: gelu'(z_H) (blocked chunk layout; the forward kernel's stash)
   const float* g_in;         // first = 0: g_l (blocked, unscaled)
   const float* z_prev;       // z_{l-1} (blocked)
   float* g_out;              // g_{l-1} (blocked, unscaled)
@@ -1098,7 +1123,7 @@ __global__ void __launch_bounds__(LB_THREADS, 1) rmlp_lbwd_kernel(const RmlpLbwd
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const f32x2 g2 = mul2(pk2(pg[2 * j], pg[2 * j + 1]), act_grad2(pk2(v[2 * j], v[2 * j + 1]), ac));
+            const f32x2 g2 = mul2(pk2(pg[2 * j], pg[2 * j + 1]), pk2(v[2 * j], v[2 * j + 1]));     // v = gelu'(z_H)
             float g0, g1;
             upk2(g2, g0, g1);
             split_h2(g0, g1, hiw[j], low[j]);
@@ -1169,7 +1194,7 @@ extern "C" int eqnn_radial_mlp_supported(int n_rb, int d_hidden, int n_hidden, i
 // one layer of the z stash: whole 128-edge tiles of 128 floats
 static size_t rm_stash_layer_floats(int64_t n_edges) { return align_up((size_t)n_edges, 128) * 128; }
 extern "C" size_t eqnn_radial_mlp_stash_bytes(int64_t n_edges, int n_hidden) {
-  return (size_t)n_hidden * rm_stash_layer_floats(n_edges) * sizeof(float);
+  return (size_t)(n_hidden + 1) * rm_stash_layer_floats(n_edges) * sizeof(float);   // z_1 .. z_{H-1}, gelu(z_H), gelu'(z_H)
 }
 
 extern "C" int eqnn_radial_mlp_fwd(const float* dist, int64_t dist_stride, int64_t n_edges, int n_rb, double r_cut,
@@ -1198,7 +1223,7 @@ extern "C" int eqnn_radial_mlp_fwd(const float* dist, int64_t dist_stride, int64
   p.act_scale = act_scale; p.act_kind = activation; p.w_t = w_t; p.ld_wt = ld_wt;
   EQNN_CHECK_ARG(!z_stash || (reinterpret_cast<uintptr_t>(z_stash) & 15) == 0, "radial_mlp_fwd: z_stash must be 16-byte aligned");
   for (int l = 0; l < RM_MAXL; ++l)
-    p.z_stash[l] = (z_stash && l < n_hidden) ? z_stash + (size_t)l * rm_stash_layer_floats(n_edges) : nullptr;
+    p.z_stash[l] = (z_stash && l <= n_hidden) ? z_stash + (size_t)l * rm_stash_layer_floats(n_edges) : nullptr;
   const uint32_t smem = rm_smem_bytes(p);
   static DeviceOnce once;
   EQNN_CUDA(configure_smem(once, rmlp_fwd_kernel, 227 * 1024));
@@ -1278,8 +1303,10 @@ static int rm_bwd_from_stash(const float* dist, int64_t dist_stride, int64_t n_e
   w += 256;
   p.absmax = absmax;
   const size_t ep = align_up((size_t)n_edges, 128);
+  // stash slots (eqnn_radial_mlp_fwd): z_1 .. z_{H-1}, gelu(z_H), gelu'(z_H)
+  const float* a_last = z_stash + (size_t)(n_hidden - 1) * rm_stash_layer_floats(n_edges);
   for (int l = 1; l <= n_hidden; ++l) {
-    p.z[l] = z_stash + (size_t)(l - 1) * rm_stash_layer_floats(n_edges);
+    p.z[l] = z_stash + (size_t)(l < n_hidden ? l - 1 : n_hidden) * rm_stash_layer_floats(n_edges);   // z[H] = gelu'(z_H)
     p.grad[l] = reinterpret_cast<float*>(w);
     w += ep * 512;
   }
@@ -1348,8 +1375,10 @@ static int rm_bwd_from_stash(const float* dist, int64_t dist_stride, int64_t n_e
   for (int l = 0; l < F; ++l) {
     if (fused && l >= 1 && l < F - 1) continue;           // done by the fused layer kernels
     const int K = rm_K(f, l);
-    const float* X = l == 0 ? radial : p.z[l];
-    const int pro = l == 0 ? 0 : 1;
+    // X = input of layer l: the Bessel basis, z_l (gelu applied by the kernel's prologue), or the stashed gelu(z_H)
+    const float* X = l == 0 ? radial : (l == F - 1 ? a_last : p.z[l]);
+    const int pro = (l == 0 || l == F - 1) ? 0 : 1;
+    const float al = l == F - 1 ? f.alpha[l] * act_scale : f.alpha[l];
     const float* G = l < F - 1 ? p.grad[l + 1] : dw_t;
     const int64_t N = l < F - 1 ? 128 : n_out, sbk = l < F - 1 ? 128 : 1, sbn = l < F - 1 ? 1 : ld_dwt;
     if (tc_ok[l] && l == 0 && bessel_wgrad && F >= 2) {
@@ -1360,7 +1389,7 @@ static int rm_bwd_from_stash(const float* dist, int64_t dist_stride, int64_t n_e
     }
     if (tc_ok[l]) {
       const int blocked = (l > 0 ? 1 : 0) | (l < F - 1 ? 2 : 0);
-      const int r = eqnn_tc_wgrad_try(K, N, n_edges, f.alpha[l], X, 1, K, G, sbk, sbn, grad_weights[l], ldw[l], 1, 0, pro,
+      const int r = eqnn_tc_wgrad_try(K, N, n_edges, al, X, 1, K, G, sbk, sbn, grad_weights[l], ldw[l], 1, 0, pro,
                                       act_scale, 0, gws, gws_bytes, st, nullptr, blocked);
       if (r < 0) return -r;
       if (r != 1) return eqnn_fail(EQNN_ERR_ARG, "radial_mlp_bwd: weight-gradient shape not covered by the tensor-core kernel");
@@ -1374,7 +1403,7 @@ static int rm_bwd_from_stash(const float* dist, int64_t dist_stride, int64_t n_e
       EQNN_CHECK_LAUNCH();
       Xr = tmp;
     }
-    const int rc = eqnn_gemm_f32(K, N, n_edges, f.alpha[l], Xr, 1, K, G, sbk, sbn, grad_weights[l], ldw[l], 1, 0, pro,
+    const int rc = eqnn_gemm_f32(K, N, n_edges, al, Xr, 1, K, G, sbk, sbn, grad_weights[l], ldw[l], 1, 0, pro,
                                  act_scale, 0, nullptr, 0, 1.f, gws, gws_bytes, stream);
     if (rc) return rc;
   }

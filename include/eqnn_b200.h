@@ -425,8 +425,9 @@ int eqnn_radial_mlp_bwd(const float* dist, int64_t dist_stride, int64_t n_edges,
 int eqnn_radial_mlp_fwd(const float* dist, int64_t dist_stride, int64_t n_edges, int n_rb, double r_cut, int n_hidden,
                         int d_hidden, const float* const* weights, const int64_t* ldw, int n_out, int activation,
                         float act_scale, float* w_t, int64_t ld_wt, float* z_stash, eqnn_stream_t stream);
-/* z_stash (optional, eqnn_radial_mlp_stash_bytes, 16-byte aligned): the forward kernel also writes the n_hidden
- * pre-activation matrices z_l for the backward pass (opaque blocked layout; 512 bytes per edge and hidden layer). */
+/* z_stash (optional, eqnn_radial_mlp_stash_bytes, 16-byte aligned): the forward kernel also writes what the backward
+ * pass reads instead of recomputing -- the pre-activations z_1 .. z_{H-1} and, for the last hidden layer, gelu(z_H) and
+ * gelu'(z_H) (opaque blocked layout; 512 bytes per edge and matrix, n_hidden + 1 matrices). */
 size_t eqnn_radial_mlp_stash_bytes(int64_t n_edges, int n_hidden);
 
 /* ---- parameter plumbing ----------------------------------------------------------------
