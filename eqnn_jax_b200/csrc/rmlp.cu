@@ -799,7 +799,7 @@ __global__ void __launch_bounds__(RM_THREADS, 1) rmlp_dgrad_kernel(const RmlpDgr
 //   a path (warps 0..15, 32 columns of one row per thread, z_{l-1} prefetched into registers one tile ahead):
 //            gelu(z_{l-1}) -> (hi, lo) -> A tile in shared memory, gelu' kept in registers              [publish a]
 //            g_{l-1} = PRE * gelu'(z_{l-1}) -> global (blocked layout) while the weight-gradient MMAs run.
-// The tensor core's fp32 accumulation truncates, so ACC spans RM_LBWD_SEG tiles (192 updates) and is then added to
+// The tensor core's fp32 accumulation truncates, so ACC spans RM_LBWD_SEG tiles (384 updates) and is then added to
 // the CTA's partial sums in global memory with IEEE adds.
 // Measured (in-kernel cycle counters, 3.2 M edges): a global->SM round trip costs 2-3 k cycles under load for loads and
 // bulk copies alike, and L2 prefetches (bulk or per line) only add to the queues -- so every stream is prefetched by the
@@ -828,7 +828,7 @@ struct RmlpLbwdP {
   int act_kind;
 };
 
-constexpr uint32_t RM_LBWD_SEG = 8;          // tiles per tensor-memory accumulation of the weight gradient (192 updates)
+constexpr uint32_t RM_LBWD_SEG = 16;         // tiles per tensor-memory accumulation of the weight gradient (384 updates)
 constexpr uint32_t RM_OPT = 2 * 128 * 128; // one (hi or lo) half of a 128-edge x 128-column fp16 operand tile: 2 slabs of 16 KB
 
 constexpr int LB_GW0 = RM_CW;                    // warps 16..19: the g path (one warp per tensor-memory lane quarter);

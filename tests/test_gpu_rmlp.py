@@ -3,6 +3,7 @@
 Tolerance: 1e-5 of the largest magnitude of each output tensor (north_star: fp32 features within 1e-5 relative);
 gradients additionally get 4x the deviation of a plain fp32 evaluation from fp64."""
 import math
+import os
 
 import numpy as np
 import pytest
@@ -75,6 +76,7 @@ def test_radial_mlp_fwd_rejects_unsupported_shapes():
 
 @pytest.mark.parametrize("E,n_rb,n_hidden,n_out,gmag", [
     (128 * 148 * 2 + 77, 64, 3, 8, 1e-6), # cfg-2 model; tiny gradients exercise the power-of-two scale
+    (128 * 148 * 20 + 5, 64, 3, 8, 1.0),  # 20 tiles per CTA: the fused layer kernel's weight-gradient accumulator rolls over
     (4096, 64, 3, 8, 1.0),
     (5000, 32, 2, 11, 3e3),
     (4200, 16, 1, 16, 1e-3),
@@ -94,8 +96,12 @@ def test_radial_mlp_bwd_matches_oracle(E, n_rb, n_hidden, n_out, gmag, variant, 
     act_scale = 1.0 / normalize_constant("gelu")
     d, Ws = _inputs(E, n_rb, n_hidden, n_out, seed=7 + E % 1000)
     rng = np.random.default_rng(E)
-    # heavy-tailed cotangent: a few edges carry most of the gradient, most are orders of magnitude smaller
-    dw = (rng.normal(size=(n_out, E)) * np.exp(rng.normal(size=(1, E)) * 2.0) * gmag).astype(np.float32)
+    # heavy-tailed cotangent: a few edges carry most of the gradient, most are orders of magnitude smaller.  The kernels
+    # bring the gradients into fp16 range with ONE power-of-two scale per launch, so rows more than ~2^13 below the largest
+    # row keep only the hi half of the (hi, lo) split: the log-normal tail is exp(2 sigma) (max / median ~ 4e3 at 4e4
+    # edges) for the small cases and exp(sigma) (~1e2) for the 379 k-edge one, which is there for the accumulator rollover.
+    tail = 1.0 if E > 100000 else 2.0
+    dw = (rng.normal(size=(n_out, E)) * np.exp(rng.normal(size=(1, E)) * tail) * gmag).astype(np.float32)
     geom = torch.zeros((E, 4), dtype=torch.float32, device="cuda")
     geom[:, 3] = torch.tensor(d, device="cuda")
     Wd = [torch.tensor(W, device="cuda") for W in Ws]
@@ -139,5 +145,7 @@ def test_radial_mlp_bwd_matches_oracle(E, n_rb, n_hidden, n_out, gmag, variant, 
         scale = float(want.abs().max())
         err = float((got - want).abs().max())
         floor = float((w32.grad.double() - want).abs().max())
+        if os.environ.get("EQNN_TEST_VERBOSE"):
+            print(f"layer {l}: err/scale {err / scale:.2e}  floor/scale {floor / scale:.2e}")
         assert err <= TOL * scale + 4 * floor, \
             f"radial MLP weight gradient, layer {l}: err {err / scale:.2e}, fp32 floor {floor / scale:.2e} (of max|want|)"
