@@ -471,6 +471,9 @@ def main():
     # the rank-local part of the step (graph build, forward, loss, backward) is captured once in a CUDA graph and
     # replayed -- what jax.jit gives the reference; --no-cuda-graph launches the ~130 kernels one by one
     ap.add_argument("--no-cuda-graph", action="store_true")
+    # default: the radial MLP is evaluated once per UNIQUE edge length (the two directions of a reciprocated edge have
+    # bit-identical lengths: NequIP.share_radial, csrc/pairs.cu); --no-share-radial evaluates it once per edge
+    ap.add_argument("--no-share-radial", action="store_true")
     args = ap.parse_args()
     if args.workload in FAMILIES:
         return run_family(args)
@@ -516,7 +519,7 @@ def main():
     resident = [(h.to(dev), y.to(dev)) for h, y in host]
     apply_pbc = GU.get_apply_pbc(std=(STD[:3] / BOX).astype(np.float32))   # train_cosmology.py:401
 
-    model = NequIP(**MODEL_KW)
+    model = NequIP(**MODEL_KW, share_radial=not args.no_share_radial)
     g0 = GU.GraphsTuple(nodes=wrap_nodes(resident[0][0]), edges=None, receivers=None, senders=None, globals=None,
                         n_node=None, n_edge=None)
     params = model.init(0, g0)                       # same seed on every rank = replicated parameters
@@ -623,8 +626,16 @@ def main():
 
     n_f, ms_mf = per_launch("radial_mlp_fwd")
     n_b, ms_mb = per_launch("radial_mlp_bwd")
-    mlp_ms_step = (n_f * ms_mf + n_b * ms_mb) / args.profile_steps
-    mlp_flops_step = E_step * steps_mp * (f_fwd + f_bwd)
+    n_c, ms_mc = per_launch("pair_combine")           # shared radial evaluations: summing the pairs' cotangents
+    ms_mc = 0.0 if ms_mc != ms_mc else ms_mc
+    mlp_ms_step = (n_f * ms_mf + n_b * ms_mb + n_c * ms_mc) / args.profile_steps
+    # radial-MLP evaluations per edge: 1, or (unique edge lengths) / edges with share_radial -- measured on this batch
+    from eqnn_jax_b200.train import wrap_graph
+    s_, r_, _ = ops.knn_pbc(resident[0][0], K_NN, apply_pbc.cell, apply_pbc.cell_inv, want_dr=False)
+    pg = model.prepare(wrap_graph(model, resident[0][0], s_, r_, K_NN, apply_pbc))
+    evals_per_edge = float(pg.pairs.n_unique.item()) / E_step if pg.pairs is not None else 1.0
+    del pg
+    mlp_flops_step = E_step * evals_per_edge * steps_mp * (f_fwd + f_bwd)     # flops of the evaluations that are executed
     mlp_tf = mlp_flops_step / (mlp_ms_step * 1e-3) / 1e12 if mlp_ms_step > 0 else float("nan")
     fused = model.fuse_radial_mlp and ops.radial_mlp_supported(MODEL_KW["n_radial_basis"], MODEL_KW["d_hidden"],
                                                                MODEL_KW["n_layers"], n_live)
@@ -646,7 +657,10 @@ def main():
     else:
         mlp_bytes = (256 + 512) + 2 * 1024 + (512 + 4 * n_live) + (4 * n_live + 1024) + 2 * 1536 + \
                     (512 + 4 * n_live) + 2 * 1024 + (256 + 512)
-    mlp_gbs = E_step * steps_mp * mlp_bytes / (mlp_ms_step * 1e-3) / 1e9 if mlp_ms_step > 0 else float("nan")
+    # per EDGE: the MLP's bytes per evaluation x evaluations per edge, plus (shared evaluations) the pair sum of the
+    # cotangents: per-slot records in, per-evaluation columns + the two slot indices out / in
+    mlp_bytes_edge = mlp_bytes * evals_per_edge + ((4 * n_live) + (4 * n_live + 8) * evals_per_edge if evals_per_edge < 1.0 else 0)
+    mlp_gbs = E_step * steps_mp * mlp_bytes_edge / (mlp_ms_step * 1e-3) / 1e9 if mlp_ms_step > 0 else float("nan")
     tr = ncu_traffic()
     tr_mlp = traffic_of(tr, args.workload, ("rmlp_", "tc_wgrad", "tc_rowgemm", "absmax", "wgrad_reduce", "lbwd_reduce"), E_step)
     tr_tp = traffic_of(tr, args.workload, ("tpconv_fwd", "tpconv_bwd", "sender_reduce", "segment_gather"), E_step)
@@ -667,7 +681,11 @@ def main():
         "config": {"workload": workload_name,
                    "graphs_per_gpu": B, "edges_per_gpu_step": E_step, "message_passing_steps": steps_mp,
                    "cuda_graph": graph_note,
-                   "step": "kNN graph build + CSR/geometry + forward + MSE + backward + grad all-reduce + AdamW",
+                   "radial_mlp": (f"one evaluation per unique edge length (the two directions of a reciprocated edge have "
+                                  f"bit-identical lengths and share it; cotangents summed per pair): {evals_per_edge:.3f} "
+                                  f"evaluations per edge on this batch") if evals_per_edge < 1.0 else "one evaluation per edge",
+                   "step": "kNN graph build + CSR/geometry" + (" + edge pairing" if evals_per_edge < 1.0 else "") +
+                           " + forward + MSE + backward + grad all-reduce + AdamW",
                    "l2": "inputs larger than L2 (per-step working set of several GB)",
                    "parallelism": f"dp{world}"},
         "e2e": {"value": e2e, "unit": "edges/s", "ms_per_step": ms_e2e / args.steps,
@@ -689,14 +707,17 @@ def main():
                      "traffic_bytes_per_edge_step": tr_mlp["bytes_per_edge_step"] if tr_mlp else None,
                      "peak_source": f"bf16_tflops_sustained of {pk['which']}",
                      "flops_per_edge_step": f_fwd + f_bwd, "executed_mma_per_product": 3,
+                     "flops_per_evaluation": f_fwd + f_bwd, "evaluations_per_edge": evals_per_edge,
                      "launches_per_step": (n_f + n_b) / args.profile_steps, "ms_per_step": mlp_ms_step,
                      "ms_fwd_per_launch": ms_mf, "ms_bwd_per_call": ms_mb,
-                     "note": "flops per SURVEY.md 8(d).2 with the live output columns; time = CUDA events around "
-                             "every eqnn_radial_mlp_fwd / _bwd call of the instrumented pass"},
+                     "note": "flops per SURVEY.md 8(d).2 with the live output columns, counted for the radial-MLP evaluations "
+                             "that are EXECUTED (evaluations_per_edge x edges); time = CUDA events around every "
+                             "eqnn_radial_mlp_fwd / _bwd (+ eqnn_pair_combine) call of the instrumented pass"},
         "roofline_mlp_hbm": {"kernel": "same launches, HBM view (bytes the design moves: forward d + w_t + z stash; backward per hidden "
                                        "layer z_{l-1} + g_l in, g_{l-1} out; first / output layer weight gradients basis + g_1, z_H + dw)",
                              "bound": "hbm", "achieved": mlp_gbs, "peak": pk["hbm"], "unit": "GB/s",
-                             "frac": mlp_gbs / pk["hbm"], "bytes_per_edge_step": mlp_bytes,
+                             "frac": mlp_gbs / pk["hbm"], "bytes_per_edge_step": mlp_bytes_edge,
+                             "bytes_per_evaluation": mlp_bytes,
                              "traffic": tr_mlp["per_launch"] if tr_mlp else None,
                              "peak_source": f"hbm_gbs of {pk['which']}"},
         "roofline_tpconv": {"kernel": "tpconv_fwd + tpconv_bwd + sender-side reduction", "bound": "hbm", "achieved": tp_gbs,

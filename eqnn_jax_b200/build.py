@@ -14,7 +14,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libeqnn_b200.so")
-SOURCES = ["knn.cu", "csr.cu", "tpconv.cu", "gemm.cu", "elementwise.cu", "tc_mlp.cu", "rmlp.cu", "tc_gemm.cu", "node.cu", "egnn.cu"]
+SOURCES = ["knn.cu", "csr.cu", "pairs.cu", "tpconv.cu", "gemm.cu", "elementwise.cu", "tc_mlp.cu", "rmlp.cu", "tc_gemm.cu", "node.cu", "egnn.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

@@ -202,6 +202,13 @@ extern "C" int eqnn_exclusive_scan_i32(const int32_t* count, int64_t n, int32_t*
   return EQNN_OK;
 }
 
+// the same scan for other translation units (pairs.cu): out[0..n] from count[0..n)
+int eqnn_scan_rows_i32(const int32_t* count, int64_t n, int32_t* out, cudaStream_t st) {
+  scan_kernel<<<1, 1024, 0, st>>>(count, n, out, nullptr);
+  EQNN_CHECK_LAUNCH();
+  return EQNN_OK;
+}
+
 extern "C" size_t eqnn_csr_workspace_bytes(int B, int N, int E) {
   return align_up(((size_t)B * N + 1) * 4, 256) * 2 + align_up((size_t)B * E * 4, 256);
 }

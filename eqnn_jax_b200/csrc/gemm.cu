@@ -447,7 +447,7 @@ size_t eqnn_tc_wgrad_workspace_bytes(int64_t M, int64_t N, int64_t K);
 int eqnn_tc_wgrad_try(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t sam, int64_t sak,
                       const float* B, int64_t sbk, int64_t sbn, float* C, int64_t scm, int64_t scn, int accumulate,
                       int pro, float pro_scale, int epi, void* ws, size_t ws_bytes, cudaStream_t st,
-                      float* colsum_out = nullptr, int blocked = 0);
+                      float* colsum_out = nullptr, int blocked = 0, const int32_t* n_dev = nullptr);
 
 size_t eqnn_tc_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K);
 int eqnn_tc_gemm_try(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t sam, int64_t sak,

@@ -51,6 +51,12 @@ struct RmlpP {
   // z_stash[n_hidden - 1] = gelu(z_H) and z_stash[n_hidden] = gelu'(z_H) instead of z_H (see the kernel); each
   // [ceil(E/32)] chunks of [32 column groups][32 rows][4 floats] (the blocked chunk layout of tc_mlp.cu's WgradP)
   float* z_stash[RM_MAXL];
+  // shared radial evaluations (pairs.cu): the live row count is a device word (<= E, the capacity every buffer is sized
+  // for), and the radial weights are also / instead written as row-major records w_rows[e][ld_rows] (gathered by
+  // eqnn_tpconv_fwd_shared through the edge -> evaluation map)
+  const int32_t* n_dev;
+  float* w_rows;
+  int ld_rows;
 };
 
 __host__ __device__ inline int rm_K(const RmlpP& p, int l) { return l == 0 ? p.n_rb : 128; }
@@ -105,6 +111,7 @@ __global__ void __launch_bounds__(RM_THREADS, 1) rmlp_fwd_kernel(const RmlpP p) 
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int F = p.n_layers;
+  const int64_t E = p.n_dev ? min((int64_t)__ldg(p.n_dev), p.E) : p.E;   // live rows
   const ActC ac = act_constants(p.act_kind);
 
   // shared-memory map: weight images | bessel frequencies | barriers
@@ -144,7 +151,7 @@ __global__ void __launch_bounds__(RM_THREADS, 1) rmlp_fwd_kernel(const RmlpP p) 
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
 
-  const int64_t n_tiles = (p.E + RM_TILE - 1) / RM_TILE;
+  const int64_t n_tiles = (E + RM_TILE - 1) / RM_TILE;
   const int64_t my_tiles = (blockIdx.x < n_tiles) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   const int64_t n_pairs = (my_tiles + 1) / 2;
   // region r (0 / 1) of slot x; layer l (1-based) accumulates into region (l - 1) & 1 and reads its operand from the other
@@ -163,7 +170,7 @@ __global__ void __launch_bounds__(RM_THREADS, 1) rmlp_fwd_kernel(const RmlpP p) 
         const int64_t tile = blockIdx.x + (2 * pr + x) * (int64_t)gridDim.x;
         const int64_t e = tile * RM_TILE + row;
         if (16 * cg < p.n_rb) {
-          const float d = (e < p.E) ? __ldg(p.dist + e * p.dist_stride) : 0.f;
+          const float d = (e < E) ? __ldg(p.dist + e * p.dist_stride) : 0.f;
           float v[16];
           bessel16(wfreq, 16 * cg, d, p.pref, v);
           uint32_t hiw[8], low[8];
@@ -202,7 +209,7 @@ __global__ void __launch_bounds__(RM_THREADS, 1) rmlp_fwd_kernel(const RmlpP p) 
               float4 a4, g4;
               upk2(a01, a4.x, a4.y); upk2(a23, a4.z, a4.w);
               upk2(g01, g4.x, g4.y); upk2(g23, g4.z, g4.w);
-              if (e < p.E) {
+              if (e < E) {
                 *reinterpret_cast<float4*>(da + i * 128) = a4;
                 *reinterpret_cast<float4*>(dg + i * 128) = g4;
               }
@@ -212,7 +219,7 @@ __global__ void __launch_bounds__(RM_THREADS, 1) rmlp_fwd_kernel(const RmlpP p) 
           } else {
             if (p.z_stash[l - 1]) {
               const int64_t e = (blockIdx.x + (2 * pr + x) * (int64_t)gridDim.x) * RM_TILE + row;
-              if (e < p.E) emit_cols<32>(p.z_stash[l - 1], 1, e, 128, 32 * cg, v);
+              if (e < E) emit_cols<32>(p.z_stash[l - 1], 1, e, 128, 32 * cg, v);
             }
             act_split32(v, ac, hiw, low);
           }
@@ -234,10 +241,18 @@ __global__ void __launch_bounds__(RM_THREADS, 1) rmlp_fwd_kernel(const RmlpP p) 
           float v[16];
           tmem_ld16(region(x, (F - 1) & 1) + lane_sel + RM_FINAL_COL, v);
           tmem_ld_wait();
-          if (e < p.E) {
+          if (e < E) {
+            if (p.w_t) {
 #pragma unroll
-            for (int c = 0; c < 16; ++c)
-              if (c < p.n_out) p.w_t[(int64_t)c * p.ld_wt + e] = v[c];
+              for (int c = 0; c < 16; ++c)
+                if (c < p.n_out) p.w_t[(int64_t)c * p.ld_wt + e] = v[c];
+            }
+            if (p.w_rows) {
+              float4* wr = reinterpret_cast<float4*>(p.w_rows + e * p.ld_rows);
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                if (4 * i < p.ld_rows) wr[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            }
           }
         }
       }
@@ -312,7 +327,9 @@ struct RmlpBwdP {
 
 constexpr uint32_t RM_GSLAB = 128 * 128;   // dw operand: 128 rows x 128 B (16 halves used), K-major, 128B swizzle
 
-__global__ void absmax_kernel(const float* __restrict__ x, int64_t ld, int rows, int64_t cols, uint32_t* __restrict__ out) {
+__global__ void absmax_kernel(const float* __restrict__ x, int64_t ld, int rows, int64_t cols, uint32_t* __restrict__ out,
+                              const int32_t* __restrict__ n_dev) {
+  if (n_dev) cols = min((int64_t)__ldg(n_dev), cols);
   uint32_t m = 0;
   for (int r = 0; r < rows; ++r)
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cols; i += (int64_t)gridDim.x * blockDim.x) {
@@ -826,6 +843,7 @@ struct RmlpLbwdP {
   float* g_out;              // g_{l-1} (blocked, unscaled)
   float* partial;            // [gridDim.x][n = 128][k = 128] per-CTA weight-gradient sums (unscaled by alpha)
   int act_kind;
+  const int32_t* n_dev;      // live row count on the device (<= E), or NULL
 };
 
 constexpr uint32_t RM_LBWD_SEG = 16;         // tiles per tensor-memory accumulation of the weight gradient (384 updates)
@@ -887,7 +905,8 @@ __global__ void __launch_bounds__(LB_THREADS, 1) rmlp_lbwd_kernel(const RmlpLbwd
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
   const uint32_t T_OP = tmem_base, T_PRE = tmem_base + 128u, T_ACC = tmem_base + 256u, T_X = tmem_base + 384u;
 
-  const int64_t n_tiles = (p.E + RM_TILE - 1) / RM_TILE;
+  const int64_t E = p.n_dev ? min((int64_t)__ldg(p.n_dev), p.E) : p.E;   // live rows
+  const int64_t n_tiles = (E + RM_TILE - 1) / RM_TILE;
   const uint32_t my_tiles = (blockIdx.x < n_tiles) ? (uint32_t)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0u;
 
   const uint32_t mbits = __ldg(p.absmax);
@@ -975,9 +994,13 @@ __global__ void __launch_bounds__(LB_THREADS, 1) rmlp_lbwd_kernel(const RmlpLbwd
       }
       tc_fence_before();
     };
+    if (my_tiles == 0) {                      // (possible only with a device-side row count below the launch bound)
+#pragma unroll
+      for (int j = 0; j < 32; ++j) part[j * 128] = 0.f;
+    }
     auto load_z = [&](uint32_t it, float* z) {
       const int64_t e = (blockIdx.x + (int64_t)it * gridDim.x) * RM_TILE + row;
-      if (e < p.E) {
+      if (e < E) {
         load_blocked32(p.z_prev, e, 32 * cg, z);
       } else {
 #pragma unroll
@@ -993,7 +1016,7 @@ __global__ void __launch_bounds__(LB_THREADS, 1) rmlp_lbwd_kernel(const RmlpLbwd
     for (uint32_t it = 0; it < my_tiles; ++it) {
       const uint32_t par = it & 1u;
       const int64_t e = (blockIdx.x + (int64_t)it * gridDim.x) * RM_TILE + row;
-      const bool live = e < p.E;
+      const bool live = e < E;
       float gp[32];
       uint32_t hiw[16], low[16];
 #pragma unroll
@@ -1082,7 +1105,7 @@ __global__ void __launch_bounds__(LB_THREADS, 1) rmlp_lbwd_kernel(const RmlpLbwd
       const int64_t e = (blockIdx.x + (int64_t)it * gridDim.x) * RM_TILE + row;
 #pragma unroll
       for (int c = 0; c < 16; ++c)
-        dnext[c] = (it < my_tiles && e < p.E && c < p.n_out) ? __ldg(p.dw + (int64_t)c * p.ld_dw + e) : 0.f;
+        dnext[c] = (it < my_tiles && e < E && c < p.n_out) ? __ldg(p.dw + (int64_t)c * p.ld_dw + e) : 0.f;
     };
     if (p.first && my_tiles > 0) {
       load_dw(0);
@@ -1091,7 +1114,7 @@ __global__ void __launch_bounds__(LB_THREADS, 1) rmlp_lbwd_kernel(const RmlpLbwd
     for (uint32_t it = 0; it < my_tiles; ++it) {
       const uint32_t par = it & 1u;
       const int64_t e = (blockIdx.x + (int64_t)it * gridDim.x) * RM_TILE + row;
-      const bool live = e < p.E;
+      const bool live = e < E;
       if (p.first) load_dw(it + 1);            // the next tile's dw row: in flight across this tile's passes
       if (p.first) {
         mbar_wait(pro_full, par);
@@ -1197,14 +1220,16 @@ extern "C" size_t eqnn_radial_mlp_stash_bytes(int64_t n_edges, int n_hidden) {
   return (size_t)(n_hidden + 1) * rm_stash_layer_floats(n_edges) * sizeof(float);   // z_1 .. z_{H-1}, gelu(z_H), gelu'(z_H)
 }
 
-extern "C" int eqnn_radial_mlp_fwd(const float* dist, int64_t dist_stride, int64_t n_edges, int n_rb, double r_cut,
-                                   int n_hidden, int d_hidden, const float* const* weights, const int64_t* ldw,
-                                   int n_out, int activation, float act_scale, float* w_t, int64_t ld_wt, float* z_stash,
-                                   eqnn_stream_t stream) {
+static int rm_fwd_impl(const float* dist, int64_t dist_stride, int64_t n_edges, const int32_t* n_dev, int n_rb, double r_cut,
+                       int n_hidden, int d_hidden, const float* const* weights, const int64_t* ldw, int n_out, int activation,
+                       float act_scale, float* w_t, int64_t ld_wt, float* w_rows, int ld_rows, float* z_stash,
+                       eqnn_stream_t stream) {
   EQNN_CHECK_ARG(activation == EQNN_ACT_GELU || activation == EQNN_ACT_SILU, "radial_mlp_fwd: unknown activation");
-  EQNN_CHECK_ARG(dist && weights && ldw && w_t && n_edges >= 0 && dist_stride >= 1, "radial_mlp_fwd: bad argument");
+  EQNN_CHECK_ARG(dist && weights && ldw && (w_t || w_rows) && n_edges >= 0 && dist_stride >= 1, "radial_mlp_fwd: bad argument");
   EQNN_CHECK_ARG(eqnn_radial_mlp_supported(n_rb, d_hidden, n_hidden, n_out), "radial_mlp_fwd: unsupported shape");
-  EQNN_CHECK_ARG(r_cut > 0.0 && ld_wt >= n_edges, "radial_mlp_fwd: bad r_cut / ld_wt");
+  EQNN_CHECK_ARG(r_cut > 0.0 && (!w_t || ld_wt >= n_edges), "radial_mlp_fwd: bad r_cut / ld_wt");
+  EQNN_CHECK_ARG(!w_rows || (ld_rows % 4 == 0 && ld_rows >= n_out && ld_rows <= 16 && (reinterpret_cast<uintptr_t>(w_rows) & 15) == 0),
+                 "radial_mlp_fwd: w_rows needs ld_rows = n_out rounded up to 4 and 16-byte alignment");
   // bessel values are bounded by sqrt(2/c) * n_rb * pi / c: they must stay inside the fp16 range of the operand split
   EQNN_CHECK_ARG(sqrt(2.0 / r_cut) * n_rb * 3.14159265358979323846 / r_cut < 60000.0, "radial_mlp_fwd: r_cut too small for the fp16 operand split");
   if (n_edges == 0) return EQNN_OK;
@@ -1221,6 +1246,7 @@ extern "C" int eqnn_radial_mlp_fwd(const float* dist, int64_t dist_stride, int64
     p.alpha[l] = (float)(1.0 / sqrt((double)rm_K(p, l)));
   }
   p.act_scale = act_scale; p.act_kind = activation; p.w_t = w_t; p.ld_wt = ld_wt;
+  p.n_dev = n_dev; p.w_rows = w_rows; p.ld_rows = ld_rows;
   EQNN_CHECK_ARG(!z_stash || (reinterpret_cast<uintptr_t>(z_stash) & 15) == 0, "radial_mlp_fwd: z_stash must be 16-byte aligned");
   for (int l = 0; l < RM_MAXL; ++l)
     p.z_stash[l] = (z_stash && l <= n_hidden) ? z_stash + (size_t)l * rm_stash_layer_floats(n_edges) : nullptr;
@@ -1235,12 +1261,32 @@ extern "C" int eqnn_radial_mlp_fwd(const float* dist, int64_t dist_stride, int64
   return EQNN_OK;
 }
 
+extern "C" int eqnn_radial_mlp_fwd(const float* dist, int64_t dist_stride, int64_t n_edges, int n_rb, double r_cut,
+                                   int n_hidden, int d_hidden, const float* const* weights, const int64_t* ldw,
+                                   int n_out, int activation, float act_scale, float* w_t, int64_t ld_wt, float* z_stash,
+                                   eqnn_stream_t stream) {
+  EQNN_CHECK_ARG(w_t, "radial_mlp_fwd: bad argument");
+  return rm_fwd_impl(dist, dist_stride, n_edges, nullptr, n_rb, r_cut, n_hidden, d_hidden, weights, ldw, n_out, activation,
+                     act_scale, w_t, ld_wt, nullptr, 0, z_stash, stream);
+}
+
+// Same MLP over a compact array of rows whose live count sits in device memory (shared radial evaluations, pairs.cu):
+// n_cap sizes every buffer and the launch, *n_rows (<= n_cap) rows are evaluated; the result is written as row-major
+// records w_rows [n_cap][ld_rows] (ld_rows = n_out rounded up to 4) and / or column-major w_t.
+extern "C" int eqnn_radial_mlp_fwd_rows(const float* dist, int64_t dist_stride, int64_t n_cap, const int32_t* n_rows, int n_rb,
+                                        double r_cut, int n_hidden, int d_hidden, const float* const* weights,
+                                        const int64_t* ldw, int n_out, int activation, float act_scale, float* w_t,
+                                        int64_t ld_wt, float* w_rows, int ld_rows, float* z_stash, eqnn_stream_t stream) {
+  return rm_fwd_impl(dist, dist_stride, n_cap, n_rows, n_rb, r_cut, n_hidden, d_hidden, weights, ldw, n_out, activation,
+                     act_scale, w_t, ld_wt, w_rows, ld_rows, z_stash, stream);
+}
+
 int eqnn_tc_wgrad_try(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t sam, int64_t sak,
                       const float* B, int64_t sbk, int64_t sbn, float* C, int64_t scm, int64_t scn, int accumulate,
                       int pro, float pro_scale, int epi, void* ws, size_t ws_bytes, cudaStream_t st,
-                      float* colsum_out, int blocked);
+                      float* colsum_out, int blocked, const int32_t* n_dev);
 int eqnn_tc_wgrad_bessel_try(int n_rb, int64_t E, float alpha, const float* geom, double r_cut, const float* G, int g_blocked,
-                             float* C, int64_t scm, void* ws, size_t ws_bytes, cudaStream_t st);
+                             float* C, int64_t scm, void* ws, size_t ws_bytes, cudaStream_t st, const int32_t* n_dev);
 
 // workspace: [absmax 256 B | bessel basis E*n_rb | n_hidden x gelu(z_l) E*128 | n_hidden x g_l E*128 | GEMM workspace]
 static size_t rm_bwd_gemm_ws(int64_t n_edges) {
@@ -1258,7 +1304,7 @@ extern "C" size_t eqnn_radial_mlp_bwd_workspace_bytes(int64_t n_edges, int n_rb,
 // Backward from the forward kernel's z stash: absmax -> data-gradient chain kernel -> weight gradients on the tcgen05
 // weight-gradient kernel (X = z_{l-1} with the gelu prologue, or the Bessel basis for the first layer; G = g_l).
 // workspace: [absmax 256 B | n_hidden x g_l | (bessel basis when radial == NULL) | GEMM workspace]
-static int rm_bwd_from_stash(const float* dist, int64_t dist_stride, int64_t n_edges, int n_rb, double r_cut, int n_hidden,
+static int rm_bwd_from_stash(const float* dist, int64_t dist_stride, int64_t n_edges, const int32_t* n_dev, int n_rb, double r_cut, int n_hidden,
                              int d_hidden, const float* const* weights, const int64_t* ldw, int n_out, int activation,
                              float act_scale, const float* dw_t, int64_t ld_dwt, const float* z_stash, const float* radial,
                              float* const* grad_weights, void* ws, size_t ws_bytes, eqnn_stream_t stream) {
@@ -1297,6 +1343,7 @@ static int rm_bwd_from_stash(const float* dist, int64_t dist_stride, int64_t n_e
     f.alpha[l] = (float)(1.0 / sqrt((double)rm_K(f, l)));
   }
   f.act_scale = act_scale; f.act_kind = activation; f.w_t = nullptr; f.ld_wt = 0;
+  f.n_dev = nullptr; f.w_rows = nullptr; f.ld_rows = 0;
   p.dw = dw_t; p.ld_dw = ld_dwt;
   char* w = reinterpret_cast<char*>(ws);
   uint32_t* absmax = reinterpret_cast<uint32_t*>(w);
@@ -1334,7 +1381,7 @@ static int rm_bwd_from_stash(const float* dist, int64_t dist_stride, int64_t n_e
   {
     const int64_t want = (n_edges + 255) / 256;
     const unsigned grid = (unsigned)(want < 1184 ? want : 1184);
-    absmax_kernel<<<grid, 256, 0, st>>>(dw_t, ld_dwt, n_out, n_edges, absmax);
+    absmax_kernel<<<grid, 256, 0, st>>>(dw_t, ld_dwt, n_out, n_edges, absmax, n_dev);
   }
   const int64_t n_tiles = (n_edges + RM_TILE - 1) / RM_TILE;
   const int sms = sm_count();
@@ -1350,7 +1397,7 @@ static int rm_bwd_from_stash(const float* dist, int64_t dist_stride, int64_t n_e
     EQNN_CHECK_LAUNCH();   // (absmax)
     for (int l = n_hidden; l >= 2; --l) {                  // 1-based hidden layer: W[l - 1] maps gelu(z_{l-1}) to z_l
       RmlpLbwdP q;
-      q.E = n_edges;
+      q.E = n_edges; q.n_dev = n_dev;
       q.W = weights[l - 1]; q.ldw = ldw[l - 1]; q.wscale = rm_wscale(f.alpha, act_scale, l - 1);
       q.Wout = weights[F - 1]; q.ldwout = ldw[F - 1]; q.wout_scale = rm_wscale(f.alpha, act_scale, F - 1); q.n_out = n_out;
       q.first = (l == n_hidden) ? 1 : 0;
@@ -1365,6 +1412,7 @@ static int rm_bwd_from_stash(const float* dist, int64_t dist_stride, int64_t n_e
       EQNN_CHECK_LAUNCH();
     }
   } else {
+    if (n_dev) return eqnn_fail(EQNN_ERR_ARG, "radial_mlp_bwd_rows: a device-side row count needs the fused layer kernels (n_hidden >= 2, n_cap >= 4096, blocked tensor-core weight gradients)");
     uint32_t smem = 1024 + 64;
     for (int l = 1; l < F; ++l) smem += 2 * w_half_bytes(rm_K(f, l), rm_N(f, l));
     static DeviceOnce once;
@@ -1382,7 +1430,7 @@ static int rm_bwd_from_stash(const float* dist, int64_t dist_stride, int64_t n_e
     const float* G = l < F - 1 ? p.grad[l + 1] : dw_t;
     const int64_t N = l < F - 1 ? 128 : n_out, sbk = l < F - 1 ? 128 : 1, sbn = l < F - 1 ? 1 : ld_dwt;
     if (tc_ok[l] && l == 0 && bessel_wgrad && F >= 2) {
-      const int r = eqnn_tc_wgrad_bessel_try(n_rb, n_edges, f.alpha[0], dist - 3, r_cut, G, 1, grad_weights[0], ldw[0], gws, gws_bytes, st);
+      const int r = eqnn_tc_wgrad_bessel_try(n_rb, n_edges, f.alpha[0], dist - 3, r_cut, G, 1, grad_weights[0], ldw[0], gws, gws_bytes, st, n_dev);
       if (r < 0) return -r;
       if (r == 1) continue;
       if (!radial) return eqnn_fail(EQNN_ERR_ARG, "radial_mlp_bwd: first-layer weight gradient not covered and no radial given");
@@ -1390,12 +1438,13 @@ static int rm_bwd_from_stash(const float* dist, int64_t dist_stride, int64_t n_e
     if (tc_ok[l]) {
       const int blocked = (l > 0 ? 1 : 0) | (l < F - 1 ? 2 : 0);
       const int r = eqnn_tc_wgrad_try(K, N, n_edges, al, X, 1, K, G, sbk, sbn, grad_weights[l], ldw[l], 1, 0, pro,
-                                      act_scale, 0, gws, gws_bytes, st, nullptr, blocked);
+                                      act_scale, 0, gws, gws_bytes, st, nullptr, blocked, n_dev);
       if (r < 0) return -r;
       if (r != 1) return eqnn_fail(EQNN_ERR_ARG, "radial_mlp_bwd: weight-gradient shape not covered by the tensor-core kernel");
       continue;
     }
     // small problems: CUDA-core GEMM on row-major operands; a blocked z_l is first copied out row-major
+    if (n_dev) return eqnn_fail(EQNN_ERR_ARG, "radial_mlp_bwd_rows: weight-gradient shape not covered by the tensor-core kernel");
     const float* Xr = X;
     if (l > 0) {
       float* tmp = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + 256 + (size_t)n_hidden * ep * 512);
@@ -1410,6 +1459,18 @@ static int rm_bwd_from_stash(const float* dist, int64_t dist_stride, int64_t n_e
   return EQNN_OK;
 }
 
+// Backward over a compact row array with a device-side live count (see eqnn_radial_mlp_fwd_rows): the z-stash variant on
+// the fused layer kernels only.
+extern "C" int eqnn_radial_mlp_bwd_rows(const float* dist, int64_t dist_stride, int64_t n_cap, const int32_t* n_rows, int n_rb,
+                                        double r_cut, int n_hidden, int d_hidden, const float* const* weights,
+                                        const int64_t* ldw, int n_out, int activation, float act_scale, const float* dw_t,
+                                        int64_t ld_dwt, const float* z_stash, const float* radial, float* const* grad_weights,
+                                        void* ws, size_t ws_bytes, eqnn_stream_t stream) {
+  EQNN_CHECK_ARG(z_stash && radial, "radial_mlp_bwd_rows: needs the forward kernel's z stash and the Bessel basis of the rows");
+  return rm_bwd_from_stash(dist, dist_stride, n_cap, n_rows, n_rb, r_cut, n_hidden, d_hidden, weights, ldw, n_out, activation,
+                           act_scale, dw_t, ld_dwt, z_stash, radial, grad_weights, ws, ws_bytes, stream);
+}
+
 extern "C" int eqnn_radial_mlp_bwd(const float* dist, int64_t dist_stride, int64_t n_edges, int n_rb, double r_cut,
                                    int n_hidden, int d_hidden, const float* const* weights, const int64_t* ldw,
                                    int n_out, int activation, float act_scale, const float* dw_t, int64_t ld_dwt,
@@ -1417,7 +1478,7 @@ extern "C" int eqnn_radial_mlp_bwd(const float* dist, int64_t dist_stride, int64
                                    size_t ws_bytes, eqnn_stream_t stream) {
   EQNN_CHECK_ARG(activation == EQNN_ACT_GELU || activation == EQNN_ACT_SILU, "radial_mlp_bwd: unknown activation");
   if (z_stash)
-    return rm_bwd_from_stash(dist, dist_stride, n_edges, n_rb, r_cut, n_hidden, d_hidden, weights, ldw, n_out, activation,
+    return rm_bwd_from_stash(dist, dist_stride, n_edges, nullptr, n_rb, r_cut, n_hidden, d_hidden, weights, ldw, n_out, activation,
                              act_scale, dw_t, ld_dwt, z_stash, radial, grad_weights, ws, ws_bytes, stream);
   EQNN_CHECK_ARG(dist && weights && ldw && dw_t && grad_weights && n_edges >= 0 && dist_stride >= 1, "radial_mlp_bwd: bad argument");
   EQNN_CHECK_ARG(eqnn_radial_mlp_supported(n_rb, d_hidden, n_hidden, n_out), "radial_mlp_bwd: unsupported shape");
@@ -1441,6 +1502,7 @@ extern "C" int eqnn_radial_mlp_bwd(const float* dist, int64_t dist_stride, int64
     f.alpha[l] = (float)(1.0 / sqrt((double)rm_K(f, l)));
   }
   f.act_scale = act_scale; f.act_kind = activation; f.w_t = nullptr; f.ld_wt = 0;
+  f.n_dev = nullptr; f.w_rows = nullptr; f.ld_rows = 0;
   for (int l = 0; l < RM_MAXL; ++l) f.z_stash[l] = nullptr;
   p.dw = dw_t; p.ld_dw = ld_dwt;
   char* w = reinterpret_cast<char*>(ws);
@@ -1480,7 +1542,7 @@ extern "C" int eqnn_radial_mlp_bwd(const float* dist, int64_t dist_stride, int64
   {
     const int64_t want = (n_edges + 255) / 256;
     const unsigned grid = (unsigned)(want < 1184 ? want : 1184);
-    absmax_kernel<<<grid, 256, 0, st>>>(dw_t, ld_dwt, n_out, n_edges, absmax);
+    absmax_kernel<<<grid, 256, 0, st>>>(dw_t, ld_dwt, n_out, n_edges, absmax, nullptr);
   }
   uint32_t smem = rm_smem_bytes(f) + 2 * RM_GSLAB;
   static DeviceOnce once;
@@ -1499,7 +1561,7 @@ extern "C" int eqnn_radial_mlp_bwd(const float* dist, int64_t dist_stride, int64
     const int64_t N = l < F - 1 ? 128 : n_out, sbk = l < F - 1 ? 128 : 1, sbn = l < F - 1 ? 1 : ld_dwt;
     if (p.blk[l]) {
       const int w = eqnn_tc_wgrad_try(K, N, n_edges, al, p.act[l], 1, K, G, sbk, sbn, grad_weights[l], ldw[l], 1, 0, 0, 1.f,
-                                      0, gws, gws_bytes, st, nullptr, l < F - 1 ? 3 : 1);
+                                      0, gws, gws_bytes, st, nullptr, l < F - 1 ? 3 : 1, nullptr);
       if (w < 0) return -w;
       if (w != 1) return eqnn_fail(EQNN_ERR_ARG, "radial_mlp_bwd: weight-gradient shape not covered by the tensor-core kernel");
       continue;

@@ -402,6 +402,7 @@ struct WgradP {
   // 512 bytes per chunk cross HBM instead of 32 * MI * 4.  geom = [E][4] floats, d in component 3.
   const float* geom;
   float r_cut, pref;
+  const int32_t* n_dev;   // live edge count on the device (<= E), or NULL: shared radial evaluations (pairs.cu)
 };
 
 // wgrad thread layout (warpgroup-aligned so that registers can be re-balanced with setmaxnreg):
@@ -457,7 +458,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const WgradP p)
   float* wfreq = reinterpret_cast<float*>(gen_base + (bars - base) + 256);   // PRO == 2: j * pi / r_cut, j = 1..MI
   if (PRO == 2 && tid < MI) wfreq[tid] = __fdiv_rn(__fmul_rn((float)(tid + 1), 3.14159265358979323846f), p.r_cut);
 
-  const int64_t n_chunks = (p.E + 31) / 32;
+  const int64_t E = p.n_dev ? min((int64_t)__ldg(p.n_dev), p.E) : p.E;   // live edges
+  const int64_t n_chunks = (E + 31) / 32;
   const int64_t per = (n_chunks + gridDim.x - 1) / gridDim.x;
   const int64_t c_beg = (int64_t)blockIdx.x * per;
   const int64_t c_end = (c_beg + per < n_chunks) ? c_beg + per : n_chunks;
@@ -499,9 +501,13 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const WgradP p)
       if (lane == 0) mbar_wait(r_empty(rs), ((g / RAW_NS) & 1u) ^ 1u);
       __syncwarp();
       const int64_t e0 = (c_beg + g) * 32;
-      const uint32_t rows = (uint32_t)((p.E - e0 < 32) ? (p.E - e0) : 32);
+      const uint32_t rows = (uint32_t)((E - e0 < 32) ? (E - e0) : 32);
       const uint32_t xdst = raw0 + rs * Cfg::RAW_STAGE, gdst = xdst + Cfg::XRAW;
-      const uint32_t gbytes = (GMODE == 0) ? rows * N * 4u : (uint32_t)p.n_valid * rows * 4u;
+      // column-major G: 32 edges of a column are one copy, whose size must be a multiple of 16 bytes -- a live count that
+      // is not a multiple of 4 (device-side counts are arbitrary) copies up to 3 floats past it, inside the padded leading
+      // dimension (ldg % 4 == 0); the transform warps mask them
+      const uint32_t rows4 = (rows + 3u) & ~3u;
+      const uint32_t gbytes = (GMODE == 0) ? rows * N * 4u : (uint32_t)p.n_valid * rows4 * 4u;
       const uint32_t xbytes = PRO == 2 ? rows * 16u : (p.x_blocked ? 32u * MI * 4u : rows * MI * 4u);
       const uint32_t gbytes_c = (GMODE == 0 && p.g_blocked) ? 32u * N * 4u : gbytes;
       if (lane == 0) mbar_expect_tx(r_full(rs), xbytes + gbytes_c);
@@ -520,7 +526,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const WgradP p)
           bulk_g2s(gdst + lane * N * 4u, p.G + (e0 + lane) * p.ldg, N * 4u, r_full(rs));
         }
       } else if (lane < p.n_valid) {
-        bulk_g2s(gdst + lane * 128u, p.G + (int64_t)lane * p.ldg + e0, rows * 4u, r_full(rs));   // 32 edges of column n
+        bulk_g2s(gdst + lane * 128u, p.G + (int64_t)lane * p.ldg + e0, rows4 * 4u, r_full(rs));   // 32 edges of column n
       }
     }
   } else if (warp >= WG_TW0 && warp < WG_MMA_WARP) {
@@ -544,7 +550,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const WgradP p)
     for (uint32_t g = 0; g < total; ++g) {
       const int s = g % NSTAGE, rs = g % RAW_NS;
       const int64_t e0 = (c_beg + g) * 32;
-      const int rows = (int)((p.E - e0 < 32) ? (p.E - e0) : 32);
+      const int rows = (int)((E - e0 < 32) ? (E - e0) : 32);
       mbar_wait(r_full(rs), (g / RAW_NS) & 1u);
       mbar_wait(a_empty(s), ((g / NSTAGE) & 1u) ^ 1u);
       const uint8_t* xraw = gen_base + (raw0 - base) + rs * Cfg::RAW_STAGE;
@@ -762,7 +768,7 @@ size_t eqnn_tc_wgrad_workspace_bytes(int64_t M, int64_t N, int64_t K) {
 int eqnn_tc_wgrad_try(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t sam, int64_t sak,
                       const float* B, int64_t sbk, int64_t sbn, float* C, int64_t scm, int64_t scn, int accumulate,
                       int pro, float pro_scale, int epi, void* ws, size_t ws_bytes, cudaStream_t st,
-                      float* colsum_out, int blocked) {
+                      float* colsum_out, int blocked, const int32_t* n_dev) {
   // blocked: bit 0 = A (X) in the blocked chunk layout, bit 1 = B (G); see WgradP
   if (accumulate || epi != 0 || K < 4096 || scn != 1) return 0;
   if (colsum_out && !(N == 128 && sbn == 1 && !(blocked & 2))) return 0;
@@ -774,7 +780,7 @@ int eqnn_tc_wgrad_try(int64_t M, int64_t N, int64_t K, float alpha, const float*
   WgradP p;
   p.X = A; p.ldx = sak; p.G = B; p.E = K; p.pro_scale = pro_scale; p.n_valid = (int)N;
   p.x_blocked = blocked & 1; p.g_blocked = (blocked >> 1) & 1;
-  p.geom = nullptr; p.r_cut = 1.f; p.pref = 0.f;
+  p.geom = nullptr; p.r_cut = 1.f; p.pref = 0.f; p.n_dev = n_dev;
   if (p.x_blocked && sak != M) return 0;
   p.partial = reinterpret_cast<float*>(ws);
   p.colsum = nullptr;
@@ -810,7 +816,7 @@ int eqnn_tc_wgrad_try(int64_t M, int64_t N, int64_t K, float alpha, const float*
 //   dW[n_rb x 128] = alpha * bessel(d)^T @ G,  d = geom[e][3], G = [E][128] row-major or blocked.
 // Same return convention as eqnn_tc_wgrad_try.
 int eqnn_tc_wgrad_bessel_try(int n_rb, int64_t E, float alpha, const float* geom, double r_cut, const float* G, int g_blocked,
-                             float* C, int64_t scm, void* ws, size_t ws_bytes, cudaStream_t st) {
+                             float* C, int64_t scm, void* ws, size_t ws_bytes, cudaStream_t st, const int32_t* n_dev) {
   if (!(n_rb == 32 || n_rb == 64) || E < 4096 || !geom || (reinterpret_cast<uintptr_t>(geom) & 15) ||
       (reinterpret_cast<uintptr_t>(G) & 15))
     return 0;
@@ -823,7 +829,7 @@ int eqnn_tc_wgrad_bessel_try(int n_rb, int64_t E, float alpha, const float* geom
   p.x_blocked = 0; p.g_blocked = g_blocked ? 1 : 0;
   p.partial = reinterpret_cast<float*>(ws);
   p.colsum = nullptr;
-  p.geom = geom; p.r_cut = (float)r_cut; p.pref = (float)sqrt(2.0 / r_cut);
+  p.geom = geom; p.r_cut = (float)r_cut; p.pref = (float)sqrt(2.0 / r_cut); p.n_dev = n_dev;
   const int rc = n_rb == 64 ? launch_wgrad<64, 128, 0, 2>(p, grid, st) : launch_wgrad<32, 128, 0, 2>(p, grid, st);
   if (rc) return -rc;
   wgrad_reduce_kernel<<<(n_rb * 128 + 31) / 32, 256, 0, st>>>(p.partial, grid, n_rb, 128, 128, alpha, C, scm);

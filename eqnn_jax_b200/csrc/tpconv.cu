@@ -38,6 +38,29 @@ __device__ __forceinline__ void load_x(const float* __restrict__ xt, int s, floa
   }
 }
 
+// radial weights of CSR slot p: column-major w_t [NLIVE][n_edges], or -- shared radial evaluations (pairs.cu) -- the
+// row-major record of the slot's unique evaluation, w_rows [n_unique][LDR], LDR = NLIVE rounded up to 4 (one or two
+// 128-bit loads behind the uidx load, which sits beside the src -> xt gather in the dependency chain)
+template <class TP>
+__device__ __forceinline__ void load_w(const float* __restrict__ w_t, int64_t n_edges, const int32_t* __restrict__ uidx,
+                                       const float* __restrict__ w_rows, int p, float* w) {
+  constexpr int LDR = (TP::NLIVE + 3) / 4 * 4;
+  if (uidx) {
+    const float4* r = reinterpret_cast<const float4*>(w_rows + (size_t)__ldg(uidx + p) * LDR);
+#pragma unroll
+    for (int i = 0; i < LDR / 4; ++i) {
+      const float4 v = __ldg(r + i);
+      if (4 * i + 0 < TP::NLIVE) w[4 * i + 0] = v.x;
+      if (4 * i + 1 < TP::NLIVE) w[4 * i + 1] = v.y;
+      if (4 * i + 2 < TP::NLIVE) w[4 * i + 2] = v.z;
+      if (4 * i + 3 < TP::NLIVE) w[4 * i + 3] = v.w;
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < TP::NLIVE; ++c) w[c] = w_t[(size_t)c * n_edges + p];
+  }
+}
+
 // AMAX: jraph.segment_max (message_passing_agg = "max", models/nequip.py:118-120): the running value is the maximum
 // over the row's edges and the CSR position of the FIRST edge that attains it is recorded, so that the backward
 // pass can route the gradient to that edge alone (ties are measure-zero for real messages; the self-loop's exact
@@ -54,7 +77,7 @@ __global__ void __launch_bounds__(TPC_THREADS)
 tpconv_fwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src,
                   const float4* __restrict__ geom, const float* __restrict__ w_t, int64_t n_edges,
                   const float* __restrict__ xt, int n_nodes, int agg, float* __restrict__ A, int ld_a,
-                  int32_t* __restrict__ argmax) {
+                  int32_t* __restrict__ argmax, const int32_t* __restrict__ uidx, const float* __restrict__ w_rows) {
   constexpr int DL = TP::DLIVE;
   constexpr int S = tpc_stride(DL), S4 = S / 4;
   constexpr int NQ = (DL + 3) / 4;                      // component quads per row
@@ -84,8 +107,7 @@ tpconv_fwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
       float x[TP::DXP], w[TP::NLIVE], Y[TP::NY];
       __align__(16) float m[S];
       load_x<TP>(xt, s, x);
-#pragma unroll
-      for (int c = 0; c < TP::NLIVE; ++c) w[c] = w_t[(size_t)c * n_edges + p];
+      load_w<TP>(w_t, n_edges, uidx, w_rows, p, w);
       TP::sh(g.x, g.y, g.z, Y);
 #pragma unroll
       for (int i = DL; i < S; ++i) m[i] = 0.f;
@@ -163,7 +185,8 @@ tpconv_bwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
                   const int32_t* __restrict__ perm, const float4* __restrict__ geom,
                   const float* __restrict__ w_t, int64_t n_edges, const float* __restrict__ xt, int n_nodes,
                   int agg, const float* __restrict__ gA, int ld_ga, float* __restrict__ dw_t,
-                  float* __restrict__ dxe, const int32_t* __restrict__ argmax) {
+                  float* __restrict__ dxe, const int32_t* __restrict__ argmax, const int32_t* __restrict__ uidx,
+                  const float* __restrict__ w_rows, float* __restrict__ dw_rows) {
   constexpr int DL = TP::DLIVE;
   constexpr int GS = DL | 1;
   __shared__ float sG[TPC_ROWS * GS];
@@ -195,14 +218,23 @@ tpconv_bwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
     const float4 gm = geom[p];
     float x[TP::DXP], w[TP::NLIVE], Y[TP::NY], g[DL], dw[TP::NLIVE], dx[TP::DXP];
     load_x<TP>(xt, s, x);
-#pragma unroll
-    for (int c = 0; c < TP::NLIVE; ++c) w[c] = w_t[(size_t)c * n_edges + p];
+    load_w<TP>(w_t, n_edges, uidx, w_rows, p, w);
 #pragma unroll
     for (int i = 0; i < DL; ++i) g[i] = (!AMAX || sArg[row * GS + i] == p) ? sG[row * GS + i] : 0.f;
     TP::sh(gm.x, gm.y, gm.z, Y);
     TP::bwd(x, Y, w, g, dw, dx);
+    if (dw_rows) {                           // shared radial evaluations: one row-major record per slot (pair_combine sums the pair)
+      constexpr int LDR = (TP::NLIVE + 3) / 4 * 4;
+      float4* dr = reinterpret_cast<float4*>(dw_rows + (size_t)p * LDR);
+      float dwp[LDR];
 #pragma unroll
-    for (int c = 0; c < TP::NLIVE; ++c) dw_t[(size_t)c * n_edges + p] = dw[c];
+      for (int c = 0; c < LDR; ++c) dwp[c] = c < TP::NLIVE ? dw[c < TP::NLIVE ? c : 0] : 0.f;
+#pragma unroll
+      for (int i = 0; i < LDR / 4; ++i) dr[i] = make_float4(dwp[4 * i], dwp[4 * i + 1], dwp[4 * i + 2], dwp[4 * i + 3]);
+    } else {
+#pragma unroll
+      for (int c = 0; c < TP::NLIVE; ++c) dw_t[(size_t)c * n_edges + p] = dw[c];
+    }
     float4* o = reinterpret_cast<float4*>(dxe + (size_t)e * TP::DXP);
 #pragma unroll
     for (int i = 0; i < TP::DXP / 4; ++i) o[i] = make_float4(dx[4 * i], dx[4 * i + 1], dx[4 * i + 2], dx[4 * i + 3]);
@@ -349,28 +381,74 @@ extern "C" int eqnn_tp_dims(int id, int* dxp, int* ny, int* n_live, int* d_live)
   return EQNN_OK;
 }
 
-extern "C" int eqnn_tpconv_fwd(int tp_id, const int32_t* rowptr, const int32_t* src, const float* geom,
-                               const float* w_t, int64_t n_edges, const float* xt, int n_nodes, int agg, float* A,
-                               int ld_a, int32_t* argmax, eqnn_stream_t stream) {
-  EQNN_CHECK_ARG(rowptr && src && geom && w_t && xt && A, "tpconv_fwd: null pointer");
+static int tpconv_fwd_impl(int tp_id, const int32_t* rowptr, const int32_t* src, const float* geom, const float* w_t,
+                           int64_t n_edges, const int32_t* uidx, const float* w_rows, int ld_rows, const float* xt,
+                           int n_nodes, int agg, float* A, int ld_a, int32_t* argmax, eqnn_stream_t stream) {
+  EQNN_CHECK_ARG(rowptr && src && geom && (w_t || (uidx && w_rows)) && xt && A, "tpconv_fwd: null pointer");
   EQNN_CHECK_ARG(agg >= 0 && agg <= 2, "tpconv_fwd: agg must be 0 (sum), 1 (mean) or 2 (max)");
   EQNN_CHECK_ARG(agg != 2 || argmax, "tpconv_fwd: max aggregation needs the argmax buffer");
   EQNN_CHECK_ARG(((uintptr_t)geom & 15) == 0 && ((uintptr_t)xt & 15) == 0, "tpconv_fwd: geom/xt must be 16-byte aligned");
+  EQNN_CHECK_ARG(!uidx || ((uintptr_t)w_rows & 15) == 0, "tpconv_fwd: w_rows must be 16-byte aligned");
   if (n_nodes <= 0) return EQNN_OK;
   const unsigned grid = (unsigned)((n_nodes + TPC_ROWS - 1) / TPC_ROWS);
   EQNN_TP_DISPATCH(tp_id, {
     EQNN_CHECK_ARG(ld_a >= TP::DLIVE, "tpconv_fwd: ld_a smaller than live width");
+    EQNN_CHECK_ARG(!uidx || ld_rows == (TP::NLIVE + 3) / 4 * 4, "tpconv_fwd: ld_rows must be NLIVE rounded up to 4");
     // the widest signatures (every message column at l_max 3: eqnn_tp_messages only) do not fit the message transpose
     if constexpr (tpc_stride(TP::DLIVE) * TPC_THREADS * 4 <= 40 * 1024) {
       if (agg == 2)
         tpconv_fwd_kernel<TP, true><<<grid, TPC_THREADS, 0, as_stream(stream)>>>(
-            rowptr, src, reinterpret_cast<const float4*>(geom), w_t, n_edges, xt, n_nodes, agg, A, ld_a, argmax);
+            rowptr, src, reinterpret_cast<const float4*>(geom), w_t, n_edges, xt, n_nodes, agg, A, ld_a, argmax, uidx, w_rows);
       else
         tpconv_fwd_kernel<TP, false><<<grid, TPC_THREADS, 0, as_stream(stream)>>>(
-            rowptr, src, reinterpret_cast<const float4*>(geom), w_t, n_edges, xt, n_nodes, agg, A, ld_a, nullptr);
+            rowptr, src, reinterpret_cast<const float4*>(geom), w_t, n_edges, xt, n_nodes, agg, A, ld_a, nullptr, uidx, w_rows);
     } else {
       return eqnn_fail(EQNN_ERR_ARG, "tpconv_fwd: this signature is wider than the reduction kernel covers");
     }
+  });
+  EQNN_CHECK_LAUNCH();
+  return EQNN_OK;
+}
+
+extern "C" int eqnn_tpconv_fwd(int tp_id, const int32_t* rowptr, const int32_t* src, const float* geom,
+                               const float* w_t, int64_t n_edges, const float* xt, int n_nodes, int agg, float* A,
+                               int ld_a, int32_t* argmax, eqnn_stream_t stream) {
+  EQNN_CHECK_ARG(w_t, "tpconv_fwd: null pointer");
+  return tpconv_fwd_impl(tp_id, rowptr, src, geom, w_t, n_edges, nullptr, nullptr, 0, xt, n_nodes, agg, A, ld_a, argmax, stream);
+}
+
+extern "C" int eqnn_tpconv_fwd_shared(int tp_id, const int32_t* rowptr, const int32_t* src, const float* geom,
+                                      const int32_t* uidx, const float* w_rows, int ld_rows, const float* xt, int n_nodes,
+                                      int agg, float* A, int ld_a, int32_t* argmax, eqnn_stream_t stream) {
+  EQNN_CHECK_ARG(uidx && w_rows, "tpconv_fwd_shared: null pointer");
+  return tpconv_fwd_impl(tp_id, rowptr, src, geom, nullptr, 0, uidx, w_rows, ld_rows, xt, n_nodes, agg, A, ld_a, argmax, stream);
+}
+
+static int tpconv_bwd_impl(int tp_id, const int32_t* rowptr, const int32_t* src, const int32_t* perm, const float* geom,
+                           const float* w_t, int64_t n_edges, const int32_t* uidx, const float* w_rows, int ld_rows,
+                           const float* xt, int n_nodes, int agg, const float* gA, int ld_ga, float* dw_t, float* dw_rows,
+                           float* dxe, const int32_t* argmax, eqnn_stream_t stream) {
+  EQNN_CHECK_ARG(rowptr && src && perm && geom && (w_t || (uidx && w_rows)) && xt && gA && (dw_t || dw_rows) && dxe,
+                 "tpconv_bwd: null pointer");
+  EQNN_CHECK_ARG(agg >= 0 && agg <= 2, "tpconv_bwd: agg must be 0 (sum), 1 (mean) or 2 (max)");
+  EQNN_CHECK_ARG(agg != 2 || argmax, "tpconv_bwd: max aggregation needs the argmax buffer of the forward pass");
+  EQNN_CHECK_ARG(((uintptr_t)geom & 15) == 0 && ((uintptr_t)xt & 15) == 0 && ((uintptr_t)dxe & 15) == 0,
+                 "tpconv_bwd: geom/xt/dxe must be 16-byte aligned");
+  EQNN_CHECK_ARG(!uidx || (((uintptr_t)w_rows & 15) == 0 && ((uintptr_t)dw_rows & 15) == 0),
+                 "tpconv_bwd: w_rows/dw_rows must be 16-byte aligned");
+  if (n_nodes <= 0) return EQNN_OK;
+  const unsigned grid = (unsigned)((n_nodes + TPC_ROWS - 1) / TPC_ROWS);
+  EQNN_TP_DISPATCH(tp_id, {
+    EQNN_CHECK_ARG(ld_ga >= TP::DLIVE, "tpconv_bwd: ld_ga smaller than live width");
+    EQNN_CHECK_ARG(!uidx || ld_rows == (TP::NLIVE + 3) / 4 * 4, "tpconv_bwd: ld_rows must be NLIVE rounded up to 4");
+    if (agg == 2)
+      tpconv_bwd_kernel<TP, true><<<grid, TPC_THREADS, 0, as_stream(stream)>>>(
+          rowptr, src, perm, reinterpret_cast<const float4*>(geom), w_t, n_edges, xt, n_nodes, agg, gA, ld_ga, dw_t,
+          dxe, argmax, uidx, w_rows, dw_rows);
+    else
+      tpconv_bwd_kernel<TP, false><<<grid, TPC_THREADS, 0, as_stream(stream)>>>(
+          rowptr, src, perm, reinterpret_cast<const float4*>(geom), w_t, n_edges, xt, n_nodes, agg, gA, ld_ga, dw_t,
+          dxe, nullptr, uidx, w_rows, dw_rows);
   });
   EQNN_CHECK_LAUNCH();
   return EQNN_OK;
@@ -380,26 +458,18 @@ extern "C" int eqnn_tpconv_bwd(int tp_id, const int32_t* rowptr, const int32_t* 
                                const float* geom, const float* w_t, int64_t n_edges, const float* xt, int n_nodes,
                                int agg, const float* gA, int ld_ga, float* dw_t, float* dxe,
                                const int32_t* argmax, eqnn_stream_t stream) {
-  EQNN_CHECK_ARG(rowptr && src && perm && geom && w_t && xt && gA && dw_t && dxe, "tpconv_bwd: null pointer");
-  EQNN_CHECK_ARG(agg >= 0 && agg <= 2, "tpconv_bwd: agg must be 0 (sum), 1 (mean) or 2 (max)");
-  EQNN_CHECK_ARG(agg != 2 || argmax, "tpconv_bwd: max aggregation needs the argmax buffer of the forward pass");
-  EQNN_CHECK_ARG(((uintptr_t)geom & 15) == 0 && ((uintptr_t)xt & 15) == 0 && ((uintptr_t)dxe & 15) == 0,
-                 "tpconv_bwd: geom/xt/dxe must be 16-byte aligned");
-  if (n_nodes <= 0) return EQNN_OK;
-  const unsigned grid = (unsigned)((n_nodes + TPC_ROWS - 1) / TPC_ROWS);
-  EQNN_TP_DISPATCH(tp_id, {
-    EQNN_CHECK_ARG(ld_ga >= TP::DLIVE, "tpconv_bwd: ld_ga smaller than live width");
-    if (agg == 2)
-      tpconv_bwd_kernel<TP, true><<<grid, TPC_THREADS, 0, as_stream(stream)>>>(
-          rowptr, src, perm, reinterpret_cast<const float4*>(geom), w_t, n_edges, xt, n_nodes, agg, gA, ld_ga, dw_t,
-          dxe, argmax);
-    else
-      tpconv_bwd_kernel<TP, false><<<grid, TPC_THREADS, 0, as_stream(stream)>>>(
-          rowptr, src, perm, reinterpret_cast<const float4*>(geom), w_t, n_edges, xt, n_nodes, agg, gA, ld_ga, dw_t,
-          dxe, nullptr);
-  });
-  EQNN_CHECK_LAUNCH();
-  return EQNN_OK;
+  EQNN_CHECK_ARG(w_t && dw_t, "tpconv_bwd: null pointer");
+  return tpconv_bwd_impl(tp_id, rowptr, src, perm, geom, w_t, n_edges, nullptr, nullptr, 0, xt, n_nodes, agg, gA, ld_ga, dw_t,
+                         nullptr, dxe, argmax, stream);
+}
+
+extern "C" int eqnn_tpconv_bwd_shared(int tp_id, const int32_t* rowptr, const int32_t* src, const int32_t* perm,
+                                      const float* geom, const int32_t* uidx, const float* w_rows, int ld_rows,
+                                      const float* xt, int n_nodes, int agg, const float* gA, int ld_ga, float* dw_rows,
+                                      float* dxe, const int32_t* argmax, eqnn_stream_t stream) {
+  EQNN_CHECK_ARG(uidx && w_rows && dw_rows, "tpconv_bwd_shared: null pointer");
+  return tpconv_bwd_impl(tp_id, rowptr, src, perm, geom, nullptr, 0, uidx, w_rows, ld_rows, xt, n_nodes, agg, gA, ld_ga, nullptr,
+                         dw_rows, dxe, argmax, stream);
 }
 
 // 128-bit variants (dxp a multiple of 4, 16-byte aligned buffers): one thread per (sender, component quad); the

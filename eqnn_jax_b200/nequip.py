@@ -368,7 +368,8 @@ class PreparedGraph(NamedTuple):
     rowptr_s: torch.Tensor
     perm_s: torch.Tensor
     geom: torch.Tensor
-    radial: torch.Tensor
+    radial: Optional[torch.Tensor]
+    pairs: Optional["ops.EdgePairs"] = None     # shared radial evaluations (NequIP.share_radial)
 
 
 def _mm(M, N, K, alpha, A, a_off, lda, Bm, b_off, ldb, Cm, c_off, ldc, ta=False, tb=False, tc=False, **kw):
@@ -412,6 +413,13 @@ class NequIP:
     # backward pass (1.5 KB per edge and step); "recompute": nothing is kept, the backward recomputes them from d.
     fuse_radial_mlp: bool = True
     radial_mlp_backward: str = "stash"
+    # not a reference field: evaluate the radial MLP once per UNIQUE edge length instead of once per edge.  The MLP sees an
+    # edge only through d = |x_s - x_r| (models/nequip.py:55-68) and the two directions of a reciprocated edge have
+    # bit-identical lengths (85 % of the edges of a kNN-20 graph are reciprocated), so both read one evaluation and their
+    # cotangents are summed before the MLP's backward pass: the same arithmetic on the same numbers, 0.58 of the radial-MLP
+    # work (csrc/pairs.cu).  Applies on the fused stash route (gelu, >= 2 hidden layers, >= 4096 edges); False = one
+    # evaluation per edge.
+    share_radial: bool = True
     # not a reference field: the reference's node task returns the processed GraphsTuple, whose `edges` are the last
     # step's messages (models/nequip.py:154-171); no caller reads them, so they are only computed on request (every message
     # column, un-reduced, (B, E, D_msg) in the reference's edge order; not differentiated through)
@@ -471,8 +479,16 @@ class NequIP:
         rowptr, perm, src = ops.csr_build(senders, receivers, N)
         rowptr_s, perm_s, _ = ops.csr_build(receivers, senders, N)
         arr = arr.contiguous()
-        geom, radial = ops.edge_geom(arr, D, B * N, rowptr, src, self.n_radial_basis, self.r_cutoff)
-        return PreparedGraph(B, N, E, rowptr, perm, src, rowptr_s, perm_s, geom, radial)
+        share = self._share_radial(self.plan(irreps_in, _n_globals_of(graphs)), B * E)
+        geom, radial = ops.edge_geom(arr, D, B * N, rowptr, src, self.n_radial_basis, self.r_cutoff, want_radial=not share)
+        pairs = ops.edge_pairs(rowptr, src, geom, B * N, self.n_radial_basis, self.r_cutoff) if share else None
+        return PreparedGraph(B, N, E, rowptr, perm, src, rowptr_s, perm_s, geom, radial, pairs)
+
+    def _share_radial(self, plan: "_Plan", n_edges: int) -> bool:
+        """One radial-MLP evaluation per unique edge length (share_radial) applies to this model and batch."""
+        return bool(self.share_radial and not self.return_edges and self.activation == "gelu"
+                    and self.radial_mlp_backward == "stash" and n_edges >= 4096 and len(plan.steps) > 0
+                    and len(plan.steps[0]["mlp"]) - 1 >= 2 and _fused_radial_ok(self, plan))
 
     # -- forward / backward -----------------------------------------------------------------
     def apply(self, params: NequIPParams, graphs: GraphsTuple, prepared: Optional[PreparedGraph] = None):
@@ -631,7 +647,14 @@ def _forward(model: NequIP, plan: _Plan, theta: torch.Tensor, pg: PreparedGraph,
         Zs, a, fan_prev, pro = [], pg.radial, plan.n_rad_in, 0
         fused = _fused_radial_ok(model, plan)
         stash = None
-        if fused:
+        if fused and pg.pairs is not None:
+            # one evaluation per unique edge length; the interaction kernel gathers the rows through pg.pairs.uidx
+            w_t = torch.empty((Et, (n_live + 3) // 4 * 4), **f32)
+            if save:
+                stash = ops.radial_mlp_stash(Et, len(st["mlp"]) - 1, dev)
+            ops.radial_mlp_fwd_rows(pg.pairs, model.n_radial_basis, model.r_cutoff, _radial_weights(theta, wexp, st, n_live),
+                                    n_live, plan.inv_c_mlp, w_t, z_stash=stash, activation=model.activation)
+        elif fused:
             w_t = torch.empty((n_live, Et), **f32)
             if save and model.radial_mlp_backward == "stash" and model.activation == "gelu":
                 stash = ops.radial_mlp_stash(Et, len(st["mlp"]) - 1, dev)
@@ -650,7 +673,10 @@ def _forward(model: NequIP, plan: _Plan, theta: torch.Tensor, pg: PreparedGraph,
                 pro=pro, pro_scale=plan.inv_c_act, tag="radial_mlp_fwd", tf32x3=model.tensor_cores)
         A = torch.empty((Nt, d_live), **f32)
         amax = torch.empty((Nt, d_live), dtype=torch.int32, device=dev) if agg == 2 else None   # segment_max winners
-        ops.tpconv_fwd(tp_id, pg.rowptr, pg.src, pg.geom, w_t, xt, Nt, agg, A, d_live, amax)
+        if fused and pg.pairs is not None:
+            ops.tpconv_fwd_shared(tp_id, pg.rowptr, pg.src, pg.geom, pg.pairs, w_t, xt, Nt, agg, A, d_live, amax)
+        else:
+            ops.tpconv_fwd(tp_id, pg.rowptr, pg.src, pg.geom, w_t, xt, Nt, agg, A, d_live, amax)
         z = torch.empty((Nt, plan.d_z), **f32)
         hn = torch.empty((Nt, D), **f32)
         g = None
@@ -797,6 +823,8 @@ def _backward(model: NequIP, plan: _Plan, theta: torch.Tensor, pg: PreparedGraph
 
     dw_t = torch.empty((n_live, Et), **f32)
     dxe = torch.empty((Et, dxp), **f32)
+    shared = pg.pairs is not None and _fused_radial_ok(model, plan)
+    dw_rows = torch.empty((Et, (n_live + 3) // 4 * 4), **f32) if shared else None
     for st, sv in zip(reversed(plan.steps), reversed(saved["steps"])):
         h, xt, Zs, w_t, A, z, g = sv["h"], sv["xt"], sv["Zs"], sv["w_t"], sv["A"], sv["z"], sv["g"]
         # h' = g @ W3
@@ -824,7 +852,11 @@ def _backward(model: NequIP, plan: _Plan, theta: torch.Tensor, pg: PreparedGraph
             else:
                 dh_prev.zero_()
         # interaction block
-        ops.tpconv_bwd(tp_id, pg.rowptr, pg.src, pg.perm, pg.geom, w_t, xt, Nt, agg, dA, d_live, dw_t, dxe, sv["amax"])
+        if shared:
+            ops.tpconv_bwd_shared(tp_id, pg.rowptr, pg.src, pg.perm, pg.geom, pg.pairs, w_t, xt, Nt, agg, dA, d_live,
+                                  dw_rows, dxe, sv["amax"])
+        else:
+            ops.tpconv_bwd(tp_id, pg.rowptr, pg.src, pg.perm, pg.geom, w_t, xt, Nt, agg, dA, d_live, dw_t, dxe, sv["amax"])
         # sender side: dxt = sum over each sender's edges -- right behind the kernel that wrote dxe, while the tail of
         # it is still in L2 (the radial-MLP backward in between streams gigabytes)
         dxt = torch.empty((Nt, dxp), **f32)
@@ -835,7 +867,13 @@ def _backward(model: NequIP, plan: _Plan, theta: torch.Tensor, pg: PreparedGraph
         _, fan, _ = mlp[-1]
         al = 1.0 / math.sqrt(fan)
         fused = _fused_radial_ok(model, plan)
-        if fused:
+        if shared:
+            # cotangents of the two directions of a pair are summed, then one backward pass per unique edge length
+            ops.pair_combine(dw_rows, n_live, pg.pairs, dw_t)
+            ops.radial_mlp_bwd_rows(pg.pairs, model.n_radial_basis, model.r_cutoff, _radial_weights(theta, wexp, st, n_live),
+                                    n_live, plan.inv_c_mlp, dw_t, _radial_weights(gtheta, gwexp, st, n_live),
+                                    z_stash=sv["stash"], activation=model.activation)
+        elif fused:
             ops.radial_mlp_bwd(pg.geom, model.n_radial_basis, model.r_cutoff, _radial_weights(theta, wexp, st, n_live),
                                n_live, plan.inv_c_mlp, dw_t, _radial_weights(gtheta, gwexp, st, n_live),
                                z_stash=sv["stash"], radial=pg.radial if sv["stash"] is not None else None,

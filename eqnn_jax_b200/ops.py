@@ -171,14 +171,53 @@ def csr_build(senders: torch.Tensor, receivers: torch.Tensor, n_nodes_per_graph:
     return rowptr, perm, src
 
 
-def edge_geom(pos: torch.Tensor, ld_pos: int, n_nodes: int, rowptr, src, n_rb: int, r_cut: float):
-    """-> geom [Etot,4] (r_hat, d), radial [Etot, max(n_rb,1)]."""
+def edge_geom(pos: torch.Tensor, ld_pos: int, n_nodes: int, rowptr, src, n_rb: int, r_cut: float, want_radial: bool = True):
+    """-> geom [Etot,4] (r_hat, d), radial [Etot, max(n_rb,1)] (None with want_radial=False)."""
     n_edges = src.numel()
     geom = torch.empty((n_edges, 4), dtype=_F32, device=src.device)
-    radial = torch.empty((n_edges, max(n_rb, 1)), dtype=_F32, device=src.device)
+    radial = torch.empty((n_edges, max(n_rb, 1)), dtype=_F32, device=src.device) if want_radial else None
     check(lib().eqnn_edge_geom(_ptr(pos), ld_pos, n_nodes, _ptr(rowptr), _ptr(src), n_rb, float(r_cut),
                                _ptr(geom), _ptr(radial), _stream()), "edge_geom")
     return geom, radial
+
+
+class EdgePairs:
+    """Unique radial evaluations of a prepared graph (eqnn_edge_pairs): every CSR slot p reads row uidx[p]; row u is
+    represented by slot rep_slot[u] (and its reverse edge rep_partner[u], or -1); d_u / radial_u are the rows' lengths and
+    Bessel bases; n_unique is a DEVICE int32 (the live row count), cap = the edge count sizes every per-row buffer."""
+    __slots__ = ("uidx", "rep_slot", "rep_partner", "d_u", "n_unique", "cap", "radial_u")
+
+    def __init__(self, uidx, rep_slot, rep_partner, d_u, n_unique, cap, radial_u):
+        self.uidx, self.rep_slot, self.rep_partner, self.d_u = uidx, rep_slot, rep_partner, d_u
+        self.n_unique, self.cap, self.radial_u = n_unique, cap, radial_u
+
+
+def edge_pairs(rowptr, src, geom, n_nodes, n_rb: int, r_cut: float) -> EdgePairs:
+    E = src.numel()
+    dev = src.device
+    uidx = torch.empty((E,), dtype=_I32, device=dev)
+    rep_slot = torch.empty((E,), dtype=_I32, device=dev)
+    rep_partner = torch.empty((E,), dtype=_I32, device=dev)
+    d_u = torch.empty((E,), dtype=_F32, device=dev)
+    n_unique = torch.empty((1,), dtype=_I32, device=dev)
+    nbytes = lib().eqnn_edge_pairs_workspace_bytes(n_nodes, E)
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+    check(lib().eqnn_edge_pairs(_ptr(rowptr), _ptr(src), _ptr(geom), n_nodes, E, _ptr(uidx), _ptr(rep_slot),
+                                _ptr(rep_partner), _ptr(d_u), _ptr(n_unique), _ptr(ws), nbytes, _stream()), "edge_pairs")
+    radial_u = None
+    if n_rb > 0:
+        radial_u = torch.empty((E, n_rb), dtype=_F32, device=dev)
+        check(lib().eqnn_bessel_rows(_ptr(d_u), E, _ptr(n_unique), n_rb, float(r_cut), _ptr(radial_u), _stream()),
+              "bessel_rows")
+    return EdgePairs(uidx, rep_slot, rep_partner, d_u, n_unique, E, radial_u)
+
+
+def pair_combine(dw_rows, n_out, pairs: EdgePairs, dw_t):
+    t0 = TIMER.begin() if TIMER else None
+    check(lib().eqnn_pair_combine(_ptr(dw_rows), dw_rows.shape[1], n_out, _ptr(pairs.rep_slot), _ptr(pairs.rep_partner),
+                                  pairs.cap, _ptr(pairs.n_unique), _ptr(dw_t), dw_t.shape[1], _stream()), "pair_combine")
+    if TIMER:
+        TIMER.end("pair_combine", t0)
 
 
 # ---------------------------------------------------------------- interaction block
@@ -198,6 +237,25 @@ def tpconv_bwd(tp_id, rowptr, src, perm, geom, w_t, xt, n_nodes, agg, gA, ld_ga,
     check(lib().eqnn_tpconv_bwd(tp_id, _ptr(rowptr), _ptr(src), _ptr(perm), _ptr(geom), _ptr(w_t), src.numel(),
                                 _ptr(xt), n_nodes, agg, _ptr(gA), ld_ga, _ptr(dw_t), _ptr(dxe), _ptr(argmax), _stream()),
           "tpconv_bwd")
+    if TIMER:
+        TIMER.end("tpconv_bwd", t0)
+
+
+def tpconv_fwd_shared(tp_id, rowptr, src, geom, pairs: EdgePairs, w_rows, xt, n_nodes, agg, out, ld_out, argmax=None):
+    t0 = TIMER.begin() if TIMER else None
+    check(lib().eqnn_tpconv_fwd_shared(tp_id, _ptr(rowptr), _ptr(src), _ptr(geom), _ptr(pairs.uidx), _ptr(w_rows),
+                                       w_rows.shape[1], _ptr(xt), n_nodes, agg, _ptr(out), ld_out, _ptr(argmax), _stream()),
+          "tpconv_fwd_shared")
+    if TIMER:
+        TIMER.end("tpconv_fwd", t0)
+
+
+def tpconv_bwd_shared(tp_id, rowptr, src, perm, geom, pairs: EdgePairs, w_rows, xt, n_nodes, agg, gA, ld_ga, dw_rows, dxe,
+                      argmax=None):
+    t0 = TIMER.begin() if TIMER else None
+    check(lib().eqnn_tpconv_bwd_shared(tp_id, _ptr(rowptr), _ptr(src), _ptr(perm), _ptr(geom), _ptr(pairs.uidx),
+                                       _ptr(w_rows), w_rows.shape[1], _ptr(xt), n_nodes, agg, _ptr(gA), ld_ga,
+                                       _ptr(dw_rows), _ptr(dxe), _ptr(argmax), _stream()), "tpconv_bwd_shared")
     if TIMER:
         TIMER.end("tpconv_bwd", t0)
 
@@ -301,6 +359,17 @@ def radial_mlp_fwd(geom, n_rb, r_cut, weights, n_out, act_scale, w_t, z_stash=No
         TIMER.end("radial_mlp_fwd", t0)
 
 
+def radial_mlp_fwd_rows(pairs: EdgePairs, n_rb, r_cut, weights, n_out, act_scale, w_rows, z_stash=None, activation="gelu"):
+    """The radial MLP once per unique edge length: pairs.d_u [cap] -> w_rows [cap, n_out rounded up to 4] (row-major)."""
+    ptrs, lds = _weight_ptrs(weights)
+    t0 = TIMER.begin() if TIMER else None
+    check(lib().eqnn_radial_mlp_fwd_rows(_ptr(pairs.d_u), 1, pairs.cap, _ptr(pairs.n_unique), n_rb, float(r_cut),
+                                         len(weights) - 1, 128, ptrs, lds, n_out, ACT[activation], float(act_scale), None, 0,
+                                         _ptr(w_rows), w_rows.shape[1], _ptr(z_stash), _stream()), "radial_mlp_fwd_rows")
+    if TIMER:
+        TIMER.end("radial_mlp_fwd", t0)
+
+
 _RMLP_WS = GemmWorkspace()
 
 
@@ -318,6 +387,23 @@ def radial_mlp_bwd(geom, n_rb, r_cut, weights, n_out, act_scale, dw_t, grad_weig
     check(lib().eqnn_radial_mlp_bwd(C.c_void_p(geom.data_ptr() + 12), 4, E, n_rb, float(r_cut), len(weights) - 1, 128,
                                     ptrs, lds, n_out, ACT[activation], float(act_scale), _ptr(dw_t), dw_t.shape[1],
                                     _ptr(z_stash), _ptr(radial), gptrs, ws, ws_bytes, _stream()), "radial_mlp_bwd")
+    if TIMER:
+        TIMER.end("radial_mlp_bwd", t0)
+
+
+def radial_mlp_bwd_rows(pairs: EdgePairs, n_rb, r_cut, weights, n_out, act_scale, dw_t, grad_weights, z_stash,
+                        activation="gelu"):
+    """Weight gradients from the per-row cotangents dw_t [n_out, cap] (eqnn_pair_combine) and the forward stash."""
+    ptrs, lds = _weight_ptrs(weights)
+    gptrs, glds = _weight_ptrs(grad_weights)
+    assert list(lds) == list(glds)
+    need = lib().eqnn_radial_mlp_bwd_workspace_bytes(pairs.cap, n_rb, len(weights) - 1)
+    ws, ws_bytes = _RMLP_WS.get(need, dw_t.device)
+    t0 = TIMER.begin() if TIMER else None
+    check(lib().eqnn_radial_mlp_bwd_rows(_ptr(pairs.d_u), 1, pairs.cap, _ptr(pairs.n_unique), n_rb, float(r_cut),
+                                         len(weights) - 1, 128, ptrs, lds, n_out, ACT[activation], float(act_scale),
+                                         _ptr(dw_t), dw_t.shape[1], _ptr(z_stash), _ptr(pairs.radial_u), gptrs, ws, ws_bytes,
+                                         _stream()), "radial_mlp_bwd_rows")
     if TIMER:
         TIMER.end("radial_mlp_bwd", t0)
 

@@ -430,6 +430,54 @@ int eqnn_radial_mlp_fwd(const float* dist, int64_t dist_stride, int64_t n_edges,
  * gelu'(z_H) (opaque blocked layout; 512 bytes per edge and matrix, n_hidden + 1 matrices). */
 size_t eqnn_radial_mlp_stash_bytes(int64_t n_edges, int n_hidden);
 
+/* ---- shared radial evaluations ----------------------------------------------------------
+ * The radial MLP (models/nequip.py:55-68) sees an edge only through its length d, and the two directions of a
+ * reciprocated edge have bit-identical lengths in fp32 (x_s - x_r is exactly antisymmetric; 85 % of the edges of a
+ * kNN-20 graph are reciprocated).  eqnn_edge_pairs finds those pairs on the receiver-sorted CSR and numbers the unique
+ * evaluations (a pair's smaller CSR slot represents it; unpaired slots -- self-loops, one-directional edges, reverse
+ * edges whose lengths differ in any bit -- represent themselves).  The MLP is then evaluated once per unique row
+ * (eqnn_radial_mlp_fwd_rows), the interaction kernels read the rows through the map (eqnn_tpconv_*_shared), and the
+ * cotangents of a pair are summed before the MLP's backward pass (eqnn_pair_combine; that pass is linear in dL/dw for a
+ * fixed d).  Same arithmetic on the same numbers per edge: the forward result is bit-identical to the per-edge evaluation.
+ * The unique count stays in device memory (n_unique): consumers take the capacity n_edges as their launch bound and read
+ * the live count from that word -- no host synchronisation, CUDA-graph capturable.
+ *   uidx        [n_edges] unique row of every CSR slot          rep_slot    [n_edges cap] CSR slot of row u's representative
+ *   rep_partner [n_edges cap] its partner slot or -1            d_u         [n_edges cap] edge length of row u
+ *   n_unique    [1] int32                                       ws: eqnn_edge_pairs_workspace_bytes                       */
+size_t eqnn_edge_pairs_workspace_bytes(int n_nodes, int64_t n_edges);
+int eqnn_edge_pairs(const int32_t* rowptr, const int32_t* src, const float* geom, int n_nodes, int64_t n_edges, int32_t* uidx,
+                    int32_t* rep_slot, int32_t* rep_partner, float* d_u, int32_t* n_unique, void* ws, size_t ws_bytes,
+                    eqnn_stream_t stream);
+/* dw_t[c][u] = dw_rows[rep_slot[u]][c] + dw_rows[rep_partner[u]][c] for u < *n_unique (dw_rows: [n_edges][ld_rows] records
+ * written by eqnn_tpconv_bwd_shared; dw_t: [n_out][ld_dwt] column-major, the layout eqnn_radial_mlp_bwd_rows reads) */
+int eqnn_pair_combine(const float* dw_rows, int ld_rows, int n_out, const int32_t* rep_slot, const int32_t* rep_partner,
+                      int64_t cap, const int32_t* n_unique, float* dw_t, int64_t ld_dwt, eqnn_stream_t stream);
+/* out [cap][n_rb] = e3nn.bessel(d_rows, n_rb, r_cut) for the first *n_rows rows (reference rounding points, as eqnn_edge_geom) */
+int eqnn_bessel_rows(const float* d_rows, int64_t cap, const int32_t* n_rows, int n_rb, double r_cut, float* out,
+                     eqnn_stream_t stream);
+/* eqnn_radial_mlp_fwd / _bwd over a compact row array whose live count *n_rows (<= n_cap) sits in device memory; n_cap sizes
+ * the buffers, the stash and the launch.  Forward: row-major records w_rows [n_cap][ld_rows] (ld_rows = n_out rounded up to
+ * 4) and / or column-major w_t (either may be NULL).  Backward: the z-stash variant on the fused layer kernels (n_hidden >= 2,
+ * n_cap >= 4096); radial = eqnn_bessel_rows of the same rows. */
+int eqnn_radial_mlp_fwd_rows(const float* dist, int64_t dist_stride, int64_t n_cap, const int32_t* n_rows, int n_rb,
+                             double r_cut, int n_hidden, int d_hidden, const float* const* weights, const int64_t* ldw,
+                             int n_out, int activation, float act_scale, float* w_t, int64_t ld_wt, float* w_rows,
+                             int ld_rows, float* z_stash, eqnn_stream_t stream);
+int eqnn_radial_mlp_bwd_rows(const float* dist, int64_t dist_stride, int64_t n_cap, const int32_t* n_rows, int n_rb,
+                             double r_cut, int n_hidden, int d_hidden, const float* const* weights, const int64_t* ldw,
+                             int n_out, int activation, float act_scale, const float* dw_t, int64_t ld_dwt,
+                             const float* z_stash, const float* radial, float* const* grad_weights, void* ws,
+                             size_t ws_bytes, eqnn_stream_t stream);
+/* eqnn_tpconv_fwd / _bwd with the radial weights of CSR slot p read from w_rows[uidx[p]] (ld_rows = NLIVE rounded up to 4);
+ * the backward writes dL/dw per slot as row-major records dw_rows [n_edges][ld_rows] (eqnn_pair_combine sums the pairs) */
+int eqnn_tpconv_fwd_shared(int tp_id, const int32_t* rowptr, const int32_t* src, const float* geom, const int32_t* uidx,
+                           const float* w_rows, int ld_rows, const float* xt, int n_nodes, int agg, float* A, int ld_a,
+                           int32_t* argmax, eqnn_stream_t stream);
+int eqnn_tpconv_bwd_shared(int tp_id, const int32_t* rowptr, const int32_t* src, const int32_t* perm, const float* geom,
+                           const int32_t* uidx, const float* w_rows, int ld_rows, const float* xt, int n_nodes, int agg,
+                           const float* gA, int ld_ga, float* dw_rows, float* dxe, const int32_t* argmax,
+                           eqnn_stream_t stream);
+
 /* ---- parameter plumbing ----------------------------------------------------------------
  * dst[t] = idx[t] < 0 ? 0 : scale[t] * params[idx[t]]     (Linear -> dense matrix, live columns)
  * grads[pidx[j]] = sum_{t in [ptr[j], ptr[j+1])} scale_t[t] * ddst[tidx[t]]               */

@@ -353,13 +353,14 @@ def _floor32(cfg, tree, g, irreps, cot):
     return val.detach().double().numpy(), p
 
 
-@pytest.mark.parametrize("lmax,N,k,task,backward", [
-    (2, 512, 20, "graph", "stash"),        # cfg-2 model (bench.py MODEL_KW)
-    (2, 512, 20, "graph", "recompute"),
-    (3, 256, 32, "graph", "stash"),        # cfg-5 model
-    (2, 300, 16, "node", "stash"),
+@pytest.mark.parametrize("lmax,N,k,task,backward,share", [
+    (2, 512, 20, "graph", "stash", True),        # cfg-2 model (bench.py MODEL_KW), one radial evaluation per unique edge length
+    (2, 512, 20, "graph", "stash", False),       # ... and one per edge
+    (2, 512, 20, "graph", "recompute", False),
+    (3, 256, 32, "graph", "stash", True),        # cfg-5 model
+    (2, 300, 16, "node", "stash", True),
 ])
-def test_bench_model_on_fused_tensor_core_route(lmax, N, k, task, backward):
+def test_bench_model_on_fused_tensor_core_route(lmax, N, k, task, backward, share):
     import os
     from eqnn_jax_b200 import ops
     from eqnn_jax_b200.nequip import NequIP
@@ -370,7 +371,7 @@ def test_bench_model_on_fused_tensor_core_route(lmax, N, k, task, backward):
     kw = dict(d_hidden=128, l_max=lmax, sphharm_norm="integral", message_passing_steps=4, n_layers=3, n_outputs=2,
               n_radial_basis=64, r_cutoff=0.6, message_passing_agg="mean", task=task)
     cfg, tree, g, model, gg, params = _setup(kw, x, k, seed=7)
-    model = NequIP(**kw, radial_mlp_backward=backward)
+    model = NequIP(**kw, radial_mlp_backward=backward, share_radial=share)
     assert B * N * k >= 4096
     cot = rng.normal(size=(B, N, 7) if task == "node" else (B, 2))
     want, grads = _oracle(cfg, tree, g, IRR, cot)
@@ -383,6 +384,7 @@ def test_bench_model_on_fused_tensor_core_route(lmax, N, k, task, backward):
         ops.TIMER = None
     # the route: one fused radial-MLP kernel per message-passing step and direction, no per-layer radial GEMM
     assert tags.get("radial_mlp_fwd", (0, 0))[0] == 4 and tags.get("radial_mlp_bwd", (0, 0))[0] == 4, tags
+    assert tags.get("pair_combine", (0, 0))[0] == (4 if share else 0), tags      # shared radial evaluations in effect
     got = out.reshape(want.shape).cpu().numpy()
     rows = []
 
@@ -416,7 +418,7 @@ def test_bench_model_on_fused_tensor_core_route(lmax, N, k, task, backward):
             bad.append(nm)
     report = "\n".join(rows)
     os.makedirs("gpurun_out", exist_ok=True)
-    with open(f"gpurun_out/parity_nequip_lmax{lmax}_N{N}_k{k}_{task}_{backward}.txt", "w") as fh:
+    with open(f"gpurun_out/parity_nequip_lmax{lmax}_N{N}_k{k}_{task}_{backward}{'_shared' if share else ''}.txt", "w") as fh:
         fh.write(report + "\n")
     assert not bad, "tensors outside the contract: " + ", ".join(bad) + "\n" + report
 

@@ -1,0 +1,118 @@
+"""GPU parity of the shared radial evaluations (csrc/pairs.cu): the pairing itself is integer work and must match the
+NumPy restatement exactly; the model-level results must not depend on whether the radial MLP (models/nequip.py:55-68)
+is evaluated once per edge or once per unique edge length."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pairs_ref as PR
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev(a, dtype=torch.float32):
+    return torch.as_tensor(np.asarray(a), dtype=dtype).cuda()
+
+
+def _pairs_of(senders, receivers, x, N, n_rb=0):
+    from eqnn_jax_b200 import ops
+    B = x.shape[0]
+    rowptr, perm, src = ops.csr_build(_dev(senders, torch.int32), _dev(receivers, torch.int32), N)
+    geom, _ = ops.edge_geom(_dev(x), x.shape[-1], B * N, rowptr, src, 0, 1.0, want_radial=False)
+    pr = ops.edge_pairs(rowptr, src, geom, B * N, n_rb, 0.6)
+    torch.cuda.synchronize()
+    return rowptr.cpu().numpy(), src.cpu().numpy(), geom.cpu().numpy(), pr
+
+
+def _check_against_restatement(rowptr, src, geom, pr):
+    d = geom[:, 3]
+    uidx, rep_slot, rep_partner = PR.edge_pairs(rowptr, src, d)
+    U = int(pr.n_unique.item())
+    assert U == len(rep_slot)
+    np.testing.assert_array_equal(pr.uidx.cpu().numpy(), uidx)
+    np.testing.assert_array_equal(pr.rep_slot.cpu().numpy()[:U], rep_slot)
+    np.testing.assert_array_equal(pr.rep_partner.cpu().numpy()[:U], rep_partner)
+    du = pr.d_u.cpu().numpy()[:U]
+    # what makes the sharing exact: every slot reads a row whose length is its own length, bit for bit
+    assert np.array_equal(du[uidx].view(np.uint32), d.view(np.uint32))
+    return U
+
+
+@pytest.mark.parametrize("B,N,k", [(1, 5, 5), (2, 64, 8), (3, 300, 20), (1, 1000, 32)])
+def test_pairs_on_knn_graphs_match_restatement(B, N, k):
+    from eqnn_jax_b200 import graph_utils as GU
+    rng = np.random.default_rng(N + k)
+    x = rng.uniform(0.0, 1.0, size=(B, N, 3)).astype(np.float32)
+    g = GU.build_graph(_dev(x), None, k, apply_pbc=None)
+    s = g.senders.reshape(B, -1).cpu().numpy()
+    r = g.receivers.reshape(B, -1).cpu().numpy()
+    rowptr, src, geom, pr = _pairs_of(s, r, x, N)
+    U = _check_against_restatement(rowptr, src, geom, pr)
+    E = B * N * k
+    assert B * N <= U <= E            # self-loops are never shared
+    if N >= 300:
+        assert U < 0.7 * E            # most edges of a kNN graph are reciprocated
+
+
+def test_pairs_on_ragged_graph_with_duplicates_and_one_way_edges():
+    # duplicated edges pair at most once, one-directional edges and self-loops stay alone, an isolated node has an empty row
+    N = 7
+    senders = np.array([[0, 1, 0, 1, 2, 3, 3, 4, 4, 2, 5, 5, 0]], dtype=np.int32)
+    receivers = np.array([[1, 0, 1, 0, 3, 2, 2, 4, 0, 2, 0, 0, 5]], dtype=np.int32)
+    rng = np.random.default_rng(0)
+    x = rng.normal(size=(1, N, 3)).astype(np.float32)
+    rowptr, src, geom, pr = _pairs_of(senders, receivers, x, N)
+    U = _check_against_restatement(rowptr, src, geom, pr)
+    members = np.bincount(pr.uidx.cpu().numpy(), minlength=U)
+    assert members.min() >= 1 and members.max() <= 2
+
+
+def test_bessel_rows_equals_edge_geom_basis():
+    from eqnn_jax_b200 import ops
+    from eqnn_jax_b200 import graph_utils as GU
+    rng = np.random.default_rng(3)
+    B, N, k = 2, 200, 12
+    x = rng.uniform(0.0, 1.0, size=(B, N, 3)).astype(np.float32)
+    g = GU.build_graph(_dev(x), None, k, apply_pbc=None)
+    rowptr, perm, src = ops.csr_build(g.senders.reshape(B, -1).contiguous(), g.receivers.reshape(B, -1).contiguous(), N)
+    geom, radial = ops.edge_geom(_dev(x), 3, B * N, rowptr, src, 64, 0.6)
+    pr = ops.edge_pairs(rowptr, src, geom, B * N, 64, 0.6)
+    U = int(pr.n_unique.item())
+    got = pr.radial_u[:U].cpu().numpy()
+    want = radial.cpu().numpy()[pr.rep_slot[:U].cpu().numpy().astype(np.int64)]
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+@pytest.mark.parametrize("agg", ["mean", "max"])
+def test_shared_radial_evaluation_does_not_change_the_model(agg):
+    """Same inputs, same parameters: forward output bit-identical (the same MLP arithmetic on the same lengths), every
+    gradient equal up to the summation order of the weight gradients (1e-5 of the module's gradient scale)."""
+    from eqnn_jax_b200 import graph_utils as GU
+    from eqnn_jax_b200.nequip import IrrepsArray, NequIP
+    rng = np.random.default_rng(11)
+    B, N, k = 2, 256, 16
+    x = rng.normal(size=(B, N, 7)).astype(np.float32)
+    x[..., :3] = rng.uniform(0.0, 3.0, size=(B, N, 3))
+    kw = dict(d_hidden=128, l_max=2, sphharm_norm="integral", message_passing_steps=2, n_layers=3, n_outputs=2,
+              n_radial_basis=64, r_cutoff=0.6, message_passing_agg=agg, task="graph")
+    xd = _dev(x)
+    g = GU.build_graph(xd, None, k, apply_pbc=GU.get_apply_pbc(np.ones(3, dtype=np.float32), cell=np.eye(3) * 3))
+    gg = g._replace(nodes=IrrepsArray("1o+1o+1x0e", xd), edges=None)
+    cot = _dev(rng.normal(size=(B, 2)))
+    res = {}
+    for share in (False, True):
+        model = NequIP(**kw, share_radial=share)
+        params = model.init(0, gg)
+        pg = model.prepare(gg)
+        assert (pg.pairs is not None) == share
+        out = model.forward_backward(params, gg, lambda o: cot, prepared=pg)
+        res[share] = (out.clone(), params.grad.clone(), params)
+    assert torch.equal(res[False][0], res[True][0]), "forward output must be bit-identical"
+    ga, gb = res[False][1], res[True][1]
+    params = res[True][2]
+    for path, shape, off in params.layout:
+        n = int(np.prod(shape))
+        a, b = ga[off:off + n], gb[off:off + n]
+        # module scale: largest gradient among the tensors that share the first path element
+        mod = max(float(ga[o:o + int(np.prod(sh))].abs().max()) for pth, sh, o in params.layout if pth[0] == path[0])
+        assert float((a - b).abs().max()) <= 1e-5 * max(mod, 1e-30), path
