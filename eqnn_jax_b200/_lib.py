@@ -48,8 +48,9 @@ SIGNATURES: Dict[str, tuple] = {
     "eqnn_radial_mlp_bwd_workspace_bytes": (_sz, [_i64, _i, _i]),
     "eqnn_radial_mlp_bwd": (_i, [_p, _i64, _i64, _i, _d, _i, _i, _p, _p, _i, _i, _f, _p, _i64, _p, _p, _p, _p, _sz, _p]),
     "eqnn_edge_pairs_workspace_bytes": (_sz, [_i, _i64]),
-    "eqnn_edge_pairs": (_i, [_p, _p, _p, _i, _i64, _p, _p, _p, _p, _p, _p, _sz, _p]),
-    "eqnn_pair_combine": (_i, [_p, _i, _i, _p, _p, _i64, _p, _p, _i64, _p]),
+    "eqnn_edge_pairs": (_i, [_p, _p, _p, _i, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "eqnn_pair_combine_workspace_bytes": (_sz, []),
+    "eqnn_pair_combine": (_i, [_p, _i, _i, _p, _p, _p, _p, _i, _i64, _p, _p, _i64, _p, _sz, _p]),
     "eqnn_bessel_rows": (_i, [_p, _i64, _p, _i, _d, _p, _p]),
     "eqnn_radial_mlp_fwd_rows": (_i, [_p, _i64, _i64, _p, _i, _d, _i, _i, _p, _p, _i, _i, _f, _p, _i64, _p, _i, _p, _p]),
     "eqnn_radial_mlp_bwd_rows": (_i, [_p, _i64, _i64, _p, _i, _d, _i, _i, _p, _p, _i, _i, _f, _p, _i64, _p, _p, _p, _p, _sz, _p]),

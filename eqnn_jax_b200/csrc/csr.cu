@@ -73,6 +73,73 @@ __global__ void __launch_bounds__(1024) scan_kernel(const int32_t* __restrict__ 
   if (tid == 0) rowptr[n] = carry_s;
 }
 
+// Multi-CTA scan for long arrays (the single-CTA kernel above takes 190 us for a batch of 160 000 rows: one SM walks the
+// array in ten latency-bound rounds).  Three launches: per-chunk totals (4096 elements per CTA) -> scan of the totals (the
+// kernel above, one round) -> per-chunk exclusive scan + offset.  Same results (integer sums).
+constexpr int SCAN_CHUNK = 256 * SCAN_PER_THREAD;
+__device__ __forceinline__ void scan_load16(const int32_t* __restrict__ count, int64_t n, int64_t i0, int* v) {
+  if (i0 + SCAN_PER_THREAD <= n && (reinterpret_cast<uintptr_t>(count + i0) & 15) == 0) {
+#pragma unroll
+    for (int j = 0; j < SCAN_PER_THREAD / 4; ++j) {
+      const int4 t = __ldg(reinterpret_cast<const int4*>(count + i0) + j);
+      v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < SCAN_PER_THREAD; ++j) v[j] = (i0 + j < n) ? count[i0 + j] : 0;
+  }
+}
+__global__ void __launch_bounds__(256) scan_totals_kernel(const int32_t* __restrict__ count, int64_t n,
+                                                          int32_t* __restrict__ totals) {
+  __shared__ int32_t ws[8];
+  const int tid = threadIdx.x;
+  int v[SCAN_PER_THREAD];
+  scan_load16(count, n, (int64_t)blockIdx.x * SCAN_CHUNK + (int64_t)tid * SCAN_PER_THREAD, v);
+  int tot = 0;
+#pragma unroll
+  for (int j = 0; j < SCAN_PER_THREAD; ++j) tot += v[j];
+  tot = __reduce_add_sync(0xffffffffu, tot);
+  if ((tid & 31) == 0) ws[tid >> 5] = tot;
+  __syncthreads();
+  if (tid == 0) {
+    int t = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += ws[w];
+    totals[blockIdx.x] = t;
+  }
+}
+__global__ void __launch_bounds__(256) scan_apply_kernel(const int32_t* __restrict__ count, int64_t n,
+                                                         const int32_t* __restrict__ offs, int n_chunks,
+                                                         int32_t* __restrict__ rowptr, int32_t* __restrict__ cursor) {
+  __shared__ int32_t ws[8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t i0 = (int64_t)blockIdx.x * SCAN_CHUNK + (int64_t)tid * SCAN_PER_THREAD;
+  int v[SCAN_PER_THREAD];
+  scan_load16(count, n, i0, v);
+  int tot = 0;
+#pragma unroll
+  for (int j = 0; j < SCAN_PER_THREAD; ++j) tot += v[j];
+  int incl = tot;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) ws[warp] = incl;
+  __syncthreads();
+  int excl = offs[blockIdx.x] + incl - tot;
+  for (int w = 0; w < warp; ++w) excl += ws[w];
+#pragma unroll
+  for (int j = 0; j < SCAN_PER_THREAD; ++j) {
+    if (i0 + j < n) {
+      rowptr[i0 + j] = excl;
+      if (cursor) cursor[i0 + j] = excl;
+    }
+    excl += v[j];
+  }
+  if (blockIdx.x == 0 && tid == 0) rowptr[n] = offs[n_chunks];
+}
+
 __global__ void fill_kernel(const int32_t* __restrict__ recv, int64_t n_edges, int E, int N,
                             int32_t* __restrict__ cursor, int32_t* __restrict__ perm) {
   int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -202,15 +269,27 @@ extern "C" int eqnn_exclusive_scan_i32(const int32_t* count, int64_t n, int32_t*
   return EQNN_OK;
 }
 
-// the same scan for other translation units (pairs.cu): out[0..n] from count[0..n)
-int eqnn_scan_rows_i32(const int32_t* count, int64_t n, int32_t* out, cudaStream_t st) {
-  scan_kernel<<<1, 1024, 0, st>>>(count, n, out, nullptr);
-  EQNN_CHECK_LAUNCH();
+// out[0..n] = exclusive scan of count[0..n) (+ a copy in cursor); scratch: eqnn_scan_scratch_bytes(n), 4-byte aligned.
+// Long arrays take the multi-CTA route; also used by other translation units (pairs.cu).
+size_t eqnn_scan_scratch_bytes(int64_t n) { return align_up((size_t)(ceil_div64(n, SCAN_CHUNK) + 1) * 2 * 4, 256); }
+int eqnn_scan_rows_i32(const int32_t* count, int64_t n, int32_t* out, int32_t* cursor, void* scratch, cudaStream_t st) {
+  const int64_t n_chunks = ceil_div64(n, SCAN_CHUNK);
+  if (!scratch || n_chunks < 4 || n_chunks > 1024 * SCAN_PER_THREAD * 64) {
+    scan_kernel<<<1, 1024, 0, st>>>(count, n, out, cursor);
+    EQNN_CHECK_LAUNCH();
+    return EQNN_OK;
+  }
+  int32_t* totals = reinterpret_cast<int32_t*>(scratch);
+  int32_t* offs = totals + n_chunks;
+  scan_totals_kernel<<<(unsigned)n_chunks, 256, 0, st>>>(count, n, totals);
+  scan_kernel<<<1, 1024, 0, st>>>(totals, n_chunks, offs, nullptr);
+  scan_apply_kernel<<<(unsigned)n_chunks, 256, 0, st>>>(count, n, offs, (int)n_chunks, out, cursor);
+  EQNN_CHECK_LAUNCH_N(3);
   return EQNN_OK;
 }
 
 extern "C" size_t eqnn_csr_workspace_bytes(int B, int N, int E) {
-  return align_up(((size_t)B * N + 1) * 4, 256) * 2 + align_up((size_t)B * E * 4, 256);
+  return align_up(((size_t)B * N + 1) * 4, 256) * 2 + align_up((size_t)B * E * 4, 256) + eqnn_scan_scratch_bytes((int64_t)B * N);
 }
 
 extern "C" int eqnn_csr_build(const int32_t* senders, const int32_t* receivers, int B, int N, int E,
@@ -228,13 +307,17 @@ extern "C" int eqnn_csr_build(const int32_t* senders, const int32_t* receivers, 
   int32_t* perm_tmp = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(ws) + 2 * seg);
   EQNN_CUDA(cudaMemsetAsync(count, 0, (n_rows + 1) * 4, st));
   if (n_edges > 0) hist_kernel<<<(unsigned)ceil_div64(n_edges, 256), 256, 0, st>>>(receivers, n_edges, E, N, count);
-  scan_kernel<<<1, 1024, 0, st>>>(count, n_rows, rowptr, cursor);
+  void* scan_scratch = reinterpret_cast<char*>(ws) + 2 * seg + align_up((size_t)n_edges * 4, 256);
+  {
+    const int rc = eqnn_scan_rows_i32(count, n_rows, rowptr, cursor, scan_scratch, st);
+    if (rc) return rc;
+  }
   if (n_edges > 0) {
     fill_kernel<<<(unsigned)ceil_div64(n_edges, 256), 256, 0, st>>>(receivers, n_edges, E, N, cursor, perm);
     rowsort_kernel<<<(unsigned)ceil_div64(n_rows * 32, 256), 256, 0, st>>>(rowptr, n_rows, senders, E, N, perm,
                                                                          perm_tmp, src);
   }
-  EQNN_CHECK_LAUNCH_N(n_edges > 0 ? 4 : 1);
+  EQNN_CHECK_LAUNCH_N(n_edges > 0 ? 3 : 0);
   return EQNN_OK;
 }
 

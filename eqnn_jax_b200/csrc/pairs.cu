@@ -13,7 +13,7 @@
 //                  pair's representative; every unpaired slot (self-loops, one-directional edges) represents itself.
 //   scan           exclusive scan of the representatives per row (csr.cu's scan) -> numbering in CSR order
 //   pair_number    u = position of the representative: uidx[p], rep_slot[u], rep_partner[u], d_u[u]; *n_unique
-//   pair_follow    uidx of the non-representatives = uidx of their partner
+//   pair_follow    uidx of the non-representatives = uidx of their partner (zero class: of its first member)
 //   pair_combine   dL/dw of a shared evaluation = sum over its (one or two) member edges, row-major records in,
 //                  column-major [n_out][ld] out (what eqnn_radial_mlp_bwd reads)
 //   bessel_rows    e3nn.bessel of the unique lengths (first radial layer's weight-gradient operand)
@@ -29,22 +29,32 @@ __device__ __forceinline__ int first_slot_with_sender(const int32_t* __restrict_
   return -1;
 }
 
+// partner[p]: >= 0 the reverse edge's slot; -1 unpaired; -2 member of the ZERO CLASS -- a self-loop (s == r) of length
+// +0.0: every node of a kNN graph has one (graph_utils.py:67, self is neighbour 0), all with the same length, so all of
+// them share ONE evaluation (5 % of the edges at k = 20).  Its representative is the smallest such slot (atomicMin: the
+// result does not depend on the order of the updates).
 __global__ void __launch_bounds__(256) pair_find_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src,
                                                         const float4* __restrict__ geom, int n_nodes,
-                                                        int32_t* __restrict__ partner, int32_t* __restrict__ rowcount) {
+                                                        int32_t* __restrict__ partner, int32_t* __restrict__ zero_slot,
+                                                        int32_t* __restrict__ zero_first) {
   const int lane = threadIdx.x & 31;
   const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= n_nodes) return;
   const int r = (int)row;
   const int p0 = rowptr[r], p1 = rowptr[r + 1];
-  int reps = 0;
+  int zs = -1;
   for (int base = p0; base < p1; base += 32) {
     const int p = base + lane;
-    bool is_rep = false;
+    bool zero = false;
     if (p < p1) {
       const int s = __ldg(src + p);
       int q = -1;
-      if (s != r && s >= 0 && s < n_nodes) {
+      if (s == r) {
+        if (__float_as_uint(geom[p].w) == 0u && first_slot_with_sender(src, p0, p1, r) == p) {
+          q = -2;
+          zero = true;
+        }
+      } else if (s >= 0 && s < n_nodes) {
         q = first_slot_with_sender(src, rowptr[s], rowptr[s + 1], r);
         if (q >= 0) {
           const bool mutual = first_slot_with_sender(src, p0, p1, s) == p;
@@ -53,28 +63,51 @@ __global__ void __launch_bounds__(256) pair_find_kernel(const int32_t* __restric
         }
       }
       partner[p] = q;
-      is_rep = q < 0 || p < q;
     }
-    reps += __popc(__ballot_sync(0xffffffffu, is_rep));
+    const unsigned m = __ballot_sync(0xffffffffu, zero);
+    if (m && zs < 0) zs = base + __ffs(m) - 1;
   }
-  if (lane == 0) rowcount[r] = reps;
+  if (lane == 0) {
+    zero_slot[r] = zs;
+    if (zs >= 0) atomicMin(zero_first, zs);
+  }
+}
+
+__device__ __forceinline__ bool pair_is_rep(int p, int q, int zero_first) {
+  return q == -1 || (q >= 0 && p < q) || (q == -2 && p == zero_first);
+}
+
+__global__ void __launch_bounds__(256) pair_count_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ partner,
+                                                         const int32_t* __restrict__ zero_first, int n_nodes,
+                                                         int32_t* __restrict__ rowcount) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= n_nodes) return;
+  const int p0 = rowptr[row], p1 = rowptr[row + 1], zf = *zero_first;
+  int reps = 0;
+  for (int base = p0; base < p1; base += 32) {
+    const int p = base + lane;
+    reps += __popc(__ballot_sync(0xffffffffu, p < p1 && pair_is_rep(p, partner[p < p1 ? p : p0], zf)));
+  }
+  if (lane == 0) rowcount[row] = reps;
 }
 
 __global__ void __launch_bounds__(256) pair_number_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ urow,
                                                           const int32_t* __restrict__ partner, const float4* __restrict__ geom,
-                                                          int n_nodes, int32_t* __restrict__ uidx, int32_t* __restrict__ rep_slot,
+                                                          const int32_t* __restrict__ zero_first, int n_nodes,
+                                                          int32_t* __restrict__ uidx, int32_t* __restrict__ rep_slot,
                                                           int32_t* __restrict__ rep_partner, float* __restrict__ d_u,
-                                                          int32_t* __restrict__ n_unique) {
+                                                          int32_t* __restrict__ n_unique, int32_t* __restrict__ zero_row) {
   const int lane = threadIdx.x & 31;
   const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= n_nodes) return;
   if (row == 0 && lane == 0) *n_unique = urow[n_nodes];
-  const int p0 = rowptr[row], p1 = rowptr[row + 1];
+  const int p0 = rowptr[row], p1 = rowptr[row + 1], zf = *zero_first;
   int u0 = urow[row];
   for (int base = p0; base < p1; base += 32) {
     const int p = base + lane;
     const int q = p < p1 ? partner[p] : 0;
-    const bool is_rep = p < p1 && (q < 0 || p < q);
+    const bool is_rep = p < p1 && pair_is_rep(p, q, zf);
     const unsigned m = __ballot_sync(0xffffffffu, is_rep);
     if (is_rep) {
       const int u = u0 + __popc(m & ((1u << lane) - 1u));
@@ -82,16 +115,65 @@ __global__ void __launch_bounds__(256) pair_number_kernel(const int32_t* __restr
       rep_slot[u] = p;
       rep_partner[u] = q;
       d_u[u] = geom[p].w;
+      if (q == -2) *zero_row = u;
     }
     u0 += __popc(m);
   }
 }
 
-__global__ void pair_follow_kernel(const int32_t* __restrict__ partner, int64_t n_edges, int32_t* __restrict__ uidx) {
+__global__ void pair_follow_kernel(const int32_t* __restrict__ partner, const int32_t* __restrict__ zero_first, int64_t n_edges,
+                                   int32_t* __restrict__ uidx) {
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n_edges) return;
   const int q = partner[p];
-  if (q >= 0 && q < p) uidx[p] = uidx[q];     // q is a representative: written by pair_number_kernel, never here
+  // the slots read here are representatives: written by pair_number_kernel, never by this kernel
+  if (q >= 0 && q < p) uidx[p] = uidx[q];
+  else if (q == -2 && p != *zero_first) uidx[p] = uidx[*zero_first];
+}
+
+// dL/dw of the zero class = sum over its member slots (one per node): per-CTA sums over a contiguous range of nodes in a
+// fixed order, then the CTA sums in CTA order -- deterministic
+constexpr int ZS_BLOCKS = 128;
+template <int NQ>
+__global__ void __launch_bounds__(256) zero_sum_kernel(const float4* __restrict__ dw_rows, const int32_t* __restrict__ zero_slot,
+                                                       int n_nodes, float* __restrict__ partial) {
+  __shared__ float red[256][4 * NQ + 1];
+  const int tid = threadIdx.x;
+  const int per = (n_nodes + gridDim.x - 1) / gridDim.x;
+  const int i0 = blockIdx.x * per, i1 = min(i0 + per, n_nodes);
+  float v[4 * NQ];
+#pragma unroll
+  for (int c = 0; c < 4 * NQ; ++c) v[c] = 0.f;
+  for (int i = i0 + tid; i < i1; i += 256) {
+    const int p = zero_slot[i];
+    if (p >= 0) {
+#pragma unroll
+      for (int j = 0; j < NQ; ++j) {
+        const float4 a = __ldg(dw_rows + (size_t)p * NQ + j);
+        v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w;
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 4 * NQ; ++c) red[tid][c] = v[c];
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (tid < o) {
+#pragma unroll
+      for (int c = 0; c < 4 * NQ; ++c) red[tid][c] += red[tid + o][c];
+    }
+    __syncthreads();
+  }
+  if (tid < 4 * NQ) partial[blockIdx.x * 16 + tid] = red[0][tid];
+}
+__global__ void zero_sum_final_kernel(const float* __restrict__ partial, int n_parts, int n_out, const int32_t* __restrict__ zero_row,
+                                      float* __restrict__ dw_t, int64_t ld) {
+  const int c = threadIdx.x;
+  const int u = *zero_row;
+  if (c >= n_out || u < 0) return;
+  float t = 0.f;
+  for (int b = 0; b < n_parts; ++b) t += partial[b * 16 + c];
+  dw_t[(int64_t)c * ld + u] = t;
 }
 
 template <int NQ>
@@ -144,20 +226,23 @@ __global__ void __launch_bounds__(256) bessel_rows_kernel(const float* __restric
 
 }  // namespace
 
-int eqnn_scan_rows_i32(const int32_t* count, int64_t n, int32_t* out, cudaStream_t st);   // csr.cu
+size_t eqnn_scan_scratch_bytes(int64_t n);                                                             // csr.cu
+int eqnn_scan_rows_i32(const int32_t* count, int64_t n, int32_t* out, int32_t* cursor, void* scratch, cudaStream_t st);
 
 extern "C" size_t eqnn_edge_pairs_workspace_bytes(int n_nodes, int64_t n_edges) {
-  return align_up((size_t)n_edges * 4, 256) + 2 * align_up(((size_t)n_nodes + 1) * 4, 256);
+  return align_up((size_t)n_edges * 4, 256) + 2 * align_up(((size_t)n_nodes + 1) * 4, 256) + 256 + eqnn_scan_scratch_bytes(n_nodes);
 }
 
 extern "C" int eqnn_edge_pairs(const int32_t* rowptr, const int32_t* src, const float* geom, int n_nodes, int64_t n_edges,
-                               int32_t* uidx, int32_t* rep_slot, int32_t* rep_partner, float* d_u, int32_t* n_unique,
-                               void* ws, size_t ws_bytes, eqnn_stream_t stream) {
-  EQNN_CHECK_ARG(rowptr && src && geom && uidx && rep_slot && rep_partner && d_u && n_unique, "edge_pairs: null pointer");
+                               int32_t* uidx, int32_t* rep_slot, int32_t* rep_partner, float* d_u, int32_t* zero_slot,
+                               int32_t* n_unique, int32_t* zero_row, void* ws, size_t ws_bytes, eqnn_stream_t stream) {
+  EQNN_CHECK_ARG(rowptr && src && geom && uidx && rep_slot && rep_partner && d_u && zero_slot && n_unique && zero_row,
+                 "edge_pairs: null pointer");
   EQNN_CHECK_ARG(n_nodes >= 0 && n_edges >= 0 && n_edges < ((int64_t)1 << 31), "edge_pairs: bad shape");
   EQNN_CHECK_ARG((reinterpret_cast<uintptr_t>(geom) & 15) == 0, "edge_pairs: geom must be 16-byte aligned");
   EQNN_CHECK_ARG(ws && ws_bytes >= eqnn_edge_pairs_workspace_bytes(n_nodes, n_edges), "edge_pairs: workspace too small");
   cudaStream_t st = as_stream(stream);
+  EQNN_CUDA(cudaMemsetAsync(zero_row, 0xFF, 4, st));          // -1: no zero class
   if (n_nodes == 0 || n_edges == 0) {
     EQNN_CUDA(cudaMemsetAsync(n_unique, 0, 4, st));
     return EQNN_OK;
@@ -168,35 +253,55 @@ extern "C" int eqnn_edge_pairs(const int32_t* rowptr, const int32_t* src, const 
   int32_t* rowcount = reinterpret_cast<int32_t*>(w);
   w += align_up(((size_t)n_nodes + 1) * 4, 256);
   int32_t* urow = reinterpret_cast<int32_t*>(w);
+  w += align_up(((size_t)n_nodes + 1) * 4, 256);
+  int32_t* zero_first = reinterpret_cast<int32_t*>(w);
+  w += 256;
+  void* scan_scratch = w;
   const float4* g4 = reinterpret_cast<const float4*>(geom);
   const unsigned wgrid = (unsigned)ceil_div64((int64_t)n_nodes * 32, 256);
-  pair_find_kernel<<<wgrid, 256, 0, st>>>(rowptr, src, g4, n_nodes, partner, rowcount);
-  EQNN_CHECK_LAUNCH();
-  const int rc = eqnn_scan_rows_i32(rowcount, n_nodes, urow, st);
+  EQNN_CUDA(cudaMemsetAsync(zero_first, 0x7F, 4, st));        // 0x7f7f7f7f: above every slot index
+  pair_find_kernel<<<wgrid, 256, 0, st>>>(rowptr, src, g4, n_nodes, partner, zero_slot, zero_first);
+  pair_count_kernel<<<wgrid, 256, 0, st>>>(rowptr, partner, zero_first, n_nodes, rowcount);
+  EQNN_CHECK_LAUNCH_N(2);
+  const int rc = eqnn_scan_rows_i32(rowcount, n_nodes, urow, nullptr, scan_scratch, st);
   if (rc) return rc;
-  pair_number_kernel<<<wgrid, 256, 0, st>>>(rowptr, urow, partner, g4, n_nodes, uidx, rep_slot, rep_partner, d_u, n_unique);
-  pair_follow_kernel<<<(unsigned)ceil_div64(n_edges, 256), 256, 0, st>>>(partner, n_edges, uidx);
+  pair_number_kernel<<<wgrid, 256, 0, st>>>(rowptr, urow, partner, g4, zero_first, n_nodes, uidx, rep_slot, rep_partner, d_u,
+                                            n_unique, zero_row);
+  pair_follow_kernel<<<(unsigned)ceil_div64(n_edges, 256), 256, 0, st>>>(partner, zero_first, n_edges, uidx);
   EQNN_CHECK_LAUNCH_N(2);
   return EQNN_OK;
 }
 
+extern "C" size_t eqnn_pair_combine_workspace_bytes(void) { return (size_t)ZS_BLOCKS * 16 * sizeof(float); }
+
 extern "C" int eqnn_pair_combine(const float* dw_rows, int ld_rows, int n_out, const int32_t* rep_slot,
-                                 const int32_t* rep_partner, int64_t cap, const int32_t* n_unique, float* dw_t, int64_t ld_dwt,
+                                 const int32_t* rep_partner, const int32_t* zero_slot, const int32_t* zero_row, int n_nodes,
+                                 int64_t cap, const int32_t* n_unique, float* dw_t, int64_t ld_dwt, void* ws, size_t ws_bytes,
                                  eqnn_stream_t stream) {
   EQNN_CHECK_ARG(dw_rows && rep_slot && rep_partner && dw_t, "pair_combine: null pointer");
   EQNN_CHECK_ARG(n_out >= 1 && n_out <= 16 && ld_rows % 4 == 0 && ld_rows >= n_out && ld_rows <= 16, "pair_combine: bad row width");
   EQNN_CHECK_ARG((reinterpret_cast<uintptr_t>(dw_rows) & 15) == 0 && ld_dwt >= cap, "pair_combine: alignment / leading dimension");
+  EQNN_CHECK_ARG(!zero_slot || (zero_row && ws && ws_bytes >= eqnn_pair_combine_workspace_bytes()),
+                 "pair_combine: the zero class needs zero_row and the workspace");
   if (cap <= 0) return EQNN_OK;
   const unsigned grid = (unsigned)ceil_div64(cap, 256);
   const float4* r4 = reinterpret_cast<const float4*>(dw_rows);
   cudaStream_t st = as_stream(stream);
+  float* partial = reinterpret_cast<float*>(ws);
+  const bool zc = zero_slot != nullptr && n_nodes > 0;
+  const int zb = n_nodes < ZS_BLOCKS * 256 ? (n_nodes + 255) / 256 : ZS_BLOCKS;
+#define EQNN_PAIR_COMBINE(NQ)                                                                                          \
+  pair_combine_kernel<NQ><<<grid, 256, 0, st>>>(r4, rep_slot, rep_partner, cap, n_unique, n_out, dw_t, ld_dwt);        \
+  if (zc) zero_sum_kernel<NQ><<<zb, 256, 0, st>>>(r4, zero_slot, n_nodes, partial)
   switch (ld_rows / 4) {
-    case 1: pair_combine_kernel<1><<<grid, 256, 0, st>>>(r4, rep_slot, rep_partner, cap, n_unique, n_out, dw_t, ld_dwt); break;
-    case 2: pair_combine_kernel<2><<<grid, 256, 0, st>>>(r4, rep_slot, rep_partner, cap, n_unique, n_out, dw_t, ld_dwt); break;
-    case 3: pair_combine_kernel<3><<<grid, 256, 0, st>>>(r4, rep_slot, rep_partner, cap, n_unique, n_out, dw_t, ld_dwt); break;
-    default: pair_combine_kernel<4><<<grid, 256, 0, st>>>(r4, rep_slot, rep_partner, cap, n_unique, n_out, dw_t, ld_dwt); break;
+    case 1: EQNN_PAIR_COMBINE(1); break;
+    case 2: EQNN_PAIR_COMBINE(2); break;
+    case 3: EQNN_PAIR_COMBINE(3); break;
+    default: EQNN_PAIR_COMBINE(4); break;
   }
-  EQNN_CHECK_LAUNCH();
+#undef EQNN_PAIR_COMBINE
+  if (zc) zero_sum_final_kernel<<<1, 32, 0, st>>>(partial, zb, n_out, zero_row, dw_t, ld_dwt);
+  EQNN_CHECK_LAUNCH_N(zc ? 3 : 1);
   return EQNN_OK;
 }
 

@@ -183,13 +183,15 @@ def edge_geom(pos: torch.Tensor, ld_pos: int, n_nodes: int, rowptr, src, n_rb: i
 
 class EdgePairs:
     """Unique radial evaluations of a prepared graph (eqnn_edge_pairs): every CSR slot p reads row uidx[p]; row u is
-    represented by slot rep_slot[u] (and its reverse edge rep_partner[u], or -1); d_u / radial_u are the rows' lengths and
-    Bessel bases; n_unique is a DEVICE int32 (the live row count), cap = the edge count sizes every per-row buffer."""
-    __slots__ = ("uidx", "rep_slot", "rep_partner", "d_u", "n_unique", "cap", "radial_u")
+    represented by slot rep_slot[u] (and its reverse edge rep_partner[u], -1 none, -2 the zero class = all self-loops of
+    length 0, one slot per node in zero_slot, row zero_row); d_u / radial_u are the rows' lengths and Bessel bases; n_unique
+    is a DEVICE int32 (the live row count), cap = the edge count sizes every per-row buffer."""
+    __slots__ = ("uidx", "rep_slot", "rep_partner", "d_u", "zero_slot", "n_unique", "zero_row", "cap", "n_nodes", "radial_u")
 
-    def __init__(self, uidx, rep_slot, rep_partner, d_u, n_unique, cap, radial_u):
+    def __init__(self, uidx, rep_slot, rep_partner, d_u, zero_slot, n_unique, zero_row, cap, n_nodes, radial_u):
         self.uidx, self.rep_slot, self.rep_partner, self.d_u = uidx, rep_slot, rep_partner, d_u
-        self.n_unique, self.cap, self.radial_u = n_unique, cap, radial_u
+        self.zero_slot, self.n_unique, self.zero_row = zero_slot, n_unique, zero_row
+        self.cap, self.n_nodes, self.radial_u = cap, n_nodes, radial_u
 
 
 def edge_pairs(rowptr, src, geom, n_nodes, n_rb: int, r_cut: float) -> EdgePairs:
@@ -199,23 +201,34 @@ def edge_pairs(rowptr, src, geom, n_nodes, n_rb: int, r_cut: float) -> EdgePairs
     rep_slot = torch.empty((E,), dtype=_I32, device=dev)
     rep_partner = torch.empty((E,), dtype=_I32, device=dev)
     d_u = torch.empty((E,), dtype=_F32, device=dev)
-    n_unique = torch.empty((1,), dtype=_I32, device=dev)
+    zero_slot = torch.empty((max(n_nodes, 1),), dtype=_I32, device=dev)
+    counts = torch.empty((2,), dtype=_I32, device=dev)
+    n_unique, zero_row = counts[0:1], counts[1:2]
     nbytes = lib().eqnn_edge_pairs_workspace_bytes(n_nodes, E)
     ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
     check(lib().eqnn_edge_pairs(_ptr(rowptr), _ptr(src), _ptr(geom), n_nodes, E, _ptr(uidx), _ptr(rep_slot),
-                                _ptr(rep_partner), _ptr(d_u), _ptr(n_unique), _ptr(ws), nbytes, _stream()), "edge_pairs")
+                                _ptr(rep_partner), _ptr(d_u), _ptr(zero_slot), _ptr(n_unique), _ptr(zero_row), _ptr(ws), nbytes,
+                                _stream()), "edge_pairs")
     radial_u = None
     if n_rb > 0:
         radial_u = torch.empty((E, n_rb), dtype=_F32, device=dev)
         check(lib().eqnn_bessel_rows(_ptr(d_u), E, _ptr(n_unique), n_rb, float(r_cut), _ptr(radial_u), _stream()),
               "bessel_rows")
-    return EdgePairs(uidx, rep_slot, rep_partner, d_u, n_unique, E, radial_u)
+    return EdgePairs(uidx, rep_slot, rep_partner, d_u, zero_slot, n_unique, zero_row, E, n_nodes, radial_u)
+
+
+_PAIR_WS = None
 
 
 def pair_combine(dw_rows, n_out, pairs: EdgePairs, dw_t):
+    global _PAIR_WS
+    if _PAIR_WS is None:
+        _PAIR_WS = GemmWorkspace()
+    ws, ws_bytes = _PAIR_WS.get(lib().eqnn_pair_combine_workspace_bytes(), dw_t.device)
     t0 = TIMER.begin() if TIMER else None
     check(lib().eqnn_pair_combine(_ptr(dw_rows), dw_rows.shape[1], n_out, _ptr(pairs.rep_slot), _ptr(pairs.rep_partner),
-                                  pairs.cap, _ptr(pairs.n_unique), _ptr(dw_t), dw_t.shape[1], _stream()), "pair_combine")
+                                  _ptr(pairs.zero_slot), _ptr(pairs.zero_row), pairs.n_nodes, pairs.cap, _ptr(pairs.n_unique),
+                                  _ptr(dw_t), dw_t.shape[1], ws, ws_bytes, _stream()), "pair_combine")
     if TIMER:
         TIMER.end("pair_combine", t0)
 

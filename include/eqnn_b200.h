@@ -441,17 +441,24 @@ size_t eqnn_radial_mlp_stash_bytes(int64_t n_edges, int n_hidden);
  * fixed d).  Same arithmetic on the same numbers per edge: the forward result is bit-identical to the per-edge evaluation.
  * The unique count stays in device memory (n_unique): consumers take the capacity n_edges as their launch bound and read
  * the live count from that word -- no host synchronisation, CUDA-graph capturable.
+ * Self-loops of length +0.0 (every node of a kNN graph has one: graph_utils.py:67) all share ONE row, the "zero class";
+ * its cotangent is the sum over all of them (eqnn_pair_combine reduces it in a fixed order).
  *   uidx        [n_edges] unique row of every CSR slot          rep_slot    [n_edges cap] CSR slot of row u's representative
- *   rep_partner [n_edges cap] its partner slot or -1            d_u         [n_edges cap] edge length of row u
+ *   rep_partner [n_edges cap] its partner slot, -1 (none) or -2 (zero class)   d_u  [n_edges cap] edge length of row u
+ *   zero_slot   [n_nodes] the row's zero-class slot or -1       zero_row    [1] unique row of the zero class or -1
  *   n_unique    [1] int32                                       ws: eqnn_edge_pairs_workspace_bytes                       */
 size_t eqnn_edge_pairs_workspace_bytes(int n_nodes, int64_t n_edges);
 int eqnn_edge_pairs(const int32_t* rowptr, const int32_t* src, const float* geom, int n_nodes, int64_t n_edges, int32_t* uidx,
-                    int32_t* rep_slot, int32_t* rep_partner, float* d_u, int32_t* n_unique, void* ws, size_t ws_bytes,
-                    eqnn_stream_t stream);
-/* dw_t[c][u] = dw_rows[rep_slot[u]][c] + dw_rows[rep_partner[u]][c] for u < *n_unique (dw_rows: [n_edges][ld_rows] records
- * written by eqnn_tpconv_bwd_shared; dw_t: [n_out][ld_dwt] column-major, the layout eqnn_radial_mlp_bwd_rows reads) */
+                    int32_t* rep_slot, int32_t* rep_partner, float* d_u, int32_t* zero_slot, int32_t* n_unique,
+                    int32_t* zero_row, void* ws, size_t ws_bytes, eqnn_stream_t stream);
+/* dw_t[c][u] = dw_rows[rep_slot[u]][c] + dw_rows[rep_partner[u]][c] for u < *n_unique, and the sum over all zero-class slots
+ * for u = *zero_row (dw_rows: [n_edges][ld_rows] records written by eqnn_tpconv_bwd_shared; dw_t: [n_out][ld_dwt]
+ * column-major, the layout eqnn_radial_mlp_bwd_rows reads); zero_slot / zero_row may be NULL (no zero class); ws:
+ * eqnn_pair_combine_workspace_bytes */
+size_t eqnn_pair_combine_workspace_bytes(void);
 int eqnn_pair_combine(const float* dw_rows, int ld_rows, int n_out, const int32_t* rep_slot, const int32_t* rep_partner,
-                      int64_t cap, const int32_t* n_unique, float* dw_t, int64_t ld_dwt, eqnn_stream_t stream);
+                      const int32_t* zero_slot, const int32_t* zero_row, int n_nodes, int64_t cap, const int32_t* n_unique,
+                      float* dw_t, int64_t ld_dwt, void* ws, size_t ws_bytes, eqnn_stream_t stream);
 /* out [cap][n_rb] = e3nn.bessel(d_rows, n_rb, r_cut) for the first *n_rows rows (reference rounding points, as eqnn_edge_geom) */
 int eqnn_bessel_rows(const float* d_rows, int64_t cap, const int32_t* n_rows, int n_rb, double r_cut, float* out,
                      eqnn_stream_t stream);

@@ -8,7 +8,8 @@ import numpy as np
 
 
 def edge_pairs(rowptr, src, d):
-    """rowptr [n+1], src [E] (global sender per slot), d [E] fp32 lengths -> (uidx [E], rep_slot [U], rep_partner [U])."""
+    """rowptr [n+1], src [E] (global sender per slot), d [E] fp32 lengths ->
+    (uidx [E], rep_slot [U], rep_partner [U] (-1 none, -2 zero class), zero_slot [n], zero_row)."""
     rowptr = np.asarray(rowptr).astype(np.int64)
     src = np.asarray(src).astype(np.int64)
     dbits = np.asarray(d, dtype=np.float32).view(np.uint32)
@@ -22,17 +23,29 @@ def edge_pairs(rowptr, src, d):
         return -1
 
     partner = np.full(E, -1, dtype=np.int64)
+    zero_slot = np.full(n, -1, dtype=np.int64)
     for p in range(E):
         r, s = recv[p], src[p]
         if s == r:
+            # zero class: the row's first self-loop, if its length is +0.0
+            if dbits[p] == 0 and first(r, r) == p:
+                partner[p] = -2
+                zero_slot[r] = p
             continue
         q = first(s, r)
         if q >= 0 and first(r, s) == p and dbits[p] == dbits[q]:
             partner[p] = q
-    is_rep = (partner < 0) | (np.arange(E) < partner)
+    zs = zero_slot[zero_slot >= 0]
+    zero_first = int(zs.min()) if len(zs) else -1
+    idx = np.arange(E)
+    is_rep = (partner == -1) | ((partner >= 0) & (idx < partner)) | ((partner == -2) & (idx == zero_first))
     rep_slot = np.nonzero(is_rep)[0]
     uidx = np.empty(E, dtype=np.int64)
     uidx[rep_slot] = np.arange(len(rep_slot))
-    follow = ~is_rep
+    follow = (~is_rep) & (partner >= 0)
     uidx[follow] = uidx[partner[follow]]
-    return uidx, rep_slot, partner[rep_slot]
+    zfollow = (~is_rep) & (partner == -2)
+    if zero_first >= 0:
+        uidx[zfollow] = uidx[zero_first]
+    zero_row = int(uidx[zero_first]) if zero_first >= 0 else -1
+    return uidx, rep_slot, partner[rep_slot], zero_slot, zero_row
