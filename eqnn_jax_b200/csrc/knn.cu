@@ -278,9 +278,15 @@ knn_cell_kernel(const float4* __restrict__ sorted, const int32_t* __restrict__ s
     }
     const int span = min(2 * Rr + 1, G);                   // cells visited per axis (never the same cell twice)
     const int z0 = (span == G) ? 0 : cz - Rr, y0 = (span == G) ? 0 : cy - Rr, x0 = (span == G) ? 0 : cx - Rr;
-    for (int dz = 0; dz < span; ++dz) {
+    // Rows of cells are visited centre-out (offset 0, +1, -1, +2, ...): the query's own row first, so that the k-th
+    // distance is close to its final value after the first few dozen candidates and far fewer of the later ones pass
+    // the threshold test into the (serial) insertion.  The result does not depend on the order: the list is kept in
+    // (distance, index) order and holds the k smallest of everything visited.
+    for (int iz = 0; iz < span; ++iz) {
+      const int dz = (span == G) ? iz : Rr + ((iz & 1) ? (iz + 1) / 2 : -(iz / 2));
       const int zz = ((z0 + dz) % G + G) % G;
-      for (int dy = 0; dy < span; ++dy) {
+      for (int iy = 0; iy < span; ++iy) {
+        const int dy = (span == G) ? iy : Rr + ((iy & 1) ? (iy + 1) / 2 : -(iy / 2));
         const int yy = ((y0 + dy) % G + G) % G;
         const int rowc = (zz * G + yy) * G;
         // the x-run [x0, x0 + span) modulo G is one or two contiguous slot ranges

@@ -8,6 +8,8 @@
 // CTAs sweep tiles of 16 nodes.  The backward kernel mirrors it and reduces the three weight gradients in
 // per-thread registers -> per-CTA partials -> fixed-order sum (deterministic, no atomics).
 #include "common.cuh"
+#include <stdlib.h>
+#include <type_traits>
 
 namespace {
 
@@ -151,7 +153,43 @@ __device__ __forceinline__ float dot4(const float4& a, const float4& b, float ac
   return fmaf(a.w, b.w, acc);
 }
 
-__global__ void __launch_bounds__(NT, 3) node_fwd_kernel(const NodeP p) {
+// Shape specialisation.  The kernels are written for run-time shapes (any lowered irreps); with every width a run-time
+// value the index arithmetic dominates them (2 400 SASS instructions, 134 of them FFMA: integer divisions, address
+// products, loop control).  For the shapes the benchmarked models produce, the same code is instantiated with the widths
+// as compile-time constants: the kernel copies its parameter block and overwrites the shape fields with the constants,
+// from where the compiler folds strides and divisions and unrolls the loops.  SH = void keeps the run-time shape.
+template <int DA, int DH, int NEXTRA, int NGATES, int MUL0, int DIM0>
+struct NodeShape {
+  static constexpr int d_a = DA, d_h = DH, n_extra = NEXTRA, n_gates = NGATES, mul0 = MUL0, dim0 = DIM0;
+};
+template <class SH>
+__device__ __forceinline__ NodeP specialise(const NodeP& in) {
+  NodeP p = in;
+  if constexpr (!std::is_void<SH>::value) {
+    p.d_a = SH::d_a; p.d_h = SH::d_h; p.n_extra = SH::n_extra; p.n_gates = SH::n_gates;
+    p.n_chunks = 1; p.mul[0] = SH::mul0; p.dim[0] = SH::dim0;
+#pragma unroll
+    for (int c = 1; c < MAX_CH; ++c) { p.mul[c] = 0; p.dim[c] = 1; }
+    p.d_gated = SH::mul0 * SH::dim0;
+    p.d_z = SH::n_extra + SH::n_gates + SH::mul0 * SH::dim0;
+    p.d_g = SH::n_extra + SH::mul0 * SH::dim0;
+  }
+  return p;
+}
+template <class SH>
+bool shape_matches(const NodeP& p) {
+  if constexpr (std::is_void<SH>::value) return true;
+  else return p.d_a == SH::d_a && p.d_h == SH::d_h && p.n_extra == SH::n_extra && p.n_gates == SH::n_gates &&
+              p.n_chunks == 1 && p.mul[0] == SH::mul0 && p.dim[0] == SH::dim0;
+}
+// the interaction blocks of the benchmarked models (bench.py MODEL_KW; messages 0e + 1o = 18 live components, node
+// features 1o + 1o + 0e = 7): l_max 2 -> 88 scalars + 14 gates + 14 x 1o; l_max 3 -> 100 scalars + 10 gates + 10 x 1o
+using ShapeCfg2 = NodeShape<18, 7, 88, 14, 14, 3>;
+using ShapeCfg5 = NodeShape<18, 7, 100, 10, 10, 3>;
+
+template <class SH>
+__global__ void __launch_bounds__(NT, 3) node_fwd_kernel(const NodeP p_in) {
+  const NodeP p = specialise<SH>(p_in);
   extern __shared__ __align__(16) float smem_f[];
   const int d_in = p.d_a + p.d_h, ldw = row4odd(p.d_z);
   Smem s;
@@ -222,7 +260,9 @@ __global__ void __launch_bounds__(NT, 3) node_fwd_kernel(const NodeP p) {
 
 // Backward: given dh_out, produces dA, dh_in (self-connection part) and per-CTA partial weight gradients
 // laid out as [dW12 (d_in x d_z) | dW3 (d_g x d_h)].
-__global__ void __launch_bounds__(NT, 3) node_bwd_kernel(const NodeP p) {
+template <class SH>
+__global__ void __launch_bounds__(NT, 3) node_bwd_kernel(const NodeP p_in) {
+  const NodeP p = specialise<SH>(p_in);
   extern __shared__ __align__(16) float smem_f[];
   const int d_in = p.d_a + p.d_h, ldw = row4odd(p.d_z);
   Smem s;
@@ -437,8 +477,16 @@ extern "C" int eqnn_node_update_fwd(const float* A, int ld_a, int d_a, const flo
   p.W0n = W0n; p.dxp = W0n ? dxp : 0; p.z = z; p.h_out = h_out; p.xt_out = xt_out;
   const size_t smem = smem_floats(p) * sizeof(float);
   EQNN_CHECK_ARG(smem <= 200 * 1024, "node_update_fwd: shared memory budget exceeded");
-  EQNN_CUDA(cudaFuncSetAttribute(node_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  node_fwd_kernel<<<grid_for(n), NT, smem, as_stream(stream)>>>(p);
+#define EQNN_NODE_FWD(SH)                                                                                         \
+  do {                                                                                                            \
+    EQNN_CUDA(cudaFuncSetAttribute(node_fwd_kernel<SH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    node_fwd_kernel<SH><<<grid_for(n), NT, smem, as_stream(stream)>>>(p);                                         \
+  } while (0)
+  const bool generic = getenv("EQNN_NODE_GENERIC") != nullptr;
+  if (!generic && shape_matches<ShapeCfg2>(p)) EQNN_NODE_FWD(ShapeCfg2);
+  else if (!generic && shape_matches<ShapeCfg5>(p)) EQNN_NODE_FWD(ShapeCfg5);
+  else EQNN_NODE_FWD(void);
+#undef EQNN_NODE_FWD
   EQNN_CHECK_LAUNCH();
   return EQNN_OK;
 }
@@ -462,9 +510,17 @@ extern "C" int eqnn_node_update_bwd(const float* A, int ld_a, int d_a, const flo
   p.partial = reinterpret_cast<float*>(ws);
   const size_t smem = smem_floats(p) * sizeof(float);
   EQNN_CHECK_ARG(smem <= 200 * 1024, "node_update_bwd: shared memory budget exceeded");
-  EQNN_CUDA(cudaFuncSetAttribute(node_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaStream_t st = as_stream(stream);
-  node_bwd_kernel<<<grid, NT, smem, st>>>(p);
+#define EQNN_NODE_BWD(SH)                                                                                         \
+  do {                                                                                                            \
+    EQNN_CUDA(cudaFuncSetAttribute(node_bwd_kernel<SH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    node_bwd_kernel<SH><<<grid, NT, smem, st>>>(p);                                                               \
+  } while (0)
+  const bool generic = getenv("EQNN_NODE_GENERIC") != nullptr;
+  if (!generic && shape_matches<ShapeCfg2>(p)) EQNN_NODE_BWD(ShapeCfg2);
+  else if (!generic && shape_matches<ShapeCfg5>(p)) EQNN_NODE_BWD(ShapeCfg5);
+  else EQNN_NODE_BWD(void);
+#undef EQNN_NODE_BWD
   node_wgrad_reduce_kernel<<<(unsigned)((per + 31) / 32), 256, 0, st>>>(p.partial, grid, d_a, d_h, p.d_z, p.d_g,
                                                                         alpha1, dW1, dW2, dW3);
   EQNN_CHECK_LAUNCH_N(2);
