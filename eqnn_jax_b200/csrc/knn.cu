@@ -199,6 +199,13 @@ __device__ __forceinline__ int cell_coord(float x, float ci, int G) {
   return c >= G ? G - 1 : (c < 0 ? 0 : c);
 }
 
+// position of x inside its cell c (cell_coord's arithmetic), in [0, 1]
+__device__ __forceinline__ float cell_frac(float x, float ci, int G, int c) {
+  float u = x * ci;
+  u -= floorf(u);
+  return fminf(fmaxf(u * (float)G - (float)c, 0.f), 1.f);
+}
+
 __global__ void knn_bin_kernel(const float* __restrict__ x, int ldx, int N, Cell cl, Grid g, int32_t* __restrict__ cell_of,
                                int32_t* __restrict__ count) {
   const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -266,6 +273,23 @@ knn_cell_kernel(const float4* __restrict__ sorted, const int32_t* __restrict__ s
   const int qi = __float_as_int(q.w);
   const int cx = cell_coord(q.x, cell.ci[0], G), cy = cell_coord(q.y, cell.ci[4], G), cz = cell_coord(q.z, cell.ci[8], G);
   const int kr = (k - 1) >> 5, kl = (k - 1) & 31;
+  // Distance from the query to the faces of its own cell, per axis and side, less the safety margin: a cell at offset
+  // o != 0 along an axis holds no point closer than (|o| - 1) h + that distance along the axis, so a row of cells (or
+  // the cells at the ends of a row) whose bound already exceeds the current k-th distance cannot change the list.
+  float gap_dn[3], gap_up[3];
+  {
+    const float f[3] = {cell_frac(q.x, cell.ci[0], G, cx), cell_frac(q.y, cell.ci[4], G, cy), cell_frac(q.z, cell.ci[8], G, cz)};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      gap_dn[a] = f[a] * g.h[a] - g.margin[a];
+      gap_up[a] = (1.f - f[a]) * g.h[a] - g.margin[a];
+    }
+  }
+  auto axis_gap = [&](int a, int o) {       // lower bound of |displacement| along axis a to a cell at signed offset o
+    if (o == 0) return 0.f;
+    const float gp = (float)(abs(o) - 1) * g.h[a] + (o > 0 ? gap_up[a] : gap_dn[a]);
+    return fmaxf(gp, 0.f);
+  };
   float ed[R];
   int ej[R];
   for (int Rr = 1;; ++Rr) {
@@ -291,6 +315,24 @@ knn_cell_kernel(const float4* __restrict__ sorted, const int32_t* __restrict__ s
         const int rowc = (zz * G + yy) * G;
         // the x-run [x0, x0 + span) modulo G is one or two contiguous slot ranges
         int xa = ((x0 % G) + G) % G, len = span;
+        if (span != G) {
+          // prune: the whole row, or cells from both ends of it, by the lower bound of the squared distance
+          const float thr_hi = thr * 1.00001f;                 // (inf stays inf: nothing is pruned before k candidates)
+          const float gz = axis_gap(2, dz - Rr), gy = axis_gap(1, dy - Rr);
+          const float rowb = gz * gz + gy * gy;
+          if (rowb > thr_hi) continue;
+          int o_lo = -Rr, o_hi = Rr;
+          while (o_lo < 0) {
+            const float gx = axis_gap(0, o_lo);
+            if (rowb + gx * gx > thr_hi) ++o_lo; else break;
+          }
+          while (o_hi > 0) {
+            const float gx = axis_gap(0, o_hi);
+            if (rowb + gx * gx > thr_hi) --o_hi; else break;
+          }
+          xa = (((x0 + o_lo + Rr) % G) + G) % G;
+          len = o_hi - o_lo + 1;
+        }
         while (len > 0) {
           const int run = min(len, G - xa);
           const int p0 = cs[rowc + xa], p1 = cs[rowc + xa + run];
