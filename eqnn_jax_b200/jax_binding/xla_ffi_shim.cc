@@ -111,6 +111,74 @@ ffi::Error TpconvBwd(cudaStream_t stream, S32 rowptr, S32 src, S32 perm, F32 geo
                                 argmax.element_count() ? argmax.typed_data() : nullptr, stream));
 }
 
+// ---- shared radial evaluations: one radial-MLP evaluation per unique edge length ----
+// counts = [n_unique, zero_row] (two int32 DEVICE words); every per-row result has the edge count as its static capacity
+ffi::Error EdgePairs(cudaStream_t stream, S32 rowptr, S32 src, F32 geom, int32_t n_rb, double r_cut, RS32 uidx, RS32 rep_slot,
+                     RS32 rep_partner, RF32 d_u, RS32 zero_slot, RS32 counts, RF32 radial_u, RU8 ws) {
+  const int n_nodes = (int)rowptr.element_count() - 1;
+  const int64_t n_edges = (int64_t)src.element_count();
+  int rc = eqnn_edge_pairs(rowptr.typed_data(), src.typed_data(), geom.typed_data(), n_nodes, n_edges, uidx->typed_data(),
+                           rep_slot->typed_data(), rep_partner->typed_data(), d_u->typed_data(), zero_slot->typed_data(),
+                           counts->typed_data(), counts->typed_data() + 1, ws->untyped_data(), ws->size_bytes(), stream);
+  if (!rc && n_rb > 0)
+    rc = eqnn_bessel_rows(d_u->typed_data(), n_edges, counts->typed_data(), n_rb, r_cut, radial_u->typed_data(), stream);
+  return status(rc);
+}
+ffi::Error RadialMlpFwdRows(cudaStream_t stream, F32 d_u, S32 counts, F32 w0, F32 w1, F32 w2, F32 wout, int32_t n_hidden,
+                            int32_t n_rb, double r_cut, int32_t activation, float act_scale, RF32 w_rows, RF32 z_stash) {
+  const float* hidden[3] = {w0.typed_data(), w1.typed_data(), w2.typed_data()};
+  const float* W[4];
+  int64_t ldw[4];
+  for (int l = 0; l < n_hidden && l < 3; ++l) { W[l] = hidden[l]; ldw[l] = 128; }
+  W[n_hidden] = wout.typed_data();
+  ldw[n_hidden] = (int64_t)wout.dimensions()[1];
+  return status(eqnn_radial_mlp_fwd_rows(d_u.typed_data(), 1, (int64_t)d_u.element_count(), counts.typed_data(), n_rb, r_cut,
+                                         n_hidden, 128, W, ldw, (int)wout.dimensions()[1], activation, act_scale, nullptr, 0,
+                                         w_rows->typed_data(), (int)w_rows->dimensions()[1],
+                                         z_stash->element_count() ? z_stash->typed_data() : nullptr, stream));
+}
+// dw_rows [n_edges, ld_rows] (from TpconvBwdShared) -> per-row cotangents (scratch result dw_t) -> weight gradients
+ffi::Error RadialMlpBwdRows(cudaStream_t stream, F32 d_u, S32 counts, S32 rep_slot, S32 rep_partner, S32 zero_slot, F32 radial_u,
+                            F32 z_stash, F32 w0, F32 w1, F32 w2, F32 wout, F32 dw_rows, int32_t n_hidden, int32_t n_rb,
+                            double r_cut, int32_t activation, float act_scale, RF32 g0, RF32 g1, RF32 g2, RF32 gout, RF32 dw_t,
+                            RU8 ws_pair, RU8 ws) {
+  const float* hidden[3] = {w0.typed_data(), w1.typed_data(), w2.typed_data()};
+  float* ghidden[3] = {g0->typed_data(), g1->typed_data(), g2->typed_data()};
+  const float* W[4];
+  float* G[4];
+  int64_t ldw[4];
+  for (int l = 0; l < n_hidden && l < 3; ++l) { W[l] = hidden[l]; G[l] = ghidden[l]; ldw[l] = 128; }
+  W[n_hidden] = wout.typed_data();
+  G[n_hidden] = gout->typed_data();
+  const int n_out = (int)wout.dimensions()[1];
+  ldw[n_hidden] = n_out;
+  const int64_t cap = (int64_t)d_u.element_count();
+  int rc = eqnn_pair_combine(dw_rows.typed_data(), (int)dw_rows.dimensions()[1], n_out, rep_slot.typed_data(),
+                             rep_partner.typed_data(), zero_slot.typed_data(), counts.typed_data() + 1,
+                             (int)zero_slot.element_count(), cap, counts.typed_data(), dw_t->typed_data(), cap,
+                             ws_pair->untyped_data(), ws_pair->size_bytes(), stream);
+  if (!rc)
+    rc = eqnn_radial_mlp_bwd_rows(d_u.typed_data(), 1, cap, counts.typed_data(), n_rb, r_cut, n_hidden, 128, W, ldw, n_out,
+                                  activation, act_scale, dw_t->typed_data(), cap, z_stash.typed_data(), radial_u.typed_data(), G,
+                                  ws->untyped_data(), ws->size_bytes(), stream);
+  return status(rc);
+}
+ffi::Error TpconvFwdShared(cudaStream_t stream, S32 rowptr, S32 src, F32 geom, S32 uidx, F32 w_rows, F32 xt, int32_t tp_id,
+                           int32_t agg, RF32 A, RS32 argmax) {
+  return status(eqnn_tpconv_fwd_shared(tp_id, rowptr.typed_data(), src.typed_data(), geom.typed_data(), uidx.typed_data(),
+                                       w_rows.typed_data(), (int)w_rows.dimensions()[1], xt.typed_data(), (int)xt.dimensions()[0],
+                                       agg, A->typed_data(), (int)A->dimensions()[1],
+                                       argmax->element_count() ? argmax->typed_data() : nullptr, stream));
+}
+ffi::Error TpconvBwdShared(cudaStream_t stream, S32 rowptr, S32 src, S32 perm, F32 geom, S32 uidx, F32 w_rows, F32 xt, F32 gA,
+                           S32 argmax, int32_t tp_id, int32_t agg, RF32 dw_rows, RF32 dxe) {
+  return status(eqnn_tpconv_bwd_shared(tp_id, rowptr.typed_data(), src.typed_data(), perm.typed_data(), geom.typed_data(),
+                                       uidx.typed_data(), w_rows.typed_data(), (int)w_rows.dimensions()[1], xt.typed_data(),
+                                       (int)xt.dimensions()[0], agg, gA.typed_data(), (int)gA.dimensions()[1],
+                                       dw_rows->typed_data(), dxe->typed_data(),
+                                       argmax.element_count() ? argmax.typed_data() : nullptr, stream));
+}
+
 // ---- fused node update: Linear + self-connection + gate + re-projection, models/nequip.py:80-90,162 ----
 ffi::Error NodeUpdateFwd(cudaStream_t stream, F32 A, F32 h, F32 W1, F32 W2, F32 W3, float alpha1, int32_t n_extra,
                          int32_t n_gates, ffi::Span<const int32_t> mul, ffi::Span<const int32_t> l, float inv_c_act,
@@ -174,3 +242,24 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(eqnn_node_update_bwd_ffi, NodeUpdateBwd,
                                   .Attr<ffi::Span<const int32_t>>("mul").Attr<ffi::Span<const int32_t>>("l")
                                   .Attr<float>("inv_c_act").Attr<float>("inv_c_gate").Ret<F32>().Ret<F32>().Ret<F32>().Ret<F32>()
                                   .Ret<F32>().Ret<U8>());
+// shared radial evaluations
+XLA_FFI_DEFINE_HANDLER_SYMBOL(eqnn_edge_pairs_ffi, EdgePairs,
+                              ffi::Ffi::Bind().EQNN_STREAM.Arg<S32>().Arg<S32>().Arg<F32>().Attr<int32_t>("n_rb")
+                                  .Attr<double>("r_cut").Ret<S32>().Ret<S32>().Ret<S32>().Ret<F32>().Ret<S32>().Ret<S32>()
+                                  .Ret<F32>().Ret<U8>());
+XLA_FFI_DEFINE_HANDLER_SYMBOL(eqnn_radial_mlp_fwd_rows_ffi, RadialMlpFwdRows,
+                              ffi::Ffi::Bind().EQNN_STREAM.Arg<F32>().Arg<S32>().Arg<F32>().Arg<F32>().Arg<F32>().Arg<F32>()
+                                  .Attr<int32_t>("n_hidden").Attr<int32_t>("n_rb").Attr<double>("r_cut").Attr<int32_t>("activation")
+                                  .Attr<float>("act_scale").Ret<F32>().Ret<F32>());
+XLA_FFI_DEFINE_HANDLER_SYMBOL(eqnn_radial_mlp_bwd_rows_ffi, RadialMlpBwdRows,
+                              ffi::Ffi::Bind().EQNN_STREAM.Arg<F32>().Arg<S32>().Arg<S32>().Arg<S32>().Arg<S32>().Arg<F32>()
+                                  .Arg<F32>().Arg<F32>().Arg<F32>().Arg<F32>().Arg<F32>().Arg<F32>().Attr<int32_t>("n_hidden")
+                                  .Attr<int32_t>("n_rb").Attr<double>("r_cut").Attr<int32_t>("activation").Attr<float>("act_scale")
+                                  .Ret<F32>().Ret<F32>().Ret<F32>().Ret<F32>().Ret<F32>().Ret<U8>().Ret<U8>());
+XLA_FFI_DEFINE_HANDLER_SYMBOL(eqnn_tpconv_fwd_shared_ffi, TpconvFwdShared,
+                              ffi::Ffi::Bind().EQNN_STREAM.Arg<S32>().Arg<S32>().Arg<F32>().Arg<S32>().Arg<F32>().Arg<F32>()
+                                  .Attr<int32_t>("tp_id").Attr<int32_t>("agg").Ret<F32>().Ret<S32>());
+XLA_FFI_DEFINE_HANDLER_SYMBOL(eqnn_tpconv_bwd_shared_ffi, TpconvBwdShared,
+                              ffi::Ffi::Bind().EQNN_STREAM.Arg<S32>().Arg<S32>().Arg<S32>().Arg<F32>().Arg<S32>().Arg<F32>()
+                                  .Arg<F32>().Arg<F32>().Arg<S32>().Attr<int32_t>("tp_id").Attr<int32_t>("agg").Ret<F32>()
+                                  .Ret<F32>());
