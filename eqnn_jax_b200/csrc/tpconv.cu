@@ -19,10 +19,19 @@
 
 namespace {
 
-constexpr int TPC_THREADS = 128;
-constexpr int TPC_ROWS = 6;
+#ifndef TPC_THREADS_N
+#define TPC_THREADS_N 128
+#endif
+#ifndef TPC_ROWS_N
+#define TPC_ROWS_N 6
+#endif
+constexpr int TPC_THREADS = TPC_THREADS_N;
+constexpr int TPC_ROWS = TPC_ROWS_N;
 #ifndef TPC_BWD_MIN_CTAS
 #define TPC_BWD_MIN_CTAS 12
+#endif
+#ifndef TPC_FWD_MIN_CTAS
+#define TPC_FWD_MIN_CTAS 12      // 40 registers, no spills (16 CTAs spill and measured 101 us against 78; without a bound: 48 registers, 10 CTAs / SM)
 #endif
 
 template <class TP>
@@ -73,7 +82,7 @@ __host__ __device__ constexpr int tpc_stride(int dl) {
 }
 
 template <class TP, bool AMAX>
-__global__ void __launch_bounds__(TPC_THREADS)
+__global__ void __launch_bounds__(TPC_THREADS, TPC_FWD_MIN_CTAS)
 tpconv_fwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src,
                   const float4* __restrict__ geom, const float* __restrict__ w_t, int64_t n_edges,
                   const float* __restrict__ xt, int n_nodes, int agg, float* __restrict__ A, int ld_a,
