@@ -51,3 +51,13 @@ __device__ __forceinline__ float gelu_tanh_grad(float x) {
   float du2 = 2.0f * k0 * (1.0f + 3.0f * k1 * x2);
   return s + x * s * (1.0f - s) * du2;
 }
+// gelu and its derivative from ONE sigmoid (one exponential instead of two)
+__device__ __forceinline__ void gelu_tanh_both(float x, float& g, float& gp) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  const float x2 = x * x;
+  const float u2 = 2.0f * k0 * (x + k1 * x * x2);
+  const float s = sigmoid_acc(u2);
+  const float du2 = 2.0f * k0 * (1.0f + 3.0f * k1 * x2);
+  g = x * s;
+  gp = s + x * s * (1.0f - s) * du2;
+}

@@ -58,7 +58,7 @@ __device__ __forceinline__ int gate_of(const NodeP& p, int j) {   // gated compo
 //     [feature][node], so that the 16 nodes of a tile are four broadcast 128-bit loads.
 struct Smem {
   float* W12;   // [d_in][ldw]    rows 0..d_a-1 = alpha1*W1, rows d_a.. = W2, pad columns zero
-  float* W3;    // [d_g][d_h]
+  float* W3;    // [d_g][MAX_DH]  rows padded to 8 floats (zeros): a row is two 128-bit loads
   float* W0n;   // [d_h][dxp]
   float* inT;   // [d_in][TILE]
   float* z;     // [TILE][d_z]
@@ -69,6 +69,8 @@ struct Smem {
   int* gidx;    // [d_gated]      gated component -> gate index
   int* goff;    // [n_gates]      gate -> first gated component
   int* gdim;    // [n_gates]      gate -> number of components it gates
+  float* sgate; // [NT / 32][n_gates]  per-warp sigmoid of the node's gate scalars (evaluated once per gate, not once per
+                //                     gated component)
 };
 
 __host__ __device__ __forceinline__ int row4odd(int n) {   // smallest multiple of 4 >= n whose quarter is odd
@@ -81,13 +83,15 @@ __host__ __device__ __forceinline__ size_t smem_layout(const NodeP& p, Smem* s, 
   const int d_in = p.d_a + p.d_h, ldw = row4odd(p.d_z);
   size_t o = 0;
   auto take = [&](size_t n) { size_t at = o; o += (n + 3) / 4 * 4; return at; };   // keep every array 16-byte aligned
-  const size_t oW12 = take((size_t)d_in * ldw), oW3 = take((size_t)p.d_g * p.d_h);
+  const size_t oW12 = take((size_t)d_in * ldw), oW3 = take((size_t)p.d_g * MAX_DH);
   const size_t oW0 = take((size_t)p.d_h * (p.dxp > 0 ? p.dxp : 1)), oIn = take((size_t)d_in * TILE);
   const size_t oZ = take((size_t)TILE * p.d_z), oG = take((size_t)TILE * p.d_g), oT = take((size_t)MAX_DH * TILE);
   const size_t oDz = take((size_t)TILE * ldw), oDg = take((size_t)TILE * p.d_g);
   const size_t oGi = take(p.d_gated > 0 ? p.d_gated : 1), oGo = take(p.n_gates > 0 ? p.n_gates : 1);
   const size_t oGd = take(p.n_gates > 0 ? p.n_gates : 1);
+  const size_t oSg = take((size_t)(NT / 32) * (p.n_gates > 0 ? p.n_gates : 1));
   if (s) {
+    s->sgate = base + oSg;
     s->W12 = base + oW12; s->W3 = base + oW3; s->W0n = base + oW0; s->inT = base + oIn; s->z = base + oZ;
     s->g = base + oG; s->tT = base + oT; s->dz = base + oDz; s->dg = base + oDg;
     s->gidx = reinterpret_cast<int*>(base + oGi); s->goff = reinterpret_cast<int*>(base + oGo);
@@ -110,7 +114,10 @@ __device__ __forceinline__ void load_weights(const NodeP& p, const Smem& s, int 
     s.W12[i] = v;
   }
   for (int i = threadIdx.x; i < TILE * ldw; i += NT) s.dz[i] = 0.f;
-  for (int i = threadIdx.x; i < p.d_g * p.d_h; i += NT) s.W3[i] = p.W3[i];
+  for (int i = threadIdx.x; i < p.d_g * MAX_DH; i += NT) {
+    const int j = i / MAX_DH, o = i - j * MAX_DH;
+    s.W3[i] = o < p.d_h ? p.W3[j * p.d_h + o] : 0.f;
+  }
   if (p.W0n)
     for (int i = threadIdx.x; i < p.d_h * p.dxp; i += NT) s.W0n[i] = p.W0n[i];
   for (int j = threadIdx.x; j < p.d_gated; j += NT) s.gidx[j] = gate_of(p, j);
@@ -196,7 +203,6 @@ __global__ void __launch_bounds__(NT, 3) node_fwd_kernel(const NodeP p_in) {
   smem_layout(p, &s, smem_f);
   load_weights(p, s, d_in);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int parts = (2 * TILE * p.d_h <= NT) ? 2 : 1;      // lanes sharing one h' element
   const int64_t n_tiles = (p.n + TILE - 1) / TILE;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t n0 = tile * TILE;
@@ -224,28 +230,42 @@ __global__ void __launch_bounds__(NT, 3) node_fwd_kernel(const NodeP p_in) {
     for (int i = tid; i < nn * p.d_z; i += NT) p.z[n0 * p.d_z + i] = s.z[i];
     for (int node = warp; node < TILE; node += NT / 32) {       // warp per node, lanes over components: no divisions
       const float* zr = s.z + node * p.d_z;
-      for (int c = lane; c < p.d_g; c += 32) {
-        float v;
-        if (c < p.n_extra) v = gelu_tanh(zr[c]) * p.inv_c_act;
-        else {
-          const int j = c - p.n_extra;
-          v = sigmoid_acc(zr[p.n_extra + s.gidx[j]]) * p.inv_c_gate * zr[p.n_extra + p.n_gates + j];
-        }
-        s.g[node * p.d_g + c] = v;
-      }
+      float* gr = s.g + node * p.d_g;
+      float* sgw = s.sgate + warp * p.n_gates;
+      for (int gi = lane; gi < p.n_gates; gi += 32) sgw[gi] = sigmoid_acc(zr[p.n_extra + gi]) * p.inv_c_gate;
+      for (int c = lane; c < p.n_extra; c += 32) gr[c] = gelu_tanh(zr[c]) * p.inv_c_act;
+      __syncwarp();
+      for (int j = lane; j < p.d_gated; j += 32) gr[p.n_extra + j] = sgw[s.gidx[j]] * zr[p.n_extra + p.n_gates + j];
+      __syncwarp();                                              // sgw is rewritten for the warp's next node
     }
     __syncthreads();
-    // h'[node][o] = sum_j g[node][j] W3[j][o]: `parts` adjacent lanes split the sum
-    if (tid < parts * TILE * p.d_h) {
-      const int part = tid % parts, idx = tid / parts;
-      const int node = idx / p.d_h, o = idx - node * p.d_h;
+    // h'[node][o] = sum_j g[node][j] W3[j][o]: 16 lanes per node split j, every lane keeps all d_h outputs (one g value
+    // and one padded W3 row -- two 128-bit loads -- per 7 FMAs), then a 4-step shuffle tree over the 16 lanes
+    {
+      constexpr int PARTS = NT / TILE;                           // 16
+      const int node = tid / PARTS, part = tid % PARTS;
       const float* gr = s.g + node * p.d_g;
-      float a = 0.f;
-      for (int j = part; j < p.d_g; j += parts) a = fmaf(gr[j], s.W3[j * p.d_h + o], a);
-      if (parts == 2) a += __shfl_xor_sync(0xffffffffu, a, 1);
-      if (part == 0) {
-        s.tT[o * TILE + node] = a;
-        if (node < nn) p.h_out[(n0 + node) * p.d_h + o] = a;
+      float a[MAX_DH];
+#pragma unroll
+      for (int o = 0; o < MAX_DH; ++o) a[o] = 0.f;
+      for (int j = part; j < p.d_g; j += PARTS) {
+        const float gv = gr[j];
+        const float4 w0 = *reinterpret_cast<const float4*>(s.W3 + j * MAX_DH);
+        const float4 w1 = *reinterpret_cast<const float4*>(s.W3 + j * MAX_DH + 4);
+        a[0] = fmaf(gv, w0.x, a[0]); a[1] = fmaf(gv, w0.y, a[1]); a[2] = fmaf(gv, w0.z, a[2]); a[3] = fmaf(gv, w0.w, a[3]);
+        a[4] = fmaf(gv, w1.x, a[4]); a[5] = fmaf(gv, w1.y, a[5]); a[6] = fmaf(gv, w1.z, a[6]); a[7] = fmaf(gv, w1.w, a[7]);
+      }
+#pragma unroll
+      for (int off = PARTS / 2; off > 0; off >>= 1) {
+#pragma unroll
+        for (int o = 0; o < MAX_DH; ++o) a[o] += __shfl_xor_sync(0xffffffffu, a[o], off);
+      }
+      if (part < p.d_h) {
+        float v = a[0];
+#pragma unroll
+        for (int o = 1; o < MAX_DH; ++o) v = (part == o) ? a[o] : v;
+        s.tT[part * TILE + node] = v;
+        if (node < nn) p.h_out[(n0 + node) * p.d_h + part] = v;
       }
     }
     __syncthreads();
@@ -287,42 +307,51 @@ __global__ void __launch_bounds__(NT, 3) node_bwd_kernel(const NodeP p_in) {
       s.tT[o * TILE + node] = (node < nn && o < p.d_h) ? p.dh_out[(n0 + node) * p.d_h + o] : 0.f;
     }
     __syncthreads();
-    // g (recomputed) and dg[node][j] = sum_o dh_out[node][o] W3[j][o]
+    // g (recomputed), dg[node][j] = sum_o dh_out[node][o] W3[j][o], dz -- one warp per node, no block barrier inside:
+    // gate sigmoids once per gate (per-warp scratch), scalars with one exponential for gelu and gelu', gated components,
+    // then the gate scalars' gradients from the products dg * z the same warp has just stored
     for (int node = warp; node < TILE; node += NT / 32) {       // warp per node, lanes over components
       const float* zr = s.z + node * p.d_z;
+      float* sgw = s.sgate + warp * p.n_gates;
       float dho[MAX_DH];
 #pragma unroll
       for (int o = 0; o < MAX_DH; ++o) dho[o] = s.tT[o * TILE + node];
-      for (int c = lane; c < p.d_g; c += 32) {
-        float dg = 0.f;
-#pragma unroll
-        for (int o = 0; o < MAX_DH; ++o)
-          if (o < p.d_h) dg = fmaf(dho[o], s.W3[c * p.d_h + o], dg);
-        float gv;
-        if (c < p.n_extra) {
-          gv = gelu_tanh(zr[c]) * p.inv_c_act;
-          s.dz[node * ldw + c] = dg * gelu_tanh_grad(zr[c]) * p.inv_c_act;
-        } else {
-          const int j = c - p.n_extra;
-          const float sg = sigmoid_acc(zr[p.n_extra + s.gidx[j]]) * p.inv_c_gate;
-          gv = sg * zr[p.n_extra + p.n_gates + j];
-          s.dz[node * ldw + p.n_extra + p.n_gates + j] = dg * sg;
-        }
-        s.g[node * p.d_g + c] = gv;        // gate output (for dW3)
-        s.dg[node * p.d_g + c] = dg;       // dg (for the gate-scalar gradients)
+      for (int gi = lane; gi < p.n_gates; gi += 32) sgw[gi] = sigmoid_acc(zr[p.n_extra + gi]);
+      for (int c = lane; c < p.n_extra; c += 32) {
+        const float4 w0 = *reinterpret_cast<const float4*>(s.W3 + c * MAX_DH);
+        const float4 w1 = *reinterpret_cast<const float4*>(s.W3 + c * MAX_DH + 4);
+        float dg = dho[0] * w0.x;                                  // (padded W3 columns and dh_out rows are zero)
+        dg = fmaf(dho[1], w0.y, dg); dg = fmaf(dho[2], w0.z, dg); dg = fmaf(dho[3], w0.w, dg);
+        dg = fmaf(dho[4], w1.x, dg); dg = fmaf(dho[5], w1.y, dg); dg = fmaf(dho[6], w1.z, dg); dg = fmaf(dho[7], w1.w, dg);
+        float gv, gp;
+        gelu_tanh_both(zr[c], gv, gp);
+        s.g[node * p.d_g + c] = gv * p.inv_c_act;                // gate output (for dW3)
+        s.dz[node * ldw + c] = dg * gp * p.inv_c_act;
       }
-    }
-    __syncthreads();
-    // gradients of the gate scalars: sum over the components they gate
-    for (int node = warp; node < TILE; node += NT / 32) {
-      const float* zr = s.z + node * p.d_z;
+      __syncwarp();
+      for (int j = lane; j < p.d_gated; j += 32) {
+        const int c = p.n_extra + j;
+        const float4 w0 = *reinterpret_cast<const float4*>(s.W3 + c * MAX_DH);
+        const float4 w1 = *reinterpret_cast<const float4*>(s.W3 + c * MAX_DH + 4);
+        float dg = dho[0] * w0.x;                                  // (padded W3 columns and dh_out rows are zero)
+        dg = fmaf(dho[1], w0.y, dg); dg = fmaf(dho[2], w0.z, dg); dg = fmaf(dho[3], w0.w, dg);
+        dg = fmaf(dho[4], w1.x, dg); dg = fmaf(dho[5], w1.y, dg); dg = fmaf(dho[6], w1.z, dg); dg = fmaf(dho[7], w1.w, dg);
+        const float sg = sgw[s.gidx[j]] * p.inv_c_gate;
+        const float zv = zr[p.n_extra + p.n_gates + j];
+        s.g[node * p.d_g + c] = sg * zv;
+        s.dz[node * ldw + p.n_extra + p.n_gates + j] = dg * sg;
+        s.dg[node * p.d_g + c] = dg * zv;                        // summed per gate below
+      }
+      __syncwarp();
+      // gradients of the gate scalars: sum over the components they gate
       for (int gi = lane; gi < p.n_gates; gi += 32) {
         const int off = s.goff[gi], dim = s.gdim[gi];
         float acc = 0.f;
-        for (int q = 0; q < dim; ++q) acc += s.dg[node * p.d_g + p.n_extra + off + q] * zr[p.n_extra + p.n_gates + off + q];
-        const float sg = sigmoid_acc(zr[p.n_extra + gi]);
+        for (int q = 0; q < dim; ++q) acc += s.dg[node * p.d_g + p.n_extra + off + q];
+        const float sg = sgw[gi];
         s.dz[node * ldw + p.n_extra + gi] = acc * sg * (1.f - sg) * p.inv_c_gate;
       }
+      __syncwarp();                                              // sgw is rewritten for the warp's next node
     }
     __syncthreads();
     // weight gradients (registers): the thread's column of dz for the 16 nodes, then per input feature
