@@ -20,12 +20,23 @@
 // The number of unique evaluations stays ON THE DEVICE (n_unique): every consumer takes the capacity as its launch
 // bound and reads the live count from that word, so the step needs no host synchronisation and replays from a CUDA graph.
 #include "common.cuh"
+#include "rmlp_common.cuh"
 
 namespace {
 
+// first slot of [p0, p1) whose sender is `who`; four loads in flight per step (the rows are ~k long and the loop is a
+// chain of L2 round trips otherwise)
 __device__ __forceinline__ int first_slot_with_sender(const int32_t* __restrict__ src, int p0, int p1, int who) {
-  for (int q = p0; q < p1; ++q)
-    if (__ldg(src + q) == who) return q;
+  for (int q = p0; q < p1; q += 4) {
+    const int a0 = __ldg(src + q);
+    const int a1 = q + 1 < p1 ? __ldg(src + q + 1) : -1;
+    const int a2 = q + 2 < p1 ? __ldg(src + q + 2) : -1;
+    const int a3 = q + 3 < p1 ? __ldg(src + q + 3) : -1;
+    if (a0 == who) return q;
+    if (a1 == who) return q + 1;
+    if (a2 == who) return q + 2;
+    if (a3 == who) return q + 3;
+  }
   return -1;
 }
 
@@ -224,6 +235,28 @@ __global__ void __launch_bounds__(256) bessel_rows_kernel(const float* __restric
   }
 }
 
+// the same basis with the FORWARD kernel's arithmetic (rmlp::bessel16: packed Cody-Waite sine on the fp32-rounded phase,
+// 1e-7 relative to the libm form above): the first radial layer's weight gradient then differentiates exactly what the
+// forward kernel fed to that layer, at a third of the instructions.  Thread = (row, group of 16 basis functions).
+__global__ void __launch_bounds__(256) bessel_rows16_kernel(const float* __restrict__ d_rows, int64_t cap,
+                                                            const int32_t* __restrict__ n_rows, int n_rb, float r_cut,
+                                                            float pref, float* __restrict__ out) {
+  __shared__ float wfreq[64];
+  if (threadIdx.x < n_rb) wfreq[threadIdx.x] = __fdiv_rn(__fmul_rn((float)(threadIdx.x + 1), 3.14159265358979323846f), r_cut);
+  __syncthreads();
+  const int gpr = n_rb / 16;                                   // groups per row
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t n = n_rows ? min((int64_t)*n_rows, cap) : cap;
+  const int64_t e = i / gpr;
+  const int g = (int)(i - e * gpr);
+  if (e >= n) return;
+  float v[16];
+  rmlp::bessel16(wfreq, 16 * g, __ldg(d_rows + e), pref, v);
+  float4* o = reinterpret_cast<float4*>(out + e * n_rb + 16 * g);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+}
+
 }  // namespace
 
 size_t eqnn_scan_scratch_bytes(int64_t n);                                                             // csr.cu
@@ -310,6 +343,13 @@ extern "C" int eqnn_bessel_rows(const float* d_rows, int64_t cap, const int32_t*
   EQNN_CHECK_ARG(d_rows && out && n_rb >= 1 && r_cut > 0.0 && cap >= 0, "bessel_rows: bad argument");
   if (cap == 0) return EQNN_OK;
   const float pref = (float)sqrt(2.0 / r_cut);
+  if ((n_rb == 16 || n_rb == 32 || n_rb == 64) && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    const int64_t threads = cap * (n_rb / 16);
+    bessel_rows16_kernel<<<(unsigned)ceil_div64(threads, 256), 256, 0, as_stream(stream)>>>(d_rows, cap, n_rows, n_rb,
+                                                                                         (float)r_cut, pref, out);
+    EQNN_CHECK_LAUNCH();
+    return EQNN_OK;
+  }
   const int64_t warps = ceil_div64(cap, 8);
   bessel_rows_kernel<<<(unsigned)ceil_div64(warps * 32, 256), 256, 0, as_stream(stream)>>>(d_rows, cap, n_rows, n_rb,
                                                                                          (float)r_cut, pref, out);
