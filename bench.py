@@ -662,7 +662,7 @@ def main():
     mlp_bytes_edge = mlp_bytes * evals_per_edge + ((4 * n_live) + (4 * n_live + 8) * evals_per_edge if evals_per_edge < 1.0 else 0)
     mlp_gbs = E_step * steps_mp * mlp_bytes_edge / (mlp_ms_step * 1e-3) / 1e9 if mlp_ms_step > 0 else float("nan")
     tr = ncu_traffic()
-    tr_mlp = traffic_of(tr, args.workload, ("rmlp_", "tc_wgrad", "tc_rowgemm", "absmax", "wgrad_reduce", "lbwd_reduce"), E_step)
+    tr_mlp = traffic_of(tr, args.workload, ("rmlp_", "tc_wgrad", "tc_rowgemm", "absmax", "wgrad_reduce", "lbwd_reduce", "pair_combine", "zero_sum"), E_step)
     tr_tp = traffic_of(tr, args.workload, ("tpconv_fwd", "tpconv_bwd", "sender_reduce", "segment_gather"), E_step)
     _, ms_tf = per_launch("tpconv_fwd")
     _, ms_tb = per_launch("tpconv_bwd")
