@@ -62,6 +62,7 @@ struct Smem {
   float* W0n;   // [d_h][dxp]
   float* inT;   // [d_in][TILE]
   float* z;     // [TILE][d_z]
+  float* z2;    // [TILE][d_z]    backward only: the other half of the z double buffer (cp.async prefetch of the next tile)
   float* g;     // [TILE][d_g]    gate output
   float* tT;    // [MAX_DH][TILE] h' (forward) / dh_out (backward)
   float* dz;    // [TILE][ldw]    backward only, pad columns zero
@@ -85,13 +86,14 @@ __host__ __device__ __forceinline__ size_t smem_layout(const NodeP& p, Smem* s, 
   auto take = [&](size_t n) { size_t at = o; o += (n + 3) / 4 * 4; return at; };   // keep every array 16-byte aligned
   const size_t oW12 = take((size_t)d_in * ldw), oW3 = take((size_t)p.d_g * MAX_DH);
   const size_t oW0 = take((size_t)p.d_h * (p.dxp > 0 ? p.dxp : 1)), oIn = take((size_t)d_in * TILE);
-  const size_t oZ = take((size_t)TILE * p.d_z), oG = take((size_t)TILE * p.d_g), oT = take((size_t)MAX_DH * TILE);
+  const size_t oZ = take((size_t)TILE * p.d_z), oZ2 = take((size_t)TILE * p.d_z), oG = take((size_t)TILE * p.d_g), oT = take((size_t)MAX_DH * TILE);
   const size_t oDz = take((size_t)TILE * ldw), oDg = take((size_t)TILE * p.d_g);
   const size_t oGi = take(p.d_gated > 0 ? p.d_gated : 1), oGo = take(p.n_gates > 0 ? p.n_gates : 1);
   const size_t oGd = take(p.n_gates > 0 ? p.n_gates : 1);
   const size_t oSg = take((size_t)(NT / 32) * (p.n_gates > 0 ? p.n_gates : 1));
   if (s) {
     s->sgate = base + oSg;
+    s->z2 = base + oZ2;
     s->W12 = base + oW12; s->W3 = base + oW3; s->W0n = base + oW0; s->inT = base + oIn; s->z = base + oZ;
     s->g = base + oG; s->tT = base + oT; s->dz = base + oDz; s->dg = base + oDg;
     s->gidx = reinterpret_cast<int*>(base + oGi); s->goff = reinterpret_cast<int*>(base + oGo);
@@ -135,14 +137,36 @@ __device__ __forceinline__ void load_weights(const NodeP& p, const Smem& s, int 
   }
 }
 
-__device__ __forceinline__ void load_inputs(const NodeP& p, const Smem& s, int d_in, int64_t n0, int nn) {
-  for (int i = threadIdx.x; i < TILE * d_in; i += NT) {
-    const int node = i / d_in, r = i - node * d_in;
+// Inputs of a tile, software-pipelined: the global loads of tile t + 1 are issued at the top of tile t into registers
+// (TILE * d_in <= 512 elements = two per thread) and stored to shared memory at the top of tile t + 1 -- the per-tile
+// chain load -> barrier -> GEMM was 15 % of the forward kernel's samples on the stores that waited for these loads.
+__device__ __forceinline__ void fetch_inputs(const NodeP& p, int d_in, int64_t n0, int nn, float (&pre)[2]) {
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int i = threadIdx.x + k * NT;
     float v = 0.f;
-    if (node < nn) v = (r < p.d_a) ? p.A[(n0 + node) * p.ld_a + r] : p.h[(n0 + node) * p.d_h + (r - p.d_a)];
-    s.inT[r * TILE + node] = v;
+    if (i < TILE * d_in) {
+      const int node = i / d_in, r = i - node * d_in;
+      if (node < nn) v = (r < p.d_a) ? __ldg(p.A + (n0 + node) * p.ld_a + r) : __ldg(p.h + (n0 + node) * p.d_h + (r - p.d_a));
+    }
+    pre[k] = v;
   }
 }
+__device__ __forceinline__ void store_inputs(const Smem& s, int d_in, const float (&pre)[2]) {
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int i = threadIdx.x + k * NT;
+    if (i < TILE * d_in) {
+      const int node = i / d_in, r = i - node * d_in;
+      s.inT[r * TILE + node] = pre[k];
+    }
+  }
+}
+__device__ __forceinline__ void cp_async16_zfill(float* dst_smem, const float* src, int src_bytes) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // the TILE node values of feature row `r` of a transposed operand: broadcast 128-bit loads
 __device__ __forceinline__ void load_tile_row(const float* rowT, float (&v)[TILE]) {
@@ -204,11 +228,18 @@ __global__ void __launch_bounds__(NT, 3) node_fwd_kernel(const NodeP p_in) {
   load_weights(p, s, d_in);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t n_tiles = (p.n + TILE - 1) / TILE;
+  float pre[2];
+  if ((int64_t)blockIdx.x < n_tiles)
+    fetch_inputs(p, d_in, (int64_t)blockIdx.x * TILE, (int)min((int64_t)TILE, p.n - (int64_t)blockIdx.x * TILE), pre);
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t n0 = tile * TILE;
     const int nn = (int)min((int64_t)TILE, p.n - n0);
     __syncthreads();
-    load_inputs(p, s, d_in, n0, nn);
+    store_inputs(s, d_in, pre);
+    if (tile + gridDim.x < n_tiles) {                          // next tile's inputs: in flight across this tile
+      const int64_t m0 = (tile + gridDim.x) * TILE;
+      fetch_inputs(p, d_in, m0, (int)min((int64_t)TILE, p.n - m0), pre);
+    }
     __syncthreads();
     // z[node][c]: thread = column c, 16 nodes in registers; per input feature 1 weight + 4 broadcast loads, 16 FMAs
     if (tid < p.d_z) {
@@ -296,16 +327,37 @@ __global__ void __launch_bounds__(NT, 3) node_bwd_kernel(const NodeP p_in) {
 #pragma unroll
   for (int o = 0; o < MAX_DH; ++o) a3[o] = 0.f;
   const int64_t n_tiles = (p.n + TILE - 1) / TILE;
+  // Software pipeline over tiles: inputs and dh_out of tile t + 1 travel in registers, its z block (TILE * d_z floats,
+  // contiguous and 64-byte aligned in global memory) lands in the other half of a shared-memory double buffer by cp.async
+  // (zero fill past the last node) while tile t is processed.
+  float pre[2], pre_t = 0.f;
+  float* zbuf[2] = {s.z, s.z2};
+  int cur = 0;
+  auto fetch_tile = [&](int64_t t, float* zdst) {
+    const int64_t m0 = t * TILE;
+    const int mn = (int)min((int64_t)TILE, p.n - m0);
+    fetch_inputs(p, d_in, m0, mn, pre);
+    if (tid < TILE * MAX_DH) {
+      const int node = tid / MAX_DH, o = tid - node * MAX_DH;
+      pre_t = (node < mn && o < p.d_h) ? __ldg(p.dh_out + (m0 + node) * p.d_h + o) : 0.f;
+    }
+    const int valid = mn * p.d_z;                              // floats of the block that exist
+    for (int f = tid; f < TILE * p.d_z / 4; f += NT) {
+      const int vf = min(max(valid - 4 * f, 0), 4);
+      cp_async16_zfill(zdst + 4 * f, p.z + m0 * p.d_z + (vf > 0 ? 4 * f : 0), 4 * vf);
+    }
+  };
+  if ((int64_t)blockIdx.x < n_tiles) fetch_tile(blockIdx.x, zbuf[0]);
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t n0 = tile * TILE;
     const int nn = (int)min((int64_t)TILE, p.n - n0);
-    __syncthreads();
-    load_inputs(p, s, d_in, n0, nn);
-    for (int i = tid; i < TILE * p.d_z; i += NT) s.z[i] = (i < nn * p.d_z) ? p.z[n0 * p.d_z + i] : 0.f;
-    for (int i = tid; i < TILE * MAX_DH; i += NT) {
-      const int node = i / MAX_DH, o = i - node * MAX_DH;
-      s.tT[o * TILE + node] = (node < nn && o < p.d_h) ? p.dh_out[(n0 + node) * p.d_h + o] : 0.f;
-    }
+    cp_async_wait_all();
+    __syncthreads();                                           // previous tile's readers are done; this tile's z has landed
+    store_inputs(s, d_in, pre);
+    if (tid < TILE * MAX_DH) s.tT[(tid % MAX_DH) * TILE + tid / MAX_DH] = pre_t;
+    s.z = zbuf[cur];
+    if (tile + gridDim.x < n_tiles) fetch_tile(tile + gridDim.x, zbuf[cur ^ 1]);
+    cur ^= 1;
     __syncthreads();
     // g (recomputed), dg[node][j] = sum_o dh_out[node][o] W3[j][o], dz -- one warp per node, no block barrier inside:
     // gate sigmoids once per gate (per-warp scratch), scalars with one exponential for gelu and gelu', gated components,
@@ -531,6 +583,7 @@ extern "C" int eqnn_node_update_bwd(const float* A, int ld_a, int d_a, const flo
                        inv_c_gate, W3, n);
   if (rc) return rc;
   EQNN_CHECK_ARG(z && dh_out && dA && dh_in && dW1 && dW3 && (dW2 || !W2), "node_update_bwd: null pointer");
+  EQNN_CHECK_ARG((reinterpret_cast<uintptr_t>(z) & 15) == 0, "node_update_bwd: z must be 16-byte aligned");
   if (n <= 0) return EQNN_OK;
   p.z = const_cast<float*>(z); p.dh_out = dh_out; p.dA = dA; p.dh_in = dh_in;
   const int grid = grid_for(n);
