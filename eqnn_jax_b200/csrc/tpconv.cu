@@ -15,6 +15,8 @@
 // edge produces dL/dw_t (coalesced column-major store) and the 32-byte dL/dxt record
 // stored at the original edge id (one full sector per edge).
 #include "common.cuh"
+#include <stdlib.h>
+#include "tc_common.cuh"
 #include "gen/tp_gen.cuh"
 
 namespace {
@@ -34,16 +36,69 @@ constexpr int TPC_ROWS = TPC_ROWS_N;
 #define TPC_FWD_MIN_CTAS 12      // 40 registers, no spills (16 CTAs spill and measured 101 us against 78; without a bound: 48 registers, 10 CTAs / SM)
 #endif
 
+// 32-byte records (sender record xt, shared radial-weight record, per-slot dL/dw and dL/dxt records) move with ONE 256-bit
+// access per lane: the interaction kernels are bound by the L1 data pipe (81 % of its wavefront peak in tpconv_fwd,
+// profiles/r2h_tpconv_node_raw.csv), and two 128-bit accesses to the same 32-byte sector cost two wavefronts.
+// (Buffers are 32-byte aligned: checked on the host.)
 template <class TP>
 __device__ __forceinline__ void load_x(const float* __restrict__ xt, int s, float* x) {
-  const float4* p = reinterpret_cast<const float4*>(xt + (size_t)s * TP::DXP);
+  if constexpr (TP::DXP == 8) {
+    tc::ldg256(xt + (size_t)s * 8, x);
+  } else {
+    const float4* p = reinterpret_cast<const float4*>(xt + (size_t)s * TP::DXP);
 #pragma unroll
-  for (int i = 0; i < TP::DXP / 4; ++i) {
-    float4 v = __ldg(p + i);
-    x[4 * i + 0] = v.x;
-    x[4 * i + 1] = v.y;
-    x[4 * i + 2] = v.z;
-    x[4 * i + 3] = v.w;
+    for (int i = 0; i < TP::DXP / 4; ++i) {
+      float4 v = __ldg(p + i);
+      x[4 * i + 0] = v.x;
+      x[4 * i + 1] = v.y;
+      x[4 * i + 2] = v.z;
+      x[4 * i + 3] = v.w;
+    }
+  }
+}
+// NLIVE values of the row-major record `r` (row stride NLIVE rounded up to 4)
+template <class TP>
+__device__ __forceinline__ void load_w_record(const float* __restrict__ w_rows, int r, float* w) {
+  constexpr int LDR = (TP::NLIVE + 3) / 4 * 4;
+  if constexpr (LDR == 8) {
+    float v[8];
+    tc::ldg256(w_rows + (size_t)r * 8, v);
+#pragma unroll
+    for (int c = 0; c < TP::NLIVE; ++c) w[c] = v[c];
+  } else {
+    const float4* q = reinterpret_cast<const float4*>(w_rows + (size_t)r * LDR);
+#pragma unroll
+    for (int i = 0; i < LDR / 4; ++i) {
+      const float4 v = __ldg(q + i);
+      if (4 * i + 0 < TP::NLIVE) w[4 * i + 0] = v.x;
+      if (4 * i + 1 < TP::NLIVE) w[4 * i + 1] = v.y;
+      if (4 * i + 2 < TP::NLIVE) w[4 * i + 2] = v.z;
+      if (4 * i + 3 < TP::NLIVE) w[4 * i + 3] = v.w;
+    }
+  }
+}
+template <class TP>
+__device__ __forceinline__ void store_dw_record(float* __restrict__ dw_rows, int p, const float* dw) {
+  constexpr int LDR = (TP::NLIVE + 3) / 4 * 4;
+  float dwp[LDR];
+#pragma unroll
+  for (int c = 0; c < LDR; ++c) dwp[c] = c < TP::NLIVE ? dw[c < TP::NLIVE ? c : 0] : 0.f;
+  if constexpr (LDR == 8) {
+    tc::stg256(dw_rows + (size_t)p * 8, dwp);
+  } else {
+    float4* dr = reinterpret_cast<float4*>(dw_rows + (size_t)p * LDR);
+#pragma unroll
+    for (int i = 0; i < LDR / 4; ++i) dr[i] = make_float4(dwp[4 * i], dwp[4 * i + 1], dwp[4 * i + 2], dwp[4 * i + 3]);
+  }
+}
+template <class TP>
+__device__ __forceinline__ void store_dx_record(float* __restrict__ dxe, int e, const float* dx) {
+  if constexpr (TP::DXP == 8) {
+    tc::stg256(dxe + (size_t)e * 8, dx);
+  } else {
+    float4* o = reinterpret_cast<float4*>(dxe + (size_t)e * TP::DXP);
+#pragma unroll
+    for (int i = 0; i < TP::DXP / 4; ++i) o[i] = make_float4(dx[4 * i], dx[4 * i + 1], dx[4 * i + 2], dx[4 * i + 3]);
   }
 }
 
@@ -53,17 +108,8 @@ __device__ __forceinline__ void load_x(const float* __restrict__ xt, int s, floa
 template <class TP>
 __device__ __forceinline__ void load_w(const float* __restrict__ w_t, int64_t n_edges, const int32_t* __restrict__ uidx,
                                        const float* __restrict__ w_rows, int p, float* w) {
-  constexpr int LDR = (TP::NLIVE + 3) / 4 * 4;
   if (uidx) {
-    const float4* r = reinterpret_cast<const float4*>(w_rows + (size_t)__ldg(uidx + p) * LDR);
-#pragma unroll
-    for (int i = 0; i < LDR / 4; ++i) {
-      const float4 v = __ldg(r + i);
-      if (4 * i + 0 < TP::NLIVE) w[4 * i + 0] = v.x;
-      if (4 * i + 1 < TP::NLIVE) w[4 * i + 1] = v.y;
-      if (4 * i + 2 < TP::NLIVE) w[4 * i + 2] = v.z;
-      if (4 * i + 3 < TP::NLIVE) w[4 * i + 3] = v.w;
-    }
+    load_w_record<TP>(w_rows, __ldg(uidx + p), w);
   } else {
 #pragma unroll
     for (int c = 0; c < TP::NLIVE; ++c) w[c] = w_t[(size_t)c * n_edges + p];
@@ -233,20 +279,238 @@ tpconv_bwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
     TP::sh(gm.x, gm.y, gm.z, Y);
     TP::bwd(x, Y, w, g, dw, dx);
     if (dw_rows) {                           // shared radial evaluations: one row-major record per slot (pair_combine sums the pair)
-      constexpr int LDR = (TP::NLIVE + 3) / 4 * 4;
-      float4* dr = reinterpret_cast<float4*>(dw_rows + (size_t)p * LDR);
-      float dwp[LDR];
-#pragma unroll
-      for (int c = 0; c < LDR; ++c) dwp[c] = c < TP::NLIVE ? dw[c < TP::NLIVE ? c : 0] : 0.f;
-#pragma unroll
-      for (int i = 0; i < LDR / 4; ++i) dr[i] = make_float4(dwp[4 * i], dwp[4 * i + 1], dwp[4 * i + 2], dwp[4 * i + 3]);
+      store_dw_record<TP>(dw_rows, p, dw);
     } else {
 #pragma unroll
       for (int c = 0; c < TP::NLIVE; ++c) dw_t[(size_t)c * n_edges + p] = dw[c];
     }
-    float4* o = reinterpret_cast<float4*>(dxe + (size_t)e * TP::DXP);
+    store_dx_record<TP>(dxe, e, dx);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Warp-autonomous variants (round 2, the default): a WARP owns RW consecutive receiver rows and walks their edges in passes
+// of 32 -- lane per edge, message into the warp's own 32-row shared-memory tile, `__syncwarp`, (row, component quad) lanes
+// add the pass's rows in ascending edge order, `__syncwarp`.  No block barrier anywhere: in the CTA-cooperative kernels above
+// the three barriers of a 6-row CTA were the second largest stall (8.7 warps per issue, behind the load chain's 11.6;
+// profiles/r2h_tpconv_node_raw.csv), because every warp waits for the slowest warp's dependent loads twice.  The indices of
+// the NEXT pass (sender, record index, geometry) are loaded before the current pass's arithmetic.  Measured: 78 us forward
+// against 80, the same 90 us backward -- the barrier stalls were a symptom of the load chain, not its cause; what did move
+// the backward kernel (116 -> 90 us) was one 256-bit access per 32-byte record instead of two 128-bit ones.
+// Same per-row summation order (ascending CSR position), so the results are bit-identical to the kernels above.
+constexpr int TPW_WARPS = 4;
+template <class TP>
+struct TpwCfg {
+  static constexpr int DL = TP::DLIVE;
+  static constexpr int S = tpc_stride(DL), S4 = S / 4;
+  static constexpr int NQ = (DL + 3) / 4;
+  static constexpr int RW = (32 / NQ) < 6 ? (32 / NQ) : 6;          // rows per warp: RW * NQ reduce lanes <= 32
+  static constexpr bool OK = NQ <= 32 && S * 32 * TPW_WARPS * 4 <= 40 * 1024;
+};
+
+template <class TP, bool AMAX>
+__global__ void __launch_bounds__(TPW_WARPS * 32)
+tpconv_fwd_warp_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src, const float4* __restrict__ geom,
+                       const float* __restrict__ w_t, int64_t n_edges, const float* __restrict__ xt, int n_nodes, int agg,
+                       float* __restrict__ A, int ld_a, int32_t* __restrict__ argmax, const int32_t* __restrict__ uidx,
+                       const float* __restrict__ w_rows) {
+  using C = TpwCfg<TP>;
+  constexpr int DL = C::DL, S = C::S, S4 = C::S4, NQ = C::NQ, RW = C::RW;
+  constexpr unsigned FULL = 0xffffffffu;
+  __shared__ __align__(16) float sm_all[TPW_WARPS * 32 * S];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* sm = sm_all + warp * 32 * S;
+  const int r0 = (blockIdx.x * TPW_WARPS + warp) * RW;
+  const int nr = min(RW, n_nodes - r0);
+  if (nr <= 0) return;
+  const int rp = (lane <= nr) ? __ldg(rowptr + r0 + lane) : 0;
+  const int p_beg = __shfl_sync(FULL, rp, 0), p_end = __shfl_sync(FULL, rp, nr);
+  const int row_i = lane / NQ, quad = lane - row_i * NQ;
+  const bool active = lane < nr * NQ;
+  const int rlo = __shfl_sync(FULL, rp, active ? row_i : 0), rhi = __shfl_sync(FULL, rp, active ? row_i + 1 : 0);
+  const float v0 = AMAX ? -INFINITY : 0.f;
+  float4 acc = make_float4(v0, v0, v0, v0);
+  int4 amax = make_int4(-1, -1, -1, -1);
+  // pass 0 indices
+  int p = p_beg + lane;
+  int c_s = 0, c_u = 0;
+  float4 c_g = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (p < p_end) {
+    c_s = __ldg(src + p);
+    if (uidx) c_u = __ldg(uidx + p);
+    c_g = __ldg(geom + p);
+  }
+  for (int base = p_beg; base < p_end; base += 32) {
+    const int pn = base + 32 + lane;
+    int n_s = 0, n_u = 0;
+    float4 n_g = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (pn < p_end) {                                      // next pass: in flight across this pass's arithmetic
+      n_s = __ldg(src + pn);
+      if (uidx) n_u = __ldg(uidx + pn);
+      n_g = __ldg(geom + pn);
+    }
+    p = base + lane;
+    if (p < p_end) {
+      float x[TP::DXP], w[TP::NLIVE], Y[TP::NY];
+      __align__(16) float m[S];
+      load_x<TP>(xt, c_s, x);
+      if (uidx) {
+        load_w_record<TP>(w_rows, c_u, w);
+      } else {
 #pragma unroll
-    for (int i = 0; i < TP::DXP / 4; ++i) o[i] = make_float4(dx[4 * i], dx[4 * i + 1], dx[4 * i + 2], dx[4 * i + 3]);
+        for (int c = 0; c < TP::NLIVE; ++c) w[c] = w_t[(size_t)c * n_edges + p];
+      }
+      TP::sh(c_g.x, c_g.y, c_g.z, Y);
+#pragma unroll
+      for (int i = DL; i < S; ++i) m[i] = 0.f;
+      TP::fwd(x, Y, w, m);
+      float4* dst = reinterpret_cast<float4*>(sm + lane * S);
+#pragma unroll
+      for (int i = 0; i < NQ; ++i) dst[i] = make_float4(m[4 * i], m[4 * i + 1], m[4 * i + 2], m[4 * i + 3]);
+    }
+    __syncwarp();
+    if (active) {
+      const int lo = max(rlo, base) - base, hi = min(rhi, base + 32) - base;
+      const float4* col = reinterpret_cast<const float4*>(sm + 4 * quad);
+      int q = lo;
+      if (AMAX) {
+        for (; q < hi; ++q) {
+          const float4 v = col[q * S4];
+          if (v.x > acc.x) { acc.x = v.x; amax.x = base + q; }
+          if (v.y > acc.y) { acc.y = v.y; amax.y = base + q; }
+          if (v.z > acc.z) { acc.z = v.z; amax.z = base + q; }
+          if (v.w > acc.w) { acc.w = v.w; amax.w = base + q; }
+        }
+      }
+      for (; q + 1 < hi; q += 2) {                         // ascending order: the order of a sequential scatter-add
+        const float4 a0 = col[q * S4], a1 = col[(q + 1) * S4];
+        acc.x = (acc.x + a0.x) + a1.x;
+        acc.y = (acc.y + a0.y) + a1.y;
+        acc.z = (acc.z + a0.z) + a1.z;
+        acc.w = (acc.w + a0.w) + a1.w;
+      }
+      if (q < hi) {
+        const float4 a0 = col[q * S4];
+        acc.x += a0.x; acc.y += a0.y; acc.z += a0.z; acc.w += a0.w;
+      }
+    }
+    __syncwarp();
+    c_s = n_s; c_u = n_u; c_g = n_g;
+  }
+  if (active) {
+    const float a[4] = {acc.x, acc.y, acc.z, acc.w};
+    const int am[4] = {amax.x, amax.y, amax.z, amax.w};
+    const float deg = (float)max(rhi - rlo, 1);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int comp = 4 * quad + j;
+      if (comp < DL) {
+        float v = a[j];
+        if (agg == 1) v = v / deg;
+        if (AMAX) {
+          if (am[j] < 0) v = 0.f;
+          argmax[(size_t)(r0 + row_i) * DL + comp] = am[j];
+        }
+        A[(size_t)(r0 + row_i) * ld_a + comp] = v;
+      }
+    }
+  }
+}
+
+template <class TP, bool AMAX>
+__global__ void __launch_bounds__(TPW_WARPS * 32)
+tpconv_bwd_warp_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src, const int32_t* __restrict__ perm,
+                       const float4* __restrict__ geom, const float* __restrict__ w_t, int64_t n_edges,
+                       const float* __restrict__ xt, int n_nodes, int agg, const float* __restrict__ gA, int ld_ga,
+                       float* __restrict__ dw_t, float* __restrict__ dxe, const int32_t* __restrict__ argmax,
+                       const int32_t* __restrict__ uidx, const float* __restrict__ w_rows, float* __restrict__ dw_rows) {
+  using C = TpwCfg<TP>;
+  constexpr int DL = C::DL, RW = C::RW;
+  constexpr int GS = (DL + 3) / 4 * 4;                       // dL/dA rows padded to whole 128-bit groups
+  constexpr unsigned FULL = 0xffffffffu;
+  __shared__ __align__(16) float sG_all[TPW_WARPS * RW * GS];
+  __shared__ int sArg_all[AMAX ? TPW_WARPS * RW * GS : 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* sG = sG_all + warp * RW * GS;
+  int* sArg = sArg_all + (AMAX ? warp * RW * GS : 0);
+  const int r0 = (blockIdx.x * TPW_WARPS + warp) * RW;
+  const int nr = min(RW, n_nodes - r0);
+  if (nr <= 0) return;
+  const int rp = (lane <= nr) ? __ldg(rowptr + r0 + lane) : 0x7fffffff;
+  const int p_beg = __shfl_sync(FULL, rp, 0), p_end = __shfl_sync(FULL, rp, nr);
+  int rps[RW];                                               // row starts 1 .. RW - 1 (0x7fffffff past the last row)
+#pragma unroll
+  for (int r = 1; r < RW; ++r) {
+    const int v = __shfl_sync(FULL, rp, r);
+    rps[r] = r < nr ? v : 0x7fffffff;
+  }
+  for (int item = lane; item < nr * GS; item += 32) {
+    const int row = item / GS, comp = item - row * GS;
+    float g = 0.f;
+    if (comp < DL) {
+      g = __ldg(gA + (size_t)(r0 + row) * ld_ga + comp);
+      if (agg == 1) {
+        const int deg = __ldg(rowptr + r0 + row + 1) - __ldg(rowptr + r0 + row);
+        g = g / (float)max(deg, 1);
+      }
+      if (AMAX) sArg[item] = __ldg(argmax + (size_t)(r0 + row) * DL + comp);
+    }
+    sG[item] = g;
+  }
+  __syncwarp();
+  int p = p_beg + lane;
+  int c_s = 0, c_u = 0, c_e = 0;
+  float4 c_g = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (p < p_end) {
+    c_s = __ldg(src + p);
+    c_e = __ldg(perm + p);
+    if (uidx) c_u = __ldg(uidx + p);
+    c_g = __ldg(geom + p);
+  }
+  for (int base = p_beg; base < p_end; base += 32) {
+    const int pn = base + 32 + lane;
+    int n_s = 0, n_u = 0, n_e = 0;
+    float4 n_g = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (pn < p_end) {
+      n_s = __ldg(src + pn);
+      n_e = __ldg(perm + pn);
+      if (uidx) n_u = __ldg(uidx + pn);
+      n_g = __ldg(geom + pn);
+    }
+    p = base + lane;
+    if (p < p_end) {
+      int row = 0;
+#pragma unroll
+      for (int r = 1; r < RW; ++r) row += (p >= rps[r]) ? 1 : 0;
+      float x[TP::DXP], w[TP::NLIVE], Y[TP::NY], g[GS], dw[TP::NLIVE], dx[TP::DXP];
+      load_x<TP>(xt, c_s, x);
+      if (uidx) {
+        load_w_record<TP>(w_rows, c_u, w);
+      } else {
+#pragma unroll
+        for (int c = 0; c < TP::NLIVE; ++c) w[c] = w_t[(size_t)c * n_edges + p];
+      }
+      const float4* gr = reinterpret_cast<const float4*>(sG + row * GS);
+#pragma unroll
+      for (int i = 0; i < GS / 4; ++i) {
+        const float4 v = gr[i];
+        g[4 * i] = v.x; g[4 * i + 1] = v.y; g[4 * i + 2] = v.z; g[4 * i + 3] = v.w;
+      }
+      if (AMAX) {
+#pragma unroll
+        for (int i = 0; i < DL; ++i) g[i] = (sArg[row * GS + i] == p) ? g[i] : 0.f;
+      }
+      TP::sh(c_g.x, c_g.y, c_g.z, Y);
+      TP::bwd(x, Y, w, g, dw, dx);
+      if (dw_rows) {
+        store_dw_record<TP>(dw_rows, p, dw);
+      } else {
+#pragma unroll
+        for (int c = 0; c < TP::NLIVE; ++c) dw_t[(size_t)c * n_edges + p] = dw[c];
+      }
+      store_dx_record<TP>(dxe, c_e, dx);
+    }
+    c_s = n_s; c_u = n_u; c_e = n_e; c_g = n_g;
   }
 }
 
@@ -396,14 +660,27 @@ static int tpconv_fwd_impl(int tp_id, const int32_t* rowptr, const int32_t* src,
   EQNN_CHECK_ARG(rowptr && src && geom && (w_t || (uidx && w_rows)) && xt && A, "tpconv_fwd: null pointer");
   EQNN_CHECK_ARG(agg >= 0 && agg <= 2, "tpconv_fwd: agg must be 0 (sum), 1 (mean) or 2 (max)");
   EQNN_CHECK_ARG(agg != 2 || argmax, "tpconv_fwd: max aggregation needs the argmax buffer");
-  EQNN_CHECK_ARG(((uintptr_t)geom & 15) == 0 && ((uintptr_t)xt & 15) == 0, "tpconv_fwd: geom/xt must be 16-byte aligned");
-  EQNN_CHECK_ARG(!uidx || ((uintptr_t)w_rows & 15) == 0, "tpconv_fwd: w_rows must be 16-byte aligned");
+  EQNN_CHECK_ARG(((uintptr_t)geom & 15) == 0 && ((uintptr_t)xt & 31) == 0, "tpconv_fwd: geom must be 16-byte, xt 32-byte aligned");
+  EQNN_CHECK_ARG(!uidx || ((uintptr_t)w_rows & 31) == 0, "tpconv_fwd: w_rows must be 32-byte aligned");
   if (n_nodes <= 0) return EQNN_OK;
   const unsigned grid = (unsigned)((n_nodes + TPC_ROWS - 1) / TPC_ROWS);
   EQNN_TP_DISPATCH(tp_id, {
     EQNN_CHECK_ARG(ld_a >= TP::DLIVE, "tpconv_fwd: ld_a smaller than live width");
     EQNN_CHECK_ARG(!uidx || ld_rows == (TP::NLIVE + 3) / 4 * 4, "tpconv_fwd: ld_rows must be NLIVE rounded up to 4");
     // the widest signatures (every message column at l_max 3: eqnn_tp_messages only) do not fit the message transpose
+    if constexpr (TpwCfg<TP>::OK) {
+      if (!getenv("EQNN_TPCONV_CTA")) {                       // default: the warp-autonomous kernel
+        const unsigned wgrid = (unsigned)ceil_div64(n_nodes, TPW_WARPS * TpwCfg<TP>::RW);
+        if (agg == 2)
+          tpconv_fwd_warp_kernel<TP, true><<<wgrid, TPW_WARPS * 32, 0, as_stream(stream)>>>(
+              rowptr, src, reinterpret_cast<const float4*>(geom), w_t, n_edges, xt, n_nodes, agg, A, ld_a, argmax, uidx, w_rows);
+        else
+          tpconv_fwd_warp_kernel<TP, false><<<wgrid, TPW_WARPS * 32, 0, as_stream(stream)>>>(
+              rowptr, src, reinterpret_cast<const float4*>(geom), w_t, n_edges, xt, n_nodes, agg, A, ld_a, nullptr, uidx, w_rows);
+        EQNN_CHECK_LAUNCH();
+        return EQNN_OK;
+      }
+    }
     if constexpr (tpc_stride(TP::DLIVE) * TPC_THREADS * 4 <= 40 * 1024) {
       if (agg == 2)
         tpconv_fwd_kernel<TP, true><<<grid, TPC_THREADS, 0, as_stream(stream)>>>(
@@ -441,15 +718,30 @@ static int tpconv_bwd_impl(int tp_id, const int32_t* rowptr, const int32_t* src,
                  "tpconv_bwd: null pointer");
   EQNN_CHECK_ARG(agg >= 0 && agg <= 2, "tpconv_bwd: agg must be 0 (sum), 1 (mean) or 2 (max)");
   EQNN_CHECK_ARG(agg != 2 || argmax, "tpconv_bwd: max aggregation needs the argmax buffer of the forward pass");
-  EQNN_CHECK_ARG(((uintptr_t)geom & 15) == 0 && ((uintptr_t)xt & 15) == 0 && ((uintptr_t)dxe & 15) == 0,
-                 "tpconv_bwd: geom/xt/dxe must be 16-byte aligned");
-  EQNN_CHECK_ARG(!uidx || (((uintptr_t)w_rows & 15) == 0 && ((uintptr_t)dw_rows & 15) == 0),
-                 "tpconv_bwd: w_rows/dw_rows must be 16-byte aligned");
+  EQNN_CHECK_ARG(((uintptr_t)geom & 15) == 0 && ((uintptr_t)xt & 31) == 0 && ((uintptr_t)dxe & 31) == 0,
+                 "tpconv_bwd: geom must be 16-byte, xt/dxe 32-byte aligned");
+  EQNN_CHECK_ARG(!uidx || (((uintptr_t)w_rows & 31) == 0 && ((uintptr_t)dw_rows & 31) == 0),
+                 "tpconv_bwd: w_rows/dw_rows must be 32-byte aligned");
   if (n_nodes <= 0) return EQNN_OK;
   const unsigned grid = (unsigned)((n_nodes + TPC_ROWS - 1) / TPC_ROWS);
   EQNN_TP_DISPATCH(tp_id, {
     EQNN_CHECK_ARG(ld_ga >= TP::DLIVE, "tpconv_bwd: ld_ga smaller than live width");
     EQNN_CHECK_ARG(!uidx || ld_rows == (TP::NLIVE + 3) / 4 * 4, "tpconv_bwd: ld_rows must be NLIVE rounded up to 4");
+    if constexpr (TpwCfg<TP>::OK) {
+      if (!getenv("EQNN_TPCONV_CTA")) {                       // default: the warp-autonomous kernel
+        const unsigned wgrid = (unsigned)ceil_div64(n_nodes, TPW_WARPS * TpwCfg<TP>::RW);
+        if (agg == 2)
+          tpconv_bwd_warp_kernel<TP, true><<<wgrid, TPW_WARPS * 32, 0, as_stream(stream)>>>(
+              rowptr, src, perm, reinterpret_cast<const float4*>(geom), w_t, n_edges, xt, n_nodes, agg, gA, ld_ga, dw_t, dxe,
+              argmax, uidx, w_rows, dw_rows);
+        else
+          tpconv_bwd_warp_kernel<TP, false><<<wgrid, TPW_WARPS * 32, 0, as_stream(stream)>>>(
+              rowptr, src, perm, reinterpret_cast<const float4*>(geom), w_t, n_edges, xt, n_nodes, agg, gA, ld_ga, dw_t, dxe,
+              nullptr, uidx, w_rows, dw_rows);
+        EQNN_CHECK_LAUNCH();
+        return EQNN_OK;
+      }
+    }
     if (agg == 2)
       tpconv_bwd_kernel<TP, true><<<grid, TPC_THREADS, 0, as_stream(stream)>>>(
           rowptr, src, perm, reinterpret_cast<const float4*>(geom), w_t, n_edges, xt, n_nodes, agg, gA, ld_ga, dw_t,
@@ -530,13 +822,61 @@ __global__ void segment_gather_sum4_kernel(const float4* __restrict__ dxe, const
   }
   dxt[i] = a;
 }
+// 256-bit variants (dxp == 8, 32-byte aligned buffers): one thread per sender, one access per 32-byte record
+__global__ void sender_reduce8_kernel(const float* __restrict__ dxe, int n_nodes, int k, float* __restrict__ dxt) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_nodes) return;
+  const float* p = dxe + (size_t)s * k * 8;
+  float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  int j = 0;
+  for (; j + 1 < k; j += 2) {                      // two records in flight, summed in ascending edge order
+    float v0[8], v1[8];
+    tc::ldg256(p + (size_t)j * 8, v0);
+    tc::ldg256(p + (size_t)(j + 1) * 8, v1);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) a[c] = (a[c] + v0[c]) + v1[c];
+  }
+  if (j < k) {
+    float v0[8];
+    tc::ldg256(p + (size_t)j * 8, v0);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) a[c] += v0[c];
+  }
+  tc::stg256(dxt + (size_t)s * 8, a);
+}
+__global__ void segment_gather_sum8_kernel(const float* __restrict__ dxe, const int32_t* __restrict__ rowptr_s,
+                                           const int32_t* __restrict__ perm_s, int n_nodes, float* __restrict__ dxt) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_nodes) return;
+  const int q1 = rowptr_s[s + 1];
+  float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  int q = rowptr_s[s];
+  for (; q + 3 < q1; q += 4) {                     // four records in flight, summed in ascending order
+    const int e0 = perm_s[q], e1 = perm_s[q + 1], e2 = perm_s[q + 2], e3 = perm_s[q + 3];
+    float v0[8], v1[8], v2[8], v3[8];
+    tc::ldg256(dxe + (size_t)e0 * 8, v0);
+    tc::ldg256(dxe + (size_t)e1 * 8, v1);
+    tc::ldg256(dxe + (size_t)e2 * 8, v2);
+    tc::ldg256(dxe + (size_t)e3 * 8, v3);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) a[c] = (((a[c] + v0[c]) + v1[c]) + v2[c]) + v3[c];
+  }
+  for (; q < q1; ++q) {
+    float v0[8];
+    tc::ldg256(dxe + (size_t)perm_s[q] * 8, v0);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) a[c] += v0[c];
+  }
+  tc::stg256(dxt + (size_t)s * 8, a);
+}
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+static inline bool aligned32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31) == 0; }
 
 extern "C" int eqnn_tp_messages(int tp_id, const int32_t* src, const int32_t* perm, const float* geom, const float* w_rows,
                                 int ld_w, const int* col, const float* scale, const float* xt, int64_t n_edges, float* out,
                                 int ld_out, eqnn_stream_t stream) {
   EQNN_CHECK_ARG(src && perm && geom && w_rows && col && scale && xt && out, "tp_messages: null pointer");
-  EQNN_CHECK_ARG(((uintptr_t)geom & 15) == 0 && ((uintptr_t)xt & 15) == 0, "tp_messages: geom/xt must be 16-byte aligned");
+  EQNN_CHECK_ARG(((uintptr_t)geom & 15) == 0 && ((uintptr_t)xt & 31) == 0, "tp_messages: geom must be 16-byte, xt 32-byte aligned");
   if (n_edges <= 0) return EQNN_OK;
   EQNN_TP_DISPATCH(tp_id, {
     EQNN_CHECK_ARG(TP::NLIVE <= 32, "tp_messages: more than 32 message columns");
@@ -558,6 +898,11 @@ extern "C" int eqnn_sender_reduce(const float* dxe, int n_nodes, int k, int dxp,
                                   eqnn_stream_t stream) {
   EQNN_CHECK_ARG(dxe && dxt && k >= 1 && dxp >= 1, "sender_reduce: bad argument");
   if (n_nodes <= 0) return EQNN_OK;
+  if (dxp == 8 && aligned32(dxe) && aligned32(dxt)) {
+    sender_reduce8_kernel<<<(unsigned)ceil_div64(n_nodes, 128), 128, 0, as_stream(stream)>>>(dxe, n_nodes, k, dxt);
+    EQNN_CHECK_LAUNCH();
+    return EQNN_OK;
+  }
   if ((dxp & 3) == 0 && aligned16(dxe) && aligned16(dxt)) {
     const int64_t n4 = (int64_t)n_nodes * (dxp / 4);
     sender_reduce4_kernel<<<(unsigned)ceil_div64(n4, 128), 128, 0, as_stream(stream)>>>(
@@ -575,6 +920,12 @@ extern "C" int eqnn_segment_gather_sum(const float* dxe, const int32_t* rowptr_s
                                        int n_nodes, int dxp, float* dxt, eqnn_stream_t stream) {
   EQNN_CHECK_ARG(dxe && rowptr_s && perm_s && dxt && dxp >= 1, "segment_gather_sum: bad argument");
   if (n_nodes <= 0) return EQNN_OK;
+  if (dxp == 8 && aligned32(dxe) && aligned32(dxt)) {
+    segment_gather_sum8_kernel<<<(unsigned)ceil_div64(n_nodes, 128), 128, 0, as_stream(stream)>>>(dxe, rowptr_s, perm_s, n_nodes,
+                                                                                              dxt);
+    EQNN_CHECK_LAUNCH();
+    return EQNN_OK;
+  }
   if ((dxp & 3) == 0 && aligned16(dxe) && aligned16(dxt)) {
     const int64_t n4 = (int64_t)n_nodes * (dxp / 4);
     segment_gather_sum4_kernel<<<(unsigned)ceil_div64(n4, 128), 128, 0, as_stream(stream)>>>(
@@ -607,6 +958,7 @@ extern "C" int eqnn_sh_scatter(int lmax, const int32_t* rowptr, const float* geo
 extern "C" int eqnn_node_tp_fwd(int tp_id, const float* x, const float* y, int64_t n, float* T,
                                 eqnn_stream_t stream) {
   EQNN_CHECK_ARG(x && y && T, "node_tp_fwd: null pointer");
+  EQNN_CHECK_ARG(((uintptr_t)x & 31) == 0, "node_tp_fwd: x must be 32-byte aligned");
   if (n <= 0) return EQNN_OK;
   EQNN_TP_DISPATCH(tp_id, {
     node_tp_fwd_kernel<TP><<<(unsigned)ceil_div64(n, 128), 128, 0, as_stream(stream)>>>(x, y, n, T);
@@ -618,6 +970,7 @@ extern "C" int eqnn_node_tp_fwd(int tp_id, const float* x, const float* y, int64
 extern "C" int eqnn_node_tp_bwd(int tp_id, const float* x, const float* y, const float* gT, int64_t n, float* dx,
                                 eqnn_stream_t stream) {
   EQNN_CHECK_ARG(x && y && gT && dx, "node_tp_bwd: null pointer");
+  EQNN_CHECK_ARG(((uintptr_t)x & 31) == 0, "node_tp_bwd: x must be 32-byte aligned");
   if (n <= 0) return EQNN_OK;
   EQNN_TP_DISPATCH(tp_id, {
     node_tp_bwd_kernel<TP><<<(unsigned)ceil_div64(n, 128), 128, 0, as_stream(stream)>>>(x, y, gT, n, dx);

@@ -131,3 +131,53 @@ def test_shared_radial_evaluation_does_not_change_the_model(agg):
         # module scale: largest gradient among the tensors that share the first path element
         mod = max(float(ga[o:o + int(np.prod(sh))].abs().max()) for pth, sh, o in params.layout if pth[0] == path[0])
         assert float((a - b).abs().max()) <= 1e-5 * max(mod, 1e-30), path
+
+
+@pytest.mark.parametrize("lmax,live,agg,shared", [(2, "0e,1o", "mean", True), (2, "0e,1o", "sum", False), (2, "0e,1o,2e", "max", False),
+                                                  (3, "0e,1o", "max", True), (1, "0e", "mean", False)])
+def test_warp_autonomous_interaction_kernels_equal_the_cta_kernels(lmax, live, agg, shared, monkeypatch):
+    """eqnn_tpconv_fwd / _bwd (and the _shared forms): the warp-per-rows kernels (default) against the CTA-cooperative ones
+    (EQNN_TPCONV_CTA=1) -- same per-row summation order, so every output is bit-identical."""
+    from eqnn_jax_b200 import graph_utils as GU
+    from eqnn_jax_b200 import ops
+    rng = np.random.default_rng(5 + lmax)
+    B, N, k = 2, 700, 20
+    x = rng.uniform(0.0, 1.0, size=(B, N, 3)).astype(np.float32)
+    g = GU.build_graph(_dev(x), None, k, apply_pbc=GU.get_apply_pbc(None, cell=np.eye(3)))
+    rowptr, perm, src = ops.csr_build(g.senders.reshape(B, -1).contiguous(), g.receivers.reshape(B, -1).contiguous(), N)
+    Nt, E = B * N, B * N * k
+    geom, _ = ops.edge_geom(_dev(x), 3, Nt, rowptr, src, 0, 1.0, want_radial=False)
+    tp_id = ops.tp_lookup(f"x=1x0e+2x1o;lmax={lmax};live={live}")
+    dxp, ny, n_live, d_live = ops.tp_dims(tp_id)
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    xt = torch.randn((Nt, dxp), device="cuda", generator=gen)
+    xt[:, 7:] = 0
+    dA = torch.randn((Nt, d_live), device="cuda", generator=gen)
+    a = ops.AGG[agg]
+    ldr = (n_live + 3) // 4 * 4
+    pr = ops.edge_pairs(rowptr, src, geom, Nt, 0, 1.0) if shared else None
+    w_t = torch.randn((n_live, E), device="cuda", generator=gen)
+    w_rows = torch.randn((E, ldr), device="cuda", generator=gen)
+    res = {}
+    for mode in ("warp", "cta"):
+        if mode == "cta":
+            monkeypatch.setenv("EQNN_TPCONV_CTA", "1")
+        else:
+            monkeypatch.delenv("EQNN_TPCONV_CTA", raising=False)
+        A = torch.zeros((Nt, d_live), device="cuda")
+        amax = torch.zeros((Nt, d_live), dtype=torch.int32, device="cuda") if a == 2 else None
+        dxe = torch.zeros((E, dxp), device="cuda")
+        if shared:
+            dw = torch.zeros((E, ldr), device="cuda")
+            ops.tpconv_fwd_shared(tp_id, rowptr, src, geom, pr, w_rows, xt, Nt, a, A, d_live, amax)
+            ops.tpconv_bwd_shared(tp_id, rowptr, src, perm, geom, pr, w_rows, xt, Nt, a, dA, d_live, dw, dxe, amax)
+        else:
+            dw = torch.zeros((n_live, E), device="cuda")
+            ops.tpconv_fwd(tp_id, rowptr, src, geom, w_t, xt, Nt, a, A, d_live, amax)
+            ops.tpconv_bwd(tp_id, rowptr, src, perm, geom, w_t, xt, Nt, a, dA, d_live, dw, dxe, amax)
+        torch.cuda.synchronize()
+        res[mode] = (A, dw, dxe, amax)
+    for i, name in enumerate(("A", "dw", "dxe")):
+        assert torch.equal(res["warp"][i], res["cta"][i]), name
+    if a == 2:
+        assert torch.equal(res["warp"][3], res["cta"][3]), "argmax"
