@@ -87,7 +87,7 @@ __host__ __device__ __forceinline__ size_t smem_layout(const NodeP& p, Smem* s, 
   const size_t oW12 = take((size_t)d_in * ldw), oW3 = take((size_t)p.d_g * MAX_DH);
   const size_t oW0 = take((size_t)p.d_h * (p.dxp > 0 ? p.dxp : 1)), oIn = take((size_t)d_in * TILE);
   const size_t oZ = take((size_t)TILE * p.d_z), oZ2 = take((size_t)TILE * p.d_z), oG = take((size_t)TILE * p.d_g), oT = take((size_t)MAX_DH * TILE);
-  const size_t oDz = take((size_t)TILE * ldw), oDg = take((size_t)TILE * p.d_g);
+  const size_t oDz = take((size_t)TILE * ldw), oDg = take((size_t)TILE * p.d_g > 2 * TILE * 32 ? (size_t)TILE * p.d_g : (size_t)2 * TILE * 32);   // also the data-gradient scratch [2][TILE][32]
   const size_t oGi = take(p.d_gated > 0 ? p.d_gated : 1), oGo = take(p.n_gates > 0 ? p.n_gates : 1);
   const size_t oGd = take(p.n_gates > 0 ? p.n_gates : 1);
   const size_t oSg = take((size_t)(NT / 32) * (p.n_gates > 0 ? p.n_gates : 1));
@@ -440,24 +440,42 @@ __global__ void __launch_bounds__(NT, 3) node_bwd_kernel(const NodeP p_in) {
         }
       }
     }
-    // ... and data gradients d_in[node][r] = sum_c dz[node][c] W12[r][c]  (128-bit loads along c; pads are zero)
-    for (int node = warp; node < TILE; node += NT / 32) {       // warp per node, lanes over input features
-      const float4* dzr = reinterpret_cast<const float4*>(s.dz + node * ldw);
-      for (int r = lane; r < d_in; r += 32) {
-        const float4* wr = reinterpret_cast<const float4*>(s.W12 + r * ldw);
-        float a0 = 0.f, a1 = 0.f;
-        const int n4 = (p.d_z + 3) / 4;
-        int c = 0;
-        for (; c + 1 < n4; c += 2) {
-          a0 = dot4(dzr[c], wr[c], a0);
-          a1 = dot4(dzr[c + 1], wr[c + 1], a1);
+    // ... and data gradients d_in[node][r] = sum_c dz[node][c] W12[r][c]  (128-bit loads along c; pads are zero).
+    // The kernel is bound by shared-memory wavefronts (73 % of the L1 data pipe's peak, profiles/r2h_tpconv_node_raw.csv), and
+    // this product was 45 % of them when every node re-read all of W12: a warp now owns FOUR nodes and one half of the
+    // columns -- lane r reads its W12 row once per four nodes, the dz rows are warp-wide broadcasts -- and the two column
+    // halves meet in a scratch (the dg array, dead after the gate phase) from which the results leave coalesced.
+    {
+      static_assert(NT / 32 == 8 && TILE == 16, "node-group x column-half mapping of the data-gradient product");
+      const int ng = warp & 3, ch = warp >> 2;
+      const int n4 = (p.d_z + 3) / 4, half = (n4 + 1) / 2;
+      const int c_lo = ch * half, c_hi = min(n4, c_lo + half);
+      float* scratch = s.dg;                                     // [2][TILE][32]
+      const float4* dz0 = reinterpret_cast<const float4*>(s.dz + (4 * ng + 0) * ldw);
+      const float4* dz1 = reinterpret_cast<const float4*>(s.dz + (4 * ng + 1) * ldw);
+      const float4* dz2 = reinterpret_cast<const float4*>(s.dz + (4 * ng + 2) * ldw);
+      const float4* dz3 = reinterpret_cast<const float4*>(s.dz + (4 * ng + 3) * ldw);
+      if (lane < d_in) {
+        const float4* wr = reinterpret_cast<const float4*>(s.W12 + lane * ldw);
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        for (int c = c_lo; c < c_hi; ++c) {
+          const float4 w4 = wr[c];
+          a0 = dot4(dz0[c], w4, a0);
+          a1 = dot4(dz1[c], w4, a1);
+          a2 = dot4(dz2[c], w4, a2);
+          a3 = dot4(dz3[c], w4, a3);
         }
-        if (c < n4) a0 = dot4(dzr[c], wr[c], a0);
-        const float a = a0 + a1;
-        if (node < nn) {
-          if (r < p.d_a) p.dA[(n0 + node) * p.d_a + r] = a;
-          else p.dh_in[(n0 + node) * p.d_h + (r - p.d_a)] = p.W2 ? a : 0.f;
-        }
+        float* o = scratch + (ch * TILE + 4 * ng) * 32 + lane;
+        o[0] = a0; o[32] = a1; o[64] = a2; o[96] = a3;
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < TILE * d_in; i += NT) {
+      const int node = i / d_in, r = i - node * d_in;
+      const float a = s.dg[node * 32 + r] + s.dg[(TILE + node) * 32 + r];
+      if (node < nn) {
+        if (r < p.d_a) p.dA[(n0 + node) * p.d_a + r] = a;
+        else p.dh_in[(n0 + node) * p.d_h + (r - p.d_a)] = p.W2 ? a : 0.f;
       }
     }
   }
