@@ -58,7 +58,8 @@ __device__ __forceinline__ int gate_of(const NodeP& p, int j) {   // gated compo
 //     [feature][node], so that the 16 nodes of a tile are four broadcast 128-bit loads.
 struct Smem {
   float* W12;   // [d_in][ldw]    rows 0..d_a-1 = alpha1*W1, rows d_a.. = W2, pad columns zero
-  float* W3;    // [d_g][MAX_DH]  rows padded to 8 floats (zeros): a row is two 128-bit loads
+  float* W3;    // [2][d_g][4]    two planes (outputs 0..3 / 4..7, zero padded): lanes that read consecutive rows read
+                //                consecutive 16-byte groups -- no bank conflicts (one [d_g][8] array: 2-way)
   float* W0n;   // [d_h][dxp]
   float* inT;   // [d_in][TILE]
   float* z;     // [TILE][d_z]
@@ -118,7 +119,7 @@ __device__ __forceinline__ void load_weights(const NodeP& p, const Smem& s, int 
   for (int i = threadIdx.x; i < TILE * ldw; i += NT) s.dz[i] = 0.f;
   for (int i = threadIdx.x; i < p.d_g * MAX_DH; i += NT) {
     const int j = i / MAX_DH, o = i - j * MAX_DH;
-    s.W3[i] = o < p.d_h ? p.W3[j * p.d_h + o] : 0.f;
+    s.W3[(o >> 2) * (p.d_g * 4) + j * 4 + (o & 3)] = o < p.d_h ? p.W3[j * p.d_h + o] : 0.f;
   }
   if (p.W0n)
     for (int i = threadIdx.x; i < p.d_h * p.dxp; i += NT) s.W0n[i] = p.W0n[i];
@@ -281,8 +282,8 @@ __global__ void __launch_bounds__(NT, 3) node_fwd_kernel(const NodeP p_in) {
       for (int o = 0; o < MAX_DH; ++o) a[o] = 0.f;
       for (int j = part; j < p.d_g; j += PARTS) {
         const float gv = gr[j];
-        const float4 w0 = *reinterpret_cast<const float4*>(s.W3 + j * MAX_DH);
-        const float4 w1 = *reinterpret_cast<const float4*>(s.W3 + j * MAX_DH + 4);
+        const float4 w0 = *reinterpret_cast<const float4*>(s.W3 + j * 4);
+        const float4 w1 = *reinterpret_cast<const float4*>(s.W3 + p.d_g * 4 + j * 4);
         a[0] = fmaf(gv, w0.x, a[0]); a[1] = fmaf(gv, w0.y, a[1]); a[2] = fmaf(gv, w0.z, a[2]); a[3] = fmaf(gv, w0.w, a[3]);
         a[4] = fmaf(gv, w1.x, a[4]); a[5] = fmaf(gv, w1.y, a[5]); a[6] = fmaf(gv, w1.z, a[6]); a[7] = fmaf(gv, w1.w, a[7]);
       }
@@ -370,8 +371,8 @@ __global__ void __launch_bounds__(NT, 3) node_bwd_kernel(const NodeP p_in) {
       for (int o = 0; o < MAX_DH; ++o) dho[o] = s.tT[o * TILE + node];
       for (int gi = lane; gi < p.n_gates; gi += 32) sgw[gi] = sigmoid_acc(zr[p.n_extra + gi]);
       for (int c = lane; c < p.n_extra; c += 32) {
-        const float4 w0 = *reinterpret_cast<const float4*>(s.W3 + c * MAX_DH);
-        const float4 w1 = *reinterpret_cast<const float4*>(s.W3 + c * MAX_DH + 4);
+        const float4 w0 = *reinterpret_cast<const float4*>(s.W3 + c * 4);
+        const float4 w1 = *reinterpret_cast<const float4*>(s.W3 + p.d_g * 4 + c * 4);
         float dg = dho[0] * w0.x;                                  // (padded W3 columns and dh_out rows are zero)
         dg = fmaf(dho[1], w0.y, dg); dg = fmaf(dho[2], w0.z, dg); dg = fmaf(dho[3], w0.w, dg);
         dg = fmaf(dho[4], w1.x, dg); dg = fmaf(dho[5], w1.y, dg); dg = fmaf(dho[6], w1.z, dg); dg = fmaf(dho[7], w1.w, dg);
@@ -383,8 +384,8 @@ __global__ void __launch_bounds__(NT, 3) node_bwd_kernel(const NodeP p_in) {
       __syncwarp();
       for (int j = lane; j < p.d_gated; j += 32) {
         const int c = p.n_extra + j;
-        const float4 w0 = *reinterpret_cast<const float4*>(s.W3 + c * MAX_DH);
-        const float4 w1 = *reinterpret_cast<const float4*>(s.W3 + c * MAX_DH + 4);
+        const float4 w0 = *reinterpret_cast<const float4*>(s.W3 + c * 4);
+        const float4 w1 = *reinterpret_cast<const float4*>(s.W3 + p.d_g * 4 + c * 4);
         float dg = dho[0] * w0.x;                                  // (padded W3 columns and dh_out rows are zero)
         dg = fmaf(dho[1], w0.y, dg); dg = fmaf(dho[2], w0.z, dg); dg = fmaf(dho[3], w0.w, dg);
         dg = fmaf(dho[4], w1.x, dg); dg = fmaf(dho[5], w1.y, dg); dg = fmaf(dho[6], w1.z, dg); dg = fmaf(dho[7], w1.w, dg);
