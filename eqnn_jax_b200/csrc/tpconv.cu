@@ -382,7 +382,14 @@ tpconv_fwd_warp_kernel(const int32_t* __restrict__ rowptr, const int32_t* __rest
           if (v.w > acc.w) { acc.w = v.w; amax.w = base + q; }
         }
       }
-      for (; q + 1 < hi; q += 2) {                         // ascending order: the order of a sequential scatter-add
+      for (; q + 3 < hi; q += 4) {                         // ascending order: the order of a sequential scatter-add
+        const float4 a0 = col[q * S4], a1 = col[(q + 1) * S4], a2 = col[(q + 2) * S4], a3 = col[(q + 3) * S4];
+        acc.x = (((acc.x + a0.x) + a1.x) + a2.x) + a3.x;   // four loads in flight, the adds stay sequential
+        acc.y = (((acc.y + a0.y) + a1.y) + a2.y) + a3.y;
+        acc.z = (((acc.z + a0.z) + a1.z) + a2.z) + a3.z;
+        acc.w = (((acc.w + a0.w) + a1.w) + a2.w) + a3.w;
+      }
+      for (; q + 1 < hi; q += 2) {
         const float4 a0 = col[q * S4], a1 = col[(q + 1) * S4];
         acc.x = (acc.x + a0.x) + a1.x;
         acc.y = (acc.y + a0.y) + a1.y;
