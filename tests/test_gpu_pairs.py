@@ -181,3 +181,44 @@ def test_warp_autonomous_interaction_kernels_equal_the_cta_kernels(lmax, live, a
         assert torch.equal(res["warp"][i], res["cta"][i]), name
     if a == 2:
         assert torch.equal(res["warp"][3], res["cta"][3]), "argmax"
+
+
+def test_shared_radial_at_cloud_scale():
+    """bench.py's model on 4 x 5000-node kNN-20 clouds (the CPU oracle cannot reach this size): the zero class sums 20 000
+    self-loop cotangents into one row, which also sets the power-of-two scale of the backward kernels' fp16 operand split.
+    Forward bit-identical to the per-edge evaluation, every gradient outside the radial MLPs bit-identical, the radial MLPs'
+    weight gradients within 1e-5 of their module's gradient scale (measured 1.4e-6 at 8 clouds, scripts/dev/diag_shared_scale.py)."""
+    from eqnn_jax_b200 import graph_utils as GU
+    from eqnn_jax_b200 import ops
+    from eqnn_jax_b200.nequip import NequIP
+    from eqnn_jax_b200.train import wrap_graph
+    rng = np.random.default_rng(2)
+    B, N, k = 4, 5000, 20
+    h = rng.normal(size=(B, N, 7)).astype(np.float32)
+    h[..., :3] = rng.uniform(0.0, 1.0, size=(B, N, 3)) / 0.2887
+    hd = _dev(h)
+    pbc = GU.get_apply_pbc(std=np.full(3, 0.2887, dtype=np.float32))
+    s_, r_, _ = ops.knn_pbc(hd, k, pbc.cell, pbc.cell_inv, want_dr=False)
+    kw = dict(d_hidden=128, l_max=2, sphharm_norm="integral", message_passing_steps=4, n_layers=3, message_passing_agg="mean",
+              readout_agg="mean", mlp_readout_widths=(4, 2, 2), task="graph", n_outputs=2, n_radial_basis=64, r_cutoff=0.6)
+    y = _dev(rng.normal(size=(B, 2)))
+    res = {}
+    for share in (False, True):
+        model = NequIP(**kw, share_radial=share)
+        g = wrap_graph(model, hd, s_, r_, k, pbc)
+        params = model.init(0, g)
+        out = model.forward_backward(params, g, lambda o: 2.0 * (o - y) / o.numel())
+        res[share] = (out.clone(), params.grad.clone(), params)
+    assert torch.equal(res[False][0], res[True][0])
+    ga, gb, params = res[False][1], res[True][1], res[True][2]
+    scale = {}
+    for path, shape, off in params.layout:
+        n = int(np.prod(shape))
+        scale[path[0]] = max(scale.get(path[0], 0.0), float(ga[off:off + n].abs().max()))
+    for path, shape, off in params.layout:
+        n = int(np.prod(shape))
+        a, b = ga[off:off + n], gb[off:off + n]
+        if path[0].startswith("MultiLayerPerceptron"):
+            assert float((a - b).abs().max()) <= 1e-5 * scale[path[0]], path
+        else:
+            assert torch.equal(a, b), path
