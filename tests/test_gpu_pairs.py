@@ -98,8 +98,8 @@ def test_bessel_rows_matches_edge_geom_basis():
     assert np.array_equal(out[:U].cpu().numpy().view(np.uint32), want24.view(np.uint32))
 
 
-@pytest.mark.parametrize("agg", ["mean", "max"])
-def test_shared_radial_evaluation_does_not_change_the_model(agg):
+@pytest.mark.parametrize("agg,n_layers,n_rb", [("mean", 3, 64), ("max", 3, 64), ("sum", 2, 32)])
+def test_shared_radial_evaluation_does_not_change_the_model(agg, n_layers, n_rb):
     """Same inputs, same parameters: forward output bit-identical (the same MLP arithmetic on the same lengths), every
     gradient equal up to the summation order of the weight gradients (1e-5 of the module's gradient scale)."""
     from eqnn_jax_b200 import graph_utils as GU
@@ -108,8 +108,8 @@ def test_shared_radial_evaluation_does_not_change_the_model(agg):
     B, N, k = 2, 256, 16
     x = rng.normal(size=(B, N, 7)).astype(np.float32)
     x[..., :3] = rng.uniform(0.0, 3.0, size=(B, N, 3))
-    kw = dict(d_hidden=128, l_max=2, sphharm_norm="integral", message_passing_steps=2, n_layers=3, n_outputs=2,
-              n_radial_basis=64, r_cutoff=0.6, message_passing_agg=agg, task="graph")
+    kw = dict(d_hidden=128, l_max=2, sphharm_norm="integral", message_passing_steps=2, n_layers=n_layers, n_outputs=2,
+              n_radial_basis=n_rb, r_cutoff=0.6, message_passing_agg=agg, task="graph")
     xd = _dev(x)
     g = GU.build_graph(xd, None, k, apply_pbc=GU.get_apply_pbc(np.ones(3, dtype=np.float32), cell=np.eye(3) * 3))
     gg = g._replace(nodes=IrrepsArray("1o+1o+1x0e", xd), edges=None)
